@@ -1,0 +1,93 @@
+"""Benchmark "plugins" of the synthetic driver: material coefficients and the Stokes right-hand side.
+
+In ASPECT these stay host C++ (material-model plugins + the FEValues assembly loop); here they are the
+numpy equivalents that feed the handler:
+  nsinker : /root/reference/benchmarks/nsinker/nsinker.cc:61-76, :196-314 (first 8 of the fixed centres are
+            enough for the BASELINE configs), pressure scaling forced to 1 (:320-331)
+  SolCx   : /root/reference/benchmarks/solcx/solcx.h:2962-2977
+  rhs     : f_i = int rho g . phi_i with the 3^dim Gauss rule (source/simulator/assemblers/stokes.cc:387-396)
+  pressure scaling: source/simulator/helper_functions.cc:253-348, geometry_model/box.cc:252-255
+"""
+import numpy as np
+
+from .cell_data import average_viscosity, quadrature_weights
+
+NSINKER_CENTERS = np.array([
+    [2.4257829890e-01, 1.3469574514e-02, 3.8313885004e-01],
+    [4.1465269048e-01, 6.7768972864e-02, 9.9312692973e-01],
+    [4.8430804651e-01, 7.6533776604e-01, 3.1833815403e-02],
+    [3.0935481671e-02, 9.3264044027e-01, 8.8787953411e-01],
+    [5.9132973039e-01, 4.7877868473e-01, 8.3335433660e-01],
+    [1.8633519681e-01, 7.3565270739e-01, 1.1505317181e-01],
+    [6.9865863058e-01, 3.5560411138e-01, 6.3830000658e-01],
+    [9.0821050755e-01, 2.9400041480e-01, 2.6497158886e-01],
+])
+
+
+def nsinker_material(x, n_sinkers=8, viscosity_ratio=1e4, sinker_density=10.0, delta=200.0, omega=0.1):
+    assert n_sinkers <= len(NSINKER_CENTERS)
+    dim = x.shape[-1]
+    chi = np.ones(x.shape[:-1])
+    for s in range(n_sinkers):
+        dist = np.sqrt(((x - NSINKER_CENTERS[s, :dim]) ** 2).sum(-1))
+        chi *= 1.0 - np.exp(-delta * np.maximum(0.0, dist - omega / 2.0) ** 2)
+    s = np.sqrt(viscosity_ratio)
+    return (s - 1.0 / s) * (1.0 - chi) + 1.0 / s, sinker_density * (1.0 - chi)
+
+
+def solcx_material(x, eta_b=1e6, background_density=0.0):
+    eta = np.where(x[..., 0] < 0.5, 1.0, eta_b)
+    return eta, background_density - np.sin(np.pi * x[..., 1]) * np.cos(np.pi * x[..., 0])
+
+
+_S = np.sqrt(3.0 / 5.0)
+_GX = np.array([0.5 - 0.5 * _S, 0.5, 0.5 + 0.5 * _S])
+
+
+def _phi2_at_quad(dim):
+    x = _GX
+    n1 = np.stack([(1 - x) * (1 - 2 * x), 4 * x * (1 - x), x * (2 * x - 1)], axis=1)      # [q][i]
+    phi = n1
+    for _ in range(dim - 1):
+        phi = np.einsum("ab,cd->acbd", n1, phi).reshape(n1.shape[0] * phi.shape[0], -1)   # slowest index first
+    return phi                                                                             # [q lex][node lex]
+
+
+def assemble_rhs(level, rho_q, gravity):
+    """Velocity right-hand side; rho_q (n_cells, 3^dim) (already averaged if `Material averaging` says so)."""
+    dim = level.dim
+    nn = 3 ** dim
+    w = quadrature_weights(dim) * float(np.prod(level.h))
+    loc = (rho_q * w[None, :]) @ _phi2_at_quad(dim)                   # (cells, nodes)
+    f = np.zeros(level.n_u)
+    for c in range(dim):
+        if gravity[c] != 0.0:
+            np.add.at(f, level.cell_dofs_u[:, c * nn:(c + 1) * nn].astype(np.int64), gravity[c] * loc)
+    return f
+
+
+def pressure_scaling_box(level, material):
+    mid = (level.cells + 0.5) * level.h
+    eta = material(mid)[0]
+    return float(np.exp(np.log(eta).mean()) / (0.01 * level.extents[0]))
+
+
+def nsinker_problem(hier, n_sinkers=8, viscosity_ratio=1e4, averaging="harmonic average"):
+    """(viscosity_q, rhs, pressure_scaling) of benchmarks/nsinker/nsinker_gmg.prm on the given box hierarchy."""
+    act = hier.active
+    eta_q, rho_q = nsinker_material(act.quadrature_points(), n_sinkers, viscosity_ratio)
+    if averaging != "none" and not averaging.endswith("only viscosity"):
+        rho_q = average_viscosity(rho_q, averaging)          # `average` also averages the density (interface.cc:908)
+    g = np.zeros(act.dim); g[-1] = -1.0
+    f = assemble_rhs(act, rho_q, g)
+    f[act.constrained_u("zero").astype(np.int64)] = 0.0
+    return eta_q, np.concatenate([f, np.zeros(act.n_p)]), 1.0
+
+
+def solcx_problem(hier, averaging="harmonic average only viscosity"):
+    act = hier.active
+    eta_q, rho_q = solcx_material(act.quadrature_points())
+    g = np.zeros(act.dim); g[-1] = -1.0
+    f = assemble_rhs(act, rho_q, g)
+    f[act.constrained_u("tangential").astype(np.int64)] = 0.0
+    return eta_q, np.concatenate([f, np.zeros(act.n_p)]), pressure_scaling_box(act, solcx_material)

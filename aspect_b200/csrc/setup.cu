@@ -1,0 +1,405 @@
+// Context life cycle and set-up side of the C ABI: what StokesMatrixFreeHandler::setup_dofs() and
+// evaluate_material_model() hand to the operators
+// (/root/reference/source/simulator/solver/stokes_matrix_free_local_smoothing.cc:1450-1851, :173-294).
+// The host code here turns the MatrixFree-style cell->DoF maps into the batched layout the kernels use
+// (DESIGN.md "Data layout"): per 64-cell batch a list of unique nodes (private nodes first) and 16-bit
+// local slots per cell, lane-transposed so a warp reads them coalesced.
+#include "smf_internal.h"
+#include <algorithm>
+#include <cstring>
+#include <chrono>
+
+using namespace smf;
+
+namespace smf {
+int launch_diag(smf_ctx *ctx, LevelDev &L);
+
+template <class T> static int upload(smf_ctx *ctx, T **dev, const std::vector<T> &host, int64_t *bytes)
+{
+  const size_t nb = std::max<size_t>(host.size(), 1) * sizeof(T);
+  SMF_CUDA(cudaMalloc((void **)dev, nb));
+  if (!host.empty()) SMF_CUDA(cudaMemcpyAsync(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *bytes += (int64_t)nb;
+  ctx->bytes += (int64_t)nb;
+  return SMF_OK;
+}
+
+static void free_level(LevelDev &L)
+{
+  cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
+  cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
+  cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M);
+  L = LevelDev();
+}
+
+// Build the batched staging layout for one DoF family.
+//   nodes: [n_cells][npc] node entries (index | flags)
+static void build_batches(const std::vector<uint32_t> &nodes, int64_t n_cells, int npc, int64_t n_index_space,
+                          const int *round_of, int n_rounds,
+                          std::vector<uint32_t> &node_list, std::vector<uint16_t> &cell_loc,
+                          std::vector<int> &n_nodes, std::vector<int> &n_excl, int &max_nodes, bool &safe)
+{
+  const int64_t nb = (n_cells + BATCH_CELLS - 1) / BATCH_CELLS;
+  std::vector<uint8_t> touch((size_t)n_index_space, 0);
+  std::vector<std::vector<uint32_t>> uniq((size_t)nb);
+  for (int64_t b = 0; b < nb; ++b) {
+    const int64_t c0 = b * BATCH_CELLS, c1 = std::min<int64_t>(n_cells, c0 + BATCH_CELLS);
+    std::vector<uint32_t> &u = uniq[(size_t)b];
+    u.assign(nodes.begin() + c0 * npc, nodes.begin() + c1 * npc);
+    std::sort(u.begin(), u.end(), [](uint32_t a, uint32_t b2) { return (a & NODE_IDX_MASK) < (b2 & NODE_IDX_MASK); });
+    u.erase(std::unique(u.begin(), u.end(), [](uint32_t a, uint32_t b2) { return (a & NODE_IDX_MASK) == (b2 & NODE_IDX_MASK); }), u.end());
+    for (uint32_t e : u) {
+      uint8_t &t = touch[e & NODE_IDX_MASK];
+      if (t < 2) ++t;
+    }
+  }
+  max_nodes = 1;
+  for (auto &u : uniq) max_nodes = std::max<int>(max_nodes, (int)u.size());
+  max_nodes = (max_nodes + 3) & ~3;
+  node_list.assign((size_t)nb * max_nodes, 0);
+  cell_loc.assign((size_t)nb * KSUB * npc * SUB, 0);
+  n_nodes.assign((size_t)nb, 0);
+  n_excl.assign((size_t)nb, 0);
+  safe = true;
+  std::vector<int> stamp_k;
+  std::vector<uint32_t> stamp_mask;
+  for (int64_t b = 0; b < nb; ++b) {
+    std::vector<uint32_t> &u = uniq[(size_t)b];
+    // private nodes first (each group keeps ascending index order -> coalesced gathers and flushes)
+    std::stable_partition(u.begin(), u.end(), [&](uint32_t e) { return touch[e & NODE_IDX_MASK] == 1; });
+    int ne = 0;
+    for (uint32_t e : u) ne += touch[e & NODE_IDX_MASK] == 1;
+    n_nodes[(size_t)b] = (int)u.size();
+    n_excl[(size_t)b] = ne;
+    std::copy(u.begin(), u.end(), node_list.begin() + b * max_nodes);
+    // slot lookup: sorted copy of (index, slot)
+    std::vector<std::pair<uint32_t, int>> look(u.size());
+    for (size_t s = 0; s < u.size(); ++s) look[s] = {u[s] & NODE_IDX_MASK, (int)s};
+    std::sort(look.begin(), look.end());
+    const int64_t c0 = b * BATCH_CELLS, c1 = std::min<int64_t>(n_cells, c0 + BATCH_CELLS);
+    stamp_k.assign(u.size(), -1);
+    stamp_mask.assign(u.size(), 0u);
+    for (int64_t cell = c0; cell < c1; ++cell) {
+      const int k = (int)((cell - c0) / SUB), lane = (int)((cell - c0) % SUB);
+      int slots[27];
+      for (int n = 0; n < npc; ++n) {
+        const uint32_t idx = nodes[cell * npc + n] & NODE_IDX_MASK;
+        auto it = std::lower_bound(look.begin(), look.end(), std::make_pair(idx, 0));
+        const int slot = slots[n] = it->second;
+        cell_loc[(((size_t)b * KSUB + k) * npc + n) * SUB + lane] = (uint16_t)slot;
+        // inside one (sub-batch, round) every (cell, node) must hit a distinct slot
+        if (stamp_k[slot] != k) { stamp_k[slot] = k; stamp_mask[slot] = 0u; }
+        if (stamp_mask[slot] & (1u << round_of[n])) safe = false;
+      }
+      for (int n = 0; n < npc; ++n) {
+        if (stamp_mask[slots[n]] & (1u << round_of[n])) {
+          // the same cell hits one slot twice in one round (degenerate cell)
+          for (int n2 = 0; n2 < n; ++n2) if (slots[n2] == slots[n] && round_of[n2] == round_of[n]) safe = false;
+        }
+        stamp_mask[slots[n]] |= 1u << round_of[n];
+      }
+    }
+  }
+}
+}  // namespace smf
+
+extern "C" {
+
+int smf_create(const smf_config *cfg, smf_ctx **out)
+{
+  if (!cfg || !out) return SMF_ERR_INVALID;
+  *out = nullptr;
+  if ((cfg->dim != 2 && cfg->dim != 3) || cfg->degree != 2 || cfg->n_levels < 1) return SMF_ERR_UNSUPPORTED;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    return SMF_ERR_CUDA;   // no CPU fallback: the product path needs a CUDA device
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return SMF_ERR_CUDA;
+  smf_ctx *ctx = new smf_ctx();
+  ctx->cfg = *cfg;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SMF_ERR_CUDA; }
+  ctx->own_stream = true;
+  ctx->levels.resize(cfg->n_levels + 1);
+  ctx->transfers.resize(cfg->n_levels);
+  ctx->smoother_A.resize(cfg->n_levels);
+  ctx->smoother_S.resize(cfg->n_levels);
+  ctx->mgv_A.resize(cfg->n_levels);
+  ctx->mgv_S.resize(cfg->n_levels);
+  *out = ctx;
+  return SMF_OK;
+}
+
+void smf_destroy(smf_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &L : ctx->levels) free_level(L);
+  for (auto &T : ctx->transfers) { cudaFree(T.patch_u); cudaFree(T.patch_p); }
+  for (auto *mg : {&ctx->mgv_A, &ctx->mgv_S})
+    for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
+  for (double *p : ctx->krylov) cudaFree(p);
+  cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
+  cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_p); cudaFree(ctx->tmp_u2); cudaFree(ctx->tmp_p2);
+  if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+  if (ctx->graph_A) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_A);
+  if (ctx->graph_S) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_S);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *smf_last_error(const smf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int smf_set_stream(smf_ctx *ctx, void *cuda_stream)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return SMF_OK;
+}
+
+int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
+{
+  if (!ctx || !m) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  if (m->geometry != 0) return ctx->fail(SMF_ERR_UNSUPPORTED, "only Cartesian level geometry (geometry = 0) is implemented");
+  if (m->n_cells < 1 || !m->cell_dofs_u || !m->cell_dofs_p || !m->cell_size) return ctx->fail(SMF_ERR_INVALID, "incomplete level mesh");
+  if (m->n_dofs_u >= (int64_t)NODE_IDX_MASK || m->n_dofs_p >= (int64_t)NODE_IDX_MASK)
+    return ctx->fail(SMF_ERR_UNSUPPORTED, "more than 2^29 local DoFs per rank");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  LevelDev &L = ctx->lev(level);
+  ctx->bytes -= L.bytes;
+  free_level(L);
+  const int dim = ctx->cfg.dim, NN = dim == 3 ? 27 : 9, NP = dim == 3 ? 8 : 4;
+  L.dim = dim; L.n_cells = m->n_cells; L.n_u = m->n_dofs_u; L.n_p = m->n_dofs_p;
+  for (int d = 0; d < dim; ++d) L.h[d] = m->cell_size[d];
+
+  // constraint bitmaps
+  std::vector<uint8_t> cu((size_t)L.n_u, 0), cp((size_t)L.n_p, 0);
+  for (int64_t i = 0; i < m->n_constrained_u; ++i) {
+    if (m->constrained_u[i] >= (uint64_t)L.n_u) return ctx->fail(SMF_ERR_INVALID, "constrained velocity index out of range");
+    cu[m->constrained_u[i]] = 1;
+  }
+  for (int64_t i = 0; i < m->n_constrained_p; ++i) {
+    if (m->constrained_p[i] >= (uint64_t)L.n_p) return ctx->fail(SMF_ERR_INVALID, "constrained pressure index out of range");
+    cp[m->constrained_p[i]] = 1;
+  }
+  // node maps (component 0 index | per-component constraint flags); verify the interleaved-components layout
+  std::vector<uint32_t> nodes_u((size_t)L.n_cells * NN), nodes_p((size_t)L.n_cells * NP);
+  for (int64_t cell = 0; cell < L.n_cells; ++cell) {
+    const uint32_t *cd = m->cell_dofs_u + cell * dim * NN;
+    for (int n = 0; n < NN; ++n) {
+      const uint32_t i0 = cd[n];
+      if ((int64_t)i0 + dim > L.n_u) return ctx->fail(SMF_ERR_INVALID, "velocity DoF index out of range");
+      uint32_t flags = 0;
+      for (int c = 0; c < dim; ++c) {
+        if (cd[c * NN + n] != i0 + c)
+          return ctx->fail(SMF_ERR_UNSUPPORTED, "cell_dofs_u: the components of a node are not consecutive DoFs");
+        if (cu[i0 + c]) flags |= 1u << (NODE_FLAG_SHIFT + c);
+      }
+      nodes_u[cell * NN + n] = i0 | flags;
+    }
+    const uint32_t *pd = m->cell_dofs_p + cell * NP;
+    for (int n = 0; n < NP; ++n) {
+      if (pd[n] >= (uint64_t)L.n_p) return ctx->fail(SMF_ERR_INVALID, "pressure DoF index out of range");
+      nodes_p[cell * NP + n] = pd[n] | (cp[pd[n]] ? (1u << 31) : 0u);
+    }
+  }
+  // batches
+  int round_u[27], round_p[8];
+  for (int n = 0; n < NN; ++n)
+    round_u[n] = dim == 3 ? ((n % 3) == 2) + 2 * (((n / 3) % 3) == 2) + 4 * ((n / 9) == 2) : ((n % 3) == 2) + 2 * ((n / 3) == 2);
+  for (int n = 0; n < NP; ++n) round_p[n] = n;
+  std::vector<uint32_t> nl_u, nl_p;
+  std::vector<uint16_t> loc_u, loc_p;
+  std::vector<int> nn_u, ne_u, nn_p, ne_p;
+  bool safe_u = true, safe_p = true;
+  build_batches(nodes_u, L.n_cells, NN, L.n_u, round_u, 1 << dim, nl_u, loc_u, nn_u, ne_u, L.max_nodes_u, safe_u);
+  build_batches(nodes_p, L.n_cells, NP, L.n_p, round_p, NP, nl_p, loc_p, nn_p, ne_p, L.max_nodes_p, safe_p);
+  if (L.max_nodes_u > 65535 || L.max_nodes_p > 65535) return ctx->fail(SMF_ERR_UNSUPPORTED, "batch too large for 16-bit slots");
+  L.safe_rounds = (safe_u && safe_p) ? 1 : 0;
+  L.n_batches = (int)nn_u.size();
+  std::vector<int> info((size_t)L.n_batches * BATCH_INFO, 0);
+  for (int b = 0; b < L.n_batches; ++b) {
+    info[b * BATCH_INFO + 0] = nn_u[b]; info[b * BATCH_INFO + 1] = ne_u[b];
+    info[b * BATCH_INFO + 2] = nn_p[b]; info[b * BATCH_INFO + 3] = ne_p[b];
+    info[b * BATCH_INFO + 4] = (int)std::min<int64_t>(BATCH_CELLS, L.n_cells - (int64_t)b * BATCH_CELLS);
+  }
+  std::vector<uint32_t> cons_u(m->constrained_u, m->constrained_u + m->n_constrained_u);
+  std::vector<uint32_t> cons_p(m->constrained_p, m->constrained_p + m->n_constrained_p);
+  L.n_constrained_u = m->n_constrained_u; L.n_constrained_p = m->n_constrained_p;
+  int e;
+  if ((e = upload(ctx, &L.batch_info, info, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.node_list_u, nl_u, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.node_list_p, nl_p, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.cell_loc_u, loc_u, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.cell_loc_p, loc_p, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.cell_nodes_u, nodes_u, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.cell_nodes_p, nodes_p, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.constrained_u, cons_u, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.constrained_p, cons_p, &L.bytes))) return e;
+  SMF_CUDA(cudaMalloc(&L.dinv_A, sizeof(double) * L.n_u));
+  SMF_CUDA(cudaMalloc(&L.dinv_M, sizeof(double) * L.n_p));
+  L.bytes += sizeof(double) * (L.n_u + L.n_p);
+  ctx->bytes += sizeof(double) * (L.n_u + L.n_p);
+  ctx->smoothers_ready = false;
+  // host copies of the raw maps are needed once more by smf_set_transfer
+  L.h_nodes_u = std::move(nodes_u);
+  L.h_nodes_p = std::move(nodes_p);
+  return SMF_OK;
+}
+
+int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
+{
+  if (!ctx || !children) return SMF_ERR_INVALID;
+  if (fine_level < 1 || fine_level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "fine_level out of range");
+  LevelDev &F = ctx->levels[fine_level], &C = ctx->levels[fine_level - 1];
+  if (F.n_cells == 0 || C.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set both levels before their transfer");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  const int dim = ctx->cfg.dim, NCH = 1 << dim;
+  TransferDev &T = ctx->transfers[fine_level];
+  cudaFree(T.patch_u); cudaFree(T.patch_p);
+  T = TransferDev();
+  T.n_parents = C.n_cells;
+  auto build = [&](int npd, const std::vector<uint32_t> &fine_nodes, int64_t n_fine_index, std::vector<uint32_t> &patch) -> bool {
+    const int npp = 2 * npd - 1;
+    int npatch = 1, nloc = 1;
+    for (int d = 0; d < dim; ++d) { npatch *= npp; nloc *= npd; }
+    patch.assign((size_t)T.n_parents * npatch, 0);
+    std::vector<uint8_t> seen((size_t)n_fine_index, 0);
+    for (int64_t par = 0; par < T.n_parents; ++par)
+      for (int s = 0; s < npatch; ++s) {
+        int r = s, child = 0, a = 0, mul = 1;
+        for (int d = 0; d < dim; ++d) {
+          const int sd = r % npp; r /= npp;
+          const int o = sd > (npd - 1) ? 1 : 0;
+          child |= o << d;
+          a += (sd - (npd - 1) * o) * mul;
+          mul *= npd;
+        }
+        const int32_t fc = children[par * NCH + child];
+        if (fc < 0 || fc >= F.n_cells) return false;
+        const uint32_t idx = fine_nodes[(size_t)fc * nloc + a] & NODE_IDX_MASK;
+        uint32_t e = idx;
+        if (!seen[idx]) { seen[idx] = 1; e |= 1u << 31; }
+        patch[(size_t)par * npatch + s] = e;
+      }
+    return true;
+  };
+  std::vector<uint32_t> pu, pp;
+  if (!build(3, F.h_nodes_u, F.n_u, pu) || !build(2, F.h_nodes_p, F.n_p, pp))
+    return ctx->fail(SMF_ERR_UNSUPPORTED, "children table has unrefined / out-of-range entries (adaptive meshes not implemented)");
+  int64_t bytes = 0;
+  int e;
+  if ((e = upload(ctx, &T.patch_u, pu, &bytes))) return e;
+  if ((e = upload(ctx, &T.patch_p, pp, &bytes))) return e;
+  T.set = true;
+  return SMF_OK;
+}
+
+int smf_set_copy_indices(smf_ctx *ctx, const uint32_t *au, const uint32_t *ap)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the active level first");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  cudaFree(ctx->copy_u); cudaFree(ctx->copy_p);
+  ctx->copy_u = ctx->copy_p = nullptr;
+  int64_t bytes = 0;
+  int e;
+  if (au) { std::vector<uint32_t> v(au, au + A.n_u); if ((e = upload(ctx, &ctx->copy_u, v, &bytes))) return e; }
+  if (ap) { std::vector<uint32_t> v(ap, ap + A.n_p); if ((e = upload(ctx, &ctx->copy_p, v, &bytes))) return e; }
+  return SMF_OK;
+}
+
+}  // extern "C"
+
+namespace smf {
+// raw [cell][n_eta] -> lane-transposed [cell/32][n_eta][32], padded with 1.0
+__global__ void transpose_eta_kernel(const double *raw, double *out, int64_t n_cells, int n_eta, int64_t n_padded_cells)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_padded_cells * n_eta) return;
+  const int64_t grp = t / ((int64_t)n_eta * SUB);
+  const int rem = (int)(t % ((int64_t)n_eta * SUB));
+  const int q = rem / SUB, lane = rem % SUB;
+  const int64_t cell = grp * SUB + lane;
+  out[t] = cell < n_cells ? raw[cell * n_eta + q] : 1.0;
+}
+}  // namespace smf
+
+extern "C" {
+
+int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *d)
+{
+  if (!ctx || !d || !d->viscosity) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  LevelDev &L = ctx->lev(level);
+  if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the level mesh first");
+  const int NN = L.dim == 3 ? 27 : 9;
+  if (d->n_per_cell != 1 && d->n_per_cell != NN) return ctx->fail(SMF_ERR_INVALID, "n_per_cell must be 1 or 3^dim");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  const int64_t padded = (int64_t)L.n_batches * BATCH_CELLS;
+  const int64_t n_out = padded * d->n_per_cell;
+  if (L.eta && L.n_eta != d->n_per_cell) { cudaFree(L.eta); L.eta = nullptr; }
+  if (!L.eta) {
+    SMF_CUDA(cudaMalloc(&L.eta, sizeof(double) * n_out));
+    L.bytes += sizeof(double) * n_out; ctx->bytes += sizeof(double) * n_out;
+  }
+  double *raw = nullptr;
+  SMF_CUDA(cudaMalloc(&raw, sizeof(double) * L.n_cells * d->n_per_cell));
+  SMF_CUDA(cudaMemcpyAsync(raw, d->viscosity, sizeof(double) * L.n_cells * d->n_per_cell, cudaMemcpyHostToDevice, ctx->stream));
+  transpose_eta_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(raw, L.eta, L.n_cells, d->n_per_cell, padded);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(raw);
+  L.n_eta = d->n_per_cell; L.ps = d->pressure_scaling; L.compressible = d->is_compressible;
+  L.has_cell_data = true; L.has_diag = false;
+  ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+int smf_vec_alloc(smf_ctx *ctx, int64_t n, double **p)
+{
+  if (!ctx || !p || n < 0) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  SMF_CUDA(cudaMalloc(p, sizeof(double) * std::max<int64_t>(n, 1)));
+  SMF_CUDA(cudaMemsetAsync(*p, 0, sizeof(double) * std::max<int64_t>(n, 1), ctx->stream));
+  ctx->bytes += sizeof(double) * n;
+  return SMF_OK;
+}
+int smf_vec_free(smf_ctx *ctx, double *p)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  SMF_CUDA(cudaFree(p));
+  return SMF_OK;
+}
+int smf_vec_h2d(smf_ctx *ctx, double *dev, const double *host, int64_t n)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaMemcpyAsync(dev, host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  return SMF_OK;
+}
+int smf_vec_d2h(smf_ctx *ctx, double *host, const double *dev, int64_t n)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SMF_OK;
+}
+int smf_synchronize(smf_ctx *ctx)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SMF_OK;
+}
+int64_t smf_kernel_launches(const smf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t smf_device_bytes(const smf_ctx *ctx) { return ctx ? ctx->bytes : 0; }
+
+}  // extern "C"

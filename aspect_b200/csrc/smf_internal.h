@@ -1,0 +1,127 @@
+// Internal declarations of the B200 matrix-free GMG Stokes library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/smf_b200.h"
+
+namespace smf {
+
+constexpr int BATCH_CELLS = 64;   // cells staged per thread block (two 32-cell sub-batches, Morton 4x4x4 / 8x8)
+constexpr int SUB = 32;           // cells per sub-batch = lanes of a warp
+constexpr int KSUB = BATCH_CELLS / SUB;
+constexpr uint32_t NODE_IDX_MASK = 0x1fffffffu;   // low 29 bits: DoF index of component 0 of the node
+constexpr uint32_t NODE_FLAG_SHIFT = 29;          // bits 29..31: component c of this node is constrained
+
+// per-batch header (ints): n_nodes_u, n_excl_u, n_nodes_p, n_excl_p, n_cells, pad x3
+constexpr int BATCH_INFO = 8;
+
+struct LevelDev {
+  int dim = 0;
+  int64_t n_cells = 0, n_u = 0, n_p = 0;
+  int n_batches = 0;
+  int max_nodes_u = 0, max_nodes_p = 0;      // padded staging sizes (nodes per batch)
+  int safe_rounds = 1;                        // 1: scatter rounds are collision-free inside every sub-batch
+  int *batch_info = nullptr;                  // [n_batches][BATCH_INFO]
+  uint32_t *node_list_u = nullptr;            // [n_batches][max_nodes_u]  exclusive nodes first
+  uint32_t *node_list_p = nullptr;            // [n_batches][max_nodes_p]
+  uint16_t *cell_loc_u = nullptr;             // [n_batches][KSUB][3^dim][SUB]
+  uint16_t *cell_loc_p = nullptr;             // [n_batches][KSUB][2^dim][SUB]
+  uint32_t *cell_nodes_u = nullptr;           // [n_cells][3^dim]   (index | flags), raw map
+  uint32_t *cell_nodes_p = nullptr;           // [n_cells][2^dim]
+  uint32_t *constrained_u = nullptr; int64_t n_constrained_u = 0;
+  uint32_t *constrained_p = nullptr; int64_t n_constrained_p = 0;
+  double h[3] = {1, 1, 1};
+  // cell data
+  double *eta = nullptr; int n_eta = 0; double ps = 1.0; int compressible = 0; bool has_cell_data = false;
+  // inverse diagonals
+  double *dinv_A = nullptr, *dinv_M = nullptr; bool has_diag = false;
+  int64_t bytes = 0;
+  std::vector<uint32_t> h_nodes_u, h_nodes_p;   // host copies of the raw maps (needed by smf_set_transfer)
+};
+
+struct TransferDev {              // level l-1 -> l
+  int64_t n_parents = 0;
+  uint32_t *patch_u = nullptr;    // [n_parents][5^dim] fine node (component-0 DoF) | bit31 = this parent owns the node
+  uint32_t *patch_p = nullptr;    // [n_parents][3^dim]
+  bool set = false;
+};
+
+struct Smoother {                 // PreconditionChebyshev state of one level
+  int degree = 4;
+  double smoothing_range = 15.0;
+  int eig_cg_n_iterations = 10;
+  double lambda_min = 0, lambda_max = 0, theta = 1, delta = 0;
+  int cg_its = 0;
+};
+
+struct MGVectors {                // per level: solution, defect, t, and a Chebyshev scratch
+  double *x = nullptr, *b = nullptr, *t = nullptr, *xo = nullptr;
+};
+
+}  // namespace smf
+
+struct smf_ctx {
+  smf_config cfg{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  std::vector<smf::LevelDev> levels;     // index 0..n_levels-1, plus [n_levels] = active
+  std::vector<smf::TransferDev> transfers;   // index l = transfer (l-1 -> l)
+  std::vector<smf::Smoother> smoother_A, smoother_S;
+  std::vector<smf::MGVectors> mgv_A, mgv_S;
+  uint32_t *copy_u = nullptr, *copy_p = nullptr;      // active -> finest level index maps (nullptr = identity)
+  bool smoothers_ready = false;
+  int64_t launches = 0;
+  int64_t bytes = 0;
+  double *scratch = nullptr; int64_t scratch_n = 0;   // reduction scratch
+  double *host_pinned = nullptr; int64_t host_pinned_n = 0;
+  // Krylov workspace
+  std::vector<double *> krylov; int64_t krylov_n = 0;
+  double *tmp_u = nullptr, *tmp_p = nullptr, *tmp_u2 = nullptr, *tmp_p2 = nullptr;
+  int n_A_prec = 0, n_S_prec = 0;
+  void *graph_A = nullptr, *graph_S = nullptr;        // cudaGraphExec_t of the V-cycles (with fixed in/out buffers)
+
+  smf::LevelDev &lev(int level) { return levels[level < 0 ? cfg.n_levels : level]; }
+  int fail(int code, const std::string &msg) { err = msg; return code; }
+};
+
+#define SMF_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ctx->fail(SMF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+namespace smf {
+// operators.cu
+int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);
+int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_p);
+int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);
+int launch_diag(smf_ctx *ctx, LevelDev &L);
+int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
+int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);
+// vector kernels (vecops.cu)
+int vec_set(smf_ctx *ctx, double *x, double v, int64_t n);
+int vec_copy(smf_ctx *ctx, double *y, const double *x, int64_t n);
+int vec_scale(smf_ctx *ctx, double *x, double a, int64_t n);
+int vec_axpy(smf_ctx *ctx, double *y, double a, const double *x, int64_t n);               // y += a x
+int vec_sadd(smf_ctx *ctx, double *y, double s, double a, const double *x, int64_t n);     // y = s y + a x
+int vec_pointwise(smf_ctx *ctx, double *z, double a, const double *d, const double *x, int64_t n);   // z = a d.x
+int vec_dot(smf_ctx *ctx, const double *x, const double *y, int64_t n, double *host_result);   // synchronises
+int vec_norm2(smf_ctx *ctx, const double *x, int64_t n, double *host_result);                  // synchronises
+// h_j = V_j . w (j < k) and w.w; results stay on the device (and go to host_out when sync is set)
+int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double *w, int64_t n, double *host_out, bool sync);
+// w -= sum_j h_j V_j with the h of the preceding vec_multi_dot; host_out = {h_0..h_{k-1}, |w_old|^2, |w_new|^2}
+int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *host_out);
+int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const double *coef_host, int k, int64_t n);
+int vec_mod11(smf_ctx *ctx, double *x, int64_t first, double mean, int64_t n);
+int cheb_first(smf_ctx *ctx, double *x, const double *dinv, const double *b, double inv_theta, int64_t n);
+int cheb_update(smf_ctx *ctx, double *x, double *xo, const double *dinv, const double *b, const double *t,
+                double f1, double f2, bool use_xo, int64_t n);   // xo <- (1+f1) x - f1 xo + f2 dinv (b - t); caller swaps
+int vec_residual(smf_ctx *ctx, double *t, const double *b, int64_t n);   // t = b - t
+int vec_gather(smf_ctx *ctx, double *y, const double *x, const uint32_t *idx, int64_t n, bool scatter);
+}  // namespace smf

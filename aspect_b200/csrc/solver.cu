@@ -1,0 +1,503 @@
+// Host driver of the block-GMG Stokes solve on device-resident vectors, plus the operator side of the C ABI.
+//
+// Mirrors /root/reference/source/simulator/solver/stokes_matrix_free_local_smoothing.cc:758-1313 (solve()):
+// Chebyshev smoother set-up and eigenvalue estimation (:774-849), coarse "solver" = level-0 smoother (:855-860),
+// V-cycles prec_A / prec_Schur (:893-916), tolerance (:977-1041), cheap GMRES (:1277-1301), and
+// /root/reference/include/aspect/simulator/solver/block_stokes_preconditioner.h:220-255, with the deal.II 9.6
+// semantics restated in SURVEY.md App. A (PreconditionChebyshev, Multigrid::level_v_step, SolverGMRES).
+// Control flow stays on the host (as in the reference); every vector lives in HBM; one stream sync per outer
+// iteration (Hessenberg column), two per CG step of the eigenvalue estimation.
+#include "smf_internal.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+using namespace smf;
+
+namespace smf {
+int launch_diag(smf_ctx *ctx, LevelDev &L);
+
+#define TRY(x) do { int e__ = (x); if (e__) return e__; } while (0)
+
+static double now_s()
+{ return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// extreme eigenvalues of the symmetric tridiagonal (diag, off) by Sturm bisection
+static void tridiag_extreme(const std::vector<double> &d, const std::vector<double> &o, double &lmin, double &lmax)
+{
+  const int n = (int)d.size();
+  if (n == 0) { lmin = lmax = 1.0; return; }
+  if (n == 1) { lmin = lmax = d[0]; return; }
+  double lo = d[0], hi = d[0];
+  for (int i = 0; i < n; ++i) {
+    const double r = (i > 0 ? std::fabs(o[i - 1]) : 0.0) + (i < n - 1 ? std::fabs(o[i]) : 0.0);
+    lo = std::min(lo, d[i] - r); hi = std::max(hi, d[i] + r);
+  }
+  auto count_below = [&](double x) {   // number of eigenvalues < x
+    int cnt = 0; double q = d[0] - x;
+    if (q < 0) ++cnt;
+    for (int i = 1; i < n; ++i) {
+      if (q == 0.0) q = 1e-300;
+      q = d[i] - x - o[i - 1] * o[i - 1] / q;
+      if (q < 0) ++cnt;
+    }
+    return cnt;
+  };
+  auto kth = [&](int k) {   // k-th smallest (0-based)
+    double a = lo, b = hi;
+    for (int it = 0; it < 200; ++it) {
+      const double m = 0.5 * (a + b);
+      if (m == a || m == b) break;
+      if (count_below(m) > k) b = m; else a = m;
+    }
+    return 0.5 * (a + b);
+  };
+  lmin = kth(0); lmax = kth(n - 1);
+}
+
+struct MGSide {           // one of the two hierarchies
+  bool velocity;
+  std::vector<Smoother> *sm;
+  std::vector<MGVectors> *v;
+  int steps;              // SmootherRelaxation steps (1 for A, 4 for Schur: local_smoothing.cc:775-776, :803-804)
+};
+
+static int64_t lsize(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].n_u : ctx->levels[l].n_p; }
+static const double *ldinv(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].dinv_A : ctx->levels[l].dinv_M; }
+static int lapply(smf_ctx *ctx, const MGSide &S, int l, double *dst, const double *src)
+{ return S.velocity ? launch_vmult_A(ctx, ctx->levels[l], dst, src) : launch_vmult_mass(ctx, ctx->levels[l], dst, src); }
+
+// PreconditionChebyshev::estimate_eigenvalues (App. A.2): Jacobi-preconditioned CG on (global index mod 11) - mean
+static int estimate_eigenvalues(smf_ctx *ctx, const MGSide &S, int l)
+{
+  Smoother &sm = (*S.sm)[l];
+  MGVectors &V = (*S.v)[l];
+  const int64_t n = lsize(ctx, S, l);
+  const double *dinv = ldinv(ctx, S, l);
+  // mean of i mod 11 over 0..n-1
+  const int64_t full = n / 11, rem = n % 11;
+  const double mean = (double)(full * 55 + rem * (rem - 1) / 2) / (double)n;
+  double *r = V.b, *z = V.t, *p = V.x, *v = V.xo;
+  TRY(vec_mod11(ctx, r, 0, mean, n));
+  double res2;
+  TRY(vec_norm2(ctx, r, n, &res2));
+  std::vector<double> diag, off;
+  int it = 0;
+  double rz_old = 0, alpha_old = 0, beta = 0;
+  const double tol = 1e-7;
+  if (std::sqrt(res2) > tol && sm.eig_cg_n_iterations > 0)
+    while (true) {
+      ++it;
+      TRY(vec_pointwise(ctx, z, 1.0, dinv, r, n));
+      double rz;
+      TRY(vec_dot(ctx, r, z, n, &rz));
+      if (it > 1) { beta = rz / rz_old; TRY(vec_sadd(ctx, p, beta, 1.0, z, n)); }
+      else TRY(vec_copy(ctx, p, z, n));
+      TRY(lapply(ctx, S, l, v, p));
+      double pv;
+      TRY(vec_dot(ctx, p, v, n, &pv));
+      const double alpha = rz / pv;
+      TRY(vec_axpy(ctx, r, -alpha, v, n));
+      TRY(vec_norm2(ctx, r, n, &res2));
+      if (it > 1) { diag.push_back(1.0 / alpha + beta / alpha_old); off.push_back(std::sqrt(beta) / alpha_old); }
+      else diag.push_back(1.0 / alpha);
+      rz_old = rz; alpha_old = alpha;
+      if (it >= sm.eig_cg_n_iterations || std::sqrt(res2) <= tol) break;
+    }
+  double lmin = 1.0, lmax = 1.0;
+  tridiag_extreme(diag, off, lmin, lmax);
+  sm.cg_its = it;
+  sm.lambda_min = lmin;
+  sm.lambda_max = 1.2 * lmax;
+  const double alpha = sm.smoothing_range > 1.0 ? sm.lambda_max / sm.smoothing_range : std::min(0.9 * sm.lambda_max, lmin);
+  sm.delta = 0.5 * (sm.lambda_max - alpha);
+  sm.theta = 0.5 * (sm.lambda_max + alpha);
+  return SMF_OK;
+}
+
+// Chebyshev iterations after the first update; x holds the current iterate, xo the previous one (if have_old)
+static int cheb_tail(smf_ctx *ctx, const MGSide &S, int l, double *&x, double *&xo, const double *b, double *t, bool have_old)
+{
+  const Smoother &sm = (*S.sm)[l];
+  const int64_t n = lsize(ctx, S, l);
+  if (sm.degree < 2 || std::fabs(sm.delta) < 1e-40) return SMF_OK;
+  double rhok = sm.delta / sm.theta;
+  const double sigma = sm.theta / sm.delta;
+  for (int k = 0; k < sm.degree - 1; ++k) {
+    TRY(lapply(ctx, S, l, t, x));
+    const double rhokp = 1.0 / (2.0 * sigma - rhok);
+    const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / sm.delta;
+    rhok = rhokp;
+    TRY(cheb_update(ctx, x, xo, ldinv(ctx, S, l), b, t, f1, f2, have_old, n));
+    std::swap(x, xo);
+    have_old = true;
+  }
+  return SMF_OK;
+}
+// PreconditionChebyshev::vmult: zero initial guess, degree-1 operator applications
+static int cheb_vmult(smf_ctx *ctx, const MGSide &S, int l, double *&x, double *&xo, const double *b, double *t)
+{
+  const Smoother &sm = (*S.sm)[l];
+  TRY(cheb_first(ctx, x, ldinv(ctx, S, l), b, 1.0 / sm.theta, lsize(ctx, S, l)));
+  return cheb_tail(ctx, S, l, x, xo, b, t, false);
+}
+// PreconditionChebyshev::step: non-zero initial guess, degree operator applications
+static int cheb_step(smf_ctx *ctx, const MGSide &S, int l, double *&x, double *&xo, const double *b, double *t)
+{
+  const Smoother &sm = (*S.sm)[l];
+  const int64_t n = lsize(ctx, S, l);
+  TRY(lapply(ctx, S, l, t, x));
+  // x_new = x + (1/theta) D^-1 (b - A x): the update kernel with f1 = 0, written to xo, then swapped
+  TRY(cheb_update(ctx, x, xo, ldinv(ctx, S, l), b, t, 0.0, 1.0 / sm.theta, false, n));
+  std::swap(x, xo);
+  return cheb_tail(ctx, S, l, x, xo, b, t, true);
+}
+
+// Multigrid::level_v_step (App. A.3); defect of level l is V[l].b, the result ends in V[l].x
+static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
+{
+  MGVectors &V = (*S.v)[l];
+  const int which = S.velocity ? 0 : 1;
+  double *x = V.x, *xo = V.xo;
+  // pre-smoothing: SmootherRelaxation::apply = vmult + (steps-1) x step; on level 0 this is the coarse solver
+  TRY(cheb_vmult(ctx, S, l, x, xo, V.b, V.t));
+  for (int s = 1; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));
+  if (l > 0) {
+    const int64_t n = lsize(ctx, S, l);
+    MGVectors &C = (*S.v)[l - 1];
+    TRY(lapply(ctx, S, l, V.t, x));
+    TRY(vec_residual(ctx, V.t, V.b, n));                                     // t = defect - A x
+    TRY(vec_set(ctx, C.b, 0.0, lsize(ctx, S, l - 1)));
+    TRY(launch_restrict_add(ctx, which, l, C.b, V.t));
+    TRY(level_v_step(ctx, S, l - 1));
+    TRY(launch_prolongate(ctx, which, l, x, C.x, true));                     // x += P x_coarse
+    for (int s = 0; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));   // post-smoothing
+  }
+  V.x = x; V.xo = xo;
+  return SMF_OK;
+}
+
+static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
+{
+  if (!ctx->smoothers_ready) return ctx->fail(SMF_ERR_INVALID, "call smf_setup_smoothers before applying a V-cycle");
+  MGSide S{velocity, velocity ? &ctx->smoother_A : &ctx->smoother_S, velocity ? &ctx->mgv_A : &ctx->mgv_S, velocity ? 1 : 4};
+  const int L = ctx->cfg.n_levels - 1;
+  const int64_t n = lsize(ctx, S, L);
+  const uint32_t *map = velocity ? ctx->copy_u : ctx->copy_p;
+  MGVectors &V = (*S.v)[L];
+  // copy_to_mg
+  if (map) TRY(vec_gather(ctx, V.b, src, map, n, true));
+  else TRY(vec_copy(ctx, V.b, src, n));
+  TRY(level_v_step(ctx, S, L));
+  // copy_from_mg
+  if (map) TRY(vec_gather(ctx, dst, V.x, map, n, false));
+  else TRY(vec_copy(ctx, dst, V.x, n));
+  return SMF_OK;
+}
+
+static int ensure_tmp(smf_ctx *ctx)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (!ctx->tmp_u) {
+    SMF_CUDA(cudaMalloc(&ctx->tmp_u, sizeof(double) * (A.n_u + A.n_p)));
+    ctx->tmp_p = ctx->tmp_u + A.n_u;
+    SMF_CUDA(cudaMalloc(&ctx->tmp_u2, sizeof(double) * (A.n_u + A.n_p)));
+    ctx->tmp_p2 = ctx->tmp_u2 + A.n_u;
+    ctx->bytes += 2 * sizeof(double) * (A.n_u + A.n_p);
+  }
+  return SMF_OK;
+}
+
+// BlockSchurPreconditioner::vmult, cheap variant (block_stokes_preconditioner.h:220-255)
+static int precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  TRY(ensure_tmp(ctx));
+  TRY(vcycle(ctx, false, dst_p, src_p));            // S^-1 (SchurApproximation::vmult :346-351)
+  ctx->n_S_prec++;
+  TRY(vec_scale(ctx, dst_p, -1.0, A.n_p));
+  TRY(launch_vmult_BT(ctx, A, ctx->tmp_u, dst_p));  // tmp = B^T z_p
+  TRY(vec_sadd(ctx, ctx->tmp_u, -1.0, 1.0, src_u, A.n_u));   // tmp = src_u - tmp
+  TRY(vcycle(ctx, true, dst_u, ctx->tmp_u));        // A^-1 (InverseVelocityBlock::vmult :148-152)
+  ctx->n_A_prec++;
+  return SMF_OK;
+}
+
+static int ensure_krylov(smf_ctx *ctx, int n_vectors)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t n = A.n_u + A.n_p;
+  if (ctx->krylov_n != n) {
+    for (double *p : ctx->krylov) cudaFree(p);
+    ctx->krylov.clear();
+    ctx->krylov_n = n;
+  }
+  while ((int)ctx->krylov.size() < n_vectors) {
+    double *p = nullptr;
+    SMF_CUDA(cudaMalloc(&p, sizeof(double) * n));
+    ctx->krylov.push_back(p);
+    ctx->bytes += sizeof(double) * n;
+  }
+  return SMF_OK;
+}
+
+// SolverGMRES with right preconditioning and delayed classical Gram-Schmidt (App. A.5)
+static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double *x_p, const double *b_u, const double *b_p,
+                 double tol, smf_solve_result *res)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t nu = A.n_u, np = A.n_p, n = nu + np;
+  const int restart = std::max(1, std::min(prm->gmres_restart_length, 100));
+  const int max_its = prm->n_cheap_stokes_solver_steps;
+  TRY(ensure_krylov(ctx, restart + 3));
+  std::vector<double *> &K = ctx->krylov;
+  double *p = K[restart + 1], *xb = K[restart + 2];   // p: scratch block vector; xb: contiguous copy of the iterate
+  TRY(vec_copy(ctx, xb, x_u, nu));
+  TRY(vec_copy(ctx, xb + nu, x_p, np));
+  const double eps = 2.220446049250313e-16;
+  std::vector<double> H((size_t)(restart + 1) * restart, 0.0), gamma(restart + 1), ci(restart), si(restart), h(restart + 3), hh(restart + 3);
+  int its = 0;
+  bool re_orth = false;
+  int state = 0;   // 0 iterate, 1 success, 2 failure
+  double rho = 0;
+  bool first = true;
+  while (state == 0) {
+    // p = b - A x
+    TRY(launch_vmult_stokes(ctx, A, p, p + nu, xb, xb + nu));
+    TRY(vec_sadd(ctx, p, -1.0, 1.0, b_u, nu));
+    TRY(vec_sadd(ctx, p + nu, -1.0, 1.0, b_p, np));
+    double r2;
+    TRY(vec_norm2(ctx, p, n, &r2));
+    rho = std::sqrt(r2);
+    if (first) { res->initial_residual = rho; first = false; }
+    if (rho <= tol) { state = 1; break; }
+    if (its >= max_its) { state = 2; break; }
+    std::fill(gamma.begin(), gamma.end(), 0.0);
+    gamma[0] = rho;
+    TRY(vec_copy(ctx, K[0], p, n));
+    TRY(vec_scale(ctx, K[0], 1.0 / rho, n));
+    int dim = 0;
+    for (int j = 0; j < restart && state == 0; ++j) {
+      ++its;
+      double *vv = K[j + 1];
+      TRY(precondition(ctx, p, p + nu, K[j], K[j] + nu));
+      TRY(launch_vmult_stokes(ctx, A, vv, vv + nu, p, p + nu));
+      dim = j + 1;
+      const bool consider = !re_orth && (its % 5 == 0);
+      TRY(vec_multi_dot(ctx, K.data(), dim, vv, n, nullptr, false));
+      TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, h.data()));   // h[0..dim-1], |vv_old|^2, |vv_new|^2
+      const double norm_start = std::sqrt(h[dim]);
+      double nrm = std::sqrt(h[dim + 1]);
+      if (consider && !(nrm > 10.0 * norm_start * std::sqrt(eps))) re_orth = true;
+      if (re_orth) {
+        TRY(vec_multi_dot(ctx, K.data(), dim, vv, n, nullptr, false));
+        TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, hh.data()));
+        for (int i = 0; i < dim; ++i) h[i] += hh[i];
+        nrm = std::sqrt(hh[dim + 1]);
+      }
+      h[dim] = nrm;
+      if (nrm != 0.0) TRY(vec_scale(ctx, vv, 1.0 / nrm, n));
+      // Givens rotations
+      for (int i = 0; i < j; ++i) {
+        const double t = h[i];
+        h[i] = ci[i] * t + si[i] * h[i + 1];
+        h[i + 1] = -si[i] * t + ci[i] * h[i + 1];
+      }
+      const double s = std::sqrt(h[j] * h[j] + h[j + 1] * h[j + 1]);
+      ci[j] = h[j] / s; si[j] = h[j + 1] / s;
+      h[j] = s;
+      gamma[j + 1] = -si[j] * gamma[j];
+      gamma[j] *= ci[j];
+      for (int i = 0; i < dim; ++i) H[(size_t)i * restart + j] = h[i];
+      rho = std::fabs(gamma[dim]);
+      if (rho <= tol) state = 1;
+      else if (its >= max_its) state = 2;
+    }
+    // x += P^-1 (V y), H y = gamma
+    std::vector<double> y(dim);
+    for (int i = dim - 1; i >= 0; --i) {
+      double s = gamma[i];
+      for (int k = i + 1; k < dim; ++k) s -= H[(size_t)i * restart + k] * y[k];
+      y[i] = s / H[(size_t)i * restart + i];
+    }
+    TRY(vec_set(ctx, p, 0.0, n));
+    TRY(vec_multi_add(ctx, p, K.data(), y.data(), dim, n));
+    double *z = K[dim];       // v_dim is not part of the combination any more: reuse its storage
+    TRY(precondition(ctx, z, z + nu, p, p + nu));
+    TRY(vec_axpy(ctx, xb, 1.0, z, n));
+  }
+  TRY(vec_copy(ctx, x_u, xb, nu));
+  TRY(vec_copy(ctx, x_p, xb + nu, np));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  res->iterations = its;
+  res->final_residual = rho;
+  return state == 1 ? SMF_OK : SMF_NO_CONVERGENCE;
+}
+
+}  // namespace smf
+
+extern "C" {
+
+int smf_vmult_stokes(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+{ if (!ctx) return SMF_ERR_INVALID; return launch_vmult_stokes(ctx, ctx->lev(SMF_ACTIVE), dst_u, dst_p, src_u, src_p); }
+int smf_vmult_A(smf_ctx *ctx, int level, double *dst, const double *src)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  return launch_vmult_A(ctx, ctx->lev(level), dst, src);
+}
+int smf_vmult_BT(smf_ctx *ctx, double *dst_u, const double *src_p)
+{ if (!ctx) return SMF_ERR_INVALID; return launch_vmult_BT(ctx, ctx->lev(SMF_ACTIVE), dst_u, src_p); }
+int smf_vmult_mass(smf_ctx *ctx, int level, double *dst, const double *src)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  return launch_vmult_mass(ctx, ctx->lev(level), dst, src);
+}
+
+int smf_vmult_stokes_host(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  TRY(ensure_tmp(ctx));
+  SMF_CUDA(cudaMemcpyAsync(ctx->tmp_u, src_u, sizeof(double) * A.n_u, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(ctx->tmp_p, src_p, sizeof(double) * A.n_p, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(launch_vmult_stokes(ctx, A, ctx->tmp_u2, ctx->tmp_p2, ctx->tmp_u, ctx->tmp_p));
+  SMF_CUDA(cudaMemcpyAsync(dst_u, ctx->tmp_u2, sizeof(double) * A.n_u, cudaMemcpyDeviceToHost, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(dst_p, ctx->tmp_p2, sizeof(double) * A.n_p, cudaMemcpyDeviceToHost, ctx->stream));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SMF_OK;
+}
+
+int smf_compute_diagonals(smf_ctx *ctx)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  for (int l = 0; l < ctx->cfg.n_levels; ++l) {
+    LevelDev &L = ctx->levels[l];
+    if (L.n_cells == 0 || !L.has_cell_data) return ctx->fail(SMF_ERR_INVALID, "level mesh / cell data missing");
+    TRY(launch_diag(ctx, L));
+  }
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.n_cells && A.has_cell_data) TRY(launch_diag(ctx, A));
+  ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+int smf_get_inverse_diagonal(smf_ctx *ctx, int level, int which, double *host_out)
+{
+  if (!ctx || !host_out) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  LevelDev &L = ctx->lev(level);
+  if (!L.has_diag) return ctx->fail(SMF_ERR_INVALID, "diagonals not computed");
+  return smf_vec_d2h(ctx, host_out, which == 0 ? L.dinv_A : L.dinv_M, which == 0 ? L.n_u : L.n_p);
+}
+
+int smf_setup_smoothers(smf_ctx *ctx)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  const int nl = ctx->cfg.n_levels;
+  for (int l = 0; l < nl; ++l) {
+    LevelDev &L = ctx->levels[l];
+    if (!L.has_diag) return ctx->fail(SMF_ERR_INVALID, "call smf_compute_diagonals first");
+    if (l > 0 && !ctx->transfers[l].set) return ctx->fail(SMF_ERR_INVALID, "transfer missing");
+    for (int side = 0; side < 2; ++side) {
+      MGVectors &V = side == 0 ? ctx->mgv_A[l] : ctx->mgv_S[l];
+      const int64_t n = side == 0 ? L.n_u : L.n_p;
+      if (!V.x) {
+        SMF_CUDA(cudaMalloc(&V.x, sizeof(double) * n)); SMF_CUDA(cudaMalloc(&V.b, sizeof(double) * n));
+        SMF_CUDA(cudaMalloc(&V.t, sizeof(double) * n)); SMF_CUDA(cudaMalloc(&V.xo, sizeof(double) * n));
+        ctx->bytes += 4 * sizeof(double) * n;
+      }
+      Smoother &sm = side == 0 ? ctx->smoother_A[l] : ctx->smoother_S[l];
+      if (l > 0) { sm.degree = 4; sm.smoothing_range = 15.0; sm.eig_cg_n_iterations = 10; }
+      else { sm.degree = 8; sm.smoothing_range = 1e-3; sm.eig_cg_n_iterations = 100; }
+      MGSide S{side == 0, side == 0 ? &ctx->smoother_A : &ctx->smoother_S, side == 0 ? &ctx->mgv_A : &ctx->mgv_S, side == 0 ? 1 : 4};
+      TRY(estimate_eigenvalues(ctx, S, l));
+    }
+  }
+  ctx->smoothers_ready = true;
+  return SMF_OK;
+}
+
+int smf_get_eigenvalue_estimates(smf_ctx *ctx, int level, int which, double *out)
+{
+  if (!ctx || !out || level < 0 || level >= ctx->cfg.n_levels) return SMF_ERR_INVALID;
+  const Smoother &sm = which == 0 ? ctx->smoother_A[level] : ctx->smoother_S[level];
+  out[0] = sm.lambda_min; out[1] = sm.lambda_max; out[2] = sm.cg_its;
+  return SMF_OK;
+}
+
+int smf_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src)
+{ if (!ctx) return SMF_ERR_INVALID; return launch_prolongate(ctx, which, to_level, dst, src, false); }
+int smf_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src)
+{ if (!ctx) return SMF_ERR_INVALID; return launch_restrict_add(ctx, which, from_level, dst, src); }
+
+int smf_vcycle_A(smf_ctx *ctx, double *dst, const double *src) { if (!ctx) return SMF_ERR_INVALID; return vcycle(ctx, true, dst, src); }
+int smf_vcycle_S(smf_ctx *ctx, double *dst, const double *src) { if (!ctx) return SMF_ERR_INVALID; return vcycle(ctx, false, dst, src); }
+int smf_precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+{ if (!ctx) return SMF_ERR_INVALID; return precondition(ctx, dst_u, dst_p, src_u, src_p); }
+
+int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,
+              const double *rhs_u, const double *rhs_p, smf_solve_result *result)
+{
+  if (!ctx || !prm || !result) return SMF_ERR_INVALID;
+  if (prm->krylov_method != 0) return ctx->fail(SMF_ERR_UNSUPPORTED, "only GMRES is implemented for the cheap phase");
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.n_cells == 0 || !A.has_cell_data) return ctx->fail(SMF_ERR_INVALID, "active level not set");
+  std::memset(result, 0, sizeof(*result));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double t0 = now_s();
+  // the reference rebuilds the smoothers (incl. eigenvalue estimation) at the start of every solve (:768-849)
+  TRY(smf_setup_smoothers(ctx));
+  TRY(ensure_tmp(ctx));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double t1 = now_s();
+  // tolerance (:1016-1025): residual with the velocity part of the guess zeroed
+  const int64_t nu = A.n_u, np = A.n_p;
+  TRY(ensure_krylov(ctx, 2));
+  double *g = ctx->krylov[0], *r = ctx->krylov[1];
+  TRY(vec_set(ctx, g, 0.0, nu));
+  TRY(vec_copy(ctx, g + nu, sol_p, np));
+  TRY(launch_vmult_stokes(ctx, A, r, r + nu, g, g + nu));
+  TRY(vec_sadd(ctx, r, -1.0, 1.0, rhs_u, nu));
+  double ru2, rp2;
+  TRY(vec_norm2(ctx, r, nu, &ru2));
+  TRY(vec_norm2(ctx, rhs_p, np, &rp2));
+  const double tol = prm->linear_solver_tolerance * std::sqrt(ru2 + rp2);
+  result->tolerance = tol;
+  ctx->n_A_prec = ctx->n_S_prec = 0;
+  const int rc = gmres(ctx, prm, sol_u, sol_p, rhs_u, rhs_p, tol, result);
+  const double t2 = now_s();
+  result->n_A_preconditioner = ctx->n_A_prec;
+  result->n_S_preconditioner = ctx->n_S_prec;
+  result->setup_seconds = t1 - t0;
+  result->solve_seconds = t2 - t1;
+  if (rc == SMF_NO_CONVERGENCE) ctx->err = "cheap Stokes solver did not converge (SolverControl::NoConvergence)";
+  return rc;
+}
+
+int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,
+                   const double *rhs_u, const double *rhs_p, smf_solve_result *result)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t nu = A.n_u, np = A.n_p;
+  double *buf = nullptr;
+  SMF_CUDA(cudaMalloc(&buf, sizeof(double) * 2 * (nu + np)));
+  double *su = buf, *sp = buf + nu, *bu = buf + nu + np, *bp = bu + nu;
+  SMF_CUDA(cudaMemcpyAsync(su, sol_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(sp, sol_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(bu, rhs_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(bp, rhs_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = smf_solve(ctx, prm, su, sp, bu, bp, result);
+  if (rc == SMF_OK || rc == SMF_NO_CONVERGENCE) {
+    cudaMemcpyAsync(sol_u, su, sizeof(double) * nu, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(sol_p, sp, sizeof(double) * np, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(buf);
+  return rc;
+}
+
+}  // extern "C"

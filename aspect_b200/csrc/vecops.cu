@@ -1,0 +1,286 @@
+// Vector kernels for the Chebyshev smoothers and the Krylov driver (HBM-streaming, FP64).
+// They replace the LinearAlgebra::distributed::Vector operations deal.II's PreconditionChebyshev,
+// SolverCG and SolverGMRES perform between operator applications.
+#include "smf_internal.h"
+
+namespace smf {
+
+constexpr int VT = 256;                 // threads per block
+constexpr int RED_BLOCKS = 148 * 4;     // persistent reduction grid: 4 blocks per SM
+constexpr int MD_CHUNK = 100;           // max basis vectors per multi-dot pass
+
+static inline unsigned ew_blocks(int64_t n)
+{
+  int64_t b = (n + VT * 2 - 1) / (VT * 2);
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (unsigned)b;
+}
+
+#define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+__global__ void k_set(double *x, double v, int64_t n) { GRID_STRIDE(i, n) x[i] = v; }
+__global__ void k_copy(double *y, const double *x, int64_t n) { GRID_STRIDE(i, n) y[i] = x[i]; }
+__global__ void k_scale(double *x, double a, int64_t n) { GRID_STRIDE(i, n) x[i] *= a; }
+__global__ void k_axpy(double *y, double a, const double *x, int64_t n) { GRID_STRIDE(i, n) y[i] += a * x[i]; }
+__global__ void k_sadd(double *y, double s, double a, const double *x, int64_t n) { GRID_STRIDE(i, n) y[i] = s * y[i] + a * x[i]; }
+__global__ void k_pointwise(double *z, double a, const double *d, const double *x, int64_t n) { GRID_STRIDE(i, n) z[i] = a * d[i] * x[i]; }
+__global__ void k_residual(double *t, const double *b, int64_t n) { GRID_STRIDE(i, n) t[i] = b[i] - t[i]; }
+__global__ void k_cheb_first(double *x, const double *dinv, const double *b, double it, int64_t n)
+{ GRID_STRIDE(i, n) x[i] = it * dinv[i] * b[i]; }
+// xo <- (1+f1) x - f1 xo + f2 dinv (b - t)   (PreconditionChebyshev vector_updates, iteration_index >= 1)
+__global__ void k_cheb_update(double *x, double *xo, const double *dinv, const double *b, const double *t,
+                              double f1, double f2, int use_xo, int64_t n)
+{
+  GRID_STRIDE(i, n) {
+    const double xi = x[i];
+    double v = xi + f2 * dinv[i] * (b[i] - t[i]);
+    if (use_xo) v += f1 * (xi - xo[i]);
+    else v += f1 * xi;
+    xo[i] = v;
+  }
+}
+__global__ void k_gather(double *y, const double *x, const uint32_t *idx, int64_t n) { GRID_STRIDE(i, n) y[i] = x[idx[i]]; }
+__global__ void k_scatter(double *y, const double *x, const uint32_t *idx, int64_t n) { GRID_STRIDE(i, n) y[idx[i]] = x[i]; }
+__global__ void k_mod11(double *x, int64_t first, double mean, int64_t n) { GRID_STRIDE(i, n) x[i] = (double)((i + first) % 11) - mean; }
+
+#define LAUNCH_EW(kernel, n, ...)                                             \
+  do {                                                                        \
+    if ((n) > 0) {                                                            \
+      kernel<<<ew_blocks(n), VT, 0, ctx->stream>>>(__VA_ARGS__);              \
+      ctx->launches++;                                                        \
+      SMF_CUDA(cudaGetLastError());                                           \
+    }                                                                         \
+  } while (0)
+
+int vec_set(smf_ctx *ctx, double *x, double v, int64_t n) { LAUNCH_EW(k_set, n, x, v, n); return SMF_OK; }
+int vec_copy(smf_ctx *ctx, double *y, const double *x, int64_t n) { LAUNCH_EW(k_copy, n, y, x, n); return SMF_OK; }
+int vec_scale(smf_ctx *ctx, double *x, double a, int64_t n) { LAUNCH_EW(k_scale, n, x, a, n); return SMF_OK; }
+int vec_axpy(smf_ctx *ctx, double *y, double a, const double *x, int64_t n) { LAUNCH_EW(k_axpy, n, y, a, x, n); return SMF_OK; }
+int vec_sadd(smf_ctx *ctx, double *y, double s, double a, const double *x, int64_t n) { LAUNCH_EW(k_sadd, n, y, s, a, x, n); return SMF_OK; }
+int vec_pointwise(smf_ctx *ctx, double *z, double a, const double *d, const double *x, int64_t n) { LAUNCH_EW(k_pointwise, n, z, a, d, x, n); return SMF_OK; }
+int vec_residual(smf_ctx *ctx, double *t, const double *b, int64_t n) { LAUNCH_EW(k_residual, n, t, b, n); return SMF_OK; }
+int cheb_first(smf_ctx *ctx, double *x, const double *dinv, const double *b, double inv_theta, int64_t n)
+{ LAUNCH_EW(k_cheb_first, n, x, dinv, b, inv_theta, n); return SMF_OK; }
+int cheb_update(smf_ctx *ctx, double *x, double *xo, const double *dinv, const double *b, const double *t,
+                double f1, double f2, bool use_xo, int64_t n)
+{ LAUNCH_EW(k_cheb_update, n, x, xo, dinv, b, t, f1, f2, use_xo ? 1 : 0, n); return SMF_OK; }
+int vec_gather(smf_ctx *ctx, double *y, const double *x, const uint32_t *idx, int64_t n, bool scatter)
+{
+  if (scatter) LAUNCH_EW(k_scatter, n, y, x, idx, n);
+  else LAUNCH_EW(k_gather, n, y, x, idx, n);
+  return SMF_OK;
+}
+int vec_mod11(smf_ctx *ctx, double *x, int64_t first, double mean, int64_t n) { LAUNCH_EW(k_mod11, n, x, first, mean, n); return SMF_OK; }
+
+// ---- reductions: warp shuffles -> shared -> one partial per block -> last block sums in fixed order ----------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[j] = sum_i V[j][i] * w[i], j < k; out[k] = w.w.  partial[(block)*(k+1) + j] then deterministic final sum.
+__global__ void __launch_bounds__(VT) k_multi_dot(const double *const *V, int k, const double *w, int64_t n,
+                                                   double *partial, unsigned int *counter, double *out)
+{
+  __shared__ double s_acc[(MD_CHUNK + 1) * (VT / 32)];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VT / 32;
+  for (int j = threadIdx.x; j < (k + 1) * nw; j += VT) s_acc[j] = 0.0;
+  __syncthreads();
+  // each block walks chunks of 4*VT elements; w chunk stays in registers while looping over the basis
+  const int64_t chunk = 4 * VT;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
+    double wr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = base + r * VT + threadIdx.x;
+      wr[r] = i < n ? w[i] : 0.0;
+    }
+    for (int j = 0; j <= k; ++j) {
+      double a = 0.0;
+      if (j < k) {
+        const double *v = V[j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int64_t i = base + r * VT + threadIdx.x;
+          if (i < n) a += v[i] * wr[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a += wr[r] * wr[r];
+      }
+      a = warp_sum(a);
+      if (lane == 0) s_acc[j * nw + warp] += a;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j <= k; j += VT) {
+    double a = 0.0;
+    for (int q = 0; q < nw; ++q) a += s_acc[j * nw + q];
+    partial[(size_t)blockIdx.x * (k + 1) + j] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = threadIdx.x; j <= k; j += VT) {
+      double a = 0.0;
+      for (unsigned bI = 0; bI < gridDim.x; ++bI) a += partial[(size_t)bI * (k + 1) + j];
+      out[j] = a;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// w -= sum_j coef[j] V[j]; out[0] = |w_new|^2
+__global__ void __launch_bounds__(VT) k_multi_axpy(double *w, const double *const *V, const double *coef, int k, int64_t n,
+                                                    double *partial, unsigned int *counter, double *out)
+{
+  __shared__ double s_coef[MD_CHUNK];
+  __shared__ double s_acc[VT / 32];
+  __shared__ bool s_last;
+  for (int j = threadIdx.x; j < k; j += VT) s_coef[j] = coef[j];
+  __syncthreads();
+  double nrm = 0.0;
+  const int64_t chunk = 4 * VT;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
+    double wr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = base + r * VT + threadIdx.x;
+      wr[r] = i < n ? w[i] : 0.0;
+    }
+    for (int j = 0; j < k; ++j) {
+      const double *v = V[j];
+      const double cj = s_coef[j];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t i = base + r * VT + threadIdx.x;
+        if (i < n) wr[r] -= cj * v[i];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = base + r * VT + threadIdx.x;
+      if (i < n) { w[i] = wr[r]; nrm += wr[r] * wr[r]; }
+    }
+  }
+  nrm = warp_sum(nrm);
+  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = nrm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int q = 0; q < VT / 32; ++q) a += s_acc[q];
+    partial[blockIdx.x] = a;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0;
+    for (unsigned bI = 0; bI < gridDim.x; ++bI) a += partial[bI];
+    out[0] = a;
+    *counter = 0;
+  }
+}
+
+// scratch layout (doubles): [0, 128) results | [128, 128 + RED_BLOCKS*(MD_CHUNK+1)) partials | then 2 counters | device pointer table
+static int ensure_scratch(smf_ctx *ctx)
+{
+  if (ctx->scratch) return SMF_OK;
+  const int64_t n = 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1) + 16 + 256;
+  SMF_CUDA(cudaMalloc(&ctx->scratch, n * sizeof(double)));
+  SMF_CUDA(cudaMemsetAsync(ctx->scratch, 0, n * sizeof(double), ctx->stream));
+  ctx->scratch_n = n;
+  SMF_CUDA(cudaMallocHost(&ctx->host_pinned, 256 * sizeof(double)));
+  ctx->host_pinned_n = 256;
+  return SMF_OK;
+}
+static double *scr_out(smf_ctx *ctx) { return ctx->scratch; }
+static double *scr_partial(smf_ctx *ctx) { return ctx->scratch + 128; }
+static unsigned int *scr_counter(smf_ctx *ctx) { return (unsigned int *)(ctx->scratch + 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1)); }
+static double **scr_ptrs(smf_ctx *ctx) { return (double **)(ctx->scratch + 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1) + 16); }
+
+static unsigned red_blocks(int64_t n)
+{
+  int64_t b = (n + 4 * VT - 1) / (4 * VT);
+  if (b < 1) b = 1;
+  if (b > RED_BLOCKS) b = RED_BLOCKS;
+  return (unsigned)b;
+}
+
+// dots of k (<= MD_CHUNK) device vectors with w, plus w.w; host_out has k+1 entries; synchronises the stream
+int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double *w, int64_t n, double *host_out, bool sync)
+{
+  if (int e = ensure_scratch(ctx)) return e;
+  if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_dot: too many vectors");
+  if (k > 0) SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
+  k_multi_dot<<<red_blocks(n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx));
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  if (sync) {
+    SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j <= k; ++j) host_out[j] = ctx->host_pinned[j];
+  }
+  return SMF_OK;
+}
+
+// w -= sum_j h_j V_j with h = the first k results of the preceding vec_multi_dot (still on the device);
+// returns h (k entries), the pre-orthogonalisation |w|^2 (entry k) and the new |w|^2 (entry k+1) on the host.
+int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *host_out)
+{
+  // pointer table already uploaded by vec_multi_dot
+  k_multi_axpy<<<red_blocks(n), VT, 0, ctx->stream>>>(w, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (MD_CHUNK + 3), cudaMemcpyDeviceToHost, ctx->stream));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int j = 0; j <= k; ++j) host_out[j] = ctx->host_pinned[j];
+  host_out[k + 1] = ctx->host_pinned[MD_CHUNK + 2];
+  return SMF_OK;
+}
+
+// x += sum_j coef[j] V_j   (coefficients from the host)
+int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const double *coef_host, int k, int64_t n)
+{
+  if (int e = ensure_scratch(ctx)) return e;
+  if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_add: too many vectors");
+  if (k == 0) return SMF_OK;
+  for (int j = 0; j < k; ++j) ctx->host_pinned[128 + j] = -coef_host[j];
+  SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 128, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+  k_multi_axpy<<<red_blocks(n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  // the pinned staging area is reused by the next call: make sure the copies above have been consumed
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SMF_OK;
+}
+
+int vec_dot(smf_ctx *ctx, const double *x, const double *y, int64_t n, double *host_result)
+{
+  if (int e = ensure_scratch(ctx)) return e;
+  double *ptr = const_cast<double *>(x);
+  double out[2];
+  if (int e = vec_multi_dot(ctx, &ptr, 1, y, n, out, true)) return e;
+  *host_result = out[0];
+  return SMF_OK;
+}
+int vec_norm2(smf_ctx *ctx, const double *x, int64_t n, double *host_result)
+{
+  double out[1];
+  if (int e = vec_multi_dot(ctx, nullptr, 0, x, n, out, true)) return e;
+  *host_result = out[0];
+  return SMF_OK;
+}
+
+}  // namespace smf

@@ -1,0 +1,237 @@
+"""Host-side mirror of ASPECT's StokesMatrixFreeHandler over the C ABI.
+
+Same life cycle and names as the reference
+(/root/reference/include/aspect/simulator/solver/stokes_matrix_free.h:46-98 and
+ stokes_matrix_free_local_smoothing.h:211-236):
+    setup_dofs() -> assemble() [evaluate_material_model] -> build_preconditioner() -> solve()
+and the same operator objects with `vmult(dst, src)`:
+    stokes_matrix, A_block_matrix, BT_block, Schur_complement_block_matrix,
+    mg_matrices_A_block[l], mg_matrices_Schur_complement[l], prec_A, prec_Schur.
+All compute goes through aspect_b200/libsmf_b200.so; this file only marshals arrays.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, cell_data
+from ._lib import SMF_ACTIVE, SmfError, ptr
+
+
+class DeviceVector:
+    """LinearAlgebra::distributed::Vector<double> analogue: n doubles in HBM, owned by the handler's context."""
+
+    def __init__(self, handler, n):
+        self.h, self.n = handler, int(n)
+        p = ctypes.c_void_p()
+        handler._check(handler.lib.smf_vec_alloc(handler.ctx, ctypes.c_int64(self.n), ctypes.byref(p)))
+        self.ptr = p.value
+
+    def from_host(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.size == self.n
+        self.h._check(self.h.lib.smf_vec_h2d(self.h.ctx, ptr(self.ptr), ptr(a), ctypes.c_int64(self.n)))
+        self.h.synchronize()
+        return self
+
+    def to_host(self):
+        out = np.empty(self.n)
+        self.h._check(self.h.lib.smf_vec_d2h(self.h.ctx, ptr(out), ptr(self.ptr), ctypes.c_int64(self.n)))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.h.lib.smf_vec_free(self.h.ctx, ptr(self.ptr))
+            self.ptr = None
+
+
+class _Op:
+    def __init__(self, handler, fn):
+        self.h, self.fn = handler, fn
+
+    def vmult(self, dst, src):
+        self.fn(dst, src)
+
+
+class StokesMatrixFreeHandler:
+    """`Stokes solver type = block GMG`, `Stokes GMG type = local smoothing`, Q2-Q1."""
+
+    def __init__(self, dim, device=0, stokes_velocity_degree=2):
+        self.lib = _lib.load()
+        self.dim = dim
+        self.degree = stokes_velocity_degree
+        self.device = device
+        self.ctx = None
+        self.hier = None
+        self.minimum_viscosity = self.maximum_viscosity = None
+        # "Solver parameters/Stokes solver parameters" (names verbatim from source/simulator/parameters.cc:439-584)
+        self.parameters = {
+            "Linear solver tolerance": 1e-7,
+            "Number of cheap Stokes solver steps": 1000,
+            "Maximum number of expensive Stokes solver steps": 1000,
+            "GMRES solver restart length": 100,
+            "Krylov method for cheap solver steps": "GMRES",
+        }
+
+    def name(self):
+        return "GMG"
+
+    # ------------------------------------------------------------------
+    def _check(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            msg = self.lib.smf_last_error(self.ctx).decode() if self.ctx else "context creation failed (no CUDA device?)"
+            raise SmfError(rc, msg)
+        return rc
+
+    def synchronize(self):
+        self._check(self.lib.smf_synchronize(self.ctx))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.smf_set_stream(self.ctx, ctypes.c_void_p(int(cuda_stream))))
+
+    def close(self):
+        if self.ctx:
+            self.lib.smf_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def setup_dofs(self, hierarchy, boundary="zero"):
+        """hierarchy: levels[l] with n_cells, n_u, n_p, cell_dofs_u, cell_dofs_p, h, constrained_u(bc); children(l).
+        boundary: 'zero' (Zero velocity boundary indicators = all), 'tangential' (Tangential velocity ... = all)."""
+        self.close()
+        self.hier = hierarchy
+        self.boundary = boundary
+        n_levels = len(hierarchy.levels)
+        cfg = _lib.Config(self.dim, self.degree, n_levels, self.device)
+        ctx = ctypes.c_void_p()
+        rc = self.lib.smf_create(ctypes.byref(cfg), ctypes.byref(ctx))
+        if rc != 0:
+            raise SmfError(rc, "smf_create failed: a CUDA device is required (no CPU fallback)")
+        self.ctx = ctx
+        self._keep = []
+        for l in list(range(n_levels)) + [SMF_ACTIVE]:
+            L = hierarchy.levels[l] if l >= 0 else hierarchy.active
+            cu = np.ascontiguousarray(L.cell_dofs_u, dtype=np.uint32)
+            cp = np.ascontiguousarray(L.cell_dofs_p, dtype=np.uint32)
+            cons = np.ascontiguousarray(L.constrained_u(boundary), dtype=np.uint32)
+            h = np.ascontiguousarray(L.h, dtype=np.float64)
+            m = _lib.LevelMesh(L.n_cells, L.n_u, L.n_p, ptr(cu), ptr(cp), len(cons), ptr(cons), 0, ptr(None), 0, ptr(h))
+            self._check(self.lib.smf_set_level(self.ctx, l, ctypes.byref(m)))
+        for l in range(1, n_levels):
+            ch = np.ascontiguousarray(hierarchy.children(l), dtype=np.int32)
+            self._check(self.lib.smf_set_transfer(self.ctx, l, ptr(ch)))
+        self._check(self.lib.smf_set_copy_indices(self.ctx, ptr(None), ptr(None)))
+        self.n_u, self.n_p = hierarchy.active.n_u, hierarchy.active.n_p
+        self.n_levels = n_levels
+        # operator objects (duck-typed vmult like the reference's)
+        lib, c = self.lib, self._check
+        self.stokes_matrix = _Op(self, lambda d, s: c(lib.smf_vmult_stokes(self.ctx, ptr(d[0].ptr), ptr(d[1].ptr), ptr(s[0].ptr), ptr(s[1].ptr))))
+        self.A_block_matrix = _Op(self, lambda d, s: c(lib.smf_vmult_A(self.ctx, SMF_ACTIVE, ptr(d.ptr), ptr(s.ptr))))
+        self.BT_block = _Op(self, lambda d, s: c(lib.smf_vmult_BT(self.ctx, ptr(d[0].ptr), ptr(s[1].ptr))))
+        self.Schur_complement_block_matrix = _Op(self, lambda d, s: c(lib.smf_vmult_mass(self.ctx, SMF_ACTIVE, ptr(d.ptr), ptr(s.ptr))))
+        self.mg_matrices_A_block = [_Op(self, lambda d, s, l=l: c(lib.smf_vmult_A(self.ctx, l, ptr(d.ptr), ptr(s.ptr)))) for l in range(n_levels)]
+        self.mg_matrices_Schur_complement = [_Op(self, lambda d, s, l=l: c(lib.smf_vmult_mass(self.ctx, l, ptr(d.ptr), ptr(s.ptr)))) for l in range(n_levels)]
+        self.prec_A = _Op(self, lambda d, s: c(lib.smf_vcycle_A(self.ctx, ptr(d.ptr), ptr(s.ptr))))
+        self.prec_Schur = _Op(self, lambda d, s: c(lib.smf_vcycle_S(self.ctx, ptr(d.ptr), ptr(s.ptr))))
+        self.preconditioner_cheap = _Op(self, lambda d, s: c(lib.smf_precondition(self.ctx, ptr(d[0].ptr), ptr(d[1].ptr), ptr(s[0].ptr), ptr(s[1].ptr))))
+
+    def initialize_dof_vector(self, block=None, level=SMF_ACTIVE):
+        """block None -> (velocity, pressure) pair for the active level; 0 / 1 -> a single vector of that level."""
+        L = self.hier.active if level == SMF_ACTIVE else self.hier.levels[level]
+        if block is None:
+            return (DeviceVector(self, L.n_u), DeviceVector(self, L.n_p))
+        return DeviceVector(self, L.n_u if block == 0 else L.n_p)
+
+    # ------------------------------------------------------------------
+    def assemble(self, viscosity_q, material_averaging="none", pressure_scaling=1.0, is_compressible=False):
+        """evaluate_material_model(): viscosity_q = plugin output at the velocity quadrature points of the
+        active cells, (n_cells, 3^dim)."""
+        children = [None] + [self.hier.children(l) for l in range(1, self.n_levels)]
+        active, levels, self.minimum_viscosity, self.maximum_viscosity = cell_data.fill_cell_data(
+            self.dim, children, viscosity_q, material_averaging)
+        self.pressure_scaling = float(pressure_scaling)
+        self.set_cell_data(SMF_ACTIVE, active, pressure_scaling, is_compressible)
+        for l in range(self.n_levels):
+            self.set_cell_data(l, levels[l], pressure_scaling, is_compressible)
+        self.active_table, self.level_tables = active, levels
+
+    def set_cell_data(self, level, table, pressure_scaling, is_compressible=False):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        if t.ndim == 1:
+            t = t[:, None]
+        d = _lib.CellData(ptr(t), t.shape[1], float(pressure_scaling), int(is_compressible))
+        self._check(self.lib.smf_set_cell_data(self.ctx, level, ctypes.byref(d)))
+
+    def build_preconditioner(self):
+        self._check(self.lib.smf_compute_diagonals(self.ctx))
+
+    def get_matrix_diagonal_inverse(self, level, which):
+        L = self.hier.active if level == SMF_ACTIVE else self.hier.levels[level]
+        out = np.empty(L.n_u if which == 0 else L.n_p)
+        self._check(self.lib.smf_get_inverse_diagonal(self.ctx, level, which, ptr(out)))
+        return out
+
+    def setup_smoothers(self):
+        self._check(self.lib.smf_setup_smoothers(self.ctx))
+
+    def eigenvalue_estimates(self, level, which):
+        out = np.zeros(3)
+        self._check(self.lib.smf_get_eigenvalue_estimates(self.ctx, level, which, ptr(out)))
+        return out
+
+    def prolongate(self, which, to_level, dst, src):
+        self._check(self.lib.smf_prolongate(self.ctx, which, to_level, ptr(dst.ptr), ptr(src.ptr)))
+
+    def restrict_and_add(self, which, from_level, dst, src):
+        self._check(self.lib.smf_restrict_add(self.ctx, which, from_level, ptr(dst.ptr), ptr(src.ptr)))
+
+    # ------------------------------------------------------------------
+    def _params(self):
+        p = self.parameters
+        if p["Krylov method for cheap solver steps"] != "GMRES":
+            raise SmfError(_lib.SMF_ERR_UNSUPPORTED, "only GMRES is implemented for the cheap phase")
+        return _lib.SolveParams(p["Linear solver tolerance"], p["Number of cheap Stokes solver steps"],
+                                p["GMRES solver restart length"], 0)
+
+    def solve(self, system_rhs, solution_vector=None):
+        """Host-buffer solve (the reference-facing call): system_rhs = concat(f_u, f_p); solution_vector = initial
+        guess in physical units (or None).  Returns (solution, SolverOutputs-like dict).  Raises SmfError with
+        code SMF_NO_CONVERGENCE if the cheap phase fails (SolverControl::NoConvergence)."""
+        nu, np_ = self.n_u, self.n_p
+        rhs = np.ascontiguousarray(system_rhs, dtype=np.float64)
+        sol = np.zeros(nu + np_) if solution_vector is None else np.array(solution_vector, dtype=np.float64)
+        sol[nu:] /= self.pressure_scaling                      # local_smoothing.cc:975
+        su, sp = np.ascontiguousarray(sol[:nu]), np.ascontiguousarray(sol[nu:])
+        ru, rp = np.ascontiguousarray(rhs[:nu]), np.ascontiguousarray(rhs[nu:])
+        prm, res = self._params(), _lib.SolveResult()
+        rc = self.lib.smf_solve_host(self.ctx, ctypes.byref(prm), ptr(su), ptr(sp), ptr(ru), ptr(rp), ctypes.byref(res))
+        out = self._outputs(res)
+        self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
+        sp *= self.pressure_scaling                             # :1421
+        out["converged"] = rc == 0
+        return np.concatenate([su, sp]), out
+
+    def solve_device(self, sol, rhs):
+        """Device-resident solve: sol, rhs are (velocity, pressure) DeviceVector pairs (pressure already scaled)."""
+        prm, res = self._params(), _lib.SolveResult()
+        rc = self.lib.smf_solve(self.ctx, ctypes.byref(prm), ptr(sol[0].ptr), ptr(sol[1].ptr), ptr(rhs[0].ptr), ptr(rhs[1].ptr),
+                                ctypes.byref(res))
+        out = self._outputs(res)
+        self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
+        out["converged"] = rc == 0
+        return out
+
+    @staticmethod
+    def _outputs(res):
+        return {k: getattr(res, k) for k, _ in _lib.SolveResult._fields_}
+
+    def kernel_launches(self):
+        return int(self.lib.smf_kernel_launches(self.ctx))
+
+    def get_cell_data_memory_consumption(self):
+        return int(self.lib.smf_device_bytes(self.ctx))

@@ -1,0 +1,162 @@
+/* smf_b200.h -- C ABI of the B200-native matrix-free GMG Stokes path.
+ *
+ * Drop-in boundary for ASPECT's `Stokes solver type = block GMG`
+ * (StokesMatrixFreeHandler, /root/reference/include/aspect/simulator/solver/stokes_matrix_free.h:46-98).
+ * Every entry point names the reference interface it replaces (paths relative to the ASPECT tree).
+ * Plain pointers and sizes only; all functions return 0 (SMF_OK) or an error code, never abort.
+ * One context per rank/GPU, single caller thread, all calls stream-ordered.
+ *
+ * Conventions
+ *  - level = 0..n_levels-1 are multigrid levels (MGLevelObject index); level = SMF_ACTIVE (-1) is the
+ *    active mesh (the operators held in stokes_matrix / A_block_matrix / BT_block /
+ *    Schur_complement_block_matrix, stokes_matrix_free_local_smoothing.h:211-216).
+ *  - cell->DoF maps are what MatrixFree stores: lexicographic node order (x fastest),
+ *    component-major [c0: 3^dim][c1: 3^dim]..., 32-bit indices into the rank-local [owned | ghost] vector.
+ *    The library never assumes a numbering beyond "the dim components of one node are consecutive DoFs"
+ *    (true for FESystem(FE_Q(2),dim)); it verifies that and returns SMF_ERR_UNSUPPORTED otherwise.
+ *  - vectors passed to *device* entry points are device pointers to doubles (smf_vec_alloc or any CUDA
+ *    allocation on the context's device); *_host entry points take host pointers and copy.
+ *  - number type: double everywhere (GMGNumberType, stokes_matrix_free.h:40).
+ */
+#ifndef SMF_B200_H
+#define SMF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMF_OK 0
+#define SMF_ERR_INVALID 1       /* bad argument / call order                          */
+#define SMF_ERR_CUDA 2          /* CUDA runtime error (see smf_last_error)            */
+#define SMF_ERR_UNSUPPORTED 3   /* feature outside the implemented path                */
+#define SMF_NO_CONVERGENCE 4    /* solver hit its iteration limit (SolverControl::NoConvergence) */
+#define SMF_ACTIVE (-1)
+
+typedef struct smf_ctx smf_ctx;
+
+typedef struct {
+  int dim;        /* 2 or 3 */
+  int degree;     /* Stokes velocity polynomial degree; only 2 (Q2-Q1) */
+  int n_levels;   /* triangulation.n_global_levels() */
+  int device;     /* CUDA device ordinal */
+} smf_config;
+
+/* create_matrix_free_solver + constructor (source/simulator/solver/stokes_matrix_free.cc:29-62) */
+int smf_create(const smf_config *cfg, smf_ctx **out);
+void smf_destroy(smf_ctx *ctx);
+/* message of the last failing call (replaces the C++ exception text) */
+const char *smf_last_error(const smf_ctx *ctx);
+/* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
+int smf_set_stream(smf_ctx *ctx, void *cuda_stream);
+
+/* One level of setup_dofs() (stokes_matrix_free_local_smoothing.cc:1450-1851): what the per-level
+ * MatrixFree<dim,double> object holds (dof_info.dof_indices, constrained DoFs, mapping_info). */
+typedef struct {
+  int64_t n_cells;
+  int64_t n_dofs_u, n_dofs_p;        /* local vector sizes (owned + ghost) */
+  const uint32_t *cell_dofs_u;       /* [n_cells][dim*3^dim] */
+  const uint32_t *cell_dofs_p;       /* [n_cells][2^dim] */
+  int64_t n_constrained_u;           /* homogeneous constraints: Dirichlet / no-normal-flux on axis-aligned
+                                        faces / MGConstrainedDoFs boundary + refinement-edge indices */
+  const uint32_t *constrained_u;
+  int64_t n_constrained_p;
+  const uint32_t *constrained_p;
+  int geometry;                      /* 0: Cartesian, one cell size for the level (cell_size[dim]) */
+  const double *cell_size;
+} smf_level_mesh;
+int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *mesh);
+
+/* MGTransferMatrixFree::build (local_smoothing.cc:1843-1850): parent->children table of level `fine_level`
+ * ([n_cells(fine_level-1)][2^dim] cell ids on fine_level, deal.II child order). */
+int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children);
+/* copy_to_mg / copy_from_mg index map: level-(n_levels-1) DoF of every active DoF (NULL = identity). */
+int smf_set_copy_indices(smf_ctx *ctx, const uint32_t *active_to_level_u, const uint32_t *active_to_level_p);
+
+/* OperatorCellData (include/aspect/simulator/solver/matrix_free_operators.h:91-208) +
+ * set_cell_data (matrix_free_operators.cc:353-359, 779-783, 966-970): the table is COPIED to the device.
+ * viscosity is [n_cells][n_per_cell] in the cell order of smf_set_level, n_per_cell = 1 or 3^dim. */
+typedef struct {
+  const double *viscosity;
+  int n_per_cell;
+  double pressure_scaling;
+  int is_compressible;
+} smf_cell_data;
+int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *data);
+
+/* ---- device vectors ------------------------------------------------------------------------- */
+int smf_vec_alloc(smf_ctx *ctx, int64_t n, double **dev_ptr);   /* initialize_dof_vector */
+int smf_vec_free(smf_ctx *ctx, double *dev_ptr);
+int smf_vec_h2d(smf_ctx *ctx, double *dev, const double *host, int64_t n);
+int smf_vec_d2h(smf_ctx *ctx, double *host, const double *dev, int64_t n);
+int smf_synchronize(smf_ctx *ctx);
+
+/* ---- operators (device pointers) ------------------------------------------------------------ */
+/* StokesOperator::vmult (matrix_free_operators.cc:606-627, local_apply :376-547), active level */
+int smf_vmult_stokes(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+/* ABlockOperator::vmult (matrix_free_operators.cc:1056-1064, :1029-1052) */
+int smf_vmult_A(smf_ctx *ctx, int level, double *dst, const double *src);
+/* BTBlockOperator::vmult (matrix_free_operators.cc:717-725, :668-701), active level */
+int smf_vmult_BT(smf_ctx *ctx, double *dst_u, const double *src_p);
+/* MassMatrixOperator::vmult (matrix_free_operators.cc:849-857, :787-845) */
+int smf_vmult_mass(smf_ctx *ctx, int level, double *dst, const double *src);
+/* host-buffer variant of the Stokes vmult (H2D, kernel, D2H on the context's stream, then synchronise) */
+int smf_vmult_stokes_host(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+
+/* build_preconditioner(): ABlockOperator::compute_diagonal / MassMatrixOperator::compute_diagonal on every
+ * level (local_smoothing.cc:1855-1867, matrix_free_operators.cc:1068-1098, :861-908) */
+int smf_compute_diagonals(smf_ctx *ctx);
+/* get_matrix_diagonal_inverse() (local_smoothing.cc:794, :822): which = 0 (A) or 1 (mass); host output */
+int smf_get_inverse_diagonal(smf_ctx *ctx, int level, int which, double *host_out);
+
+/* PreconditionChebyshev set-up + estimate_eigenvalues on every level, both hierarchies
+ * (local_smoothing.cc:774-849).  Must follow smf_compute_diagonals. */
+int smf_setup_smoothers(smf_ctx *ctx);
+/* (lambda_min_estimate, lambda_max_estimate*1.2, cg iterations) per level; which = 0 (A) / 1 (mass) */
+int smf_get_eigenvalue_estimates(smf_ctx *ctx, int level, int which, double *min_max_its);
+
+/* MGTransfer prolongate / restrict_and_add (which = 0 velocity, 1 pressure), level vectors */
+int smf_prolongate(smf_ctx *ctx, int which, int to_level, double *dst_fine, const double *src_coarse);
+int smf_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst_coarse, const double *src_fine);
+
+/* PreconditionMG::vmult = one V-cycle (local_smoothing.cc:893-916): prec_A / prec_Schur */
+int smf_vcycle_A(smf_ctx *ctx, double *dst_u, const double *src_u);
+int smf_vcycle_S(smf_ctx *ctx, double *dst_p, const double *src_p);
+/* BlockSchurPreconditioner::vmult, cheap variant (block_stokes_preconditioner.h:220-255) */
+int smf_precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+
+/* ---- solve() ------------------------------------------------------------------------------- */
+typedef struct {
+  double linear_solver_tolerance;        /* "Linear solver tolerance" (parameters.cc:491)              */
+  int n_cheap_stokes_solver_steps;       /* "Number of cheap Stokes solver steps" (:515)               */
+  int gmres_restart_length;              /* "GMRES solver restart length" (:538)                       */
+  int krylov_method;                     /* 0 = GMRES ("Krylov method for cheap solver steps", :469)   */
+} smf_solve_params;
+
+typedef struct {
+  int iterations;                        /* outer (cheap) iterations                                   */
+  int n_A_preconditioner;                /* InverseVelocityBlock::n_iterations                         */
+  int n_S_preconditioner;                /* SchurApproximation::n_iterations                           */
+  double initial_residual;               /* outputs.initial_nonlinear_residual                         */
+  double final_residual;                 /* outputs.final_linear_residual                              */
+  double tolerance;                      /* absolute tolerance used (local_smoothing.cc:1024-1025)     */
+  double setup_seconds;                  /* smoother set-up + eigenvalue estimation (host wall clock)  */
+  double solve_seconds;                  /* Krylov iteration (host wall clock, synchronised)           */
+} smf_solve_result;
+
+/* The cheap phase of StokesMatrixFreeHandler::solve() (local_smoothing.cc:758-1313) on device vectors:
+ * rhs_{u,p}: right-hand side; sol_{u,p}: in = initial guess (pressure already divided by the pressure
+ * scaling, constrained entries zero), out = solution.  Returns SMF_OK or SMF_NO_CONVERGENCE. */
+int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,
+              const double *rhs_u, const double *rhs_p, smf_solve_result *result);
+/* same with host buffers (the reference-facing plugin call: H2D of rhs/guess, solve, D2H of the solution) */
+int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,
+                   const double *rhs_u, const double *rhs_p, smf_solve_result *result);
+
+/* bookkeeping the bench harness reports */
+int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this context so far */
+int64_t smf_device_bytes(const smf_ctx *ctx);        /* get_*_memory_consumption() analogue      */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
