@@ -38,7 +38,8 @@ def average_viscosity(eta_q, averaging):
     if op == "arithmetic average":
         a = eta_q.mean(axis=1)
     elif op == "harmonic average":
-        a = np.where((eta_q == 0.0).any(axis=1), 0.0, 1.0 / (1.0 / eta_q).mean(axis=1))
+        with np.errstate(divide="ignore"):      # a zero value makes the harmonic mean zero (interface.cc:578-585)
+            a = np.where((eta_q == 0.0).any(axis=1), 0.0, 1.0 / (1.0 / eta_q).mean(axis=1))
     elif op == "geometric average":
         a = np.prod(eta_q ** (1.0 / eta_q.shape[1]), axis=1)
     else:

@@ -142,11 +142,12 @@ void smf_destroy(smf_ctx *ctx)
     for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
   for (double *p : ctx->krylov) cudaFree(p);
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
-  cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_p); cudaFree(ctx->tmp_u2); cudaFree(ctx->tmp_p2);
+  cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_u2);   // tmp_p / tmp_p2 point into the same allocations
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
   if (ctx->graph_A) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_A);
   if (ctx->graph_S) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_S);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   delete ctx;
 }
 

@@ -258,7 +258,10 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
   const double eps = 2.220446049250313e-16;
   std::vector<double> H((size_t)(restart + 1) * restart, 0.0), gamma(restart + 1), ci(restart), si(restart), h(restart + 3), hh(restart + 3);
   int its = 0;
-  bool re_orth = false;
+  // deal.II 9.6's default (delayed classical Gram-Schmidt, DCGS2) orthogonalises twice per iteration; its
+  // numerics are those of CGS2, restated here as "always re-orthogonalise".  Single-pass CGS loses the
+  // orthogonality of the basis on badly scaled problems (SolCx, pressure scaling 1e5) and stagnates.
+  bool re_orth = true;
   int state = 0;   // 0 iterate, 1 success, 2 failure
   double rho = 0;
   bool first = true;

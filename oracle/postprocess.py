@@ -62,3 +62,10 @@ def solcx_errors(level, u, p, eta_b=1e6):
     u_l2 = np.sqrt(((eu ** 2).sum(axis=2) * JxW).sum())
     p_l2 = np.sqrt(((ep ** 2) * JxW).sum())
     return u_l1, p_l1, u_l2, p_l2
+
+
+def normalize_pressure_volume(level, p):
+    """`Pressure normalization = volume` (benchmarks/nsinker/nsinker_gmg.prm): subtract the volume mean of the
+    Q1 pressure (exact integral: cell volume times the mean of the cell's nodal values)."""
+    mean = p[level.cell_dofs_p].mean(axis=1).sum() * level.cell_volume() / float(np.prod(level.extents))
+    return p - mean, mean

@@ -1,0 +1,123 @@
+"""Pin the oracle against the reference's own golden outputs (CPU only).
+
+Goldens: /root/reference/tests/{sol_cx_2_gmg,sol_cx_4_gmg,sol_cx_4_gmg_no_avg,nsinker_gmg_gc,nsinker_gmg_no_avg}/screen-output
+(deal.II 9.6; values copied into this file, nothing is read from /root/reference at run time).
+The assembled-matrix backend is independent of any matrix-free code; the C matrix-free backend is then
+checked against it operator by operator.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import assembled, coeff, cpu, mesh, postprocess, solver
+
+HAVE_SOLCX_REF = os.path.exists(os.path.join(os.path.dirname(postprocess.__file__), "_ref", "libsolcx.so"))
+
+
+def _nsinker(R, avg, backend, n_sinkers=4):
+    hier = mesh.Hierarchy(3, R)
+    act = hier.active
+    eta_q, rho_q = coeff.nsinker(act.quadrature_points(), n_sinkers, 1e4)
+    active, levels, emin, emax = coeff.viscosity_tables(hier, eta_q, avg)
+    be = backend(hier, active, levels, 1.0, "zero")
+    f = assembled.rhs_gravity(act, rho_q, np.array([0, 0, -1.0]))
+    f[act.constrained_u("zero")] = 0
+    rhs = np.concatenate([f, np.zeros(act.n_p)])
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-6, restart=100, max_its=1000)
+    return act, emin, emax, out
+
+
+@pytest.mark.parametrize("backend", [solver.AssembledBackend, cpu.backend_from_hierarchy], ids=["assembled", "matrix_free_c"])
+def test_nsinker_gmg_goldens(backend):
+    act, emin, emax, out = _nsinker(2, "harmonic", backend)
+    assert (act.n_u, act.n_p) == (2187, 125)                               # "2,187+125"
+    assert f"{emin:.6g} - {emax:.6g}" == "0.01 - 0.198921"                 # "Viscosity range"
+    assert out["iterations"] == 21 and out["n_prec"] == 22                 # "21+0", 22 V-cycles
+    act, emin, emax, out = _nsinker(2, "none", backend)
+    assert f"{emin:.6g} - {emax:.6g}" == "0.01 - 100"
+    assert abs(out["iterations"] - 172) <= 1                               # "172+0" (+-1: App. D6)
+    assert out["n_prec"] == out["iterations"] + 2                          # 174 = 172 + one per restart cycle
+
+
+GOLD_SOLCX = {2: (162, 25, 11, "7.964441e-05, 1.174943e-01, 1.069688e-04, 1.192654e-01"),
+              4: (2178, 289, 15, "1.125999e-06, 1.101883e-01, 1.670011e-06, 1.106214e-01")}
+
+
+@pytest.mark.parametrize("R", [2, 4])
+@pytest.mark.parametrize("avg", ["harmonic", "none"])
+def test_solcx_goldens(R, avg):
+    if avg == "none" and R == 2:
+        pytest.skip("no golden for sol_cx_2 without averaging")
+    hier = mesh.Hierarchy(2, R)
+    act = hier.active
+    eta_q, rho_q = coeff.solcx(act.quadrature_points())
+    active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, avg)
+    ps = coeff.pressure_scaling_box(hier, lambda x: coeff.solcx(x)[0])
+    assert abs(ps - 1e5) < 1e-6
+    be = solver.AssembledBackend(hier, active, levels, ps, "tangential")
+    f = assembled.rhs_gravity(act, rho_q, np.array([0, -1.0]))
+    f[be.cu[-1]] = 0
+    rhs = np.concatenate([f, np.zeros(act.n_p)])
+    s = solver.BlockGMGStokes(be)
+    out = s.solve(rhs, tol_rel=1e-7, restart=100, max_its=1000)
+    nu, npp, its, errs = GOLD_SOLCX[R]
+    assert (act.n_u, act.n_p) == (nu, npp)
+    assert out["iterations"] == its and out["n_prec"] == its + 1
+    assert s.solve(rhs, x0=out["x"], tol_rel=1e-7)["iterations"] == 0      # "0+0 iterations"
+    if HAVE_SOLCX_REF:
+        p, _ = postprocess.normalize_pressure_surface(act, out["x"][act.n_u:] * ps)
+        e = postprocess.solcx_errors(act, out["x"][:act.n_u], p)
+        assert ", ".join(f"{v:.6e}" for v in e) == errs
+
+
+@pytest.mark.parametrize("dim,R,bc", [(2, 3, "tangential"), (3, 2, "zero"), (3, 2, "tangential")])
+def test_matrix_free_c_equals_assembled(dim, R, bc):
+    rng = np.random.default_rng(0)
+    hier = mesh.Hierarchy(dim, R)
+    act = hier.active
+    eta_q = np.exp(rng.uniform(-3, 3, size=(act.n_cells, 3 ** dim)))
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    for avg in ("none", "harmonic"):
+        active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, avg)
+        ab = solver.AssembledBackend(hier, active, levels, 3.7, bc)
+        cb = cpu.backend_from_hierarchy(hier, active, levels, 3.7, bc)
+        xu, xp = rng.standard_normal(act.n_u), rng.standard_normal(act.n_p)
+        yu, yp = cb.stokes(xu, xp)
+        zu, zp = ab.stokes(xu, xp)
+        errs = [rel(yu, zu), rel(yp, zp), rel(cb.BT(xp), ab.BT(xp)), rel(cb.A_active(xu), ab.A_active(xu)), rel(cb.M_active(xp), ab.M_active(xp))]
+        for l in range(hier.R + 1):
+            L = hier.levels[l]
+            x, q = rng.standard_normal(L.n_u), rng.standard_normal(L.n_p)
+            errs += [rel(cb.apply_A(l, x), ab.apply_A(l, x)), rel(cb.apply_M(l, q), ab.apply_M(l, q)),
+                     rel(cb.dinv_A(l), ab.dinv_A(l)), rel(cb.dinv_M(l), ab.dinv_M(l))]
+            if l > 0:
+                xc, qc = rng.standard_normal(hier.levels[l - 1].n_u), rng.standard_normal(hier.levels[l - 1].n_p)
+                errs += [rel(cb.prolongate_u(l, xc), ab.prolongate_u(l, xc)), rel(cb.prolongate_p(l, qc), ab.prolongate_p(l, qc)),
+                         rel(cb.restrict_u(l, x), ab.restrict_u(l, x)), rel(cb.restrict_p(l, q), ab.restrict_p(l, q))]
+        assert max(errs) < 1e-13
+
+
+def test_operator_properties():
+    """Size-independent properties: symmetry of A and M, B^T adjoint to the pressure rows of the Stokes operator,
+    restriction = transpose of prolongation, prolongation reproduces Q2/Q1 functions."""
+    rng = np.random.default_rng(1)
+    hier = mesh.Hierarchy(3, 2)
+    act = hier.active
+    eta_q = np.exp(rng.uniform(-3, 3, size=(act.n_cells, 27)))
+    active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, "none")
+    cb = cpu.backend_from_hierarchy(hier, active, levels, 2.0, "zero")
+    x, y = rng.standard_normal(act.n_u), rng.standard_normal(act.n_u)
+    assert abs(y @ cb.A_active(x) - x @ cb.A_active(y)) < 1e-10 * abs(y @ cb.A_active(x))
+    p, q = rng.standard_normal(act.n_p), rng.standard_normal(act.n_p)
+    assert abs(q @ cb.M_active(p) - p @ cb.M_active(q)) < 1e-12 * abs(q @ cb.M_active(p))
+    xz = x.copy(); xz[act.constrained_u("zero")] = 0
+    _, bp = cb.stokes(xz, np.zeros(act.n_p))
+    assert abs(p @ bp - xz @ cb.BT(p)) < 1e-10 * abs(p @ bp)
+    xc = rng.standard_normal(hier.levels[1].n_u)
+    assert abs(x @ cb.prolongate_u(2, xc) - xc @ cb.restrict_u(2, x)) < 1e-12 * np.linalg.norm(x) * np.linalg.norm(xc)
+    # a Q2 function on the coarse level is reproduced exactly on the fine level (no constraints)
+    cb0 = cpu.backend_from_hierarchy(hier, active, levels, 2.0, "none")
+    fc = lambda X: X[:, 0] ** 2 - 0.5 * X[:, 1] * X[:, 2] + X[:, 2] ** 2
+    uc = fc(hier.levels[1].dof_coords_u())
+    assert np.abs(cb0.prolongate_u(2, uc) - fc(hier.levels[2].dof_coords_u())).max() < 1e-14
