@@ -607,7 +607,11 @@ template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &
     SMF_CUDA(cudaFuncSetAttribute(velocity_kernel<DIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  velocity_kernel<DIM, MODE><<<L.n_batches, 32 * DIM, smem, ctx->stream>>>(P);
+  const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
+  {
+    ProfScope prof(ctx, MODE == 1 ? B_STOKES : (MODE == 2 ? B_BT : (fine ? B_A_FINE : B_A_COARSE)));
+    velocity_kernel<DIM, MODE><<<L.n_batches, 32 * DIM, smem, ctx->stream>>>(P);
+  }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;
@@ -654,6 +658,7 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
   P.src_p = src; P.dst_p = dst;
   SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
   const size_t smem = (size_t)(1 + KSUB) * L.max_nodes_p * sizeof(double);
+  ProfScope prof(ctx, B_MASS);
   if (L.dim == 3) mass_kernel<3><<<L.n_batches, BATCH_CELLS, smem, ctx->stream>>>(P);
   else mass_kernel<2><<<L.n_batches, BATCH_CELLS, smem, ctx->stream>>>(P);
   ctx->launches++;
@@ -702,6 +707,7 @@ static void launch_transfer_t(smf_ctx *ctx, const TransferParams &P, bool prolon
   constexpr int NPATCH = DIM == 3 ? NPP * NPP * NPP : NPP * NPP;
   constexpr int NC = DIM == 3 ? NPD * NPD * NPD : NPD * NPD;
   const int bs = 128;
+  ProfScope prof(ctx, B_TRANSFER);
   if (prolong) {
     const int64_t nt = P.n_parents * NPATCH;
     prolongate_kernel<DIM, NPD, NCOMP><<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(P);

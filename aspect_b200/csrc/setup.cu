@@ -142,8 +142,11 @@ void smf_destroy(smf_ctx *ctx)
     for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
   for (double *p : ctx->krylov) cudaFree(p);
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
+  cudaFree(ctx->io_buf);
   cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_u2);   // tmp_p / tmp_p2 point into the same allocations
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+  for (auto &e : ctx->prof_live) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->graph_A) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_A);
   if (ctx->graph_S) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_S);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -393,6 +396,11 @@ int smf_vec_d2h(smf_ctx *ctx, double *host, const double *dev, int64_t n)
   SMF_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   return SMF_OK;
+}
+int smf_vec_set(smf_ctx *ctx, double *dev, double value, int64_t n)
+{
+  if (!ctx || (!dev && n > 0)) return SMF_ERR_INVALID;
+  return smf::vec_set(ctx, dev, value, n);
 }
 int smf_synchronize(smf_ctx *ctx)
 {

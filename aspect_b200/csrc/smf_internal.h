@@ -57,6 +57,10 @@ struct Smoother {                 // PreconditionChebyshev state of one level
   int cg_its = 0;
 };
 
+// device-time buckets of the optional profiler (smf_profile_*): the split SURVEY.md 8(d) asks for
+enum Bucket { B_STOKES = 0, B_A_FINE, B_A_COARSE, B_MASS, B_BT, B_TRANSFER, B_SMOOTH_VEC, B_ORTHO, B_VEC, B_COUNT };
+struct ProfEvent { int bucket; cudaEvent_t a, b; };
+
 struct MGVectors {                // per level: solution, defect, t, and a Chebyshev scratch
   double *x = nullptr, *b = nullptr, *t = nullptr, *xo = nullptr;
 };
@@ -81,8 +85,16 @@ struct smf_ctx {
   // Krylov workspace
   std::vector<double *> krylov; int64_t krylov_n = 0;
   double *tmp_u = nullptr, *tmp_p = nullptr, *tmp_u2 = nullptr, *tmp_p2 = nullptr;
+  double *io_buf = nullptr; int64_t io_n = 0;         // device staging of smf_solve_host
   int n_A_prec = 0, n_S_prec = 0;
   void *graph_A = nullptr, *graph_S = nullptr;        // cudaGraphExec_t of the V-cycles (with fixed in/out buffers)
+  // profiler: 0 off, 1 operator kernels of the finest level only, 2 every launch
+  int prof_mode = 0;
+  int vec_bucket = smf::B_VEC;                        // bucket the vector kernels are booked under right now
+  std::vector<smf::ProfEvent> prof_live;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[smf::B_COUNT] = {0};
+  int64_t prof_cnt[smf::B_COUNT] = {0};
 
   smf::LevelDev &lev(int level) { return levels[level < 0 ? cfg.n_levels : level]; }
   int fail(int code, const std::string &msg) { err = msg; return code; }
@@ -96,6 +108,28 @@ struct smf_ctx {
   } while (0)
 
 namespace smf {
+// RAII pair of CUDA events around one launch on the context's stream (no-op unless profiling is on)
+struct ProfScope {
+  smf_ctx *ctx; cudaEvent_t b = nullptr;
+  ProfScope(smf_ctx *c, int bucket) : ctx(c)
+  {
+    if (c->prof_mode == 0 || (c->prof_mode == 1 && bucket != B_STOKES && bucket != B_A_FINE)) return;
+    cudaEvent_t a;
+    auto get = [&](cudaEvent_t &e) {
+      if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+      else cudaEventCreate(&e);
+    };
+    get(a); get(b);
+    cudaEventRecord(a, c->stream);
+    c->prof_live.push_back({bucket, a, b});
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, ctx->stream); }
+};
+struct VecBucket {      // books the vector kernels launched in this scope under `bucket`
+  smf_ctx *ctx; int saved;
+  VecBucket(smf_ctx *c, int bucket) : ctx(c), saved(c->vec_bucket) { c->vec_bucket = bucket; }
+  ~VecBucket() { ctx->vec_bucket = saved; }
+};
 // operators.cu
 int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);
 int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p);

@@ -159,6 +159,7 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
 {
   MGVectors &V = (*S.v)[l];
   const int which = S.velocity ? 0 : 1;
+  VecBucket vb(ctx, B_SMOOTH_VEC);
   double *x = V.x, *xo = V.xo;
   // pre-smoothing: SmootherRelaxation::apply = vmult + (steps-1) x step; on level 0 this is the coarse solver
   TRY(cheb_vmult(ctx, S, l, x, xo, V.b, V.t));
@@ -288,6 +289,7 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
       TRY(launch_vmult_stokes(ctx, A, vv, vv + nu, p, p + nu));
       dim = j + 1;
       const bool consider = !re_orth && (its % 5 == 0);
+      VecBucket vb(ctx, B_ORTHO);
       TRY(vec_multi_dot(ctx, K.data(), dim, vv, n, nullptr, false));
       TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, h.data()));   // h[0..dim-1], |vv_old|^2, |vv_new|^2
       const double norm_start = std::sqrt(h[dim]);
@@ -436,6 +438,32 @@ int smf_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const dou
 int smf_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src)
 { if (!ctx) return SMF_ERR_INVALID; return launch_restrict_add(ctx, which, from_level, dst, src); }
 
+int smf_profile_enable(smf_ctx *ctx, int mode)
+{
+  if (!ctx || mode < 0 || mode > 2) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &e : ctx->prof_live) { ctx->prof_pool.push_back(e.a); ctx->prof_pool.push_back(e.b); }
+  ctx->prof_live.clear();
+  for (int b = 0; b < B_COUNT; ++b) { ctx->prof_ms[b] = 0.0; ctx->prof_cnt[b] = 0; }
+  ctx->prof_mode = mode;
+  return SMF_OK;
+}
+
+int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out)
+{
+  if (!ctx || !ms_out || !count_out) return SMF_ERR_INVALID;
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &e : ctx->prof_live) {
+    float ms = 0.f;
+    SMF_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+    ctx->prof_ms[e.bucket] += ms; ctx->prof_cnt[e.bucket]++;
+    ctx->prof_pool.push_back(e.a); ctx->prof_pool.push_back(e.b);
+  }
+  ctx->prof_live.clear();
+  for (int b = 0; b < B_COUNT; ++b) { ms_out[b] = ctx->prof_ms[b]; count_out[b] = ctx->prof_cnt[b]; }
+  return SMF_OK;
+}
+
 int smf_vcycle_A(smf_ctx *ctx, double *dst, const double *src) { if (!ctx) return SMF_ERR_INVALID; return vcycle(ctx, true, dst, src); }
 int smf_vcycle_S(smf_ctx *ctx, double *dst, const double *src) { if (!ctx) return SMF_ERR_INVALID; return vcycle(ctx, false, dst, src); }
 int smf_precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
@@ -486,8 +514,13 @@ int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, dou
   if (!ctx) return SMF_ERR_INVALID;
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   const int64_t nu = A.n_u, np = A.n_p;
-  double *buf = nullptr;
-  SMF_CUDA(cudaMalloc(&buf, sizeof(double) * 2 * (nu + np)));
+  if (ctx->io_n != 2 * (nu + np)) {      // persistent staging of the host-facing vectors (a17: the H2D/D2H point)
+    cudaFree(ctx->io_buf); ctx->io_buf = nullptr; ctx->io_n = 0;
+    SMF_CUDA(cudaMalloc(&ctx->io_buf, sizeof(double) * 2 * (nu + np)));
+    ctx->io_n = 2 * (nu + np);
+    ctx->bytes += sizeof(double) * 2 * (nu + np);
+  }
+  double *buf = ctx->io_buf;
   double *su = buf, *sp = buf + nu, *bu = buf + nu + np, *bp = bu + nu;
   SMF_CUDA(cudaMemcpyAsync(su, sol_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
   SMF_CUDA(cudaMemcpyAsync(sp, sol_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
@@ -499,7 +532,6 @@ int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, dou
     cudaMemcpyAsync(sol_p, sp, sizeof(double) * np, cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(buf);
   return rc;
 }
 

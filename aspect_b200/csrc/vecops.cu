@@ -47,6 +47,7 @@ __global__ void k_mod11(double *x, int64_t first, double mean, int64_t n) { GRID
 #define LAUNCH_EW(kernel, n, ...)                                             \
   do {                                                                        \
     if ((n) > 0) {                                                            \
+      ProfScope prof__(ctx, ctx->vec_bucket);                                 \
       kernel<<<ew_blocks(n), VT, 0, ctx->stream>>>(__VA_ARGS__);              \
       ctx->launches++;                                                        \
       SMF_CUDA(cudaGetLastError());                                           \
@@ -221,7 +222,8 @@ int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double 
   if (int e = ensure_scratch(ctx)) return e;
   if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_dot: too many vectors");
   if (k > 0) SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
-  k_multi_dot<<<red_blocks(n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx));
+  { ProfScope prof(ctx, ctx->vec_bucket);
+  k_multi_dot<<<red_blocks(n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx)); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   if (sync) {
@@ -237,8 +239,9 @@ int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double 
 int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *host_out)
 {
   // pointer table already uploaded by vec_multi_dot
+  { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(n), VT, 0, ctx->stream>>>(w, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
-                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2);
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (MD_CHUNK + 3), cudaMemcpyDeviceToHost, ctx->stream));
@@ -257,8 +260,9 @@ int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const dou
   for (int j = 0; j < k; ++j) ctx->host_pinned[128 + j] = -coef_host[j];
   SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
   SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 128, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+  { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
-                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2);
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   // the pinned staging area is reused by the next call: make sure the copies above have been consumed

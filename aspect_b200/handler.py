@@ -33,6 +33,10 @@ class DeviceVector:
         self.h.synchronize()
         return self
 
+    def zero(self):
+        self.h._check(self.h.lib.smf_vec_set(self.h.ctx, ptr(self.ptr), ctypes.c_double(0.0), ctypes.c_int64(self.n)))
+        return self
+
     def to_host(self):
         out = np.empty(self.n)
         self.h._check(self.h.lib.smf_vec_d2h(self.h.ctx, ptr(out), ptr(self.ptr), ctypes.c_int64(self.n)))
@@ -198,23 +202,30 @@ class StokesMatrixFreeHandler:
         return _lib.SolveParams(p["Linear solver tolerance"], p["Number of cheap Stokes solver steps"],
                                 p["GMRES solver restart length"], 0)
 
-    def solve(self, system_rhs, solution_vector=None):
+    def solve(self, system_rhs, solution_vector=None, out=None):
         """Host-buffer solve (the reference-facing call): system_rhs = concat(f_u, f_p); solution_vector = initial
         guess in physical units (or None).  Returns (solution, SolverOutputs-like dict).  Raises SmfError with
-        code SMF_NO_CONVERGENCE if the cheap phase fails (SolverControl::NoConvergence)."""
+        code SMF_NO_CONVERGENCE if the cheap phase fails (SolverControl::NoConvergence).
+        `out`: optional float64 array of n_u + n_p (e.g. pinned memory) that receives the solution in place."""
         nu, np_ = self.n_u, self.n_p
         rhs = np.ascontiguousarray(system_rhs, dtype=np.float64)
-        sol = np.zeros(nu + np_) if solution_vector is None else np.array(solution_vector, dtype=np.float64)
-        sol[nu:] /= self.pressure_scaling                      # local_smoothing.cc:975
+        if out is not None:
+            sol = out
+            sol[:] = 0.0 if solution_vector is None else solution_vector
+        else:
+            sol = np.zeros(nu + np_) if solution_vector is None else np.array(solution_vector, dtype=np.float64)
+        if self.pressure_scaling != 1.0:
+            sol[nu:] /= self.pressure_scaling                  # local_smoothing.cc:975
         su, sp = np.ascontiguousarray(sol[:nu]), np.ascontiguousarray(sol[nu:])
         ru, rp = np.ascontiguousarray(rhs[:nu]), np.ascontiguousarray(rhs[nu:])
         prm, res = self._params(), _lib.SolveResult()
         rc = self.lib.smf_solve_host(self.ctx, ctypes.byref(prm), ptr(su), ptr(sp), ptr(ru), ptr(rp), ctypes.byref(res))
         out = self._outputs(res)
         self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
-        sp *= self.pressure_scaling                             # :1421
+        if self.pressure_scaling != 1.0:
+            sp *= self.pressure_scaling                         # :1421
         out["converged"] = rc == 0
-        return np.concatenate([su, sp]), out
+        return sol, out
 
     def solve_device(self, sol, rhs):
         """Device-resident solve: sol, rhs are (velocity, pressure) DeviceVector pairs (pressure already scaled)."""
@@ -229,6 +240,18 @@ class StokesMatrixFreeHandler:
     @staticmethod
     def _outputs(res):
         return {k: getattr(res, k) for k, _ in _lib.SolveResult._fields_}
+
+    PROFILE_BUCKETS = ("stokes_vmult", "A_fine", "A_coarse", "mass", "BT", "transfer", "chebyshev_vec", "gmres_ortho", "other_vec")
+
+    def profile_enable(self, mode):
+        """'Execute solver timings' analogue: 0 off, 1 finest-level operator kernels, 2 every launch."""
+        self._check(self.lib.smf_profile_enable(self.ctx, int(mode)))
+
+    def profile_read(self):
+        ms = np.zeros(len(self.PROFILE_BUCKETS))
+        cnt = np.zeros(len(self.PROFILE_BUCKETS), dtype=np.int64)
+        self._check(self.lib.smf_profile_read(self.ctx, ptr(ms), ptr(cnt)))
+        return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_BUCKETS, ms, cnt)}
 
     def kernel_launches(self):
         return int(self.lib.smf_kernel_launches(self.ctx))

@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native block-GMG Stokes path (BASELINE.json metric:
+"Stokes vmult GDoF/s + nsinker block-GMG Stokes solve wall-time, 1/2/4/8 B200").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference algorithm
+
+One JSON line on stdout (rank 0).  A "step" is ONE complete block-GMG Stokes solve (StokesMatrixFreeHandler::
+solve(), /root/reference/source/simulator/solver/stokes_matrix_free_local_smoothing.cc:758-1313: Chebyshev set-up
++ eigenvalue estimation + tolerance + right-preconditioned GMRES(100) to 1e-6) of the synthetic nsinker problem
+(benchmarks/nsinker/nsinker_gmg.prm: 8 sinkers, viscosity ratio 1e4, harmonic averaging, no-slip box).
+
+  value        solve throughput = (N_u + N_p) / wall time of one solve, vectors resident in HBM        [MDoF/s]
+  e2e          the same through the reference-facing host call (StokesMatrixFreeHandler.solve -> smf_solve_host):
+               right-hand side and initial guess copied from pinned host memory, solution copied back, every step
+  vmult        Stokes / A-block operator throughput in GDoF/s (CUDA events, 20 launches, vectors >> L2)
+  roofline     finest-level A-block kernel (the dominant kernel of the solve) against the measured HBM peak
+  cpu_baseline the oracle (CPU restatement, OpenMP) on the host cores, complete solve at a smaller refinement
+
+Everything under oracle/ is used here only by the cpu_baseline leg and the --impl reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SINKERS, VISCOSITY_RATIO, AVERAGING = 8, 1e4, "harmonic average"
+TOL, RESTART, CHEAP_STEPS = 1e-6, 100, 200          # nsinker_gmg.prm
+METRIC = "nsinker_block_gmg_stokes_solve_throughput"
+UNIT = "MDoF/s"
+
+
+def workload_name(R):
+    return (f"nsinker 3D box, {N_SINKERS} sinkers, viscosity ratio 1e4, harmonic average, Q2-Q1, block GMG "
+            f"(GMRES({RESTART}), tol {TOL:g}), global refinement {R}")
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_solve_throughput(R, steps, warmup, budget_s=240.0):
+    """Complete block-GMG solves with the oracle (C cell kernels + OpenMP, numpy driver) on the host cores."""
+    from oracle import coeff, cpu, mesh as omesh, solver as osolver
+    from aspect_b200 import benchmarks, synthetic
+    hier = synthetic.BoxHierarchy(3, R)
+    eta_q, rhs, ps = benchmarks.nsinker_problem(hier, N_SINKERS, VISCOSITY_RATIO, AVERAGING)
+    ohier = omesh.Hierarchy(3, R)
+    active, levels, _, _ = coeff.viscosity_tables(ohier, eta_q, "harmonic")
+    ob = cpu.backend_from_hierarchy(ohier, active, levels, ps, "zero")
+    n = hier.active.n_u + hier.active.n_p
+    times, its = [], None
+    t_all = time.time()
+    for i in range(warmup + steps):
+        s = osolver.BlockGMGStokes(ob)       # rebuilt every solve, like the reference (eigenvalue estimation inside)
+        t0 = time.time()
+        out = s.solve(rhs, tol_rel=TOL, restart=RESTART, max_its=CHEAP_STEPS)
+        dt = time.time() - t0
+        its = out["iterations"]
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_all > budget_s and times:
+            break
+    t = float(np.mean(times))
+    return {"value": n / t / 1e6, "unit": UNIT, "cores": int(cpu.lib().smf_cpu_num_threads()), "kind": "port",
+            "sample": f"{len(times)} complete solve(s) of the same benchmark at global refinement {R} "
+                      f"({n} DoFs, {its} outer iterations, {t:.2f} s each); throughput in DoFs per solve-second",
+            "wall_s": t, "iterations": its, "dofs": n}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; deal.II/ASPECT cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R = args.ref_refinement
+    warm = min(args.warmup, 1)
+    res = cpu_solve_throughput(R, args.steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": res["wall_s"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.refinement), "parallelism": "host cores (OpenMP)"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "solve_wall_s": res["wall_s"], "iterations": res["iterations"]}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[0]) for r in rows]
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][1])
+        out["power_w_max"] = max(float(r[2]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for j, n in enumerate(names) if any(r[3 + j].strip().lower().startswith("active") for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+def build_problem(R, device):
+    from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
+    hier = synthetic.BoxHierarchy(3, R)
+    eta_q, rhs, ps = benchmarks.nsinker_problem(hier, N_SINKERS, VISCOSITY_RATIO, AVERAGING)
+    h = StokesMatrixFreeHandler(3, device=device)
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, AVERAGING, ps)
+    h.build_preconditioner()
+    h.parameters.update({"Linear solver tolerance": TOL, "Number of cheap Stokes solver steps": CHEAP_STEPS,
+                         "GMRES solver restart length": RESTART})
+    del eta_q
+    return hier, h, rhs
+
+
+def timed_solves(torch, h, stream, rhs_dev, sol_dev, n_u, n_p, steps, barrier):
+    """K device-resident solves from a zero guess; CUDA events on the launching stream, barrier + sync both sides."""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    outs = []
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(steps):
+        sol_dev[0].zero(); sol_dev[1].zero()
+        outs.append(h.solve_device(sol_dev, rhs_dev))
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    return ev0.elapsed_time(ev1) / 1e3, outs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--refinement", type=int, default=int(os.environ.get("SMF_BENCH_REFINEMENT", "7")),
+                    help="global refinement per GPU (7 = north-star single-GPU target; 8 GPUs x 7 = BASELINE cfg 5)")
+    ap.add_argument("--ref-refinement", type=int, default=4, help="refinement of the CPU sample (complete solves)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg2", action="store_true", help="skip the extra BASELINE cfg 2 (refinement 5) solve")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the block-GMG path has no CPU fallback (use --impl reference for the CPU arm)")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sync_t = torch.zeros(1, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.all_reduce(sync_t)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from aspect_b200 import SMF_ACTIVE
+    R = args.refinement
+    t_setup = time.time()
+    hier, h, rhs = build_problem(R, local_rank)
+    stream = torch.cuda.Stream()
+    h.set_stream(stream.cuda_stream)
+    n_u, n_p, n_cells = hier.active.n_u, hier.active.n_p, hier.active.n_cells
+    n = n_u + n_p
+    setup_s = time.time() - t_setup
+
+    rhs_dev, sol_dev = h.initialize_dof_vector(), h.initialize_dof_vector()
+    rhs_dev[0].from_host(rhs[:n_u]); rhs_dev[1].from_host(rhs[n_u:])
+    # pinned host buffers of the end-to-end arm
+    rhs_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    sol_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    rhs_pin.numpy()[:] = rhs
+    del rhs
+
+    with torch.cuda.stream(stream):
+        # ---- warm-up, then the timed device-resident solves --------------------------------------------------
+        for _ in range(max(args.warmup, 3)):
+            sol_dev[0].zero(); sol_dev[1].zero()
+            h.solve_device(sol_dev, rhs_dev)
+        h.profile_enable(1)
+        launches0 = h.kernel_launches()
+        clocks = ClockSampler(local_rank)
+        t_dev, outs = timed_solves(torch, h, stream, rhs_dev, sol_dev, n_u, n_p, args.steps, barrier)
+        clock_info = clocks.stop()
+        launches = h.kernel_launches() - launches0
+        prof = h.profile_read()
+        h.profile_enable(0)
+        t_dev = max_over_ranks(t_dev)
+        # ---- the same through the host-facing call ----------------------------------------------------------
+        sol_np, rhs_np = sol_pin.numpy(), rhs_pin.numpy()
+        for _ in range(1):
+            h.solve(rhs_np, None, out=sol_np)
+        barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            _, out_e2e = h.solve(rhs_np, None, out=sol_np)
+        ev1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        t_e2e = max_over_ranks(max(ev0.elapsed_time(ev1) / 1e3, time.time() - t0))
+        # ---- bucket split of one more solve (every launch bracketed by events; not part of the timed region) --
+        h.profile_enable(2)
+        sol_dev[0].zero(); sol_dev[1].zero()
+        h.solve_device(sol_dev, rhs_dev)
+        split = h.profile_read()
+        h.profile_enable(0)
+        # ---- operator throughput --------------------------------------------------------------------------
+        src, dst = h.initialize_dof_vector(), h.initialize_dof_vector()
+        rng = np.random.default_rng(0)
+        xu = rng.uniform(-1, 1, n_u); xu[hier.active.constrained_u("zero").astype(np.int64)] = 0.0
+        src[0].from_host(xu); src[1].from_host(rng.uniform(-1, 1, n_p))
+        del xu
+
+        def time_op(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return max_over_ranks(a.elapsed_time(b) / 1e3 / reps)
+
+        t_stokes = time_op(lambda: h.stokes_matrix.vmult(dst, src))
+        t_A = time_op(lambda: h.A_block_matrix.vmult(dst[0], src[0]))
+        t_M = time_op(lambda: h.Schur_complement_block_matrix.vmult(dst[1], src[1]))
+        h.profile_enable(1)
+        for _ in range(20):
+            h.stokes_matrix.vmult(dst, src)
+        pk = h.profile_read()
+        h.profile_enable(0)
+        t_stokes_kernel = pk["stokes_vmult"][0] / 1e3 / max(pk["stokes_vmult"][1], 1)
+        # host-buffer Stokes vmult (smf_vmult_stokes_host): PCIe-bound, reported for completeness
+        dst_pin = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        from aspect_b200._lib import ptr
+        def host_vmult():
+            h._check(h.lib.smf_vmult_stokes_host(h.ctx, ptr(dst_pin[:n_u]), ptr(dst_pin[n_u:]), ptr(rhs_np[:n_u]), ptr(rhs_np[n_u:])))
+        host_vmult()
+        t0 = time.time()
+        for _ in range(3):
+            host_vmult()
+        t_stokes_host = max_over_ranks((time.time() - t0) / 3)
+
+    its = outs[-1]["iterations"]
+    wall = t_dev / args.steps
+    wall_e2e = t_e2e / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    # algorithmic bytes: A-block = 16 N_u + 8 N_cell n_eta (level tables: 1 value per cell)
+    bytes_A = 16.0 * n_u + 8.0 * n_cells
+    bytes_stokes = 16.0 * n + 8.0 * n_cells
+    a_ms, a_cnt = prof["A_fine"]
+    t_A_kernel = a_ms / 1e3 / max(a_cnt, 1)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"A_fine_R{R}")
+    except (OSError, ValueError):
+        pass
+    line = {
+        "metric": METRIC, "value": world * n / wall / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(R), "dofs_per_gpu": n, "cells_per_gpu": n_cells, "levels": R + 1,
+                   "parallelism": "1 subdomain per GPU" if world == 1 else f"{world} independent replicas (no exchange yet)",
+                   "l2": "vectors (%.0f MB each) exceed the 126 MB L2" % (8e-6 * n) if 8 * n > 126e6 else "vectors fit L2: each solve streams >100 distinct vectors between reuses",
+                   "impl": "b200"},
+        "solve_wall_s": wall, "iterations": its,
+        "n_A_preconditioner": outs[-1]["n_A_preconditioner"], "n_S_preconditioner": outs[-1]["n_S_preconditioner"],
+        "solve_setup_s": outs[-1]["setup_seconds"], "final_residual_over_tol": outs[-1]["final_residual"] / outs[-1]["tolerance"],
+        "e2e": {"value": world * n / wall_e2e / 1e6, "unit": UNIT, "wall_s": wall_e2e,
+                "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
+                "call": "StokesMatrixFreeHandler.solve -> smf_solve_host (pinned host rhs + guess in, solution out)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "velocity_kernel<3,0> (A block, finest level)", "achieved": bytes_A / t_A_kernel / 1e9,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes_A / t_A_kernel / 1e9 / peak,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": bytes_A, "launches_timed": a_cnt,
+                     "avg_launch_us": t_A_kernel * 1e6, "share_of_solve": a_ms / 1e3 / t_dev},
+        "vmult": {"stokes_gdofs": world * n / t_stokes / 1e9, "stokes_kernel_gdofs": world * n / t_stokes_kernel / 1e9,
+                  "stokes_roofline_frac": bytes_stokes / t_stokes_kernel / 1e9 / peak,
+                  "A_gdofs": world * n_u / t_A / 1e9, "mass_gdofs": world * n_p / t_M / 1e9,
+                  "stokes_host_buffers_gdofs": world * n / t_stokes_host / 1e9,
+                  "note": "stokes_gdofs includes zeroing dst (StokesOperator::vmult); *_kernel_* is the cell kernel alone"},
+        "time_split_ms": {k: round(v[0], 3) for k, v in split.items()},
+        "launch_split": {k: v[1] for k, v in split.items()},
+        "clocks": clock_info, "host_setup_s": setup_s,
+    }
+    h.close()
+    # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------
+    if not args.no_cfg2 and R != 5:
+        hier5, h5, rhs5 = build_problem(5, local_rank)
+        n5 = hier5.active.n_u + hier5.active.n_p
+        pin5 = torch.empty(n5, dtype=torch.float64).pin_memory().numpy()
+        rp5 = torch.empty(n5, dtype=torch.float64).pin_memory().numpy(); rp5[:] = rhs5
+        for _ in range(2):
+            _, o5 = h5.solve(rp5, None, out=pin5)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(3):
+            _, o5 = h5.solve(rp5, None, out=pin5)
+        t5 = (time.time() - t0) / 3
+        line["cfg2_refinement5"] = {"workload": workload_name(5), "dofs": n5, "e2e_wall_s": t5, "e2e_mdofs": n5 / t5 / 1e6,
+                                    "iterations": o5["iterations"]}
+        h5.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_solve_throughput(args.ref_refinement, 1, 0).items()
+                                if k in ("value", "unit", "cores", "kind", "sample")}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

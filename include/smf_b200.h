@@ -88,6 +88,7 @@ int smf_vec_alloc(smf_ctx *ctx, int64_t n, double **dev_ptr);   /* initialize_do
 int smf_vec_free(smf_ctx *ctx, double *dev_ptr);
 int smf_vec_h2d(smf_ctx *ctx, double *dev, const double *host, int64_t n);
 int smf_vec_d2h(smf_ctx *ctx, double *host, const double *dev, int64_t n);
+int smf_vec_set(smf_ctx *ctx, double *dev, double value, int64_t n);   /* Vector::operator=(value) */
 int smf_synchronize(smf_ctx *ctx);
 
 /* ---- operators (device pointers) ------------------------------------------------------------ */
@@ -151,6 +152,16 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
 /* same with host buffers (the reference-facing plugin call: H2D of rhs/guess, solve, D2H of the solution) */
 int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,
                    const double *rhs_u, const double *rhs_p, smf_solve_result *result);
+
+/* Device-time profiler: the reference's "Execute solver timings" switch (local_smoothing.cc:60-65, :1119-1260)
+ * and TimerOutput sections, done with CUDA event pairs on the context's stream around every launch.
+ * mode 0 = off, 1 = operator kernels of the finest level only (Stokes, A), 2 = every launch.
+ * smf_profile_read synchronises and returns accumulated milliseconds and launch counts per bucket:
+ * 0 Stokes vmult, 1 A finest level, 2 A coarser levels, 3 pressure mass, 4 B^T, 5 MG transfer,
+ * 6 Chebyshev vector updates, 7 GMRES orthogonalisation, 8 other vector kernels. */
+#define SMF_PROFILE_BUCKETS 9
+int smf_profile_enable(smf_ctx *ctx, int mode);
+int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out);
 
 /* bookkeeping the bench harness reports */
 int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this context so far */
