@@ -13,6 +13,7 @@
 // dim warps of the block.  Results are accumulated in the shared staging area in collision-free rounds and
 // flushed once per batch: nodes private to the batch with plain stores, shared nodes with one RED each.
 #include "smf_internal.h"
+#include <type_traits>
 
 namespace smf {
 
@@ -184,181 +185,278 @@ struct CellParams {
   const uint32_t *node_list_u; const uint16_t *cell_loc_u;
   const uint32_t *node_list_p; const uint16_t *cell_loc_p;
   int max_nodes_u, max_nodes_p;
-  const double *eta_t; int n_eta;     // lane-transposed table [batch][k][n_eta][32]
-  double ee[3];                        // 1 / (h_d * a)
+  const double *eta_t; int n_eta;     // lane-transposed table [batch][n_eta][32]
+  double ee[3];                        // 1 / (2 h_d a): the line derivative below returns 2 D'
   double vol, ps;
   const double *src_u, *src_p;
   double *dst_u, *dst_p;
 };
 
-template <int DIM> __host__ __device__ constexpr int npair() { return DIM == 3 ? 3 : 1; }
-template <int DIM> size_t vel_smem_bytes(int max_nodes_u, int max_nodes_p, int mode)
+// ---- line primitives (3 values along one direction) ---------------------------------------------------------
+// 2 D' (a, b, c): rows (-3, 4, -1), (-1, 0, 1), (1, -4, 3)
+__device__ __forceinline__ void dline(double a, double b, double c, double &ga, double &gb, double &gc)
 {
-  size_t d = 2 * (size_t)DIM * max_nodes_u + (size_t)npair<DIM>() * nn<DIM>() * 32;
-  if (mode != 0) d += 2 * (size_t)max_nodes_p + (size_t)DIM * np<DIM>() * 32;
-  return d * sizeof(double);
+  const double d1 = b - a, d2 = c - b;
+  gb = c - a;
+  ga = fma(4.0, d1, -gb);
+  gc = fma(4.0, d2, -gb);
+}
+// T += s * (2 D')^T x
+__device__ __forceinline__ void dTline_add(double &Ta, double &Tb, double &Tc, double xa, double xb, double xc, double s, double s3, double s4)
+{
+  Ta = fma(-s3, xa, Ta); Ta = fma(-s, xb, Ta); Ta = fma(s, xc, Ta);
+  Tb = fma(s4, xa - xc, Tb);
+  Tc = fma(-s, xa, Tc); Tc = fma(s, xb, Tc); Tc = fma(s3, xc, Tc);
 }
 
-// MODE 0: A block (u -> u); MODE 1: Stokes ((u,p) -> (u,p)); MODE 2: B^T (p -> u)
-template <int DIM, int MODE>
-__global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 2 : 4) velocity_kernel(const CellParams P)
+template <int DIM> __host__ __device__ constexpr int npair() { return DIM == 3 ? 3 : 1; }
+template <int DIM> __host__ __device__ constexpr int pair_slot(int lo, int hi) { return DIM == 3 ? lo + hi - 1 : 0; }
+
+template <int DIM> size_t vel_smem_bytes(int max_nodes_u, int max_nodes_p, int mode)
 {
-  constexpr int NN = nn<DIM>(), NP = np<DIM>(), NT = 32 * DIM;
+  size_t b = ((size_t)DIM * max_nodes_u + (size_t)npair<DIM>() * nn<DIM>() * SUB) * sizeof(double) + (size_t)nn<DIM>() * SUB * sizeof(uint16_t);
+  if (mode != 0) b += ((size_t)max_nodes_p + (size_t)DIM * np<DIM>() * SUB) * sizeof(double) + (size_t)np<DIM>() * SUB * sizeof(uint16_t);
+  return b;
+}
+
+// The per-direction pieces are templates on the direction so that every register index is a compile-time constant.
+template <int DIM, int DIR, bool PERQ>
+__device__ __forceinline__ void diag_dir(const double (&u)[nn<DIM>()], double (&T)[nn<DIM>()], double f2, const double *etab, bool add)
+{
+  // T (+)= (2D')^T [ f2 w_q eta_q (2D' u) ] along DIR, line by line
+  for_lines<DIM, DIR>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(u[a], u[b], u[c], ga, gb, gc);
+    if (PERQ) { ga *= f2 * qweight<DIM>(a) * etab[a * SUB]; gb *= f2 * qweight<DIM>(b) * etab[b * SUB]; gc *= f2 * qweight<DIM>(c) * etab[c * SUB]; }
+    else { ga *= f2 * qweight<DIM>(a); gb *= f2 * qweight<DIM>(b); gc *= f2 * qweight<DIM>(c); }
+    double ta = fma(-3.0, ga, gc - gb), tb = 4.0 * (ga - gc), tc = fma(3.0, gc, gb - ga);
+    if (add) { T[a] += ta; T[b] += tb; T[c] += tc; }
+    else { T[a] = ta; T[b] = tb; T[c] = tc; }
+  });
+}
+// publish e * (2D'_DIR u) for the partner thread
+template <int DIM, int DIR>
+__device__ __forceinline__ void publish_dir(const double (&u)[nn<DIM>()], double *slot, double e)
+{
+  for_lines<DIM, DIR>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(u[a], u[b], u[c], ga, gb, gc);
+    slot[a * SUB] = e * ga; slot[b * SUB] = e * gb; slot[c * SUB] = e * gc;
+  });
+}
+// upper thread of a pair: X = coef_q (e_d 2D'_DIR u + partner), publish X, T += e_d (2D'_DIR)^T X
+template <int DIM, int DIR, bool PERQ>
+__device__ __forceinline__ void upper_dir(const double (&u)[nn<DIM>()], double (&T)[nn<DIM>()], double *slot, double e, double cvol, const double *etab)
+{
+  const double e3 = 3.0 * e, e4 = 4.0 * e;
+  for_lines<DIM, DIR>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(u[a], u[b], u[c], ga, gb, gc);
+    double xa = fma(e, ga, slot[a * SUB]), xb = fma(e, gb, slot[b * SUB]), xc = fma(e, gc, slot[c * SUB]);
+    if (PERQ) { xa *= cvol * qweight<DIM>(a) * etab[a * SUB]; xb *= cvol * qweight<DIM>(b) * etab[b * SUB]; xc *= cvol * qweight<DIM>(c) * etab[c * SUB]; }
+    else { xa *= cvol * qweight<DIM>(a); xb *= cvol * qweight<DIM>(b); xc *= cvol * qweight<DIM>(c); }
+    slot[a * SUB] = xa; slot[b * SUB] = xb; slot[c * SUB] = xc;
+    dTline_add(T[a], T[b], T[c], xa, xb, xc, e, e3, e4);
+  });
+}
+// lower thread of a pair: T += e_d (2D'_DIR)^T X
+template <int DIM, int DIR>
+__device__ __forceinline__ void lower_dir(double (&T)[nn<DIM>()], const double *slot, double e)
+{
+  const double e3 = 3.0 * e, e4 = 4.0 * e;
+  for_lines<DIM, DIR>([&](int a, int b, int c) {
+    dTline_add(T[a], T[b], T[c], slot[a * SUB], slot[b * SUB], slot[c * SUB], e, e3, e4);
+  });
+}
+#define SMF_DIR_SWITCH(dir, CALL0, CALL1, CALL2) \
+  do { if ((dir) == 0) { CALL0; } else if ((dir) == 1) { CALL1; } else if (DIM == 3) { CALL2; } } while (0)
+
+// MODE 0: A block (u -> u); MODE 1: Stokes ((u,p) -> (u,p)); MODE 2: B^T (p -> u).  PERQ: one viscosity per
+// quadrature point instead of one per cell.  One block = one batch of 32 cells (a Morton 4x4x2 / 8x4 brick);
+// warp c of the block owns velocity component c of those cells, one cell per lane.
+// compile-time part of the structured-brick slot of local node n (smf_internal.h); the lane part is lb[variant]
+__host__ __device__ constexpr int sbn_variant(int n) { return sb_variant((n % 3) & 1, ((n / 3) % 3) & 1); }
+__host__ __device__ constexpr int sbn_const(int n)
+{ return sb_class_base(sbn_variant(n), (n / 9) & 1) + sb_offset(sbn_variant(n), (n % 3) >> 1, ((n / 3) % 3) >> 1, (n / 9) >> 1); }
+
+template <int DIM, int MODE, bool PERQ, bool STRUCT>
+__global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(const CellParams P)
+{
+  static_assert(!STRUCT || DIM == 3, "structured bricks are a 3D layout");
+  constexpr int NN = nn<DIM>(), NP = np<DIM>(), NT = 32 * DIM, D2 = DIM == 3 ? 2 : 0;
   extern __shared__ double smem[];
   const int c = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
   const int *info = P.batch_info + (size_t)b * BATCH_INFO;
   const int n_nodes_u = info[0], n_excl_u = info[1], n_nodes_p = info[2], n_excl_p = info[3], n_cells_b = info[4];
   const int MU = P.max_nodes_u, MP = P.max_nodes_p;
-  double *s_src = smem;                       // [DIM][MU]
-  double *s_dst = s_src + DIM * MU;           // [DIM][MU]
-  double *s_ex = s_dst + DIM * MU;            // [npair][NN][32]
-  double *s_srcp = s_ex + npair<DIM>() * NN * 32;   // [MP]
-  double *s_dstp = s_srcp + MP;               // [MP]
-  double *s_pex = s_dstp + MP;                // [DIM][NP][32]
+  double *s_stage = smem;                              // [DIM][MU]: source values, later the accumulated result
+  double *s_ex = s_stage + DIM * MU;                   // [npair][NN][32]
+  double *s_stagep = s_ex + npair<DIM>() * NN * SUB;   // [MP]           (MODE != 0)
+  double *s_pex = s_stagep + (MODE != 0 ? MP : 0);     // [DIM][NP][32]  (MODE != 0)
+  uint16_t *s_loc = reinterpret_cast<uint16_t *>(s_pex + (MODE != 0 ? DIM * NP * SUB : 0));   // [NN][32]
+  uint16_t *s_locp = s_loc + NN * SUB;                 // [NP][32]       (MODE != 0)
 
   const uint32_t *nlu = P.node_list_u + (size_t)b * MU;
   const uint32_t *nlp = P.node_list_p + (size_t)b * MP;
-  // ---- stage the batch's unique DoFs (constrained DoFs read as zero: read_dof_values semantics) ----
-  for (int j = threadIdx.x; j < n_nodes_u; j += NT) {
-    const uint32_t e = nlu[j];
-    const uint32_t idx = e & NODE_IDX_MASK;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      if (MODE != 2) s_src[d * MU + j] = ((e >> (NODE_FLAG_SHIFT + d)) & 1u) ? 0.0 : P.src_u[idx + d];
-      s_dst[d * MU + j] = 0.0;
+  // ---- stage the batch's unique DoFs (constrained DoFs read as zero: read_dof_values semantics) and its slot map ----
+  {
+    if (!STRUCT) {
+      const uint32_t *gl = reinterpret_cast<const uint32_t *>(P.cell_loc_u + (size_t)b * NN * SUB);
+      uint32_t *sl = reinterpret_cast<uint32_t *>(s_loc);
+      for (int j = threadIdx.x; j < NN * SUB / 2; j += NT) sl[j] = gl[j];
+    }
+    if (MODE != 0) {
+      const uint32_t *glp = reinterpret_cast<const uint32_t *>(P.cell_loc_p + (size_t)b * NP * SUB);
+      uint32_t *slp = reinterpret_cast<uint32_t *>(s_locp);
+      for (int j = threadIdx.x; j < NP * SUB / 2; j += NT) slp[j] = glp[j];
     }
   }
+  // all index loads of a thread first, then all value loads: two exposed memory latencies per block instead of 2 x SU
+  constexpr int SU = STRUCT ? 7 : (DIM == 3 ? 5 : 3);   // ceil(staged nodes of a brick / threads): 580 / 96, 405 / 96, 153 / 64
+  if (MODE != 2)
+    for (int j0 = threadIdx.x; j0 < n_nodes_u; j0 += NT * SU) {
+      uint32_t e[SU];
+      double v[SU][DIM];
+#pragma unroll
+      for (int i = 0; i < SU; ++i) e[i] = (j0 + i * NT < n_nodes_u) ? nlu[j0 + i * NT] : NODE_INVALID;
+#pragma unroll
+      for (int i = 0; i < SU; ++i)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+          v[i][d] = ((e[i] >> (NODE_FLAG_SHIFT + d)) & 1u) ? 0.0 : P.src_u[(e[i] & NODE_IDX_MASK) + d];
+#pragma unroll
+      for (int i = 0; i < SU; ++i)
+        if (j0 + i * NT < n_nodes_u) {
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) s_stage[d * MU + j0 + i * NT] = v[i][d];
+        }
+    }
   if (MODE != 0)
     for (int j = threadIdx.x; j < n_nodes_p; j += NT) {
       const uint32_t e = nlp[j];
-      s_srcp[j] = (e >> 31) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
-      s_dstp[j] = 0.0;
+      s_stagep[j] = (e >> 31) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
     }
+  const bool active = lane < n_cells_b;
+  const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+  const double eta0 = PERQ ? 1.0 : etab[0];
+  const double ec = P.ee[c];
   __syncthreads();
 
-  const double ec = P.ee[c];
-  for (int k = 0; k < KSUB; ++k) {
-    const bool active = (k * SUB + lane) < n_cells_b;
-    const uint16_t *loc = P.cell_loc_u + (((size_t)b * KSUB + k) * NN) * SUB + lane;
-    const uint16_t *locp = P.cell_loc_p + (((size_t)b * KSUB + k) * NP) * SUB + lane;
-    const double *etab = P.eta_t + ((size_t)b * KSUB + k) * P.n_eta * SUB + lane;
-    const int eq = (P.n_eta == 1) ? 0 : SUB;           // stride between quadrature points in the table
-    double u[NN], T[NN];
+  // staging slot of local node n of this lane's cell
+  int lb[4] = {0, 0, 0, 0};
+  if (STRUCT) {
+    const int x = sb_x(lane), y = sb_y(lane), z = sb_z(lane);
+    lb[0] = x + 12 * y + 60 * z; lb[1] = x + 4 * y + 20 * z; lb[2] = y + 4 * x + 20 * z; lb[3] = x + 4 * y + 16 * z;
+  }
+  double *my_stage = s_stage + c * MU;
+  const auto slot = [&](int n) -> int { return STRUCT ? sbn_const(n) + lb[sbn_variant(n)] : (int)s_loc[n * SUB + lane]; };
 
-    if (MODE != 2) {
+  double u[NN], T[NN];
+  if (MODE != 2) {
 #pragma unroll
-      for (int n = 0; n < NN; ++n) u[n] = s_src[c * MU + loc[n * SUB]];
-      interp_all<DIM>(u);
+    for (int n = 0; n < NN; ++n) u[n] = my_stage[slot(n)];
+    interp_all<DIM>(u);
+  }
+  // ---- pressure contribution to the velocity rows: T = (2D'_c)^T [ -e_c ps vol w_q p_q ] ----
+  if (MODE != 0) {
+    double pn[NP], pq[NN];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pn[i] = s_stagep[s_locp[i * SUB + lane]];
+    q1_to_quad<DIM>(pn, pq);
+    const double f = -ec * P.ps * P.vol;
+#pragma unroll
+    for (int q = 0; q < NN; ++q) pq[q] *= f * qweight<DIM>(q);
+    const auto pT = [&](auto dirc) {
+      constexpr int DIR = decltype(dirc)::value;
+      for_lines<DIM, DIR>([&](int a, int b2, int c2) {
+        T[a] = fma(-3.0, pq[a], pq[c2] - pq[b2]); T[b2] = 4.0 * (pq[a] - pq[c2]); T[c2] = fma(3.0, pq[c2], pq[b2] - pq[a]);
+      });
+    };
+    SMF_DIR_SWITCH(c, pT(std::integral_constant<int, 0>()), pT(std::integral_constant<int, 1>()), pT(std::integral_constant<int, D2>()));
+  }
+  if (MODE == 1) {   // pressure rows: -ps (div u, q): this component's share, summed below by warp 0
+    double dq[NN], y[NP];
+    const double f = -P.ps * P.vol * ec;
+    const auto dv = [&](auto dirc) {
+      constexpr int DIR = decltype(dirc)::value;
+      for_lines<DIM, DIR>([&](int a, int b2, int c2) {
+        dline(u[a], u[b2], u[c2], dq[a], dq[b2], dq[c2]);
+        dq[a] *= f * qweight<DIM>(a); dq[b2] *= f * qweight<DIM>(b2); dq[c2] *= f * qweight<DIM>(c2);
+      });
+    };
+    SMF_DIR_SWITCH(c, dv(std::integral_constant<int, 0>()), dv(std::integral_constant<int, 1>()), dv(std::integral_constant<int, D2>()));
+    quad_to_q1T<DIM>(dq, y);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) s_pex[(c * NP + i) * SUB + lane] = y[i];
+  }
+  if (MODE != 2) {
+    // ---- diagonal direction: T (+)= (2D'_c)^T [ 2 eta w vol e_c^2 (2D'_c u) ] ----
+    const double f2 = 2.0 * ec * ec * P.vol * eta0;
+    SMF_DIR_SWITCH(c, (diag_dir<DIM, 0, PERQ>(u, T, f2, etab, MODE != 0)), (diag_dir<DIM, 1, PERQ>(u, T, f2, etab, MODE != 0)),
+                   (diag_dir<DIM, D2, PERQ>(u, T, f2, etab, MODE != 0)));
+    // ---- off-diagonal pairs {c,d}: X = eta w vol (e_d g_cd + e_c g_dc) is symmetric; the lower thread publishes
+    //      its scaled derivative, the higher one forms X, uses it and publishes it back ----
+    if (c == 0) {
+      publish_dir<DIM, 1>(u, s_ex + (size_t)pair_slot<DIM>(0, 1) * NN * SUB + lane, P.ee[1]);
+      if (DIM == 3) publish_dir<DIM, D2>(u, s_ex + (size_t)pair_slot<DIM>(0, 2) * NN * SUB + lane, P.ee[2]);
+    } else if (DIM == 3 && c == 1) {
+      publish_dir<DIM, D2>(u, s_ex + (size_t)pair_slot<DIM>(1, 2) * NN * SUB + lane, P.ee[2]);
     }
-    // ---- diagonal direction: T = D'_c^T [ 2 eta w vol e_c^2 g_cc - e_c ps w vol p ] ----
-    if (MODE != 0) {
-      double pn[NP], pq[NN];
-#pragma unroll
-      for (int i = 0; i < NP; ++i) pn[i] = s_srcp[locp[i * SUB]];
-      q1_to_quad<DIM>(pn, pq);
-      const double f = -ec * P.ps * P.vol;
-#pragma unroll
-      for (int q = 0; q < NN; ++q) T[q] = f * qweight<DIM>(q) * pq[q];
-    } else {
-#pragma unroll
-      for (int q = 0; q < NN; ++q) T[q] = 0.0;
-    }
-    if (MODE != 2) {
-      double g[NN];
-      deriv_dir<DIM>(c, u, g);
-      if (MODE == 1) {   // pressure rows: -ps (div u, q): this component's share, reduced below by warp 0
-        double dq[NN], y[NP];
-        const double f = -P.ps * P.vol * ec;
-#pragma unroll
-        for (int q = 0; q < NN; ++q) dq[q] = f * qweight<DIM>(q) * g[q];
-        quad_to_q1T<DIM>(dq, y);
-#pragma unroll
-        for (int i = 0; i < NP; ++i) s_pex[(c * NP + i) * SUB + lane] = y[i];
-      }
-      const double f2 = 2.0 * ec * ec * P.vol;
-#pragma unroll
-      for (int q = 0; q < NN; ++q) T[q] += f2 * qweight<DIM>(q) * etab[q * eq] * g[q];
-    }
-    {
-      double Tc[NN];
-#pragma unroll
-      for (int q = 0; q < NN; ++q) { Tc[q] = T[q]; T[q] = 0.0; }
-      derivT_add_dir<DIM>(c, T, Tc, 1.0);
-    }
-    // ---- off-diagonal pairs {c,d}: X = eta w vol (e_d g_cd + e_c g_dc) is symmetric; the lower thread
-    //      publishes g, the higher one forms X, uses it and publishes it back ----
-    if (MODE != 2) {
-#pragma unroll
-      for (int d = 1; d < DIM; ++d)
-        if (c < d) {
-          double g[NN];
-          deriv_dir<DIM>(d, u, g);
-          double *slot = s_ex + (size_t)(c + d - 1) * NN * SUB + lane;
-#pragma unroll
-          for (int q = 0; q < NN; ++q) slot[q * SUB] = g[q];
-        }
-    }
-    __syncthreads();
-    if (MODE == 1 && c == 0) {   // pressure scatter (one warp: collision-free rounds over the 2^dim nodes)
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        double y = s_pex[i * SUB + lane];
-#pragma unroll
-        for (int d = 1; d < DIM; ++d) y += s_pex[(d * NP + i) * SUB + lane];
-        if (active) s_dstp[locp[i * SUB]] += y;
-        __syncwarp();
-      }
-    }
-    if (MODE != 2) {
-#pragma unroll
-      for (int d = 0; d < DIM - 1; ++d)
-        if (d < c) {
-          double g[NN];
-          deriv_dir<DIM>(d, u, g);           // g_cd = D'_d Uq_c
-          double *slot = s_ex + (size_t)(c + d - 1) * NN * SUB + lane;
-          const double ed = P.ee[d], vol = P.vol;
-#pragma unroll
-          for (int q = 0; q < NN; ++q) {
-            const double x = vol * qweight<DIM>(q) * etab[q * eq] * (ed * g[q] + ec * slot[q * SUB]);
-            slot[q * SUB] = x;
-            g[q] = x;
-          }
-          derivT_add_dir<DIM>(d, T, g, ed);
-        }
+  }
+  __syncthreads();       // every gather from the staging areas is done: they become the accumulation buffers
+  for (int j = threadIdx.x; j < DIM * MU; j += NT) s_stage[j] = 0.0;
+  if (MODE == 1)
+    for (int j = threadIdx.x; j < MP; j += NT) s_stagep[j] = 0.0;
+  if (MODE != 2) {
+    const double cvol = P.vol * eta0;
+    if (c == 1) {
+      upper_dir<DIM, 0, PERQ>(u, T, s_ex + (size_t)pair_slot<DIM>(0, 1) * NN * SUB + lane, P.ee[0], cvol, etab);
+    } else if (DIM == 3 && c == 2) {
+      upper_dir<DIM, 0, PERQ>(u, T, s_ex + (size_t)pair_slot<DIM>(0, 2) * NN * SUB + lane, P.ee[0], cvol, etab);
+      upper_dir<DIM, 1, PERQ>(u, T, s_ex + (size_t)pair_slot<DIM>(1, 2) * NN * SUB + lane, P.ee[1], cvol, etab);
     }
     __syncthreads();
-    if (MODE != 2) {
-#pragma unroll
-      for (int d = 1; d < DIM; ++d)
-        if (c < d) {
-          double x[NN];
-          const double *slot = s_ex + (size_t)(c + d - 1) * NN * SUB + lane;
-#pragma unroll
-          for (int q = 0; q < NN; ++q) x[q] = slot[q * SUB];
-          derivT_add_dir<DIM>(d, T, x, P.ee[d]);
-        }
+    if (c == 0) {
+      lower_dir<DIM, 1>(T, s_ex + (size_t)pair_slot<DIM>(0, 1) * NN * SUB + lane, P.ee[1]);
+      if (DIM == 3) lower_dir<DIM, D2>(T, s_ex + (size_t)pair_slot<DIM>(0, 2) * NN * SUB + lane, P.ee[2]);
+    } else if (DIM == 3 && c == 1) {
+      lower_dir<DIM, D2>(T, s_ex + (size_t)pair_slot<DIM>(1, 2) * NN * SUB + lane, P.ee[2]);
     }
-    interpT_all<DIM>(T);
-    // ---- accumulate into the staging area, one collision-free round at a time ----
+  } else {
+    __syncthreads();     // (zeroing of s_stage finished)
+  }
+  if (MODE == 1 && c == DIM - 1) {   // pressure rows: sum the components' shares, scatter in collision-free rounds (one warp)
 #pragma unroll
-    for (int r = 0; r < (1 << DIM); ++r) {
+    for (int i = 0; i < NP; ++i) {
+      double y = s_pex[i * SUB + lane];
 #pragma unroll
-      for (int n = 0; n < NN; ++n)
-        if (round_q2<DIM>(n) == r && active) s_dst[c * MU + loc[n * SUB]] += T[n];
+      for (int d = 1; d < DIM; ++d) y += s_pex[(d * NP + i) * SUB + lane];
+      if (active) s_stagep[s_locp[i * SUB + lane]] += y;
       __syncwarp();
     }
+  }
+  interpT_all<DIM>(T);
+  // ---- accumulate into the staging area, one collision-free round at a time ----
+#pragma unroll
+  for (int r = 0; r < (1 << DIM); ++r) {
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+      if (round_q2<DIM>(n) == r && active) my_stage[slot(n)] += T[n];
+    __syncwarp();
   }
   __syncthreads();
   // ---- flush: private nodes with plain stores, shared nodes with one RED per DoF; constrained DoFs get the
   //      unit diagonal of MatrixFreeOperators::Base (dst = src) ----
   for (int j = threadIdx.x; j < n_nodes_u; j += NT) {
     const uint32_t e = nlu[j];
+    if (STRUCT && e == NODE_INVALID) continue;
     const uint32_t idx = e & NODE_IDX_MASK;
+    const bool excl = STRUCT ? !(e & NODE_SHARED_BIT) : (j < n_excl_u);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       if ((e >> (NODE_FLAG_SHIFT + d)) & 1u) P.dst_u[idx + d] = (MODE == 2) ? 0.0 : P.src_u[idx + d];
-      else if (j < n_excl_u) P.dst_u[idx + d] = s_dst[d * MU + j];
-      else atomicAdd(P.dst_u + idx + d, s_dst[d * MU + j]);
+      else if (excl) P.dst_u[idx + d] = s_stage[d * MU + j];
+      else atomicAdd(P.dst_u + idx + d, s_stage[d * MU + j]);
     }
   }
   if (MODE == 1)
@@ -366,63 +464,87 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 2 : 4) velocity_kernel(co
       const uint32_t e = nlp[j];
       const uint32_t idx = e & NODE_IDX_MASK;
       if (e >> 31) P.dst_p[idx] = P.src_p[idx];
-      else if (j < n_excl_p) P.dst_p[idx] = s_dstp[j];
-      else atomicAdd(P.dst_p + idx, s_dstp[j]);
+      else if (j < n_excl_p) P.dst_p[idx] = s_stagep[j];
+      else atomicAdd(P.dst_p + idx, s_stagep[j]);
     }
 }
 
-// ---- pressure mass matrix: one thread per cell, two warps (= two sub-batches) per block -------------------
-template <int DIM>
-__global__ void __launch_bounds__(BATCH_CELLS) mass_kernel(const CellParams P)
+// ---- pressure mass matrix: one warp per batch (one cell per lane), MASS_WARPS independent warps per block --------
+// With one viscosity per cell the cell matrix is (ps^2 vol / eta) M1 x M1 x M1 with the exact 1D Q1 mass matrix
+// M1 = [2 1; 1 2] / 6 (the 3-point Gauss rule integrates it exactly), applied as 2x2 sweeps on the 2^dim nodal
+// values; with one viscosity per quadrature point the Q1 values go through the quadrature points.
+constexpr int MASS_WARPS = 4;
+constexpr int MASS_SU = 3;     // staging rounds unrolled together: ceil(75 / 32) nodes of a structured brick per lane
+template <int DIM, bool PERQ>
+__global__ void __launch_bounds__(32 * MASS_WARPS, PERQ ? 3 : 8) mass_kernel(const CellParams P, int n_batches)
 {
   constexpr int NN = nn<DIM>(), NP = np<DIM>();
   extern __shared__ double smem[];
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * MASS_WARPS + w;
+  if (b >= n_batches) return;
   const int *info = P.batch_info + (size_t)b * BATCH_INFO;
   const int n_nodes_p = info[2], n_excl_p = info[3], n_cells_b = info[4];
   const int MP = P.max_nodes_p;
-  double *s_src = smem;            // [MP]
-  double *s_dst = smem + MP;       // [KSUB][MP]
+  double *s_src = smem + (size_t)w * 2 * MP;   // [MP]
+  double *s_dst = s_src + MP;                  // [MP]
   const uint32_t *nlp = P.node_list_p + (size_t)b * MP;
-  for (int j = threadIdx.x; j < n_nodes_p; j += BATCH_CELLS) {
-    const uint32_t e = nlp[j];
-    s_src[j] = (e >> 31) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
+  const uint16_t *locp = P.cell_loc_p + (size_t)b * NP * SUB + lane;
+  uint16_t loc[NP];
 #pragma unroll
-    for (int kk = 0; kk < KSUB; ++kk) s_dst[kk * MP + j] = 0.0;
+  for (int i = 0; i < NP; ++i) loc[i] = locp[i * SUB];
+  const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+  const double eta0 = PERQ ? 1.0 : etab[0];
+  for (int j0 = lane; j0 < n_nodes_p; j0 += 32 * MASS_SU) {
+    uint32_t e[MASS_SU];
+    double v[MASS_SU];
+#pragma unroll
+    for (int i = 0; i < MASS_SU; ++i) e[i] = (j0 + 32 * i < n_nodes_p) ? nlp[j0 + 32 * i] : 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < MASS_SU; ++i) v[i] = (e[i] >> 31) ? 0.0 : P.src_p[e[i] & NODE_IDX_MASK];
+#pragma unroll
+    for (int i = 0; i < MASS_SU; ++i)
+      if (j0 + 32 * i < n_nodes_p) { s_src[j0 + 32 * i] = v[i]; s_dst[j0 + 32 * i] = 0.0; }
   }
-  __syncthreads();
-  const bool active = (k * SUB + lane) < n_cells_b;
-  const uint16_t *locp = P.cell_loc_p + (((size_t)b * KSUB + k) * NP) * SUB + lane;
-  const double *etab = P.eta_t + ((size_t)b * KSUB + k) * P.n_eta * SUB + lane;
-  double pn[NP], pq[NN], y[NP];
+  __syncwarp();
+  const bool active = lane < n_cells_b;
+  double y[NP];
 #pragma unroll
-  for (int i = 0; i < NP; ++i) pn[i] = s_src[locp[i * SUB]];
-  q1_to_quad<DIM>(pn, pq);
+  for (int i = 0; i < NP; ++i) y[i] = s_src[loc[i]];
   const double f = P.ps * P.ps * P.vol;
-  if (P.n_eta == 1) {
-    const double ce = active ? f / etab[0] : 0.0;
+  if (!PERQ) {
 #pragma unroll
-    for (int q = 0; q < NN; ++q) pq[q] *= ce * qweight<DIM>(q);
+    for (int d = 0; d < DIM; ++d) {
+      const int S = 1 << d;
+#pragma unroll
+      for (int i = 0; i < NP; ++i)
+        if (!(i & S)) {
+          const double a = y[i], c = y[i + S];
+          y[i] = fma(2.0, a, c); y[i + S] = fma(2.0, c, a);
+        }
+    }
+    const double ce = f / (eta0 * (DIM == 3 ? 216.0 : 36.0));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) y[i] *= ce;
   } else {
+    double pn[NP], pq[NN];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pn[i] = y[i];
+    q1_to_quad<DIM>(pn, pq);
 #pragma unroll
     for (int q = 0; q < NN; ++q) pq[q] *= active ? (f / etab[q * SUB]) * qweight<DIM>(q) : 0.0;
+    quad_to_q1T<DIM>(pq, y);
   }
-  quad_to_q1T<DIM>(pq, y);
 #pragma unroll
   for (int i = 0; i < NP; ++i) {     // node i of different cells never alias: one round per node
-    if (active) s_dst[k * MP + locp[i * SUB]] += y[i];
+    if (active) s_dst[loc[i]] += y[i];
     __syncwarp();
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < n_nodes_p; j += BATCH_CELLS) {
+  for (int j = lane; j < n_nodes_p; j += 32) {
     const uint32_t e = nlp[j];
     const uint32_t idx = e & NODE_IDX_MASK;
-    double v = s_dst[j];
-#pragma unroll
-    for (int kk = 1; kk < KSUB; ++kk) v += s_dst[kk * MP + j];
     if (e >> 31) P.dst_p[idx] = P.src_p[idx];
-    else if (j < n_excl_p) P.dst_p[idx] = v;
-    else atomicAdd(P.dst_p + idx, v);
+    else if (j < n_excl_p) P.dst_p[idx] = s_dst[j];
+    else atomicAdd(P.dst_p + idx, s_dst[j]);
   }
 }
 
@@ -517,9 +639,38 @@ struct TransferParams {
   int add;
 };
 
+// Sparse 1D prolongation rows: patch position r touches coarse nodes [first, first + count) with weights w[]
+struct Row1D { int first, count; double w0, w1, w2; __device__ __forceinline__ double w(int k) const { return k == 0 ? w0 : (k == 1 ? w1 : w2); } };
+template <int NPD> __device__ __forceinline__ Row1D prow(int r)
+{
+  if (NPD == 3) {
+    if ((r & 1) == 0) return {r >> 1, 1, 1.0, 0.0, 0.0};
+    if (r == 1) return {0, 3, 0.375, 0.75, -0.125};
+    return {0, 3, -0.125, 0.75, 0.375};
+  }
+  if ((r & 1) == 0) return {r >> 1, 1, 1.0, 0.0, 0.0};
+  return {0, 2, 0.5, 0.5, 0.0};
+}
+// transposed: coarse node j receives from patch positions pos[0..count) with weights w[]
+struct Col1D {
+  int count, p0, p1, p2; double w0, w1, w2;
+  __device__ __forceinline__ double w(int k) const { return k == 0 ? w0 : (k == 1 ? w1 : w2); }
+  __device__ __forceinline__ int pos(int k) const { return k == 0 ? p0 : (k == 1 ? p1 : p2); }
+};
+template <int NPD> __device__ __forceinline__ Col1D pcol(int j)
+{
+  if (NPD == 3) {
+    if (j == 0) return {3, 0, 1, 3, 1.0, 0.375, -0.125};
+    if (j == 1) return {3, 1, 2, 3, 0.75, 1.0, 0.75};
+    return {3, 1, 3, 4, -0.125, 0.375, 1.0};
+  }
+  if (j == 0) return {2, 0, 1, 0, 1.0, 0.5, 0.0};
+  return {2, 1, 2, 0, 0.5, 1.0, 0.0};
+}
+
 // one thread per (parent, fine patch entry): interpolate the coarse cell function at that patch node; only the
 // owning parent writes (all parents would write the same value), so no atomics and no weights are needed.
-template <int DIM, int NPD, int NCOMP> __global__ void prolongate_kernel(const TransferParams P)
+template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(128) prolongate_kernel(const TransferParams P)
 {
   constexpr int NPP = 2 * NPD - 1;
   constexpr int NPATCH = DIM == 3 ? NPP * NPP * NPP : NPP * NPP;
@@ -530,22 +681,29 @@ template <int DIM, int NPD, int NCOMP> __global__ void prolongate_kernel(const T
   if (par >= P.n_parents) return;
   const uint32_t pe = P.patch[par * NPATCH + s];
   if (!(pe >> 31)) return;
-  const int sd[3] = {s % NPP, (s / NPP) % NPP, DIM == 3 ? s / (NPP * NPP) : 0};
+  const Row1D rx = prow<NPD>(s % NPP), ry = prow<NPD>((s / NPP) % NPP);
+  const Row1D rz = DIM == 3 ? prow<NPD>(s / (NPP * NPP)) : Row1D{0, 1, 1.0, 0.0, 0.0};
+  const uint32_t *cn = P.coarse_nodes + par * NC;
   double acc[NCOMP];
+#pragma unroll
   for (int c = 0; c < NCOMP; ++c) acc[c] = 0.0;
-  for (int j = 0; j < NC; ++j) {
-    const int jd[3] = {j % NPD, (j / NPD) % NPD, DIM == 3 ? j / (NPD * NPD) : 0};
-    double w = 1.0;
-    for (int d = 0; d < DIM; ++d) w *= (NPD == 3) ? p2row(sd[d], jd[d]) : p1row(sd[d], jd[d]);
-    if (w == 0.0) continue;
-    const uint32_t ce = P.coarse_nodes[par * NC + j];
-    const uint32_t ci = ce & NODE_IDX_MASK;
-    for (int c = 0; c < NCOMP; ++c) {
-      const bool cons = (NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u);
-      if (!cons) acc[c] += w * P.src[ci + c];
+  for (int kz = 0; kz < rz.count; ++kz)
+    for (int ky = 0; ky < ry.count; ++ky) {
+      const double wzy = rz.w(kz) * ry.w(ky);
+      const int base = (DIM == 3 ? (rz.first + kz) * NPD * NPD : 0) + (ry.first + ky) * NPD + rx.first;
+      for (int kx = 0; kx < rx.count; ++kx) {
+        const double w = wzy * rx.w(kx);
+        const uint32_t ce = cn[base + kx];
+        const uint32_t ci = ce & NODE_IDX_MASK;
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+          const bool cons = (NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u);
+          if (!cons) acc[c] = fma(w, P.src[ci + c], acc[c]);
+        }
+      }
     }
-  }
   const uint32_t fi = pe & NODE_IDX_MASK;
+#pragma unroll
   for (int c = 0; c < NCOMP; ++c) {
     if (P.add) P.dst[fi + c] += acc[c];
     else P.dst[fi + c] = acc[c];
@@ -554,7 +712,7 @@ template <int DIM, int NPD, int NCOMP> __global__ void prolongate_kernel(const T
 
 // one thread per (parent, coarse node): gather the owned fine patch values with the transposed weights and add
 // into the coarse vector (coarse Dirichlet DoFs stay untouched = zero).
-template <int DIM, int NPD, int NCOMP> __global__ void restrict_kernel(const TransferParams P)
+template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(128) restrict_kernel(const TransferParams P)
 {
   constexpr int NPP = 2 * NPD - 1;
   constexpr int NPATCH = DIM == 3 ? NPP * NPP * NPP : NPP * NPP;
@@ -563,21 +721,36 @@ template <int DIM, int NPD, int NCOMP> __global__ void restrict_kernel(const Tra
   const int64_t par = t / NC;
   const int j = (int)(t % NC);
   if (par >= P.n_parents) return;
-  const int jd[3] = {j % NPD, (j / NPD) % NPD, DIM == 3 ? j / (NPD * NPD) : 0};
-  double acc[NCOMP];
-  for (int c = 0; c < NCOMP; ++c) acc[c] = 0.0;
-  for (int s = 0; s < NPATCH; ++s) {
-    const int sd[3] = {s % NPP, (s / NPP) % NPP, DIM == 3 ? s / (NPP * NPP) : 0};
-    double w = 1.0;
-    for (int d = 0; d < DIM; ++d) w *= (NPD == 3) ? p2row(sd[d], jd[d]) : p1row(sd[d], jd[d]);
-    if (w == 0.0) continue;
-    const uint32_t pe = P.patch[par * NPATCH + s];
-    if (!(pe >> 31)) continue;
-    const uint32_t fi = pe & NODE_IDX_MASK;
-    for (int c = 0; c < NCOMP; ++c) acc[c] += w * P.src[fi + c];
-  }
   const uint32_t ce = P.coarse_nodes[par * NC + j];
+  bool any = false;
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) any |= !((NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u));
+  if (!any) return;
+  const Col1D cx = pcol<NPD>(j % NPD), cy = pcol<NPD>((j / NPD) % NPD);
+  const Col1D cz = DIM == 3 ? pcol<NPD>(j / (NPD * NPD)) : Col1D{1, 0, 0, 0, 1.0, 0.0, 0.0};
+  const uint32_t *pt = P.patch + par * NPATCH;
+  double acc[NCOMP];
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) acc[c] = 0.0;
+  for (int kz = 0; kz < cz.count; ++kz)
+    for (int ky = 0; ky < cy.count; ++ky) {
+      const double wzy = cz.w(kz) * cy.w(ky);
+      const int base = (DIM == 3 ? cz.pos(kz) * NPP * NPP : 0) + cy.pos(ky) * NPP;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (kx < cx.count) {
+          const uint32_t pe = pt[base + cx.pos(kx)];
+          if (pe >> 31) {
+            const double w = wzy * cx.w(kx);
+            const uint32_t fi = pe & NODE_IDX_MASK;
+#pragma unroll
+            for (int c = 0; c < NCOMP; ++c) acc[c] = fma(w, P.src[fi + c], acc[c]);
+          }
+        }
+      }
+    }
   const uint32_t ci = ce & NODE_IDX_MASK;
+#pragma unroll
   for (int c = 0; c < NCOMP; ++c) {
     const bool cons = (NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u);
     if (!cons && acc[c] != 0.0) atomicAdd(P.dst + ci + c, acc[c]);
@@ -594,27 +767,36 @@ static CellParams make_params(const LevelDev &L)
   P.max_nodes_u = L.max_nodes_u; P.max_nodes_p = L.max_nodes_p;
   P.eta_t = L.eta; P.n_eta = L.n_eta;
   double vol = 1.0;
-  for (int d = 0; d < L.dim; ++d) { P.ee[d] = 1.0 / (L.h[d] * HOST_GAUSS_A); vol *= L.h[d]; }
+  for (int d = 0; d < L.dim; ++d) { P.ee[d] = 0.5 / (L.h[d] * HOST_GAUSS_A); vol *= L.h[d]; }
   P.vol = vol; P.ps = L.ps;
   return P;
 }
 
-template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &L, CellParams &P)
+template <int DIM, int MODE, bool PERQ, bool STRUCT> static int launch_velocity_t(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
   const size_t smem = vel_smem_bytes<DIM>(L.max_nodes_u, L.max_nodes_p, MODE);
   static size_t configured = 0;
   if (smem > configured) {
-    SMF_CUDA(cudaFuncSetAttribute(velocity_kernel<DIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SMF_CUDA(cudaFuncSetAttribute(velocity_kernel<DIM, MODE, PERQ, STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
   {
     ProfScope prof(ctx, MODE == 1 ? B_STOKES : (MODE == 2 ? B_BT : (fine ? B_A_FINE : B_A_COARSE)));
-    velocity_kernel<DIM, MODE><<<L.n_batches, 32 * DIM, smem, ctx->stream>>>(P);
+    velocity_kernel<DIM, MODE, PERQ, STRUCT><<<L.n_batches, 32 * DIM, smem, ctx->stream>>>(P);
   }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;
+}
+template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &L, CellParams &P)
+{
+  if (DIM == 3 && L.structured) {
+    if (MODE != 2 && L.n_eta != 1) return launch_velocity_t<3, MODE, true, true>(ctx, L, P);
+    return launch_velocity_t<3, MODE, false, true>(ctx, L, P);
+  }
+  if (MODE != 2 && L.n_eta != 1) return launch_velocity_t<DIM, MODE, true, false>(ctx, L, P);
+  return launch_velocity_t<DIM, MODE, false, false>(ctx, L, P);
 }
 
 static int check_level(smf_ctx *ctx, const LevelDev &L)
@@ -657,10 +839,16 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
   CellParams P = make_params(L);
   P.src_p = src; P.dst_p = dst;
   SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
-  const size_t smem = (size_t)(1 + KSUB) * L.max_nodes_p * sizeof(double);
+  const size_t smem = (size_t)MASS_WARPS * 2 * L.max_nodes_p * sizeof(double);
+  const unsigned grid = (unsigned)((L.n_batches + MASS_WARPS - 1) / MASS_WARPS);
   ProfScope prof(ctx, B_MASS);
-  if (L.dim == 3) mass_kernel<3><<<L.n_batches, BATCH_CELLS, smem, ctx->stream>>>(P);
-  else mass_kernel<2><<<L.n_batches, BATCH_CELLS, smem, ctx->stream>>>(P);
+  if (L.dim == 3) {
+    if (L.n_eta == 1) mass_kernel<3, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+    else mass_kernel<3, true><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+  } else {
+    if (L.n_eta == 1) mass_kernel<2, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+    else mass_kernel<2, true><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+  }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;

@@ -102,6 +102,51 @@ static void build_batches(const std::vector<uint32_t> &nodes, int64_t n_cells, i
     }
   }
 }
+
+// Structured-brick staging layout of the velocity nodes (3D): succeeds when every batch is a full 4x4x2 Morton brick
+// whose cell maps are consistent with a 9x9x5 lattice.  node_list[b][sb_slot] = node entry | NODE_SHARED_BIT.
+static bool build_structured3(const std::vector<uint32_t> &nodes, int64_t n_cells, int64_t n_index_space,
+                              std::vector<uint32_t> &node_list)
+{
+  if (n_cells % BATCH_CELLS != 0) return false;
+  const int64_t nb = n_cells / BATCH_CELLS;
+  constexpr int NL = 9 * 9 * 5;
+  std::vector<uint32_t> lat((size_t)nb * NL);
+  std::vector<uint8_t> touch((size_t)n_index_space, 0);
+  std::vector<int32_t> seen_at((size_t)n_index_space, -1);     // lattice id of a node inside the current batch
+  std::vector<uint32_t> batch_nodes;
+  for (int64_t b = 0; b < nb; ++b) {
+    uint32_t *L = lat.data() + (size_t)b * NL;
+    std::fill(L, L + NL, NODE_INVALID);
+    batch_nodes.clear();
+    bool ok = true;
+    for (int l = 0; l < BATCH_CELLS && ok; ++l) {
+      const uint32_t *cn = nodes.data() + ((size_t)b * BATCH_CELLS + l) * 27;
+      const int x = sb_x(l), y = sb_y(l), z = sb_z(l);
+      for (int n = 0; n < 27; ++n) {
+        const int id = (2 * x + n % 3) + 9 * ((2 * y + (n / 3) % 3) + 9 * (2 * z + n / 9));
+        const uint32_t idx = cn[n] & NODE_IDX_MASK;
+        if (L[id] == NODE_INVALID) {
+          if (seen_at[idx] >= 0) { ok = false; break; }       // the same node at two lattice points
+          L[id] = cn[n]; seen_at[idx] = id; batch_nodes.push_back(idx);
+        } else if ((L[id] & NODE_IDX_MASK) != idx) { ok = false; break; }
+      }
+    }
+    for (uint32_t idx : batch_nodes) { seen_at[idx] = -1; if (touch[idx] < 2) ++touch[idx]; }
+    if (!ok) return false;
+  }
+  node_list.assign((size_t)nb * SB_SLOTS, NODE_INVALID);
+  for (int64_t b = 0; b < nb; ++b) {
+    const uint32_t *L = lat.data() + (size_t)b * NL;
+    for (int Z = 0; Z < 5; ++Z)
+      for (int Y = 0; Y < 9; ++Y)
+        for (int X = 0; X < 9; ++X) {
+          const uint32_t e = L[X + 9 * (Y + 9 * Z)];
+          node_list[(size_t)b * SB_SLOTS + sb_slot(X, Y, Z)] = e | (touch[e & NODE_IDX_MASK] > 1 ? NODE_SHARED_BIT : 0u);
+        }
+  }
+  return true;
+}
 }  // namespace smf
 
 extern "C" {
@@ -225,6 +270,17 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   build_batches(nodes_u, L.n_cells, NN, L.n_u, round_u, 1 << dim, nl_u, loc_u, nn_u, ne_u, L.max_nodes_u, safe_u);
   build_batches(nodes_p, L.n_cells, NP, L.n_p, round_p, NP, nl_p, loc_p, nn_p, ne_p, L.max_nodes_p, safe_p);
   if (L.max_nodes_u > 65535 || L.max_nodes_p > 65535) return ctx->fail(SMF_ERR_UNSUPPORTED, "batch too large for 16-bit slots");
+  if (dim == 3 && ctx->allow_structured) {
+    std::vector<uint32_t> nl_s;
+    if (build_structured3(nodes_u, L.n_cells, L.n_u, nl_s)) {
+      L.structured = 1;
+      nl_u.swap(nl_s);
+      L.max_nodes_u = SB_SLOTS;
+      for (size_t b = 0; b < nn_u.size(); ++b) { nn_u[b] = SB_SLOTS; ne_u[b] = 0; }
+      loc_u.assign(2, 0);                    // slots are computed in the kernel
+      safe_u = true;
+    }
+  }
   L.safe_rounds = (safe_u && safe_p) ? 1 : 0;
   L.n_batches = (int)nn_u.size();
   std::vector<int> info((size_t)L.n_batches * BATCH_INFO, 0);

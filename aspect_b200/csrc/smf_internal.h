@@ -9,11 +9,48 @@
 
 namespace smf {
 
-constexpr int BATCH_CELLS = 64;   // cells staged per thread block (two 32-cell sub-batches, Morton 4x4x4 / 8x8)
+constexpr int BATCH_CELLS = 32;   // cells staged per thread block (a Morton 4x4x2 / 8x4 brick)
 constexpr int SUB = 32;           // cells per sub-batch = lanes of a warp
 constexpr int KSUB = BATCH_CELLS / SUB;
-constexpr uint32_t NODE_IDX_MASK = 0x1fffffffu;   // low 29 bits: DoF index of component 0 of the node
+constexpr uint32_t NODE_IDX_MASK = 0x0fffffffu;   // low 28 bits: DoF index of component 0 of the node
+constexpr uint32_t NODE_SHARED_BIT = 1u << 28;    // structured bricks: the node is also touched by another batch
+constexpr uint32_t NODE_INVALID = 0xffffffffu;    // structured bricks: padding slot of the staging layout
 constexpr uint32_t NODE_FLAG_SHIFT = 29;          // bits 29..31: component c of this node is constrained
+
+// ---- structured bricks (3D) ------------------------------------------------------------------------------
+// When the 32 cells of a batch form a 4x4x2 brick in Morton order (always the case on uniformly refined levels),
+// its 9x9x5 node lattice is staged in shared memory in a layout that needs no per-cell slot table and is free of
+// bank conflicts: nodes are grouped by the parity of their lattice coordinates (X, Y, Z) -- for a fixed local node
+// of the cell, all 32 cells hit the same parity class at (x, y, z) + const -- and inside a class the two fast
+// strides are chosen so that the 16 (x, y) combinations of a z-plane of cells fall into 16 different 8-byte banks:
+//   class (X even, Y even): X/2 + 12 Y/2 + 60 Z/2      (5 x 5 used of a 12-wide row)
+//   class (X odd,  Y even): X/2 +  4 Y/2 + 20 Z/2
+//   class (X even, Y odd ): Y/2 +  4 X/2 + 20 Z/2
+//   class (X odd,  Y odd ): X/2 +  4 Y/2 + 16 Z/2
+__host__ __device__ constexpr int sb_variant(int px, int py) { return px + 2 * py; }
+__host__ __device__ constexpr int sb_plane(int v) { return v == 0 ? 60 : (v == 3 ? 16 : 20); }
+__host__ __device__ constexpr int sb_class_size(int v, int pz) { return sb_plane(v) * (pz ? 2 : 3); }
+__host__ __device__ constexpr int sb_class_base(int v, int pz)
+{
+  int b = 0;
+  for (int z = 0; z < 2; ++z)
+    for (int w = 0; w < 4; ++w) {
+      if (z == pz && w == v) return b;
+      b += sb_class_size(w, z);
+    }
+  return b;
+}
+__host__ __device__ constexpr int sb_offset(int v, int ox, int oy, int oz)
+{ return v == 0 ? ox + 12 * oy + 60 * oz : (v == 1 ? ox + 4 * oy + 20 * oz : (v == 2 ? oy + 4 * ox + 20 * oz : ox + 4 * oy + 16 * oz)); }
+// slot of lattice point (X, Y, Z), 0 <= X, Y < 9, 0 <= Z < 5
+__host__ __device__ constexpr int sb_slot(int X, int Y, int Z)
+{ return sb_class_base(sb_variant(X & 1, Y & 1), Z & 1) + sb_offset(sb_variant(X & 1, Y & 1), X >> 1, Y >> 1, Z >> 1); }
+constexpr int SB_SLOTS = 580;   // = sb_class_base(3, 1) + sb_class_size(3, 1)
+static_assert(sb_class_base(3, 1) + sb_class_size(3, 1) == SB_SLOTS, "structured brick layout size");
+// brick coordinates of lane l (Morton order inside the batch: x0 y0 z0 x1 y1)
+__host__ __device__ constexpr int sb_x(int l) { return (l & 1) | (((l >> 3) & 1) << 1); }
+__host__ __device__ constexpr int sb_y(int l) { return ((l >> 1) & 1) | (((l >> 4) & 1) << 1); }
+__host__ __device__ constexpr int sb_z(int l) { return (l >> 2) & 1; }
 
 // per-batch header (ints): n_nodes_u, n_excl_u, n_nodes_p, n_excl_p, n_cells, pad x3
 constexpr int BATCH_INFO = 8;
@@ -24,6 +61,7 @@ struct LevelDev {
   int n_batches = 0;
   int max_nodes_u = 0, max_nodes_p = 0;      // padded staging sizes (nodes per batch)
   int safe_rounds = 1;                        // 1: scatter rounds are collision-free inside every sub-batch
+  int structured = 0;                         // 1: every batch is a structured brick (velocity staging by sb_slot)
   int *batch_info = nullptr;                  // [n_batches][BATCH_INFO]
   uint32_t *node_list_u = nullptr;            // [n_batches][max_nodes_u]  exclusive nodes first
   uint32_t *node_list_p = nullptr;            // [n_batches][max_nodes_p]
@@ -63,6 +101,7 @@ struct ProfEvent { int bucket; cudaEvent_t a, b; };
 
 struct MGVectors {                // per level: solution, defect, t, and a Chebyshev scratch
   double *x = nullptr, *b = nullptr, *t = nullptr, *xo = nullptr;
+  double *res = nullptr;          // where the last level_v_step left the solution (x or xo)
 };
 
 }  // namespace smf
@@ -87,7 +126,14 @@ struct smf_ctx {
   double *tmp_u = nullptr, *tmp_p = nullptr, *tmp_u2 = nullptr, *tmp_p2 = nullptr;
   double *io_buf = nullptr; int64_t io_n = 0;         // device staging of smf_solve_host
   int n_A_prec = 0, n_S_prec = 0;
-  void *graph_A = nullptr, *graph_S = nullptr;        // cudaGraphExec_t of the V-cycles (with fixed in/out buffers)
+  int md_vec2 = 0;                                    // the pointer table of the last multi_dot allows 16-byte loads
+  // CUDA graphs of the coarse part of the two V-cycles (level_v_step(graph_level) on the fixed MG buffers)
+  void *graph_A = nullptr, *graph_S = nullptr;        // cudaGraphExec_t
+  bool graph_A_stale = true, graph_S_stale = true;    // smoother coefficients changed since the capture
+  int64_t graph_A_launches = 0, graph_S_launches = 0; // kernels inside one replay
+  int graph_level = -1;                               // finest level inside the graphs (-1: graphs unused)
+  int use_graphs = 1;
+  int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)
   // profiler: 0 off, 1 operator kernels of the finest level only, 2 every launch
   int prof_mode = 0;
   int vec_bucket = smf::B_VEC;                        // bucket the vector kernels are booked under right now

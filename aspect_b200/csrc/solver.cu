@@ -56,6 +56,8 @@ static void tridiag_extreme(const std::vector<double> &d, const std::vector<doub
   lmin = kth(0); lmax = kth(n - 1);
 }
 
+constexpr int64_t GRAPH_MAX_CELLS = 40000;   // levels up to this size are replayed from a CUDA graph
+
 struct MGSide {           // one of the two hierarchies
   bool velocity;
   std::vector<Smoother> *sm;
@@ -154,7 +156,9 @@ static int cheb_step(smf_ctx *ctx, const MGSide &S, int l, double *&x, double *&
   return cheb_tail(ctx, S, l, x, xo, b, t, true);
 }
 
-// Multigrid::level_v_step (App. A.3); defect of level l is V[l].b, the result ends in V[l].x
+static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l);
+
+// Multigrid::level_v_step (App. A.3); defect of level l is V[l].b, the result ends in V[l].res
 static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
 {
   MGVectors &V = (*S.v)[l];
@@ -171,11 +175,50 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
     TRY(vec_residual(ctx, V.t, V.b, n));                                     // t = defect - A x
     TRY(vec_set(ctx, C.b, 0.0, lsize(ctx, S, l - 1)));
     TRY(launch_restrict_add(ctx, which, l, C.b, V.t));
-    TRY(level_v_step(ctx, S, l - 1));
-    TRY(launch_prolongate(ctx, which, l, x, C.x, true));                     // x += P x_coarse
+    TRY(level_v_step_maybe_graph(ctx, S, l - 1));
+    TRY(launch_prolongate(ctx, which, l, x, C.res, true));                   // x += P x_coarse
     for (int s = 0; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));   // post-smoothing
   }
-  V.x = x; V.xo = xo;
+  V.res = x;
+  return SMF_OK;
+}
+
+// Levels <= ctx->graph_level are small: their part of the V-cycle is launch-latency bound, so it is captured once per
+// smoother set-up into a CUDA graph (all buffers and coefficients are fixed between set-ups) and replayed.
+static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
+{
+  const bool profiling_inside = ctx->prof_mode == 2 || (ctx->prof_mode == 1 && l == ctx->cfg.n_levels - 1);
+  if (!ctx->use_graphs || l != ctx->graph_level || profiling_inside) return level_v_step(ctx, S, l);
+  void *&exec = S.velocity ? ctx->graph_A : ctx->graph_S;
+  bool &stale = S.velocity ? ctx->graph_A_stale : ctx->graph_S_stale;
+  int64_t &n_launch = S.velocity ? ctx->graph_A_launches : ctx->graph_S_launches;
+  if (stale) {
+    cudaGraph_t graph = nullptr;
+    SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    const int64_t l0 = ctx->launches;
+    const int rc = level_v_step(ctx, S, l);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return ctx->fail(SMF_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    n_launch = ctx->launches - l0;
+    ctx->launches = l0;
+    bool updated = false;
+    if (exec) {
+      cudaGraphExecUpdateResultInfo info;
+      updated = cudaGraphExecUpdate((cudaGraphExec_t)exec, graph, &info) == cudaSuccess;
+      if (!updated) { cudaGetLastError(); cudaGraphExecDestroy((cudaGraphExec_t)exec); exec = nullptr; }
+    }
+    if (!updated) {
+      cudaGraphExec_t ge = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&ge, graph, 0);
+      if (ie != cudaSuccess) { cudaGraphDestroy(graph); return ctx->fail(SMF_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+      exec = ge;
+    }
+    cudaGraphDestroy(graph);
+    stale = false;
+  }
+  SMF_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, ctx->stream));
+  ctx->launches += n_launch;
   return SMF_OK;
 }
 
@@ -190,10 +233,10 @@ static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
   // copy_to_mg
   if (map) TRY(vec_gather(ctx, V.b, src, map, n, true));
   else TRY(vec_copy(ctx, V.b, src, n));
-  TRY(level_v_step(ctx, S, L));
+  TRY(level_v_step_maybe_graph(ctx, S, L));
   // copy_from_mg
-  if (map) TRY(vec_gather(ctx, dst, V.x, map, n, false));
-  else TRY(vec_copy(ctx, dst, V.x, n));
+  if (map) TRY(vec_gather(ctx, dst, V.res, map, n, false));
+  else TRY(vec_copy(ctx, dst, V.res, n));
   return SMF_OK;
 }
 
@@ -422,6 +465,10 @@ int smf_setup_smoothers(smf_ctx *ctx)
     }
   }
   ctx->smoothers_ready = true;
+  ctx->graph_A_stale = ctx->graph_S_stale = true;
+  ctx->graph_level = -1;
+  for (int l = 0; l < nl; ++l)
+    if (ctx->levels[l].n_cells <= GRAPH_MAX_CELLS) ctx->graph_level = l;
   return SMF_OK;
 }
 

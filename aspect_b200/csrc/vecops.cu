@@ -82,45 +82,65 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
-// out[j] = sum_i V[j][i] * w[i], j < k; out[k] = w.w.  partial[(block)*(k+1) + j] then deterministic final sum.
-__global__ void __launch_bounds__(VT) k_multi_dot(const double *const *V, int k, const double *w, int64_t n,
-                                                   double *partial, unsigned int *counter, double *out)
+// out[j] = sum_i V[j][i] * w[i], j < k; out[k] = w.w.  A block keeps a chunk of w in registers (MD_W doubles per
+// thread) and walks the whole basis over it in groups of MD_GROUP vectors, all loads of a group in flight at once;
+// each group ends in a warp reduction into the warp's own shared accumulators, so w and V are read exactly once.
+// partial[block][j], then the last block sums the partials in a fixed order (deterministic).
+constexpr int MD_W = 8;        // doubles of w per thread and chunk (as MD_W / 2 16-byte loads)
+constexpr int MD_GROUP = 4;
+// two consecutive doubles at p[i], p[i+1] (zero past the end); one 16-byte load when the vector allows it
+__device__ __forceinline__ double2 load2(const double *p, int64_t i, int64_t n, bool vec2)
 {
-  __shared__ double s_acc[(MD_CHUNK + 1) * (VT / 32)];
+  if (vec2 && i + 1 < n) return *reinterpret_cast<const double2 *>(p + i);
+  double2 r;
+  r.x = (i < n) ? p[i] : 0.0;
+  r.y = (i + 1 < n) ? p[i + 1] : 0.0;
+  return r;
+}
+__global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int k, const double *w, int64_t n,
+                                                      double *partial, unsigned int *counter, double *out, int vec2)
+{
+  __shared__ double s_acc[VT / 32][MD_CHUNK + 4];
+  __shared__ const double *s_v[MD_CHUNK];
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VT / 32;
-  for (int j = threadIdx.x; j < (k + 1) * nw; j += VT) s_acc[j] = 0.0;
+  for (int j = threadIdx.x; j < nw * (MD_CHUNK + 4); j += VT) (&s_acc[0][0])[j] = 0.0;
+  for (int j = threadIdx.x; j < k; j += VT) s_v[j] = V[j];
   __syncthreads();
-  // each block walks chunks of 4*VT elements; w chunk stays in registers while looping over the basis
-  const int64_t chunk = 4 * VT;
+  constexpr int NL = MD_W / 2;
+  const int64_t chunk = (int64_t)VT * MD_W;
   for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
-    double wr[4];
+    double2 ww[NL];
+    double wn = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t i = base + r * VT + threadIdx.x;
-      wr[r] = i < n ? w[i] : 0.0;
+    for (int r = 0; r < NL; ++r) {
+      ww[r] = load2(w, base + ((int64_t)r * VT + threadIdx.x) * 2, n, vec2);
+      wn = fma(ww[r].x, ww[r].x, fma(ww[r].y, ww[r].y, wn));
     }
-    for (int j = 0; j <= k; ++j) {
-      double a = 0.0;
-      if (j < k) {
-        const double *v = V[j];
+    for (int g = 0; g < k; g += MD_GROUP) {
+      double2 vv[MD_GROUP][NL];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int64_t i = base + r * VT + threadIdx.x;
-          if (i < n) a += v[i] * wr[r];
-        }
-      } else {
+      for (int jj = 0; jj < MD_GROUP; ++jj) {
+        const double *v = s_v[min(g + jj, k - 1)];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a += wr[r] * wr[r];
+        for (int r = 0; r < NL; ++r) vv[jj][r] = load2(v, base + ((int64_t)r * VT + threadIdx.x) * 2, n, vec2);
       }
-      a = warp_sum(a);
-      if (lane == 0) s_acc[j * nw + warp] += a;
+#pragma unroll
+      for (int jj = 0; jj < MD_GROUP; ++jj) {
+        double a = 0.0;
+#pragma unroll
+        for (int r = 0; r < NL; ++r) a = fma(vv[jj][r].x, ww[r].x, fma(vv[jj][r].y, ww[r].y, a));
+        a = warp_sum(a);
+        if (lane == 0 && g + jj < k) s_acc[warp][g + jj] += a;
+      }
     }
+    wn = warp_sum(wn);
+    if (lane == 0) s_acc[warp][k] += wn;
   }
   __syncthreads();
   for (int j = threadIdx.x; j <= k; j += VT) {
     double a = 0.0;
-    for (int q = 0; q < nw; ++q) a += s_acc[j * nw + q];
+    for (int q = 0; q < nw; ++q) a += s_acc[q][j];
     partial[(size_t)blockIdx.x * (k + 1) + j] = a;
   }
   __threadfence();
@@ -129,47 +149,48 @@ __global__ void __launch_bounds__(VT) k_multi_dot(const double *const *V, int k,
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int j = threadIdx.x; j <= k; j += VT) {
+    // one warp per result; lanes stride over the blocks' partials, then a shuffle tree: the order is fixed
+    for (int j = warp; j <= k; j += nw) {
       double a = 0.0;
-      for (unsigned bI = 0; bI < gridDim.x; ++bI) a += partial[(size_t)bI * (k + 1) + j];
-      out[j] = a;
+      for (unsigned bI = lane; bI < gridDim.x; bI += 32) a += partial[(size_t)bI * (k + 1) + j];
+      a = warp_sum(a);
+      if (lane == 0) out[j] = a;
     }
     if (threadIdx.x == 0) *counter = 0;
   }
 }
 
 // w -= sum_j coef[j] V[j]; out[0] = |w_new|^2
+constexpr int MA_UNROLL = 8;
 __global__ void __launch_bounds__(VT) k_multi_axpy(double *w, const double *const *V, const double *coef, int k, int64_t n,
-                                                    double *partial, unsigned int *counter, double *out)
+                                                    double *partial, unsigned int *counter, double *out, int vec2)
 {
   __shared__ double s_coef[MD_CHUNK];
+  __shared__ const double *s_v[MD_CHUNK];
   __shared__ double s_acc[VT / 32];
   __shared__ bool s_last;
-  for (int j = threadIdx.x; j < k; j += VT) s_coef[j] = coef[j];
+  for (int j = threadIdx.x; j < k; j += VT) { s_coef[j] = coef[j]; s_v[j] = V[j]; }
   __syncthreads();
   double nrm = 0.0;
-  const int64_t chunk = 4 * VT;
-  for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
-    double wr[4];
+  const int64_t stride = (int64_t)gridDim.x * VT * 2;
+  for (int64_t i = ((int64_t)blockIdx.x * VT + threadIdx.x) * 2; i < n; i += stride) {
+    double2 ww = load2(w, i, n, vec2);
+    int j = 0;
+    for (; j + MA_UNROLL <= k; j += MA_UNROLL) {
+      double2 vv[MA_UNROLL];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t i = base + r * VT + threadIdx.x;
-      wr[r] = i < n ? w[i] : 0.0;
+      for (int jj = 0; jj < MA_UNROLL; ++jj) vv[jj] = load2(s_v[j + jj], i, n, vec2);
+#pragma unroll
+      for (int jj = 0; jj < MA_UNROLL; ++jj) { const double cj = s_coef[j + jj]; ww.x = fma(-cj, vv[jj].x, ww.x); ww.y = fma(-cj, vv[jj].y, ww.y); }
     }
-    for (int j = 0; j < k; ++j) {
-      const double *v = V[j];
+    for (; j < k; ++j) {
+      const double2 vv = load2(s_v[j], i, n, vec2);
       const double cj = s_coef[j];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int64_t i = base + r * VT + threadIdx.x;
-        if (i < n) wr[r] -= cj * v[i];
-      }
+      ww.x = fma(-cj, vv.x, ww.x); ww.y = fma(-cj, vv.y, ww.y);
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t i = base + r * VT + threadIdx.x;
-      if (i < n) { w[i] = wr[r]; nrm += wr[r] * wr[r]; }
-    }
+    if (vec2 && i + 1 < n) *reinterpret_cast<double2 *>(w + i) = ww;
+    else { w[i] = ww.x; if (i + 1 < n) w[i + 1] = ww.y; }
+    nrm = fma(ww.x, ww.x, fma(ww.y, ww.y, nrm));
   }
   nrm = warp_sum(nrm);
   if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = nrm;
@@ -208,11 +229,27 @@ static double *scr_partial(smf_ctx *ctx) { return ctx->scratch + 128; }
 static unsigned int *scr_counter(smf_ctx *ctx) { return (unsigned int *)(ctx->scratch + 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1)); }
 static double **scr_ptrs(smf_ctx *ctx) { return (double **)(ctx->scratch + 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1) + 16); }
 
-static unsigned red_blocks(int64_t n)
+static int all_aligned16(const void *w, double *const *V, int k)
 {
-  int64_t b = (n + 4 * VT - 1) / (4 * VT);
+  uintptr_t m = (uintptr_t)w;
+  for (int j = 0; j < k; ++j) m |= (uintptr_t)V[j];
+  return (m & 15u) == 0 ? 1 : 0;
+}
+// persistent grids: never more blocks than are resident at once (a partial second wave would idle most SMs)
+template <class K> static unsigned red_blocks(K kernel, int64_t n)
+{
+  static int resident = 0;
+  if (resident == 0) {
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, VT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    resident = per_sm * sms;
+    if (resident > RED_BLOCKS) resident = RED_BLOCKS;
+  }
+  int64_t b = (n + 8 * VT - 1) / (8 * VT);
   if (b < 1) b = 1;
-  if (b > RED_BLOCKS) b = RED_BLOCKS;
+  if (b > resident) b = resident;
   return (unsigned)b;
 }
 
@@ -223,7 +260,8 @@ int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double 
   if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_dot: too many vectors");
   if (k > 0) SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
   { ProfScope prof(ctx, ctx->vec_bucket);
-  k_multi_dot<<<red_blocks(n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx)); }
+  k_multi_dot<<<red_blocks(k_multi_dot, n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx),
+                                                      ctx->md_vec2 = all_aligned16(w, V_host_ptrs, k)); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   if (sync) {
@@ -240,8 +278,9 @@ int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *
 {
   // pointer table already uploaded by vec_multi_dot
   { ProfScope prof(ctx, ctx->vec_bucket);
-  k_multi_axpy<<<red_blocks(n), VT, 0, ctx->stream>>>(w, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
-                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2); }
+  k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(w, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2,
+                                                       ctx->md_vec2 && ((uintptr_t)w & 15u) == 0); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (MD_CHUNK + 3), cudaMemcpyDeviceToHost, ctx->stream));
@@ -261,8 +300,9 @@ int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const dou
   SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
   SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 128, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
   { ProfScope prof(ctx, ctx->vec_bucket);
-  k_multi_axpy<<<red_blocks(n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
-                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2); }
+  k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2,
+                                                       all_aligned16(x, V_host_ptrs, k)); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   // the pinned staging area is reused by the next call: make sure the copies above have been consumed
