@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libsmf_b200.so")
 
 SMF_OK, SMF_ERR_INVALID, SMF_ERR_CUDA, SMF_ERR_UNSUPPORTED, SMF_NO_CONVERGENCE = 0, 1, 2, 3, 4
 SMF_ACTIVE = -1
+SMF_OPT_STRUCTURED_BRICKS, SMF_OPT_CUDA_GRAPHS = 0, 1
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
 
@@ -46,7 +47,7 @@ class SolveResult(ctypes.Structure):
 
 # every symbol include/smf_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "smf_create", "smf_destroy", "smf_last_error", "smf_set_stream", "smf_set_level", "smf_set_transfer",
+    "smf_create", "smf_destroy", "smf_last_error", "smf_set_option", "smf_set_stream", "smf_set_level", "smf_set_transfer",
     "smf_set_copy_indices", "smf_set_cell_data", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set",
     "smf_synchronize", "smf_vmult_stokes", "smf_vmult_A", "smf_vmult_BT", "smf_vmult_mass", "smf_vmult_stokes_host",
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",

@@ -182,7 +182,7 @@ template <int DIM> __host__ __device__ constexpr int round_q2(int n)
 // ---------------------------------------------------------------------------------------------------------
 struct CellParams {
   const int *batch_info;
-  const uint32_t *node_list_u; const uint16_t *cell_loc_u;
+  const uint32_t *node_list_u; const uint16_t *node_slot_u; const uint16_t *cell_loc_u; int list_stride_u;
   const uint32_t *node_list_p; const uint16_t *cell_loc_p;
   int max_nodes_u, max_nodes_p;
   const double *eta_t; int n_eta;     // lane-transposed table [batch][n_eta][32]
@@ -191,6 +191,15 @@ struct CellParams {
   const double *src_u, *src_p;
   double *dst_u, *dst_p;
 };
+
+// Loads whose issue order the compiler must keep (asm volatile): the staging code issues every index load of a thread,
+// then every value load, so a block exposes two memory latencies instead of two per staged item.
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t *p)
+{ uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_u16(const uint16_t *p)
+{ uint16_t v; asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
+__device__ __forceinline__ double ldg_f64(const double *p)
+{ double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
 
 // ---- line primitives (3 values along one direction) ---------------------------------------------------------
 // 2 D' (a, b, c): rows (-3, 4, -1), (-1, 0, 1), (1, -4, 3)
@@ -287,8 +296,10 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
   extern __shared__ double smem[];
   const int c = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
   const int *info = P.batch_info + (size_t)b * BATCH_INFO;
-  const int n_nodes_u = info[0], n_excl_u = info[1], n_nodes_p = info[2], n_excl_p = info[3], n_cells_b = info[4];
-  const int MU = P.max_nodes_u, MP = P.max_nodes_p;
+  // (a structured brick always has 9 x 9 x 5 nodes and 32 cells: no dependent load in front of the staging loads)
+  const int n_nodes_u = STRUCT ? 405 : info[0], n_excl_u = STRUCT ? 0 : info[1], n_cells_b = STRUCT ? SUB : info[4];
+  const int n_nodes_p = MODE != 0 ? info[2] : 0, n_excl_p = MODE != 0 ? info[3] : 0;
+  const int MU = STRUCT ? SB_SLOTS : P.max_nodes_u, MP = P.max_nodes_p;
   double *s_stage = smem;                              // [DIM][MU]: source values, later the accumulated result
   double *s_ex = s_stage + DIM * MU;                   // [npair][NN][32]
   double *s_stagep = s_ex + npair<DIM>() * NN * SUB;   // [MP]           (MODE != 0)
@@ -296,7 +307,8 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
   uint16_t *s_loc = reinterpret_cast<uint16_t *>(s_pex + (MODE != 0 ? DIM * NP * SUB : 0));   // [NN][32]
   uint16_t *s_locp = s_loc + NN * SUB;                 // [NP][32]       (MODE != 0)
 
-  const uint32_t *nlu = P.node_list_u + (size_t)b * MU;
+  const uint32_t *nlu = P.node_list_u + (size_t)b * P.list_stride_u;
+  const uint16_t *nsl = P.node_slot_u + (size_t)b * P.list_stride_u;   // (structured bricks only)
   const uint32_t *nlp = P.node_list_p + (size_t)b * MP;
   // ---- stage the batch's unique DoFs (constrained DoFs read as zero: read_dof_values semantics) and its slot map ----
   {
@@ -311,25 +323,34 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
       for (int j = threadIdx.x; j < NP * SUB / 2; j += NT) slp[j] = glp[j];
     }
   }
-  // all index loads of a thread first, then all value loads: two exposed memory latencies per block instead of 2 x SU
-  constexpr int SU = STRUCT ? 7 : (DIM == 3 ? 5 : 3);   // ceil(staged nodes of a brick / threads): 580 / 96, 405 / 96, 153 / 64
+  // One lane per (node, component), nodes in ascending DoF order: consecutive lanes read consecutive doubles wherever
+  // the batch's DoFs are contiguous in the vector.  All index loads of a thread first, then all value loads: two
+  // exposed memory latencies per block.
+  constexpr int SU = DIM == 3 ? 13 : 5;      // ceil(DIM * nodes of a structured brick / threads): 3 * 405 / 96, 2 * 153 / 64
+  const int n_items = DIM * n_nodes_u;
   if (MODE != 2)
-    for (int j0 = threadIdx.x; j0 < n_nodes_u; j0 += NT * SU) {
+    for (int t0 = threadIdx.x; t0 < n_items; t0 += NT * SU) {
       uint32_t e[SU];
-      double v[SU][DIM];
+      int sl[SU];
+      double v[SU];
 #pragma unroll
-      for (int i = 0; i < SU; ++i) e[i] = (j0 + i * NT < n_nodes_u) ? nlu[j0 + i * NT] : NODE_INVALID;
+      for (int i = 0; i < SU; ++i) {       // (items past the end repeat the last one: no predicated loads)
+        const int j = min(t0 + i * NT, n_items - 1) / DIM;
+        e[i] = ldg_u32(nlu + j);
+        sl[i] = STRUCT ? (int)ldg_u16(nsl + j) : j;
+      }
 #pragma unroll
-      for (int i = 0; i < SU; ++i)
+      for (int i = 0; i < SU; ++i) {
+        const int t = min(t0 + i * NT, n_items - 1), d = t - (t / DIM) * DIM;
+        const bool cons = (e[i] >> (NODE_FLAG_SHIFT + d)) & 1u;
+        v[i] = ldg_f64(P.src_u + (e[i] & NODE_IDX_MASK) + d);      // constrained DoFs are valid addresses, too
+        if (cons) v[i] = 0.0;
+      }
 #pragma unroll
-        for (int d = 0; d < DIM; ++d)
-          v[i][d] = ((e[i] >> (NODE_FLAG_SHIFT + d)) & 1u) ? 0.0 : P.src_u[(e[i] & NODE_IDX_MASK) + d];
-#pragma unroll
-      for (int i = 0; i < SU; ++i)
-        if (j0 + i * NT < n_nodes_u) {
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) s_stage[d * MU + j0 + i * NT] = v[i][d];
-        }
+      for (int i = 0; i < SU; ++i) {
+        const int t = t0 + i * NT, d = t - (t / DIM) * DIM;
+        if (t < n_items) s_stage[d * MU + sl[i]] = v[i];
+      }
     }
   if (MODE != 0)
     for (int j = threadIdx.x; j < n_nodes_p; j += NT) {
@@ -447,16 +468,24 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
   __syncthreads();
   // ---- flush: private nodes with plain stores, shared nodes with one RED per DoF; constrained DoFs get the
   //      unit diagonal of MatrixFreeOperators::Base (dst = src) ----
-  for (int j = threadIdx.x; j < n_nodes_u; j += NT) {
-    const uint32_t e = nlu[j];
-    if (STRUCT && e == NODE_INVALID) continue;
-    const uint32_t idx = e & NODE_IDX_MASK;
-    const bool excl = STRUCT ? !(e & NODE_SHARED_BIT) : (j < n_excl_u);
+  for (int t0 = threadIdx.x; t0 < n_items; t0 += NT * SU) {
+    uint32_t e[SU];
+    int sl[SU];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      if ((e >> (NODE_FLAG_SHIFT + d)) & 1u) P.dst_u[idx + d] = (MODE == 2) ? 0.0 : P.src_u[idx + d];
-      else if (excl) P.dst_u[idx + d] = s_stage[d * MU + j];
-      else atomicAdd(P.dst_u + idx + d, s_stage[d * MU + j]);
+    for (int i = 0; i < SU; ++i) {
+      const int j = min(t0 + i * NT, n_items - 1) / DIM;
+      e[i] = ldg_u32(nlu + j);
+      sl[i] = STRUCT ? (int)ldg_u16(nsl + j) : j;
+    }
+#pragma unroll
+    for (int i = 0; i < SU; ++i) {
+      const int t = t0 + i * NT, j = t / DIM, d = t - j * DIM;
+      if (t >= n_items) continue;
+      const uint32_t idx = e[i] & NODE_IDX_MASK;
+      const bool excl = STRUCT ? !(e[i] & NODE_SHARED_BIT) : (j < n_excl_u);
+      if ((e[i] >> (NODE_FLAG_SHIFT + d)) & 1u) P.dst_u[idx + d] = (MODE == 2) ? 0.0 : P.src_u[idx + d];
+      else if (excl) P.dst_u[idx + d] = s_stage[d * MU + sl[i]];
+      else atomicAdd(P.dst_u + idx + d, s_stage[d * MU + sl[i]]);
     }
   }
   if (MODE == 1)
@@ -668,67 +697,91 @@ template <int NPD> __device__ __forceinline__ Col1D pcol(int j)
   return {2, 1, 2, 0, 0.5, 1.0, 0.0};
 }
 
-// one thread per (parent, fine patch entry): interpolate the coarse cell function at that patch node; only the
-// owning parent writes (all parents would write the same value), so no atomics and no weights are needed.
-template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(128) prolongate_kernel(const TransferParams P)
+// One warp per parent cell.  Prolongation: the lanes stage the parent's coarse values (constrained ones as zero) in
+// shared memory, then every lane evaluates the coarse function at its patch nodes with the sparse tensor-product
+// rows; only the parent that owns a fine node writes it (all parents would write the same value), so no atomics
+// and no valence weights are needed.
+constexpr int TR_WARPS = 4;
+template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(32 * TR_WARPS) prolongate_kernel(const TransferParams P)
 {
   constexpr int NPP = 2 * NPD - 1;
   constexpr int NPATCH = DIM == 3 ? NPP * NPP * NPP : NPP * NPP;
   constexpr int NC = DIM == 3 ? NPD * NPD * NPD : NPD * NPD;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t par = t / NPATCH;
-  const int s = (int)(t % NPATCH);
+  __shared__ double s_c[TR_WARPS][NCOMP][NC];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t par = (int64_t)blockIdx.x * TR_WARPS + w;
   if (par >= P.n_parents) return;
-  const uint32_t pe = P.patch[par * NPATCH + s];
-  if (!(pe >> 31)) return;
-  const Row1D rx = prow<NPD>(s % NPP), ry = prow<NPD>((s / NPP) % NPP);
-  const Row1D rz = DIM == 3 ? prow<NPD>(s / (NPP * NPP)) : Row1D{0, 1, 1.0, 0.0, 0.0};
-  const uint32_t *cn = P.coarse_nodes + par * NC;
-  double acc[NCOMP];
+  if (lane < NC) {
+    const uint32_t ce = P.coarse_nodes[par * NC + lane];
+    const uint32_t ci = ce & NODE_IDX_MASK;
 #pragma unroll
-  for (int c = 0; c < NCOMP; ++c) acc[c] = 0.0;
-  for (int kz = 0; kz < rz.count; ++kz)
-    for (int ky = 0; ky < ry.count; ++ky) {
-      const double wzy = rz.w(kz) * ry.w(ky);
-      const int base = (DIM == 3 ? (rz.first + kz) * NPD * NPD : 0) + (ry.first + ky) * NPD + rx.first;
-      for (int kx = 0; kx < rx.count; ++kx) {
-        const double w = wzy * rx.w(kx);
-        const uint32_t ce = cn[base + kx];
-        const uint32_t ci = ce & NODE_IDX_MASK;
+    for (int c = 0; c < NCOMP; ++c) {
+      const bool cons = (NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u);
+      s_c[w][c][lane] = cons ? 0.0 : P.src[ci + c];
+    }
+  }
+  __syncwarp();
+  constexpr int ROUNDS = (NPATCH + 31) / 32;
+  uint32_t pe[ROUNDS];
 #pragma unroll
-        for (int c = 0; c < NCOMP; ++c) {
-          const bool cons = (NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u);
-          if (!cons) acc[c] = fma(w, P.src[ci + c], acc[c]);
+  for (int r = 0; r < ROUNDS; ++r) pe[r] = (lane + 32 * r < NPATCH) ? P.patch[par * NPATCH + lane + 32 * r] : 0u;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    if (!(pe[r] >> 31)) continue;
+    const int s = lane + 32 * r;
+    const Row1D rx = prow<NPD>(s % NPP), ry = prow<NPD>((s / NPP) % NPP);
+    const Row1D rz = DIM == 3 ? prow<NPD>(s / (NPP * NPP)) : Row1D{0, 1, 1.0, 0.0, 0.0};
+    double acc[NCOMP];
+#pragma unroll
+    for (int c = 0; c < NCOMP; ++c) acc[c] = 0.0;
+    for (int kz = 0; kz < rz.count; ++kz)
+      for (int ky = 0; ky < ry.count; ++ky) {
+        const double wzy = rz.w(kz) * ry.w(ky);
+        const int base = (DIM == 3 ? (rz.first + kz) * NPD * NPD : 0) + (ry.first + ky) * NPD + rx.first;
+        for (int kx = 0; kx < rx.count; ++kx) {
+          const double wt = wzy * rx.w(kx);
+#pragma unroll
+          for (int c = 0; c < NCOMP; ++c) acc[c] = fma(wt, s_c[w][c][base + kx], acc[c]);
         }
       }
-    }
-  const uint32_t fi = pe & NODE_IDX_MASK;
+    const uint32_t fi = pe[r] & NODE_IDX_MASK;
 #pragma unroll
-  for (int c = 0; c < NCOMP; ++c) {
-    if (P.add) P.dst[fi + c] += acc[c];
-    else P.dst[fi + c] = acc[c];
+    for (int c = 0; c < NCOMP; ++c) {
+      if (P.add) P.dst[fi + c] += acc[c];
+      else P.dst[fi + c] = acc[c];
+    }
   }
 }
 
-// one thread per (parent, coarse node): gather the owned fine patch values with the transposed weights and add
-// into the coarse vector (coarse Dirichlet DoFs stay untouched = zero).
-template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(128) restrict_kernel(const TransferParams P)
+// Restriction (transpose): the lanes stage the fine patch values this parent owns, then lane j < NC gathers them with
+// the transposed rows and adds into coarse node j (coarse Dirichlet DoFs stay untouched = zero).
+template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(32 * TR_WARPS) restrict_kernel(const TransferParams P)
 {
   constexpr int NPP = 2 * NPD - 1;
   constexpr int NPATCH = DIM == 3 ? NPP * NPP * NPP : NPP * NPP;
   constexpr int NC = DIM == 3 ? NPD * NPD * NPD : NPD * NPD;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t par = t / NC;
-  const int j = (int)(t % NC);
+  __shared__ double s_f[TR_WARPS][NCOMP][NPATCH];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t par = (int64_t)blockIdx.x * TR_WARPS + w;
   if (par >= P.n_parents) return;
-  const uint32_t ce = P.coarse_nodes[par * NC + j];
-  bool any = false;
+  constexpr int ROUNDS = (NPATCH + 31) / 32;
+  uint32_t pe[ROUNDS];
 #pragma unroll
-  for (int c = 0; c < NCOMP; ++c) any |= !((NCOMP == 1) ? (ce >> 31) : ((ce >> (NODE_FLAG_SHIFT + c)) & 1u));
-  if (!any) return;
+  for (int r = 0; r < ROUNDS; ++r) pe[r] = (lane + 32 * r < NPATCH) ? P.patch[par * NPATCH + lane + 32 * r] : 0u;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r)
+    if (lane + 32 * r < NPATCH) {
+      const bool own = pe[r] >> 31;
+      const uint32_t fi = pe[r] & NODE_IDX_MASK;
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) s_f[w][c][lane + 32 * r] = own ? P.src[fi + c] : 0.0;
+    }
+  __syncwarp();
+  if (lane >= NC) return;
+  const int j = lane;
+  const uint32_t ce = P.coarse_nodes[par * NC + j];
   const Col1D cx = pcol<NPD>(j % NPD), cy = pcol<NPD>((j / NPD) % NPD);
   const Col1D cz = DIM == 3 ? pcol<NPD>(j / (NPD * NPD)) : Col1D{1, 0, 0, 0, 1.0, 0.0, 0.0};
-  const uint32_t *pt = P.patch + par * NPATCH;
   double acc[NCOMP];
 #pragma unroll
   for (int c = 0; c < NCOMP; ++c) acc[c] = 0.0;
@@ -736,17 +789,10 @@ template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(128) re
     for (int ky = 0; ky < cy.count; ++ky) {
       const double wzy = cz.w(kz) * cy.w(ky);
       const int base = (DIM == 3 ? cz.pos(kz) * NPP * NPP : 0) + cy.pos(ky) * NPP;
+      for (int kx = 0; kx < cx.count; ++kx) {
+        const double wt = wzy * cx.w(kx);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        if (kx < cx.count) {
-          const uint32_t pe = pt[base + cx.pos(kx)];
-          if (pe >> 31) {
-            const double w = wzy * cx.w(kx);
-            const uint32_t fi = pe & NODE_IDX_MASK;
-#pragma unroll
-            for (int c = 0; c < NCOMP; ++c) acc[c] = fma(w, P.src[fi + c], acc[c]);
-          }
-        }
+        for (int c = 0; c < NCOMP; ++c) acc[c] = fma(wt, s_f[w][c][base + cx.pos(kx)], acc[c]);
       }
     }
   const uint32_t ci = ce & NODE_IDX_MASK;
@@ -762,7 +808,7 @@ static CellParams make_params(const LevelDev &L)
 {
   CellParams P{};
   P.batch_info = L.batch_info;
-  P.node_list_u = L.node_list_u; P.cell_loc_u = L.cell_loc_u;
+  P.node_list_u = L.node_list_u; P.node_slot_u = L.node_slot_u; P.cell_loc_u = L.cell_loc_u; P.list_stride_u = L.list_stride_u;
   P.node_list_p = L.node_list_p; P.cell_loc_p = L.cell_loc_p;
   P.max_nodes_u = L.max_nodes_u; P.max_nodes_p = L.max_nodes_p;
   P.eta_t = L.eta; P.n_eta = L.n_eta;
@@ -891,18 +937,10 @@ int launch_diag(smf_ctx *ctx, LevelDev &L)
 template <int DIM, int NPD, int NCOMP>
 static void launch_transfer_t(smf_ctx *ctx, const TransferParams &P, bool prolong)
 {
-  constexpr int NPP = 2 * NPD - 1;
-  constexpr int NPATCH = DIM == 3 ? NPP * NPP * NPP : NPP * NPP;
-  constexpr int NC = DIM == 3 ? NPD * NPD * NPD : NPD * NPD;
-  const int bs = 128;
+  const unsigned grid = (unsigned)((P.n_parents + TR_WARPS - 1) / TR_WARPS);
   ProfScope prof(ctx, B_TRANSFER);
-  if (prolong) {
-    const int64_t nt = P.n_parents * NPATCH;
-    prolongate_kernel<DIM, NPD, NCOMP><<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(P);
-  } else {
-    const int64_t nt = P.n_parents * NC;
-    restrict_kernel<DIM, NPD, NCOMP><<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(P);
-  }
+  if (prolong) prolongate_kernel<DIM, NPD, NCOMP><<<grid, 32 * TR_WARPS, 0, ctx->stream>>>(P);
+  else restrict_kernel<DIM, NPD, NCOMP><<<grid, 32 * TR_WARPS, 0, ctx->stream>>>(P);
   ctx->launches++;
 }
 

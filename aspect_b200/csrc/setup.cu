@@ -27,7 +27,7 @@ template <class T> static int upload(smf_ctx *ctx, T **dev, const std::vector<T>
 
 static void free_level(LevelDev &L)
 {
-  cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
+  cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
   cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
   cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M);
   L = LevelDev();
@@ -106,7 +106,7 @@ static void build_batches(const std::vector<uint32_t> &nodes, int64_t n_cells, i
 // Structured-brick staging layout of the velocity nodes (3D): succeeds when every batch is a full 4x4x2 Morton brick
 // whose cell maps are consistent with a 9x9x5 lattice.  node_list[b][sb_slot] = node entry | NODE_SHARED_BIT.
 static bool build_structured3(const std::vector<uint32_t> &nodes, int64_t n_cells, int64_t n_index_space,
-                              std::vector<uint32_t> &node_list)
+                              std::vector<uint32_t> &node_list, std::vector<uint16_t> &node_slot)
 {
   if (n_cells % BATCH_CELLS != 0) return false;
   const int64_t nb = n_cells / BATCH_CELLS;
@@ -135,15 +135,25 @@ static bool build_structured3(const std::vector<uint32_t> &nodes, int64_t n_cell
     for (uint32_t idx : batch_nodes) { seen_at[idx] = -1; if (touch[idx] < 2) ++touch[idx]; }
     if (!ok) return false;
   }
-  node_list.assign((size_t)nb * SB_SLOTS, NODE_INVALID);
+  // list entries in ascending DoF-index order (coalesced global access), each with its staging slot
+  node_list.assign((size_t)nb * SB_LIST, NODE_INVALID);
+  node_slot.assign((size_t)nb * SB_LIST, 0);
+  std::vector<std::pair<uint32_t, uint16_t>> ent(NL);
   for (int64_t b = 0; b < nb; ++b) {
     const uint32_t *L = lat.data() + (size_t)b * NL;
+    int m = 0;
     for (int Z = 0; Z < 5; ++Z)
       for (int Y = 0; Y < 9; ++Y)
         for (int X = 0; X < 9; ++X) {
           const uint32_t e = L[X + 9 * (Y + 9 * Z)];
-          node_list[(size_t)b * SB_SLOTS + sb_slot(X, Y, Z)] = e | (touch[e & NODE_IDX_MASK] > 1 ? NODE_SHARED_BIT : 0u);
+          ent[m++] = {e | (touch[e & NODE_IDX_MASK] > 1 ? NODE_SHARED_BIT : 0u), (uint16_t)sb_slot(X, Y, Z)};
         }
+    std::sort(ent.begin(), ent.end(), [](const std::pair<uint32_t, uint16_t> &a, const std::pair<uint32_t, uint16_t> &c) {
+      return (a.first & NODE_IDX_MASK) < (c.first & NODE_IDX_MASK); });
+    for (int i = 0; i < NL; ++i) {
+      node_list[(size_t)b * SB_LIST + i] = ent[i].first;
+      node_slot[(size_t)b * SB_LIST + i] = ent[i].second;
+    }
   }
   return true;
 }
@@ -200,6 +210,15 @@ void smf_destroy(smf_ctx *ctx)
 }
 
 const char *smf_last_error(const smf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int smf_set_option(smf_ctx *ctx, int option, int value)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  if (option == SMF_OPT_STRUCTURED_BRICKS) ctx->allow_structured = value ? 1 : 0;
+  else if (option == SMF_OPT_CUDA_GRAPHS) { ctx->use_graphs = value ? 1 : 0; ctx->graph_A_stale = ctx->graph_S_stale = true; }
+  else return ctx->fail(SMF_ERR_INVALID, "unknown option");
+  return SMF_OK;
+}
 
 int smf_set_stream(smf_ctx *ctx, void *cuda_stream)
 {
@@ -270,13 +289,16 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   build_batches(nodes_u, L.n_cells, NN, L.n_u, round_u, 1 << dim, nl_u, loc_u, nn_u, ne_u, L.max_nodes_u, safe_u);
   build_batches(nodes_p, L.n_cells, NP, L.n_p, round_p, NP, nl_p, loc_p, nn_p, ne_p, L.max_nodes_p, safe_p);
   if (L.max_nodes_u > 65535 || L.max_nodes_p > 65535) return ctx->fail(SMF_ERR_UNSUPPORTED, "batch too large for 16-bit slots");
+  std::vector<uint16_t> slot_u(2, 0);
+  L.list_stride_u = L.max_nodes_u;
   if (dim == 3 && ctx->allow_structured) {
     std::vector<uint32_t> nl_s;
-    if (build_structured3(nodes_u, L.n_cells, L.n_u, nl_s)) {
+    if (build_structured3(nodes_u, L.n_cells, L.n_u, nl_s, slot_u)) {
       L.structured = 1;
       nl_u.swap(nl_s);
       L.max_nodes_u = SB_SLOTS;
-      for (size_t b = 0; b < nn_u.size(); ++b) { nn_u[b] = SB_SLOTS; ne_u[b] = 0; }
+      L.list_stride_u = SB_LIST;
+      for (size_t b = 0; b < nn_u.size(); ++b) { nn_u[b] = 9 * 9 * 5; ne_u[b] = 0; }
       loc_u.assign(2, 0);                    // slots are computed in the kernel
       safe_u = true;
     }
@@ -295,6 +317,7 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   int e;
   if ((e = upload(ctx, &L.batch_info, info, &L.bytes))) return e;
   if ((e = upload(ctx, &L.node_list_u, nl_u, &L.bytes))) return e;
+  if ((e = upload(ctx, &L.node_slot_u, slot_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.node_list_p, nl_p, &L.bytes))) return e;
   if ((e = upload(ctx, &L.cell_loc_u, loc_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.cell_loc_p, loc_p, &L.bytes))) return e;

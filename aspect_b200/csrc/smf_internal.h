@@ -46,6 +46,7 @@ __host__ __device__ constexpr int sb_offset(int v, int ox, int oy, int oz)
 __host__ __device__ constexpr int sb_slot(int X, int Y, int Z)
 { return sb_class_base(sb_variant(X & 1, Y & 1), Z & 1) + sb_offset(sb_variant(X & 1, Y & 1), X >> 1, Y >> 1, Z >> 1); }
 constexpr int SB_SLOTS = 580;   // = sb_class_base(3, 1) + sb_class_size(3, 1)
+constexpr int SB_LIST = 408;    // node-list entries per structured brick (9 * 9 * 5 = 405, padded)
 static_assert(sb_class_base(3, 1) + sb_class_size(3, 1) == SB_SLOTS, "structured brick layout size");
 // brick coordinates of lane l (Morton order inside the batch: x0 y0 z0 x1 y1)
 __host__ __device__ constexpr int sb_x(int l) { return (l & 1) | (((l >> 3) & 1) << 1); }
@@ -63,7 +64,9 @@ struct LevelDev {
   int safe_rounds = 1;                        // 1: scatter rounds are collision-free inside every sub-batch
   int structured = 0;                         // 1: every batch is a structured brick (velocity staging by sb_slot)
   int *batch_info = nullptr;                  // [n_batches][BATCH_INFO]
-  uint32_t *node_list_u = nullptr;            // [n_batches][max_nodes_u]  exclusive nodes first
+  uint32_t *node_list_u = nullptr;            // [n_batches][list_stride_u]  ascending DoF index (general: exclusive nodes first)
+  uint16_t *node_slot_u = nullptr;            // [n_batches][list_stride_u]  structured bricks: staging slot of each list entry
+  int list_stride_u = 0;                      // entries per batch in node_list_u (general path: = max_nodes_u)
   uint32_t *node_list_p = nullptr;            // [n_batches][max_nodes_p]
   uint16_t *cell_loc_u = nullptr;             // [n_batches][KSUB][3^dim][SUB]
   uint16_t *cell_loc_p = nullptr;             // [n_batches][KSUB][2^dim][SUB]

@@ -67,6 +67,8 @@ class StokesMatrixFreeHandler:
         self.ctx = None
         self.hier = None
         self.minimum_viscosity = self.maximum_viscosity = None
+        self.allow_structured_bricks = True      # implementation switches (smf_set_option); tests exercise both paths
+        self.use_cuda_graphs = True
         # "Solver parameters/Stokes solver parameters" (names verbatim from source/simulator/parameters.cc:439-584)
         self.parameters = {
             "Linear solver tolerance": 1e-7,
@@ -117,6 +119,8 @@ class StokesMatrixFreeHandler:
         if rc != 0:
             raise SmfError(rc, "smf_create failed: a CUDA device is required (no CPU fallback)")
         self.ctx = ctx
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_STRUCTURED_BRICKS, int(self.allow_structured_bricks)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CUDA_GRAPHS, int(self.use_cuda_graphs)))
         self._keep = []
         for l in list(range(n_levels)) + [SMF_ACTIVE]:
             L = hierarchy.levels[l] if l >= 0 else hierarchy.active

@@ -46,6 +46,10 @@ int smf_create(const smf_config *cfg, smf_ctx **out);
 void smf_destroy(smf_ctx *ctx);
 /* message of the last failing call (replaces the C++ exception text) */
 const char *smf_last_error(const smf_ctx *ctx);
+/* implementation switches (all on by default); set before smf_set_level */
+#define SMF_OPT_STRUCTURED_BRICKS 0   /* conflict-free staging layout for batches that are 4x4x2 Morton bricks */
+#define SMF_OPT_CUDA_GRAPHS 1         /* replay the coarse-level part of the V-cycles from CUDA graphs */
+int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
 int smf_set_stream(smf_ctx *ctx, void *cuda_stream);
 

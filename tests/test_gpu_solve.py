@@ -12,7 +12,7 @@ import pytest
 
 from oracle import assembled, coeff, mesh as omesh, postprocess, solver as osolver
 from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
-from util import oracle_backend, rel, seeded
+from util import golden, oracle_backend, rel, seeded
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +49,8 @@ def test_nsinker_r2_goldens(averaging, golden_its, golden_range):
     sol, out = h.solve(rhs)
     ohier, ob, s, oout = _oracle_solve(3, 2, "zero", eta_q, averaging, ps, rhs, 1e-6)
     assert out["converged"]
+    gold = golden("nsinker_gmg_gc" if golden_its == 21 else "nsinker_gmg_no_avg")
+    assert gold["stokes_iterations_cheap_expensive"][0][0] == golden_its and gold["dofs_u_p"][0] == [2187, 125]
     assert abs(out["iterations"] - golden_its) <= 1
     assert out["iterations"] == oout["iterations"]
     assert out["n_A_preconditioner"] == oout["n_prec"] and out["n_S_preconditioner"] == oout["n_prec"]
@@ -71,6 +73,9 @@ def test_solcx_goldens(R, golden_its, golden_err):
     hier, h, eta_q, rhs, ps = _gpu_problem(2, R, "tangential", benchmarks.solcx_problem, avg, 1e-7)
     assert abs(ps - 1e5) < 1e-6
     sol, out = h.solve(rhs)
+    gold = golden(f"sol_cx_{R}_gmg")
+    assert gold["stokes_iterations_cheap_expensive"][0][0] == golden_its
+    assert tuple(float(x) for x in gold["errors_uL1_pL1_uL2_pL2"][0]) == golden_err
     assert out["converged"] and out["iterations"] == golden_its
     ohier, ob, s, oout = _oracle_solve(2, R, "tangential", eta_q, avg, ps, rhs, 1e-7)
     # free slip on all sides: pressure defined up to a constant; compare after the reference's default

@@ -1,7 +1,8 @@
 """Pin the oracle against the reference's own golden outputs (CPU only).
 
 Goldens: /root/reference/tests/{sol_cx_2_gmg,sol_cx_4_gmg,sol_cx_4_gmg_no_avg,nsinker_gmg_gc,nsinker_gmg_no_avg}/screen-output
-(deal.II 9.6; values copied into this file, nothing is read from /root/reference at run time).
+(deal.II 9.6; extracted once into tests/golden/reference_screen_output.json by tools/extract_goldens.py -- nothing is
+read from /root/reference at run time).
 The assembled-matrix backend is independent of any matrix-free code; the C matrix-free backend is then
 checked against it operator by operator.
 """
@@ -11,6 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import assembled, coeff, cpu, mesh, postprocess, solver
+from util import golden
 
 HAVE_SOLCX_REF = os.path.exists(os.path.join(os.path.dirname(postprocess.__file__), "_ref", "libsolcx.so"))
 
@@ -30,18 +32,22 @@ def _nsinker(R, avg, backend, n_sinkers=4):
 
 @pytest.mark.parametrize("backend", [solver.AssembledBackend, cpu.backend_from_hierarchy], ids=["assembled", "matrix_free_c"])
 def test_nsinker_gmg_goldens(backend):
+    g = golden("nsinker_gmg_gc")                                           # mesh 1 of the test
     act, emin, emax, out = _nsinker(2, "harmonic", backend)
-    assert (act.n_u, act.n_p) == (2187, 125)                               # "2,187+125"
-    assert f"{emin:.6g} - {emax:.6g}" == "0.01 - 0.198921"                 # "Viscosity range"
-    assert out["iterations"] == 21 and out["n_prec"] == 22                 # "21+0", 22 V-cycles
+    assert [act.n_u, act.n_p] == g["dofs_u_p"][0] == [2187, 125]           # "2,187+125"
+    assert [float(f"{emin:.6g}"), float(f"{emax:.6g}")] == g["viscosity_range"][0] == [0.01, 0.198921]   # "Viscosity range"
+    assert out["iterations"] == g["stokes_iterations_cheap_expensive"][0][0] == 21                         # "21+0"
+    assert out["n_prec"] == g["A_preconditioner_applications"][0] == g["schur_preconditioner_applications"][0] == 22
+    g = golden("nsinker_gmg_no_avg")
     act, emin, emax, out = _nsinker(2, "none", backend)
-    assert f"{emin:.6g} - {emax:.6g}" == "0.01 - 100"
-    assert abs(out["iterations"] - 172) <= 1                               # "172+0" (+-1: App. D6)
-    assert out["n_prec"] == out["iterations"] + 2                          # 174 = 172 + one per restart cycle
+    assert [float(f"{emin:.6g}"), float(f"{emax:.6g}")] == g["viscosity_range"][0] == [0.01, 100.0]
+    assert abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 1                      # "172+0" (+-1: App. D6)
+    assert g["A_preconditioner_applications"][0] == 174 and out["n_prec"] == out["iterations"] + 2         # one extra per restart cycle
 
 
-GOLD_SOLCX = {2: (162, 25, 11, "7.964441e-05, 1.174943e-01, 1.069688e-04, 1.192654e-01"),
-              4: (2178, 289, 15, "1.125999e-06, 1.101883e-01, 1.670011e-06, 1.106214e-01")}
+def _gold_solcx(R, avg):
+    g = golden({(2, "harmonic"): "sol_cx_2_gmg", (4, "harmonic"): "sol_cx_4_gmg", (4, "none"): "sol_cx_4_gmg_no_avg"}[(R, avg)])
+    return g["dofs_u_p"][0][0], g["dofs_u_p"][0][1], g["stokes_iterations_cheap_expensive"][0][0], ", ".join(g["errors_uL1_pL1_uL2_pL2"][0])
 
 
 @pytest.mark.parametrize("R", [2, 4])
@@ -61,7 +67,8 @@ def test_solcx_goldens(R, avg):
     rhs = np.concatenate([f, np.zeros(act.n_p)])
     s = solver.BlockGMGStokes(be)
     out = s.solve(rhs, tol_rel=1e-7, restart=100, max_its=1000)
-    nu, npp, its, errs = GOLD_SOLCX[R]
+    nu, npp, its, errs = _gold_solcx(R, avg)
+    assert (nu, npp, its) == {2: (162, 25, 11), 4: (2178, 289, 15)}[R]
     assert (act.n_u, act.n_p) == (nu, npp)
     assert out["iterations"] == its and out["n_prec"] == its + 1
     assert s.solve(rhs, x0=out["x"], tol_rel=1e-7)["iterations"] == 0      # "0+0 iterations"

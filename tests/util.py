@@ -1,4 +1,7 @@
 """Shared helpers of the parity tests (test infrastructure)."""
+import json
+import os
+
 import numpy as np
 
 from oracle import coeff, cpu, mesh
@@ -18,3 +21,16 @@ def oracle_backend(hier, eta_q, averaging, ps, bc):
 
 def seeded(n, seed):
     return np.random.default_rng(seed).uniform(-1.0, 1.0, size=n)
+
+
+_GOLDEN = None
+
+
+def golden(test):
+    """Pinned values of the reference's own test `test` (tests/golden/reference_screen_output.json, written by
+    tools/extract_goldens.py from /root/reference/tests/<test>/screen-output)."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_screen_output.json")) as f:
+            _GOLDEN = json.load(f)
+    return _GOLDEN[test]
