@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmf_b200.so")
-SOURCES = ["operators.cu", "vecops.cu", "setup.cu", "solver.cu"]
+SOURCES = ["operators.cu", "vecops.cu", "setup.cu", "solver.cu", "comm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas", "-v"]
 
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on " + src)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

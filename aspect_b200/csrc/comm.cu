@@ -1,0 +1,310 @@
+// Distributed vectors: one context per rank/GPU, one subdomain (a range of coarse-cell trees) per rank.
+//
+// Replaces what deal.II's LinearAlgebra::distributed::Vector / Utilities::MPI::Partitioner do around every cell loop
+// of the reference (update_ghost_values before, compress(add) after: matrix_free_operators.cc:626, 724, 856, 1063;
+// explicit calls stokes_matrix_free_local_smoothing.cc:645, 746, 1407) and the MPI_Allreduce inside every dot product.
+//
+// Layout: every rank stores ALL DoFs its cells touch; a DoF on a subdomain interface therefore exists on every rank
+// that touches it, and all copies are kept equal ("consistent").  Point-wise vector updates preserve that by
+// construction; an operator application produces per-rank partial sums on the interface, which one exchange turns
+// into the full sum on every copy (compress(add) and update_ghost_values in a single step).  The sum is taken in
+// ascending rank order on every rank, so the copies stay BITWISE equal.  Inner products weight every DoF with
+// 1 / (number of ranks sharing it) and finish with an all-reduce.
+//
+// Transport: NCCL send/recv groups over NVLink for the interface values, ncclAllReduce for the inner products.
+// NCCL is bound at run time (dlopen) so that the single-GPU library has no NCCL dependency.
+#include "smf_internal.h"
+#include <algorithm>
+#include <dlfcn.h>
+#include <map>
+#include <nccl.h>
+
+namespace smf {
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api(std::string *why)
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // the copy PyTorch already loaded wins (same SONAME); otherwise the system library
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.Send = (decltype(api.Send))dlsym(h, "ncclSend");
+      api.Recv = (decltype(api.Recv))dlsym(h, "ncclRecv");
+      api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv && api.GroupStart &&
+          api.GroupEnd && api.GetErrorString)
+        api.handle = h;
+    }
+  }
+  if (!api.handle) {
+    if (why) *why = "libnccl.so.2 could not be loaded (needed for more than one rank)";
+    return nullptr;
+  }
+  return &api;
+}
+
+#define SMF_NCCL(call)                                                                            \
+  do {                                                                                            \
+    ncclResult_t r__ = (call);                                                                    \
+    if (r__ != ncclSuccess)                                                                       \
+      return ctx->fail(SMF_ERR_CUDA, std::string(#call) + ": " + nccl_api(nullptr)->GetErrorString(r__)); \
+  } while (0)
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+__global__ void k_pack(double *buf, const double *vec, const uint32_t *idx, int64_t n_nodes, int ncomp)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes * ncomp) return;
+  const int64_t i = t / ncomp;
+  const int c = (int)(t - i * ncomp);
+  buf[t] = vec[idx[i] + c];
+}
+// every copy of an interface DoF := sum of all ranks' partial values, added in ascending rank order.
+// if_src[e] >= 0: position (node) in the receive buffer; -1: this rank's own value.  Bit (29 + c) of if_idx marks a
+// constrained component: its copies already agree (unit diagonal of MatrixFreeOperators::Base) and are left alone.
+__global__ void k_accumulate(double *vec, const double *recv, const uint32_t *if_idx, const int *if_ptr, const int *if_src,
+                             int64_t n_if, int ncomp)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_if * ncomp) return;
+  const int64_t i = t / ncomp;
+  const int c = (int)(t - i * ncomp);
+  const uint32_t e = if_idx[i];
+  if ((e >> (NODE_FLAG_SHIFT + c)) & 1u) return;
+  double *p = vec + (e & NODE_IDX_MASK) + c;
+  double sum = 0.0;
+  for (int k = if_ptr[i]; k < if_ptr[i + 1]; ++k) {
+    const int s = if_src[k];
+    sum += (s < 0) ? *p : recv[(int64_t)s * ncomp + c];
+  }
+  *p = sum;
+}
+__global__ void k_mod11_gid(double *x, const int64_t *gid, double mean, int64_t n)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = (double)(gid[i] % 11) - mean;
+}
+
+void free_exchange(ExchangeDev &E)
+{
+  cudaFree(E.send_idx); cudaFree(E.send_buf); cudaFree(E.recv_buf); cudaFree(E.if_idx); cudaFree(E.if_ptr); cudaFree(E.if_src);
+  cudaFree(E.weights); cudaFree(E.gid);
+  E = ExchangeDev();
+}
+
+// one exchange: pack -> grouped send/recv with every neighbour -> rank-ordered accumulation
+int exchange_add(smf_ctx *ctx, ExchangeDev &E, double *vec)
+{
+  if (ctx->world == 1 || E.n_send == 0) return SMF_OK;
+  NcclApi *api = nccl_api(&ctx->err);
+  if (!api || !ctx->comm) return ctx->fail(SMF_ERR_INVALID, "exchange without a communicator (smf_comm_init)");
+  ProfScope prof(ctx, B_EXCHANGE);
+  const int64_t n = E.n_send * E.ncomp;
+  k_pack<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(E.send_buf, vec, E.send_idx, E.n_send, E.ncomp);
+  ctx->launches++;
+  SMF_NCCL(api->GroupStart());
+  for (size_t k = 0; k < E.ranks.size(); ++k) {
+    const size_t cnt = (size_t)E.counts[k] * E.ncomp, off = (size_t)E.offsets[k] * E.ncomp;
+    SMF_NCCL(api->Send(E.send_buf + off, cnt, ncclDouble, E.ranks[k], (ncclComm_t)ctx->comm, ctx->stream));
+    SMF_NCCL(api->Recv(E.recv_buf + off, cnt, ncclDouble, E.ranks[k], (ncclComm_t)ctx->comm, ctx->stream));
+  }
+  SMF_NCCL(api->GroupEnd());
+  const int64_t m = E.n_if * E.ncomp;
+  k_accumulate<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(vec, E.recv_buf, E.if_idx, E.if_ptr, E.if_src, E.n_if, E.ncomp);
+  ctx->launches++;
+  ctx->exchanges++;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
+// sum of `count` doubles at `dev` over all ranks (in place, stream ordered)
+int allreduce_sum(smf_ctx *ctx, double *dev, int count)
+{
+  if (ctx->world == 1) return SMF_OK;
+  NcclApi *api = nccl_api(&ctx->err);
+  if (!api || !ctx->comm) return ctx->fail(SMF_ERR_INVALID, "all-reduce without a communicator (smf_comm_init)");
+  SMF_NCCL(api->AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  return SMF_OK;
+}
+
+int start_vector_mod11(smf_ctx *ctx, const ExchangeDev &E, double *x, int64_t n)
+{
+  k_mod11_gid<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, E.gid, E.gid_mean, n);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
+}  // namespace smf
+
+using namespace smf;
+
+extern "C" {
+
+int smf_comm_get_unique_id(char *id)
+{
+  if (!id) return SMF_ERR_INVALID;
+  NcclApi *api = nccl_api(nullptr);
+  if (!api) return SMF_ERR_UNSUPPORTED;
+  ncclUniqueId u;
+  if (api->GetUniqueId(&u) != ncclSuccess) return SMF_ERR_CUDA;
+  memcpy(id, u.internal, SMF_UNIQUE_ID_BYTES);
+  return SMF_OK;
+}
+
+int smf_comm_init(smf_ctx *ctx, int rank, int world, const char *id)
+{
+  if (!ctx || world < 1 || rank < 0 || rank >= world) return SMF_ERR_INVALID;
+  ctx->rank = rank; ctx->world = world;
+  if (world == 1) return SMF_OK;
+  if (!id) return ctx->fail(SMF_ERR_INVALID, "unique id missing");
+  NcclApi *api = nccl_api(&ctx->err);
+  if (!api) return SMF_ERR_UNSUPPORTED;
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  ncclUniqueId u;
+  memcpy(u.internal, id, SMF_UNIQUE_ID_BYTES);
+  ncclComm_t comm = nullptr;
+  SMF_NCCL(api->CommInitRank(&comm, world, u, rank));
+  ctx->comm = comm;
+  ctx->use_graphs = 0;      // (NCCL calls inside the V-cycle graphs are not enabled yet)
+  return SMF_OK;
+}
+
+void smf_comm_destroy_internal(smf_ctx *ctx)
+{
+  if (ctx->comm) {
+    NcclApi *api = nccl_api(nullptr);
+    if (api) api->CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
+  }
+}
+
+int smf_set_exchange(smf_ctx *ctx, int level, int family, const smf_exchange *x)
+{
+  if (!ctx || !x || (family != 0 && family != 1)) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  LevelDev &L = ctx->lev(level);
+  if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the level mesh first");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  ExchangeDev &E = family == 0 ? L.ex_u : L.ex_p;
+  free_exchange(E);
+  const int ncomp = family == 0 ? L.dim : 1;
+  const int64_t n_dofs = family == 0 ? L.n_u : L.n_p;
+  const std::vector<uint8_t> &cons = family == 0 ? L.h_cons_u : L.h_cons_p;
+  E.ncomp = ncomp;
+  // ---- neighbour lists ----
+  std::vector<uint32_t> send_idx;
+  std::map<uint32_t, std::vector<std::pair<int, int>>> sharers;     // first DoF of the node -> (rank, position in recv buffer)
+  int64_t off = 0;
+  for (int k = 0; k < x->n_neighbors; ++k) {
+    const int q = x->neighbor_ranks[k];
+    if (q < 0 || q >= ctx->world || q == ctx->rank) return ctx->fail(SMF_ERR_INVALID, "bad neighbour rank");
+    if (k > 0 && q <= x->neighbor_ranks[k - 1]) return ctx->fail(SMF_ERR_INVALID, "neighbour ranks must be ascending");
+    E.ranks.push_back(q); E.counts.push_back(x->counts[k]); E.offsets.push_back(off);
+    for (int64_t i = 0; i < x->counts[k]; ++i) {
+      const uint32_t d0 = x->nodes[k][i];
+      if ((int64_t)d0 + ncomp > n_dofs) return ctx->fail(SMF_ERR_INVALID, "exchange index out of range");
+      send_idx.push_back(d0);
+      sharers[d0].push_back({q, (int)(off + i)});
+    }
+    off += x->counts[k];
+  }
+  E.n_send = off;
+  // ---- rank-ordered accumulation tables, weights, ownership ----
+  std::vector<uint32_t> if_idx;
+  std::vector<int> if_ptr(1, 0), if_src;
+  std::vector<double> weights((size_t)n_dofs, 1.0);
+  std::vector<uint8_t> &not_owned = family == 0 ? L.h_not_owned_u : L.h_not_owned_p;
+  not_owned.assign((size_t)n_dofs, 0);
+  for (auto &kv : sharers) {
+    const uint32_t d0 = kv.first;
+    auto &lst = kv.second;       // ascending rank (neighbours were ascending)
+    uint32_t flags = 0;
+    for (int c = 0; c < ncomp; ++c)
+      if (!cons.empty() && cons[d0 + c]) flags |= 1u << (NODE_FLAG_SHIFT + c);
+    if_idx.push_back(d0 | flags);
+    bool own_done = false;
+    for (auto &pr : lst) {
+      if (!own_done && pr.first > ctx->rank) { if_src.push_back(-1); own_done = true; }
+      if_src.push_back(pr.second);
+    }
+    if (!own_done) if_src.push_back(-1);
+    if_ptr.push_back((int)if_src.size());
+    const double w = 1.0 / (double)(lst.size() + 1);
+    for (int c = 0; c < ncomp; ++c) { weights[d0 + c] = w; if (lst.front().first < ctx->rank) not_owned[d0 + c] = 1; }
+  }
+  E.n_if = (int64_t)if_idx.size();
+  auto up = [&](auto **dev, const auto &host) -> int {
+    using T = typename std::remove_reference<decltype(host[0])>::type;
+    const size_t nb = std::max<size_t>(host.size(), 1) * sizeof(T);
+    SMF_CUDA(cudaMalloc((void **)dev, nb));
+    if (!host.empty()) SMF_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    ctx->bytes += (int64_t)nb;
+    return SMF_OK;
+  };
+  int e;
+  if (E.n_send > 0) {
+    if ((e = up(&E.send_idx, send_idx))) return e;
+    if ((e = up(&E.if_idx, if_idx))) return e;
+    if ((e = up(&E.if_ptr, if_ptr))) return e;
+    if ((e = up(&E.if_src, if_src))) return e;
+    SMF_CUDA(cudaMalloc(&E.send_buf, sizeof(double) * E.n_send * ncomp));
+    SMF_CUDA(cudaMalloc(&E.recv_buf, sizeof(double) * E.n_send * ncomp));
+    ctx->bytes += 2 * (int64_t)sizeof(double) * E.n_send * ncomp;
+  }
+  if (ctx->world > 1) {
+    if ((e = up(&E.weights, weights))) return e;
+  }
+  // ---- global DoF numbers for the Chebyshev start vector ((global index mod 11) - mean, App. A.2) ----
+  if (x->global_dof_ids) {
+    std::vector<int64_t> gid(x->global_dof_ids, x->global_dof_ids + n_dofs);
+    if ((e = up(&E.gid, gid))) return e;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = 0; i < n_dofs; ++i) { acc[0] += weights[i] * (double)(gid[i] % 11); acc[1] += weights[i]; }
+    if (ctx->world > 1) {          // collective: every rank calls smf_set_exchange for the same (level, family)
+      double *d = nullptr;
+      SMF_CUDA(cudaMalloc(&d, 2 * sizeof(double)));
+      SMF_CUDA(cudaMemcpyAsync(d, acc, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      if ((e = allreduce_sum(ctx, d, 2))) { cudaFree(d); return e; }
+      SMF_CUDA(cudaMemcpyAsync(acc, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(d);
+    }
+    E.gid_mean = acc[0] / acc[1];
+  }
+  E.set = true;
+  ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+int smf_exchange_add(smf_ctx *ctx, int level, int family, double *vec)
+{
+  if (!ctx || !vec || (family != 0 && family != 1)) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  LevelDev &L = ctx->lev(level);
+  return exchange_add(ctx, family == 0 ? L.ex_u : L.ex_p, vec);
+}
+
+}  // extern "C"

@@ -771,7 +771,7 @@ template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(32 * TR
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r)
     if (lane + 32 * r < NPATCH) {
-      const bool own = pe[r] >> 31;
+      const bool own = (pe[r] >> 30) & 1u;
       const uint32_t fi = pe[r] & NODE_IDX_MASK;
 #pragma unroll
       for (int c = 0; c < NCOMP; ++c) s_f[w][c][lane + 32 * r] = own ? P.src[fi + c] : 0.0;
@@ -860,7 +860,8 @@ int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
   CellParams P = make_params(L);
   P.src_u = src; P.dst_u = dst;
   SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_u, ctx->stream));
-  return L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P);
+  if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
+  return exchange_add(ctx, L.ex_u, dst);
 }
 int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
 {
@@ -869,7 +870,9 @@ int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p,
   P.src_u = src_u; P.src_p = src_p; P.dst_u = dst_u; P.dst_p = dst_p;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
   SMF_CUDA(cudaMemsetAsync(dst_p, 0, sizeof(double) * L.n_p, ctx->stream));
-  return L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P);
+  if (int e = L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P)) return e;
+  if (int e = exchange_add(ctx, L.ex_u, dst_u)) return e;
+  return exchange_add(ctx, L.ex_p, dst_p);
 }
 int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_p)
 {
@@ -877,7 +880,8 @@ int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_
   CellParams P = make_params(L);
   P.src_p = src_p; P.dst_u = dst_u;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
-  return L.dim == 3 ? launch_velocity<3, 2>(ctx, L, P) : launch_velocity<2, 2>(ctx, L, P);
+  if (int e = L.dim == 3 ? launch_velocity<3, 2>(ctx, L, P) : launch_velocity<2, 2>(ctx, L, P)) return e;
+  return exchange_add(ctx, L.ex_u, dst_u);
 }
 int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
 {
@@ -887,17 +891,19 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
   SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
   const size_t smem = (size_t)MASS_WARPS * 2 * L.max_nodes_p * sizeof(double);
   const unsigned grid = (unsigned)((L.n_batches + MASS_WARPS - 1) / MASS_WARPS);
-  ProfScope prof(ctx, B_MASS);
-  if (L.dim == 3) {
-    if (L.n_eta == 1) mass_kernel<3, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
-    else mass_kernel<3, true><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
-  } else {
-    if (L.n_eta == 1) mass_kernel<2, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
-    else mass_kernel<2, true><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+  {
+    ProfScope prof(ctx, B_MASS);
+    if (L.dim == 3) {
+      if (L.n_eta == 1) mass_kernel<3, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+      else mass_kernel<3, true><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+    } else {
+      if (L.n_eta == 1) mass_kernel<2, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+      else mass_kernel<2, true><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
+    }
   }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
-  return SMF_OK;
+  return exchange_add(ctx, L.ex_p, dst);
 }
 
 int launch_diag(smf_ctx *ctx, LevelDev &L)
@@ -917,6 +923,9 @@ int launch_diag(smf_ctx *ctx, LevelDev &L)
   if (L.dim == 3) diag_kernel<3><<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(P);
   else diag_kernel<2><<<(unsigned)((nt + bs - 1) / bs), bs, 0, ctx->stream>>>(P);
   ctx->launches++;
+  // compress(add) of the per-rank partial diagonals
+  if (int e = exchange_add(ctx, L.ex_u, L.dinv_A)) return e;
+  if (int e = exchange_add(ctx, L.ex_p, L.dinv_M)) return e;
   // set_constrained_entries_to_one, then invert (matrix_free_operators.cc:1085-1097)
   if (L.n_constrained_u) {
     set_entries_kernel<<<(unsigned)((L.n_constrained_u + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_A, L.constrained_u, L.n_constrained_u, 1.0);
@@ -961,6 +970,8 @@ static int launch_transfer(smf_ctx *ctx, int which, int fine_level, double *dst,
     if (dim == 3) launch_transfer_t<3, 2, 1>(ctx, P, prolong); else launch_transfer_t<2, 2, 1>(ctx, P, prolong);
   }
   SMF_CUDA(cudaGetLastError());
+  // restriction: the coarse vector holds per-rank partial sums on the subdomain interfaces
+  if (!prolong) return exchange_add(ctx, which == 0 ? C.ex_u : C.ex_p, dst);
   return SMF_OK;
 }
 

@@ -30,6 +30,7 @@ static void free_level(LevelDev &L)
   cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
   cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
   cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M);
+  free_exchange(L.ex_u); free_exchange(L.ex_p);
   L = LevelDev();
 }
 
@@ -159,6 +160,8 @@ static bool build_structured3(const std::vector<uint32_t> &nodes, int64_t n_cell
 }
 }  // namespace smf
 
+extern "C" void smf_comm_destroy_internal(smf_ctx *ctx);
+
 extern "C" {
 
 int smf_create(const smf_config *cfg, smf_ctx **out)
@@ -197,7 +200,8 @@ void smf_destroy(smf_ctx *ctx)
     for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
   for (double *p : ctx->krylov) cudaFree(p);
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
-  cudaFree(ctx->io_buf);
+  cudaFree(ctx->io_buf); cudaFree(ctx->block_weights);
+  smf_comm_destroy_internal(ctx);
   cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_u2);   // tmp_p / tmp_p2 point into the same allocations
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
   for (auto &e : ctx->prof_live) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -333,6 +337,8 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   // host copies of the raw maps are needed once more by smf_set_transfer
   L.h_nodes_u = std::move(nodes_u);
   L.h_nodes_p = std::move(nodes_p);
+  L.h_cons_u = std::move(cu);
+  L.h_cons_p = std::move(cp);
   return SMF_OK;
 }
 
@@ -348,7 +354,10 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
   cudaFree(T.patch_u); cudaFree(T.patch_p);
   T = TransferDev();
   T.n_parents = C.n_cells;
-  auto build = [&](int npd, const std::vector<uint32_t> &fine_nodes, int64_t n_fine_index, std::vector<uint32_t> &patch) -> bool {
+  // bit 31: this parent writes the node in prolongation (first local parent that touches it);
+  // bit 30: this parent contributes the node in restriction (same, and no lower rank owns the node)
+  auto build = [&](int npd, const std::vector<uint32_t> &fine_nodes, int64_t n_fine_index, const std::vector<uint8_t> &not_owned,
+                   std::vector<uint32_t> &patch) -> bool {
     const int npp = 2 * npd - 1;
     int npatch = 1, nloc = 1;
     for (int d = 0; d < dim; ++d) { npatch *= npp; nloc *= npd; }
@@ -368,13 +377,17 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
         if (fc < 0 || fc >= F.n_cells) return false;
         const uint32_t idx = fine_nodes[(size_t)fc * nloc + a] & NODE_IDX_MASK;
         uint32_t e = idx;
-        if (!seen[idx]) { seen[idx] = 1; e |= 1u << 31; }
+        if (!seen[idx]) {
+          seen[idx] = 1;
+          e |= 1u << 31;
+          if (not_owned.empty() || !not_owned[idx]) e |= 1u << 30;
+        }
         patch[(size_t)par * npatch + s] = e;
       }
     return true;
   };
   std::vector<uint32_t> pu, pp;
-  if (!build(3, F.h_nodes_u, F.n_u, pu) || !build(2, F.h_nodes_p, F.n_p, pp))
+  if (!build(3, F.h_nodes_u, F.n_u, F.h_not_owned_u, pu) || !build(2, F.h_nodes_p, F.n_p, F.h_not_owned_p, pp))
     return ctx->fail(SMF_ERR_UNSUPPORTED, "children table has unrefined / out-of-range entries (adaptive meshes not implemented)");
   int64_t bytes = 0;
   int e;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "../../include/smf_b200.h"
@@ -56,6 +57,21 @@ __host__ __device__ constexpr int sb_z(int l) { return (l >> 2) & 1; }
 // per-batch header (ints): n_nodes_u, n_excl_u, n_nodes_p, n_excl_p, n_cells, pad x3
 constexpr int BATCH_INFO = 8;
 
+// halo exchange of one level and DoF family (comm.cu)
+struct ExchangeDev {
+  bool set = false;
+  int ncomp = 1;
+  std::vector<int> ranks;                     // neighbour ranks, ascending
+  std::vector<int64_t> counts, offsets;       // shared nodes per neighbour / start in the buffers (in nodes)
+  int64_t n_send = 0;                         // total shared-node entries (= sum of counts)
+  uint32_t *send_idx = nullptr;               // [n_send] first DoF of each shared node
+  double *send_buf = nullptr, *recv_buf = nullptr;   // [n_send * ncomp]
+  int64_t n_if = 0;                           // distinct interface nodes
+  uint32_t *if_idx = nullptr; int *if_ptr = nullptr, *if_src = nullptr;   // rank-ordered accumulation tables
+  double *weights = nullptr;                  // [n_dofs] 1 / (ranks sharing the DoF); nullptr on one rank
+  int64_t *gid = nullptr; double gid_mean = 0.0;     // global DoF numbers (Chebyshev start vector)
+};
+
 struct LevelDev {
   int dim = 0;
   int64_t n_cells = 0, n_u = 0, n_p = 0;
@@ -81,6 +97,9 @@ struct LevelDev {
   double *dinv_A = nullptr, *dinv_M = nullptr; bool has_diag = false;
   int64_t bytes = 0;
   std::vector<uint32_t> h_nodes_u, h_nodes_p;   // host copies of the raw maps (needed by smf_set_transfer)
+  std::vector<uint8_t> h_cons_u, h_cons_p;      // host constraint bitmaps (needed by smf_set_exchange)
+  std::vector<uint8_t> h_not_owned_u, h_not_owned_p;   // DoFs whose owner is a lower rank (set by smf_set_exchange)
+  ExchangeDev ex_u, ex_p;
 };
 
 struct TransferDev {              // level l-1 -> l
@@ -99,7 +118,7 @@ struct Smoother {                 // PreconditionChebyshev state of one level
 };
 
 // device-time buckets of the optional profiler (smf_profile_*): the split SURVEY.md 8(d) asks for
-enum Bucket { B_STOKES = 0, B_A_FINE, B_A_COARSE, B_MASS, B_BT, B_TRANSFER, B_SMOOTH_VEC, B_ORTHO, B_VEC, B_COUNT };
+enum Bucket { B_STOKES = 0, B_A_FINE, B_A_COARSE, B_MASS, B_BT, B_TRANSFER, B_SMOOTH_VEC, B_ORTHO, B_VEC, B_EXCHANGE, B_COUNT };
 struct ProfEvent { int bucket; cudaEvent_t a, b; };
 
 struct MGVectors {                // per level: solution, defect, t, and a Chebyshev scratch
@@ -129,6 +148,12 @@ struct smf_ctx {
   double *tmp_u = nullptr, *tmp_p = nullptr, *tmp_u2 = nullptr, *tmp_p2 = nullptr;
   double *io_buf = nullptr; int64_t io_n = 0;         // device staging of smf_solve_host
   int n_A_prec = 0, n_S_prec = 0;
+  // distributed run (comm.cu): one subdomain per rank
+  int rank = 0, world = 1;
+  void *comm = nullptr;                               // ncclComm_t
+  int64_t exchanges = 0;
+  const double *dot_weights = nullptr;                // weights the inner products use right now (nullptr: none)
+  double *block_weights = nullptr;                    // [n_u + n_p] of the active level
   int md_vec2 = 0;                                    // the pointer table of the last multi_dot allows 16-byte loads
   // CUDA graphs of the coarse part of the two V-cycles (level_v_step(graph_level) on the fixed MG buffers)
   void *graph_A = nullptr, *graph_S = nullptr;        // cudaGraphExec_t
@@ -174,6 +199,11 @@ struct ProfScope {
   }
   ~ProfScope() { if (b) cudaEventRecord(b, ctx->stream); }
 };
+struct DotWeights {     // inner products in this scope weight every DoF with 1 / (number of ranks sharing it)
+  smf_ctx *ctx; const double *saved;
+  DotWeights(smf_ctx *c, const double *w) : ctx(c), saved(c->dot_weights) { c->dot_weights = w; }
+  ~DotWeights() { ctx->dot_weights = saved; }
+};
 struct VecBucket {      // books the vector kernels launched in this scope under `bucket`
   smf_ctx *ctx; int saved;
   VecBucket(smf_ctx *c, int bucket) : ctx(c), saved(c->vec_bucket) { c->vec_bucket = bucket; }
@@ -187,6 +217,11 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
 int launch_diag(smf_ctx *ctx, LevelDev &L);
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);
+// comm.cu
+void free_exchange(ExchangeDev &E);
+int exchange_add(smf_ctx *ctx, ExchangeDev &E, double *vec);
+int allreduce_sum(smf_ctx *ctx, double *dev, int count);
+int start_vector_mod11(smf_ctx *ctx, const ExchangeDev &E, double *x, int64_t n);
 // vector kernels (vecops.cu)
 int vec_set(smf_ctx *ctx, double *x, double v, int64_t n);
 int vec_copy(smf_ctx *ctx, double *y, const double *x, int64_t n);

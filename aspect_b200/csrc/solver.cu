@@ -81,7 +81,10 @@ static int estimate_eigenvalues(smf_ctx *ctx, const MGSide &S, int l)
   const int64_t full = n / 11, rem = n % 11;
   const double mean = (double)(full * 55 + rem * (rem - 1) / 2) / (double)n;
   double *r = V.b, *z = V.t, *p = V.x, *v = V.xo;
-  TRY(vec_mod11(ctx, r, 0, mean, n));
+  const ExchangeDev &E = S.velocity ? ctx->levels[l].ex_u : ctx->levels[l].ex_p;
+  DotWeights dw(ctx, E.weights);
+  if (E.gid) TRY(start_vector_mod11(ctx, E, r, n));     // partition-independent global DoF numbers
+  else TRY(vec_mod11(ctx, r, 0, mean, n));
   double res2;
   TRY(vec_norm2(ctx, r, n, &res2));
   std::vector<double> diag, off;
@@ -295,6 +298,7 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
   const int restart = std::max(1, std::min(prm->gmres_restart_length, 100));
   const int max_its = prm->n_cheap_stokes_solver_steps;
   TRY(ensure_krylov(ctx, restart + 3));
+  DotWeights dw(ctx, ctx->block_weights);
   std::vector<double *> &K = ctx->krylov;
   double *p = K[restart + 1], *xb = K[restart + 2];   // p: scratch block vector; xb: contiguous copy of the iterate
   TRY(vec_copy(ctx, xb, x_u, nu));
@@ -540,8 +544,14 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
   TRY(launch_vmult_stokes(ctx, A, r, r + nu, g, g + nu));
   TRY(vec_sadd(ctx, r, -1.0, 1.0, rhs_u, nu));
   double ru2, rp2;
-  TRY(vec_norm2(ctx, r, nu, &ru2));
-  TRY(vec_norm2(ctx, rhs_p, np, &rp2));
+  if (ctx->world > 1 && !ctx->block_weights) {
+    if (!A.ex_u.weights || !A.ex_p.weights) return ctx->fail(SMF_ERR_INVALID, "smf_set_exchange missing for the active level");
+    SMF_CUDA(cudaMalloc(&ctx->block_weights, sizeof(double) * (nu + np)));
+    SMF_CUDA(cudaMemcpyAsync(ctx->block_weights, A.ex_u.weights, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+    SMF_CUDA(cudaMemcpyAsync(ctx->block_weights + nu, A.ex_p.weights, sizeof(double) * np, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  { DotWeights dw(ctx, A.ex_u.weights); TRY(vec_norm2(ctx, r, nu, &ru2)); }
+  { DotWeights dw(ctx, A.ex_p.weights); TRY(vec_norm2(ctx, rhs_p, np, &rp2)); }
   const double tol = prm->linear_solver_tolerance * std::sqrt(ru2 + rp2);
   result->tolerance = tol;
   ctx->n_A_prec = ctx->n_S_prec = 0;

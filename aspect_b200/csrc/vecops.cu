@@ -98,7 +98,8 @@ __device__ __forceinline__ double2 load2(const double *p, int64_t i, int64_t n, 
   return r;
 }
 __global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int k, const double *w, int64_t n,
-                                                      double *partial, unsigned int *counter, double *out, int vec2)
+                                                      double *partial, unsigned int *counter, double *out, int vec2,
+                                                      const double *wgt)
 {
   __shared__ double s_acc[VT / 32][MD_CHUNK + 4];
   __shared__ const double *s_v[MD_CHUNK];
@@ -114,8 +115,14 @@ __global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int
     double wn = 0.0;
 #pragma unroll
     for (int r = 0; r < NL; ++r) {
-      ww[r] = load2(w, base + ((int64_t)r * VT + threadIdx.x) * 2, n, vec2);
-      wn = fma(ww[r].x, ww[r].x, fma(ww[r].y, ww[r].y, wn));
+      const int64_t i = base + ((int64_t)r * VT + threadIdx.x) * 2;
+      ww[r] = load2(w, i, n, vec2);
+      const double x0 = ww[r].x, y0 = ww[r].y;
+      if (wgt) {       // distributed run: every shared DoF counts 1 / (number of ranks that hold it)
+        const double2 g = load2(wgt, i, n, vec2);
+        ww[r].x *= g.x; ww[r].y *= g.y;
+      }
+      wn = fma(ww[r].x, x0, fma(ww[r].y, y0, wn));
     }
     for (int g = 0; g < k; g += MD_GROUP) {
       double2 vv[MD_GROUP][NL];
@@ -163,7 +170,8 @@ __global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int
 // w -= sum_j coef[j] V[j]; out[0] = |w_new|^2
 constexpr int MA_UNROLL = 8;
 __global__ void __launch_bounds__(VT) k_multi_axpy(double *w, const double *const *V, const double *coef, int k, int64_t n,
-                                                    double *partial, unsigned int *counter, double *out, int vec2)
+                                                    double *partial, unsigned int *counter, double *out, int vec2,
+                                                    const double *wgt)
 {
   __shared__ double s_coef[MD_CHUNK];
   __shared__ const double *s_v[MD_CHUNK];
@@ -190,7 +198,12 @@ __global__ void __launch_bounds__(VT) k_multi_axpy(double *w, const double *cons
     }
     if (vec2 && i + 1 < n) *reinterpret_cast<double2 *>(w + i) = ww;
     else { w[i] = ww.x; if (i + 1 < n) w[i + 1] = ww.y; }
-    nrm = fma(ww.x, ww.x, fma(ww.y, ww.y, nrm));
+    if (wgt) {
+      const double2 g = load2(wgt, i, n, vec2);
+      nrm = fma(ww.x * g.x, ww.x, fma(ww.y * g.y, ww.y, nrm));
+    } else {
+      nrm = fma(ww.x, ww.x, fma(ww.y, ww.y, nrm));
+    }
   }
   nrm = warp_sum(nrm);
   if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = nrm;
@@ -261,7 +274,9 @@ int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double 
   if (k > 0) SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
   { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_dot<<<red_blocks(k_multi_dot, n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx),
-                                                      ctx->md_vec2 = all_aligned16(w, V_host_ptrs, k)); }
+                                                      ctx->md_vec2 = (all_aligned16(w, V_host_ptrs, k) && ((uintptr_t)ctx->dot_weights & 15u) == 0),
+                                                      ctx->dot_weights); }
+  if (int e = allreduce_sum(ctx, scr_out(ctx), k + 1)) return e;
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   if (sync) {
@@ -280,7 +295,8 @@ int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *
   { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(w, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
                                                        scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2,
-                                                       ctx->md_vec2 && ((uintptr_t)w & 15u) == 0); }
+                                                       ctx->md_vec2 && ((uintptr_t)w & 15u) == 0, ctx->dot_weights); }
+  if (int e = allreduce_sum(ctx, scr_out(ctx) + MD_CHUNK + 2, 1)) return e;
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (MD_CHUNK + 3), cudaMemcpyDeviceToHost, ctx->stream));
@@ -302,7 +318,7 @@ int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const dou
   { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
                                                        scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2,
-                                                       all_aligned16(x, V_host_ptrs, k)); }
+                                                       all_aligned16(x, V_host_ptrs, k), nullptr); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   // the pinned staging area is reused by the next call: make sure the copies above have been consumed

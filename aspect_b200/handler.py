@@ -69,6 +69,8 @@ class StokesMatrixFreeHandler:
         self.minimum_viscosity = self.maximum_viscosity = None
         self.allow_structured_bricks = True      # implementation switches (smf_set_option); tests exercise both paths
         self.use_cuda_graphs = True
+        # Chebyshev eigenvalue start vector from partition-independent global DoF numbers (always on for >1 rank)
+        self.global_start_vector = False
         # "Solver parameters/Stokes solver parameters" (names verbatim from source/simulator/parameters.cc:439-584)
         self.parameters = {
             "Linear solver tolerance": 1e-7,
@@ -122,6 +124,8 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_STRUCTURED_BRICKS, int(self.allow_structured_bricks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CUDA_GRAPHS, int(self.use_cuda_graphs)))
         self._keep = []
+        self.rank, self.world = getattr(hierarchy, "rank", 0), getattr(hierarchy, "world", 1)
+        self._comm_init()
         for l in list(range(n_levels)) + [SMF_ACTIVE]:
             L = hierarchy.levels[l] if l >= 0 else hierarchy.active
             cu = np.ascontiguousarray(L.cell_dofs_u, dtype=np.uint32)
@@ -130,6 +134,11 @@ class StokesMatrixFreeHandler:
             h = np.ascontiguousarray(L.h, dtype=np.float64)
             m = _lib.LevelMesh(L.n_cells, L.n_u, L.n_p, ptr(cu), ptr(cp), len(cons), ptr(cons), 0, ptr(None), 0, ptr(h))
             self._check(self.lib.smf_set_level(self.ctx, l, ctypes.byref(m)))
+        if self.world > 1 or self.global_start_vector:
+            for l in list(range(n_levels)) + [SMF_ACTIVE]:
+                L = hierarchy.levels[l] if l >= 0 else hierarchy.active
+                for family in (0, 1):
+                    self._set_exchange(l, family, L)
         for l in range(1, n_levels):
             ch = np.ascontiguousarray(hierarchy.children(l), dtype=np.int32)
             self._check(self.lib.smf_set_transfer(self.ctx, l, ptr(ch)))
@@ -147,6 +156,38 @@ class StokesMatrixFreeHandler:
         self.prec_A = _Op(self, lambda d, s: c(lib.smf_vcycle_A(self.ctx, ptr(d.ptr), ptr(s.ptr))))
         self.prec_Schur = _Op(self, lambda d, s: c(lib.smf_vcycle_S(self.ctx, ptr(d.ptr), ptr(s.ptr))))
         self.preconditioner_cheap = _Op(self, lambda d, s: c(lib.smf_precondition(self.ctx, ptr(d[0].ptr), ptr(d[1].ptr), ptr(s[0].ptr), ptr(s[1].ptr))))
+
+    def _comm_init(self):
+        """One context per rank: rank 0 creates the NCCL id, torch.distributed carries it to the others."""
+        idbuf = ctypes.create_string_buffer(_lib.SMF_UNIQUE_ID_BYTES)
+        if self.world > 1:
+            import torch.distributed as dist
+            if self.rank == 0:
+                self._check(self.lib.smf_comm_get_unique_id(idbuf))
+            box = [idbuf.raw]
+            dist.broadcast_object_list(box, src=0)
+            idbuf = ctypes.create_string_buffer(box[0], _lib.SMF_UNIQUE_ID_BYTES)
+        self._check(self.lib.smf_comm_init(self.ctx, self.rank, self.world, idbuf))
+
+    def _set_exchange(self, level, family, L):
+        fam = "u" if family == 0 else "p"
+        ncomp = self.dim if family == 0 else 1
+        lists = L.exchange_lists(fam) if self.world > 1 else {}
+        ranks = sorted(lists)
+        arrs = [np.ascontiguousarray(lists[q].astype(np.uint32) * ncomp) for q in ranks]     # first DoF of every shared node
+        gid = L.global_node_ids(fam)
+        if ncomp > 1:
+            gid = (gid[:, None] * ncomp + np.arange(ncomp)[None, :]).ravel()
+        gid = np.ascontiguousarray(gid, dtype=np.int64)
+        rk = np.ascontiguousarray(ranks, dtype=np.int32)
+        cnt = np.ascontiguousarray([len(a) for a in arrs], dtype=np.int64)
+        ptrs = (ctypes.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+        x = _lib.Exchange(len(ranks), ptr(rk), ptr(cnt), ctypes.cast(ptrs, ctypes.c_void_p), ptr(gid))
+        self._check(self.lib.smf_set_exchange(self.ctx, level, family, ctypes.byref(x)))
+
+    def exchange_add(self, vec, family, level=SMF_ACTIVE):
+        """compress(add) + update_ghost_values of a device vector (e.g. a right-hand side assembled per rank)."""
+        self._check(self.lib.smf_exchange_add(self.ctx, level, family, ptr(vec.ptr)))
 
     def initialize_dof_vector(self, block=None, level=SMF_ACTIVE):
         """block None -> (velocity, pressure) pair for the active level; 0 / 1 -> a single vector of that level."""
@@ -245,7 +286,8 @@ class StokesMatrixFreeHandler:
     def _outputs(res):
         return {k: getattr(res, k) for k, _ in _lib.SolveResult._fields_}
 
-    PROFILE_BUCKETS = ("stokes_vmult", "A_fine", "A_coarse", "mass", "BT", "transfer", "chebyshev_vec", "gmres_ortho", "other_vec")
+    PROFILE_BUCKETS = ("stokes_vmult", "A_fine", "A_coarse", "mass", "BT", "transfer", "chebyshev_vec", "gmres_ortho", "other_vec",
+                       "halo_exchange")
 
     def profile_enable(self, mode):
         """'Execute solver timings' analogue: 0 off, 1 finest-level operator kernels, 2 every launch."""

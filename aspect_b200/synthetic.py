@@ -47,9 +47,10 @@ def morton_cells(level, dim):
 
 
 def _first_touch(cells, npd_minus1, local_order, lex_order, grid):
-    """Number the grid nodes in first-touch order; returns (cell_nodes_lex, node_grid)."""
+    """Number the grid nodes in first-touch order; returns (cell_nodes_lex, node_grid).  grid: nodes per dimension."""
     dim = cells.shape[1]
-    mult = grid ** np.arange(dim, dtype=np.int64)
+    grid = np.asarray(grid, dtype=np.int64)
+    mult = np.concatenate([[1], np.cumprod(grid[:-1])]).astype(np.int64)
 
     def keys(order):
         out = np.zeros((len(cells), len(order)), dtype=np.int64)
@@ -61,26 +62,46 @@ def _first_touch(cells, npd_minus1, local_order, lex_order, grid):
     uniq, first = np.unique(kfe, return_index=True)
     rank = np.empty(len(uniq), dtype=np.int64)
     rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
-    table = np.full(grid ** dim, -1, dtype=np.int64)
-    table[uniq] = rank
     del kfe
-    cell_nodes = table[keys(lex_order)]
+    klex = keys(lex_order)
+    cell_nodes = rank[np.searchsorted(uniq, klex.ravel())].reshape(klex.shape)
     node_grid = np.zeros((len(uniq), dim), dtype=np.int64)
     for d in range(dim):
-        node_grid[rank, d] = (uniq // mult[d]) % grid
+        node_grid[rank, d] = (uniq // mult[d]) % grid[d]
     return cell_nodes, node_grid
 
 
 class BoxLevel:
-    def __init__(self, dim, level, extents=None):
+    """One level of the (rank-local part of the) box mesh.
+
+    The box has `repetitions` coarse cells per direction (`X/Y/Z repetitions` of the box geometry model,
+    /root/reference/source/geometry_model/box.cc:66-74); every coarse cell is the root of one tree.  A rank owns a
+    contiguous range of trees (p4est orders cells tree by tree along the space-filling curve) and numbers the DoFs
+    of its cells locally in first-touch order; DoFs on faces shared with trees of other ranks exist on every
+    rank that touches them (`sharers`), which is what the halo exchange of the C ABI works with."""
+
+    def __init__(self, dim, level, extents=None, repetitions=None, rank=0, world=1):
         self.dim, self.level = dim, level
         self.n = n = 1 << level
         self.extents = np.ones(dim) if extents is None else np.asarray(extents, float)
-        self.h = self.extents / n
-        self.cells = morton_cells(level, dim)
+        self.rep = rep = np.ones(dim, dtype=np.int64) if repetitions is None else np.asarray(repetitions, dtype=np.int64)
+        self.rank, self.world = rank, world
+        n_trees = int(np.prod(rep))
+        assert n_trees % world == 0, "the number of coarse cells must be a multiple of the number of ranks"
+        self.trees_per_rank = tpr = n_trees // world
+        self.h = self.extents / (rep * n)
+        m = morton_cells(level, dim)
+        trees = np.arange(rank * tpr, (rank + 1) * tpr, dtype=np.int64)
+        origin = np.zeros((tpr, dim), dtype=np.int64)
+        t = trees.copy()
+        for d in range(dim):
+            origin[:, d] = (t % rep[d]) * n
+            t //= rep[d]
+        self.cells = (origin[:, None, :] + m[None, :, :]).reshape(-1, dim)
         self.n_cells = len(self.cells)
-        nodes_u, self.node_grid_u = _first_touch(self.cells, 2, _fe_local_order(2, dim), _lex(3, dim), 2 * n + 1)
-        nodes_p, self.node_grid_p = _first_touch(self.cells, 1, _fe_local_order(1, dim), _lex(2, dim), n + 1)
+        self.grid_u, self.grid_p = 2 * rep * n + 1, rep * n + 1
+        nodes_u, self.node_grid_u = _first_touch(self.cells, 2, _fe_local_order(2, dim), _lex(3, dim), self.grid_u)
+        nodes_p, self.node_grid_p = _first_touch(self.cells, 1, _fe_local_order(1, dim), _lex(2, dim), self.grid_p)
         self.n_u = dim * len(self.node_grid_u)
         self.n_p = len(self.node_grid_p)
         nn = 3 ** dim
@@ -92,8 +113,8 @@ class BoxLevel:
 
     def constrained_u(self, bc):
         """'zero' (all components on every face), 'tangential' (normal component on each face), 'none'."""
-        g, hi, dim = self.node_grid_u, 2 * self.n, self.dim
-        on = (g == 0) | (g == hi)                                  # (nodes, dim)
+        g, hi, dim = self.node_grid_u, self.grid_u - 1, self.dim
+        on = (g == 0) | (g == hi[None, :])                         # (nodes, dim)
         if bc == "zero":
             mask = np.repeat(on.any(axis=1)[:, None], dim, axis=1)
         elif bc == "tangential":
@@ -113,13 +134,60 @@ class BoxLevel:
     def dof_coords_u(self):
         return np.repeat(self.node_grid_u * (self.h / 2.0), self.dim, axis=0)
 
+    # -- distributed layout --------------------------------------------------------------------------------
+    def global_node_ids(self, family):
+        """Partition-independent id of every local node (lexicographic index in the global node lattice)."""
+        g, grid = (self.node_grid_u, self.grid_u) if family == "u" else (self.node_grid_p, self.grid_p)
+        mult = np.concatenate([[1], np.cumprod(grid[:-1])]).astype(np.int64)
+        return (g * mult[None, :]).sum(axis=1)
+
+    def sharers(self, family):
+        """(interface node indices, (n, 2^dim) ranks touching each of them, -1 padded / duplicates removed)."""
+        g = self.node_grid_u if family == "u" else self.node_grid_p
+        step = (2 if family == "u" else 1) * self.n              # lattice distance between tree planes
+        dim, rep = self.dim, self.rep
+        on_plane = (g % step == 0) & (g > 0) & (g < (rep * step)[None, :])
+        idx = np.flatnonzero(on_plane.any(axis=1))
+        gi, pl = g[idx], on_plane[idx]
+        hi_tree = np.minimum(gi // step, rep[None, :] - 1)        # tree coordinate on the upper side
+        ranks = np.zeros((len(idx), 1 << dim), dtype=np.int64)
+        for corner in range(1 << dim):
+            tree = np.zeros(len(idx), dtype=np.int64)
+            mult = 1
+            for d in range(dim):
+                lower = ((corner >> d) & 1) == 1
+                td = np.where(pl[:, d] & lower, hi_tree[:, d] - 1, hi_tree[:, d])
+                tree += td * mult
+                mult *= rep[d]
+            ranks[:, corner] = tree // self.trees_per_rank
+        ranks.sort(axis=1)
+        dup = np.zeros_like(ranks, dtype=bool)
+        dup[:, 1:] = ranks[:, 1:] == ranks[:, :-1]
+        ranks[dup] = -1
+        multi = ((ranks >= 0) & (ranks != self.rank)).any(axis=1)     # interior tree planes between two local trees are not interfaces
+        return idx[multi], ranks[multi]
+
+    def exchange_lists(self, family):
+        """{neighbour rank: local node indices shared with it, ordered by global node id (identical on both sides)}."""
+        idx, ranks = self.sharers(family)
+        gid = self.global_node_ids(family)[idx]
+        order = np.argsort(gid, kind="stable")
+        idx, ranks = idx[order], ranks[order]
+        out = {}
+        for q in np.unique(ranks):
+            if q < 0 or q == self.rank:
+                continue
+            out[int(q)] = idx[(ranks == q).any(axis=1)].astype(_UINT)
+        return out
+
 
 class BoxHierarchy:
-    """Levels 0..R of the uniformly refined box with one coarse cell; active mesh = level R."""
+    """Levels 0..R of the uniformly refined box (rank-local part); active mesh = level R."""
 
-    def __init__(self, dim, refinement, extents=None):
+    def __init__(self, dim, refinement, extents=None, repetitions=None, rank=0, world=1):
         self.dim, self.R = dim, refinement
-        self.levels = [BoxLevel(dim, l, extents) for l in range(refinement + 1)]
+        self.rank, self.world = rank, world
+        self.levels = [BoxLevel(dim, l, extents, repetitions, rank, world) for l in range(refinement + 1)]
         self.active = self.levels[-1]
 
     def children(self, level):

@@ -76,6 +76,30 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children);
 /* copy_to_mg / copy_from_mg index map: level-(n_levels-1) DoF of every active DoF (NULL = identity). */
 int smf_set_copy_indices(smf_ctx *ctx, const uint32_t *active_to_level_u, const uint32_t *active_to_level_p);
 
+/* ---- distributed runs: one context per MPI rank / GPU ----------------------------------------------------------
+ * Replaces LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) around every cell loop
+ * (matrix_free_operators.cc:626, 724, 856, 1063; local_smoothing.cc:645, 746, 1407) and the MPI_Allreduce of every
+ * inner product.  Vectors hold every DoF the rank's cells touch; copies of a shared DoF are kept equal on all ranks.
+ * smf_comm_get_unique_id: rank 0 creates the id, the host broadcasts it (MPI_Bcast / torch.distributed), every rank
+ * passes it to smf_comm_init (collective; NCCL over NVLink). */
+#define SMF_UNIQUE_ID_BYTES 128
+int smf_comm_get_unique_id(char *id);
+int smf_comm_init(smf_ctx *ctx, int rank, int world, const char *id);
+/* Utilities::MPI::Partitioner of one level and DoF family (0: velocity, 1: pressure): for every neighbour rank
+ * (ascending) the shared nodes, given by their first local DoF index, in an order both sides agree on (e.g. by
+ * global index).  global_dof_ids (optional, [n_dofs]): partition-independent DoF numbers, used for the Chebyshev
+ * eigenvalue start vector.  Collective.  Call after smf_set_level and before smf_set_transfer. */
+typedef struct {
+  int n_neighbors;
+  const int *neighbor_ranks;
+  const int64_t *counts;
+  const uint32_t *const *nodes;
+  const int64_t *global_dof_ids;
+} smf_exchange;
+int smf_set_exchange(smf_ctx *ctx, int level, int family, const smf_exchange *x);
+/* compress(add) + update_ghost_values: every copy of a shared DoF := sum over the ranks (device vector). Collective. */
+int smf_exchange_add(smf_ctx *ctx, int level, int family, double *vec);
+
 /* OperatorCellData (include/aspect/simulator/solver/matrix_free_operators.h:91-208) +
  * set_cell_data (matrix_free_operators.cc:353-359, 779-783, 966-970): the table is COPIED to the device.
  * viscosity is [n_cells][n_per_cell] in the cell order of smf_set_level, n_per_cell = 1 or 3^dim. */
@@ -162,8 +186,8 @@ int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, dou
  * mode 0 = off, 1 = operator kernels of the finest level only (Stokes, A), 2 = every launch.
  * smf_profile_read synchronises and returns accumulated milliseconds and launch counts per bucket:
  * 0 Stokes vmult, 1 A finest level, 2 A coarser levels, 3 pressure mass, 4 B^T, 5 MG transfer,
- * 6 Chebyshev vector updates, 7 GMRES orthogonalisation, 8 other vector kernels. */
-#define SMF_PROFILE_BUCKETS 9
+ * 6 Chebyshev vector updates, 7 GMRES orthogonalisation, 8 other vector kernels, 9 halo exchanges. */
+#define SMF_PROFILE_BUCKETS 10
 int smf_profile_enable(smf_ctx *ctx, int mode);
 int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out);
 

@@ -1,0 +1,110 @@
+"""Distributed parity check, run as one process per GPU:
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py [R]
+The box has N coarse cells (one tree per rank).  Rank 0 additionally solves the SAME global problem on one GPU
+(world = 1, all trees local); the distributed operator application and the distributed solve must agree with it:
+operator relative 1e-12, outer iterations within +-1, solution relative 1e-8, and all copies of shared DoFs bitwise equal."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic  # noqa: E402
+
+REPS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def seeded_by_gid(gid, salt):
+    return np.sin(0.37 * gid.astype(np.float64) + salt)
+
+
+def setup(R, rep, rank, world, avg):
+    hier = synthetic.BoxHierarchy(3, R, None, rep, rank, world)
+    eta_q, rhs, ps = benchmarks.nsinker_problem(hier, 8, 1e4, avg)
+    h = StokesMatrixFreeHandler(3, device=torch.cuda.current_device())
+    h.global_start_vector = True
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, avg, ps)
+    h.build_preconditioner()
+    h.parameters.update({"Linear solver tolerance": 1e-6, "Number of cheap Stokes solver steps": 200})
+    return hier, h, rhs
+
+
+def gids(level, dim):
+    gu = level.global_node_ids("u")
+    gu = (gu[:, None] * dim + np.arange(dim)[None, :]).ravel()
+    return gu, level.global_node_ids("p")
+
+
+def run(h, hier, rhs):
+    act = hier.active
+    gu, gp = gids(act, 3)
+    xu, xp = seeded_by_gid(gu, 1.0), seeded_by_gid(gp, 2.0)
+    xu[act.constrained_u("zero").astype(np.int64)] = 0.0
+    src, dst = h.initialize_dof_vector(), h.initialize_dof_vector()
+    src[0].from_host(xu); src[1].from_host(xp)
+    h.stokes_matrix.vmult(dst, src)
+    yu, yp = dst[0].to_host(), dst[1].to_host()
+    # right-hand side: per-rank assembly gives partial sums on the interfaces -> compress(add)
+    n_u = act.n_u
+    b = h.initialize_dof_vector()
+    b[0].from_host(rhs[:n_u]); b[1].from_host(rhs[n_u:])
+    h.exchange_add(b[0], 0); h.exchange_add(b[1], 1)
+    sol = h.initialize_dof_vector()
+    out = h.solve_device(sol, b)
+    return gu, gp, yu, yp, sol[0].to_host(), sol[1].to_host(), out
+
+
+def main():
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    avg = "harmonic average"
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29513")
+    os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+    dist.init_process_group("nccl" if world > 1 else "gloo", device_id=torch.device("cuda", torch.cuda.current_device()) if world > 1 else None)
+    rep = REPS[world]
+    hier, h, rhs = setup(R, rep, rank, world, avg)
+    gu, gp, yu, yp, su, sp, out = run(h, hier, rhs)
+    h.close()
+    ref = [None]
+    if rank == 0:
+        hier1, h1, rhs1 = setup(R, rep, 0, 1, avg)
+        ref[0] = run(h1, hier1, rhs1)
+        h1.close()
+    dist.broadcast_object_list(ref, src=0)
+    gu1, gp1, yu1, yp1, su1, sp1, out1 = ref[0]
+    pu, pp = np.argsort(gu1), np.argsort(gp1)
+    iu, ip = pu[np.searchsorted(gu1[pu], gu)], pp[np.searchsorted(gp1[pp], gp)]
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    e_op = max(rel(yu, yu1[iu]), rel(yp, yp1[ip]))
+    e_sol_u = rel(su, su1[iu])
+    # no-slip box: pressure up to a constant
+    e_sol_p = rel(sp - sp.mean() + sp1[ip].mean(), sp1[ip])
+    ok = e_op < 1e-12 and abs(out["iterations"] - out1["iterations"]) <= 1 and e_sol_u < 1e-8 and out["converged"]
+    # copies of shared DoFs must be bitwise equal across ranks
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (gu, su))
+    if rank == 0:
+        table = {}
+        bitwise = True
+        for g, s in gathered:
+            for k, v in zip(g[::97], s[::97]):
+                if k in table and table[k] != v:
+                    bitwise = False
+                table[k] = v
+        ok = ok and bitwise
+        print(f"dist_check world={world} R={R}: operator rel err {e_op:.2e}, iterations {out['iterations']} (1 GPU: {out1['iterations']}), "
+              f"velocity rel diff {e_sol_u:.2e}, pressure rel diff {e_sol_p:.2e}, shared copies bitwise equal: {bitwise} -> {'OK' if ok else 'FAIL'}",
+              flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    if world > 1:
+        dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() > 0))
+
+
+if __name__ == "__main__":
+    main()
