@@ -58,7 +58,7 @@ EXPORTS = [
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",
     "smf_solve_host", "smf_kernel_launches", "smf_device_bytes", "smf_profile_enable", "smf_profile_read",
-    "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
+    "smf_exchange_count", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
 ]
 
 _lib = None
@@ -84,6 +84,8 @@ def load():
         lib.smf_kernel_launches.argtypes = [c_vp]
         lib.smf_device_bytes.restype = c_i64
         lib.smf_device_bytes.argtypes = [c_vp]
+        lib.smf_exchange_count.restype = c_i64
+        lib.smf_exchange_count.argtypes = [c_vp]
         lib.smf_destroy.restype = None
         lib.smf_destroy.argtypes = [c_vp]
         _lib = lib

@@ -502,5 +502,6 @@ int smf_synchronize(smf_ctx *ctx)
 }
 int64_t smf_kernel_launches(const smf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t smf_device_bytes(const smf_ctx *ctx) { return ctx ? ctx->bytes : 0; }
+int64_t smf_exchange_count(const smf_ctx *ctx) { return ctx ? ctx->exchanges : 0; }
 
 }  // extern "C"

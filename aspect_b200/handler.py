@@ -299,6 +299,9 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_profile_read(self.ctx, ptr(ms), ptr(cnt)))
         return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_BUCKETS, ms, cnt)}
 
+    def exchange_count(self):
+        return int(self.lib.smf_exchange_count(self.ctx))
+
     def kernel_launches(self):
         return int(self.lib.smf_kernel_launches(self.ctx))
 

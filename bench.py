@@ -39,9 +39,15 @@ METRIC = "nsinker_block_gmg_stokes_solve_throughput"
 UNIT = "MDoF/s"
 
 
-def workload_name(R):
-    return (f"nsinker 3D box, {N_SINKERS} sinkers, viscosity ratio 1e4, harmonic average, Q2-Q1, block GMG "
-            f"(GMRES({RESTART}), tol {TOL:g}), global refinement {R}")
+REPETITIONS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}      # coarse cells of the unit box, one tree per GPU
+
+
+def workload_name(R, world=1):
+    rep = REPETITIONS[world]
+    mesh = f"global refinement {R}" if world == 1 else (
+        f"{rep[0]}x{rep[1]}x{rep[2]} coarse cells x global refinement {R}" + (f" (= refinement {R + 1} of the unit cube)" if world == 8 else ""))
+    return (f"nsinker 3D unit box, {N_SINKERS} sinkers, viscosity ratio 1e4, harmonic average, Q2-Q1, block GMG "
+            f"(GMRES({RESTART}), tol {TOL:g}), {mesh}")
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -85,7 +91,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": warm, "ms_per_step": res["wall_s"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.refinement), "parallelism": "host cores (OpenMP)"},
+            "config": {"workload": workload_name(args.refinement, args.gpus if args.gpus in REPETITIONS else 1),
+                       "parallelism": "host cores (OpenMP)"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "solve_wall_s": res["wall_s"], "iterations": res["iterations"]}
@@ -129,9 +136,9 @@ class ClockSampler:
         return out
 
 
-def build_problem(R, device):
+def build_problem(R, device, rank=0, world=1):
     from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
-    hier = synthetic.BoxHierarchy(3, R)
+    hier = synthetic.BoxHierarchy(3, R, None, REPETITIONS[world], rank, world)
     eta_q, rhs, ps = benchmarks.nsinker_problem(hier, N_SINKERS, VISCOSITY_RATIO, AVERAGING)
     h = StokesMatrixFreeHandler(3, device=device)
     h.setup_dofs(hier, "zero")
@@ -201,7 +208,7 @@ def main():
     from aspect_b200 import SMF_ACTIVE
     R = args.refinement
     t_setup = time.time()
-    hier, h, rhs = build_problem(R, local_rank)
+    hier, h, rhs = build_problem(R, local_rank, rank, world)
     stream = torch.cuda.Stream()
     h.set_stream(stream.cuda_stream)
     n_u, n_p, n_cells = hier.active.n_u, hier.active.n_p, hier.active.n_cells
@@ -210,6 +217,14 @@ def main():
 
     rhs_dev, sol_dev = h.initialize_dof_vector(), h.initialize_dof_vector()
     rhs_dev[0].from_host(rhs[:n_u]); rhs_dev[1].from_host(rhs[n_u:])
+    if world > 1:       # per-rank assembly leaves partial sums on the subdomain interfaces: compress(add)
+        h.exchange_add(rhs_dev[0], 0); h.exchange_add(rhs_dev[1], 1)
+        rhs = np.concatenate([rhs_dev[0].to_host(), rhs_dev[1].to_host()])
+    # global DoF count: shared DoFs counted once
+    n_global = n
+    if world > 1:
+        act = hier.active
+        n_global = 3 * int(np.prod(act.grid_u)) + int(np.prod(act.grid_p))
     # pinned host buffers of the end-to-end arm
     rhs_pin = torch.empty(n, dtype=torch.float64).pin_memory()
     sol_pin = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -222,11 +237,12 @@ def main():
             sol_dev[0].zero(); sol_dev[1].zero()
             h.solve_device(sol_dev, rhs_dev)
         h.profile_enable(1)
-        launches0 = h.kernel_launches()
+        launches0, exch0 = h.kernel_launches(), h.exchange_count()
         clocks = ClockSampler(local_rank)
         t_dev, outs = timed_solves(torch, h, stream, rhs_dev, sol_dev, n_u, n_p, args.steps, barrier)
         clock_info = clocks.stop()
         launches = h.kernel_launches() - launches0
+        exchanges = (h.exchange_count() - exch0) // max(args.steps, 1)
         prof = h.profile_read()
         h.profile_enable(0)
         t_dev = max_over_ranks(t_dev)
@@ -308,17 +324,17 @@ def main():
     except (OSError, ValueError):
         pass
     line = {
-        "metric": METRIC, "value": world * n / wall / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": n_global / wall / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(R), "dofs_per_gpu": n, "cells_per_gpu": n_cells, "levels": R + 1,
-                   "parallelism": "1 subdomain per GPU" if world == 1 else f"{world} independent replicas (no exchange yet)",
+        "config": {"workload": workload_name(R, world), "dofs_global": n_global, "dofs_per_gpu": n, "cells_per_gpu": n_cells, "levels": R + 1,
+                   "parallelism": "1 subdomain per GPU" if world == 1 else f"domain decomposition, {world} subdomains (one coarse-cell tree per GPU), NCCL halo exchange + all-reduce",
                    "l2": "vectors (%.0f MB each) exceed the 126 MB L2" % (8e-6 * n) if 8 * n > 126e6 else "vectors fit L2: each solve streams >100 distinct vectors between reuses",
                    "impl": "b200"},
         "solve_wall_s": wall, "iterations": its,
         "n_A_preconditioner": outs[-1]["n_A_preconditioner"], "n_S_preconditioner": outs[-1]["n_S_preconditioner"],
         "solve_setup_s": outs[-1]["setup_seconds"], "final_residual_over_tol": outs[-1]["final_residual"] / outs[-1]["tolerance"],
-        "e2e": {"value": world * n / wall_e2e / 1e6, "unit": UNIT, "wall_s": wall_e2e,
+        "e2e": {"value": n_global / wall_e2e / 1e6, "unit": UNIT, "wall_s": wall_e2e,
                 "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
                 "call": "StokesMatrixFreeHandler.solve -> smf_solve_host (pinned host rhs + guess in, solution out)"},
         "gpu_launches": int(launches),
@@ -326,18 +342,18 @@ def main():
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes_A / t_A_kernel / 1e9 / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_A, "launches_timed": a_cnt,
                      "avg_launch_us": t_A_kernel * 1e6, "share_of_solve": a_ms / 1e3 / t_dev},
-        "vmult": {"stokes_gdofs": world * n / t_stokes / 1e9, "stokes_kernel_gdofs": world * n / t_stokes_kernel / 1e9,
+        "vmult": {"stokes_gdofs": n_global / t_stokes / 1e9, "stokes_kernel_gdofs": n_global / t_stokes_kernel / 1e9,
                   "stokes_roofline_frac": bytes_stokes / t_stokes_kernel / 1e9 / peak,
-                  "A_gdofs": world * n_u / t_A / 1e9, "mass_gdofs": world * n_p / t_M / 1e9,
-                  "stokes_host_buffers_gdofs": world * n / t_stokes_host / 1e9,
+                  "A_gdofs": n_global / n * n_u / t_A / 1e9, "mass_gdofs": n_global / n * n_p / t_M / 1e9,
+                  "stokes_host_buffers_gdofs": n_global / t_stokes_host / 1e9,
                   "note": "stokes_gdofs includes zeroing dst (StokesOperator::vmult); *_kernel_* is the cell kernel alone"},
         "time_split_ms": {k: round(v[0], 3) for k, v in split.items()},
         "launch_split": {k: v[1] for k, v in split.items()},
-        "clocks": clock_info, "host_setup_s": setup_s,
+        "clocks": clock_info, "host_setup_s": setup_s, "halo_exchanges_per_solve": int(exchanges),
     }
     h.close()
     # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------
-    if not args.no_cfg2 and R != 5:
+    if not args.no_cfg2 and R != 5 and world == 1:
         hier5, h5, rhs5 = build_problem(5, local_rank)
         n5 = hier5.active.n_u + hier5.active.n_p
         pin5 = torch.empty(n5, dtype=torch.float64).pin_memory().numpy()

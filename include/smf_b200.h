@@ -194,6 +194,7 @@ int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out);
 /* bookkeeping the bench harness reports */
 int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this context so far */
 int64_t smf_device_bytes(const smf_ctx *ctx);        /* get_*_memory_consumption() analogue      */
+int64_t smf_exchange_count(const smf_ctx *ctx);      /* halo exchanges performed by this context so far */
 
 #ifdef __cplusplus
 }
