@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libsmf_b200.so")
 
 SMF_OK, SMF_ERR_INVALID, SMF_ERR_CUDA, SMF_ERR_UNSUPPORTED, SMF_NO_CONVERGENCE = 0, 1, 2, 3, 4
 SMF_ACTIVE = -1
-SMF_OPT_STRUCTURED_BRICKS, SMF_OPT_CUDA_GRAPHS = 0, 1
+SMF_OPT_STRUCTURED_BRICKS, SMF_OPT_CUDA_GRAPHS, SMF_OPT_ORTHO_SINGLE_PASS, SMF_OPT_PIPELINED_KERNEL, SMF_OPT_MAX_GRID_BLOCKS = 0, 1, 2, 3, 4
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p

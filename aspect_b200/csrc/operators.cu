@@ -14,6 +14,7 @@
 // flushed once per batch: nodes private to the batch with plain stores, shared nodes with one RED each.
 #include "smf_internal.h"
 #include <type_traits>
+#include <algorithm>
 
 namespace smf {
 
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
   int lb[4] = {0, 0, 0, 0};
   if (STRUCT) {
     const int x = sb_x(lane), y = sb_y(lane), z = sb_z(lane);
-    lb[0] = x + 12 * y + 60 * z; lb[1] = x + 4 * y + 20 * z; lb[2] = y + 4 * x + 20 * z; lb[3] = x + 4 * y + 16 * z;
+    #pragma unroll
+    for (int v = 0; v < 4; ++v) lb[v] = x + sb_sy(v) * y + sb_sz(v) * z;
   }
   double *my_stage = s_stage + c * MU;
   const auto slot = [&](int n) -> int { return STRUCT ? sbn_const(n) + lb[sbn_variant(n)] : (int)s_loc[n * SUB + lane]; };
@@ -496,6 +498,166 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
       else if (j < n_excl_p) P.dst_p[idx] = s_stagep[j];
       else atomicAdd(P.dst_p + idx, s_stagep[j]);
     }
+}
+
+// ---- structured bricks, persistent and software-pipelined (3D, A block and Stokes) -------------------------------
+// Same arithmetic as velocity_kernel<3, MODE, PERQ, true>, organised so that no global-memory latency is exposed:
+//  * the grid is one wave of resident blocks (4 per SM); block k walks bricks k, k + G, k + 2G, ...;
+//  * while brick i is computed, cp.async copies the node list of brick i+1 (16-byte chunks) and then its DoF values
+//    (8-byte copies straight into the staging slots; constrained DoFs arrive as zero through the src-size operand);
+//  * two staging buffers: sA receives source values, sB accumulates results.  Accumulation needs no zero fill: the
+//    rounds run in ascending order of the node's low-face pattern, so for every lattice point the first cell to touch
+//    it is known per lane (first-touch mask) and stores instead of adding;
+//  * the flush reads the node list from shared memory (no dependent global load in front of the stores / REDs);
+//  * the three symmetric-stress pairs are spread evenly: component c is the "lower" thread of pair {c, c+1} and the
+//    "upper" thread of pair {c-1, c}.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void *src, int src_bytes)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// low-face pattern of local node n: bit d set when the node lies on the cell's low face in direction d
+__host__ __device__ constexpr int lowface(int n) { return ((n % 3) == 0) + 2 * (((n / 3) % 3) == 0) + 4 * ((n / 9) == 0); }
+
+constexpr int SBK_THREADS = 96;
+constexpr int SBK_SU = 13;            // ceil(3 * 405 / 96) staged items per thread
+constexpr size_t sbk_smem_bytes() { return (size_t)(2 * 3 * SB_SLOTS + 3 * 27 * SUB) * sizeof(double) + 2 * (size_t)SB_LIST_BYTES; }
+
+template <int MODE, bool PERQ>
+__global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellParams P, const unsigned char *lists, int n_batches)
+{
+  static_assert(MODE == 0, "only the A block is implemented in the pipelined kernel so far");
+  constexpr int DIM = 3, NN = 27, MU = SB_SLOTS;
+  extern __shared__ __align__(16) double smem[];
+  double *sA = smem;                       // [3][MU] source values of the current brick (cp.async target)
+  double *sB = sA + 3 * MU;                // [3][MU] accumulated results of the current brick
+  double *s_ex = sB + 3 * MU;              // [3][NN][32] pair buffers, indexed by the lower component of the pair
+  unsigned char *sI = reinterpret_cast<unsigned char *>(s_ex + 3 * NN * SUB);   // [2][SB_LIST_BYTES] node lists
+  const int tid = threadIdx.x, c = tid >> 5, lane = tid & 31, G = gridDim.x;
+  int b = blockIdx.x;
+  if (b >= n_batches) return;
+
+  // lane constants: slot offsets of this lane's cell and its first-touch mask
+  const int x = sb_x(lane), y = sb_y(lane), z = sb_z(lane);
+  int lb[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) lb[v] = x + sb_sy(v) * y + sb_sz(v) * z;
+  unsigned first_mask = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if ((!(r & 1) || x == 0) && (!(r & 2) || y == 0) && (!(r & 4) || z == 0)) first_mask |= 1u << r;
+  const auto slot = [&](int n) -> int { return sbn_const(n) + lb[sbn_variant(n)]; };
+  const int j0 = tid / 3, d0 = tid - 3 * j0;      // staged item k of this thread: node j0 + 32 k, component d0
+  const double ec = P.ee[c];
+  const int cl = c == 2 ? 0 : c + 1;              // partner in the pair where this thread is the lower one
+  const int cu = c == 0 ? 2 : c - 1;              // partner in the pair where this thread is the upper one
+  const double el = P.ee[cl], eu = P.ee[cu];
+  double *ex_lo = s_ex + (size_t)c * NN * SUB + lane;     // pair {c, c+1}
+  double *ex_up = s_ex + (size_t)cu * NN * SUB + lane;    // pair {c-1, c}
+  double *myA = sA + c * MU, *myB = sB + c * MU;
+
+  const auto load_list = [&](unsigned char *dst, int brick) {
+    const unsigned char *src = lists + (size_t)brick * SB_LIST_BYTES;
+    for (int ch = tid; ch < SB_LIST_BYTES / 16; ch += SBK_THREADS) cp_async16(smem_u32(dst + 16 * ch), src + 16 * ch);
+  };
+  const auto issue_values = [&](const unsigned char *I) {
+    const uint32_t *le = reinterpret_cast<const uint32_t *>(I);
+    const uint16_t *ls = reinterpret_cast<const uint16_t *>(I + SB_LIST * 4);
+    const uint32_t base = smem_u32(sA + d0 * MU);
+#pragma unroll
+    for (int k = 0; k < SBK_SU; ++k) {
+      const int j = j0 + 32 * k;
+      if (j < 405) {
+        const uint32_t e = le[j];
+        const bool cons = (e >> (NODE_FLAG_SHIFT + d0)) & 1u;
+        cp_async8_zfill(base + 8u * ls[j], P.src_u + (e & NODE_IDX_MASK) + d0, cons ? 0 : 8);
+      }
+    }
+  };
+
+  // prologue: node list and values of the first brick
+  load_list(sI, b);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  issue_values(sI);
+  cp_async_commit();
+  double eta_next = PERQ ? 1.0 : P.eta_t[(size_t)b * P.n_eta * SUB + lane];
+
+  for (int it = 0; b < n_batches; b += G, ++it) {
+    unsigned char *I_cur = sI + (it & 1) * SB_LIST_BYTES, *I_nxt = sI + ((it + 1) & 1) * SB_LIST_BYTES;
+    const int bn = b + G;
+    cp_async_wait_all();
+    __syncthreads();                        // values of this brick are in sA; the previous flush is done with sB / I_nxt
+    if (bn < n_batches) load_list(I_nxt, bn);
+    cp_async_commit();
+    const double eta0 = eta_next;
+    const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+
+    double u[NN], T[NN];
+#pragma unroll
+    for (int n = 0; n < NN; ++n) u[n] = myA[slot(n)];
+    interp_all<DIM>(u);
+    // diagonal direction: T = (2D'_c)^T [ 2 eta w vol e_c^2 (2D'_c u) ]
+    {
+      const double f2 = 2.0 * ec * ec * P.vol * eta0;
+      SMF_DIR_SWITCH(c, (diag_dir<DIM, 0, PERQ>(u, T, f2, etab, false)), (diag_dir<DIM, 1, PERQ>(u, T, f2, etab, false)),
+                     (diag_dir<DIM, 2, PERQ>(u, T, f2, etab, false)));
+    }
+    // pair {c, c+1}: publish e_{c+1} (2D'_{c+1} u_c)
+    SMF_DIR_SWITCH(cl, (publish_dir<DIM, 0>(u, ex_lo, el)), (publish_dir<DIM, 1>(u, ex_lo, el)), (publish_dir<DIM, 2>(u, ex_lo, el)));
+    cp_async_wait_all();                    // (this thread's chunks of the next node list)
+    __syncthreads();                        // publishes visible; every gather from sA is done; next list visible
+    if (bn < n_batches) {
+      issue_values(I_nxt);
+      if (!PERQ) eta_next = P.eta_t[(size_t)bn * P.n_eta * SUB + lane];
+    }
+    cp_async_commit();
+    // pair {c-1, c}: X = eta w vol (e_{c-1} 2D'_{c-1} u_c + partner), T += e_{c-1} (2D'_{c-1})^T X, X published
+    {
+      const double cvol = P.vol * eta0;
+      SMF_DIR_SWITCH(cu, (upper_dir<DIM, 0, PERQ>(u, T, ex_up, eu, cvol, etab)), (upper_dir<DIM, 1, PERQ>(u, T, ex_up, eu, cvol, etab)),
+                     (upper_dir<DIM, 2, PERQ>(u, T, ex_up, eu, cvol, etab)));
+    }
+    __syncthreads();
+    SMF_DIR_SWITCH(cl, (lower_dir<DIM, 0>(T, ex_lo, el)), (lower_dir<DIM, 1>(T, ex_lo, el)), (lower_dir<DIM, 2>(T, ex_lo, el)));
+    interpT_all<DIM>(T);
+    // accumulate into sB in ascending order of the low-face pattern; the first cell to touch a lattice point stores
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const bool first = (first_mask >> r) & 1u;
+#pragma unroll
+      for (int n = 0; n < NN; ++n)
+        if (lowface(n) == r) {
+          double v = T[n];
+          if (r != 0 && !first) v += myB[slot(n)];
+          myB[slot(n)] = v;
+        }
+      __syncwarp();
+    }
+    __syncthreads();
+    // flush: private nodes with plain stores, shared nodes with one RED per DoF, constrained DoFs dst = src
+    {
+      const uint32_t *le = reinterpret_cast<const uint32_t *>(I_cur);
+      const uint16_t *ls = reinterpret_cast<const uint16_t *>(I_cur + SB_LIST * 4);
+      const double *sBd = sB + d0 * MU;
+#pragma unroll
+      for (int k = 0; k < SBK_SU; ++k) {
+        const int j = j0 + 32 * k;
+        if (j < 405) {
+          const uint32_t e = le[j];
+          const uint32_t idx = (e & NODE_IDX_MASK) + d0;
+          const double v = sBd[ls[j]];
+          if ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) P.dst_u[idx] = P.src_u[idx];
+          else if (!(e & NODE_SHARED_BIT)) P.dst_u[idx] = v;
+          else atomicAdd(P.dst_u + idx, v);
+        }
+      }
+    }
+  }
 }
 
 // ---- pressure mass matrix: one warp per batch (one cell per lane), MASS_WARPS independent warps per block --------
@@ -835,8 +997,35 @@ template <int DIM, int MODE, bool PERQ, bool STRUCT> static int launch_velocity_
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;
 }
+template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, LevelDev &L, CellParams &P)
+{
+  constexpr size_t smem = sbk_smem_bytes();
+  static int resident = 0;
+  if (resident == 0) {
+    SMF_CUDA(cudaFuncSetAttribute(velocity_sb_kernel<MODE, PERQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 148;
+    SMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+    SMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, velocity_sb_kernel<MODE, PERQ>, SBK_THREADS, smem));
+    if (per_sm < 1) return ctx->fail(SMF_ERR_CUDA, "velocity_sb_kernel does not fit on an SM");
+    resident = per_sm * sms;
+  }
+  const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
+  {
+    ProfScope prof(ctx, MODE == 1 ? B_STOKES : (fine ? B_A_FINE : B_A_COARSE));
+    int grid = std::min(L.n_batches, resident);
+    if (ctx->max_grid_blocks > 0) grid = std::min(grid, ctx->max_grid_blocks);
+    velocity_sb_kernel<MODE, PERQ><<<grid, SBK_THREADS, smem, ctx->stream>>>(P, L.sb_lists, L.n_batches);
+  }
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
 template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
+  if (DIM == 3 && L.structured && MODE == 0 && ctx->use_pipelined && L.sb_lists) {
+    if (L.n_eta != 1) return launch_velocity_sb<0, true>(ctx, L, P);
+    return launch_velocity_sb<0, false>(ctx, L, P);
+  }
   if (DIM == 3 && L.structured) {
     if (MODE != 2 && L.n_eta != 1) return launch_velocity_t<3, MODE, true, true>(ctx, L, P);
     return launch_velocity_t<3, MODE, false, true>(ctx, L, P);

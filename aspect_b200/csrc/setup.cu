@@ -27,7 +27,7 @@ template <class T> static int upload(smf_ctx *ctx, T **dev, const std::vector<T>
 
 static void free_level(LevelDev &L)
 {
-  cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
+  cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.sb_lists); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
   cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
   cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M);
   free_exchange(L.ex_u); free_exchange(L.ex_p);
@@ -220,6 +220,9 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   if (!ctx) return SMF_ERR_INVALID;
   if (option == SMF_OPT_STRUCTURED_BRICKS) ctx->allow_structured = value ? 1 : 0;
   else if (option == SMF_OPT_CUDA_GRAPHS) { ctx->use_graphs = value ? 1 : 0; ctx->graph_A_stale = ctx->graph_S_stale = true; }
+  else if (option == SMF_OPT_ORTHO_SINGLE_PASS) ctx->ortho_single_pass = value ? 1 : 0;
+  else if (option == SMF_OPT_PIPELINED_KERNEL) ctx->use_pipelined = value ? 1 : 0;
+  else if (option == SMF_OPT_MAX_GRID_BLOCKS) ctx->max_grid_blocks = value > 0 ? value : 0;
   else return ctx->fail(SMF_ERR_INVALID, "unknown option");
   return SMF_OK;
 }
@@ -322,6 +325,14 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   if ((e = upload(ctx, &L.batch_info, info, &L.bytes))) return e;
   if ((e = upload(ctx, &L.node_list_u, nl_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.node_slot_u, slot_u, &L.bytes))) return e;
+  if (L.structured) {     // entries and slots of a brick side by side: one contiguous block per brick for the pipelined kernel
+    std::vector<unsigned char> sbl((size_t)L.n_batches * SB_LIST_BYTES, 0);
+    for (int b = 0; b < L.n_batches; ++b) {
+      std::memcpy(sbl.data() + (size_t)b * SB_LIST_BYTES, nl_u.data() + (size_t)b * SB_LIST, SB_LIST * 4);
+      std::memcpy(sbl.data() + (size_t)b * SB_LIST_BYTES + SB_LIST * 4, slot_u.data() + (size_t)b * SB_LIST, SB_LIST * 2);
+    }
+    if ((e = upload(ctx, &L.sb_lists, sbl, &L.bytes))) return e;
+  }
   if ((e = upload(ctx, &L.node_list_p, nl_p, &L.bytes))) return e;
   if ((e = upload(ctx, &L.cell_loc_u, loc_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.cell_loc_p, loc_p, &L.bytes))) return e;

@@ -22,15 +22,21 @@ constexpr uint32_t NODE_FLAG_SHIFT = 29;          // bits 29..31: component c of
 // When the 32 cells of a batch form a 4x4x2 brick in Morton order (always the case on uniformly refined levels),
 // its 9x9x5 node lattice is staged in shared memory in a layout that needs no per-cell slot table and is free of
 // bank conflicts: nodes are grouped by the parity of their lattice coordinates (X, Y, Z) -- for a fixed local node
-// of the cell, all 32 cells hit the same parity class at (x, y, z) + const -- and inside a class the two fast
-// strides are chosen so that the 16 (x, y) combinations of a z-plane of cells fall into 16 different 8-byte banks:
-//   class (X even, Y even): X/2 + 12 Y/2 + 60 Z/2      (5 x 5 used of a 12-wide row)
-//   class (X odd,  Y even): X/2 +  4 Y/2 + 20 Z/2
-//   class (X even, Y odd ): Y/2 +  4 X/2 + 20 Z/2
-//   class (X odd,  Y odd ): X/2 +  4 Y/2 + 16 Z/2
+// of the cell, all 32 cells hit the same parity class at (x, y, z) + const -- and inside a class the strides are
+// chosen so that the 16 lanes of a half-warp (a 64-bit shared-memory access is served one half-warp at a time; in
+// Morton order the lane bits are x0 y0 z0 x1 | y1) fall into 16 different 8-byte banks:
+//   offset = ox * 1 + oy * SY + oz * SZ  with (SY, SZ) mod 16 = (8, 4) or (4, 8)  ->  bank bits x0:1 x1:2 y0:SY z0:SZ
+//   class (X even, Y even): SY  8, SZ 52   (5 x 5 nodes per plane)
+//   class (X odd,  Y even): SY  4, SZ 24   (4 x 5)
+//   class (X even, Y odd ): SY  8, SZ 36   (5 x 4)
+//   class (X odd,  Y odd ): SY  4, SZ 24   (4 x 4)
 __host__ __device__ constexpr int sb_variant(int px, int py) { return px + 2 * py; }
-__host__ __device__ constexpr int sb_plane(int v) { return v == 0 ? 60 : (v == 3 ? 16 : 20); }
-__host__ __device__ constexpr int sb_class_size(int v, int pz) { return sb_plane(v) * (pz ? 2 : 3); }
+__host__ __device__ constexpr int sb_sy(int v) { return (v & 1) ? 4 : 8; }
+__host__ __device__ constexpr int sb_sz(int v) { return v == 0 ? 52 : (v == 2 ? 36 : 24); }
+__host__ __device__ constexpr int sb_nx(int v) { return (v & 1) ? 4 : 5; }
+__host__ __device__ constexpr int sb_ny(int v) { return (v & 2) ? 4 : 5; }
+__host__ __device__ constexpr int sb_class_size(int v, int pz)
+{ return sb_sz(v) * (pz ? 1 : 2) + sb_sy(v) * (sb_ny(v) - 1) + sb_nx(v); }
 __host__ __device__ constexpr int sb_class_base(int v, int pz)
 {
   int b = 0;
@@ -41,13 +47,14 @@ __host__ __device__ constexpr int sb_class_base(int v, int pz)
     }
   return b;
 }
-__host__ __device__ constexpr int sb_offset(int v, int ox, int oy, int oz)
-{ return v == 0 ? ox + 12 * oy + 60 * oz : (v == 1 ? ox + 4 * oy + 20 * oz : (v == 2 ? oy + 4 * ox + 20 * oz : ox + 4 * oy + 16 * oz)); }
+__host__ __device__ constexpr int sb_offset(int v, int ox, int oy, int oz) { return ox + sb_sy(v) * oy + sb_sz(v) * oz; }
 // slot of lattice point (X, Y, Z), 0 <= X, Y < 9, 0 <= Z < 5
 __host__ __device__ constexpr int sb_slot(int X, int Y, int Z)
 { return sb_class_base(sb_variant(X & 1, Y & 1), Z & 1) + sb_offset(sb_variant(X & 1, Y & 1), X >> 1, Y >> 1, Z >> 1); }
-constexpr int SB_SLOTS = 580;   // = sb_class_base(3, 1) + sb_class_size(3, 1)
+constexpr int SB_SLOTS = 612;   // = sb_class_base(3, 1) + sb_class_size(3, 1)
 constexpr int SB_LIST = 408;    // node-list entries per structured brick (9 * 9 * 5 = 405, padded)
+constexpr int SB_LIST_BYTES = SB_LIST * 6;   // pipelined kernel: per brick [SB_LIST] uint32 entries, then [SB_LIST] uint16 slots
+static_assert(SB_LIST_BYTES % 16 == 0, "node lists are copied in 16-byte chunks");
 static_assert(sb_class_base(3, 1) + sb_class_size(3, 1) == SB_SLOTS, "structured brick layout size");
 // brick coordinates of lane l (Morton order inside the batch: x0 y0 z0 x1 y1)
 __host__ __device__ constexpr int sb_x(int l) { return (l & 1) | (((l >> 3) & 1) << 1); }
@@ -83,6 +90,7 @@ struct LevelDev {
   uint32_t *node_list_u = nullptr;            // [n_batches][list_stride_u]  ascending DoF index (general: exclusive nodes first)
   uint16_t *node_slot_u = nullptr;            // [n_batches][list_stride_u]  structured bricks: staging slot of each list entry
   int list_stride_u = 0;                      // entries per batch in node_list_u (general path: = max_nodes_u)
+  unsigned char *sb_lists = nullptr;          // structured bricks: [n_batches][SB_LIST_BYTES] entries + slots (velocity_sb_kernel)
   uint32_t *node_list_p = nullptr;            // [n_batches][max_nodes_p]
   uint16_t *cell_loc_u = nullptr;             // [n_batches][KSUB][3^dim][SUB]
   uint16_t *cell_loc_p = nullptr;             // [n_batches][KSUB][2^dim][SUB]
@@ -161,6 +169,9 @@ struct smf_ctx {
   int64_t graph_A_launches = 0, graph_S_launches = 0; // kernels inside one replay
   int graph_level = -1;                               // finest level inside the graphs (-1: graphs unused)
   int use_graphs = 1;
+  int ortho_single_pass = 1;                          // GMRES: re-orthogonalise through the Gram matrix (1) or with a second pass over the basis (0)
+  int max_grid_blocks = 0;                            // > 0: cap on the persistent grids (tests: forces several bricks per block)
+  int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
   int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)
   // profiler: 0 off, 1 operator kernels of the finest level only, 2 every launch
   int prof_mode = 0;
@@ -233,6 +244,9 @@ int vec_dot(smf_ctx *ctx, const double *x, const double *y, int64_t n, double *h
 int vec_norm2(smf_ctx *ctx, const double *x, int64_t n, double *host_result);                  // synchronises
 // h_j = V_j . w (j < k) and w.w; results stay on the device (and go to host_out when sync is set)
 int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double *w, int64_t n, double *host_out, bool sync);
+// as vec_multi_dot (results stay on the device), and V[k-1] is dotted with the basis in the same pass: leaves the
+// re-orthogonalised (CGS2-equivalent) coefficients h = h1 - (V^T V - I) h1 on the device for vec_multi_axpy_from_dots
+int vec_multi_dot_gram(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double *w, int64_t n);
 // w -= sum_j h_j V_j with the h of the preceding vec_multi_dot; host_out = {h_0..h_{k-1}, |w_old|^2, |w_new|^2}
 int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *host_out);
 int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const double *coef_host, int k, int64_t n);

@@ -309,7 +309,10 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
   // deal.II 9.6's default (delayed classical Gram-Schmidt, DCGS2) orthogonalises twice per iteration; its
   // numerics are those of CGS2, restated here as "always re-orthogonalise".  Single-pass CGS loses the
   // orthogonality of the basis on badly scaled problems (SolCx, pressure scaling 1e5) and stagnates.
+  // As in DCGS2 the second projection costs no second sweep over the basis: it is formed from the Gram matrix
+  // of the basis (vec_multi_dot_gram), so one iteration streams the basis twice (dots, update).
   bool re_orth = true;
+  const bool single_pass = ctx->ortho_single_pass != 0;
   int state = 0;   // 0 iterate, 1 success, 2 failure
   double rho = 0;
   bool first = true;
@@ -337,12 +340,13 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
       dim = j + 1;
       const bool consider = !re_orth && (its % 5 == 0);
       VecBucket vb(ctx, B_ORTHO);
-      TRY(vec_multi_dot(ctx, K.data(), dim, vv, n, nullptr, false));
+      if (single_pass) TRY(vec_multi_dot_gram(ctx, K.data(), dim, vv, n));
+      else TRY(vec_multi_dot(ctx, K.data(), dim, vv, n, nullptr, false));
       TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, h.data()));   // h[0..dim-1], |vv_old|^2, |vv_new|^2
       const double norm_start = std::sqrt(h[dim]);
       double nrm = std::sqrt(h[dim + 1]);
       if (consider && !(nrm > 10.0 * norm_start * std::sqrt(eps))) re_orth = true;
-      if (re_orth) {
+      if (re_orth && !single_pass) {
         TRY(vec_multi_dot(ctx, K.data(), dim, vv, n, nullptr, false));
         TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, hh.data()));
         for (int i = 0; i < dim; ++i) h[i] += hh[i];

@@ -97,30 +97,37 @@ __device__ __forceinline__ double2 load2(const double *p, int64_t i, int64_t n, 
   r.y = (i + 1 < n) ? p[i + 1] : 0.0;
   return r;
 }
-__global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int k, const double *w, int64_t n,
+// TWO: a second right-hand side w2 is dotted with the same basis in the same pass (out[k + 1 + j] = V[j] . w2): the
+// Gram-matrix column the single-pass re-orthogonalisation of the GMRES driver needs (vec_multi_dot_gram below).
+template <bool TWO>
+__global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int k, const double *w, const double *w2, int64_t n,
                                                       double *partial, unsigned int *counter, double *out, int vec2,
                                                       const double *wgt)
 {
-  __shared__ double s_acc[VT / 32][MD_CHUNK + 4];
+  constexpr int NR = TWO ? 2 : 1;
+  __shared__ double s_acc[VT / 32][NR * (MD_CHUNK + 4)];
   __shared__ const double *s_v[MD_CHUNK];
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VT / 32;
-  for (int j = threadIdx.x; j < nw * (MD_CHUNK + 4); j += VT) (&s_acc[0][0])[j] = 0.0;
+  for (int j = threadIdx.x; j < nw * NR * (MD_CHUNK + 4); j += VT) (&s_acc[0][0])[j] = 0.0;
   for (int j = threadIdx.x; j < k; j += VT) s_v[j] = V[j];
   __syncthreads();
   constexpr int NL = MD_W / 2;
   const int64_t chunk = (int64_t)VT * MD_W;
+  const int nout = NR * k + 1;
   for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
-    double2 ww[NL];
+    double2 ww[NL], ww2[TWO ? NL : 1];
     double wn = 0.0;
 #pragma unroll
     for (int r = 0; r < NL; ++r) {
       const int64_t i = base + ((int64_t)r * VT + threadIdx.x) * 2;
       ww[r] = load2(w, i, n, vec2);
+      if (TWO) ww2[r] = load2(w2, i, n, vec2);
       const double x0 = ww[r].x, y0 = ww[r].y;
       if (wgt) {       // distributed run: every shared DoF counts 1 / (number of ranks that hold it)
         const double2 g = load2(wgt, i, n, vec2);
         ww[r].x *= g.x; ww[r].y *= g.y;
+        if (TWO) { ww2[r].x *= g.x; ww2[r].y *= g.y; }
       }
       wn = fma(ww[r].x, x0, fma(ww[r].y, y0, wn));
     }
@@ -139,16 +146,23 @@ __global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int
         for (int r = 0; r < NL; ++r) a = fma(vv[jj][r].x, ww[r].x, fma(vv[jj][r].y, ww[r].y, a));
         a = warp_sum(a);
         if (lane == 0 && g + jj < k) s_acc[warp][g + jj] += a;
+        if (TWO) {
+          double a2 = 0.0;
+#pragma unroll
+          for (int r = 0; r < NL; ++r) a2 = fma(vv[jj][r].x, ww2[r].x, fma(vv[jj][r].y, ww2[r].y, a2));
+          a2 = warp_sum(a2);
+          if (lane == 0 && g + jj < k) s_acc[warp][k + 1 + g + jj] += a2;
+        }
       }
     }
     wn = warp_sum(wn);
     if (lane == 0) s_acc[warp][k] += wn;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j <= k; j += VT) {
+  for (int j = threadIdx.x; j < nout; j += VT) {
     double a = 0.0;
     for (int q = 0; q < nw; ++q) a += s_acc[q][j];
-    partial[(size_t)blockIdx.x * (k + 1) + j] = a;
+    partial[(size_t)blockIdx.x * nout + j] = a;
   }
   __threadfence();
   __syncthreads();
@@ -157,9 +171,9 @@ __global__ void __launch_bounds__(VT, 2) k_multi_dot(const double *const *V, int
   if (s_last) {
     __threadfence();
     // one warp per result; lanes stride over the blocks' partials, then a shuffle tree: the order is fixed
-    for (int j = warp; j <= k; j += nw) {
+    for (int j = warp; j < nout; j += nw) {
       double a = 0.0;
-      for (unsigned bI = lane; bI < gridDim.x; bI += 32) a += partial[(size_t)bI * (k + 1) + j];
+      for (unsigned bI = lane; bI < gridDim.x; bI += 32) a += partial[(size_t)bI * nout + j];
       a = warp_sum(a);
       if (lane == 0) out[j] = a;
     }
@@ -225,22 +239,28 @@ __global__ void __launch_bounds__(VT) k_multi_axpy(double *w, const double *cons
   }
 }
 
-// scratch layout (doubles): [0, 128) results | [128, 128 + RED_BLOCKS*(MD_CHUNK+1)) partials | then 2 counters | device pointer table
+// scratch layout (doubles): [0, SCR_OUT) results | [SCR_OUT, SCR_OUT + RED_BLOCKS*SCR_PART) partials | then 2 counters |
+// device pointer table | Gram-matrix defect E = V^T V - I of the current Krylov basis (GRAM_LD x GRAM_LD)
+constexpr int SCR_OUT = 384;                    // results: [0, 2k] dots, [OUT_NRM] the norm multi_axpy returns
+constexpr int OUT_NRM = 2 * MD_CHUNK + 4;
+constexpr int SCR_PART = 2 * MD_CHUNK + 1;      // partials per block
+constexpr int GRAM_LD = MD_CHUNK + 4;
 static int ensure_scratch(smf_ctx *ctx)
 {
   if (ctx->scratch) return SMF_OK;
-  const int64_t n = 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1) + 16 + 256;
+  const int64_t n = SCR_OUT + (int64_t)RED_BLOCKS * SCR_PART + 16 + 256 + (int64_t)GRAM_LD * GRAM_LD;
   SMF_CUDA(cudaMalloc(&ctx->scratch, n * sizeof(double)));
   SMF_CUDA(cudaMemsetAsync(ctx->scratch, 0, n * sizeof(double), ctx->stream));
   ctx->scratch_n = n;
-  SMF_CUDA(cudaMallocHost(&ctx->host_pinned, 256 * sizeof(double)));
-  ctx->host_pinned_n = 256;
+  SMF_CUDA(cudaMallocHost(&ctx->host_pinned, 512 * sizeof(double)));
+  ctx->host_pinned_n = 512;
   return SMF_OK;
 }
 static double *scr_out(smf_ctx *ctx) { return ctx->scratch; }
-static double *scr_partial(smf_ctx *ctx) { return ctx->scratch + 128; }
-static unsigned int *scr_counter(smf_ctx *ctx) { return (unsigned int *)(ctx->scratch + 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1)); }
-static double **scr_ptrs(smf_ctx *ctx) { return (double **)(ctx->scratch + 128 + (int64_t)RED_BLOCKS * (MD_CHUNK + 1) + 16); }
+static double *scr_partial(smf_ctx *ctx) { return ctx->scratch + SCR_OUT; }
+static unsigned int *scr_counter(smf_ctx *ctx) { return (unsigned int *)(ctx->scratch + SCR_OUT + (int64_t)RED_BLOCKS * SCR_PART); }
+static double **scr_ptrs(smf_ctx *ctx) { return (double **)(ctx->scratch + SCR_OUT + (int64_t)RED_BLOCKS * SCR_PART + 16); }
+static double *scr_gram(smf_ctx *ctx) { return ctx->scratch + SCR_OUT + (int64_t)RED_BLOCKS * SCR_PART + 16 + 256; }
 
 static int all_aligned16(const void *w, double *const *V, int k)
 {
@@ -273,7 +293,7 @@ int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double 
   if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_dot: too many vectors");
   if (k > 0) SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
   { ProfScope prof(ctx, ctx->vec_bucket);
-  k_multi_dot<<<red_blocks(k_multi_dot, n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx),
+  k_multi_dot<false><<<red_blocks(k_multi_dot<false>, n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, nullptr, n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx),
                                                       ctx->md_vec2 = (all_aligned16(w, V_host_ptrs, k) && ((uintptr_t)ctx->dot_weights & 15u) == 0),
                                                       ctx->dot_weights); }
   if (int e = allreduce_sum(ctx, scr_out(ctx), k + 1)) return e;
@@ -287,6 +307,45 @@ int vec_multi_dot(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double 
   return SMF_OK;
 }
 
+// Re-orthogonalised classical Gram-Schmidt in ONE pass over the basis.  CGS2 computes h1 = V^T w, w1 = w - V h1,
+// h2 = V^T w1, w2 = w1 - V h2.  Since V^T w1 = (I - G) h1 with the Gram matrix G = V^T V, the second projection is
+// known without touching w1: h = h1 + h2 = h1 - E h1, E = G - I.  The column of G that belongs to the newest basis
+// vector V[k-1] is measured in the same pass that computes h1 (second right-hand side of k_multi_dot), so one
+// orthogonalisation reads the basis twice (dots, update) instead of four times.  On return the device holds the
+// corrected coefficients where vec_multi_axpy_from_dots expects them.
+__global__ void k_gram_correct(double *E, double *out, int k)
+{
+  __shared__ double s_h[MD_CHUNK];
+  const int m = threadIdx.x, j = k - 1;
+  if (m < k) {
+    s_h[m] = out[m];
+    const double e = out[k + 1 + m] - (m == j ? 1.0 : 0.0);
+    E[(size_t)m * GRAM_LD + j] = e;
+    E[(size_t)j * GRAM_LD + m] = e;
+  }
+  __syncthreads();
+  if (m < k) {
+    double c = 0.0;
+    for (int l = 0; l < k; ++l) c = fma(E[(size_t)m * GRAM_LD + l], s_h[l], c);
+    out[m] = s_h[m] - c;
+  }
+}
+int vec_multi_dot_gram(smf_ctx *ctx, double *const *V_host_ptrs, int k, const double *w, int64_t n)
+{
+  if (int e = ensure_scratch(ctx)) return e;
+  if (k < 1 || k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_dot_gram: bad number of vectors");
+  SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
+  { ProfScope prof(ctx, ctx->vec_bucket);
+  k_multi_dot<true><<<red_blocks(k_multi_dot<true>, n), VT, 0, ctx->stream>>>((const double *const *)scr_ptrs(ctx), k, w, V_host_ptrs[k - 1], n, scr_partial(ctx), scr_counter(ctx), scr_out(ctx),
+                                                      ctx->md_vec2 = (all_aligned16(w, V_host_ptrs, k) && ((uintptr_t)ctx->dot_weights & 15u) == 0),
+                                                      ctx->dot_weights); }
+  if (int e = allreduce_sum(ctx, scr_out(ctx), 2 * k + 1)) return e;
+  k_gram_correct<<<1, 128, 0, ctx->stream>>>(scr_gram(ctx), scr_out(ctx), k);
+  ctx->launches += 2;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
 // w -= sum_j h_j V_j with h = the first k results of the preceding vec_multi_dot (still on the device);
 // returns h (k entries), the pre-orthogonalisation |w|^2 (entry k) and the new |w|^2 (entry k+1) on the host.
 int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *host_out)
@@ -294,15 +353,15 @@ int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *
   // pointer table already uploaded by vec_multi_dot
   { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(w, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
-                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2,
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + OUT_NRM,
                                                        ctx->md_vec2 && ((uintptr_t)w & 15u) == 0, ctx->dot_weights); }
-  if (int e = allreduce_sum(ctx, scr_out(ctx) + MD_CHUNK + 2, 1)) return e;
+  if (int e = allreduce_sum(ctx, scr_out(ctx) + OUT_NRM, 1)) return e;
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
-  SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (MD_CHUNK + 3), cudaMemcpyDeviceToHost, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(ctx->host_pinned, scr_out(ctx), sizeof(double) * (OUT_NRM + 1), cudaMemcpyDeviceToHost, ctx->stream));
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int j = 0; j <= k; ++j) host_out[j] = ctx->host_pinned[j];
-  host_out[k + 1] = ctx->host_pinned[MD_CHUNK + 2];
+  host_out[k + 1] = ctx->host_pinned[OUT_NRM];
   return SMF_OK;
 }
 
@@ -312,12 +371,12 @@ int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const dou
   if (int e = ensure_scratch(ctx)) return e;
   if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_add: too many vectors");
   if (k == 0) return SMF_OK;
-  for (int j = 0; j < k; ++j) ctx->host_pinned[128 + j] = -coef_host[j];
+  for (int j = 0; j < k; ++j) ctx->host_pinned[256 + j] = -coef_host[j];
   SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
-  SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 128, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 256, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
   { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
-                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + MD_CHUNK + 2,
+                                                       scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + OUT_NRM,
                                                        all_aligned16(x, V_host_ptrs, k), nullptr); }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());

@@ -69,6 +69,9 @@ class StokesMatrixFreeHandler:
         self.minimum_viscosity = self.maximum_viscosity = None
         self.allow_structured_bricks = True      # implementation switches (smf_set_option); tests exercise both paths
         self.use_cuda_graphs = True
+        self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
+        self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
+        self.gram_reorthogonalization = True     # GMRES: CGS2 in one sweep over the basis (False: two sweeps)
         # Chebyshev eigenvalue start vector from partition-independent global DoF numbers (always on for >1 rank)
         self.global_start_vector = False
         # "Solver parameters/Stokes solver parameters" (names verbatim from source/simulator/parameters.cc:439-584)
@@ -123,6 +126,9 @@ class StokesMatrixFreeHandler:
         self.ctx = ctx
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_STRUCTURED_BRICKS, int(self.allow_structured_bricks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CUDA_GRAPHS, int(self.use_cuda_graphs)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_ORTHO_SINGLE_PASS, int(self.gram_reorthogonalization)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_PIPELINED_KERNEL, int(self.use_pipelined_kernel)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._keep = []
         self.rank, self.world = getattr(hierarchy, "rank", 0), getattr(hierarchy, "world", 1)
         self._comm_init()

@@ -49,6 +49,9 @@ const char *smf_last_error(const smf_ctx *ctx);
 /* implementation switches (all on by default); set before smf_set_level */
 #define SMF_OPT_STRUCTURED_BRICKS 0   /* conflict-free staging layout for batches that are 4x4x2 Morton bricks */
 #define SMF_OPT_CUDA_GRAPHS 1         /* replay the coarse-level part of the V-cycles from CUDA graphs */
+#define SMF_OPT_MAX_GRID_BLOCKS 4      /* > 0: cap on the grid of the persistent kernels (testing aid; default 0 = one resident wave) */
+#define SMF_OPT_PIPELINED_KERNEL 3     /* structured levels: persistent, cp.async-pipelined velocity kernel (default 1) */
+#define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
 int smf_set_stream(smf_ctx *ctx, void *cuda_stream);

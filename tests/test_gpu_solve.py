@@ -132,3 +132,32 @@ def test_no_convergence_is_a_status():
     sol, out = h.solve(rhs)
     assert not out["converged"] and out["iterations"] == 5
     h.close()
+
+
+@pytest.mark.parametrize("case", ["solcx4", "nsinker_none"])
+def test_gram_reorthogonalization_equals_two_sweeps(case):
+    """The one-sweep re-orthogonalisation (h = h1 - (V^T V - I) h1) is CGS2 in exact arithmetic: same iteration
+    counts and the same solution as two sweeps over the basis, on the two worst-conditioned goldens."""
+    res = []
+    for gram in (True, False):
+        if case == "solcx4":
+            hier = synthetic.BoxHierarchy(2, 4)
+            avg, bc, tol = "harmonic average only viscosity", "tangential", 1e-7
+            eta_q, rhs, ps = benchmarks.solcx_problem(hier, averaging=avg)
+        else:
+            hier = synthetic.BoxHierarchy(3, 2)
+            avg, bc, tol = "none", "zero", 1e-6
+            eta_q, rhs, ps = benchmarks.nsinker_problem(hier, averaging=avg, n_sinkers=4)
+        h = StokesMatrixFreeHandler(hier.dim)
+        h.gram_reorthogonalization = gram
+        h.setup_dofs(hier, bc)
+        h.assemble(eta_q, avg, ps)
+        h.build_preconditioner()
+        h.parameters["Linear solver tolerance"] = tol
+        sol, out = h.solve(rhs)
+        assert out["converged"]
+        res.append((sol, out))
+        h.close()
+    assert res[0][1]["iterations"] == res[1][1]["iterations"]
+    nu = hier.active.n_u
+    assert rel(res[0][0][:nu], res[1][0][:nu]) < 1e-8
