@@ -509,8 +509,12 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
 //    rounds run in ascending order of the node's low-face pattern, so for every lattice point the first cell to touch
 //    it is known per lane (first-touch mask) and stores instead of adding;
 //  * the flush reads the node list from shared memory (no dependent global load in front of the stores / REDs);
-//  * the three symmetric-stress pairs are spread evenly: component c is the "lower" thread of pair {c, c+1} and the
-//    "upper" thread of pair {c-1, c}.
+//  * ROTATED FRAMES: warp c keeps its 27 values in a register frame whose direction r is the actual direction
+//    (c + r) mod 3.  The operator is invariant under cyclic permutation of the axes, so in these frames all three
+//    warps execute the SAME instructions (diagonal stress along register direction 0, pair {c, c+1} along 1, pair
+//    {c-1, c} along 2); only the gathers / scatters between shared memory and registers differ per warp.  This cuts
+//    the instruction footprint of the kernel by almost 3x (the one-brick-per-block kernel stalls on instruction
+//    fetch).  A point with frame coordinates (q0, q1, q2) of warp c+1 is the point (q2, q0, q1) of warp c.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void *src, int src_bytes)
 { asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory"); }
@@ -519,23 +523,121 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// low-face pattern of local node n: bit d set when the node lies on the cell's low face in direction d
+// low-face pattern of (actual) local node n: bit d set when the node lies on the cell's low face in direction d
 __host__ __device__ constexpr int lowface(int n) { return ((n % 3) == 0) + 2 * (((n / 3) % 3) == 0) + 4 * ((n / 9) == 0); }
+// actual lexicographic index (base B digits, x fastest) of frame index m of component C
+template <int C, int B> __host__ __device__ constexpr int rot_actual(int m)
+{
+  const int q0 = m % B, q1 = (m / B) % B, q2 = m / (B * B);
+  return C == 0 ? q0 + B * q1 + B * B * q2 : (C == 1 ? q2 + B * q0 + B * B * q1 : q1 + B * q2 + B * B * q0);
+}
+// index in the frame of warp c-1 of the point with index m in the frame of warp c
+__host__ __device__ constexpr int xperm(int m) { return (m / 9) + 3 * (m % 3) + 9 * ((m / 3) % 3); }
 
 constexpr int SBK_THREADS = 96;
 constexpr int SBK_SU = 13;            // ceil(3 * 405 / 96) staged items per thread
-constexpr size_t sbk_smem_bytes() { return (size_t)(2 * 3 * SB_SLOTS + 3 * 27 * SUB) * sizeof(double) + 2 * (size_t)SB_LIST_BYTES; }
+constexpr size_t sbk_smem_bytes(int mode)
+{
+  return (size_t)(2 * 3 * SB_SLOTS + 3 * 27 * SUB) * sizeof(double) + 2 * (size_t)(mode == 0 ? SB_LIST_BYTES : SB_BLOCK_BYTES)
+         + (mode == 0 ? 0 : SB_PLIST * sizeof(double));
+}
+
+// viscosity at frame point m: es[r] = SUB * 3^(actual direction of register direction r)
+struct EtaRot {
+  const double *etab; int es0, es1, es2;
+  __device__ __forceinline__ double operator()(int m) const { return etab[(m % 3) * es0 + ((m / 3) % 3) * es1 + (m / 9) * es2]; }
+};
+// T (+)= (2D'_0)^T [ f2 w_q eta_q (2D'_0 u) ]
+template <bool PERQ> __device__ __forceinline__ void sb_diag(const double (&u)[27], double (&T)[27], double f2, const EtaRot &eta, bool add)
+{
+  for_lines<3, 0>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(u[a], u[b], u[c], ga, gb, gc);
+    if (PERQ) { ga *= f2 * qweight<3>(a) * eta(a); gb *= f2 * qweight<3>(b) * eta(b); gc *= f2 * qweight<3>(c) * eta(c); }
+    else { ga *= f2 * qweight<3>(a); gb *= f2 * qweight<3>(b); gc *= f2 * qweight<3>(c); }
+    const double ta = fma(-3.0, ga, gc - gb), tb = 4.0 * (ga - gc), tc = fma(3.0, gc, gb - ga);
+    if (add) { T[a] += ta; T[b] += tb; T[c] += tc; }
+    else { T[a] = ta; T[b] = tb; T[c] = tc; }
+  });
+}
+// pair {c, c+1}, lower thread: publish e1 (2D'_1 u) in its own frame
+__device__ __forceinline__ void sb_publish(const double (&u)[27], double *buf, double e1)
+{
+  for_lines<3, 1>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(u[a], u[b], u[c], ga, gb, gc);
+    buf[a * SUB] = e1 * ga; buf[b * SUB] = e1 * gb; buf[c * SUB] = e1 * gc;
+  });
+}
+// pair {c-1, c}, upper thread: X = coef_q (e2 2D'_2 u + partner), published in the partner's frame; T += e2 (2D'_2)^T X
+template <bool PERQ> __device__ __forceinline__ void sb_upper(const double (&u)[27], double (&T)[27], double *buf, double e2, double cvol, const EtaRot &eta)
+{
+  const double e3 = 3.0 * e2, e4 = 4.0 * e2;
+  for_lines<3, 2>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(u[a], u[b], u[c], ga, gb, gc);
+    double xa = fma(e2, ga, buf[xperm(a) * SUB]), xb = fma(e2, gb, buf[xperm(b) * SUB]), xc = fma(e2, gc, buf[xperm(c) * SUB]);
+    if (PERQ) { xa *= cvol * qweight<3>(a) * eta(a); xb *= cvol * qweight<3>(b) * eta(b); xc *= cvol * qweight<3>(c) * eta(c); }
+    else { xa *= cvol * qweight<3>(a); xb *= cvol * qweight<3>(b); xc *= cvol * qweight<3>(c); }
+    buf[xperm(a) * SUB] = xa; buf[xperm(b) * SUB] = xb; buf[xperm(c) * SUB] = xc;
+    dTline_add(T[a], T[b], T[c], xa, xb, xc, e2, e3, e4);
+  });
+}
+// pair {c, c+1}, lower thread: T += e1 (2D'_1)^T X
+__device__ __forceinline__ void sb_lower(double (&T)[27], const double *buf, double e1)
+{
+  const double e3 = 3.0 * e1, e4 = 4.0 * e1;
+  for_lines<3, 1>([&](int a, int b, int c) { dTline_add(T[a], T[b], T[c], buf[a * SUB], buf[b * SUB], buf[c * SUB], e1, e3, e4); });
+}
+// registers <-> staging slots of this lane's cell, per component frame
+template <int C> __device__ __forceinline__ void sb_gather(double (&u)[27], const double *stage, const int (&lb)[4])
+{
+#pragma unroll
+  for (int m = 0; m < 27; ++m) { const int n = rot_actual<C, 3>(m); u[m] = stage[sbn_const(n) + lb[sbn_variant(n)]]; }
+}
+template <int C> __device__ __forceinline__ void sb_accumulate(double (&T)[27], double *stage, const int (&lb)[4], unsigned first_mask)
+{
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const bool first = (first_mask >> r) & 1u;
+    if (r != 0) {       // (all loads of a round before its stores: the slots of a round are distinct)
+#pragma unroll
+      for (int m = 0; m < 27; ++m) {
+        const int n = rot_actual<C, 3>(m);
+        if (lowface(n) == r) { const double old = first ? 0.0 : stage[sbn_const(n) + lb[sbn_variant(n)]]; T[m] += old; }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 27; ++m) {
+      const int n = rot_actual<C, 3>(m);
+      if (lowface(n) == r) stage[sbn_const(n) + lb[sbn_variant(n)]] = T[m];
+    }
+    __syncwarp();
+  }
+}
+template <int C> __device__ __forceinline__ void sb_gather_p(double (&pn)[8], const double *sPA, int x, int y, int z)
+{
+#pragma unroll
+  for (int m = 0; m < 8; ++m) { const int n = rot_actual<C, 2>(m); pn[m] = sPA[(x + (n & 1)) + 5 * (y + ((n >> 1) & 1)) + 25 * (z + (n >> 2))]; }
+}
+template <int C> __device__ __forceinline__ void sb_park_p(const double (&yv)[8], double *park)
+{
+#pragma unroll
+  for (int m = 0; m < 8; ++m) park[rot_actual<C, 2>(m) * SUB] = yv[m];
+}
 
 template <int MODE, bool PERQ>
 __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellParams P, const unsigned char *lists, int n_batches)
 {
-  static_assert(MODE == 0, "only the A block is implemented in the pipelined kernel so far");
-  constexpr int DIM = 3, NN = 27, MU = SB_SLOTS;
+  static_assert(MODE == 0 || MODE == 1, "A block and Stokes operator");
+  constexpr int DIM = 3, NN = 27, NP = 8, MU = SB_SLOTS;
+  constexpr int LBYTES = MODE == 0 ? SB_LIST_BYTES : SB_BLOCK_BYTES;     // bytes of a brick's lists that this mode needs
   extern __shared__ __align__(16) double smem[];
   double *sA = smem;                       // [3][MU] source values of the current brick (cp.async target)
   double *sB = sA + 3 * MU;                // [3][MU] accumulated results of the current brick
   double *s_ex = sB + 3 * MU;              // [3][NN][32] pair buffers, indexed by the lower component of the pair
-  unsigned char *sI = reinterpret_cast<unsigned char *>(s_ex + 3 * NN * SUB);   // [2][SB_LIST_BYTES] node lists
+  unsigned char *sI = reinterpret_cast<unsigned char *>(s_ex + 3 * NN * SUB);   // [2][LBYTES] node lists
+  double *sPA = reinterpret_cast<double *>(sI + 2 * LBYTES);                    // [SB_PLIST] pressure values (MODE 1)
   const int tid = threadIdx.x, c = tid >> 5, lane = tid & 31, G = gridDim.x;
   int b = blockIdx.x;
   if (b >= n_batches) return;
@@ -549,32 +651,44 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
 #pragma unroll
   for (int r = 0; r < 8; ++r)
     if ((!(r & 1) || x == 0) && (!(r & 2) || y == 0) && (!(r & 4) || z == 0)) first_mask |= 1u << r;
-  const auto slot = [&](int n) -> int { return sbn_const(n) + lb[sbn_variant(n)]; };
   const int j0 = tid / 3, d0 = tid - 3 * j0;      // staged item k of this thread: node j0 + 32 k, component d0
-  const double ec = P.ee[c];
-  const int cl = c == 2 ? 0 : c + 1;              // partner in the pair where this thread is the lower one
-  const int cu = c == 0 ? 2 : c - 1;              // partner in the pair where this thread is the upper one
-  const double el = P.ee[cl], eu = P.ee[cu];
-  double *ex_lo = s_ex + (size_t)c * NN * SUB + lane;     // pair {c, c+1}
-  double *ex_up = s_ex + (size_t)cu * NN * SUB + lane;    // pair {c-1, c}
+  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;      // actual directions of register directions 1, 2
+  const double e0 = P.ee[c], e1 = P.ee[c1], e2 = P.ee[c2];
+  double *ex_lo = s_ex + (size_t)c * NN * SUB + lane;      // pair {c, c+1}: this thread is the lower one
+  double *ex_up = s_ex + (size_t)c2 * NN * SUB + lane;     // pair {c-1, c}: this thread is the upper one
   double *myA = sA + c * MU, *myB = sB + c * MU;
+  EtaRot eta;
+  eta.es0 = SUB * stride3(c); eta.es1 = SUB * stride3(c1); eta.es2 = SUB * stride3(c2);
 
   const auto load_list = [&](unsigned char *dst, int brick) {
-    const unsigned char *src = lists + (size_t)brick * SB_LIST_BYTES;
-    for (int ch = tid; ch < SB_LIST_BYTES / 16; ch += SBK_THREADS) cp_async16(smem_u32(dst + 16 * ch), src + 16 * ch);
+    const unsigned char *src = lists + (size_t)brick * SB_BLOCK_BYTES;
+    for (int ch = tid; ch < LBYTES / 16; ch += SBK_THREADS) cp_async16(smem_u32(dst + 16 * ch), src + 16 * ch);
   };
   const auto issue_values = [&](const unsigned char *I) {
     const uint32_t *le = reinterpret_cast<const uint32_t *>(I);
     const uint16_t *ls = reinterpret_cast<const uint16_t *>(I + SB_LIST * 4);
     const uint32_t base = smem_u32(sA + d0 * MU);
+    const double *srcd = P.src_u + d0;
+    // (sub-batches: the list reads of a batch are in flight before its first copy is issued; u and T are live here)
+    constexpr int SUBB = 4;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 16; k0 += SUBB) {
+      uint32_t e[SUBB], sl[SUBB];
 #pragma unroll
-    for (int k = 0; k < SBK_SU; ++k) {
-      const int j = j0 + 32 * k;
-      if (j < 405) {
-        const uint32_t e = le[j];
-        const bool cons = (e >> (NODE_FLAG_SHIFT + d0)) & 1u;
-        cp_async8_zfill(base + 8u * ls[j], P.src_u + (e & NODE_IDX_MASK) + d0, cons ? 0 : 8);
+      for (int k = 0; k < SUBB; ++k) {
+        const int j = min(j0 + 32 * (k0 + k), 404);
+        e[k] = le[j]; sl[k] = ls[j];
       }
+#pragma unroll
+      for (int k = 0; k < SUBB; ++k)
+        if (j0 + 32 * (k0 + k) < 405) {
+          const bool cons = (e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u;
+          cp_async8_zfill(base + 8u * sl[k], srcd + (e[k] & NODE_IDX_MASK), cons ? 0 : 8);
+        }
+    }
+    if (MODE == 1 && tid < 75) {      // pressure values in lattice order
+      const uint32_t e = reinterpret_cast<const uint32_t *>(I + SB_LIST_BYTES)[tid];
+      cp_async8_zfill(smem_u32(sPA + tid), P.src_p + (e & NODE_IDX_MASK), (e >> 31) ? 0 : 8);
     }
   };
 
@@ -588,27 +702,48 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
   double eta_next = PERQ ? 1.0 : P.eta_t[(size_t)b * P.n_eta * SUB + lane];
 
   for (int it = 0; b < n_batches; b += G, ++it) {
-    unsigned char *I_cur = sI + (it & 1) * SB_LIST_BYTES, *I_nxt = sI + ((it + 1) & 1) * SB_LIST_BYTES;
+    unsigned char *I_cur = sI + (it & 1) * LBYTES, *I_nxt = sI + ((it + 1) & 1) * LBYTES;
     const int bn = b + G;
     cp_async_wait_all();
     __syncthreads();                        // values of this brick are in sA; the previous flush is done with sB / I_nxt
     if (bn < n_batches) load_list(I_nxt, bn);
     cp_async_commit();
     const double eta0 = eta_next;
-    const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+    eta.etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
 
     double u[NN], T[NN];
-#pragma unroll
-    for (int n = 0; n < NN; ++n) u[n] = myA[slot(n)];
+    if (c == 0) sb_gather<0>(u, myA, lb); else if (c == 1) sb_gather<1>(u, myA, lb); else sb_gather<2>(u, myA, lb);
     interp_all<DIM>(u);
-    // diagonal direction: T = (2D'_c)^T [ 2 eta w vol e_c^2 (2D'_c u) ]
-    {
-      const double f2 = 2.0 * ec * ec * P.vol * eta0;
-      SMF_DIR_SWITCH(c, (diag_dir<DIM, 0, PERQ>(u, T, f2, etab, false)), (diag_dir<DIM, 1, PERQ>(u, T, f2, etab, false)),
-                     (diag_dir<DIM, 2, PERQ>(u, T, f2, etab, false)));
+    if (MODE == 1) {
+      // pressure contribution to the velocity rows: T = (2D'_0)^T [ -e_c ps vol w_q p_q ]
+      {
+        double pn[NP], pq[NN];
+        if (c == 0) sb_gather_p<0>(pn, sPA, x, y, z); else if (c == 1) sb_gather_p<1>(pn, sPA, x, y, z); else sb_gather_p<2>(pn, sPA, x, y, z);
+        q1_to_quad<DIM>(pn, pq);
+        const double f = -e0 * P.ps * P.vol;
+#pragma unroll
+        for (int q = 0; q < NN; ++q) pq[q] *= f * qweight<DIM>(q);
+        for_lines<DIM, 0>([&](int a, int b2, int c2_) {
+          T[a] = fma(-3.0, pq[a], pq[c2_] - pq[b2]); T[b2] = 4.0 * (pq[a] - pq[c2_]); T[c2_] = fma(3.0, pq[c2_], pq[b2] - pq[a]);
+        });
+      }
+      // pressure rows -ps (div u, q): this component's share, parked in sB (free until the accumulation) for the
+      // lattice-wise sum after the next barrier
+      {
+        double dq[NN], yv[NP];
+        const double f = -P.ps * P.vol * e0;
+        for_lines<DIM, 0>([&](int a, int b2, int c2_) {
+          dline(u[a], u[b2], u[c2_], dq[a], dq[b2], dq[c2_]);
+          dq[a] *= f * qweight<DIM>(a); dq[b2] *= f * qweight<DIM>(b2); dq[c2_] *= f * qweight<DIM>(c2_);
+        });
+        quad_to_q1T<DIM>(dq, yv);
+        if (c == 0) sb_park_p<0>(yv, myB + lane); else if (c == 1) sb_park_p<1>(yv, myB + lane); else sb_park_p<2>(yv, myB + lane);
+      }
     }
-    // pair {c, c+1}: publish e_{c+1} (2D'_{c+1} u_c)
-    SMF_DIR_SWITCH(cl, (publish_dir<DIM, 0>(u, ex_lo, el)), (publish_dir<DIM, 1>(u, ex_lo, el)), (publish_dir<DIM, 2>(u, ex_lo, el)));
+    // diagonal direction: T (+)= (2D'_0)^T [ 2 eta w vol e_c^2 (2D'_0 u) ]
+    sb_diag<PERQ>(u, T, 2.0 * e0 * e0 * P.vol * eta0, eta, MODE == 1);
+    // pair {c, c+1}: publish e_{c+1} (2D'_1 u)
+    sb_publish(u, ex_lo, e1);
     cp_async_wait_all();                    // (this thread's chunks of the next node list)
     __syncthreads();                        // publishes visible; every gather from sA is done; next list visible
     if (bn < n_batches) {
@@ -616,44 +751,73 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
       if (!PERQ) eta_next = P.eta_t[(size_t)bn * P.n_eta * SUB + lane];
     }
     cp_async_commit();
-    // pair {c-1, c}: X = eta w vol (e_{c-1} 2D'_{c-1} u_c + partner), T += e_{c-1} (2D'_{c-1})^T X, X published
-    {
-      const double cvol = P.vol * eta0;
-      SMF_DIR_SWITCH(cu, (upper_dir<DIM, 0, PERQ>(u, T, ex_up, eu, cvol, etab)), (upper_dir<DIM, 1, PERQ>(u, T, ex_up, eu, cvol, etab)),
-                     (upper_dir<DIM, 2, PERQ>(u, T, ex_up, eu, cvol, etab)));
+    if (MODE == 1 && tid < 75) {
+      // pressure rows: lattice node tid sums the shares of the (up to 8) cells around it, all components, in a fixed
+      // order, and goes straight to global memory (private node: store, shared: RED, constrained: dst = src)
+      const int X = tid % 5, Y = (tid / 5) % 5, Z = tid / 25;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int cx = X - i, cy = Y - j, cz = Z - k;
+            if (cx >= 0 && cx < 4 && cy >= 0 && cy < 4 && cz >= 0 && cz < 2) {
+              const int ln = (cx & 1) | ((cy & 1) << 1) | (cz << 2) | ((cx >> 1) << 3) | ((cy >> 1) << 4);
+              const int off = (i + 2 * j + 4 * k) * SUB + ln;
+              acc += sB[off] + sB[MU + off] + sB[2 * MU + off];
+            }
+          }
+      const uint32_t e = reinterpret_cast<const uint32_t *>(I_cur + SB_LIST_BYTES)[tid];
+      const uint32_t idx = e & NODE_IDX_MASK;
+      if (e >> 31) P.dst_p[idx] = P.src_p[idx];
+      else if (!(e & NODE_SHARED_BIT)) P.dst_p[idx] = acc;
+      else atomicAdd(P.dst_p + idx, acc);
     }
+    // pair {c-1, c}: X = eta w vol (e_{c-1} 2D'_2 u + partner), T += e_{c-1} (2D'_2)^T X, X published
+    sb_upper<PERQ>(u, T, ex_up, e2, P.vol * eta0, eta);
     __syncthreads();
-    SMF_DIR_SWITCH(cl, (lower_dir<DIM, 0>(T, ex_lo, el)), (lower_dir<DIM, 1>(T, ex_lo, el)), (lower_dir<DIM, 2>(T, ex_lo, el)));
+    sb_lower(T, ex_lo, e1);
     interpT_all<DIM>(T);
     // accumulate into sB in ascending order of the low-face pattern; the first cell to touch a lattice point stores
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const bool first = (first_mask >> r) & 1u;
-#pragma unroll
-      for (int n = 0; n < NN; ++n)
-        if (lowface(n) == r) {
-          double v = T[n];
-          if (r != 0 && !first) v += myB[slot(n)];
-          myB[slot(n)] = v;
-        }
-      __syncwarp();
-    }
+    if (c == 0) sb_accumulate<0>(T, myB, lb, first_mask); else if (c == 1) sb_accumulate<1>(T, myB, lb, first_mask); else sb_accumulate<2>(T, myB, lb, first_mask);
     __syncthreads();
-    // flush: private nodes with plain stores, shared nodes with one RED per DoF, constrained DoFs dst = src
+    // flush: private nodes with plain stores, shared nodes with one RED per DoF; constrained DoFs (dst = src) are
+    // skipped here and handled by a separate pass over the (few) bricks that have any
     {
       const uint32_t *le = reinterpret_cast<const uint32_t *>(I_cur);
       const uint16_t *ls = reinterpret_cast<const uint16_t *>(I_cur + SB_LIST * 4);
       const double *sBd = sB + d0 * MU;
+      double *dstd = P.dst_u + d0;
+      const int n_private = (int)le[405];
+      constexpr int SUBB = 4;
+#pragma unroll 1
+      for (int k0 = 0; k0 < 16; k0 += SUBB) {
+        uint32_t e[SUBB], sl[SUBB];
+        double v[SUBB];
 #pragma unroll
-      for (int k = 0; k < SBK_SU; ++k) {
-        const int j = j0 + 32 * k;
-        if (j < 405) {
+        for (int k = 0; k < SUBB; ++k) {
+          const int j = min(j0 + 32 * (k0 + k), 404);
+          e[k] = le[j]; sl[k] = ls[j];
+        }
+#pragma unroll
+        for (int k = 0; k < SUBB; ++k) v[k] = sBd[sl[k]];
+#pragma unroll
+        for (int k = 0; k < SUBB; ++k) {
+          const int j = j0 + 32 * (k0 + k);
+          const bool cons = (e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u;
+          if (j < 405 && !cons) {
+            if (j < n_private) dstd[e[k] & NODE_IDX_MASK] = v[k];
+            else atomicAdd(dstd + (e[k] & NODE_IDX_MASK), v[k]);
+          }
+        }
+      }
+      if (le[406] != 0) {
+#pragma unroll 1
+        for (int j = j0; j < 405; j += 32) {
           const uint32_t e = le[j];
-          const uint32_t idx = (e & NODE_IDX_MASK) + d0;
-          const double v = sBd[ls[j]];
-          if ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) P.dst_u[idx] = P.src_u[idx];
-          else if (!(e & NODE_SHARED_BIT)) P.dst_u[idx] = v;
-          else atomicAdd(P.dst_u + idx, v);
+          if ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) { const uint32_t idx = (e & NODE_IDX_MASK) + d0; P.dst_u[idx] = P.src_u[idx]; }
         }
       }
     }
@@ -736,6 +900,89 @@ __global__ void __launch_bounds__(32 * MASS_WARPS, PERQ ? 3 : 8) mass_kernel(con
     if (e >> 31) P.dst_p[idx] = P.src_p[idx];
     else if (j < n_excl_p) P.dst_p[idx] = s_dst[j];
     else atomicAdd(P.dst_p + idx, s_dst[j]);
+  }
+}
+
+// ---- pressure mass matrix on structured bricks: one warp per brick, no slot tables, no accumulation rounds -------
+// The warp stages the 5 x 5 x 3 pressure lattice of its brick (node list in lattice order, part of the brick's block
+// in LevelDev::sb_lists), every lane applies the cell matrix to the 8 values of its cell and publishes the 8 results;
+// then lattice node t sums the results of the (up to 8) cells around it in a fixed order and writes once: private
+// node plain store, shared node one RED, constrained node dst = src.
+constexpr int MSB_WARPS = 8;
+template <bool PERQ>
+__global__ void __launch_bounds__(32 * MSB_WARPS) mass_sb_kernel(const CellParams P, const unsigned char *lists, int n_batches)
+{
+  constexpr int NN = 27, NP = 8;
+  __shared__ double s_x[MSB_WARPS][SB_PLIST];
+  __shared__ double s_y[MSB_WARPS][NP * SUB];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x * MSB_WARPS + w;
+  if (b >= n_batches) return;
+  const uint32_t *pl = reinterpret_cast<const uint32_t *>(lists + (size_t)b * SB_BLOCK_BYTES + SB_LIST_BYTES);
+  uint32_t e[3];
+  double v[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) e[k] = pl[min(lane + 32 * k, 74)];
+  const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+  const double eta0 = PERQ ? 1.0 : etab[0];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] = P.src_p[e[k] & NODE_IDX_MASK];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (lane + 32 * k < 75) s_x[w][lane + 32 * k] = (e[k] >> 31) ? 0.0 : v[k];
+  __syncwarp();
+  const int x = sb_x(lane), y = sb_y(lane), z = sb_z(lane);
+  double yv[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) yv[i] = s_x[w][(x + (i & 1)) + 5 * (y + ((i >> 1) & 1)) + 25 * (z + (i >> 2))];
+  const double f = P.ps * P.ps * P.vol;
+  if (!PERQ) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int S = 1 << d;
+#pragma unroll
+      for (int i = 0; i < NP; ++i)
+        if (!(i & S)) {
+          const double a = yv[i], c = yv[i + S];
+          yv[i] = fma(2.0, a, c); yv[i + S] = fma(2.0, c, a);
+        }
+    }
+    const double ce = f / (eta0 * 216.0);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) yv[i] *= ce;
+  } else {
+    double pn[NP], pq[NN];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pn[i] = yv[i];
+    q1_to_quad<3>(pn, pq);
+#pragma unroll
+    for (int q = 0; q < NN; ++q) pq[q] *= (f / etab[q * SUB]) * qweight<3>(q);
+    quad_to_q1T<3>(pq, yv);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s_y[w][i * SUB + lane] = yv[i];
+  __syncwarp();
+#pragma unroll
+  for (int k3 = 0; k3 < 3; ++k3) {
+    const int t = lane + 32 * k3;
+    if (t >= 75) break;
+    const int X = t % 5, Y = (t / 5) % 5, Z = t / 25;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cx = X - i, cy = Y - j, cz = Z - k;
+          if (cx >= 0 && cx < 4 && cy >= 0 && cy < 4 && cz >= 0 && cz < 2) {
+            const int ln = (cx & 1) | ((cy & 1) << 1) | (cz << 2) | ((cx >> 1) << 3) | ((cy >> 1) << 4);
+            acc += s_y[w][(i + 2 * j + 4 * k) * SUB + ln];
+          }
+        }
+    const uint32_t idx = e[k3] & NODE_IDX_MASK;
+    if (e[k3] >> 31) P.dst_p[idx] = v[k3];
+    else if (!(e[k3] & NODE_SHARED_BIT)) P.dst_p[idx] = acc;
+    else atomicAdd(P.dst_p + idx, acc);
   }
 }
 
@@ -965,6 +1212,138 @@ template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(32 * TR
   }
 }
 
+// ---- velocity transfers on structured fine levels: one block per FINE brick -----------------------------------
+// A 4x4x2 brick of fine cells lies under 2x2x1 parents: the 5x5x3 coarse node lattice is interpolated to the brick's
+// 9x9x5 fine lattice by three 1D sweeps in shared memory (two-cell macro line: coarse node I sits at fine position
+// 2 I; fine position X takes the Q2 row p2row(X - 2 I0, .) on coarse nodes I0 .. I0 + 2, I0 = min(2 (X >> 2), NC - 3)),
+// and the fine side goes through the brick's own node list (ascending DoF order: coalesced) with one owner bit per
+// node, so every fine DoF is written (prolongation) / read (restriction) exactly once and the fine side needs no
+// atomics.  Restriction is the exact transpose; coarse nodes are shared between bricks, so they take one RED each.
+constexpr int TSB_THREADS = 96;
+__device__ __forceinline__ int sb_slot_rt(int X, int Y, int Z)
+{
+  const int v = (X & 1) + 2 * (Y & 1);
+  constexpr int B00 = sb_class_base(0, 0), B10 = sb_class_base(1, 0), B20 = sb_class_base(2, 0), B30 = sb_class_base(3, 0);
+  constexpr int B01 = sb_class_base(0, 1), B11 = sb_class_base(1, 1), B21 = sb_class_base(2, 1), B31 = sb_class_base(3, 1);
+  const int base = (Z & 1) ? (v == 0 ? B01 : (v == 1 ? B11 : (v == 2 ? B21 : B31))) : (v == 0 ? B00 : (v == 1 ? B10 : (v == 2 ? B20 : B30)));
+  const int sy = (v & 1) ? 4 : 8, sz = v == 0 ? 52 : (v == 2 ? 36 : 24);
+  return base + (X >> 1) + sy * (Y >> 1) + sz * (Z >> 1);
+}
+// first coarse node of the Q2 row of fine position X on a macro line with NC coarse nodes
+template <int NC> __device__ __forceinline__ int tr_i0(int X) { return NC == 3 ? 0 : min(2 * (X >> 2), NC - 3); }
+// weight of coarse node I in the row of fine position X (0 outside the row)
+template <int NC> __device__ __forceinline__ double tr_w(int X, int I)
+{
+  const int i0 = tr_i0<NC>(X), k = I - i0;
+  return (k < 0 || k > 2) ? 0.0 : p2row(X - 2 * i0, k);
+}
+
+struct TransferSbParams {
+  const unsigned char *tb;       // [n_bricks][TB_BYTES]
+  const unsigned char *lists;    // fine level's sb_lists [n_bricks][SB_BLOCK_BYTES]
+  const double *src; double *dst;
+  int add;
+};
+
+__global__ void __launch_bounds__(TSB_THREADS) prolongate_sb_kernel(const TransferSbParams P)
+{
+  __shared__ __align__(16) unsigned char s_tb[TB_BYTES];
+  __shared__ __align__(16) unsigned char s_l[SB_LIST_BYTES];
+  __shared__ double sC[3][TB_COARSE], A1[3][3 * 5 * 9], A2[3][3 * 9 * 9], sO[3][SB_SLOTS];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  {
+    const uint4 *g1 = reinterpret_cast<const uint4 *>(P.tb + (size_t)b * TB_BYTES);
+    const uint4 *g2 = reinterpret_cast<const uint4 *>(P.lists + (size_t)b * SB_BLOCK_BYTES);
+    for (int i = tid; i < TB_BYTES / 16; i += TSB_THREADS) reinterpret_cast<uint4 *>(s_tb)[i] = g1[i];
+    for (int i = tid; i < SB_LIST_BYTES / 16; i += TSB_THREADS) reinterpret_cast<uint4 *>(s_l)[i] = g2[i];
+  }
+  __syncthreads();
+  const uint32_t *cl = reinterpret_cast<const uint32_t *>(s_tb);
+  const unsigned char *ob = s_tb + TB_COARSE * 4;
+  for (int t = tid; t < 225; t += TSB_THREADS) {       // coarse values, constrained ones as zero
+    const int j = t / 3, d = t - 3 * j;
+    const uint32_t e = cl[j];
+    sC[d][j] = ((e >> (NODE_FLAG_SHIFT + d)) & 1u) ? 0.0 : P.src[(e & NODE_IDX_MASK) + d];
+  }
+  __syncthreads();
+  for (int t = tid; t < 405; t += TSB_THREADS) {       // x: [K][J][I] -> [K][J][X]
+    const int d = t / 135, rem = t - 135 * d, jk = rem / 9, X = rem - 9 * jk;
+    const int i0 = tr_i0<5>(X), r = X - 2 * i0;
+    const double *cc = &sC[d][jk * 5 + i0];
+    A1[d][rem] = p2row(r, 0) * cc[0] + p2row(r, 1) * cc[1] + p2row(r, 2) * cc[2];
+  }
+  __syncthreads();
+  for (int t = tid; t < 729; t += TSB_THREADS) {       // y: [K][J][X] -> [K][Y][X]
+    const int d = t / 243, rem = t - 243 * d, K = rem / 81, r2 = rem - 81 * K, Y = r2 / 9, X = r2 - 9 * Y;
+    const int j0 = tr_i0<5>(Y), r = Y - 2 * j0;
+    const double *cc = &A1[d][(K * 5 + j0) * 9 + X];
+    A2[d][rem] = p2row(r, 0) * cc[0] + p2row(r, 1) * cc[9] + p2row(r, 2) * cc[18];
+  }
+  __syncthreads();
+  for (int t = tid; t < 1215; t += TSB_THREADS) {      // z: [K][Y][X] -> staging slot of (X, Y, Z)
+    const int d = t / 405, rem = t - 405 * d, Z = rem / 81, yx = rem - 81 * Z, Y = yx / 9, X = yx - 9 * Y;
+    const double *cc = &A2[d][yx];
+    sO[d][sb_slot_rt(X, Y, Z)] = p2row(Z, 0) * cc[0] + p2row(Z, 1) * cc[81] + p2row(Z, 2) * cc[162];
+  }
+  __syncthreads();
+  const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
+  const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
+  const int j0 = tid / 3, d0 = tid - 3 * j0;
+  for (int j = j0; j < 405; j += 32) {
+    if (!(ob[j] & 1)) continue;
+    const uint32_t idx = (le[j] & NODE_IDX_MASK) + d0;
+    const double v = sO[d0][ls[j]];
+    if (P.add) P.dst[idx] += v; else P.dst[idx] = v;
+  }
+}
+
+__global__ void __launch_bounds__(TSB_THREADS) restrict_sb_kernel(const TransferSbParams P)
+{
+  __shared__ __align__(16) unsigned char s_tb[TB_BYTES];
+  __shared__ __align__(16) unsigned char s_l[SB_LIST_BYTES];
+  __shared__ double sO[3][SB_SLOTS], B2[3][3 * 9 * 9], B1[3][3 * 5 * 9];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  {
+    const uint4 *g1 = reinterpret_cast<const uint4 *>(P.tb + (size_t)b * TB_BYTES);
+    const uint4 *g2 = reinterpret_cast<const uint4 *>(P.lists + (size_t)b * SB_BLOCK_BYTES);
+    for (int i = tid; i < TB_BYTES / 16; i += TSB_THREADS) reinterpret_cast<uint4 *>(s_tb)[i] = g1[i];
+    for (int i = tid; i < SB_LIST_BYTES / 16; i += TSB_THREADS) reinterpret_cast<uint4 *>(s_l)[i] = g2[i];
+  }
+  __syncthreads();
+  const uint32_t *cl = reinterpret_cast<const uint32_t *>(s_tb);
+  const unsigned char *ob = s_tb + TB_COARSE * 4;
+  const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
+  const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
+  {
+    const int j0 = tid / 3, d0 = tid - 3 * j0;
+    for (int j = j0; j < 405; j += 32)
+      sO[d0][ls[j]] = (ob[j] & 2) ? P.src[(le[j] & NODE_IDX_MASK) + d0] : 0.0;
+  }
+  __syncthreads();
+  for (int t = tid; t < 729; t += TSB_THREADS) {       // z^T: slots -> [K][Y][X]
+    const int d = t / 243, rem = t - 243 * d, K = rem / 81, yx = rem - 81 * K, Y = yx / 9, X = yx - 9 * Y;
+    double a = 0.0;
+#pragma unroll
+    for (int Z = 0; Z < 5; ++Z) a = fma(tr_w<3>(Z, K), sO[d][sb_slot_rt(X, Y, Z)], a);
+    B2[d][rem] = a;
+  }
+  __syncthreads();
+  for (int t = tid; t < 405; t += TSB_THREADS) {       // y^T: [K][Y][X] -> [K][J][X]
+    const int d = t / 135, rem = t - 135 * d, jk = rem / 9, X = rem - 9 * jk, K = jk / 5, J = jk - 5 * K;
+    double a = 0.0;
+    for (int Y = max(0, 2 * J - 3); Y <= min(8, 2 * J + 3); ++Y) a = fma(tr_w<5>(Y, J), B2[d][(K * 9 + Y) * 9 + X], a);
+    B1[d][rem] = a;
+  }
+  __syncthreads();
+  for (int t = tid; t < 225; t += TSB_THREADS) {       // x^T: [K][J][X] -> coarse node (I, J, K), one RED per DoF
+    const int j = t / 3, d = t - 3 * j, I = j % 5, jk = j / 5;
+    double a = 0.0;
+    for (int X = max(0, 2 * I - 3); X <= min(8, 2 * I + 3); ++X) a = fma(tr_w<5>(X, I), B1[d][jk * 9 + X], a);
+    const uint32_t e = cl[j];
+    if (!((e >> (NODE_FLAG_SHIFT + d)) & 1u) && a != 0.0) atomicAdd(P.dst + (e & NODE_IDX_MASK) + d, a);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 static CellParams make_params(const LevelDev &L)
 {
@@ -999,7 +1378,7 @@ template <int DIM, int MODE, bool PERQ, bool STRUCT> static int launch_velocity_
 }
 template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
-  constexpr size_t smem = sbk_smem_bytes();
+  constexpr size_t smem = sbk_smem_bytes(MODE);
   static int resident = 0;
   if (resident == 0) {
     SMF_CUDA(cudaFuncSetAttribute(velocity_sb_kernel<MODE, PERQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1022,9 +1401,9 @@ template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, Level
 }
 template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
-  if (DIM == 3 && L.structured && MODE == 0 && ctx->use_pipelined && L.sb_lists) {
-    if (L.n_eta != 1) return launch_velocity_sb<0, true>(ctx, L, P);
-    return launch_velocity_sb<0, false>(ctx, L, P);
+  if (DIM == 3 && L.structured && MODE != 2 && ctx->use_pipelined && L.sb_lists) {
+    if (L.n_eta != 1) return launch_velocity_sb<(MODE == 2 ? 0 : MODE), true>(ctx, L, P);
+    return launch_velocity_sb<(MODE == 2 ? 0 : MODE), false>(ctx, L, P);
   }
   if (DIM == 3 && L.structured) {
     if (MODE != 2 && L.n_eta != 1) return launch_velocity_t<3, MODE, true, true>(ctx, L, P);
@@ -1043,12 +1422,12 @@ static int check_level(smf_ctx *ctx, const LevelDev &L)
   return SMF_OK;
 }
 
-int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
+int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero)
 {
   if (int e = check_level(ctx, L)) return e;
   CellParams P = make_params(L);
   P.src_u = src; P.dst_u = dst;
-  SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_u, ctx->stream));
+  if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_u, ctx->stream));
   if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
   return exchange_add(ctx, L.ex_u, dst);
 }
@@ -1072,15 +1451,20 @@ int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_
   if (int e = L.dim == 3 ? launch_velocity<3, 2>(ctx, L, P) : launch_velocity<2, 2>(ctx, L, P)) return e;
   return exchange_add(ctx, L.ex_u, dst_u);
 }
-int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
+int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero)
 {
   if (int e = check_level(ctx, L)) return e;
   CellParams P = make_params(L);
   P.src_p = src; P.dst_p = dst;
-  SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
+  if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
   const size_t smem = (size_t)MASS_WARPS * 2 * L.max_nodes_p * sizeof(double);
   const unsigned grid = (unsigned)((L.n_batches + MASS_WARPS - 1) / MASS_WARPS);
-  {
+  if (L.dim == 3 && L.structured && L.sb_lists && ctx->use_pipelined) {
+    ProfScope prof(ctx, B_MASS);
+    const unsigned g = (unsigned)((L.n_batches + MSB_WARPS - 1) / MSB_WARPS);
+    if (L.n_eta == 1) mass_sb_kernel<false><<<g, 32 * MSB_WARPS, 0, ctx->stream>>>(P, L.sb_lists, L.n_batches);
+    else mass_sb_kernel<true><<<g, 32 * MSB_WARPS, 0, ctx->stream>>>(P, L.sb_lists, L.n_batches);
+  } else {
     ProfScope prof(ctx, B_MASS);
     if (L.dim == 3) {
       if (L.n_eta == 1) mass_kernel<3, false><<<grid, 32 * MASS_WARPS, smem, ctx->stream>>>(P, L.n_batches);
@@ -1151,7 +1535,14 @@ static int launch_transfer(smf_ctx *ctx, int which, int fine_level, double *dst,
   TransferParams P{};
   P.n_parents = T.n_parents; P.src = src; P.dst = dst; P.add = add ? 1 : 0;
   const int dim = ctx->cfg.dim;
-  if (which == 0) {
+  LevelDev &F = ctx->levels[fine_level];
+  if (which == 0 && dim == 3 && T.tb_u && F.sb_lists && ctx->use_pipelined) {
+    TransferSbParams Q{T.tb_u, F.sb_lists, src, dst, add ? 1 : 0};
+    ProfScope prof(ctx, B_TRANSFER);
+    if (prolong) prolongate_sb_kernel<<<F.n_batches, TSB_THREADS, 0, ctx->stream>>>(Q);
+    else restrict_sb_kernel<<<F.n_batches, TSB_THREADS, 0, ctx->stream>>>(Q);
+    ctx->launches++;
+  } else if (which == 0) {
     P.patch = T.patch_u; P.coarse_nodes = C.cell_nodes_u;
     if (dim == 3) launch_transfer_t<3, 3, 3>(ctx, P, prolong); else launch_transfer_t<2, 3, 2>(ctx, P, prolong);
   } else {

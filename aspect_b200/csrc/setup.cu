@@ -106,6 +106,42 @@ static void build_batches(const std::vector<uint32_t> &nodes, int64_t n_cells, i
 
 // Structured-brick staging layout of the velocity nodes (3D): succeeds when every batch is a full 4x4x2 Morton brick
 // whose cell maps are consistent with a 9x9x5 lattice.  node_list[b][sb_slot] = node entry | NODE_SHARED_BIT.
+// Pressure nodes of structured bricks in lattice order (5 x 5 x 3): entry | NODE_SHARED_BIT, bit 31 = constrained.
+static bool build_structured3_p(const std::vector<uint32_t> &nodes_p, int64_t n_cells, int64_t n_index_space, std::vector<uint32_t> &plist)
+{
+  const int64_t nb = n_cells / BATCH_CELLS;
+  constexpr int NL = 5 * 5 * 3;
+  plist.assign((size_t)nb * SB_PLIST, NODE_INVALID);
+  std::vector<uint8_t> touch((size_t)n_index_space, 0);
+  std::vector<int32_t> seen_at((size_t)n_index_space, -1);
+  std::vector<uint32_t> batch_nodes;
+  for (int64_t b = 0; b < nb; ++b) {
+    uint32_t *L = plist.data() + (size_t)b * SB_PLIST;
+    batch_nodes.clear();
+    bool ok = true;
+    for (int l = 0; l < BATCH_CELLS && ok; ++l) {
+      const uint32_t *cn = nodes_p.data() + ((size_t)b * BATCH_CELLS + l) * 8;
+      const int x = sb_x(l), y = sb_y(l), z = sb_z(l);
+      for (int n = 0; n < 8; ++n) {
+        const int id = (x + (n & 1)) + 5 * ((y + ((n >> 1) & 1)) + 5 * (z + (n >> 2)));
+        const uint32_t idx = cn[n] & NODE_IDX_MASK;
+        if (L[id] == NODE_INVALID) {
+          if (seen_at[idx] >= 0) { ok = false; break; }
+          L[id] = cn[n]; seen_at[idx] = id; batch_nodes.push_back(idx);
+        } else if ((L[id] & NODE_IDX_MASK) != idx) { ok = false; break; }
+      }
+    }
+    for (uint32_t idx : batch_nodes) { seen_at[idx] = -1; if (touch[idx] < 2) ++touch[idx]; }
+    if (!ok) return false;
+  }
+  for (int64_t b = 0; b < nb; ++b)
+    for (int i = 0; i < NL; ++i) {
+      uint32_t &e = plist[(size_t)b * SB_PLIST + i];
+      if (touch[e & NODE_IDX_MASK] > 1) e |= NODE_SHARED_BIT;
+    }
+  return true;
+}
+
 static bool build_structured3(const std::vector<uint32_t> &nodes, int64_t n_cells, int64_t n_index_space,
                               std::vector<uint32_t> &node_list, std::vector<uint16_t> &node_slot)
 {
@@ -136,25 +172,35 @@ static bool build_structured3(const std::vector<uint32_t> &nodes, int64_t n_cell
     for (uint32_t idx : batch_nodes) { seen_at[idx] = -1; if (touch[idx] < 2) ++touch[idx]; }
     if (!ok) return false;
   }
-  // list entries in ascending DoF-index order (coalesced global access), each with its staging slot
+  // list entries: nodes private to the brick first, then the shared ones, each group in ascending DoF-index order
+  // (coalesced global access; the flush is warp-uniform except at the group boundary), each with its staging slot.
+  // Padding entries carry brick facts: [405] = number of private nodes, [406] = 1 if any DoF of the brick is constrained.
   node_list.assign((size_t)nb * SB_LIST, NODE_INVALID);
   node_slot.assign((size_t)nb * SB_LIST, 0);
   std::vector<std::pair<uint32_t, uint16_t>> ent(NL);
   for (int64_t b = 0; b < nb; ++b) {
     const uint32_t *L = lat.data() + (size_t)b * NL;
     int m = 0;
+    uint32_t n_private = 0, any_cons = 0;
     for (int Z = 0; Z < 5; ++Z)
       for (int Y = 0; Y < 9; ++Y)
         for (int X = 0; X < 9; ++X) {
           const uint32_t e = L[X + 9 * (Y + 9 * Z)];
-          ent[m++] = {e | (touch[e & NODE_IDX_MASK] > 1 ? NODE_SHARED_BIT : 0u), (uint16_t)sb_slot(X, Y, Z)};
+          const bool shared = touch[e & NODE_IDX_MASK] > 1;
+          n_private += shared ? 0 : 1;
+          if (e >> NODE_FLAG_SHIFT) any_cons = 1;
+          ent[m++] = {e | (shared ? NODE_SHARED_BIT : 0u), (uint16_t)sb_slot(X, Y, Z)};
         }
     std::sort(ent.begin(), ent.end(), [](const std::pair<uint32_t, uint16_t> &a, const std::pair<uint32_t, uint16_t> &c) {
+      const uint32_t sa = a.first & NODE_SHARED_BIT, sc = c.first & NODE_SHARED_BIT;
+      if (sa != sc) return sa < sc;
       return (a.first & NODE_IDX_MASK) < (c.first & NODE_IDX_MASK); });
     for (int i = 0; i < NL; ++i) {
       node_list[(size_t)b * SB_LIST + i] = ent[i].first;
       node_slot[(size_t)b * SB_LIST + i] = ent[i].second;
     }
+    node_list[(size_t)b * SB_LIST + 405] = n_private;
+    node_list[(size_t)b * SB_LIST + 406] = any_cons;
   }
   return true;
 }
@@ -195,7 +241,7 @@ void smf_destroy(smf_ctx *ctx)
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &L : ctx->levels) free_level(L);
-  for (auto &T : ctx->transfers) { cudaFree(T.patch_u); cudaFree(T.patch_p); }
+  for (auto &T : ctx->transfers) { cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u); }
   for (auto *mg : {&ctx->mgv_A, &ctx->mgv_S})
     for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
   for (double *p : ctx->krylov) cudaFree(p);
@@ -325,11 +371,16 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   if ((e = upload(ctx, &L.batch_info, info, &L.bytes))) return e;
   if ((e = upload(ctx, &L.node_list_u, nl_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.node_slot_u, slot_u, &L.bytes))) return e;
-  if (L.structured) {     // entries and slots of a brick side by side: one contiguous block per brick for the pipelined kernel
-    std::vector<unsigned char> sbl((size_t)L.n_batches * SB_LIST_BYTES, 0);
+  std::vector<uint32_t> plist;
+  if (L.structured) L.h_sb_list = nl_u;      // (smf_set_transfer derives the owner bits of the brick-wise transfers from it)
+  if (L.structured && build_structured3_p(nodes_p, L.n_cells, L.n_p, plist)) {
+    // entries and slots of a brick side by side, then its pressure entries: one contiguous block per brick for the pipelined kernel
+    std::vector<unsigned char> sbl((size_t)L.n_batches * SB_BLOCK_BYTES, 0);
     for (int b = 0; b < L.n_batches; ++b) {
-      std::memcpy(sbl.data() + (size_t)b * SB_LIST_BYTES, nl_u.data() + (size_t)b * SB_LIST, SB_LIST * 4);
-      std::memcpy(sbl.data() + (size_t)b * SB_LIST_BYTES + SB_LIST * 4, slot_u.data() + (size_t)b * SB_LIST, SB_LIST * 2);
+      unsigned char *blk = sbl.data() + (size_t)b * SB_BLOCK_BYTES;
+      std::memcpy(blk, nl_u.data() + (size_t)b * SB_LIST, SB_LIST * 4);
+      std::memcpy(blk + SB_LIST * 4, slot_u.data() + (size_t)b * SB_LIST, SB_LIST * 2);
+      std::memcpy(blk + SB_LIST_BYTES, plist.data() + (size_t)b * SB_PLIST, SB_PLIST * 4);
     }
     if ((e = upload(ctx, &L.sb_lists, sbl, &L.bytes))) return e;
   }
@@ -362,7 +413,7 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   const int dim = ctx->cfg.dim, NCH = 1 << dim;
   TransferDev &T = ctx->transfers[fine_level];
-  cudaFree(T.patch_u); cudaFree(T.patch_p);
+  cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u);
   T = TransferDev();
   T.n_parents = C.n_cells;
   // bit 31: this parent writes the node in prolongation (first local parent that touches it);
@@ -404,6 +455,48 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
   int e;
   if ((e = upload(ctx, &T.patch_u, pu, &bytes))) return e;
   if ((e = upload(ctx, &T.patch_p, pp, &bytes))) return e;
+  // Structured fine level in 3D: transfer blocks per fine brick (a 4x4x2 brick of fine cells = 2x2x1 parents).
+  if (dim == 3 && F.structured && F.sb_lists && !F.h_sb_list.empty()) {
+    std::vector<int32_t> parent_of((size_t)F.n_cells, -1), child_no((size_t)F.n_cells, -1);
+    for (int64_t par = 0; par < T.n_parents; ++par)
+      for (int ch = 0; ch < 8; ++ch) { parent_of[children[par * 8 + ch]] = (int32_t)par; child_no[children[par * 8 + ch]] = ch; }
+    const int nbr = F.n_batches;
+    std::vector<unsigned char> tb((size_t)nbr * TB_BYTES, 0);
+    std::vector<uint8_t> seen((size_t)F.n_u, 0);
+    bool ok = true;
+    for (int b = 0; b < nbr && ok; ++b) {
+      uint32_t *cl = reinterpret_cast<uint32_t *>(tb.data() + (size_t)b * TB_BYTES);
+      unsigned char *ob = tb.data() + (size_t)b * TB_BYTES + TB_COARSE * 4;
+      for (int i = 0; i < TB_COARSE; ++i) cl[i] = NODE_INVALID;
+      for (int q = 0; q < 4 && ok; ++q) {          // parent q = qx + 2 qy of the brick: fine lanes 8 q .. 8 q + 7
+        const int32_t par = parent_of[(size_t)b * BATCH_CELLS + 8 * q];
+        for (int l = 0; l < 8; ++l) {
+          const size_t fc = (size_t)b * BATCH_CELLS + 8 * q + l;
+          if (parent_of[fc] != par || child_no[fc] != l) ok = false;
+        }
+        if (!ok || par < 0) { ok = false; break; }
+        const int qx = q & 1, qy = q >> 1;
+        for (int n = 0; n < 27; ++n) {
+          const int id = (2 * qx + n % 3) + 5 * ((2 * qy + (n / 3) % 3) + 5 * (n / 9));
+          const uint32_t ce = C.h_nodes_u[(size_t)par * 27 + n];
+          if (cl[id] == NODE_INVALID) cl[id] = ce;
+          else if ((cl[id] & NODE_IDX_MASK) != (ce & NODE_IDX_MASK)) ok = false;
+        }
+      }
+      const uint32_t *fl = F.h_sb_list.data() + (size_t)b * SB_LIST;
+      for (int j = 0; j < 405; ++j) {
+        const uint32_t idx = fl[j] & NODE_IDX_MASK;
+        unsigned char o = 0;
+        if (!seen[idx]) {
+          seen[idx] = 1;
+          o |= 1;
+          if (F.h_not_owned_u.empty() || !F.h_not_owned_u[idx]) o |= 2;
+        }
+        ob[j] = o;
+      }
+    }
+    if (ok && (e = upload(ctx, &T.tb_u, tb, &bytes))) return e;
+  }
   T.set = true;
   return SMF_OK;
 }

@@ -54,7 +54,9 @@ __host__ __device__ constexpr int sb_slot(int X, int Y, int Z)
 constexpr int SB_SLOTS = 612;   // = sb_class_base(3, 1) + sb_class_size(3, 1)
 constexpr int SB_LIST = 408;    // node-list entries per structured brick (9 * 9 * 5 = 405, padded)
 constexpr int SB_LIST_BYTES = SB_LIST * 6;   // pipelined kernel: per brick [SB_LIST] uint32 entries, then [SB_LIST] uint16 slots
-static_assert(SB_LIST_BYTES % 16 == 0, "node lists are copied in 16-byte chunks");
+constexpr int SB_PLIST = 76;                 // pressure nodes of a brick in lattice order (5 x 5 x 3 = 75, padded)
+constexpr int SB_BLOCK_BYTES = SB_LIST_BYTES + SB_PLIST * 4;   // stride of a brick in LevelDev::sb_lists
+static_assert(SB_LIST_BYTES % 16 == 0 && SB_BLOCK_BYTES % 16 == 0, "node lists are copied in 16-byte chunks");
 static_assert(sb_class_base(3, 1) + sb_class_size(3, 1) == SB_SLOTS, "structured brick layout size");
 // brick coordinates of lane l (Morton order inside the batch: x0 y0 z0 x1 y1)
 __host__ __device__ constexpr int sb_x(int l) { return (l & 1) | (((l >> 3) & 1) << 1); }
@@ -90,7 +92,7 @@ struct LevelDev {
   uint32_t *node_list_u = nullptr;            // [n_batches][list_stride_u]  ascending DoF index (general: exclusive nodes first)
   uint16_t *node_slot_u = nullptr;            // [n_batches][list_stride_u]  structured bricks: staging slot of each list entry
   int list_stride_u = 0;                      // entries per batch in node_list_u (general path: = max_nodes_u)
-  unsigned char *sb_lists = nullptr;          // structured bricks: [n_batches][SB_LIST_BYTES] entries + slots (velocity_sb_kernel)
+  unsigned char *sb_lists = nullptr;          // structured bricks: [n_batches][SB_BLOCK_BYTES] velocity entries + slots, pressure entries (velocity_sb_kernel)
   uint32_t *node_list_p = nullptr;            // [n_batches][max_nodes_p]
   uint16_t *cell_loc_u = nullptr;             // [n_batches][KSUB][3^dim][SUB]
   uint16_t *cell_loc_p = nullptr;             // [n_batches][KSUB][2^dim][SUB]
@@ -105,13 +107,21 @@ struct LevelDev {
   double *dinv_A = nullptr, *dinv_M = nullptr; bool has_diag = false;
   int64_t bytes = 0;
   std::vector<uint32_t> h_nodes_u, h_nodes_p;   // host copies of the raw maps (needed by smf_set_transfer)
+  std::vector<uint32_t> h_sb_list;              // host copy of the structured velocity node lists [n_batches][SB_LIST]
   std::vector<uint8_t> h_cons_u, h_cons_p;      // host constraint bitmaps (needed by smf_set_exchange)
   std::vector<uint8_t> h_not_owned_u, h_not_owned_p;   // DoFs whose owner is a lower rank (set by smf_set_exchange)
   ExchangeDev ex_u, ex_p;
 };
 
+constexpr int TB_COARSE = 76;      // coarse velocity nodes under a fine brick: 5 x 5 x 3 lattice = 75, padded
+constexpr int TB_BYTES = TB_COARSE * 4 + SB_LIST + 8;   // + one owner byte per entry of the fine brick's node list (+ padding: 720 bytes)
+static_assert(TB_BYTES % 16 == 0, "transfer blocks are read in 16-byte chunks");
 struct TransferDev {              // level l-1 -> l
   int64_t n_parents = 0;
+  // structured fine level: per fine brick [TB_COARSE] uint32 coarse node entries (lattice order), then [SB_LIST] bytes
+  // in the order of the brick's node list: bit 0 = this brick writes the node in prolongation, bit 1 = contributes it
+  // in restriction (velocity transfers, prolongate_sb_kernel / restrict_sb_kernel)
+  unsigned char *tb_u = nullptr;
   uint32_t *patch_u = nullptr;    // [n_parents][5^dim] fine node (component-0 DoF) | bit31 = this parent owns the node
   uint32_t *patch_p = nullptr;    // [n_parents][3^dim]
   bool set = false;
@@ -132,6 +142,7 @@ struct ProfEvent { int bucket; cudaEvent_t a, b; };
 struct MGVectors {                // per level: solution, defect, t, and a Chebyshev scratch
   double *x = nullptr, *b = nullptr, *t = nullptr, *xo = nullptr;
   double *res = nullptr;          // where the last level_v_step left the solution (x or xo)
+  bool t_zero = false;            // t is known to be all zero (left so by cheb_update): the next operator application skips its memset
 };
 
 }  // namespace smf
@@ -221,10 +232,10 @@ struct VecBucket {      // books the vector kernels launched in this scope under
   ~VecBucket() { ctx->vec_bucket = saved; }
 };
 // operators.cu
-int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);
+int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero = false);
 int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
 int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_p);
-int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);
+int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero = false);
 int launch_diag(smf_ctx *ctx, LevelDev &L);
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);
@@ -252,8 +263,8 @@ int vec_multi_axpy_from_dots(smf_ctx *ctx, double *w, int k, int64_t n, double *
 int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const double *coef_host, int k, int64_t n);
 int vec_mod11(smf_ctx *ctx, double *x, int64_t first, double mean, int64_t n);
 int cheb_first(smf_ctx *ctx, double *x, const double *dinv, const double *b, double inv_theta, int64_t n);
-int cheb_update(smf_ctx *ctx, double *x, double *xo, const double *dinv, const double *b, const double *t,
-                double f1, double f2, bool use_xo, int64_t n);   // xo <- (1+f1) x - f1 xo + f2 dinv (b - t); caller swaps
+int cheb_update(smf_ctx *ctx, double *x, double *xo, const double *dinv, const double *b, double *t,
+                double f1, double f2, bool use_xo, int64_t n);   // xo <- (1+f1) x - f1 xo + f2 dinv (b - t); t <- 0; caller swaps
 int vec_residual(smf_ctx *ctx, double *t, const double *b, int64_t n);   // t = b - t
 int vec_gather(smf_ctx *ctx, double *y, const double *x, const uint32_t *idx, int64_t n, bool scatter);
 }  // namespace smf

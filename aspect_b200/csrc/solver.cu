@@ -67,8 +67,16 @@ struct MGSide {           // one of the two hierarchies
 
 static int64_t lsize(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].n_u : ctx->levels[l].n_p; }
 static const double *ldinv(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].dinv_A : ctx->levels[l].dinv_M; }
-static int lapply(smf_ctx *ctx, const MGSide &S, int l, double *dst, const double *src)
-{ return S.velocity ? launch_vmult_A(ctx, ctx->levels[l], dst, src) : launch_vmult_mass(ctx, ctx->levels[l], dst, src); }
+static int lapply(smf_ctx *ctx, const MGSide &S, int l, double *dst, const double *src, bool dst_is_zero = false)
+{ return S.velocity ? launch_vmult_A(ctx, ctx->levels[l], dst, src, dst_is_zero) : launch_vmult_mass(ctx, ctx->levels[l], dst, src, dst_is_zero); }
+// operator application into the level's t vector: the memset is skipped when the last cheb_update left t zeroed
+static int lapply_t(smf_ctx *ctx, const MGSide &S, int l, const double *src)
+{
+  MGVectors &V = (*S.v)[l];
+  const bool z = V.t_zero;
+  V.t_zero = false;
+  return lapply(ctx, S, l, V.t, src, z);
+}
 
 // PreconditionChebyshev::estimate_eigenvalues (App. A.2): Jacobi-preconditioned CG on (global index mod 11) - mean
 static int estimate_eigenvalues(smf_ctx *ctx, const MGSide &S, int l)
@@ -118,6 +126,7 @@ static int estimate_eigenvalues(smf_ctx *ctx, const MGSide &S, int l)
   const double alpha = sm.smoothing_range > 1.0 ? sm.lambda_max / sm.smoothing_range : std::min(0.9 * sm.lambda_max, lmin);
   sm.delta = 0.5 * (sm.lambda_max - alpha);
   sm.theta = 0.5 * (sm.lambda_max + alpha);
+  V.t_zero = false;         // (t served as the CG's z vector)
   return SMF_OK;
 }
 
@@ -129,12 +138,14 @@ static int cheb_tail(smf_ctx *ctx, const MGSide &S, int l, double *&x, double *&
   if (sm.degree < 2 || std::fabs(sm.delta) < 1e-40) return SMF_OK;
   double rhok = sm.delta / sm.theta;
   const double sigma = sm.theta / sm.delta;
+  MGVectors &V = (*S.v)[l];
   for (int k = 0; k < sm.degree - 1; ++k) {
-    TRY(lapply(ctx, S, l, t, x));
+    TRY(lapply_t(ctx, S, l, x));
     const double rhokp = 1.0 / (2.0 * sigma - rhok);
     const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / sm.delta;
     rhok = rhokp;
     TRY(cheb_update(ctx, x, xo, ldinv(ctx, S, l), b, t, f1, f2, have_old, n));
+    V.t_zero = true;
     std::swap(x, xo);
     have_old = true;
   }
@@ -152,9 +163,10 @@ static int cheb_step(smf_ctx *ctx, const MGSide &S, int l, double *&x, double *&
 {
   const Smoother &sm = (*S.sm)[l];
   const int64_t n = lsize(ctx, S, l);
-  TRY(lapply(ctx, S, l, t, x));
+  TRY(lapply_t(ctx, S, l, x));
   // x_new = x + (1/theta) D^-1 (b - A x): the update kernel with f1 = 0, written to xo, then swapped
   TRY(cheb_update(ctx, x, xo, ldinv(ctx, S, l), b, t, 0.0, 1.0 / sm.theta, false, n));
+  (*S.v)[l].t_zero = true;
   std::swap(x, xo);
   return cheb_tail(ctx, S, l, x, xo, b, t, true);
 }
@@ -174,7 +186,7 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
   if (l > 0) {
     const int64_t n = lsize(ctx, S, l);
     MGVectors &C = (*S.v)[l - 1];
-    TRY(lapply(ctx, S, l, V.t, x));
+    TRY(lapply_t(ctx, S, l, x));
     TRY(vec_residual(ctx, V.t, V.b, n));                                     // t = defect - A x
     TRY(vec_set(ctx, C.b, 0.0, lsize(ctx, S, l - 1)));
     TRY(launch_restrict_add(ctx, which, l, C.b, V.t));

@@ -29,7 +29,8 @@ __global__ void k_residual(double *t, const double *b, int64_t n) { GRID_STRIDE(
 __global__ void k_cheb_first(double *x, const double *dinv, const double *b, double it, int64_t n)
 { GRID_STRIDE(i, n) x[i] = it * dinv[i] * b[i]; }
 // xo <- (1+f1) x - f1 xo + f2 dinv (b - t)   (PreconditionChebyshev vector_updates, iteration_index >= 1)
-__global__ void k_cheb_update(double *x, double *xo, const double *dinv, const double *b, const double *t,
+// t is left zeroed: the next operator application into t then needs no separate memset pass
+__global__ void k_cheb_update(double *x, double *xo, const double *dinv, const double *b, double *t,
                               double f1, double f2, int use_xo, int64_t n)
 {
   GRID_STRIDE(i, n) {
@@ -38,6 +39,7 @@ __global__ void k_cheb_update(double *x, double *xo, const double *dinv, const d
     if (use_xo) v += f1 * (xi - xo[i]);
     else v += f1 * xi;
     xo[i] = v;
+    t[i] = 0.0;
   }
 }
 __global__ void k_gather(double *y, const double *x, const uint32_t *idx, int64_t n) { GRID_STRIDE(i, n) y[i] = x[idx[i]]; }
@@ -63,7 +65,7 @@ int vec_pointwise(smf_ctx *ctx, double *z, double a, const double *d, const doub
 int vec_residual(smf_ctx *ctx, double *t, const double *b, int64_t n) { LAUNCH_EW(k_residual, n, t, b, n); return SMF_OK; }
 int cheb_first(smf_ctx *ctx, double *x, const double *dinv, const double *b, double inv_theta, int64_t n)
 { LAUNCH_EW(k_cheb_first, n, x, dinv, b, inv_theta, n); return SMF_OK; }
-int cheb_update(smf_ctx *ctx, double *x, double *xo, const double *dinv, const double *b, const double *t,
+int cheb_update(smf_ctx *ctx, double *x, double *xo, const double *dinv, const double *b, double *t,
                 double f1, double f2, bool use_xo, int64_t n)
 { LAUNCH_EW(k_cheb_update, n, x, xo, dinv, b, t, f1, f2, use_xo ? 1 : 0, n); return SMF_OK; }
 int vec_gather(smf_ctx *ctx, double *y, const double *x, const uint32_t *idx, int64_t n, bool scatter)
