@@ -191,6 +191,8 @@ struct CellParams {
   double vol, ps;
   const double *src_u, *src_p;
   double *dst_u, *dst_p;
+  int plain;                           // 1: read_dof_values_plain (constrained DoFs keep their values on read; their rows
+                                       //    receive nothing): the operator of correct_stokes_rhs()
 };
 
 // Loads whose issue order the compiler must keep (asm volatile): the staging code issues every index load of a thread,
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
         const int t = min(t0 + i * NT, n_items - 1), d = t - (t / DIM) * DIM;
         const bool cons = (e[i] >> (NODE_FLAG_SHIFT + d)) & 1u;
         v[i] = ldg_f64(P.src_u + (e[i] & NODE_IDX_MASK) + d);      // constrained DoFs are valid addresses, too
-        if (cons) v[i] = 0.0;
+        if (cons && !P.plain) v[i] = 0.0;
       }
 #pragma unroll
       for (int i = 0; i < SU; ++i) {
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
   if (MODE != 0)
     for (int j = threadIdx.x; j < n_nodes_p; j += NT) {
       const uint32_t e = nlp[j];
-      s_stagep[j] = (e >> 31) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
+      s_stagep[j] = ((e >> 31) && !P.plain) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
     }
   const bool active = lane < n_cells_b;
   const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
       if (t >= n_items) continue;
       const uint32_t idx = e[i] & NODE_IDX_MASK;
       const bool excl = STRUCT ? !(e[i] & NODE_SHARED_BIT) : (j < n_excl_u);
-      if ((e[i] >> (NODE_FLAG_SHIFT + d)) & 1u) P.dst_u[idx + d] = (MODE == 2) ? 0.0 : P.src_u[idx + d];
+      if ((e[i] >> (NODE_FLAG_SHIFT + d)) & 1u) P.dst_u[idx + d] = (MODE == 2 || P.plain) ? 0.0 : P.src_u[idx + d];
       else if (excl) P.dst_u[idx + d] = s_stage[d * MU + sl[i]];
       else atomicAdd(P.dst_u + idx + d, s_stage[d * MU + sl[i]]);
     }
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(32 * DIM, DIM == 3 ? 4 : 8) velocity_kernel(co
     for (int j = threadIdx.x; j < n_nodes_p; j += NT) {
       const uint32_t e = nlp[j];
       const uint32_t idx = e & NODE_IDX_MASK;
-      if (e >> 31) P.dst_p[idx] = P.src_p[idx];
+      if (e >> 31) P.dst_p[idx] = P.plain ? 0.0 : P.src_p[idx];
       else if (j < n_excl_p) P.dst_p[idx] = s_stagep[j];
       else atomicAdd(P.dst_p + idx, s_stagep[j]);
     }
@@ -629,7 +631,7 @@ template <int C> __device__ __forceinline__ void sb_park_p(const double (&yv)[8]
 template <int MODE, bool PERQ>
 __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellParams P, const unsigned char *lists, int n_batches)
 {
-  static_assert(MODE == 0 || MODE == 1, "A block and Stokes operator");
+  static_assert(MODE >= 0 && MODE <= 2, "A block, Stokes operator, B^T");
   constexpr int DIM = 3, NN = 27, NP = 8, MU = SB_SLOTS;
   constexpr int LBYTES = MODE == 0 ? SB_LIST_BYTES : SB_BLOCK_BYTES;     // bytes of a brick's lists that this mode needs
   extern __shared__ __align__(16) double smem[];
@@ -671,24 +673,26 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
     const double *srcd = P.src_u + d0;
     // (sub-batches: the list reads of a batch are in flight before its first copy is issued; u and T are live here)
     constexpr int SUBB = 4;
+    if (MODE != 2) {
 #pragma unroll 1
-    for (int k0 = 0; k0 < 16; k0 += SUBB) {
-      uint32_t e[SUBB], sl[SUBB];
+      for (int k0 = 0; k0 < 16; k0 += SUBB) {
+        uint32_t e[SUBB], sl[SUBB];
 #pragma unroll
-      for (int k = 0; k < SUBB; ++k) {
-        const int j = min(j0 + 32 * (k0 + k), 404);
-        e[k] = le[j]; sl[k] = ls[j];
-      }
-#pragma unroll
-      for (int k = 0; k < SUBB; ++k)
-        if (j0 + 32 * (k0 + k) < 405) {
-          const bool cons = (e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u;
-          cp_async8_zfill(base + 8u * sl[k], srcd + (e[k] & NODE_IDX_MASK), cons ? 0 : 8);
+        for (int k = 0; k < SUBB; ++k) {
+          const int j = min(j0 + 32 * (k0 + k), 404);
+          e[k] = le[j]; sl[k] = ls[j];
         }
+#pragma unroll
+        for (int k = 0; k < SUBB; ++k)
+          if (j0 + 32 * (k0 + k) < 405) {
+            const bool cons = ((e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u) && !P.plain;
+            cp_async8_zfill(base + 8u * sl[k], srcd + (e[k] & NODE_IDX_MASK), cons ? 0 : 8);
+          }
+      }
     }
-    if (MODE == 1 && tid < 75) {      // pressure values in lattice order
+    if (MODE != 0 && tid < 75) {      // pressure values in lattice order
       const uint32_t e = reinterpret_cast<const uint32_t *>(I + SB_LIST_BYTES)[tid];
-      cp_async8_zfill(smem_u32(sPA + tid), P.src_p + (e & NODE_IDX_MASK), (e >> 31) ? 0 : 8);
+      cp_async8_zfill(smem_u32(sPA + tid), P.src_p + (e & NODE_IDX_MASK), ((e >> 31) && !P.plain) ? 0 : 8);
     }
   };
 
@@ -699,7 +703,7 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
   __syncthreads();
   issue_values(sI);
   cp_async_commit();
-  double eta_next = PERQ ? 1.0 : P.eta_t[(size_t)b * P.n_eta * SUB + lane];
+  double eta_next = (PERQ || MODE == 2) ? 1.0 : P.eta_t[(size_t)b * P.n_eta * SUB + lane];
 
   for (int it = 0; b < n_batches; b += G, ++it) {
     unsigned char *I_cur = sI + (it & 1) * LBYTES, *I_nxt = sI + ((it + 1) & 1) * LBYTES;
@@ -712,9 +716,11 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
     eta.etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
 
     double u[NN], T[NN];
-    if (c == 0) sb_gather<0>(u, myA, lb); else if (c == 1) sb_gather<1>(u, myA, lb); else sb_gather<2>(u, myA, lb);
-    interp_all<DIM>(u);
-    if (MODE == 1) {
+    if (MODE != 2) {
+      if (c == 0) sb_gather<0>(u, myA, lb); else if (c == 1) sb_gather<1>(u, myA, lb); else sb_gather<2>(u, myA, lb);
+      interp_all<DIM>(u);
+    }
+    if (MODE != 0) {
       // pressure contribution to the velocity rows: T = (2D'_0)^T [ -e_c ps vol w_q p_q ]
       {
         double pn[NP], pq[NN];
@@ -729,7 +735,7 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
       }
       // pressure rows -ps (div u, q): this component's share, parked in sB (free until the accumulation) for the
       // lattice-wise sum after the next barrier
-      {
+      if (MODE == 1) {
         double dq[NN], yv[NP];
         const double f = -P.ps * P.vol * e0;
         for_lines<DIM, 0>([&](int a, int b2, int c2_) {
@@ -740,15 +746,17 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
         if (c == 0) sb_park_p<0>(yv, myB + lane); else if (c == 1) sb_park_p<1>(yv, myB + lane); else sb_park_p<2>(yv, myB + lane);
       }
     }
-    // diagonal direction: T (+)= (2D'_0)^T [ 2 eta w vol e_c^2 (2D'_0 u) ]
-    sb_diag<PERQ>(u, T, 2.0 * e0 * e0 * P.vol * eta0, eta, MODE == 1);
-    // pair {c, c+1}: publish e_{c+1} (2D'_1 u)
-    sb_publish(u, ex_lo, e1);
+    if (MODE != 2) {
+      // diagonal direction: T (+)= (2D'_0)^T [ 2 eta w vol e_c^2 (2D'_0 u) ]
+      sb_diag<PERQ>(u, T, 2.0 * e0 * e0 * P.vol * eta0, eta, MODE == 1);
+      // pair {c, c+1}: publish e_{c+1} (2D'_1 u)
+      sb_publish(u, ex_lo, e1);
+    }
     cp_async_wait_all();                    // (this thread's chunks of the next node list)
     __syncthreads();                        // publishes visible; every gather from sA is done; next list visible
     if (bn < n_batches) {
       issue_values(I_nxt);
-      if (!PERQ) eta_next = P.eta_t[(size_t)bn * P.n_eta * SUB + lane];
+      if (!PERQ && MODE != 2) eta_next = P.eta_t[(size_t)bn * P.n_eta * SUB + lane];
     }
     cp_async_commit();
     if (MODE == 1 && tid < 75) {
@@ -771,14 +779,16 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
           }
       const uint32_t e = reinterpret_cast<const uint32_t *>(I_cur + SB_LIST_BYTES)[tid];
       const uint32_t idx = e & NODE_IDX_MASK;
-      if (e >> 31) P.dst_p[idx] = P.src_p[idx];
+      if (e >> 31) P.dst_p[idx] = P.plain ? 0.0 : P.src_p[idx];
       else if (!(e & NODE_SHARED_BIT)) P.dst_p[idx] = acc;
       else atomicAdd(P.dst_p + idx, acc);
     }
     // pair {c-1, c}: X = eta w vol (e_{c-1} 2D'_2 u + partner), T += e_{c-1} (2D'_2)^T X, X published
-    sb_upper<PERQ>(u, T, ex_up, e2, P.vol * eta0, eta);
-    __syncthreads();
-    sb_lower(T, ex_lo, e1);
+    if (MODE != 2) {
+      sb_upper<PERQ>(u, T, ex_up, e2, P.vol * eta0, eta);
+      __syncthreads();
+      sb_lower(T, ex_lo, e1);
+    }
     interpT_all<DIM>(T);
     // accumulate into sB in ascending order of the low-face pattern; the first cell to touch a lattice point stores
     if (c == 0) sb_accumulate<0>(T, myB, lb, first_mask); else if (c == 1) sb_accumulate<1>(T, myB, lb, first_mask); else sb_accumulate<2>(T, myB, lb, first_mask);
@@ -817,7 +827,7 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
 #pragma unroll 1
         for (int j = j0; j < 405; j += 32) {
           const uint32_t e = le[j];
-          if ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) { const uint32_t idx = (e & NODE_IDX_MASK) + d0; P.dst_u[idx] = P.src_u[idx]; }
+          if ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) { const uint32_t idx = (e & NODE_IDX_MASK) + d0; P.dst_u[idx] = (MODE == 2 || P.plain) ? 0.0 : P.src_u[idx]; }
         }
       }
     }
@@ -1220,22 +1230,43 @@ template <int DIM, int NPD, int NCOMP> __global__ void __launch_bounds__(32 * TR
 // node, so every fine DoF is written (prolongation) / read (restriction) exactly once and the fine side needs no
 // atomics.  Restriction is the exact transpose; coarse nodes are shared between bricks, so they take one RED each.
 constexpr int TSB_THREADS = 96;
-__device__ __forceinline__ int sb_slot_rt(int X, int Y, int Z)
+// 1D Q2 prolongation on a two-cell macro line (5 coarse -> 9 fine), on one cell (3 -> 5), and their transposes
+__device__ __forceinline__ void pro9(const double (&c)[5], double (&f)[9])
+{
+  f[0] = c[0]; f[2] = c[1]; f[4] = c[2]; f[6] = c[3]; f[8] = c[4];
+  f[1] = 0.375 * c[0] + 0.75 * c[1] - 0.125 * c[2]; f[3] = -0.125 * c[0] + 0.75 * c[1] + 0.375 * c[2];
+  f[5] = 0.375 * c[2] + 0.75 * c[3] - 0.125 * c[4]; f[7] = -0.125 * c[2] + 0.75 * c[3] + 0.375 * c[4];
+}
+__device__ __forceinline__ void pro5(const double (&c)[3], double (&f)[5])
+{
+  f[0] = c[0]; f[2] = c[1]; f[4] = c[2];
+  f[1] = 0.375 * c[0] + 0.75 * c[1] - 0.125 * c[2]; f[3] = -0.125 * c[0] + 0.75 * c[1] + 0.375 * c[2];
+}
+__device__ __forceinline__ void res9(const double (&f)[9], double (&c)[5])
+{
+  c[0] = f[0] + 0.375 * f[1] - 0.125 * f[3];
+  c[1] = 0.75 * f[1] + f[2] + 0.75 * f[3];
+  c[2] = -0.125 * f[1] + 0.375 * f[3] + f[4] + 0.375 * f[5] - 0.125 * f[7];
+  c[3] = 0.75 * f[5] + f[6] + 0.75 * f[7];
+  c[4] = -0.125 * f[5] + 0.375 * f[7] + f[8];
+}
+__device__ __forceinline__ void res5(const double (&f)[5], double (&c)[3])
+{
+  c[0] = f[0] + 0.375 * f[1] - 0.125 * f[3];
+  c[1] = 0.75 * f[1] + f[2] + 0.75 * f[3];
+  c[2] = -0.125 * f[1] + 0.375 * f[3] + f[4];
+}
+// staging slots of the five lattice points (X, Y, Z = 0..4) of one z-line
+__device__ __forceinline__ void zline_slots(int X, int Y, int (&sl)[5])
 {
   const int v = (X & 1) + 2 * (Y & 1);
   constexpr int B00 = sb_class_base(0, 0), B10 = sb_class_base(1, 0), B20 = sb_class_base(2, 0), B30 = sb_class_base(3, 0);
   constexpr int B01 = sb_class_base(0, 1), B11 = sb_class_base(1, 1), B21 = sb_class_base(2, 1), B31 = sb_class_base(3, 1);
-  const int base = (Z & 1) ? (v == 0 ? B01 : (v == 1 ? B11 : (v == 2 ? B21 : B31))) : (v == 0 ? B00 : (v == 1 ? B10 : (v == 2 ? B20 : B30)));
+  const int be = v == 0 ? B00 : (v == 1 ? B10 : (v == 2 ? B20 : B30)), bo = v == 0 ? B01 : (v == 1 ? B11 : (v == 2 ? B21 : B31));
   const int sy = (v & 1) ? 4 : 8, sz = v == 0 ? 52 : (v == 2 ? 36 : 24);
-  return base + (X >> 1) + sy * (Y >> 1) + sz * (Z >> 1);
-}
-// first coarse node of the Q2 row of fine position X on a macro line with NC coarse nodes
-template <int NC> __device__ __forceinline__ int tr_i0(int X) { return NC == 3 ? 0 : min(2 * (X >> 2), NC - 3); }
-// weight of coarse node I in the row of fine position X (0 outside the row)
-template <int NC> __device__ __forceinline__ double tr_w(int X, int I)
-{
-  const int i0 = tr_i0<NC>(X), k = I - i0;
-  return (k < 0 || k > 2) ? 0.0 : p2row(X - 2 * i0, k);
+  const int o = (X >> 1) + sy * (Y >> 1);
+  sl[0] = be + o; sl[2] = be + o + sz; sl[4] = be + o + 2 * sz;
+  sl[1] = bo + o; sl[3] = bo + o + sz;
 }
 
 struct TransferSbParams {
@@ -1245,6 +1276,7 @@ struct TransferSbParams {
   int add;
 };
 
+// One thread per line of each sweep; all weights and loop bounds are compile-time constants.
 __global__ void __launch_bounds__(TSB_THREADS) prolongate_sb_kernel(const TransferSbParams P)
 {
   __shared__ __align__(16) unsigned char s_tb[TB_BYTES];
@@ -1260,35 +1292,46 @@ __global__ void __launch_bounds__(TSB_THREADS) prolongate_sb_kernel(const Transf
   __syncthreads();
   const uint32_t *cl = reinterpret_cast<const uint32_t *>(s_tb);
   const unsigned char *ob = s_tb + TB_COARSE * 4;
-  for (int t = tid; t < 225; t += TSB_THREADS) {       // coarse values, constrained ones as zero
-    const int j = t / 3, d = t - 3 * j;
+  const int j0 = tid / 3, d0 = tid - 3 * j0;
+  for (int j = j0; j < 75; j += 32) {                  // coarse values, constrained ones as zero
     const uint32_t e = cl[j];
-    sC[d][j] = ((e >> (NODE_FLAG_SHIFT + d)) & 1u) ? 0.0 : P.src[(e & NODE_IDX_MASK) + d];
+    sC[d0][j] = ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) ? 0.0 : P.src[(e & NODE_IDX_MASK) + d0];
   }
   __syncthreads();
-  for (int t = tid; t < 405; t += TSB_THREADS) {       // x: [K][J][I] -> [K][J][X]
-    const int d = t / 135, rem = t - 135 * d, jk = rem / 9, X = rem - 9 * jk;
-    const int i0 = tr_i0<5>(X), r = X - 2 * i0;
-    const double *cc = &sC[d][jk * 5 + i0];
-    A1[d][rem] = p2row(r, 0) * cc[0] + p2row(r, 1) * cc[1] + p2row(r, 2) * cc[2];
+  if (tid < 45) {                                      // x: lines (d, K, J): 5 coarse -> 9 fine
+    const int d = tid / 15, jk = tid - 15 * d;
+    double c[5], f[9];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c[i] = sC[d][jk * 5 + i];
+    pro9(c, f);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A1[d][jk * 9 + i] = f[i];
   }
   __syncthreads();
-  for (int t = tid; t < 729; t += TSB_THREADS) {       // y: [K][J][X] -> [K][Y][X]
-    const int d = t / 243, rem = t - 243 * d, K = rem / 81, r2 = rem - 81 * K, Y = r2 / 9, X = r2 - 9 * Y;
-    const int j0 = tr_i0<5>(Y), r = Y - 2 * j0;
-    const double *cc = &A1[d][(K * 5 + j0) * 9 + X];
-    A2[d][rem] = p2row(r, 0) * cc[0] + p2row(r, 1) * cc[9] + p2row(r, 2) * cc[18];
+  if (tid < 81) {                                      // y: lines (d, K, X)
+    const int d = tid / 27, r = tid - 27 * d, K = r / 9, X = r - 9 * K;
+    double c[5], f[9];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c[i] = A1[d][(K * 5 + i) * 9 + X];
+    pro9(c, f);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A2[d][(K * 9 + i) * 9 + X] = f[i];
   }
   __syncthreads();
-  for (int t = tid; t < 1215; t += TSB_THREADS) {      // z: [K][Y][X] -> staging slot of (X, Y, Z)
-    const int d = t / 405, rem = t - 405 * d, Z = rem / 81, yx = rem - 81 * Z, Y = yx / 9, X = yx - 9 * Y;
-    const double *cc = &A2[d][yx];
-    sO[d][sb_slot_rt(X, Y, Z)] = p2row(Z, 0) * cc[0] + p2row(Z, 1) * cc[81] + p2row(Z, 2) * cc[162];
+  for (int t = tid; t < 243; t += TSB_THREADS) {       // z: lines (d, Y, X): 3 -> 5, into the staging slots
+    const int d = t / 81, yx = t - 81 * d, Y = yx / 9, X = yx - 9 * Y;
+    double c[3], f[5];
+    int sl[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c[i] = A2[d][i * 81 + yx];
+    pro5(c, f);
+    zline_slots(X, Y, sl);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) sO[d][sl[i]] = f[i];
   }
   __syncthreads();
   const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
   const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
-  const int j0 = tid / 3, d0 = tid - 3 * j0;
   for (int j = j0; j < 405; j += 32) {
     if (!(ob[j] & 1)) continue;
     const uint32_t idx = (le[j] & NODE_IDX_MASK) + d0;
@@ -1314,33 +1357,43 @@ __global__ void __launch_bounds__(TSB_THREADS) restrict_sb_kernel(const Transfer
   const unsigned char *ob = s_tb + TB_COARSE * 4;
   const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
   const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
-  {
-    const int j0 = tid / 3, d0 = tid - 3 * j0;
-    for (int j = j0; j < 405; j += 32)
-      sO[d0][ls[j]] = (ob[j] & 2) ? P.src[(le[j] & NODE_IDX_MASK) + d0] : 0.0;
-  }
+  const int j0 = tid / 3, d0 = tid - 3 * j0;
+  for (int j = j0; j < 405; j += 32)
+    sO[d0][ls[j]] = (ob[j] & 2) ? P.src[(le[j] & NODE_IDX_MASK) + d0] : 0.0;
   __syncthreads();
-  for (int t = tid; t < 729; t += TSB_THREADS) {       // z^T: slots -> [K][Y][X]
-    const int d = t / 243, rem = t - 243 * d, K = rem / 81, yx = rem - 81 * K, Y = yx / 9, X = yx - 9 * Y;
-    double a = 0.0;
+  for (int t = tid; t < 243; t += TSB_THREADS) {       // z^T: lines (d, Y, X): 5 -> 3
+    const int d = t / 81, yx = t - 81 * d, Y = yx / 9, X = yx - 9 * Y;
+    double f[5], c[3];
+    int sl[5];
+    zline_slots(X, Y, sl);
 #pragma unroll
-    for (int Z = 0; Z < 5; ++Z) a = fma(tr_w<3>(Z, K), sO[d][sb_slot_rt(X, Y, Z)], a);
-    B2[d][rem] = a;
+    for (int i = 0; i < 5; ++i) f[i] = sO[d][sl[i]];
+    res5(f, c);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) B2[d][i * 81 + yx] = c[i];
   }
   __syncthreads();
-  for (int t = tid; t < 405; t += TSB_THREADS) {       // y^T: [K][Y][X] -> [K][J][X]
-    const int d = t / 135, rem = t - 135 * d, jk = rem / 9, X = rem - 9 * jk, K = jk / 5, J = jk - 5 * K;
-    double a = 0.0;
-    for (int Y = max(0, 2 * J - 3); Y <= min(8, 2 * J + 3); ++Y) a = fma(tr_w<5>(Y, J), B2[d][(K * 9 + Y) * 9 + X], a);
-    B1[d][rem] = a;
+  if (tid < 81) {                                      // y^T: lines (d, K, X): 9 -> 5
+    const int d = tid / 27, r = tid - 27 * d, K = r / 9, X = r - 9 * K;
+    double f[9], c[5];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = B2[d][(K * 9 + i) * 9 + X];
+    res9(f, c);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) B1[d][(K * 5 + i) * 9 + X] = c[i];
   }
   __syncthreads();
-  for (int t = tid; t < 225; t += TSB_THREADS) {       // x^T: [K][J][X] -> coarse node (I, J, K), one RED per DoF
-    const int j = t / 3, d = t - 3 * j, I = j % 5, jk = j / 5;
-    double a = 0.0;
-    for (int X = max(0, 2 * I - 3); X <= min(8, 2 * I + 3); ++X) a = fma(tr_w<5>(X, I), B1[d][jk * 9 + X], a);
-    const uint32_t e = cl[j];
-    if (!((e >> (NODE_FLAG_SHIFT + d)) & 1u) && a != 0.0) atomicAdd(P.dst + (e & NODE_IDX_MASK) + d, a);
+  if (tid < 45) {                                      // x^T: lines (d, K, J): 9 -> 5 coarse nodes, one RED per DoF
+    const int d = tid / 15, jk = tid - 15 * d;
+    double f[9], c[5];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = B1[d][jk * 9 + i];
+    res9(f, c);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t e = cl[jk * 5 + i];
+      if (!((e >> (NODE_FLAG_SHIFT + d)) & 1u) && c[i] != 0.0) atomicAdd(P.dst + (e & NODE_IDX_MASK) + d, c[i]);
+    }
   }
 }
 
@@ -1390,7 +1443,7 @@ template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, Level
   }
   const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
   {
-    ProfScope prof(ctx, MODE == 1 ? B_STOKES : (fine ? B_A_FINE : B_A_COARSE));
+    ProfScope prof(ctx, MODE == 1 ? B_STOKES : (MODE == 2 ? B_BT : (fine ? B_A_FINE : B_A_COARSE)));
     int grid = std::min(L.n_batches, resident);
     if (ctx->max_grid_blocks > 0) grid = std::min(grid, ctx->max_grid_blocks);
     velocity_sb_kernel<MODE, PERQ><<<grid, SBK_THREADS, smem, ctx->stream>>>(P, L.sb_lists, L.n_batches);
@@ -1401,9 +1454,9 @@ template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, Level
 }
 template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
-  if (DIM == 3 && L.structured && MODE != 2 && ctx->use_pipelined && L.sb_lists) {
-    if (L.n_eta != 1) return launch_velocity_sb<(MODE == 2 ? 0 : MODE), true>(ctx, L, P);
-    return launch_velocity_sb<(MODE == 2 ? 0 : MODE), false>(ctx, L, P);
+  if (DIM == 3 && L.structured && ctx->use_pipelined && L.sb_lists) {
+    if (MODE != 2 && L.n_eta != 1) return launch_velocity_sb<MODE, true>(ctx, L, P);
+    return launch_velocity_sb<MODE, false>(ctx, L, P);
   }
   if (DIM == 3 && L.structured) {
     if (MODE != 2 && L.n_eta != 1) return launch_velocity_t<3, MODE, true, true>(ctx, L, P);
@@ -1431,11 +1484,12 @@ int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bo
   if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
   return exchange_add(ctx, L.ex_u, dst);
 }
-int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool plain)
 {
   if (int e = check_level(ctx, L)) return e;
   CellParams P = make_params(L);
   P.src_u = src_u; P.src_p = src_p; P.dst_u = dst_u; P.dst_p = dst_p;
+  P.plain = plain ? 1 : 0;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
   SMF_CUDA(cudaMemsetAsync(dst_p, 0, sizeof(double) * L.n_p, ctx->stream));
   if (int e = L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P)) return e;

@@ -233,7 +233,7 @@ struct VecBucket {      // books the vector kernels launched in this scope under
 };
 // operators.cu
 int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero = false);
-int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool plain = false);
 int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_p);
 int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero = false);
 int launch_diag(smf_ctx *ctx, LevelDev &L);

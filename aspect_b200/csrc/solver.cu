@@ -245,6 +245,23 @@ static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
   const int64_t n = lsize(ctx, S, L);
   const uint32_t *map = velocity ? ctx->copy_u : ctx->copy_p;
   MGVectors &V = (*S.v)[L];
+  // Identity copy_to_mg / copy_from_mg and a finest level outside the CUDA graph: no copies at all.  The defect is
+  // only read, so src serves as V.b; the smoothers alternate between x and xo, and the number of updates on the
+  // level is known, so the buffer the result will end in is replaced by dst for the duration of the cycle.
+  const Smoother &sm = (*S.sm)[L];
+  const bool replayed = ctx->use_graphs && L == ctx->graph_level && ctx->prof_mode != 2 && !(ctx->prof_mode == 1 && L == ctx->cfg.n_levels - 1);
+  if (!map && dst != src && !replayed && L > 0 && sm.degree >= 2 && std::fabs(sm.delta) >= 1e-40) {
+    const int swaps = (sm.degree - 1) + (S.steps - 1) * sm.degree + S.steps * sm.degree;
+    double *const b0 = V.b, *const x0 = V.x, *const xo0 = V.xo;
+    V.b = const_cast<double *>(src);
+    if (swaps & 1) V.xo = dst; else V.x = dst;
+    const int rc = level_v_step(ctx, S, L);
+    double *res = V.res;
+    V.b = b0; V.x = x0; V.xo = xo0;
+    if (rc) return rc;
+    if (res != dst) TRY(vec_copy(ctx, dst, res, n));
+    return SMF_OK;
+  }
   // copy_to_mg
   if (map) TRY(vec_gather(ctx, V.b, src, map, n, true));
   else TRY(vec_copy(ctx, V.b, src, n));
@@ -422,6 +439,19 @@ int smf_vmult_mass(smf_ctx *ctx, int level, double *dst, const double *src)
   if (!ctx) return SMF_ERR_INVALID;
   if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
   return launch_vmult_mass(ctx, ctx->lev(level), dst, src);
+}
+
+// StokesMatrixFreeHandler::correct_stokes_rhs (local_smoothing.cc:617-754): rhs -= Stokes(u0), u0 read with
+// read_dof_values_plain (boundary values kept), constrained rows receive nothing
+int smf_correct_stokes_rhs(smf_ctx *ctx, double *rhs_u, double *rhs_p, const double *u0_u, const double *u0_p)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  TRY(ensure_tmp(ctx));
+  TRY(launch_vmult_stokes(ctx, A, ctx->tmp_u, ctx->tmp_p, u0_u, u0_p, true));
+  TRY(vec_axpy(ctx, rhs_u, -1.0, ctx->tmp_u, A.n_u));
+  TRY(vec_axpy(ctx, rhs_p, -1.0, ctx->tmp_p, A.n_p));
+  return SMF_OK;
 }
 
 int smf_vmult_stokes_host(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)

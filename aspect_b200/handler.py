@@ -278,6 +278,11 @@ class StokesMatrixFreeHandler:
         out["converged"] = rc == 0
         return sol, out
 
+    def correct_stokes_rhs(self, rhs, u0):
+        """`StokesMatrixFreeHandler::correct_stokes_rhs` (local_smoothing.cc:617-754): rhs -= Stokes(u0) for inhomogeneous
+        boundary values; rhs and u0 are (velocity, pressure) DeviceVector pairs, u0 = boundary values, zero elsewhere."""
+        self._check(self.lib.smf_correct_stokes_rhs(self.ctx, ptr(rhs[0].ptr), ptr(rhs[1].ptr), ptr(u0[0].ptr), ptr(u0[1].ptr)))
+
     def solve_device(self, sol, rhs):
         """Device-resident solve: sol, rhs are (velocity, pressure) DeviceVector pairs (pressure already scaled)."""
         prm, res = self._params(), _lib.SolveResult()

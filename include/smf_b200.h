@@ -125,6 +125,10 @@ int smf_synchronize(smf_ctx *ctx);
 /* ---- operators (device pointers) ------------------------------------------------------------ */
 /* StokesOperator::vmult (matrix_free_operators.cc:606-627, local_apply :376-547), active level */
 int smf_vmult_stokes(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+/* StokesMatrixFreeHandler::correct_stokes_rhs (stokes_matrix_free_local_smoothing.cc:617-754): rhs -= Stokes(u0) with
+   u0 read by read_dof_values_plain (boundary values are kept), nothing is added to constrained rows.  u0 holds the
+   inhomogeneous boundary values and zeros elsewhere (AffineConstraints::distribute of the zero vector, :632-642). */
+int smf_correct_stokes_rhs(smf_ctx *ctx, double *rhs_u, double *rhs_p, const double *u0_u, const double *u0_p);
 /* ABlockOperator::vmult (matrix_free_operators.cc:1056-1064, :1029-1052) */
 int smf_vmult_A(smf_ctx *ctx, int level, double *dst, const double *src);
 /* BTBlockOperator::vmult (matrix_free_operators.cc:717-725, :668-701), active level */
