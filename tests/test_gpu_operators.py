@@ -114,3 +114,38 @@ def test_pipelined_velocity_kernel(averaging, grid_cap, pipelined):
         h.mg_matrices_A_block[l].vmult(du, su)
         assert rel(du.to_host(), ob.apply_A(l, xl)) < TOL
     h.close()
+
+
+@pytest.mark.parametrize("dim,R,bc,averaging", [(2, 3, "tangential", "none"), (3, 2, "zero", "harmonic average"), (3, 3, "zero", "none")])
+def test_correct_stokes_rhs(dim, R, bc, averaging):
+    """StokesMatrixFreeHandler::correct_stokes_rhs (local_smoothing.cc:617-754): rhs -= Stokes(u0) with plain reads of
+    u0 (boundary values kept) and nothing added to constrained rows, against the UNCONSTRAINED assembled operator."""
+    from oracle import assembled, coeff
+    hier = synthetic.BoxHierarchy(dim, R)
+    ohier = omesh.Hierarchy(dim, R)
+    rng = np.random.default_rng(11)
+    eta_q = np.exp(rng.uniform(-3, 3, size=(hier.active.n_cells, 3 ** dim)))
+    ps = 1.7
+    h = StokesMatrixFreeHandler(dim)
+    h.setup_dofs(hier, bc)
+    h.assemble(eta_q, averaging, ps)
+    h.build_preconditioner()
+    act = ohier.active
+    op = {"none": "none", "harmonic average": "harmonic"}[averaging]
+    eta_active, _, _, _ = coeff.viscosity_tables(ohier, eta_q, op)
+    K, _, _ = assembled.stokes_matrix(act, eta_active, ps, None)
+    cons = hier.active.constrained_u(bc).astype(np.int64)
+    u0 = np.zeros(act.n_u + act.n_p)
+    u0[cons] = rng.uniform(-1, 1, len(cons))                       # inhomogeneous boundary values, zero elsewhere
+    rhs = rng.uniform(-1, 1, act.n_u + act.n_p)
+    corr = -(K @ u0)
+    corr[cons] = 0.0
+    want = rhs + corr
+    r, u = h.initialize_dof_vector(), h.initialize_dof_vector()
+    r[0].from_host(rhs[:act.n_u]); r[1].from_host(rhs[act.n_u:])
+    u[0].from_host(u0[:act.n_u]); u[1].from_host(u0[act.n_u:])
+    h.correct_stokes_rhs(r, u)
+    got = np.concatenate([r[0].to_host(), r[1].to_host()])
+    assert rel(got, want) < TOL
+    assert np.array_equal(got[cons], rhs[cons])                     # constrained rows untouched
+    h.close()
