@@ -87,6 +87,8 @@ def nsinker_problem(hier, n_sinkers=8, viscosity_ratio=1e4, averaging="harmonic 
 def solcx_problem(hier, averaging="harmonic average only viscosity"):
     act = hier.active
     eta_q, rho_q = solcx_material(act.quadrature_points())
+    if averaging != "none" and not averaging.endswith("only viscosity"):
+        rho_q = average_viscosity(rho_q, averaging)          # (tests/no_cheap_gmg: `harmonic average` of the density too)
     g = np.zeros(act.dim); g[-1] = -1.0
     f = assemble_rhs(act, rho_q, g)
     f[act.constrained_u("tangential").astype(np.int64)] = 0.0

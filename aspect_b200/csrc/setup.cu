@@ -593,6 +593,8 @@ int smf_vec_d2h(smf_ctx *ctx, double *host, const double *dev, int64_t n)
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   return SMF_OK;
 }
+int smf_vec_copy(smf_ctx *ctx, double *dst, const double *src, int64_t n)
+{ if (!ctx) return SMF_ERR_INVALID; return vec_copy(ctx, dst, src, n); }
 int smf_vec_set(smf_ctx *ctx, double *dev, double value, int64_t n)
 {
   if (!ctx || (!dev && n > 0)) return SMF_ERR_INVALID;

@@ -167,6 +167,9 @@ struct smf_ctx {
   double *tmp_u = nullptr, *tmp_p = nullptr, *tmp_u2 = nullptr, *tmp_p2 = nullptr;
   double *io_buf = nullptr; int64_t io_n = 0;         // device staging of smf_solve_host
   int n_A_prec = 0, n_S_prec = 0;
+  int n_A_exp = 0, n_S_exp = 0;                       // inner CG iterations of the expensive phase
+  double *cg_buf = nullptr;                           // [3][n_u] scratch of the inner CG solves
+  double *idr_normals = nullptr; int64_t idr_normals_n = 0;   // IDR(s) shadow-vector entries (kept between solves)
   // distributed run (comm.cu): one subdomain per rank
   int rank = 0, world = 1;
   void *comm = nullptr;                               // ncclComm_t

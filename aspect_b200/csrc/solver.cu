@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <random>
 
 using namespace smf;
 
@@ -285,18 +286,91 @@ static int ensure_tmp(smf_ctx *ctx)
   return SMF_OK;
 }
 
-// BlockSchurPreconditioner::vmult, cheap variant (block_stokes_preconditioner.h:220-255)
-static int precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src);
+
+// deal.II SolverCG from a zero start vector, preconditioned by the V-cycle: the inner solves of the expensive phase
+// (InverseVelocityBlock::vmult with do_solve_A, block_stokes_preconditioner.h:108-135; SchurApproximation::vmult with
+// do_solve_Schur_complement, :312-345).  Iterations = SolverControl::last_step().
+static int inner_cg(smf_ctx *ctx, bool velocity, double *x, const double *b, double tol, int max_its, int *its_out)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t n = velocity ? A.n_u : A.n_p;
+  if (!ctx->cg_buf) {
+    SMF_CUDA(cudaMalloc(&ctx->cg_buf, sizeof(double) * 3 * A.n_u));
+    ctx->bytes += sizeof(double) * 3 * A.n_u;
+  }
+  double *g = ctx->cg_buf, *d = g + A.n_u, *h = d + A.n_u;
+  DotWeights dw(ctx, velocity ? A.ex_u.weights : A.ex_p.weights);
+  *its_out = 0;
+  TRY(vec_set(ctx, x, 0.0, n));
+  TRY(vec_copy(ctx, g, b, n));
+  TRY(vec_scale(ctx, g, -1.0, n));                    // g = A x - b
+  double r2;
+  TRY(vec_norm2(ctx, g, n, &r2));
+  if (std::sqrt(r2) <= tol) return SMF_OK;
+  double gh = 0.0;
+  for (int it = 1;; ++it) {
+    TRY(vcycle(ctx, velocity, h, g));
+    if (it > 1) {
+      double beta = gh;
+      TRY(vec_dot(ctx, g, h, n, &gh));
+      beta = gh / beta;
+      TRY(vec_sadd(ctx, d, beta, -1.0, h, n));        // d = -h + beta d
+    } else {
+      TRY(vec_copy(ctx, d, h, n));
+      TRY(vec_scale(ctx, d, -1.0, n));
+      TRY(vec_dot(ctx, g, h, n, &gh));
+    }
+    TRY(velocity ? launch_vmult_A(ctx, A, h, d) : launch_vmult_mass(ctx, A, h, d));
+    double dAd;
+    TRY(vec_dot(ctx, d, h, n, &dAd));
+    const double alpha = gh / dAd;
+    TRY(vec_axpy(ctx, x, alpha, d, n));
+    TRY(vec_axpy(ctx, g, alpha, h, n));
+    TRY(vec_norm2(ctx, g, n, &r2));
+    *its_out = it;
+    if (std::sqrt(r2) <= tol) return SMF_OK;
+    if (it >= max_its) return SMF_NO_CONVERGENCE;
+  }
+}
+
+// BlockSchurPreconditioner::vmult (block_stokes_preconditioner.h:220-255): cheap variant = one V-cycle per block;
+// expensive variant = CG solves with the active-level mass matrix / A block, preconditioned by the V-cycles
+static int precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p,
+                        const smf_solve_params *expensive = nullptr)
 {
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   TRY(ensure_tmp(ctx));
-  TRY(vcycle(ctx, false, dst_p, src_p));            // S^-1 (SchurApproximation::vmult :346-351)
-  ctx->n_S_prec++;
+  if (!expensive) {
+    TRY(vcycle(ctx, false, dst_p, src_p));            // S^-1 (SchurApproximation::vmult :346-351)
+    ctx->n_S_prec++;
+  } else {
+    double r2;
+    { DotWeights dw(ctx, A.ex_p.weights); TRY(vec_norm2(ctx, src_p, A.n_p, &r2)); }
+    const double nrm = std::sqrt(r2);
+    if (nrm > 1e-50) {
+      int its = 0;
+      const int rc = inner_cg(ctx, false, dst_p, src_p, nrm * expensive->linear_solver_S_block_tolerance, 100, &its);
+      ctx->n_S_exp += its;
+      if (rc == SMF_NO_CONVERGENCE) return ctx->fail(SMF_NO_CONVERGENCE, "iterative (bottom right) solver did not converge in BlockSchurPreconditioner::vmult");
+      TRY(rc);
+    } else TRY(vec_set(ctx, dst_p, 0.0, A.n_p));
+  }
   TRY(vec_scale(ctx, dst_p, -1.0, A.n_p));
   TRY(launch_vmult_BT(ctx, A, ctx->tmp_u, dst_p));  // tmp = B^T z_p
   TRY(vec_sadd(ctx, ctx->tmp_u, -1.0, 1.0, src_u, A.n_u));   // tmp = src_u - tmp
-  TRY(vcycle(ctx, true, dst_u, ctx->tmp_u));        // A^-1 (InverseVelocityBlock::vmult :148-152)
-  ctx->n_A_prec++;
+  if (!expensive) {
+    TRY(vcycle(ctx, true, dst_u, ctx->tmp_u));        // A^-1 (InverseVelocityBlock::vmult :148-152)
+    ctx->n_A_prec++;
+  } else {
+    double r2;
+    { DotWeights dw(ctx, A.ex_u.weights); TRY(vec_norm2(ctx, ctx->tmp_u, A.n_u, &r2)); }
+    int its = 0;
+    const int rc = inner_cg(ctx, true, dst_u, ctx->tmp_u, std::sqrt(r2) * expensive->linear_solver_A_block_tolerance, 10000, &its);
+    ctx->n_A_exp += its;
+    if (rc == SMF_NO_CONVERGENCE) return ctx->fail(SMF_NO_CONVERGENCE, "iterative (top left) solver did not converge in BlockSchurPreconditioner::vmult");
+    TRY(rc);
+  }
   return SMF_OK;
 }
 
@@ -416,6 +490,270 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
   TRY(vec_copy(ctx, x_p, xb + nu, np));
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   res->iterations = its;
+  res->final_residual = rho;
+  return state == 1 ? SMF_OK : SMF_NO_CONVERGENCE;
+}
+
+
+// SolverFGMRES(AdditionalData(restart)) with the expensive preconditioner (local_smoothing.cc:1333-1350).  The basis
+// vectors v_j and the preconditioned vectors z_j are allocated as the iteration proceeds (K[2 + 2j], K[3 + 2j]).
+static int fgmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double *x_p, const double *b_u, const double *b_p,
+                  double tol, smf_solve_result *res)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t nu = A.n_u, np = A.n_p, n = nu + np;
+  const int restart = std::max(1, std::min(prm->gmres_restart_length, 100));
+  const int max_its = prm->n_expensive_stokes_solver_steps;
+  TRY(ensure_krylov(ctx, 4));
+  DotWeights dw(ctx, ctx->block_weights);
+  std::vector<double *> &K = ctx->krylov;
+  double *xb = K[0], *p = K[1];
+  TRY(vec_copy(ctx, xb, x_u, nu));
+  TRY(vec_copy(ctx, xb + nu, x_p, np));
+  std::vector<double> H((size_t)(restart + 1) * restart, 0.0), gamma(restart + 1), ci(restart), si(restart), h(restart + 3), hh(restart + 3);
+  std::vector<double *> V, Z;
+  int its = 0, state = 0;
+  double rho = 0;
+  while (state == 0) {
+    TRY(launch_vmult_stokes(ctx, A, p, p + nu, xb, xb + nu));
+    TRY(vec_sadd(ctx, p, -1.0, 1.0, b_u, nu));
+    TRY(vec_sadd(ctx, p + nu, -1.0, 1.0, b_p, np));
+    double r2;
+    TRY(vec_norm2(ctx, p, n, &r2));
+    rho = std::sqrt(r2);
+    if (its == 0 && res->iterations == 0) res->initial_residual = rho;
+    if (rho <= tol) { state = 1; break; }
+    if (its >= max_its) { state = 2; break; }
+    std::fill(gamma.begin(), gamma.end(), 0.0);
+    gamma[0] = rho;
+    V.assign(1, K[2]); Z.clear();
+    TRY(vec_copy(ctx, V[0], p, n));
+    TRY(vec_scale(ctx, V[0], 1.0 / rho, n));
+    int dim = 0;
+    for (int j = 0; j < restart && state == 0; ++j) {
+      ++its;
+      TRY(ensure_krylov(ctx, 2 + 2 * (j + 1) + 1));
+      Z.push_back(K[3 + 2 * j]);
+      V.push_back(K[2 + 2 * (j + 1)]);
+      double *vv = V[j + 1];
+      TRY(precondition(ctx, Z[j], Z[j] + nu, V[j], V[j] + nu, prm));
+      TRY(launch_vmult_stokes(ctx, A, vv, vv + nu, Z[j], Z[j] + nu));
+      dim = j + 1;
+      {
+        VecBucket vb(ctx, B_ORTHO);
+        TRY(vec_multi_dot(ctx, V.data(), dim, vv, n, nullptr, false));
+        TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, h.data()));
+        TRY(vec_multi_dot(ctx, V.data(), dim, vv, n, nullptr, false));
+        TRY(vec_multi_axpy_from_dots(ctx, vv, dim, n, hh.data()));
+      }
+      for (int i = 0; i < dim; ++i) h[i] += hh[i];
+      const double nrm = std::sqrt(hh[dim + 1]);
+      h[dim] = nrm;
+      if (nrm != 0.0) TRY(vec_scale(ctx, vv, 1.0 / nrm, n));
+      for (int i = 0; i < j; ++i) {
+        const double t = h[i];
+        h[i] = ci[i] * t + si[i] * h[i + 1];
+        h[i + 1] = -si[i] * t + ci[i] * h[i + 1];
+      }
+      const double s = std::sqrt(h[j] * h[j] + h[j + 1] * h[j + 1]);
+      ci[j] = h[j] / s; si[j] = h[j + 1] / s;
+      h[j] = s;
+      gamma[j + 1] = -si[j] * gamma[j];
+      gamma[j] *= ci[j];
+      for (int i = 0; i < dim; ++i) H[(size_t)i * restart + j] = h[i];
+      rho = std::fabs(gamma[dim]);
+      if (rho <= tol) state = 1;
+      else if (its >= max_its) state = 2;
+    }
+    std::vector<double> y(dim);
+    for (int i = dim - 1; i >= 0; --i) {
+      double s = gamma[i];
+      for (int k = i + 1; k < dim; ++k) s -= H[(size_t)i * restart + k] * y[k];
+      y[i] = s / H[(size_t)i * restart + i];
+    }
+    TRY(vec_multi_add(ctx, xb, Z.data(), y.data(), dim, n));     // x += Z y
+  }
+  TRY(vec_copy(ctx, x_u, xb, nu));
+  TRY(vec_copy(ctx, x_p, xb + nu, np));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  res->iterations_expensive = its;
+  res->final_residual = rho;
+  return state == 1 ? SMF_OK : SMF_NO_CONVERGENCE;
+}
+
+// Shadow vectors of SolverIDR: Q_1..Q_{s-1} are filled with std::normal_distribution<double>(0,1) values drawn from a
+// default-seeded std::mt19937, entry by entry over the locally owned DoFs (velocity block, then pressure block), the
+// stream continuing from one vector to the next.  nvcc's host compiler is g++, so this IS deal.II's stream (libstdc++).
+// The values only depend on (n, s): they are kept on the device between solves.  With several ranks the entries are a
+// hash of the partition-independent global DoF number instead (every copy of a shared DoF must get the same value).
+static uint64_t mix64(uint64_t z)
+{ z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); }
+static int idr_shadow_vectors(smf_ctx *ctx, int s, int64_t nu, int64_t np)
+{
+  const int64_t n = nu + np;
+  if (ctx->idr_normals && ctx->idr_normals_n == (int64_t)(s - 1) * n) return SMF_OK;
+  cudaFree(ctx->idr_normals); ctx->idr_normals = nullptr; ctx->idr_normals_n = 0;
+  if (s < 2) return SMF_OK;
+  std::vector<double> host((size_t)(s - 1) * n);
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (ctx->world == 1) {
+    std::mt19937 rng;
+    std::normal_distribution<double> normal(0.0, 1.0);
+    for (double &v : host) v = normal(rng);
+  } else {
+    if (!A.ex_u.gid || !A.ex_p.gid) return ctx->fail(SMF_ERR_INVALID, "IDR(s) on several ranks needs the global DoF numbers (smf_set_exchange)");
+    std::vector<int64_t> gid(n);
+    SMF_CUDA(cudaMemcpy(gid.data(), A.ex_u.gid, sizeof(int64_t) * nu, cudaMemcpyDeviceToHost));
+    SMF_CUDA(cudaMemcpy(gid.data() + nu, A.ex_p.gid, sizeof(int64_t) * np, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < s - 1; ++i)
+      for (int64_t k = 0; k < n; ++k) {
+        const uint64_t key = mix64((uint64_t)gid[k] * 2 + (k >= nu ? 1 : 0) + ((uint64_t)(i + 1) << 56));
+        const double u1 = ((double)(mix64(key) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)(mix64(key ^ 0x5bf03635ull) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+        host[(size_t)i * n + k] = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+      }
+  }
+  SMF_CUDA(cudaMalloc(&ctx->idr_normals, sizeof(double) * host.size()));
+  SMF_CUDA(cudaMemcpy(ctx->idr_normals, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
+  ctx->idr_normals_n = (int64_t)host.size();
+  ctx->bytes += sizeof(double) * host.size();
+  return SMF_OK;
+}
+
+// SolverIDR(AdditionalData(s)) with the cheap preconditioner (local_smoothing.cc:1286-1297; deal.II 9.6 semantics in
+// SURVEY App. A.5): s + 1 preconditioner and operator applications per complete step, early exit inside the step
+static int idr(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double *x_p, const double *b_u, const double *b_p,
+               double tol, smf_solve_result *res)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t nu = A.n_u, np = A.n_p, n = nu + np;
+  const int s = std::max(1, prm->idr_s_parameter);
+  const int max_its = prm->n_cheap_stokes_solver_steps;
+  TRY(ensure_krylov(ctx, 3 * s + 4));
+  DotWeights dw(ctx, ctx->block_weights);
+  std::vector<double *> &K = ctx->krylov;
+  double *xb = K[0], *r = K[1], *v = K[2], *uhat = K[3];
+  std::vector<double *> G(K.begin() + 4, K.begin() + 4 + s), U(K.begin() + 4 + s, K.begin() + 4 + 2 * s),
+      Q(K.begin() + 4 + 2 * s, K.begin() + 4 + 3 * s);
+  TRY(vec_copy(ctx, xb, x_u, nu));
+  TRY(vec_copy(ctx, xb + nu, x_p, np));
+  TRY(launch_vmult_stokes(ctx, A, r, r + nu, xb, xb + nu));
+  TRY(vec_sadd(ctx, r, -1.0, 1.0, b_u, nu));
+  TRY(vec_sadd(ctx, r + nu, -1.0, 1.0, b_p, np));
+  double r2;
+  TRY(vec_norm2(ctx, r, n, &r2));
+  double rho = std::sqrt(r2);
+  res->initial_residual = rho;
+  int step = 0, state = rho <= tol ? 1 : 0;
+  if (state == 0) {
+    TRY(idr_shadow_vectors(ctx, s, nu, np));
+    for (int i = 0; i < s; ++i) {
+      TRY(vec_set(ctx, G[i], 0.0, n));
+      TRY(vec_set(ctx, U[i], 0.0, n));
+      if (i == 0) TRY(vec_copy(ctx, Q[0], r, n));
+      else TRY(vec_copy(ctx, Q[i], ctx->idr_normals + (size_t)(i - 1) * n, n));
+      for (int j = 0; j < i; ++j) {      // v = Q_j (Q_j . q) / (q . q); q -= v
+        double a, b;
+        TRY(vec_dot(ctx, Q[j], Q[i], n, &a));
+        TRY(vec_norm2(ctx, Q[i], n, &b));
+        TRY(vec_axpy(ctx, Q[i], -a / b, Q[j], n));
+      }
+      if (i != 0) {
+        double b;
+        TRY(vec_norm2(ctx, Q[i], n, &b));
+        TRY(vec_scale(ctx, Q[i], 1.0 / std::sqrt(b), n));
+      }
+    }
+  }
+  std::vector<double> M((size_t)s * s, 0.0), phi(s + 1), gamma(s), Mk((size_t)s * s), rhs(s);
+  for (int i = 0; i < s; ++i) M[(size_t)i * s + i] = 1.0;
+  double omega = 1.0;
+  auto solve_sub = [&](int k) {      // M(k:s, k:s) gamma = phi(k:s): Gaussian elimination with partial pivoting
+    const int m = s - k;
+    for (int i = 0; i < m; ++i) { rhs[i] = phi[k + i]; for (int j = 0; j < m; ++j) Mk[(size_t)i * m + j] = M[(size_t)(k + i) * s + k + j]; }
+    for (int c = 0; c < m; ++c) {
+      int piv = c;
+      for (int i = c + 1; i < m; ++i) if (std::fabs(Mk[(size_t)i * m + c]) > std::fabs(Mk[(size_t)piv * m + c])) piv = i;
+      if (piv != c) { for (int j = 0; j < m; ++j) std::swap(Mk[(size_t)c * m + j], Mk[(size_t)piv * m + j]); std::swap(rhs[c], rhs[piv]); }
+      for (int i = c + 1; i < m; ++i) {
+        const double f = Mk[(size_t)i * m + c] / Mk[(size_t)c * m + c];
+        for (int j = c; j < m; ++j) Mk[(size_t)i * m + j] -= f * Mk[(size_t)c * m + j];
+        rhs[i] -= f * rhs[c];
+      }
+    }
+    for (int i = m - 1; i >= 0; --i) {
+      double t = rhs[i];
+      for (int j = i + 1; j < m; ++j) t -= Mk[(size_t)i * m + j] * gamma[j];
+      gamma[i] = t / Mk[(size_t)i * m + i];
+    }
+  };
+  while (state == 0) {
+    ++step;
+    {
+      VecBucket vb(ctx, B_ORTHO);
+      TRY(vec_multi_dot(ctx, Q.data(), s, r, n, phi.data(), true));       // phi_i = Q_i . r
+    }
+    bool early_exit = false;
+    for (int k = 0; k < s; ++k) {
+      solve_sub(k);
+      std::vector<double> mg(s - k);
+      for (int j = 0; j < s - k; ++j) mg[j] = -gamma[j];
+      TRY(vec_copy(ctx, v, r, n));
+      TRY(vec_multi_add(ctx, v, G.data() + k, mg.data(), s - k, n));      // v = r - sum gamma_j G_{k+j}
+      TRY(precondition(ctx, uhat, uhat + nu, v, v + nu));
+      if (omega != 1.0) TRY(vec_scale(ctx, uhat, omega, n));
+      TRY(vec_multi_add(ctx, uhat, U.data() + k, gamma.data(), s - k, n));   // uhat = omega P^-1 v + sum gamma_j U_{k+j}
+      TRY(launch_vmult_stokes(ctx, A, G[k], G[k] + nu, uhat, uhat + nu));
+      if (k > 0) {                    // orthogonalise G_k against Q_0..Q_{k-1}, same combination on uhat
+        double alpha;
+        TRY(vec_dot(ctx, Q[0], G[k], n, &alpha));
+        alpha /= M[0];
+        for (int i = 1; i < k; ++i) {
+          TRY(vec_axpy(ctx, G[k], -alpha, G[i - 1], n));
+          TRY(vec_axpy(ctx, uhat, -alpha, U[i - 1], n));
+          TRY(vec_dot(ctx, Q[i], G[k], n, &alpha));
+          alpha /= M[(size_t)i * s + i];
+        }
+        TRY(vec_axpy(ctx, G[k], -alpha, G[k - 1], n));
+        TRY(vec_axpy(ctx, uhat, -alpha, U[k - 1], n));
+      }
+      {                               // column k of M: M(i, k) = Q_i . G_k, i >= k
+        std::vector<double> col(s - k + 1);
+        VecBucket vb(ctx, B_ORTHO);
+        TRY(vec_multi_dot(ctx, Q.data() + k, s - k, G[k], n, col.data(), true));
+        for (int i = k; i < s; ++i) M[(size_t)i * s + k] = col[i - k];
+      }
+      const double beta = phi[k] / M[(size_t)k * s + k];
+      TRY(vec_axpy(ctx, r, -beta, G[k], n));
+      TRY(vec_axpy(ctx, xb, beta, uhat, n));
+      std::swap(U[k], uhat);
+      TRY(vec_norm2(ctx, r, n, &r2));
+      rho = std::sqrt(r2);
+      if (rho <= tol) { state = 1; early_exit = true; break; }
+      if (step >= max_its) { state = 2; early_exit = true; break; }
+      if (k + 1 < s) {
+        for (int i = 0; i <= k; ++i) phi[i] = 0.0;
+        for (int i = k + 1; i < s; ++i) phi[i] -= beta * M[(size_t)i * s + k];
+      }
+    }
+    if (early_exit) break;
+    TRY(precondition(ctx, uhat, uhat + nu, r, r + nu));
+    TRY(launch_vmult_stokes(ctx, A, v, v + nu, uhat, uhat + nu));
+    double vr, vv;
+    TRY(vec_dot(ctx, v, r, n, &vr));
+    TRY(vec_norm2(ctx, v, n, &vv));
+    omega = vr / vv;
+    TRY(vec_axpy(ctx, r, -omega, v, n));
+    TRY(vec_norm2(ctx, r, n, &r2));
+    rho = std::sqrt(r2);
+    TRY(vec_axpy(ctx, xb, omega, uhat, n));
+    if (rho <= tol) state = 1;
+    else if (step >= max_its) state = 2;
+  }
+  TRY(vec_copy(ctx, x_u, xb, nu));
+  TRY(vec_copy(ctx, x_p, xb + nu, np));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  res->iterations = step;
   res->final_residual = rho;
   return state == 1 ? SMF_OK : SMF_NO_CONVERGENCE;
 }
@@ -570,10 +908,11 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
               const double *rhs_u, const double *rhs_p, smf_solve_result *result)
 {
   if (!ctx || !prm || !result) return SMF_ERR_INVALID;
-  if (prm->krylov_method != 0) return ctx->fail(SMF_ERR_UNSUPPORTED, "only GMRES is implemented for the cheap phase");
+  if (prm->krylov_method != 0 && prm->krylov_method != 1) return ctx->fail(SMF_ERR_INVALID, "krylov_method: 0 = GMRES, 1 = IDR(s)");
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   if (A.n_cells == 0 || !A.has_cell_data) return ctx->fail(SMF_ERR_INVALID, "active level not set");
   std::memset(result, 0, sizeof(*result));
+  ctx->err.clear();
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   const double t0 = now_s();
   // the reference rebuilds the smoothers (incl. eigenvalue estimation) at the start of every solve (:768-849)
@@ -600,14 +939,22 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
   { DotWeights dw(ctx, A.ex_p.weights); TRY(vec_norm2(ctx, rhs_p, np, &rp2)); }
   const double tol = prm->linear_solver_tolerance * std::sqrt(ru2 + rp2);
   result->tolerance = tol;
-  ctx->n_A_prec = ctx->n_S_prec = 0;
-  const int rc = gmres(ctx, prm, sol_u, sol_p, rhs_u, rhs_p, tol, result);
+  ctx->n_A_prec = ctx->n_S_prec = ctx->n_A_exp = ctx->n_S_exp = 0;
+  // step 1a: the cheap phase (skipped when no cheap steps are allowed, :1270-1272)
+  int rc = SMF_NO_CONVERGENCE;
+  if (prm->n_cheap_stokes_solver_steps > 0)
+    rc = prm->krylov_method == 0 ? gmres(ctx, prm, sol_u, sol_p, rhs_u, rhs_p, tol, result) : idr(ctx, prm, sol_u, sol_p, rhs_u, rhs_p, tol, result);
+  // step 1b: FGMRES with inner CG solves, starting from the last cheap iterate (:1317-1350)
+  if (rc == SMF_NO_CONVERGENCE && prm->n_expensive_stokes_solver_steps > 0)
+    rc = fgmres(ctx, prm, sol_u, sol_p, rhs_u, rhs_p, tol, result);
   const double t2 = now_s();
   result->n_A_preconditioner = ctx->n_A_prec;
   result->n_S_preconditioner = ctx->n_S_prec;
+  result->n_A_expensive = ctx->n_A_exp;
+  result->n_S_expensive = ctx->n_S_exp;
   result->setup_seconds = t1 - t0;
   result->solve_seconds = t2 - t1;
-  if (rc == SMF_NO_CONVERGENCE) ctx->err = "cheap Stokes solver did not converge (SolverControl::NoConvergence)";
+  if (rc == SMF_NO_CONVERGENCE && ctx->err.empty()) ctx->err = "iterative Stokes solver did not converge (SolverControl::NoConvergence)";
   return rc;
 }
 

@@ -80,7 +80,10 @@ class StokesMatrixFreeHandler:
             "Number of cheap Stokes solver steps": 1000,
             "Maximum number of expensive Stokes solver steps": 1000,
             "GMRES solver restart length": 100,
-            "Krylov method for cheap solver steps": "GMRES",
+            "Krylov method for cheap solver steps": "GMRES",      # or "IDR(s)"
+            "IDR(s) parameter": 2,
+            "Linear solver A block tolerance": 1e-2,
+            "Linear solver S block tolerance": 1e-6,
         }
 
     def name(self):
@@ -248,10 +251,13 @@ class StokesMatrixFreeHandler:
     # ------------------------------------------------------------------
     def _params(self):
         p = self.parameters
-        if p["Krylov method for cheap solver steps"] != "GMRES":
-            raise SmfError(_lib.SMF_ERR_UNSUPPORTED, "only GMRES is implemented for the cheap phase")
+        methods = {"GMRES": 0, "IDR(s)": 1}              # parameters.cc:469-481
+        if p["Krylov method for cheap solver steps"] not in methods:
+            raise SmfError(_lib.SMF_ERR_INVALID, "Krylov method for cheap solver steps: GMRES | IDR(s)")
         return _lib.SolveParams(p["Linear solver tolerance"], p["Number of cheap Stokes solver steps"],
-                                p["GMRES solver restart length"], 0)
+                                p["GMRES solver restart length"], methods[p["Krylov method for cheap solver steps"]],
+                                p["IDR(s) parameter"], p["Maximum number of expensive Stokes solver steps"],
+                                p["Linear solver A block tolerance"], p["Linear solver S block tolerance"])
 
     def solve(self, system_rhs, solution_vector=None, out=None):
         """Host-buffer solve (the reference-facing call): system_rhs = concat(f_u, f_p); solution_vector = initial
@@ -292,6 +298,63 @@ class StokesMatrixFreeHandler:
         self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
         out["converged"] = rc == 0
         return out
+
+    def execute_solver_timings(self, rhs, n_timings=10, out=print):
+        """`Stokes solver parameters/Execute solver timings` (local_smoothing.cc:60-65, :1119-1260): warm-up + n_timings
+        wall-clock timings (synchronised) of stokes_vmult (10 repeats), stokes_preconditioner, A_preconditioner,
+        S_preconditioner (5 repeats), Stokes_solve_cheap_idr and Stokes_solve_cheap_gmres on device vectors, with the same
+        names and the same "prepare" steps (src = dst between timings; the solves restart from the zero guess).
+        rhs = host array [f_u | f_p].  Returns {name: average seconds per call}."""
+        import time
+        self.setup_smoothers()
+        nu = self.n_u
+        r = self.initialize_dof_vector(); d = self.initialize_dof_vector(); s = self.initialize_dof_vector()
+        results = {}
+        lib, c = self.lib, self._check
+
+        def copy(dst, src):
+            for b in (0, 1):
+                c(lib.smf_vec_copy(self.ctx, ptr(dst[b].ptr), ptr(src[b].ptr), ctypes.c_int64(src[b].n)))
+
+        def reset():
+            r[0].from_host(rhs[:nu]); r[1].from_host(rhs[nu:])
+            d[0].zero(); d[1].zero()
+            copy(s, r)
+
+        def time_this(name, repeats, body, prepare):
+            out(f"Timing {name} {n_timings} time(s) and repeat {repeats} time(s) within each timing:")
+            body(); self.synchronize()
+            total = 0.0
+            for _ in range(n_timings):
+                prepare(); self.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(repeats):
+                    body()
+                self.synchronize()
+                dt = (time.perf_counter() - t0) / repeats
+                out(f"\t...{dt:g}")
+                total += dt
+            results[name] = total / n_timings
+            out(f"\taverage wall time of all: {results[name]:g} seconds")
+
+        src_is_dst = lambda: copy(s, d)
+        reset(); time_this("stokes_vmult", 10, lambda: self.stokes_matrix.vmult(d, s), src_is_dst)
+        reset(); time_this("stokes_preconditioner", 1, lambda: self.preconditioner_cheap.vmult(d, s), src_is_dst)
+        reset(); time_this("A_preconditioner", 1, lambda: self.prec_A.vmult(d[0], s[0]), src_is_dst)
+        reset(); time_this("S_preconditioner", 5, lambda: self.prec_Schur.vmult(d[1], s[1]), src_is_dst)
+        saved = dict(self.parameters)
+        self.parameters["Number of cheap Stokes solver steps"] = 1000          # (:1211: always cheap iterations)
+        self.parameters["Maximum number of expensive Stokes solver steps"] = 0
+        zero = lambda: (d[0].zero(), d[1].zero())
+        try:
+            for name, method in (("Stokes_solve_cheap_idr", "IDR(s)"), ("Stokes_solve_cheap_gmres", "GMRES")):
+                self.parameters["Krylov method for cheap solver steps"] = method
+                reset(); time_this(name, 1, lambda: self.solve_device(d, r), zero)
+        finally:
+            self.parameters = saved
+        for v in r + d + s:
+            v.free()
+        return results
 
     @staticmethod
     def _outputs(res):

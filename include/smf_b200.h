@@ -120,6 +120,7 @@ int smf_vec_free(smf_ctx *ctx, double *dev_ptr);
 int smf_vec_h2d(smf_ctx *ctx, double *dev, const double *host, int64_t n);
 int smf_vec_d2h(smf_ctx *ctx, double *host, const double *dev, int64_t n);
 int smf_vec_set(smf_ctx *ctx, double *dev, double value, int64_t n);   /* Vector::operator=(value) */
+int smf_vec_copy(smf_ctx *ctx, double *dst, const double *src, int64_t n);   /* Vector::operator=(const Vector &), device to device */
 int smf_synchronize(smf_ctx *ctx);
 
 /* ---- operators (device pointers) ------------------------------------------------------------ */
@@ -165,7 +166,11 @@ typedef struct {
   double linear_solver_tolerance;        /* "Linear solver tolerance" (parameters.cc:491)              */
   int n_cheap_stokes_solver_steps;       /* "Number of cheap Stokes solver steps" (:515)               */
   int gmres_restart_length;              /* "GMRES solver restart length" (:538)                       */
-  int krylov_method;                     /* 0 = GMRES ("Krylov method for cheap solver steps", :469)   */
+  int krylov_method;                     /* "Krylov method for cheap solver steps" (:469): 0 = GMRES, 1 = IDR(s) */
+  int idr_s_parameter;                   /* "IDR(s) parameter" (:483)                                  */
+  int n_expensive_stokes_solver_steps;   /* "Maximum number of expensive Stokes solver steps" (:531)   */
+  double linear_solver_A_block_tolerance;   /* "Linear solver A block tolerance" (:546)                */
+  double linear_solver_S_block_tolerance;   /* "Linear solver S block tolerance" (:584)                */
 } smf_solve_params;
 
 typedef struct {
@@ -177,9 +182,13 @@ typedef struct {
   double tolerance;                      /* absolute tolerance used (local_smoothing.cc:1024-1025)     */
   double setup_seconds;                  /* smoother set-up + eigenvalue estimation (host wall clock)  */
   double solve_seconds;                  /* Krylov iteration (host wall clock, synchronised)           */
+  int iterations_expensive;              /* FGMRES iterations of the expensive phase ("cheap+expensive") */
+  int n_A_expensive;                     /* inner CG iterations with the A block (expensive phase)     */
+  int n_S_expensive;                     /* inner CG iterations with the pressure mass matrix          */
 } smf_solve_result;
 
-/* The cheap phase of StokesMatrixFreeHandler::solve() (local_smoothing.cc:758-1313) on device vectors:
+/* StokesMatrixFreeHandler::solve() (local_smoothing.cc:758-1446) on device vectors: the cheap phase (GMRES or IDR(s) with
+ * one V-cycle per block) and, if it fails or is skipped, the expensive phase (FGMRES with inner CG solves, :1317-1350).
  * rhs_{u,p}: right-hand side; sol_{u,p}: in = initial guess (pressure already divided by the pressure
  * scaling, constrained entries zero), out = solution.  Returns SMF_OK or SMF_NO_CONVERGENCE. */
 int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,

@@ -331,6 +331,211 @@ def gmres_right(op, prec, b, x0, tol, restart, max_its, history=None):
     return x, its, rho, state == "success"
 
 
+def cg(apply, prec, b, tol, max_its):
+    """deal.II SolverCG from a zero start vector (InverseVelocityBlock / SchurApproximation with do_solve = true,
+    block_stokes_preconditioner.h:108-135, :312-345).  Returns (x, iterations = SolverControl::last_step, converged)."""
+    x = np.zeros_like(b)
+    g = -b                                  # g = A x - b
+    res = np.linalg.norm(g)
+    if res <= tol:
+        return x, 0, True
+    d = None
+    gh = 0.0
+    it = 0
+    while True:
+        it += 1
+        h = prec(g)
+        if it > 1:
+            beta = gh
+            gh = g @ h
+            beta = gh / beta
+            d = -h + beta * d
+        else:
+            d = -h
+            gh = g @ h
+        Ad = apply(d)
+        alpha = gh / (d @ Ad)
+        x = x + alpha * d
+        g = g + alpha * Ad
+        res = np.linalg.norm(g)
+        if res <= tol:
+            return x, it, True
+        if it >= max_its:
+            return x, it, False
+
+
+def fgmres(op, prec, b, x0, tol, restart, max_its, history=None):
+    """deal.II SolverFGMRES(AdditionalData(max_basis_size = restart)) (local_smoothing.cc:1333-1350): flexible GMRES,
+    the preconditioned vectors z_j are stored and x += Z y.  Returns (x, iterations, last_residual, converged)."""
+    x = x0.copy()
+    its = 0
+    state = "iterate"
+    rho = np.nan
+    while state == "iterate":
+        p = b - op(x)
+        rho = np.linalg.norm(p)
+        if history is not None and its == 0:
+            history.append(rho)
+        if rho <= tol:
+            state = "success"; break
+        if its >= max_its:
+            state = "failure"; break
+        V, Z = [p / rho], []
+        gamma = np.zeros(restart + 1); gamma[0] = rho
+        H = np.zeros((restart + 1, restart))
+        ci, si = np.zeros(restart), np.zeros(restart)
+        dim = 0
+        for j in range(restart):
+            if state != "iterate":
+                break
+            its += 1
+            Z.append(prec(V[j]))
+            vv = op(Z[j])
+            dim = j + 1
+            Vm = np.stack(V[:dim], axis=1)
+            h = np.zeros(dim + 1)
+            for _ in range(2):                   # CGS2 (= deal.II's delayed classical Gram-Schmidt numerics)
+                hh = Vm.T @ vv
+                vv = vv - Vm @ hh
+                h[:dim] += hh
+            h[dim] = np.linalg.norm(vv)
+            V.append(vv / h[dim] if h[dim] != 0 else vv)
+            for i in range(j):
+                t = h[i]
+                h[i] = ci[i] * t + si[i] * h[i + 1]
+                h[i + 1] = -si[i] * t + ci[i] * h[i + 1]
+            s = np.hypot(h[j], h[j + 1])
+            ci[j], si[j] = h[j] / s, h[j + 1] / s
+            h[j] = s
+            gamma[j + 1] = -si[j] * gamma[j]
+            gamma[j] *= ci[j]
+            H[:dim, j] = h[:dim]
+            rho = abs(gamma[dim])
+            if history is not None:
+                history.append(rho)
+            if rho <= tol:
+                state = "success"
+            elif its >= max_its:
+                state = "failure"
+        y = sla.solve_triangular(H[:dim, :dim], gamma[:dim])
+        for i in range(dim):
+            x = x + y[i] * Z[i]
+    return x, its, rho, state == "success"
+
+
+def libstdcxx_normal_stream(n):
+    """The first n values of `std::mt19937 rng; std::normal_distribution<double> nd(0, 1); nd(rng)` as libstdc++
+    produces them (default seed 5489; generate_canonical<double, 53> = two 32-bit draws; Marsaglia polar method that
+    returns y*mult first and keeps x*mult for the next call).  deal.II's SolverIDR fills its shadow vectors Q_1..Q_{s-1}
+    with this stream, entry by entry in DoF order, continuing across the vectors."""
+    rs = np.random.RandomState(5489)                      # init_genrand(5489) = std::mt19937's default seeding
+    out = np.empty(n)
+    k = 0
+    buf = np.empty(0, dtype=np.uint64); pos = 0
+
+    def canonical():
+        nonlocal buf, pos
+        if pos + 2 > len(buf):
+            buf = rs.randint(0, 2 ** 32, size=1 << 16, dtype=np.uint64); pos = 0
+        lo, hi = int(buf[pos]), int(buf[pos + 1]); pos += 2
+        r = (lo + hi * 4294967296.0) / 18446744073709551616.0
+        return r if r < 1.0 else np.nextafter(1.0, 0.0)
+    while k < n:
+        while True:
+            xx = 2.0 * canonical() - 1.0
+            yy = 2.0 * canonical() - 1.0
+            r2 = xx * xx + yy * yy
+            if not (r2 > 1.0 or r2 == 0.0):
+                break
+        mult = np.sqrt(-2.0 * np.log(r2) / r2)
+        out[k] = yy * mult; k += 1
+        if k < n:
+            out[k] = xx * mult; k += 1
+    return out
+
+
+def idr(op, prec, b, x0, tol, s, max_its, normals=None, history=None):
+    """deal.II 9.6 SolverIDR(AdditionalData(s)) with (right) preconditioning (local_smoothing.cc:1286-1297), recalled
+    from the public source (SURVEY App. A.5): shadow vectors Q_0 = r_0, Q_i = orthonormalised normal random vectors;
+    per outer step s inner steps (one preconditioner + one operator application each) with an early exit as soon as
+    the residual norm passes the tolerance, then one more application for omega.
+    Returns (x, iterations, last_residual, converged)."""
+    n = len(b)
+    x = x0.copy()
+    r = b - op(x)
+    res = np.linalg.norm(r)
+    if history is not None:
+        history.append(res)
+    step = 0
+    if res <= tol:
+        return x, 0, res, True
+    if normals is None:
+        normals = libstdcxx_normal_stream((s - 1) * n)
+    G = [np.zeros(n) for _ in range(s)]
+    U = [np.zeros(n) for _ in range(s)]
+    Q = []
+    for i in range(s):
+        q = r.copy() if i == 0 else normals[(i - 1) * n:i * n].copy()
+        for j in range(i):
+            v = Q[j] * ((Q[j] @ q) / (q @ q))
+            q = q - v
+        if i != 0:
+            q = q / np.linalg.norm(q)
+        Q.append(q)
+    M = np.eye(s)
+    omega = 1.0
+    while True:
+        step += 1
+        phi = np.array([Q[i] @ r for i in range(s)])
+        for k in range(s):
+            gamma = np.linalg.solve(M[k:, k:], phi[k:])
+            v = r.copy()
+            for j, i in enumerate(range(k, s)):
+                v -= gamma[j] * G[i]
+            uhat = prec(v) * omega
+            for j, i in enumerate(range(k, s)):
+                uhat += gamma[j] * U[i]
+            ghat = op(uhat)
+            if k > 0:
+                alpha = (Q[0] @ ghat) / M[0, 0]
+                for i in range(1, k):
+                    ghat -= alpha * G[i - 1]
+                    uhat -= alpha * U[i - 1]
+                    alpha = (Q[i] @ ghat) / M[i, i]
+                ghat -= alpha * G[k - 1]
+                uhat -= alpha * U[k - 1]
+            G[k] = ghat
+            M[k, k] = G[k] @ Q[k]
+            beta = phi[k] / M[k, k]
+            r = r - beta * G[k]
+            x = x + beta * uhat
+            U[k] = uhat
+            res = np.linalg.norm(r)
+            if history is not None:
+                history.append(res)
+            if res <= tol:
+                return x, step, res, True
+            if step >= max_its:
+                return x, step, res, False
+            if k + 1 < s:
+                phi[:k + 1] = 0.0
+                for i in range(k + 1, s):
+                    M[i, k] = Q[i] @ G[k]
+                    phi[i] -= beta * M[i, k]
+        uhat = prec(r)
+        v = op(uhat)
+        omega = (v @ r) / (v @ v)
+        r = r - omega * v
+        res = np.linalg.norm(r)
+        x = x + omega * uhat
+        if history is not None:
+            history.append(res)
+        if res <= tol:
+            return x, step, res, True
+        if step >= max_its:
+            return x, step, res, False
+
+
 # ---------------------------------------------------------------------------
 class BlockGMGStokes:
     """The cheap-phase solver of StokesMatrixFreeHandlerLocalSmoothingImplementation::solve()."""
@@ -354,7 +559,29 @@ class BlockGMGStokes:
         zu = self.mg_A.vmult(t)
         return np.concatenate([zu, zp])
 
-    def solve(self, rhs, x0=None, tol_rel=1e-6, restart=100, max_its=200, history=None):
+    def prec_expensive(self, r, a_tol=1e-2, s_tol=1e-6):
+        """BlockSchurPreconditioner with do_solve_A = do_solve_Schur = true: inner CG solves preconditioned by the
+        V-cycles (block_stokes_preconditioner.h:108-135: 10000 its, |src| * A-block tolerance; :312-345: 100 its,
+        |src| * S-block tolerance, skipped when |src| <= 1e-50)."""
+        rp = r[self.n_u:]
+        zp = np.zeros(self.n_p)
+        if np.linalg.norm(rp) > 1e-50:
+            zp, its, ok = cg(self.be.M_active, self.mg_S.vmult, rp, np.linalg.norm(rp) * s_tol, 100)
+            self.n_S_cg += its
+            if not ok:
+                raise RuntimeError("iterative (bottom right) solver did not converge")
+        zp = -zp
+        t = r[:self.n_u] - self.be.BT(zp)
+        zu, its, ok = cg(self.be.A_active, self.mg_A.vmult, t, np.linalg.norm(t) * a_tol, 10000)
+        self.n_A_cg += its
+        if not ok:
+            raise RuntimeError("iterative (top left) solver did not converge")
+        return np.concatenate([zu, zp])
+
+    def solve(self, rhs, x0=None, tol_rel=1e-6, restart=100, max_its=200, history=None, krylov="gmres", idr_s=2,
+              n_expensive=0, a_tol=1e-2, s_tol=1e-6):
+        """Cheap phase (GMRES or IDR(s), at most max_its steps; 0 skips it, local_smoothing.cc:1270-1272), then on
+        failure the expensive phase: FGMRES(restart) with inner CG solves, at most n_expensive steps (:1317-1350)."""
         if x0 is None:
             x0 = np.zeros_like(rhs)
         # tolerance: local_smoothing.cc:1016-1025 (velocity part of the guess zeroed)
@@ -364,5 +591,14 @@ class BlockGMGStokes:
         rp = np.linalg.norm(rhs[self.n_u:])
         tol = tol_rel * np.sqrt(ru * ru + rp * rp)
         self.n_prec = 0
-        x, its, res, ok = gmres_right(self.op, self.prec, rhs, x0, tol, restart, max_its, history)
-        return dict(x=x, iterations=its, residual=res, converged=ok, tolerance=tol, n_prec=self.n_prec)
+        self.n_A_cg = self.n_S_cg = 0
+        its, its_exp, ok, x, res = 0, 0, False, x0, np.nan
+        if max_its > 0:
+            if krylov == "gmres":
+                x, its, res, ok = gmres_right(self.op, self.prec, rhs, x0, tol, restart, max_its, history)
+            else:
+                x, its, res, ok = idr(self.op, self.prec, rhs, x0, tol, idr_s, max_its, history=history)
+        if not ok and n_expensive > 0:
+            x, its_exp, res, ok = fgmres(self.op, lambda v: self.prec_expensive(v, a_tol, s_tol), rhs, x, tol, restart, n_expensive, history)
+        return dict(x=x, iterations=its, iterations_expensive=its_exp, residual=res, converged=ok, tolerance=tol, n_prec=self.n_prec,
+                    n_A_cg=self.n_A_cg, n_S_cg=self.n_S_cg)

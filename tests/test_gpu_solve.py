@@ -129,8 +129,96 @@ def test_vcycles_and_preconditioner_match_oracle():
 def test_no_convergence_is_a_status():
     hier, h, eta_q, rhs, ps = _gpu_problem(3, 2, "zero", benchmarks.nsinker_problem, "none", 1e-6, n_sinkers=4)
     h.parameters["Number of cheap Stokes solver steps"] = 5
+    h.parameters["Maximum number of expensive Stokes solver steps"] = 0
     sol, out = h.solve(rhs)
-    assert not out["converged"] and out["iterations"] == 5
+    assert not out["converged"] and out["iterations"] == 5 and out["iterations_expensive"] == 0
+    h.close()
+
+
+def test_idr_golden_r2():
+    """tests/nsinker_gmg_idr: R=2, harmonic average only viscosity, IDR(2): "9+0 iterations", 25 preconditioner applications.
+    The shadow vectors come from the same std::mt19937 / std::normal_distribution stream as deal.II's."""
+    avg = "harmonic average only viscosity"
+    hier, h, eta_q, rhs, ps = _gpu_problem(3, 2, "zero", benchmarks.nsinker_problem, avg, 1e-6, n_sinkers=4)
+    h.parameters["Krylov method for cheap solver steps"] = "IDR(s)"
+    h.parameters["IDR(s) parameter"] = 2
+    sol, out = h.solve(rhs)
+    g = golden("nsinker_gmg_idr")
+    assert out["converged"]
+    assert out["iterations"] == g["stokes_iterations_cheap_expensive"][0][0] == 9
+    assert out["n_A_preconditioner"] == g["A_preconditioner_applications"][0] == 25
+    assert out["n_S_preconditioner"] == g["schur_preconditioner_applications"][0] == 25
+    ohier = omesh.Hierarchy(3, 2)
+    ob, *_ = oracle_backend(ohier, eta_q, avg, ps, "zero")
+    oout = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-6, krylov="idr", idr_s=2, max_its=1000)
+    assert oout["iterations"] == out["iterations"] and oout["n_prec"] == 25
+    nu = hier.active.n_u
+    assert rel(sol[:nu], oout["x"][:nu]) < 1e-8
+    pg, _ = postprocess.normalize_pressure_volume(ohier.active, sol[nu:])
+    po, _ = postprocess.normalize_pressure_volume(ohier.active, oout["x"][nu:] * ps)
+    assert rel(pg, po) < 1e-8
+    # a second solve re-uses the cached shadow vectors and must repeat the first one exactly
+    sol2, out2 = h.solve(rhs)
+    assert out2["iterations"] == 9 and np.array_equal(sol, sol2)
+    # IDR(1) and IDR(4) against the oracle
+    for s_par in (1, 4):
+        h.parameters["IDR(s) parameter"] = s_par
+        sol3, out3 = h.solve(rhs)
+        o3 = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-6, krylov="idr", idr_s=s_par, max_its=1000)
+        assert out3["converged"] and out3["iterations"] == o3["iterations"] and out3["n_A_preconditioner"] == o3["n_prec"]
+    h.close()
+
+
+def test_idr_performance_golden_r6():
+    """tests/performance/performance_nsinker_gmg_idr: R=6 (6,440,067+274,625 DoFs, 7 levels), harmonic average only viscosity,
+    IDR(2): "12+0 iterations", 34 preconditioner applications -- the largest mesh the reference pins, run on the GPU only."""
+    avg = "harmonic average only viscosity"
+    hier, h, eta_q, rhs, ps = _gpu_problem(3, 6, "zero", benchmarks.nsinker_problem, avg, 1e-6, n_sinkers=4)
+    g = golden("performance_nsinker_gmg_idr")
+    assert [hier.active.n_u, hier.active.n_p] == g["dofs_u_p"][0] == [6440067, 274625]
+    assert abs(h.minimum_viscosity - 0.01) < 5e-7 and abs(h.maximum_viscosity / 100.0 - 1) < 5e-6
+    h.parameters["Krylov method for cheap solver steps"] = "IDR(s)"
+    sol, out = h.solve(rhs)
+    assert out["converged"]
+    assert abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 1          # 12 (+-1: BASELINE.json)
+    assert abs(out["n_A_preconditioner"] - g["A_preconditioner_applications"][0]) <= 3          # 34
+    h.close()
+
+
+def test_no_cheap_gmg_golden():
+    """tests/no_cheap_gmg: SolCx R=4, `harmonic average` (viscosity and density), 0 cheap steps: "0+12 iterations" of FGMRES
+    with inner CG solves, errors 1.211886e-05, 1.081996e-01, 1.694600e-05, 1.086264e-01."""
+    avg = "harmonic average"
+    hier, h, eta_q, rhs, ps = _gpu_problem(2, 4, "tangential", benchmarks.solcx_problem, avg, 1e-7)
+    h.parameters["Number of cheap Stokes solver steps"] = 0
+    sol, out = h.solve(rhs)
+    g = golden("no_cheap_gmg")
+    assert out["converged"]
+    assert [out["iterations"], out["iterations_expensive"]] == g["stokes_iterations_cheap_expensive"][0] == [0, 12]
+    ohier = omesh.Hierarchy(2, 4)
+    ob, *_ = oracle_backend(ohier, eta_q, avg, ps, "tangential")
+    oout = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-7, restart=100, max_its=0, n_expensive=1000)
+    assert oout["iterations_expensive"] == 12
+    assert (out["n_A_expensive"], out["n_S_expensive"]) == (oout["n_A_cg"], oout["n_S_cg"])
+    act = ohier.active
+    assert rel(sol[:act.n_u], oout["x"][:act.n_u]) < 1e-8
+    p, _ = postprocess.normalize_pressure_surface(act, sol[act.n_u:])
+    err = postprocess.solcx_errors(act, sol[:act.n_u], p)
+    assert [f"{e:.6e}" for e in err] == g["errors_uL1_pL1_uL2_pL2"][0]
+    h.close()
+
+
+def test_cheap_failure_falls_back_to_expensive():
+    """local_smoothing.cc:1317-1350: when the cheap phase runs out of steps, FGMRES continues from its last iterate."""
+    hier, h, eta_q, rhs, ps = _gpu_problem(3, 2, "zero", benchmarks.nsinker_problem, "none", 1e-6, n_sinkers=4)
+    h.parameters["Number of cheap Stokes solver steps"] = 5
+    sol, out = h.solve(rhs)
+    assert out["converged"] and out["iterations"] == 5 and out["iterations_expensive"] > 0
+    ohier, ob, s, oout = _oracle_solve(3, 2, "zero", eta_q, "none", ps, rhs, 1e-6)
+    o2 = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-6, restart=100, max_its=5, n_expensive=1000)
+    assert abs(out["iterations_expensive"] - o2["iterations_expensive"]) <= 1
+    nu = hier.active.n_u
+    assert rel(sol[:nu], oout["x"][:nu]) < 1e-5           # both solved to the same relative tolerance 1e-6
     h.close()
 
 

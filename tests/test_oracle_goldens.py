@@ -78,6 +78,65 @@ def test_solcx_goldens(R, avg):
         assert ", ".join(f"{v:.6e}" for v in e) == errs
 
 
+def test_idr_golden():
+    """tests/nsinker_gmg_idr (R=2, 4 sinkers, harmonic average only viscosity, IDR(2)): "9+0 iterations", 25 applications of
+    both preconditioners (8 complete IDR(2) steps x 3 + the early exit after the first inner step of the ninth)."""
+    g = golden("nsinker_gmg_idr")
+    hier = mesh.Hierarchy(3, 2)
+    act = hier.active
+    eta_q, rho_q = coeff.nsinker(act.quadrature_points(), 4, 1e4)
+    active, levels, emin, emax = coeff.viscosity_tables(hier, eta_q, "harmonic")
+    assert [float(f"{emin:.6g}"), float(f"{emax:.6g}")] == g["viscosity_range"][0]
+    be = solver.AssembledBackend(hier, active, levels, 1.0, "zero")
+    f = assembled.rhs_gravity(act, rho_q, np.array([0, 0, -1.0]))
+    f[act.constrained_u("zero")] = 0
+    rhs = np.concatenate([f, np.zeros(act.n_p)])
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-6, krylov="idr", idr_s=2, max_its=1000)
+    assert out["converged"]
+    assert out["iterations"] == g["stokes_iterations_cheap_expensive"][0][0] == 9
+    assert out["n_prec"] == g["A_preconditioner_applications"][0] == g["schur_preconditioner_applications"][0] == 25
+
+
+def test_libstdcxx_normal_stream():
+    """First values of std::mt19937 + std::normal_distribution<double> (libstdc++), the stream deal.II's SolverIDR draws its
+    shadow vectors from; compared with a C++ program when g++ is available, else with recorded values."""
+    import shutil, subprocess, tempfile
+    got = solver.libstdcxx_normal_stream(7)
+    recorded = None
+    if shutil.which("g++"):
+        with tempfile.TemporaryDirectory() as d:
+            src = os.path.join(d, "n.cc")
+            open(src, "w").write('#include <random>\n#include <cstdio>\nint main(){std::mt19937 r;std::normal_distribution<double> n(0.0,1.0);'
+                                 'for(int i=0;i<7;++i)std::printf("%.17g\\n",n(r));}\n')
+            subprocess.check_call(["g++", "-O1", "-o", os.path.join(d, "n"), src])
+            recorded = np.array([float(x) for x in subprocess.check_output([os.path.join(d, "n")]).split()])
+        assert np.array_equal(got, recorded)
+    assert got[0] == 0.13452965847232812
+
+
+def test_no_cheap_gmg_golden():
+    """tests/no_cheap_gmg (SolCx R=4, `harmonic average` of viscosity AND density, 0 cheap steps): the expensive phase
+    (FGMRES + inner CG solves) takes "0+12 iterations" and the four SolCx errors match digit for digit."""
+    g = golden("no_cheap_gmg")
+    hier = mesh.Hierarchy(2, 4)
+    act = hier.active
+    eta_q, rho_q = coeff.solcx(act.quadrature_points())
+    rho_q = coeff.average(rho_q, "harmonic")
+    active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, "harmonic")
+    ps = coeff.pressure_scaling_box(hier, lambda x: coeff.solcx(x)[0])
+    be = solver.AssembledBackend(hier, active, levels, ps, "tangential")
+    f = assembled.rhs_gravity(act, rho_q, np.array([0, -1.0]))
+    f[be.cu[-1]] = 0
+    rhs = np.concatenate([f, np.zeros(act.n_p)])
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-7, restart=100, max_its=0, n_expensive=1000)
+    assert out["converged"]
+    assert [out["iterations"], out["iterations_expensive"]] == g["stokes_iterations_cheap_expensive"][0] == [0, 12]
+    if HAVE_SOLCX_REF:
+        p, _ = postprocess.normalize_pressure_surface(act, out["x"][act.n_u:] * ps)
+        e = postprocess.solcx_errors(act, out["x"][:act.n_u], p)
+        assert [f"{v:.6e}" for v in e] == g["errors_uL1_pL1_uL2_pL2"][0]
+
+
 @pytest.mark.parametrize("dim,R,bc", [(2, 3, "tangential"), (3, 2, "zero"), (3, 2, "tangential")])
 def test_matrix_free_c_equals_assembled(dim, R, bc):
     rng = np.random.default_rng(0)
