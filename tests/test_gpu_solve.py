@@ -218,7 +218,8 @@ def test_cheap_failure_falls_back_to_expensive():
     o2 = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-6, restart=100, max_its=5, n_expensive=1000)
     assert abs(out["iterations_expensive"] - o2["iterations_expensive"]) <= 1
     nu = hier.active.n_u
-    assert rel(sol[:nu], oout["x"][:nu]) < 1e-5           # both solved to the same relative tolerance 1e-6
+    assert rel(sol[:nu], o2["x"][:nu]) < 1e-6             # same algorithm: GMRES(5 steps) then FGMRES + CG
+    assert rel(sol[:nu], oout["x"][:nu]) < 1e-2           # different Krylov path to the same tolerance (viscosity ratio 1e4)
     h.close()
 
 
