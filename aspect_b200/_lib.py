@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsmf_b200.so")
 SMF_OK, SMF_ERR_INVALID, SMF_ERR_CUDA, SMF_ERR_UNSUPPORTED, SMF_NO_CONVERGENCE = 0, 1, 2, 3, 4
 SMF_ACTIVE = -1
 SMF_OPT_STRUCTURED_BRICKS, SMF_OPT_CUDA_GRAPHS, SMF_OPT_ORTHO_SINGLE_PASS, SMF_OPT_PIPELINED_KERNEL, SMF_OPT_MAX_GRID_BLOCKS = 0, 1, 2, 3, 4
+SMF_OPT_P2P_EXCHANGE = 5
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -61,7 +62,7 @@ EXPORTS = [
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",
     "smf_solve_host", "smf_kernel_launches", "smf_device_bytes", "smf_profile_enable", "smf_profile_read",
-    "smf_exchange_count", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
+    "smf_exchange_count", "smf_exchange_transport", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
 ]
 
 _lib = None

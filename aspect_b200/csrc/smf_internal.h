@@ -79,6 +79,8 @@ struct ExchangeDev {
   uint32_t *if_idx = nullptr; int *if_ptr = nullptr, *if_src = nullptr;   // rank-ordered accumulation tables
   double *weights = nullptr;                  // [n_dofs] 1 / (ranks sharing the DoF); nullptr on one rank
   int64_t *gid = nullptr; double gid_mean = 0.0;     // global DoF numbers (Chebyshev start vector)
+  // fused peer-memory transport (comm.cu): neighbour table, {epoch, counters}, this rank's inbox (2 parity buffers)
+  void *p2p_tab = nullptr, *p2p_state = nullptr; double *p2p_inbox = nullptr;
 };
 
 struct LevelDev {
@@ -173,6 +175,8 @@ struct smf_ctx {
   // distributed run (comm.cu): one subdomain per rank
   int rank = 0, world = 1;
   void *comm = nullptr;                               // ncclComm_t
+  void *p2p = nullptr;                                // P2PState (comm.cu): inbox arena + mapped peer arenas; nullptr = NCCL transport
+  int use_p2p = 1;                                    // fused peer-memory halo exchange when the IPC mapping is available
   int64_t exchanges = 0;
   const double *dot_weights = nullptr;                // weights the inner products use right now (nullptr: none)
   double *block_weights = nullptr;                    // [n_u + n_p] of the active level

@@ -71,6 +71,7 @@ class StokesMatrixFreeHandler:
         self.use_cuda_graphs = True
         self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
+        self.p2p_exchange = True                 # >1 rank: halo exchange as one kernel over NVLink peer memory (False: NCCL send/recv)
         self.gram_reorthogonalization = True     # GMRES: CGS2 in one sweep over the basis (False: two sweeps)
         # Chebyshev eigenvalue start vector from partition-independent global DoF numbers (always on for >1 rank)
         self.global_start_vector = False
@@ -132,6 +133,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_ORTHO_SINGLE_PASS, int(self.gram_reorthogonalization)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_PIPELINED_KERNEL, int(self.use_pipelined_kernel)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
         self._keep = []
         self.rank, self.world = getattr(hierarchy, "rank", 0), getattr(hierarchy, "world", 1)
         self._comm_init()
@@ -372,6 +374,9 @@ class StokesMatrixFreeHandler:
         cnt = np.zeros(len(self.PROFILE_BUCKETS), dtype=np.int64)
         self._check(self.lib.smf_profile_read(self.ctx, ptr(ms), ptr(cnt)))
         return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_BUCKETS, ms, cnt)}
+
+    def exchange_transport(self):
+        return {0: "single rank", 1: "nccl send/recv", 2: "fused peer-memory kernel (CUDA IPC over NVLink)"}[int(self.lib.smf_exchange_transport(self.ctx))]
 
     def exchange_count(self):
         return int(self.lib.smf_exchange_count(self.ctx))

@@ -349,7 +349,7 @@ def main():
                   "note": "stokes_gdofs includes zeroing dst (StokesOperator::vmult); *_kernel_* is the cell kernel alone"},
         "time_split_ms": {k: round(v[0], 3) for k, v in split.items()},
         "launch_split": {k: v[1] for k, v in split.items()},
-        "clocks": clock_info, "host_setup_s": setup_s, "halo_exchanges_per_solve": int(exchanges),
+        "clocks": clock_info, "host_setup_s": setup_s, "halo_exchanges_per_solve": int(exchanges), "halo_transport": h.exchange_transport(),
     }
     h.close()
     # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------

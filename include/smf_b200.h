@@ -51,6 +51,7 @@ const char *smf_last_error(const smf_ctx *ctx);
 #define SMF_OPT_CUDA_GRAPHS 1         /* replay the coarse-level part of the V-cycles from CUDA graphs */
 #define SMF_OPT_MAX_GRID_BLOCKS 4      /* > 0: cap on the grid of the persistent kernels (testing aid; default 0 = one resident wave) */
 #define SMF_OPT_PIPELINED_KERNEL 3     /* structured levels: persistent, cp.async-pipelined velocity kernel (default 1) */
+#define SMF_OPT_P2P_EXCHANGE 5        /* halo exchange as one kernel over NVLink peer memory (default 1); 0 = pack + NCCL send/recv + accumulate */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
@@ -211,6 +212,7 @@ int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out);
 int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this context so far */
 int64_t smf_device_bytes(const smf_ctx *ctx);        /* get_*_memory_consumption() analogue      */
 int64_t smf_exchange_count(const smf_ctx *ctx);      /* halo exchanges performed by this context so far */
+int smf_exchange_transport(const smf_ctx *ctx);      /* 0 = single rank, 1 = NCCL send/recv, 2 = fused peer-memory kernel (CUDA IPC over NVLink) */
 
 #ifdef __cplusplus
 }

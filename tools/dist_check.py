@@ -68,6 +68,7 @@ def main():
     rep = REPS[world]
     hier, h, rhs = setup(R, rep, rank, world, avg)
     gu, gp, yu, yp, su, sp, out = run(h, hier, rhs)
+    transport = h.exchange_transport()
     h.close()
     ref = [None]
     if rank == 0:
@@ -96,7 +97,7 @@ def main():
                     bitwise = False
                 table[k] = v
         ok = ok and bitwise
-        print(f"dist_check world={world} R={R}: operator rel err {e_op:.2e}, iterations {out['iterations']} (1 GPU: {out1['iterations']}), "
+        print(f"dist_check world={world} R={R} transport={transport!r}: operator rel err {e_op:.2e}, iterations {out['iterations']} (1 GPU: {out1['iterations']}), "
               f"velocity rel diff {e_sol_u:.2e}, pressure rel diff {e_sol_p:.2e}, shared copies bitwise equal: {bitwise} -> {'OK' if ok else 'FAIL'}",
               flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
