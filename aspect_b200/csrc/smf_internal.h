@@ -185,6 +185,7 @@ struct smf_ctx {
   void *graph_A = nullptr, *graph_S = nullptr;        // cudaGraphExec_t
   bool graph_A_stale = true, graph_S_stale = true;    // smoother coefficients changed since the capture
   int64_t graph_A_launches = 0, graph_S_launches = 0; // kernels inside one replay
+  int64_t graph_A_exchanges = 0, graph_S_exchanges = 0;   // halo exchanges inside one replay
   int graph_level = -1;                               // finest level inside the graphs (-1: graphs unused)
   int use_graphs = 1;
   int ortho_single_pass = 1;                          // GMRES: re-orthogonalise through the Gram matrix (1) or with a second pass over the basis (0)

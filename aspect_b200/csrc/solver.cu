@@ -208,16 +208,19 @@ static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
   void *&exec = S.velocity ? ctx->graph_A : ctx->graph_S;
   bool &stale = S.velocity ? ctx->graph_A_stale : ctx->graph_S_stale;
   int64_t &n_launch = S.velocity ? ctx->graph_A_launches : ctx->graph_S_launches;
+  int64_t &n_exch = S.velocity ? ctx->graph_A_exchanges : ctx->graph_S_exchanges;
   if (stale) {
     cudaGraph_t graph = nullptr;
     SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
-    const int64_t l0 = ctx->launches;
+    const int64_t l0 = ctx->launches, x0 = ctx->exchanges;
     const int rc = level_v_step(ctx, S, l);
     const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return ctx->fail(SMF_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
     n_launch = ctx->launches - l0;
     ctx->launches = l0;
+    n_exch = ctx->exchanges - x0;
+    ctx->exchanges = x0;
     bool updated = false;
     if (exec) {
       cudaGraphExecUpdateResultInfo info;
@@ -235,6 +238,7 @@ static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
   }
   SMF_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, ctx->stream));
   ctx->launches += n_launch;
+  ctx->exchanges += n_exch;
   return SMF_OK;
 }
 
