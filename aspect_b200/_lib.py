@@ -40,6 +40,14 @@ class CellData(ctypes.Structure):
     _fields_ = [("viscosity", c_vp), ("n_per_cell", c_int), ("pressure_scaling", c_dbl), ("is_compressible", c_int)]
 
 
+class NewtonData(ctypes.Structure):
+    _fields_ = [("enable_newton_derivatives", c_int), ("symmetrize_newton_system", c_int), ("average_newton_factors", c_int),
+                ("enable_prescribed_dilation", c_int), ("apply_stabilization_free_surface_faces", c_int),
+                ("strain_rate_table", c_vp), ("newton_factor_wrt_strain_rate_table", c_vp),
+                ("newton_factor_wrt_pressure_table", c_vp), ("dilation_lhs_term_table", c_vp),
+                ("dilation_derivative_wrt_strain_rate_table", c_vp), ("dilation_derivative_wrt_pressure_table", c_vp)]
+
+
 class SolveParams(ctypes.Structure):
     _fields_ = [("linear_solver_tolerance", c_dbl), ("n_cheap_stokes_solver_steps", c_int),
                 ("gmres_restart_length", c_int), ("krylov_method", c_int), ("idr_s_parameter", c_int),
@@ -57,7 +65,7 @@ class SolveResult(ctypes.Structure):
 # every symbol include/smf_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "smf_create", "smf_destroy", "smf_last_error", "smf_set_option", "smf_set_stream", "smf_set_level", "smf_set_transfer",
-    "smf_set_copy_indices", "smf_set_cell_data", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
+    "smf_set_copy_indices", "smf_set_cell_data", "smf_set_newton_data", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
     "smf_synchronize", "smf_vmult_stokes", "smf_vmult_A", "smf_vmult_BT", "smf_vmult_mass", "smf_vmult_stokes_host", "smf_correct_stokes_rhs",
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",

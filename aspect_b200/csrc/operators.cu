@@ -1466,11 +1466,232 @@ template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &
   return launch_velocity_t<DIM, MODE, false, false>(ctx, L, P);
 }
 
+
+// ---- general cell operation: every branch of StokesOperator::local_apply ---------------------------------------
+// Compressible / prescribed-dilation / Newton-derivative terms (matrix_free_operators.cc:400-446, :464-538) and the
+// deviatoric A block (:999-1005) couple all components of the symmetric gradient at a quadrature point, which the
+// component-per-warp kernels above do not exchange.  This kernel is the straightforward restatement -- one thread per
+// cell, the cell's values in local memory, basis functions evaluated on the fly -- used only when one of those
+// flags is set (no BASELINE configuration sets them); it is correct for every flag combination and not tuned.
+struct GeneralParams {
+  int64_t n_cells;
+  const uint32_t *cell_nodes_u, *cell_nodes_p;
+  const double *src_u, *src_p;
+  double *dst_u, *dst_p;
+  const double *eta; int n_eta;
+  double ih[3], vol, ps;
+  int mode;                 // 0 = A block, 1 = Stokes operator
+  int compressible, newton, symmetrize, average, dilation, plain;
+  const double *eps, *deta, *detadp, *dil_lhs, *ddil, *ddildp;     // [cell][q][n_sym] / [cell][q]
+};
+
+template <int DIM> __device__ __forceinline__ double sym_contract(const double *t, const double (&g)[DIM][DIM])
+{
+  // t: unrolled symmetric tensor (00, 11, (22,) 01, (02, 12)); g: symmetric DIM x DIM
+  if (DIM == 2) return t[0] * g[0][0] + t[1] * g[1][1] + 2.0 * t[2] * g[0][1];
+  return t[0] * g[0][0] + t[1] * g[1][1] + t[2] * g[2][2] + 2.0 * (t[3] * g[0][1] + t[4] * g[0][2] + t[5] * g[1][2]);
+}
+template <int DIM> __device__ __forceinline__ double sym_entry(const double *t, int i, int j)
+{
+  if (i == j) return t[i];
+  if (DIM == 2) return t[2];
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  return lo == 0 ? (hi == 1 ? t[3] : t[4]) : t[5];
+}
+template <int DIM> __device__ __forceinline__ double sym_trace(const double *t) { return DIM == 2 ? t[0] + t[1] : t[0] + t[1] + t[2]; }
+
+template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(const GeneralParams P)
+{
+  constexpr int NN = nn<DIM>(), NP = np<DIM>(), NS = DIM * (DIM + 1) / 2;
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= P.n_cells) return;
+  double u[DIM][NN], T[DIM][NN], pn[NP], Tp[NP];
+  for (int i = 0; i < NN; ++i) {
+    const uint32_t e = P.cell_nodes_u[cell * NN + i];
+    const uint32_t idx = e & NODE_IDX_MASK;
+    for (int c = 0; c < DIM; ++c) {
+      const bool cons = ((e >> (NODE_FLAG_SHIFT + c)) & 1u) && !P.plain;
+      u[c][i] = cons ? 0.0 : P.src_u[idx + c];
+      T[c][i] = 0.0;
+    }
+  }
+  for (int a = 0; a < NP; ++a) {
+    pn[a] = 0.0; Tp[a] = 0.0;
+    if (P.mode == 1) {
+      const uint32_t e = P.cell_nodes_p[cell * NP + a];
+      pn[a] = ((e >> 31) && !P.plain) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
+    }
+  }
+  const bool deviatoric = P.compressible || P.dilation;
+  const bool newton = P.mode == 1 && P.newton;
+  // symmetric gradient, divergence and pressure at quadrature point q
+  auto evaluate = [&](int q, double (&sg)[DIM][DIM], double &div, double &valp) {
+    int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
+    double g[DIM][DIM];
+    for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) g[c][d] = 0.0;
+    for (int i = 0; i < NN; ++i) {
+      int id[3] = {i % 3, (i / 3) % 3, DIM == 3 ? i / 9 : 0};
+      double dphi[DIM];
+      for (int d = 0; d < DIM; ++d) {
+        double v = P.ih[d];
+        for (int e = 0; e < DIM; ++e) v *= (e == d) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
+        dphi[d] = v;
+      }
+      for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) g[c][d] = fma(u[c][i], dphi[d], g[c][d]);
+    }
+    div = 0.0;
+    for (int c = 0; c < DIM; ++c) { div += g[c][c]; for (int d = 0; d < DIM; ++d) sg[c][d] = 0.5 * (g[c][d] + g[d][c]); }
+    valp = 0.0;
+    if (P.mode == 1)
+      for (int a = 0; a < NP; ++a) {
+        int ad[3] = {a % 2, (a / 2) % 2, DIM == 3 ? a / 4 : 0};
+        double v = pn[a];
+        for (int d = 0; d < DIM; ++d) v *= q1v(qd[d], ad[d]);
+        valp += v;
+      }
+  };
+  // averaged Newton factors (:400-446)
+  double deta_deps_times_sym_grad_u = 0.0, deta_dp_times_p = 0.0, eps_times_sym_grad_u_JxW = 0.0, theta_times_div_u_JxW = 0.0;
+  if (newton && P.average)
+    for (int q = 0; q < NN; ++q) {
+      double sg[DIM][DIM], div, valp;
+      evaluate(q, sg, div, valp);
+      const int64_t tq = cell * NN + q;
+      deta_deps_times_sym_grad_u += sym_contract<DIM>(P.deta + tq * NS, sg);
+      deta_dp_times_p += P.detadp[tq] * valp;
+      if (P.symmetrize) {
+        const double JxW = qweight<DIM>(q) * P.vol;
+        eps_times_sym_grad_u_JxW += sym_contract<DIM>(P.eps + tq * NS, sg) * JxW;
+        if (deviatoric) theta_times_div_u_JxW += sym_trace<DIM>(P.eps + tq * NS) * div * JxW;
+      }
+    }
+  for (int q = 0; q < NN; ++q) {
+    double sg[DIM][DIM], div_u, val_p;
+    evaluate(q, sg, div_u, val_p);
+    const int64_t tq = cell * NN + q;
+    const double JxW = qweight<DIM>(q) * P.vol;
+    const double viscosity_x_2 = 2.0 * P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)];
+    double pressure_terms = -P.ps * div_u;
+    double vt[DIM][DIM];
+    for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) vt[c][d] = viscosity_x_2 * sg[c][d];
+    if (P.mode == 1) {
+      if (P.dilation) pressure_terms -= P.ps * P.ps * P.dil_lhs[tq] * val_p;
+      for (int d = 0; d < DIM; ++d) vt[d][d] -= P.ps * val_p;
+    }
+    if (deviatoric) for (int d = 0; d < DIM; ++d) vt[d][d] -= viscosity_x_2 / 3.0 * div_u;
+    if (newton) {
+      const double *eps = P.eps + tq * NS, *deta = P.deta + tq * NS;
+      double eps_times_sym_grad_u = 0.0, theta_times_div_u = 0.0;
+      if (P.average) {
+        if (P.symmetrize) eps_times_sym_grad_u = eps_times_sym_grad_u_JxW / JxW;
+      } else {
+        deta_deps_times_sym_grad_u = sym_contract<DIM>(deta, sg);
+        deta_dp_times_p = P.detadp[tq] * val_p;
+        if (P.symmetrize) eps_times_sym_grad_u = sym_contract<DIM>(eps, sg);
+      }
+      for (int c = 0; c < DIM; ++c)
+        for (int d = 0; d < DIM; ++d) {
+          const double e_cd = sym_entry<DIM>(eps, c, d), n_cd = sym_entry<DIM>(deta, c, d);
+          vt[c][d] += (P.symmetrize ? e_cd * deta_deps_times_sym_grad_u + n_cd * eps_times_sym_grad_u : 2.0 * e_cd * deta_deps_times_sym_grad_u)
+                      + 2.0 * e_cd * deta_dp_times_p;
+        }
+      if (deviatoric) {
+        const double tr = sym_trace<DIM>(eps);
+        if (P.symmetrize) {
+          theta_times_div_u = P.average ? theta_times_div_u_JxW / JxW : tr * div_u;
+          for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) vt[c][d] -= (1.0 / 3.0) * sym_entry<DIM>(deta, c, d) * theta_times_div_u;
+          for (int d = 0; d < DIM; ++d) vt[d][d] -= (1.0 / 3.0) * tr * deta_deps_times_sym_grad_u;
+        } else {
+          for (int d = 0; d < DIM; ++d) vt[d][d] -= (2.0 / 3.0) * tr * deta_deps_times_sym_grad_u;
+        }
+        if (P.dilation)
+          pressure_terms += (sym_contract<DIM>(P.ddil + tq * NS, sg) + P.ddildp[tq] * P.ps * val_p) * P.ps;
+      }
+    }
+    // submit_symmetric_gradient / submit_value, integrate
+    int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
+    for (int i = 0; i < NN; ++i) {
+      int id[3] = {i % 3, (i / 3) % 3, DIM == 3 ? i / 9 : 0};
+      double dphi[DIM];
+      for (int d = 0; d < DIM; ++d) {
+        double v = P.ih[d] * JxW;
+        for (int e = 0; e < DIM; ++e) v *= (e == d) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
+        dphi[d] = v;
+      }
+      for (int c = 0; c < DIM; ++c) {
+        double acc = T[c][i];
+        for (int d = 0; d < DIM; ++d) acc = fma(vt[c][d], dphi[d], acc);
+        T[c][i] = acc;
+      }
+    }
+    if (P.mode == 1)
+      for (int a = 0; a < NP; ++a) {
+        int ad[3] = {a % 2, (a / 2) % 2, DIM == 3 ? a / 4 : 0};
+        double v = pressure_terms * JxW;
+        for (int d = 0; d < DIM; ++d) v *= q1v(qd[d], ad[d]);
+        Tp[a] += v;
+      }
+  }
+  // distribute_local_to_global: nothing is added to constrained rows
+  for (int i = 0; i < NN; ++i) {
+    const uint32_t e = P.cell_nodes_u[cell * NN + i];
+    const uint32_t idx = e & NODE_IDX_MASK;
+    for (int c = 0; c < DIM; ++c)
+      if (!((e >> (NODE_FLAG_SHIFT + c)) & 1u)) atomicAdd(P.dst_u + idx + c, T[c][i]);
+  }
+  if (P.mode == 1)
+    for (int a = 0; a < NP; ++a) {
+      const uint32_t e = P.cell_nodes_p[cell * NP + a];
+      if (!(e >> 31)) atomicAdd(P.dst_p + (e & NODE_IDX_MASK), Tp[a]);
+    }
+}
+// dst[c] = src[c] on constrained DoFs (unit diagonal of MatrixFreeOperators::Base)
+__global__ void copy_entries_kernel(double *dst, const double *src, const uint32_t *idx, int64_t n)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[idx[i]];
+}
+
+static bool needs_general(const LevelDev &L, int mode)
+{ return L.compressible || L.nd.dilation || (mode == 1 && L.nd.newton); }
+
+// dst must be zeroed by the caller
+static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool plain)
+{
+  GeneralParams P{};
+  P.n_cells = L.n_cells; P.cell_nodes_u = L.cell_nodes_u; P.cell_nodes_p = L.cell_nodes_p;
+  P.src_u = src_u; P.src_p = src_p; P.dst_u = dst_u; P.dst_p = dst_p;
+  P.eta = L.eta; P.n_eta = L.n_eta;
+  double vol = 1.0;
+  for (int d = 0; d < L.dim; ++d) { P.ih[d] = 1.0 / L.h[d]; vol *= L.h[d]; }
+  P.vol = vol; P.ps = L.ps; P.mode = mode; P.plain = plain ? 1 : 0;
+  P.compressible = L.compressible; P.newton = L.nd.newton; P.symmetrize = L.nd.symmetrize; P.average = L.nd.average; P.dilation = L.nd.dilation;
+  P.eps = L.nd.eps; P.deta = L.nd.deta; P.detadp = L.nd.detadp; P.dil_lhs = L.nd.dil_lhs; P.ddil = L.nd.ddil; P.ddildp = L.nd.ddildp;
+  {
+    ProfScope prof(ctx, mode == 1 ? B_STOKES : B_A_COARSE);
+    const unsigned grid = (unsigned)((L.n_cells + 63) / 64);
+    if (L.dim == 3) general_cell_kernel<3><<<grid, 64, 0, ctx->stream>>>(P);
+    else general_cell_kernel<2><<<grid, 64, 0, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  if (!plain) {
+    if (L.n_constrained_u) {
+      copy_entries_kernel<<<(unsigned)((L.n_constrained_u + 255) / 256), 256, 0, ctx->stream>>>(dst_u, src_u, L.constrained_u, L.n_constrained_u);
+      ctx->launches++;
+    }
+    if (mode == 1 && L.n_constrained_p) {
+      copy_entries_kernel<<<(unsigned)((L.n_constrained_p + 255) / 256), 256, 0, ctx->stream>>>(dst_p, src_p, L.constrained_p, L.n_constrained_p);
+      ctx->launches++;
+    }
+  }
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
 static int check_level(smf_ctx *ctx, const LevelDev &L)
 {
   if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "level mesh not set (smf_set_level)");
   if (!L.has_cell_data) return ctx->fail(SMF_ERR_INVALID, "cell data not set (smf_set_cell_data)");
-  if (L.compressible) return ctx->fail(SMF_ERR_UNSUPPORTED, "is_compressible = true is not implemented on the device path yet");
   if (!L.safe_rounds) return ctx->fail(SMF_ERR_UNSUPPORTED, "cell batches with aliasing scatter rounds (unstructured orientation) not implemented");
   return SMF_OK;
 }
@@ -1481,7 +1702,8 @@ int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bo
   CellParams P = make_params(L);
   P.src_u = src; P.dst_u = dst;
   if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_u, ctx->stream));
-  if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
+  if (needs_general(L, 0)) { if (int e = launch_general(ctx, L, 0, dst, nullptr, src, nullptr, false)) return e; }
+  else if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
   return exchange_add(ctx, L.ex_u, dst);
 }
 int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool plain)
@@ -1492,7 +1714,8 @@ int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p,
   P.plain = plain ? 1 : 0;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
   SMF_CUDA(cudaMemsetAsync(dst_p, 0, sizeof(double) * L.n_p, ctx->stream));
-  if (int e = L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P)) return e;
+  if (needs_general(L, 1)) { if (int e = launch_general(ctx, L, 1, dst_u, dst_p, src_u, src_p, plain)) return e; }
+  else if (int e = L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P)) return e;
   if (int e = exchange_add(ctx, L.ex_u, dst_u)) return e;
   return exchange_add(ctx, L.ex_p, dst_p);
 }
@@ -1540,7 +1763,7 @@ int launch_diag(smf_ctx *ctx, LevelDev &L)
   P.eta = L.eta; P.n_eta = L.n_eta;
   double vol = 1.0;
   for (int d = 0; d < L.dim; ++d) { P.ih[d] = 1.0 / L.h[d]; vol *= L.h[d]; }
-  P.vol = vol; P.ps = L.ps; P.compressible = L.compressible;
+  P.vol = vol; P.ps = L.ps; P.compressible = L.compressible || L.nd.dilation;   // deviatoric A block (:999-1005)
   P.diag_A = L.dinv_A; P.diag_M = L.dinv_M;
   SMF_CUDA(cudaMemsetAsync(L.dinv_A, 0, sizeof(double) * L.n_u, ctx->stream));
   SMF_CUDA(cudaMemsetAsync(L.dinv_M, 0, sizeof(double) * L.n_p, ctx->stream));

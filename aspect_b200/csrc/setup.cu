@@ -30,6 +30,7 @@ static void free_level(LevelDev &L)
   cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.sb_lists); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
   cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
   cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M);
+  cudaFree(L.nd.eps); cudaFree(L.nd.deta); cudaFree(L.nd.detadp); cudaFree(L.nd.dil_lhs); cudaFree(L.nd.ddil); cudaFree(L.nd.ddildp);
   free_exchange(L.ex_u); free_exchange(L.ex_p);
   L = LevelDev();
 }
@@ -562,6 +563,50 @@ int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *d)
   L.n_eta = d->n_per_cell; L.ps = d->pressure_scaling; L.compressible = d->is_compressible;
   L.has_cell_data = true; L.has_diag = false;
   ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+int smf_set_newton_data(smf_ctx *ctx, const smf_newton_data *d)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  LevelDev &L = ctx->lev(SMF_ACTIVE);
+  if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the active level mesh first");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  NewtonDev &N = L.nd;
+  cudaFree(N.eps); cudaFree(N.deta); cudaFree(N.detadp); cudaFree(N.dil_lhs); cudaFree(N.ddil); cudaFree(N.ddildp);
+  N = NewtonDev();
+  L.has_diag = false;                 // (prescribed dilation makes the A block deviatoric)
+  ctx->smoothers_ready = false;
+  if (!d) return SMF_OK;
+  if (d->apply_stabilization_free_surface_faces)
+    return ctx->fail(SMF_ERR_UNSUPPORTED, "free-surface stabilisation faces (matrix_free_operators.cc:563-602) are not implemented");
+  const int nq = L.dim == 3 ? 27 : 9, ns = L.dim * (L.dim + 1) / 2;
+  auto up = [&](double **dev, const double *host, int per_q) -> int {
+    if (!host) return ctx->fail(SMF_ERR_INVALID, "smf_set_newton_data: a table required by the enabled flags is missing");
+    const size_t nb = sizeof(double) * (size_t)L.n_cells * nq * per_q;
+    SMF_CUDA(cudaMalloc((void **)dev, nb));
+    SMF_CUDA(cudaMemcpy(*dev, host, nb, cudaMemcpyHostToDevice));
+    ctx->bytes += (int64_t)nb;
+    return SMF_OK;
+  };
+  int e;
+  if (d->enable_newton_derivatives) {
+    if ((e = up(&N.eps, d->strain_rate_table, ns))) return e;
+    if ((e = up(&N.deta, d->newton_factor_wrt_strain_rate_table, ns))) return e;
+    if ((e = up(&N.detadp, d->newton_factor_wrt_pressure_table, 1))) return e;
+  }
+  if (d->enable_prescribed_dilation) {
+    if ((e = up(&N.dil_lhs, d->dilation_lhs_term_table, 1))) return e;
+    if (d->enable_newton_derivatives) {
+      if ((e = up(&N.ddil, d->dilation_derivative_wrt_strain_rate_table, ns))) return e;
+      if ((e = up(&N.ddildp, d->dilation_derivative_wrt_pressure_table, 1))) return e;
+    }
+  }
+  N.newton = d->enable_newton_derivatives ? 1 : 0;
+  N.symmetrize = d->symmetrize_newton_system ? 1 : 0;
+  N.average = d->average_newton_factors ? 1 : 0;
+  N.dilation = d->enable_prescribed_dilation ? 1 : 0;
   return SMF_OK;
 }
 

@@ -83,6 +83,12 @@ struct ExchangeDev {
   void *p2p_tab = nullptr, *p2p_state = nullptr; double *p2p_inbox = nullptr;
 };
 
+// Newton / prescribed-dilation tables of OperatorCellData (active level only; matrix_free_operators.h:128-196)
+struct NewtonDev {
+  int newton = 0, symmetrize = 0, average = 0, dilation = 0;
+  double *eps = nullptr, *deta = nullptr, *detadp = nullptr, *dil_lhs = nullptr, *ddil = nullptr, *ddildp = nullptr;
+};
+
 struct LevelDev {
   int dim = 0;
   int64_t n_cells = 0, n_u = 0, n_p = 0;
@@ -105,6 +111,7 @@ struct LevelDev {
   double h[3] = {1, 1, 1};
   // cell data
   double *eta = nullptr; int n_eta = 0; double ps = 1.0; int compressible = 0; bool has_cell_data = false;
+  NewtonDev nd;
   // inverse diagonals
   double *dinv_A = nullptr, *dinv_M = nullptr; bool has_diag = false;
   int64_t bytes = 0;

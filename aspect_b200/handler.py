@@ -227,6 +227,23 @@ class StokesMatrixFreeHandler:
         d = _lib.CellData(ptr(t), t.shape[1], float(pressure_scaling), int(is_compressible))
         self._check(self.lib.smf_set_cell_data(self.ctx, level, ctypes.byref(d)))
 
+    def set_newton_data(self, enable_newton_derivatives=False, symmetrize_newton_system=False, average_newton_factors=False,
+                        enable_prescribed_dilation=False, strain_rate_table=None, newton_factor_wrt_strain_rate_table=None,
+                        newton_factor_wrt_pressure_table=None, dilation_lhs_term_table=None,
+                        dilation_derivative_wrt_strain_rate_table=None, dilation_derivative_wrt_pressure_table=None):
+        """The Newton / prescribed-dilation fields of the active `OperatorCellData` (matrix_free_operators.h:128-196; filled by
+        local_smoothing.cc:296-612 in the reference): tables [cells][3^dim][n_sym] / [cells][3^dim], symmetric tensors in
+        deal.II's unrolled order.  Call with no arguments to clear."""
+        keep = [None if t is None else np.ascontiguousarray(t, dtype=np.float64) for t in (
+            strain_rate_table, newton_factor_wrt_strain_rate_table, newton_factor_wrt_pressure_table, dilation_lhs_term_table,
+            dilation_derivative_wrt_strain_rate_table, dilation_derivative_wrt_pressure_table)]
+        if not (enable_newton_derivatives or enable_prescribed_dilation):
+            self._check(self.lib.smf_set_newton_data(self.ctx, None))
+            return
+        d = _lib.NewtonData(int(enable_newton_derivatives), int(symmetrize_newton_system), int(average_newton_factors),
+                            int(enable_prescribed_dilation), 0, *[None if t is None else t.ctypes.data for t in keep])
+        self._check(self.lib.smf_set_newton_data(self.ctx, ctypes.byref(d)))
+
     def build_preconditioner(self):
         self._check(self.lib.smf_compute_diagonals(self.ctx))
 

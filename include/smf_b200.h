@@ -115,6 +115,27 @@ typedef struct {
 } smf_cell_data;
 int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *data);
 
+/* The remaining fields of OperatorCellData (matrix_free_operators.h:128-196), ACTIVE level only as in the reference
+ * (local_smoothing.cc:296-612; the level operators never see them, :308-314): Newton-derivative and prescribed-dilation
+ * tables, [n_cells][n_q][n_sym] or [n_cells][n_q] in the cell order of smf_set_level, n_q = 3^dim, symmetric tensors in
+ * deal.II's unrolled order 00, 11, (22,) 01, (02, 12).  Tables are COPIED.  They enter StokesOperator::local_apply
+ * (matrix_free_operators.cc:400-446, :464-538); enable_prescribed_dilation also makes the A block deviatoric
+ * (:999-1005).  Passing NULL clears them.  The free-surface face term (:563-602) returns SMF_ERR_UNSUPPORTED. */
+typedef struct {
+  int enable_newton_derivatives;
+  int symmetrize_newton_system;
+  int average_newton_factors;
+  int enable_prescribed_dilation;
+  int apply_stabilization_free_surface_faces;
+  const double *strain_rate_table;
+  const double *newton_factor_wrt_strain_rate_table;
+  const double *newton_factor_wrt_pressure_table;
+  const double *dilation_lhs_term_table;
+  const double *dilation_derivative_wrt_strain_rate_table;
+  const double *dilation_derivative_wrt_pressure_table;
+} smf_newton_data;
+int smf_set_newton_data(smf_ctx *ctx, const smf_newton_data *data);
+
 /* ---- device vectors ------------------------------------------------------------------------- */
 int smf_vec_alloc(smf_ctx *ctx, int64_t n, double **dev_ptr);   /* initialize_dof_vector */
 int smf_vec_free(smf_ctx *ctx, double *dev_ptr);

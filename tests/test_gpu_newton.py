@@ -1,0 +1,116 @@
+"""GPU parity of the general cell kernel: compressible, prescribed-dilation and Newton-derivative branches of
+StokesOperator::local_apply (matrix_free_operators.cc:376-547) and the deviatoric A block (:974-1009), against the
+oracle's restatement (oracle/newton.py, itself anchored on the assembled operator and on symmetry)."""
+import numpy as np
+import pytest
+
+from oracle import assembled, coeff, mesh as omesh, newton, solver as osolver
+from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
+from test_newton_oracle import random_newton_data
+from util import rel, seeded
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _setup(dim, R, bc, averaging, compressible, seed=1):
+    hier = synthetic.BoxHierarchy(dim, R)
+    ohier = omesh.Hierarchy(dim, R)
+    rng = np.random.default_rng(seed)
+    eta_q = np.exp(rng.uniform(-2, 2, size=(hier.active.n_cells, 3 ** dim)))
+    ps = 1.3
+    h = StokesMatrixFreeHandler(dim)
+    h.setup_dofs(hier, bc)
+    h.assemble(eta_q, averaging, ps, is_compressible=compressible)
+    op = {"none": "none", "harmonic average": "harmonic"}[averaging]
+    eta_active, eta_levels, _, _ = coeff.viscosity_tables(ohier, eta_q, op)
+    return hier, ohier, h, eta_active, eta_levels, ps
+
+
+def _vectors(h, act, bc, seed):
+    xu, xp = seeded(act.n_u, seed), seeded(act.n_p, seed + 1)
+    src, dst = h.initialize_dof_vector(), h.initialize_dof_vector()
+    src[0].from_host(xu); src[1].from_host(xp)
+    return xu, xp, src, dst
+
+
+@pytest.mark.parametrize("dim,R,bc", [(2, 3, "tangential"), (3, 2, "zero")])
+@pytest.mark.parametrize("averaging", ["none", "harmonic average"])
+def test_compressible_operators(dim, R, bc, averaging):
+    hier, ohier, h, eta_active, eta_levels, ps = _setup(dim, R, bc, averaging, True)
+    h.build_preconditioner()
+    act = ohier.active
+    cons = act.constrained_u(bc)
+    xu, xp, src, dst = _vectors(h, act, bc, 3)
+    h.stokes_matrix.vmult(dst, src)
+    yu, yp = newton.stokes_apply(act, eta_active, ps, cons, xu, xp, True)
+    assert rel(np.concatenate([dst[0].to_host(), dst[1].to_host()]), np.concatenate([yu, yp])) < TOL
+    h.A_block_matrix.vmult(dst[0], src[0])
+    assert rel(dst[0].to_host(), newton.A_apply(act, eta_active, cons, xu, True)) < TOL
+    for l, lev in enumerate(ohier.levels):            # level operators and their diagonals (deviatoric)
+        cl = lev.constrained_u(bc)
+        x = seeded(lev.n_u, 10 + l)
+        s, d = h.initialize_dof_vector(0, l), h.initialize_dof_vector(0, l)
+        s.from_host(x)
+        h.mg_matrices_A_block[l].vmult(d, s)
+        assert rel(d.to_host(), newton.A_apply(lev, eta_levels[l], cl, x, True)) < TOL
+        A = assembled.assemble_A(lev, eta_levels[l], cl, True)
+        assert rel(1.0 / h.get_matrix_diagonal_inverse(l, 0), A.diagonal()) < TOL
+    h.close()
+
+
+FLAGS = [dict(enable_newton_derivatives=True, symmetrize_newton_system=s, average_newton_factors=a, enable_prescribed_dilation=d)
+         for s in (False, True) for a in (False, True) for d in (False, True)] + [dict(enable_prescribed_dilation=True)]
+
+
+@pytest.mark.parametrize("dim,R,bc", [(2, 3, "tangential"), (3, 2, "zero")])
+@pytest.mark.parametrize("compressible", [False, True])
+@pytest.mark.parametrize("flags", FLAGS, ids=lambda f: "".join(k[7] if v else "-" for k, v in sorted(f.items())))
+def test_newton_and_dilation_branches(dim, R, bc, compressible, flags):
+    hier, ohier, h, eta_active, eta_levels, ps = _setup(dim, R, bc, "none", compressible, seed=4)
+    act = ohier.active
+    cons = act.constrained_u(bc)
+    nd = random_newton_data(act, np.random.default_rng(9), **flags)
+    h.set_newton_data(**{k: getattr(nd, k) for k in (
+        "enable_newton_derivatives", "symmetrize_newton_system", "average_newton_factors", "enable_prescribed_dilation",
+        "strain_rate_table", "newton_factor_wrt_strain_rate_table", "newton_factor_wrt_pressure_table", "dilation_lhs_term_table",
+        "dilation_derivative_wrt_strain_rate_table", "dilation_derivative_wrt_pressure_table")})
+    xu, xp, src, dst = _vectors(h, act, bc, 5)
+    h.stokes_matrix.vmult(dst, src)
+    yu, yp = newton.stokes_apply(act, eta_active, ps, cons, xu, xp, compressible, nd)
+    assert rel(np.concatenate([dst[0].to_host(), dst[1].to_host()]), np.concatenate([yu, yp])) < TOL
+    # the A block only sees the deviatoric switch (matrix_free_operators.cc:999-1005)
+    h.A_block_matrix.vmult(dst[0], src[0])
+    assert rel(dst[0].to_host(), newton.A_apply(act, eta_active, cons, xu, compressible, nd.enable_prescribed_dilation)) < TOL
+    # correct_stokes_rhs reads u0 plainly and adds nothing to constrained rows
+    r = h.initialize_dof_vector()
+    r[0].zero(); r[1].zero()
+    h.correct_stokes_rhs(r, src)
+    cu, cp = newton.stokes_apply(act, eta_active, ps, cons, xu, xp, compressible, nd, plain=True)
+    assert rel(np.concatenate([r[0].to_host(), r[1].to_host()]), -np.concatenate([cu, cp])) < TOL
+    # clearing the tables restores the plain operator
+    h.set_newton_data()
+    h.stokes_matrix.vmult(dst, src)
+    yu, yp = newton.stokes_apply(act, eta_active, ps, cons, xu, xp, compressible)
+    assert rel(np.concatenate([dst[0].to_host(), dst[1].to_host()]), np.concatenate([yu, yp])) < TOL
+    h.close()
+
+
+def test_compressible_solve_matches_oracle():
+    """A complete block-GMG solve with is_compressible = true (deviatoric A block on every level, general kernel)."""
+    dim, R, bc, avg = 2, 3, "tangential", "harmonic average"
+    hier = synthetic.BoxHierarchy(dim, R)
+    eta_q, rhs, ps = benchmarks.solcx_problem(hier, averaging=avg)
+    h = StokesMatrixFreeHandler(dim)
+    h.setup_dofs(hier, bc)
+    h.assemble(eta_q, avg, ps, is_compressible=True)
+    h.build_preconditioner()
+    h.parameters["Linear solver tolerance"] = 1e-7
+    sol, out = h.solve(rhs)
+    ohier = omesh.Hierarchy(dim, R)
+    active, levels, _, _ = coeff.viscosity_tables(ohier, eta_q, "harmonic")
+    ob = osolver.AssembledBackend(ohier, active, levels, ps, bc, compressible=True)
+    oout = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-7, restart=100, max_its=1000)
+    assert out["converged"] and out["iterations"] == oout["iterations"]
+    assert rel(sol[:hier.active.n_u], oout["x"][:hier.active.n_u]) < 1e-8
+    h.close()
