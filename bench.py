@@ -176,6 +176,7 @@ def main():
                     help="global refinement per GPU (7 = north-star single-GPU target; 8 GPUs x 7 = BASELINE cfg 5)")
     ap.add_argument("--ref-refinement", type=int, default=4, help="refinement of the CPU sample (complete solves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solver-timings", action="store_true", help="skip the Execute-solver-timings harness (incl. the IDR(2) solve)")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the extra BASELINE cfg 2 (refinement 5) solve")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -303,6 +304,11 @@ def main():
         for _ in range(3):
             host_vmult()
         t_stokes_host = max_over_ranks((time.time() - t0) / 3)
+        # ---- the reference's own "Execute solver timings" harness (local_smoothing.cc:1119-1260), 3 timings each --------
+        solver_timings = None
+        if not args.no_solver_timings:
+            solver_timings = h.execute_solver_timings(rhs_np, n_timings=3, out=lambda *_: None)
+            solver_timings = {k: max_over_ranks(v) for k, v in solver_timings.items()}
 
     its = outs[-1]["iterations"]
     wall = t_dev / args.steps
@@ -349,7 +355,7 @@ def main():
                   "note": "stokes_gdofs includes zeroing dst (StokesOperator::vmult); *_kernel_* is the cell kernel alone"},
         "time_split_ms": {k: round(v[0], 3) for k, v in split.items()},
         "launch_split": {k: v[1] for k, v in split.items()},
-        "clocks": clock_info, "host_setup_s": setup_s, "halo_exchanges_per_solve": int(exchanges), "halo_transport": h.exchange_transport(),
+        "clocks": clock_info, "host_setup_s": setup_s, "solver_timings_s": solver_timings, "halo_exchanges_per_solve": int(exchanges), "halo_transport": h.exchange_transport(),
     }
     h.close()
     # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------
