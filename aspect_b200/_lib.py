@@ -52,25 +52,27 @@ class SolveParams(ctypes.Structure):
     _fields_ = [("linear_solver_tolerance", c_dbl), ("n_cheap_stokes_solver_steps", c_int),
                 ("gmres_restart_length", c_int), ("krylov_method", c_int), ("idr_s_parameter", c_int),
                 ("n_expensive_stokes_solver_steps", c_int), ("linear_solver_A_block_tolerance", c_dbl),
-                ("linear_solver_S_block_tolerance", c_dbl)]
+                ("linear_solver_S_block_tolerance", c_dbl), ("rescale_pressure", c_int), ("normalize_pressure", c_int),
+                ("surface_pressure", c_dbl)]
 
 
 class SolveResult(ctypes.Structure):
     _fields_ = [("iterations", c_int), ("n_A_preconditioner", c_int), ("n_S_preconditioner", c_int),
                 ("initial_residual", c_dbl), ("final_residual", c_dbl), ("tolerance", c_dbl),
                 ("setup_seconds", c_dbl), ("solve_seconds", c_dbl), ("iterations_expensive", c_int),
-                ("n_A_expensive", c_int), ("n_S_expensive", c_int)]
+                ("n_A_expensive", c_int), ("n_S_expensive", c_int), ("pressure_normalization_adjustment", c_dbl)]
 
 
 # every symbol include/smf_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "smf_create", "smf_destroy", "smf_last_error", "smf_set_option", "smf_set_stream", "smf_set_level", "smf_set_transfer",
-    "smf_set_copy_indices", "smf_set_cell_data", "smf_set_newton_data", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
+    "smf_set_copy_indices", "smf_set_cell_data", "smf_fill_cell_data", "smf_get_cell_data", "smf_set_newton_data", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
     "smf_synchronize", "smf_vmult_stokes", "smf_vmult_A", "smf_vmult_BT", "smf_vmult_mass", "smf_vmult_stokes_host", "smf_correct_stokes_rhs",
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",
     "smf_solve_host", "smf_kernel_launches", "smf_device_bytes", "smf_profile_enable", "smf_profile_read",
-    "smf_exchange_count", "smf_exchange_transport", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
+    "smf_exchange_count", "smf_exchange_transport", "smf_assemble_rhs", "smf_set_pressure_normalization",
+    "smf_postprocess_pressure", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
 ]
 
 _lib = None

@@ -1688,6 +1688,47 @@ static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, do
   return SMF_OK;
 }
 
+
+// ---- Stokes right-hand side on the device -------------------------------------------------------
+// f_i = sum_q force_q . phi_i JxW_q with force = density * gravity from the plugins (assemblers/stokes.cc:387-396),
+// one thread per (cell, node); constrained rows receive nothing (the reference condenses them away, assembly.cc:761-889)
+template <int DIM> __global__ void rhs_kernel(const double *force_q, const uint32_t *cell_nodes_u, double *rhs_u, int64_t n_cells, double vol)
+{
+  constexpr int NN = nn<DIM>();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t cell = t / NN;
+  const int i = (int)(t % NN);
+  if (cell >= n_cells) return;
+  int id[3] = {i % 3, (i / 3) % 3, DIM == 3 ? i / 9 : 0};
+  double acc[DIM];
+  for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
+  for (int q = 0; q < NN; ++q) {
+    int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
+    double phi = qweight<DIM>(q) * vol;
+    for (int d = 0; d < DIM; ++d) phi *= q2v(qd[d], id[d]);
+    const double *f = force_q + (cell * NN + q) * DIM;
+    for (int c = 0; c < DIM; ++c) acc[c] = fma(f[c], phi, acc[c]);
+  }
+  const uint32_t e = cell_nodes_u[cell * NN + i];
+  const uint32_t idx = e & NODE_IDX_MASK;
+  for (int c = 0; c < DIM; ++c)
+    if (!((e >> (NODE_FLAG_SHIFT + c)) & 1u) && acc[c] != 0.0) atomicAdd(rhs_u + idx + c, acc[c]);
+}
+
+int launch_rhs(smf_ctx *ctx, LevelDev &L, const double *force_q_dev, double *rhs_u)
+{
+  double vol = 1.0;
+  for (int d = 0; d < L.dim; ++d) vol *= L.h[d];
+  const int NN = L.dim == 3 ? 27 : 9;
+  const int64_t nt = L.n_cells * NN;
+  SMF_CUDA(cudaMemsetAsync(rhs_u, 0, sizeof(double) * L.n_u, ctx->stream));
+  if (L.dim == 3) rhs_kernel<3><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(force_q_dev, L.cell_nodes_u, rhs_u, L.n_cells, vol);
+  else rhs_kernel<2><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(force_q_dev, L.cell_nodes_u, rhs_u, L.n_cells, vol);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  return exchange_add(ctx, L.ex_u, rhs_u);        // compress(add) of the per-rank partial sums
+}
+
 static int check_level(smf_ctx *ctx, const LevelDev &L)
 {
   if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "level mesh not set (smf_set_level)");

@@ -242,12 +242,12 @@ void smf_destroy(smf_ctx *ctx)
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &L : ctx->levels) free_level(L);
-  for (auto &T : ctx->transfers) { cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u); }
+  for (auto &T : ctx->transfers) { cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u); cudaFree(T.children); }
   for (auto *mg : {&ctx->mgv_A, &ctx->mgv_S})
     for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
   for (double *p : ctx->krylov) cudaFree(p);
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
-  cudaFree(ctx->io_buf); cudaFree(ctx->block_weights);
+  cudaFree(ctx->io_buf); cudaFree(ctx->block_weights); cudaFree(ctx->pnorm_weights); cudaFree(ctx->cg_buf); cudaFree(ctx->idr_normals);
   smf_comm_destroy_internal(ctx);
   cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_u2);   // tmp_p / tmp_p2 point into the same allocations
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
@@ -415,9 +415,11 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   const int dim = ctx->cfg.dim, NCH = 1 << dim;
   TransferDev &T = ctx->transfers[fine_level];
-  cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u);
+  cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u); cudaFree(T.children);
   T = TransferDev();
   T.n_parents = C.n_cells;
+  SMF_CUDA(cudaMalloc(&T.children, sizeof(int32_t) * (size_t)C.n_cells * NCH));      // (smf_fill_cell_data: interpolate_to_mg of the DGQ0 viscosity)
+  SMF_CUDA(cudaMemcpy(T.children, children, sizeof(int32_t) * (size_t)C.n_cells * NCH, cudaMemcpyHostToDevice));
   // bit 31: this parent writes the node in prolongation (first local parent that touches it);
   // bit 30: this parent contributes the node in restriction (same, and no lower rank owns the node)
   auto build = [&](int npd, const std::vector<uint32_t> &fine_nodes, int64_t n_fine_index, const std::vector<uint8_t> &not_owned,
@@ -532,6 +534,57 @@ __global__ void transpose_eta_kernel(const double *raw, double *out, int64_t n_c
   const int64_t cell = grp * SUB + lane;
   out[t] = cell < n_cells ? raw[cell * n_eta + q] : 1.0;
 }
+
+// ---- coefficient-table pipeline on the device ---------------------------------------------------
+// The array work of evaluate_material_model(): cell-wise averaging of the plugin's quadrature-point viscosities
+// (material_model/interface.cc:523-650, unweighted over the points), cellwise L2 projection onto DGQ0 = JxW-weighted
+// mean (utilities.cc:2738-2812; matrix_free_operators.cc:227-246), min / max after averaging (:248-262), and
+// interpolate_to_mg of the DGQ0 vector = mean of the 2^dim children, level by level (local_smoothing.cc:220-226).
+// One thread per cell; per-block extrema are finished on the host.
+__host__ __device__ constexpr double gw1(int i) { return i == 1 ? 8.0 / 18.0 : 5.0 / 18.0; }      // 3-point Gauss weights on [0,1]
+__global__ void k_average_viscosity(const double *raw_q, int64_t n_cells, int nq, int op, double *active_raw, double *dg0,
+                                    double *blk_min, double *blk_max)
+{
+  __shared__ double s_min[256], s_max[256];
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double vmin = 1e300, vmax = -1e300;
+  if (cell < n_cells) {
+    const double *v = raw_q + cell * nq;
+    const int dim = nq == 27 ? 3 : 2;
+    double avg = 0.0;
+    if (op == 1) { for (int q = 0; q < nq; ++q) avg += v[q]; avg /= nq; }
+    else if (op == 2) {
+      bool zero = false;
+      for (int q = 0; q < nq; ++q) { zero = zero || v[q] == 0.0; avg += 1.0 / v[q]; }
+      avg = zero ? 0.0 : 1.0 / (avg / nq);
+    } else if (op == 3) { avg = 1.0; for (int q = 0; q < nq; ++q) avg *= pow(v[q], 1.0 / nq); }
+    double proj = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double o = op == 0 ? v[q] : avg;
+      const double w = dim == 3 ? gw1(q % 3) * gw1((q / 3) % 3) * gw1(q / 9) : gw1(q % 3) * gw1(q / 3);
+      proj += w * o;                                   // (the reference-cell weights sum to 1)
+      vmin = fmin(vmin, o); vmax = fmax(vmax, o);
+      if (op == 0) active_raw[cell * nq + q] = o;
+    }
+    if (op != 0) active_raw[cell] = proj;
+    dg0[cell] = proj;
+  }
+  s_min[threadIdx.x] = vmin; s_max[threadIdx.x] = vmax;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { s_min[threadIdx.x] = fmin(s_min[threadIdx.x], s_min[threadIdx.x + s]); s_max[threadIdx.x] = fmax(s_max[threadIdx.x], s_max[threadIdx.x + s]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { blk_min[blockIdx.x] = s_min[0]; blk_max[blockIdx.x] = s_max[0]; }
+}
+__global__ void k_coarsen_dg0(const double *fine, const int32_t *children, int nch, double *coarse, int64_t n_parents)
+{
+  const int64_t par = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (par >= n_parents) return;
+  double s = 0.0;
+  for (int c = 0; c < nch; ++c) s += fine[children[par * nch + c]];
+  coarse[par] = s / nch;
+}
 }  // namespace smf
 
 extern "C" {
@@ -563,6 +616,98 @@ int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *d)
   L.n_eta = d->n_per_cell; L.ps = d->pressure_scaling; L.compressible = d->is_compressible;
   L.has_cell_data = true; L.has_diag = false;
   ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+// table of one level from a raw device array [n_cells][n_per_cell] (shared by smf_set_cell_data / smf_fill_cell_data)
+static int install_table(smf_ctx *ctx, LevelDev &L, const double *raw_dev, int n_per_cell, double ps, int compressible)
+{
+  const int64_t padded = (int64_t)L.n_batches * BATCH_CELLS;
+  const int64_t n_out = padded * n_per_cell;
+  if (L.eta && L.n_eta != n_per_cell) { cudaFree(L.eta); L.eta = nullptr; }
+  if (!L.eta) {
+    SMF_CUDA(cudaMalloc(&L.eta, sizeof(double) * n_out));
+    L.bytes += sizeof(double) * n_out; ctx->bytes += sizeof(double) * n_out;
+  }
+  transpose_eta_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(raw_dev, L.eta, L.n_cells, n_per_cell, padded);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  L.n_eta = n_per_cell; L.ps = ps; L.compressible = compressible;
+  L.has_cell_data = true; L.has_diag = false;
+  return SMF_OK;
+}
+
+int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, double pressure_scaling, int is_compressible,
+                       double *min_max_out)
+{
+  if (!ctx || !viscosity_q) return SMF_ERR_INVALID;
+  if (averaging < 0 || averaging > 3) return ctx->fail(SMF_ERR_UNSUPPORTED, "averaging: 0 none, 1 arithmetic, 2 harmonic, 3 geometric (project to Q1 / pick largest / log average are not on the GMG path)");
+  const int nl = ctx->cfg.n_levels;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the level meshes first");
+  if (A.n_cells != ctx->levels[nl - 1].n_cells) return ctx->fail(SMF_ERR_UNSUPPORTED, "active mesh differs from the finest level (adaptive refinement)");
+  for (int l = 1; l < nl; ++l)
+    if (!ctx->transfers[l].children) return ctx->fail(SMF_ERR_INVALID, "smf_set_transfer must precede smf_fill_cell_data");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  const int nq = A.dim == 3 ? 27 : 9, nch = 1 << A.dim;
+  const int64_t nc = A.n_cells;
+  const int n_act = averaging == 0 ? nq : 1;
+  const unsigned blocks = (unsigned)((nc + 255) / 256);
+  double *raw = nullptr, *act = nullptr, *dg0 = nullptr, *ext = nullptr;
+  SMF_CUDA(cudaMalloc(&raw, sizeof(double) * nc * nq));
+  SMF_CUDA(cudaMalloc(&act, sizeof(double) * nc * n_act));
+  SMF_CUDA(cudaMalloc(&dg0, sizeof(double) * nc));
+  SMF_CUDA(cudaMalloc(&ext, sizeof(double) * 2 * blocks));
+  SMF_CUDA(cudaMemcpyAsync(raw, viscosity_q, sizeof(double) * nc * nq, cudaMemcpyHostToDevice, ctx->stream));
+  k_average_viscosity<<<blocks, 256, 0, ctx->stream>>>(raw, nc, nq, averaging, act, dg0, ext, ext + blocks);
+  ctx->launches++;
+  int rc = install_table(ctx, A, act, n_act, pressure_scaling, is_compressible);
+  double *fine = dg0;
+  std::vector<double *> tmp;
+  for (int l = nl - 1; l >= 0 && rc == SMF_OK; --l) {
+    LevelDev &L = ctx->levels[l];
+    rc = install_table(ctx, L, fine, 1, pressure_scaling, is_compressible);
+    if (l > 0 && rc == SMF_OK) {
+      LevelDev &C = ctx->levels[l - 1];
+      double *coarse = nullptr;
+      if (cudaMalloc(&coarse, sizeof(double) * C.n_cells) != cudaSuccess) { rc = ctx->fail(SMF_ERR_CUDA, "cudaMalloc failed"); break; }
+      tmp.push_back(coarse);
+      k_coarsen_dg0<<<(unsigned)((C.n_cells + 255) / 256), 256, 0, ctx->stream>>>(fine, ctx->transfers[l].children, nch, coarse, C.n_cells);
+      ctx->launches++;
+      fine = coarse;
+    }
+  }
+  std::vector<double> h_ext(2 * (size_t)blocks);
+  if (rc == SMF_OK && cudaMemcpyAsync(h_ext.data(), ext, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SMF_ERR_CUDA;
+  cudaStreamSynchronize(ctx->stream);
+  if (rc == SMF_OK && cudaGetLastError() != cudaSuccess) rc = ctx->fail(SMF_ERR_CUDA, "smf_fill_cell_data: kernel failure");
+  cudaFree(raw); cudaFree(act); cudaFree(dg0); cudaFree(ext);
+  for (double *p : tmp) cudaFree(p);
+  if (rc != SMF_OK) return rc;
+  if (min_max_out) {
+    double mn = 1e300, mx = -1e300;
+    for (unsigned b = 0; b < blocks; ++b) { mn = std::min(mn, h_ext[b]); mx = std::max(mx, h_ext[blocks + b]); }
+    min_max_out[0] = mn; min_max_out[1] = mx;
+  }
+  ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+// un-transposed copy of a level's viscosity table [n_cells][n_per_cell] (tests, post-processing)
+int smf_get_cell_data(smf_ctx *ctx, int level, double *host_out, int *n_per_cell_out)
+{
+  if (!ctx || !host_out) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  LevelDev &L = ctx->lev(level);
+  if (!L.has_cell_data) return ctx->fail(SMF_ERR_INVALID, "cell data not set");
+  const int64_t padded = (int64_t)L.n_batches * BATCH_CELLS;
+  std::vector<double> t((size_t)padded * L.n_eta);
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  SMF_CUDA(cudaMemcpy(t.data(), L.eta, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+  for (int64_t cell = 0; cell < L.n_cells; ++cell)
+    for (int q = 0; q < L.n_eta; ++q)
+      host_out[cell * L.n_eta + q] = t[((size_t)(cell / BATCH_CELLS) * L.n_eta + q) * BATCH_CELLS + cell % BATCH_CELLS];
+  if (n_per_cell_out) *n_per_cell_out = L.n_eta;
   return SMF_OK;
 }
 

@@ -133,6 +133,7 @@ struct TransferDev {              // level l-1 -> l
   unsigned char *tb_u = nullptr;
   uint32_t *patch_u = nullptr;    // [n_parents][5^dim] fine node (component-0 DoF) | bit31 = this parent owns the node
   uint32_t *patch_p = nullptr;    // [n_parents][3^dim]
+  int32_t *children = nullptr;    // [n_parents][2^dim] fine cells of every coarse cell (device copy)
   bool set = false;
 };
 
@@ -177,6 +178,7 @@ struct smf_ctx {
   double *io_buf = nullptr; int64_t io_n = 0;         // device staging of smf_solve_host
   int n_A_prec = 0, n_S_prec = 0;
   int n_A_exp = 0, n_S_exp = 0;                       // inner CG iterations of the expensive phase
+  double *pnorm_weights = nullptr; double pnorm_area = 0.0;   // pressure normalisation: integral of every pressure shape function over the surface / volume
   double *cg_buf = nullptr;                           // [3][n_u] scratch of the inner CG solves
   double *idr_normals = nullptr; int64_t idr_normals_n = 0;   // IDR(s) shadow-vector entries (kept between solves)
   // distributed run (comm.cu): one subdomain per rank
@@ -252,6 +254,7 @@ int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p,
 int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_p);
 int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero = false);
 int launch_diag(smf_ctx *ctx, LevelDev &L);
+int launch_rhs(smf_ctx *ctx, LevelDev &L, const double *force_q_dev, double *rhs_u);
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);
 // comm.cu
@@ -261,6 +264,7 @@ int allreduce_sum(smf_ctx *ctx, double *dev, int count);
 int start_vector_mod11(smf_ctx *ctx, const ExchangeDev &E, double *x, int64_t n);
 // vector kernels (vecops.cu)
 int vec_set(smf_ctx *ctx, double *x, double v, int64_t n);
+int vec_shift(smf_ctx *ctx, double *x, double v, int64_t n);                                 // x += v (Vector::add(scalar))
 int vec_copy(smf_ctx *ctx, double *y, const double *x, int64_t n);
 int vec_scale(smf_ctx *ctx, double *x, double a, int64_t n);
 int vec_axpy(smf_ctx *ctx, double *y, double a, const double *x, int64_t n);               // y += a x

@@ -903,6 +903,70 @@ int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out)
   return SMF_OK;
 }
 
+// Simulator::normalize_pressure (source/simulator/helper_functions.cc:765-870) and the rescaling of the pressure to
+// physical units (local_smoothing.cc:1421) on the device.  weights[i] = integral of the i-th pressure shape function
+// over the top boundary ("surface") or over this rank's cells ("volume"); the adapter computes them once per mesh.
+int smf_set_pressure_normalization(smf_ctx *ctx, const double *weights)
+{
+  if (!ctx) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the active level mesh first");
+  cudaFree(ctx->pnorm_weights); ctx->pnorm_weights = nullptr; ctx->pnorm_area = 0.0;
+  if (!weights) return SMF_OK;
+  SMF_CUDA(cudaMalloc(&ctx->pnorm_weights, sizeof(double) * A.n_p));
+  SMF_CUDA(cudaMemcpy(ctx->pnorm_weights, weights, sizeof(double) * A.n_p, cudaMemcpyHostToDevice));
+  double area = 0.0;
+  for (int64_t i = 0; i < A.n_p; ++i) area += weights[i];
+  if (ctx->world > 1) {      // Utilities::MPI::sum of the per-rank integrals
+    double *d = nullptr;
+    SMF_CUDA(cudaMalloc(&d, sizeof(double)));
+    SMF_CUDA(cudaMemcpyAsync(d, &area, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(allreduce_sum(ctx, d, 1));
+    SMF_CUDA(cudaMemcpyAsync(&area, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+  }
+  if (!(area > 0.0)) return ctx->fail(SMF_ERR_INVALID, "the area / volume to integrate the pressure over is zero or negative");
+  ctx->pnorm_area = area;
+  return SMF_OK;
+}
+
+int smf_postprocess_pressure(smf_ctx *ctx, double *sol_p, double pressure_scaling, int normalize, double surface_pressure,
+                             double *adjustment_out)
+{
+  if (!ctx || !sol_p) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (pressure_scaling != 1.0) TRY(vec_scale(ctx, sol_p, pressure_scaling, A.n_p));
+  double adjustment = 0.0;
+  if (normalize) {
+    if (!ctx->pnorm_weights) return ctx->fail(SMF_ERR_INVALID, "call smf_set_pressure_normalization first");
+    DotWeights dw(ctx, nullptr);          // the weights already partition the integral between the ranks
+    double integral;
+    TRY(vec_dot(ctx, ctx->pnorm_weights, sol_p, A.n_p, &integral));
+    adjustment = -integral / ctx->pnorm_area + surface_pressure;
+    TRY(vec_shift(ctx, sol_p, adjustment, A.n_p));
+  }
+  if (adjustment_out) *adjustment_out = adjustment;
+  return SMF_OK;
+}
+
+// right-hand side of the velocity block from the plugins' force density at the quadrature points (host array
+// [n_cells][3^dim][dim] = density * gravity), assembled on the device into rhs_u (device vector)
+int smf_assemble_rhs(smf_ctx *ctx, const double *force_q, double *rhs_u)
+{
+  if (!ctx || !force_q || !rhs_u) return SMF_ERR_INVALID;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the active level mesh first");
+  const size_t nb = sizeof(double) * (size_t)A.n_cells * (A.dim == 3 ? 27 : 9) * A.dim;
+  double *d = nullptr;
+  SMF_CUDA(cudaMalloc(&d, nb));
+  SMF_CUDA(cudaMemcpyAsync(d, force_q, nb, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = launch_rhs(ctx, A, d, rhs_u);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  return rc;
+}
+
 int smf_vcycle_A(smf_ctx *ctx, double *dst, const double *src) { if (!ctx) return SMF_ERR_INVALID; return vcycle(ctx, true, dst, src); }
 int smf_vcycle_S(smf_ctx *ctx, double *dst, const double *src) { if (!ctx) return SMF_ERR_INVALID; return vcycle(ctx, false, dst, src); }
 int smf_precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
@@ -959,6 +1023,13 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
   result->setup_seconds = t1 - t0;
   result->solve_seconds = t2 - t1;
   if (rc == SMF_NO_CONVERGENCE && ctx->err.empty()) ctx->err = "iterative Stokes solver did not converge (SolverControl::NoConvergence)";
+  // back to physical units, pressure normalisation (local_smoothing.cc:1421, :1441-1443)
+  if ((rc == SMF_OK || rc == SMF_NO_CONVERGENCE) && (prm->rescale_pressure || prm->normalize_pressure)) {
+    const std::string keep = ctx->err;
+    TRY(smf_postprocess_pressure(ctx, sol_p, prm->rescale_pressure ? A.ps : 1.0, prm->normalize_pressure, prm->surface_pressure,
+                                 &result->pressure_normalization_adjustment));
+    ctx->err = keep;
+  }
   return rc;
 }
 

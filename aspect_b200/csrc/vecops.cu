@@ -42,6 +42,7 @@ __global__ void k_cheb_update(double *x, double *xo, const double *dinv, const d
     t[i] = 0.0;
   }
 }
+__global__ void k_shift(double *x, double v, int64_t n) { GRID_STRIDE(i, n) x[i] += v; }
 __global__ void k_gather(double *y, const double *x, const uint32_t *idx, int64_t n) { GRID_STRIDE(i, n) y[i] = x[idx[i]]; }
 __global__ void k_scatter(double *y, const double *x, const uint32_t *idx, int64_t n) { GRID_STRIDE(i, n) y[idx[i]] = x[i]; }
 __global__ void k_mod11(double *x, int64_t first, double mean, int64_t n) { GRID_STRIDE(i, n) x[i] = (double)((i + first) % 11) - mean; }
@@ -57,6 +58,7 @@ __global__ void k_mod11(double *x, int64_t first, double mean, int64_t n) { GRID
   } while (0)
 
 int vec_set(smf_ctx *ctx, double *x, double v, int64_t n) { LAUNCH_EW(k_set, n, x, v, n); return SMF_OK; }
+int vec_shift(smf_ctx *ctx, double *x, double v, int64_t n) { LAUNCH_EW(k_shift, n, x, v, n); return SMF_OK; }
 int vec_copy(smf_ctx *ctx, double *y, const double *x, int64_t n) { LAUNCH_EW(k_copy, n, y, x, n); return SMF_OK; }
 int vec_scale(smf_ctx *ctx, double *x, double a, int64_t n) { LAUNCH_EW(k_scale, n, x, a, n); return SMF_OK; }
 int vec_axpy(smf_ctx *ctx, double *y, double a, const double *x, int64_t n) { LAUNCH_EW(k_axpy, n, y, a, x, n); return SMF_OK; }

@@ -69,6 +69,7 @@ class StokesMatrixFreeHandler:
         self.minimum_viscosity = self.maximum_viscosity = None
         self.allow_structured_bricks = True      # implementation switches (smf_set_option); tests exercise both paths
         self.use_cuda_graphs = True
+        self.device_cell_data = True             # assemble(): averaging / projection / level tables on the device (False: host numpy)
         self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
         self.p2p_exchange = True                 # >1 rank: halo exchange as one kernel over NVLink peer memory (False: NCCL send/recv)
@@ -85,6 +86,9 @@ class StokesMatrixFreeHandler:
             "IDR(s) parameter": 2,
             "Linear solver A block tolerance": 1e-2,
             "Linear solver S block tolerance": 1e-6,
+            # global parameters the solve's post-processing reads (parameters.cc: "Pressure normalization", "Surface pressure")
+            "Pressure normalization": "no",                        # "surface" | "volume" | "no" (reference default: surface)
+            "Surface pressure": 0.0,
         }
 
     def name(self):
@@ -211,14 +215,43 @@ class StokesMatrixFreeHandler:
     def assemble(self, viscosity_q, material_averaging="none", pressure_scaling=1.0, is_compressible=False):
         """evaluate_material_model(): viscosity_q = plugin output at the velocity quadrature points of the
         active cells, (n_cells, 3^dim)."""
+        self.pressure_scaling = float(pressure_scaling)
+        if self.device_cell_data:
+            # averaging, DGQ0 projection, min / max and the level tables on the device (smf_fill_cell_data)
+            op = material_averaging.replace(" only viscosity", "")
+            codes = {"none": 0, "arithmetic average": 1, "harmonic average": 2, "geometric average": 3}
+            if op not in codes:
+                raise SmfError(_lib.SMF_ERR_UNSUPPORTED, f"unsupported Material averaging for the GMG path: {material_averaging}")
+            q = np.ascontiguousarray(viscosity_q, dtype=np.float64)
+            assert q.shape == (self.hier.active.n_cells, 3 ** self.dim)
+            mm = np.zeros(2)
+            self._check(self.lib.smf_fill_cell_data(self.ctx, ptr(q), codes[op], ctypes.c_double(pressure_scaling), int(is_compressible), ptr(mm)))
+            self.minimum_viscosity, self.maximum_viscosity = float(mm[0]), float(mm[1])
+            self._tables = None
+            return
         children = [None] + [self.hier.children(l) for l in range(1, self.n_levels)]
         active, levels, self.minimum_viscosity, self.maximum_viscosity = cell_data.fill_cell_data(
             self.dim, children, viscosity_q, material_averaging)
-        self.pressure_scaling = float(pressure_scaling)
         self.set_cell_data(SMF_ACTIVE, active, pressure_scaling, is_compressible)
         for l in range(self.n_levels):
             self.set_cell_data(l, levels[l], pressure_scaling, is_compressible)
-        self.active_table, self.level_tables = active, levels
+        self._tables = (active, levels)
+
+    def get_cell_data(self, level):
+        """The viscosity table of a level as the kernels see it, (n_cells, 1 or 3^dim)."""
+        L = self.hier.active if level == SMF_ACTIVE else self.hier.levels[level]
+        buf = np.zeros(L.n_cells * 3 ** self.dim)
+        n = ctypes.c_int(0)
+        self._check(self.lib.smf_get_cell_data(self.ctx, level, ptr(buf), ctypes.byref(n)))
+        return buf[:L.n_cells * n.value].reshape(L.n_cells, n.value).copy()
+
+    @property
+    def active_table(self):
+        return self._tables[0] if self._tables else self.get_cell_data(SMF_ACTIVE)
+
+    @property
+    def level_tables(self):
+        return self._tables[1] if self._tables else [self.get_cell_data(l) for l in range(self.n_levels)]
 
     def set_cell_data(self, level, table, pressure_scaling, is_compressible=False):
         t = np.ascontiguousarray(table, dtype=np.float64)
@@ -268,7 +301,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_restrict_add(self.ctx, which, from_level, ptr(dst.ptr), ptr(src.ptr)))
 
     # ------------------------------------------------------------------
-    def _params(self):
+    def _params(self, host_call=False):
         p = self.parameters
         methods = {"GMRES": 0, "IDR(s)": 1}              # parameters.cc:469-481
         if p["Krylov method for cheap solver steps"] not in methods:
@@ -276,7 +309,53 @@ class StokesMatrixFreeHandler:
         return _lib.SolveParams(p["Linear solver tolerance"], p["Number of cheap Stokes solver steps"],
                                 p["GMRES solver restart length"], methods[p["Krylov method for cheap solver steps"]],
                                 p["IDR(s) parameter"], p["Maximum number of expensive Stokes solver steps"],
-                                p["Linear solver A block tolerance"], p["Linear solver S block tolerance"])
+                                p["Linear solver A block tolerance"], p["Linear solver S block tolerance"],
+                                int(host_call and self.pressure_scaling != 1.0), int(host_call and self._pressure_normalization_set()),
+                                float(p["Surface pressure"]))
+
+    def _pressure_normalization_set(self):
+        """Uploads the normalisation weights when "Pressure normalization" asks for them (once per mesh and kind)."""
+        kind = self.parameters["Pressure normalization"]
+        if kind == "no":
+            return False
+        if getattr(self, "_pnorm_kind", None) != kind:
+            self.set_pressure_normalization(kind)
+        return True
+
+    def set_pressure_normalization(self, kind):
+        """Weights of `Simulator::normalize_pressure` (helper_functions.cc:765-870) for the box meshes of this package:
+        integral of every Q1 pressure shape function over this rank's cells ("volume") or over the top boundary faces
+        ("surface", the faces with the last coordinate at its maximum)."""
+        act, dim = self.hier.active, self.dim
+        w = np.zeros(act.n_p)
+        cp = np.asarray(act.cell_dofs_p, dtype=np.int64)
+        if kind == "volume":
+            np.add.at(w, cp.ravel(), float(np.prod(act.h)) / 2 ** dim)
+        elif kind == "surface":
+            top = np.asarray(act.cells)[:, dim - 1] == np.asarray(act.cells)[:, dim - 1].max()
+            if getattr(self.hier, "world", 1) > 1:       # only the ranks whose subdomain touches the global top boundary
+                top &= np.asarray(act.cells)[:, dim - 1] == act.grid_p - 2
+            upper = [a for a in range(2 ** dim) if (a >> (dim - 1)) & 1]
+            area = float(np.prod(act.h[:dim - 1])) / 2 ** (dim - 1)
+            np.add.at(w, cp[top][:, upper].ravel(), area)
+        else:
+            raise SmfError(_lib.SMF_ERR_INVALID, "Pressure normalization: surface | volume | no")
+        self._check(self.lib.smf_set_pressure_normalization(self.ctx, ptr(w)))
+        self._pnorm_kind = kind
+
+    def postprocess_pressure(self, sol_p, pressure_scaling=1.0, normalize=True):
+        """Rescale and normalise a device pressure vector in place; returns the pressure normalisation adjustment."""
+        adj = ctypes.c_double(0.0)
+        self._check(self.lib.smf_postprocess_pressure(self.ctx, ptr(sol_p.ptr), ctypes.c_double(pressure_scaling), int(normalize),
+                                                      ctypes.c_double(self.parameters["Surface pressure"]), ctypes.byref(adj)))
+        return adj.value
+
+    def assemble_stokes_rhs(self, force_q, rhs_u):
+        """Velocity block of the right-hand side on the device (assemblers/stokes.cc:387-396): force_q = density * gravity at
+        the quadrature points, (n_cells, 3^dim, dim); rhs_u = DeviceVector of the velocity block."""
+        f = np.ascontiguousarray(force_q, dtype=np.float64)
+        assert f.shape == (self.hier.active.n_cells, 3 ** self.dim, self.dim)
+        self._check(self.lib.smf_assemble_rhs(self.ctx, ptr(f), ptr(rhs_u.ptr)))
 
     def solve(self, system_rhs, solution_vector=None, out=None):
         """Host-buffer solve (the reference-facing call): system_rhs = concat(f_u, f_p); solution_vector = initial
@@ -294,12 +373,10 @@ class StokesMatrixFreeHandler:
             sol[nu:] /= self.pressure_scaling                  # local_smoothing.cc:975
         su, sp = np.ascontiguousarray(sol[:nu]), np.ascontiguousarray(sol[nu:])
         ru, rp = np.ascontiguousarray(rhs[:nu]), np.ascontiguousarray(rhs[nu:])
-        prm, res = self._params(), _lib.SolveResult()
+        prm, res = self._params(host_call=True), _lib.SolveResult()      # (pressure rescaled / normalised on the device, :1421, :1441)
         rc = self.lib.smf_solve_host(self.ctx, ctypes.byref(prm), ptr(su), ptr(sp), ptr(ru), ptr(rp), ctypes.byref(res))
         out = self._outputs(res)
         self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
-        if self.pressure_scaling != 1.0:
-            sp *= self.pressure_scaling                         # :1421
         out["converged"] = rc == 0
         return sol, out
 

@@ -115,6 +115,22 @@ typedef struct {
 } smf_cell_data;
 int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *data);
 
+/* The array work of evaluate_material_model() on the device: viscosity_q = the material plugin's output at
+ * the 3^dim velocity quadrature points of every active cell, host array [n_cells][3^dim].  Averaging over the points of a
+ * cell (source/material_model/interface.cc:523-650; 0 none, 1 arithmetic, 2 harmonic, 3 geometric), cellwise projection
+ * onto DGQ0 (source/utilities.cc:2738-2812), the active table (matrix_free_operators.cc:227-246: n_q values per cell without
+ * averaging, else 1), min / max after averaging (:248-262) and the level tables by interpolate_to_mg = mean of the children
+ * (local_smoothing.cc:211-294).  Needs smf_set_level on all levels and smf_set_transfer; uniformly refined meshes.
+ * Equivalent to smf_set_cell_data on the active mesh and on every level. */
+#define SMF_AVG_NONE 0
+#define SMF_AVG_ARITHMETIC 1
+#define SMF_AVG_HARMONIC 2
+#define SMF_AVG_GEOMETRIC 3
+int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, double pressure_scaling, int is_compressible,
+                       double *min_max_out);
+/* host copy [n_cells][n_per_cell] of a level's table as the kernels see it */
+int smf_get_cell_data(smf_ctx *ctx, int level, double *host_out, int *n_per_cell_out);
+
 /* The remaining fields of OperatorCellData (matrix_free_operators.h:128-196), ACTIVE level only as in the reference
  * (local_smoothing.cc:296-612; the level operators never see them, :308-314): Newton-derivative and prescribed-dilation
  * tables, [n_cells][n_q][n_sym] or [n_cells][n_q] in the cell order of smf_set_level, n_q = 3^dim, symmetric tensors in
@@ -193,6 +209,9 @@ typedef struct {
   int n_expensive_stokes_solver_steps;   /* "Maximum number of expensive Stokes solver steps" (:531)   */
   double linear_solver_A_block_tolerance;   /* "Linear solver A block tolerance" (:546)                */
   double linear_solver_S_block_tolerance;   /* "Linear solver S block tolerance" (:584)                */
+  int rescale_pressure;                  /* 1: the returned pressure is multiplied by the pressure scaling (local_smoothing.cc:1421) */
+  int normalize_pressure;                /* 1: Simulator::normalize_pressure with the weights of smf_set_pressure_normalization   */
+  double surface_pressure;               /* "Surface pressure" (target of the surface normalisation)   */
 } smf_solve_params;
 
 typedef struct {
@@ -207,6 +226,7 @@ typedef struct {
   int iterations_expensive;              /* FGMRES iterations of the expensive phase ("cheap+expensive") */
   int n_A_expensive;                     /* inner CG iterations with the A block (expensive phase)     */
   int n_S_expensive;                     /* inner CG iterations with the pressure mass matrix          */
+  double pressure_normalization_adjustment;   /* outputs.pressure_normalization_adjustment (0 without normalisation) */
 } smf_solve_result;
 
 /* StokesMatrixFreeHandler::solve() (local_smoothing.cc:758-1446) on device vectors: the cheap phase (GMRES or IDR(s) with
@@ -218,6 +238,22 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
 /* same with host buffers (the reference-facing plugin call: H2D of rhs/guess, solve, D2H of the solution) */
 int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *sol_p,
                    const double *rhs_u, const double *rhs_p, smf_solve_result *result);
+
+/* ---- callers either side of the solve ------------------------------------------------ */
+/* Velocity block of the Stokes right-hand side, f_i = int force . phi_i (source/simulator/assemblers/stokes.cc:387-396;
+ * cell loop source/simulator/assembly.cc:761-889): force_q = density * gravity from the plugins, host array
+ * [n_cells][3^dim][dim]; rhs_u = device vector.  Constrained rows receive nothing; on several ranks the per-rank partial
+ * sums are exchanged (compress(add)). */
+int smf_assemble_rhs(smf_ctx *ctx, const double *force_q, double *rhs_u);
+/* Simulator::normalize_pressure (source/simulator/helper_functions.cc:765-870): weights[i] = integral of the i-th pressure
+ * shape function over the top boundary (`Pressure normalization = surface`) or over this rank's cells (`volume`),
+ * host array [n_p]; NULL switches the normalisation off. */
+int smf_set_pressure_normalization(smf_ctx *ctx, const double *weights);
+/* sol_p *= pressure_scaling (local_smoothing.cc:1421), then, if normalize, sol_p += adjustment with
+ * adjustment = -(integral of p) / area + surface_pressure (helper_functions.cc:843-850); returns the adjustment
+ * (SolverOutputs::pressure_normalization_adjustment). */
+int smf_postprocess_pressure(smf_ctx *ctx, double *sol_p, double pressure_scaling, int normalize, double surface_pressure,
+                             double *adjustment_out);
 
 /* Device-time profiler: the reference's "Execute solver timings" switch (local_smoothing.cc:60-65, :1119-1260)
  * and TimerOutput sections, done with CUDA event pairs on the context's stream around every launch.

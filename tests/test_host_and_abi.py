@@ -97,3 +97,34 @@ def test_product_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle-free", ""), f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct of include/smf_b200.h, measured by a C program compiled with gcc, against the ctypes
+    mirrors in aspect_b200/_lib.py (a silent mismatch would corrupt parameters on the GPU box)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    pairs = {"smf_config": _lib.Config, "smf_level_mesh": _lib.LevelMesh, "smf_exchange": _lib.Exchange, "smf_cell_data": _lib.CellData,
+             "smf_newton_data": _lib.NewtonData, "smf_solve_params": _lib.SolveParams, "smf_solve_result": _lib.SolveResult}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smf_b200.h"', 'int main(void){']
+    header = open(os.path.join(ROOT, "include", "smf_b200.h")).read()
+    for cname, cls in pairs.items():
+        body = re.search(r"typedef struct \{([^}]*)\}\s*" + cname + r"\s*;", header).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = [n for decl in body.split(";") if decl.strip() for n in re.findall(r"[\*\s](\w+)\s*(?:,|$)", decl.strip())]
+        assert names == [f[0] for f in cls._fields_], f"{cname}: field names / order differ: {names} vs {[f[0] for f in cls._fields_]}"
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for n in names:
+            lines.append(f'printf("{cname}.{n} %zu\\n", offsetof({cname}, {n}));')
+    lines.append("return 0;}")
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for n, _ in cls._fields_:
+            assert int(got[f"{cname}.{n}"]) == getattr(cls, n).offset, f"{cname}.{n}"
