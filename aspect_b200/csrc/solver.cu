@@ -588,8 +588,9 @@ static int fgmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double
 // Shadow vectors of SolverIDR: Q_1..Q_{s-1} are filled with std::normal_distribution<double>(0,1) values drawn from a
 // default-seeded std::mt19937, entry by entry over the locally owned DoFs (velocity block, then pressure block), the
 // stream continuing from one vector to the next.  nvcc's host compiler is g++, so this IS deal.II's stream (libstdc++).
-// The values only depend on (n, s): they are kept on the device between solves.  With several ranks the entries are a
-// hash of the partition-independent global DoF number instead (every copy of a shared DoF must get the same value).
+// The values only depend on (n, s): they are kept on the device between solves.  With several ranks -- or whenever
+// global DoF numbers were supplied -- the entries are a hash of the partition-independent global DoF number instead
+// (every copy of a shared DoF must get the same value, and a P-rank run then repeats the 1-rank run).
 static uint64_t mix64(uint64_t z)
 { z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); }
 static int idr_shadow_vectors(smf_ctx *ctx, int s, int64_t nu, int64_t np)
@@ -600,7 +601,7 @@ static int idr_shadow_vectors(smf_ctx *ctx, int s, int64_t nu, int64_t np)
   if (s < 2) return SMF_OK;
   std::vector<double> host((size_t)(s - 1) * n);
   LevelDev &A = ctx->lev(SMF_ACTIVE);
-  if (ctx->world == 1) {
+  if (ctx->world == 1 && !(A.ex_u.gid && A.ex_p.gid)) {
     std::mt19937 rng;
     std::normal_distribution<double> normal(0.0, 1.0);
     for (double &v : host) v = normal(rng);

@@ -29,6 +29,11 @@ def setup(R, rep, rank, world, avg):
     h.assemble(eta_q, avg, ps)
     h.build_preconditioner()
     h.parameters.update({"Linear solver tolerance": 1e-6, "Number of cheap Stokes solver steps": 200})
+    mode = sys.argv[2] if len(sys.argv) > 2 else "gmres"
+    if mode == "idr":            # shadow vectors hashed from the global DoF numbers: partition independent
+        h.parameters["Krylov method for cheap solver steps"] = "IDR(s)"
+    elif mode == "expensive":    # 5 cheap steps, then FGMRES with inner CG solves (weighted inner products on every rank)
+        h.parameters["Number of cheap Stokes solver steps"] = 5
     return hier, h, rhs
 
 
@@ -84,7 +89,10 @@ def main():
     e_sol_u = rel(su, su1[iu])
     # no-slip box: pressure up to a constant
     e_sol_p = rel(sp - sp.mean() + sp1[ip].mean(), sp1[ip])
-    ok = e_op < 1e-12 and abs(out["iterations"] - out1["iterations"]) <= 1 and e_sol_u < 1e-8 and out["converged"]
+    mode = sys.argv[2] if len(sys.argv) > 2 else "gmres"
+    its, its1 = out["iterations"] + out["iterations_expensive"], out1["iterations"] + out1["iterations_expensive"]
+    # (the inner CG solves of the expensive phase stop at a relative 1e-2: the iterates agree to solver tolerance only)
+    ok = e_op < 1e-12 and abs(its - its1) <= (1 if mode != "expensive" else 3) and e_sol_u < (1e-8 if mode != "expensive" else 1e-3) and out["converged"]
     # copies of shared DoFs must be bitwise equal across ranks
     gathered = [None] * world
     dist.all_gather_object(gathered, (gu, su))
@@ -97,7 +105,7 @@ def main():
                     bitwise = False
                 table[k] = v
         ok = ok and bitwise
-        print(f"dist_check world={world} R={R} transport={transport!r}: operator rel err {e_op:.2e}, iterations {out['iterations']} (1 GPU: {out1['iterations']}), "
+        print(f"dist_check world={world} R={R} mode={mode} transport={transport!r}: operator rel err {e_op:.2e}, iterations {out['iterations']}+{out['iterations_expensive']} (1 GPU: {out1['iterations']}+{out1['iterations_expensive']}), "
               f"velocity rel diff {e_sol_u:.2e}, pressure rel diff {e_sol_p:.2e}, shared copies bitwise equal: {bitwise} -> {'OK' if ok else 'FAIL'}",
               flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
