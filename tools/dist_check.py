@@ -91,8 +91,12 @@ def main():
     e_sol_p = rel(sp - sp.mean() + sp1[ip].mean(), sp1[ip])
     mode = sys.argv[2] if len(sys.argv) > 2 else "gmres"
     its, its1 = out["iterations"] + out["iterations_expensive"], out1["iterations"] + out1["iterations_expensive"]
-    # (the inner CG solves of the expensive phase stop at a relative 1e-2: the iterates agree to solver tolerance only)
-    ok = e_op < 1e-12 and abs(its - its1) <= (1 if mode != "expensive" else 3) and e_sol_u < (1e-8 if mode != "expensive" else 1e-3) and out["converged"]
+    # GMRES repeats the 1-GPU run (same iterations, 1e-15).  IDR(s) is a short-recurrence method: the different
+    # summation order of a different partition is amplified from step to step, so the two runs leave each other's path
+    # after ~20 steps (measured: 28 vs 30 iterations) and agree to the solver tolerance only; same for the expensive
+    # phase in general (inner CG solves stop at a relative 1e-2), although it happened to repeat exactly (5+46).
+    strict = mode == "gmres"
+    ok = e_op < 1e-12 and abs(its - its1) <= (1 if strict else 3) and e_sol_u < (1e-8 if strict else 1e-3) and out["converged"]
     # copies of shared DoFs must be bitwise equal across ranks
     gathered = [None] * world
     dist.all_gather_object(gathered, (gu, su))
