@@ -674,20 +674,25 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
     // (sub-batches: the list reads of a batch are in flight before its first copy is issued; u and T are live here)
     constexpr int SUBB = 4;
     if (MODE != 2) {
+      // 405 nodes = 12 full rounds of 32 (no bounds checks) + 21 nodes in a 13th round
 #pragma unroll 1
-      for (int k0 = 0; k0 < 16; k0 += SUBB) {
+      for (int k0 = 0; k0 < 12; k0 += SUBB) {
         uint32_t e[SUBB], sl[SUBB];
 #pragma unroll
         for (int k = 0; k < SUBB; ++k) {
-          const int j = min(j0 + 32 * (k0 + k), 404);
+          const int j = j0 + 32 * (k0 + k);
           e[k] = le[j]; sl[k] = ls[j];
         }
 #pragma unroll
-        for (int k = 0; k < SUBB; ++k)
-          if (j0 + 32 * (k0 + k) < 405) {
-            const bool cons = ((e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u) && !P.plain;
-            cp_async8_zfill(base + 8u * sl[k], srcd + (e[k] & NODE_IDX_MASK), cons ? 0 : 8);
-          }
+        for (int k = 0; k < SUBB; ++k) {
+          const bool cons = ((e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u) && !P.plain;
+          cp_async8_zfill(base + 8u * sl[k], srcd + (e[k] & NODE_IDX_MASK), cons ? 0 : 8);
+        }
+      }
+      if (j0 < 405 - 384) {
+        const uint32_t e = le[j0 + 384], sl = ls[j0 + 384];
+        const bool cons = ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) && !P.plain;
+        cp_async8_zfill(base + 8u * sl, srcd + (e & NODE_IDX_MASK), cons ? 0 : 8);
       }
     }
     if (MODE != 0 && tid < 75) {      // pressure values in lattice order
@@ -793,8 +798,9 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
     // accumulate into sB in ascending order of the low-face pattern; the first cell to touch a lattice point stores
     if (c == 0) sb_accumulate<0>(T, myB, lb, first_mask); else if (c == 1) sb_accumulate<1>(T, myB, lb, first_mask); else sb_accumulate<2>(T, myB, lb, first_mask);
     __syncthreads();
-    // flush: private nodes with plain stores, shared nodes with one RED per DoF; constrained DoFs (dst = src) are
-    // skipped here and handled by a separate pass over the (few) bricks that have any
+    // flush: private nodes with plain stores, shared nodes with one RED per DoF; constrained DoFs are skipped (dst is
+    // zero there on entry; dst = src of MatrixFreeOperators::Base is one small kernel over the constrained list after
+    // this one -- inside this kernel it was a dependent global load per boundary brick, 7 % of the stall samples)
     {
       const uint32_t *le = reinterpret_cast<const uint32_t *>(I_cur);
       const uint16_t *ls = reinterpret_cast<const uint16_t *>(I_cur + SB_LIST * 4);
@@ -803,12 +809,12 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
       const int n_private = (int)le[405];
       constexpr int SUBB = 4;
 #pragma unroll 1
-      for (int k0 = 0; k0 < 16; k0 += SUBB) {
+      for (int k0 = 0; k0 < 12; k0 += SUBB) {
         uint32_t e[SUBB], sl[SUBB];
         double v[SUBB];
 #pragma unroll
         for (int k = 0; k < SUBB; ++k) {
-          const int j = min(j0 + 32 * (k0 + k), 404);
+          const int j = j0 + 32 * (k0 + k);
           e[k] = le[j]; sl[k] = ls[j];
         }
 #pragma unroll
@@ -817,17 +823,19 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
         for (int k = 0; k < SUBB; ++k) {
           const int j = j0 + 32 * (k0 + k);
           const bool cons = (e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u;
-          if (j < 405 && !cons) {
+          if (!cons) {
             if (j < n_private) dstd[e[k] & NODE_IDX_MASK] = v[k];
             else atomicAdd(dstd + (e[k] & NODE_IDX_MASK), v[k]);
           }
         }
       }
-      if (le[406] != 0) {
-#pragma unroll 1
-        for (int j = j0; j < 405; j += 32) {
-          const uint32_t e = le[j];
-          if ((e >> (NODE_FLAG_SHIFT + d0)) & 1u) { const uint32_t idx = (e & NODE_IDX_MASK) + d0; P.dst_u[idx] = (MODE == 2 || P.plain) ? 0.0 : P.src_u[idx]; }
+      if (j0 < 405 - 384) {
+        const int j = j0 + 384;
+        const uint32_t e = le[j];
+        const double v = sBd[ls[j]];
+        if (!((e >> (NODE_FLAG_SHIFT + d0)) & 1u)) {
+          if (j < n_private) dstd[e & NODE_IDX_MASK] = v;
+          else atomicAdd(dstd + (e & NODE_IDX_MASK), v);
         }
       }
     }
@@ -1429,6 +1437,8 @@ template <int DIM, int MODE, bool PERQ, bool STRUCT> static int launch_velocity_
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;
 }
+__global__ void copy_entries_kernel(double *dst, const double *src, const uint32_t *idx, int64_t n);
+
 template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
   constexpr size_t smem = sbk_smem_bytes(MODE);
@@ -1447,6 +1457,10 @@ template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, Level
     int grid = std::min(L.n_batches, resident);
     if (ctx->max_grid_blocks > 0) grid = std::min(grid, ctx->max_grid_blocks);
     velocity_sb_kernel<MODE, PERQ><<<grid, SBK_THREADS, smem, ctx->stream>>>(P, L.sb_lists, L.n_batches);
+    if (MODE != 2 && !P.plain && L.n_constrained_u) {      // unit diagonal on the constrained rows: dst = src
+      copy_entries_kernel<<<(unsigned)((L.n_constrained_u + 255) / 256), 256, 0, ctx->stream>>>(P.dst_u, P.src_u, L.constrained_u, L.n_constrained_u);
+      ctx->launches++;
+    }
   }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
