@@ -374,6 +374,27 @@ def main():
         line["cfg2_refinement5"] = {"workload": workload_name(5), "dofs": n5, "e2e_wall_s": t5, "e2e_mdofs": n5 / t5 / 1e6,
                                     "iterations": o5["iterations"]}
         h5.close()
+        # ---- BASELINE cfg 1: benchmarks/solcx, 2D Q2-Q1, global refinement 6 (general-batch 2D kernels) ----------------
+        from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
+        hier1 = synthetic.BoxHierarchy(2, 6)
+        avg1 = "harmonic average only viscosity"
+        eta1, rhs1, ps1 = benchmarks.solcx_problem(hier1, averaging=avg1)
+        h1 = StokesMatrixFreeHandler(2, device=local_rank)
+        h1.setup_dofs(hier1, "tangential")
+        h1.assemble(eta1, avg1, ps1)
+        h1.build_preconditioner()
+        h1.parameters.update({"Linear solver tolerance": 1e-7, "Pressure normalization": "surface"})
+        for _ in range(2):
+            _, o1 = h1.solve(rhs1)
+        t0 = time.time()
+        for _ in range(3):
+            _, o1 = h1.solve(rhs1)
+        t1 = (time.time() - t0) / 3
+        n1 = hier1.active.n_u + hier1.active.n_p
+        line["cfg1_solcx_refinement6"] = {"workload": "SolCx 2D unit square, viscosity jump 1e6, free slip, Q2-Q1, block GMG (GMRES(100), tol 1e-07), global refinement 6",
+                                          "dofs": n1, "e2e_wall_s": t1, "e2e_mdofs": n1 / t1 / 1e6, "iterations": o1["iterations"],
+                                          "pressure_normalization_adjustment": o1["pressure_normalization_adjustment"]}
+        h1.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_solve_throughput(args.ref_refinement, 1, 0).items()
                                 if k in ("value", "unit", "cores", "kind", "sample")}
