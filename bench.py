@@ -308,7 +308,7 @@ def main():
         solver_timings = None
         if not args.no_solver_timings:
             solver_timings = h.execute_solver_timings(rhs_np, n_timings=3, out=lambda *_: None)
-            solver_timings = {k: max_over_ranks(v) for k, v in solver_timings.items()}
+            solver_timings = {k: max_over_ranks(v) for k, v in sorted(solver_timings.items())}
 
     its = outs[-1]["iterations"]
     wall = t_dev / args.steps
