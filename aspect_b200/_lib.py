@@ -15,6 +15,7 @@ SMF_OK, SMF_ERR_INVALID, SMF_ERR_CUDA, SMF_ERR_UNSUPPORTED, SMF_NO_CONVERGENCE =
 SMF_ACTIVE = -1
 SMF_OPT_STRUCTURED_BRICKS, SMF_OPT_CUDA_GRAPHS, SMF_OPT_ORTHO_SINGLE_PASS, SMF_OPT_PIPELINED_KERNEL, SMF_OPT_MAX_GRID_BLOCKS = 0, 1, 2, 3, 4
 SMF_OPT_P2P_EXCHANGE = 5
+SMF_OPT_CURVED_SUMFAC = 6
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -29,7 +30,7 @@ class LevelMesh(ctypes.Structure):
                 ("cell_dofs_u", c_vp), ("cell_dofs_p", c_vp),
                 ("n_constrained_u", c_i64), ("constrained_u", c_vp),
                 ("n_constrained_p", c_i64), ("constrained_p", c_vp),
-                ("geometry", c_int), ("cell_size", c_vp)]
+                ("geometry", c_int), ("cell_size", c_vp), ("inverse_jacobians", c_vp), ("jxw", c_vp)]
 
 
 class Exchange(ctypes.Structure):

@@ -21,6 +21,22 @@ NSINKER_CENTERS = np.array([
     [1.8633519681e-01, 7.3565270739e-01, 1.1505317181e-01],
     [6.9865863058e-01, 3.5560411138e-01, 6.3830000658e-01],
     [9.0821050755e-01, 2.9400041480e-01, 2.6497158886e-01],
+    [3.7749399775e-01, 5.4162011554e-01, 9.2818150340e-03],
+    [8.5247022139e-01, 4.6701098395e-01, 5.3607231962e-02],
+    [9.7674759057e-01, 1.9675474344e-01, 8.5697294067e-01],
+    [1.4421375987e-01, 8.0066218823e-01, 7.2939761948e-01],
+    [9.8579064709e-01, 1.8340570954e-01, 4.9976021075e-01],
+    [4.6986202126e-01, 9.7099129947e-01, 4.5077026191e-01],
+    [9.5791877292e-02, 9.7408164664e-01, 3.9023506101e-01],
+    [6.8067035576e-01, 2.6669318800e-02, 2.3124107450e-01],
+    [4.6873909443e-01, 9.7960100555e-02, 4.1541002524e-01],
+    [7.9629418710e-01, 3.1640260216e-01, 7.7853444953e-01],
+    [8.2849331472e-01, 4.8714042059e-01, 3.6904878000e-01],
+    [6.0284549678e-01, 2.4264360789e-02, 8.1111178631e-01],
+    [3.5579259291e-01, 8.0610905439e-01, 2.7487712366e-01],
+    [8.5981739865e-01, 9.5101905612e-01, 7.7727618477e-01],
+    [6.8083745971e-01, 8.3518540665e-01, 9.6112961413e-01],
+    [7.0542474869e-01, 7.3751226102e-02, 5.3685709440e-01],
 ])
 
 
@@ -50,6 +66,15 @@ def _phi2_at_quad(dim):
     phi = n1
     for _ in range(dim - 1):
         phi = np.einsum("ab,cd->acbd", n1, phi).reshape(n1.shape[0] * phi.shape[0], -1)   # slowest index first
+    return phi                                                                             # [q lex][node lex]
+
+
+def _phi1_at_quad(dim):
+    x = _GX
+    n1 = np.stack([1 - x, x], axis=1)
+    phi = n1
+    for _ in range(dim - 1):
+        phi = np.einsum("ab,cd->acbd", n1, phi).reshape(n1.shape[0] * phi.shape[0], -1)
     return phi                                                                             # [q lex][node lex]
 
 
@@ -93,3 +118,49 @@ def solcx_problem(hier, averaging="harmonic average only viscosity"):
     f = assemble_rhs(act, rho_q, g)
     f[act.constrained_u("tangential").astype(np.int64)] = 0.0
     return eta_q, np.concatenate([f, np.zeros(act.n_p)]), pressure_scaling_box(act, solcx_material)
+
+
+# ---- benchmarks/nsinker_spherical_shell (BASELINE config 3) --------------------------------------------------------
+def shell_sinker_centers(inner=0.54, outer=1.0):
+    """nsinker_spherical_shell/nsinker.cc:284-296: centres rescaled from [0,1]^3 to [-1,1]^3; those outside the shell are dropped."""
+    p = 2.0 * NSINKER_CENTERS - 1.0
+    r = np.sqrt((p * p).sum(-1))
+    return p[(r >= inner) & (r <= outer)]
+
+
+def nsinker_shell_material(x, n_sinkers=5, viscosity_ratio=1e2, sinker_density=10.0, transition_zone_jump=100.0,
+                           delta=400.0, omega=0.2):
+    """nsinker_spherical_shell/nsinker.cc:57-71 (delta, omega: :204-205); gmg.prm: 5 sinkers, ratio 1e2, jump 100."""
+    centers = shell_sinker_centers()
+    assert n_sinkers <= len(centers)
+    chi = np.ones(x.shape[:-1])
+    for s in range(n_sinkers):
+        dist = np.sqrt(((x - centers[s]) ** 2).sum(-1))
+        chi *= 1.0 - np.exp(-delta * np.maximum(0.0, dist - omega / 2.0) ** 2)
+    s = np.sqrt(viscosity_ratio)
+    eta = (s - 1.0 / s) * (1.0 - chi) + 1.0 / s
+    eta = np.where(np.sqrt((x * x).sum(-1)) < 0.89583, eta * transition_zone_jump, eta)
+    return eta, sinker_density * (1.0 - chi)
+
+
+def pressure_scaling_shell(level, material):
+    """helper_functions.cc:253-348 (JxW-weighted log average at the cell midpoints) over SphericalShell::length_scale()
+    = 1e4 / (6336000 - 3481000) * (R1 - R0) (geometry_model/spherical_shell.cc:724-737)."""
+    xm, det = level.midpoint_geometry()
+    eta = material(xm)[0]
+    ref = np.exp((np.log(eta) * det).sum() / det.sum())
+    return float(ref / (1e4 / (6336000.0 - 3481000.0) * (level.R1 - level.R0)))
+
+
+def nsinker_shell_problem(hier, n_sinkers=5, viscosity_ratio=1e2, averaging="harmonic average"):
+    """(viscosity_q, force_q, pressure_scaling) of benchmarks/nsinker_spherical_shell/gmg.prm on a ShellHierarchy:
+    force_q = rho * g at the quadrature points with `Gravity model = radial constant`, magnitude 1, pointing inwards
+    (source/gravity_model/radial.cc); the right-hand side itself is integrated on the device (smf_assemble_rhs)."""
+    act = hier.active
+    x = act.quadrature_points()
+    material = lambda y: nsinker_shell_material(y, n_sinkers, viscosity_ratio)
+    eta_q, rho_q = material(x)
+    if averaging != "none" and not averaging.endswith("only viscosity"):
+        rho_q = average_viscosity(rho_q, averaging)
+    g = -x / np.sqrt((x * x).sum(-1, keepdims=True))
+    return eta_q, rho_q[..., None] * g, pressure_scaling_shell(act, material)

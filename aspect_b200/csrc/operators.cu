@@ -1013,6 +1013,7 @@ struct DiagParams {
   const double *eta; int n_eta;     // lane-transposed table [cell/32][n_eta][32]
   double ih[3]; double vol, ps; int compressible;
   double *diag_A, *diag_M;
+  const double *geo;                // curved cells: [q][dim*dim + 1][n_cells] (NULL = Cartesian)
 };
 __device__ __forceinline__ double q2v(int q, int i)
 { return q == 1 ? (i == 1 ? 1.0 : 0.0) : (i == 1 ? NB : ((i == 0) == (q == 0) ? NA : NC)); }
@@ -1035,10 +1036,19 @@ template <int DIM> __global__ void diag_kernel(const DiagParams P)
   double a[3] = {0, 0, 0};
   for (int q = 0; q < NN; ++q) {
     int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
-    const double coef = qweight<DIM>(q) * P.vol * P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)];
+    const double *gq = P.geo ? P.geo + (int64_t)q * (DIM * DIM + 1) * P.n_cells + cell : nullptr;
+    const double JxW = gq ? gq[(int64_t)(DIM * DIM) * P.n_cells] : qweight<DIM>(q) * P.vol;
+    const double coef = JxW * P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)];
+    double ref[DIM];
+    for (int r = 0; r < DIM; ++r) {
+      double g = 1.0;
+      for (int e = 0; e < DIM; ++e) g *= (e == r) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
+      ref[r] = g;
+    }
     for (int d = 0; d < DIM; ++d) {
-      double g = P.ih[d];
-      for (int e = 0; e < DIM; ++e) g *= (e == d) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
+      double g = 0.0;
+      if (gq) { for (int r = 0; r < DIM; ++r) g = fma(ref[r], gq[(int64_t)(r * DIM + d) * P.n_cells], g); }
+      else g = ref[d] * P.ih[d];
       a[d] += coef * g * g;
     }
   }
@@ -1059,7 +1069,8 @@ template <int DIM> __global__ void diag_kernel(const DiagParams P)
       int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
       double v = 1.0;
       for (int d = 0; d < DIM; ++d) v *= q1v(qd[d], jd[d]);
-      m += qweight<DIM>(q) * P.vol * (P.ps * P.ps / P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)]) * v * v;
+      const double JxW = P.geo ? P.geo[((int64_t)q * (DIM * DIM + 1) + DIM * DIM) * P.n_cells + cell] : qweight<DIM>(q) * P.vol;
+      m += JxW * (P.ps * P.ps / P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)]) * v * v;
     }
     const uint32_t ep = P.cell_nodes_p[cell * NP + i];
     if (!(ep >> 31)) atomicAdd(P.diag_M + (ep & NODE_IDX_MASK), m);
@@ -1494,7 +1505,8 @@ struct GeneralParams {
   double *dst_u, *dst_p;
   const double *eta; int n_eta;
   double ih[3], vol, ps;
-  int mode;                 // 0 = A block, 1 = Stokes operator
+  int mode;                 // 0 = A block, 1 = Stokes operator, 2 = B^T
+  const double *geo;        // curved cells: [q][dim*dim + 1][n_cells] inverse Jacobian (d xi_r / d x_d, r-major) and JxW; NULL = Cartesian
   int compressible, newton, symmetrize, average, dilation, plain;
   const double *eps, *deta, *detadp, *dil_lhs, *ddil, *ddildp;     // [cell][q][n_sym] / [cell][q]
 };
@@ -1525,13 +1537,39 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
     const uint32_t idx = e & NODE_IDX_MASK;
     for (int c = 0; c < DIM; ++c) {
       const bool cons = ((e >> (NODE_FLAG_SHIFT + c)) & 1u) && !P.plain;
-      u[c][i] = cons ? 0.0 : P.src_u[idx + c];
+      u[c][i] = (cons || P.mode == 2) ? 0.0 : P.src_u[idx + c];
       T[c][i] = 0.0;
     }
   }
+  // inverse Jacobian and JxW at quadrature point q (Cartesian: diag(1/h), w_q vol)
+  auto geometry = [&](int q, double (&Ji)[DIM][DIM], double &JxW) {
+    if (P.geo) {
+      const double *g = P.geo + (int64_t)q * (DIM * DIM + 1) * P.n_cells + cell;
+      for (int r = 0; r < DIM; ++r) for (int d = 0; d < DIM; ++d) Ji[r][d] = g[(int64_t)(r * DIM + d) * P.n_cells];
+      JxW = g[(int64_t)(DIM * DIM) * P.n_cells];
+    } else {
+      for (int r = 0; r < DIM; ++r) for (int d = 0; d < DIM; ++d) Ji[r][d] = r == d ? P.ih[d] : 0.0;
+      JxW = qweight<DIM>(q) * P.vol;
+    }
+  };
+  // real-space gradient of the scalar Q2 shape function i at point q
+  auto shape_grad = [&](const int (&qd)[3], int i, const double (&Ji)[DIM][DIM], double (&dphi)[DIM]) {
+    int id[3] = {i % 3, (i / 3) % 3, DIM == 3 ? i / 9 : 0};
+    double ref[DIM];
+    for (int r = 0; r < DIM; ++r) {
+      double v = 1.0;
+      for (int e = 0; e < DIM; ++e) v *= (e == r) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
+      ref[r] = v;
+    }
+    for (int d = 0; d < DIM; ++d) {
+      double v = 0.0;
+      for (int r = 0; r < DIM; ++r) v = fma(ref[r], Ji[r][d], v);
+      dphi[d] = v;
+    }
+  };
   for (int a = 0; a < NP; ++a) {
     pn[a] = 0.0; Tp[a] = 0.0;
-    if (P.mode == 1) {
+    if (P.mode != 0) {
       const uint32_t e = P.cell_nodes_p[cell * NP + a];
       pn[a] = ((e >> 31) && !P.plain) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
     }
@@ -1539,24 +1577,20 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
   const bool deviatoric = P.compressible || P.dilation;
   const bool newton = P.mode == 1 && P.newton;
   // symmetric gradient, divergence and pressure at quadrature point q
-  auto evaluate = [&](int q, double (&sg)[DIM][DIM], double &div, double &valp) {
+  auto evaluate = [&](int q, const double (&Ji)[DIM][DIM], double (&sg)[DIM][DIM], double &div, double &valp) {
     int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
     double g[DIM][DIM];
     for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) g[c][d] = 0.0;
-    for (int i = 0; i < NN; ++i) {
-      int id[3] = {i % 3, (i / 3) % 3, DIM == 3 ? i / 9 : 0};
-      double dphi[DIM];
-      for (int d = 0; d < DIM; ++d) {
-        double v = P.ih[d];
-        for (int e = 0; e < DIM; ++e) v *= (e == d) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
-        dphi[d] = v;
+    if (P.mode != 2)
+      for (int i = 0; i < NN; ++i) {
+        double dphi[DIM];
+        shape_grad(qd, i, Ji, dphi);
+        for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) g[c][d] = fma(u[c][i], dphi[d], g[c][d]);
       }
-      for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) g[c][d] = fma(u[c][i], dphi[d], g[c][d]);
-    }
     div = 0.0;
     for (int c = 0; c < DIM; ++c) { div += g[c][c]; for (int d = 0; d < DIM; ++d) sg[c][d] = 0.5 * (g[c][d] + g[d][c]); }
     valp = 0.0;
-    if (P.mode == 1)
+    if (P.mode != 0)
       for (int a = 0; a < NP; ++a) {
         int ad[3] = {a % 2, (a / 2) % 2, DIM == 3 ? a / 4 : 0};
         double v = pn[a];
@@ -1568,26 +1602,27 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
   double deta_deps_times_sym_grad_u = 0.0, deta_dp_times_p = 0.0, eps_times_sym_grad_u_JxW = 0.0, theta_times_div_u_JxW = 0.0;
   if (newton && P.average)
     for (int q = 0; q < NN; ++q) {
-      double sg[DIM][DIM], div, valp;
-      evaluate(q, sg, div, valp);
+      double sg[DIM][DIM], div, valp, Ji[DIM][DIM], JxW;
+      geometry(q, Ji, JxW);
+      evaluate(q, Ji, sg, div, valp);
       const int64_t tq = cell * NN + q;
       deta_deps_times_sym_grad_u += sym_contract<DIM>(P.deta + tq * NS, sg);
       deta_dp_times_p += P.detadp[tq] * valp;
       if (P.symmetrize) {
-        const double JxW = qweight<DIM>(q) * P.vol;
         eps_times_sym_grad_u_JxW += sym_contract<DIM>(P.eps + tq * NS, sg) * JxW;
         if (deviatoric) theta_times_div_u_JxW += sym_trace<DIM>(P.eps + tq * NS) * div * JxW;
       }
     }
   for (int q = 0; q < NN; ++q) {
-    double sg[DIM][DIM], div_u, val_p;
-    evaluate(q, sg, div_u, val_p);
+    double sg[DIM][DIM], div_u, val_p, Ji[DIM][DIM], JxW;
+    geometry(q, Ji, JxW);
+    evaluate(q, Ji, sg, div_u, val_p);
     const int64_t tq = cell * NN + q;
-    const double JxW = qweight<DIM>(q) * P.vol;
-    const double viscosity_x_2 = 2.0 * P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)];
+    const double viscosity_x_2 = P.mode == 2 ? 0.0 : 2.0 * P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)];
     double pressure_terms = -P.ps * div_u;
     double vt[DIM][DIM];
     for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) vt[c][d] = viscosity_x_2 * sg[c][d];
+    if (P.mode == 2) for (int d = 0; d < DIM; ++d) vt[d][d] -= P.ps * val_p;
     if (P.mode == 1) {
       if (P.dilation) pressure_terms -= P.ps * P.ps * P.dil_lhs[tq] * val_p;
       for (int d = 0; d < DIM; ++d) vt[d][d] -= P.ps * val_p;
@@ -1624,14 +1659,10 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
     }
     // submit_symmetric_gradient / submit_value, integrate
     int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
+    for (int c = 0; c < DIM; ++c) for (int d = 0; d < DIM; ++d) vt[c][d] *= JxW;
     for (int i = 0; i < NN; ++i) {
-      int id[3] = {i % 3, (i / 3) % 3, DIM == 3 ? i / 9 : 0};
       double dphi[DIM];
-      for (int d = 0; d < DIM; ++d) {
-        double v = P.ih[d] * JxW;
-        for (int e = 0; e < DIM; ++e) v *= (e == d) ? q2d(qd[e], id[e]) : q2v(qd[e], id[e]);
-        dphi[d] = v;
-      }
+      shape_grad(qd, i, Ji, dphi);
       for (int c = 0; c < DIM; ++c) {
         double acc = T[c][i];
         for (int d = 0; d < DIM; ++d) acc = fma(vt[c][d], dphi[d], acc);
@@ -1659,6 +1690,172 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
       if (!(e >> 31)) atomicAdd(P.dst_p + (e & NODE_IDX_MASK), Tp[a]);
     }
 }
+
+// ---- curved cells (geometry = 1): sum factorisation with per-quadrature-point Jacobians ------------------------
+// BASELINE config 3 (spherical shell, MappingQ(4)): the inverse Jacobian is a full matrix that changes from point to point,
+// so all components of the gradient meet at every quadrature point (grad_x u = grad_xi u J^-1) and the component-per-warp
+// split of the Cartesian kernels does not apply.  One thread per cell: the values of the three components at the 27 Gauss
+// points live in the thread's own column of shared memory (lane-fastest, conflict-free, no barriers), the 81 accumulated
+// test-side values in registers; per point 4 small (3 x 3) contractions: reference gradient by collocation
+// (D'/a along the three lines through the point), J^-1, the stress, J^-T, and the transposed collocation derivative.
+// HBM per cell: 27 x 10 doubles of geometry (2,160 B, coalesced: consecutive threads read consecutive doubles) next to
+// the ~400 B of vector data, i.e. the kernel is bound by the geometry stream (G term).  The node lists of
+// unstructured meshes have no collision-free rounds, results go to global memory with one RED per DoF.
+constexpr int CV_THREADS = 64;
+// collocation derivative at Gauss point i from the values at the Gauss points j of the line, per unit reference length
+__host__ __device__ constexpr double dpc(int i, int j)
+{
+  return (i == 0 ? (j == 0 ? -1.5 : (j == 1 ? 2.0 : -0.5)) : (i == 1 ? (j == 0 ? -0.5 : (j == 1 ? 0.0 : 0.5)) : (j == 0 ? 0.5 : (j == 1 ? -2.0 : 1.5))))
+         / HOST_GAUSS_A;
+}
+template <int MODE, bool PERQ>
+__global__ void __launch_bounds__(CV_THREADS) curved_cell_kernel(const GeneralParams P)
+{
+  static_assert(MODE >= 0 && MODE <= 2, "A block, Stokes operator, B^T");
+  constexpr int NN = 27, NP = 8, G = 10;
+  extern __shared__ __align__(16) double cv_smem[];
+  const int64_t cell = (int64_t)blockIdx.x * CV_THREADS + threadIdx.x;
+  if (cell >= P.n_cells) return;                      // (no barriers below: every thread works in its own column)
+  double *U = cv_smem + threadIdx.x;                  // U[(c * 27 + q) * CV_THREADS]
+  if (MODE != 2) {
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      double v[NN];
+#pragma unroll
+      for (int i = 0; i < NN; ++i) {
+        const uint32_t e = P.cell_nodes_u[cell * NN + i];
+        const bool cons = ((e >> (NODE_FLAG_SHIFT + c)) & 1u) && !P.plain;
+        v[i] = cons ? 0.0 : P.src_u[(e & NODE_IDX_MASK) + c];
+      }
+      interp_all<3>(v);
+#pragma unroll
+      for (int q = 0; q < NN; ++q) U[(c * NN + q) * CV_THREADS] = v[q];
+    }
+  }
+  double pn[NP], Tp[NP];
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    pn[a] = 0.0; Tp[a] = 0.0;
+    if (MODE != 0) {
+      const uint32_t e = P.cell_nodes_p[cell * NP + a];
+      pn[a] = ((e >> 31) && !P.plain) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
+    }
+  }
+  double T[3][NN];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < NN; ++i) T[c][i] = 0.0;
+  const double *geo = P.geo + cell;
+  const double *etab = P.eta + (cell / SUB) * P.n_eta * SUB + (cell % SUB);
+  const double eta_cell = (MODE != 2 && !PERQ) ? etab[0] : 1.0;
+#pragma unroll
+  for (int q = 0; q < NN; ++q) {
+    const int qd[3] = {q % 3, (q / 3) % 3, q / 9};
+    double Ji[3][3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ji[k / 3][k % 3] = geo[(int64_t)(q * G + k) * P.n_cells];
+    const double JxW = geo[(int64_t)(q * G + 9) * P.n_cells];
+    double S[3][3];                                   // stress times JxW
+    double div = 0.0;
+    if (MODE != 2) {
+      double Gx[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double gh[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int st = stride3(r), base = q - qd[r] * st;
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (dpc(qd[r], j) != 0.0) acc = fma(dpc(qd[r], j), U[(c * NN + base + j * st) * CV_THREADS], acc);
+          gh[r] = acc;
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Gx[c][d] = gh[0] * Ji[0][d] + gh[1] * Ji[1][d] + gh[2] * Ji[2][d];
+      }
+      div = Gx[0][0] + Gx[1][1] + Gx[2][2];
+      const double ew = (PERQ ? etab[q * SUB] : eta_cell) * JxW;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) S[c][d] = ew * (Gx[c][d] + Gx[d][c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) S[c][d] = 0.0;
+    }
+    if (MODE != 0) {
+      double valp = 0.0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) valp = fma(pn[a], q1v(qd[0], a & 1) * q1v(qd[1], (a >> 1) & 1) * q1v(qd[2], a >> 2), valp);
+      const double pw = P.ps * valp * JxW;
+      S[0][0] -= pw; S[1][1] -= pw; S[2][2] -= pw;
+      if (MODE == 1) {
+        const double pt = -P.ps * div * JxW;
+#pragma unroll
+        for (int a = 0; a < NP; ++a) Tp[a] = fma(pt, q1v(qd[0], a & 1) * q1v(qd[1], (a >> 1) & 1) * q1v(qd[2], a >> 2), Tp[a]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double sh = S[c][0] * Ji[r][0] + S[c][1] * Ji[r][1] + S[c][2] * Ji[r][2];
+        const int st = stride3(r), base = q - qd[r] * st;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (dpc(qd[r], j) != 0.0) T[c][base + j * st] = fma(dpc(qd[r], j), sh, T[c][base + j * st]);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    interpT_all<3>(T[c]);
+#pragma unroll
+    for (int i = 0; i < NN; ++i) {
+      const uint32_t e = P.cell_nodes_u[cell * NN + i];
+      if (!((e >> (NODE_FLAG_SHIFT + c)) & 1u)) atomicAdd(P.dst_u + (e & NODE_IDX_MASK) + c, T[c][i]);
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      const uint32_t e = P.cell_nodes_p[cell * NP + a];
+      if (!(e >> 31)) atomicAdd(P.dst_p + (e & NODE_IDX_MASK), Tp[a]);
+    }
+  }
+}
+
+// pressure mass matrix on curved cells (or any mesh without batch structure): one thread per cell
+template <int DIM, bool PERQ>
+__global__ void __launch_bounds__(128) curved_mass_kernel(const GeneralParams P)
+{
+  constexpr int NN = nn<DIM>(), NP = np<DIM>(), G = DIM * DIM + 1;
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= P.n_cells) return;
+  double pn[NP], pq[NN], out[NP];
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    const uint32_t e = P.cell_nodes_p[cell * NP + a];
+    pn[a] = (e >> 31) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
+  }
+  q1_to_quad<DIM>(pn, pq);
+  const double *etab = P.eta + (cell / SUB) * P.n_eta * SUB + (cell % SUB);
+  const double ps2 = P.ps * P.ps;
+#pragma unroll
+  for (int q = 0; q < NN; ++q) {
+    const double JxW = P.geo ? P.geo[(int64_t)(q * G + DIM * DIM) * P.n_cells + cell] : qweight<DIM>(q) * P.vol;
+    pq[q] *= JxW * (ps2 / etab[PERQ ? q * SUB : 0]);
+  }
+  quad_to_q1T<DIM>(pq, out);
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    const uint32_t e = P.cell_nodes_p[cell * NP + a];
+    if (!(e >> 31)) atomicAdd(P.dst_p + (e & NODE_IDX_MASK), out[a]);
+  }
+}
 // dst[c] = src[c] on constrained DoFs (unit diagonal of MatrixFreeOperators::Base)
 __global__ void copy_entries_kernel(double *dst, const double *src, const uint32_t *idx, int64_t n)
 {
@@ -1667,7 +1864,7 @@ __global__ void copy_entries_kernel(double *dst, const double *src, const uint32
 }
 
 static bool needs_general(const LevelDev &L, int mode)
-{ return L.compressible || L.nd.dilation || (mode == 1 && L.nd.newton); }
+{ return L.geo || L.compressible || L.nd.dilation || (mode == 1 && L.nd.newton); }
 
 // dst must be zeroed by the caller
 static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool plain)
@@ -1678,17 +1875,29 @@ static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, do
   P.eta = L.eta; P.n_eta = L.n_eta;
   double vol = 1.0;
   for (int d = 0; d < L.dim; ++d) { P.ih[d] = 1.0 / L.h[d]; vol *= L.h[d]; }
-  P.vol = vol; P.ps = L.ps; P.mode = mode; P.plain = plain ? 1 : 0;
+  P.vol = vol; P.ps = L.ps; P.mode = mode; P.plain = plain ? 1 : 0; P.geo = L.geo;
   P.compressible = L.compressible; P.newton = L.nd.newton; P.symmetrize = L.nd.symmetrize; P.average = L.nd.average; P.dilation = L.nd.dilation;
   P.eps = L.nd.eps; P.deta = L.nd.deta; P.detadp = L.nd.detadp; P.dil_lhs = L.nd.dil_lhs; P.ddil = L.nd.ddil; P.ddildp = L.nd.ddildp;
+  const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
+  // curved cells without Newton / compressible / dilation terms: the sum-factorised kernel
+  const bool fast = L.geo && L.dim == 3 && ctx->use_curved_fast && !L.compressible && !L.nd.dilation && !(mode == 1 && L.nd.newton);
   {
-    ProfScope prof(ctx, mode == 1 ? B_STOKES : B_A_COARSE);
-    const unsigned grid = (unsigned)((L.n_cells + 63) / 64);
-    if (L.dim == 3) general_cell_kernel<3><<<grid, 64, 0, ctx->stream>>>(P);
-    else general_cell_kernel<2><<<grid, 64, 0, ctx->stream>>>(P);
+    ProfScope prof(ctx, mode == 1 ? B_STOKES : (mode == 2 ? B_BT : (fine ? B_A_FINE : B_A_COARSE)));
+    if (fast) {
+      const unsigned grid = (unsigned)((L.n_cells + CV_THREADS - 1) / CV_THREADS);
+      const size_t smem = sizeof(double) * 81 * CV_THREADS;
+      const bool perq = L.n_eta != 1;
+      if (mode == 0) { if (perq) curved_cell_kernel<0, true><<<grid, CV_THREADS, smem, ctx->stream>>>(P); else curved_cell_kernel<0, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P); }
+      else if (mode == 1) { if (perq) curved_cell_kernel<1, true><<<grid, CV_THREADS, smem, ctx->stream>>>(P); else curved_cell_kernel<1, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P); }
+      else curved_cell_kernel<2, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P);
+    } else {
+      const unsigned grid = (unsigned)((L.n_cells + 63) / 64);
+      if (L.dim == 3) general_cell_kernel<3><<<grid, 64, 0, ctx->stream>>>(P);
+      else general_cell_kernel<2><<<grid, 64, 0, ctx->stream>>>(P);
+    }
   }
   ctx->launches++;
-  if (!plain) {
+  if (!plain && mode != 2) {
     if (L.n_constrained_u) {
       copy_entries_kernel<<<(unsigned)((L.n_constrained_u + 255) / 256), 256, 0, ctx->stream>>>(dst_u, src_u, L.constrained_u, L.n_constrained_u);
       ctx->launches++;
@@ -1706,7 +1915,7 @@ static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, do
 // ---- Stokes right-hand side on the device -------------------------------------------------------
 // f_i = sum_q force_q . phi_i JxW_q with force = density * gravity from the plugins (assemblers/stokes.cc:387-396),
 // one thread per (cell, node); constrained rows receive nothing (the reference condenses them away, assembly.cc:761-889)
-template <int DIM> __global__ void rhs_kernel(const double *force_q, const uint32_t *cell_nodes_u, double *rhs_u, int64_t n_cells, double vol)
+template <int DIM> __global__ void rhs_kernel(const double *force_q, const uint32_t *cell_nodes_u, double *rhs_u, int64_t n_cells, double vol, const double *geo)
 {
   constexpr int NN = nn<DIM>();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1718,7 +1927,7 @@ template <int DIM> __global__ void rhs_kernel(const double *force_q, const uint3
   for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
   for (int q = 0; q < NN; ++q) {
     int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
-    double phi = qweight<DIM>(q) * vol;
+    double phi = geo ? geo[((int64_t)q * (DIM * DIM + 1) + DIM * DIM) * n_cells + cell] : qweight<DIM>(q) * vol;
     for (int d = 0; d < DIM; ++d) phi *= q2v(qd[d], id[d]);
     const double *f = force_q + (cell * NN + q) * DIM;
     for (int c = 0; c < DIM; ++c) acc[c] = fma(f[c], phi, acc[c]);
@@ -1736,8 +1945,8 @@ int launch_rhs(smf_ctx *ctx, LevelDev &L, const double *force_q_dev, double *rhs
   const int NN = L.dim == 3 ? 27 : 9;
   const int64_t nt = L.n_cells * NN;
   SMF_CUDA(cudaMemsetAsync(rhs_u, 0, sizeof(double) * L.n_u, ctx->stream));
-  if (L.dim == 3) rhs_kernel<3><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(force_q_dev, L.cell_nodes_u, rhs_u, L.n_cells, vol);
-  else rhs_kernel<2><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(force_q_dev, L.cell_nodes_u, rhs_u, L.n_cells, vol);
+  if (L.dim == 3) rhs_kernel<3><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(force_q_dev, L.cell_nodes_u, rhs_u, L.n_cells, vol, L.geo);
+  else rhs_kernel<2><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(force_q_dev, L.cell_nodes_u, rhs_u, L.n_cells, vol, L.geo);
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
   return exchange_add(ctx, L.ex_u, rhs_u);        // compress(add) of the per-rank partial sums
@@ -1747,7 +1956,7 @@ static int check_level(smf_ctx *ctx, const LevelDev &L)
 {
   if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "level mesh not set (smf_set_level)");
   if (!L.has_cell_data) return ctx->fail(SMF_ERR_INVALID, "cell data not set (smf_set_cell_data)");
-  if (!L.safe_rounds) return ctx->fail(SMF_ERR_UNSUPPORTED, "cell batches with aliasing scatter rounds (unstructured orientation) not implemented");
+  if (!L.safe_rounds && !L.geo) return ctx->fail(SMF_ERR_UNSUPPORTED, "cell batches with aliasing scatter rounds (unstructured orientation) need geometry = 1 (the per-cell kernels)");
   return SMF_OK;
 }
 
@@ -1780,7 +1989,8 @@ int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_
   CellParams P = make_params(L);
   P.src_p = src_p; P.dst_u = dst_u;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
-  if (int e = L.dim == 3 ? launch_velocity<3, 2>(ctx, L, P) : launch_velocity<2, 2>(ctx, L, P)) return e;
+  if (L.geo) { if (int e = launch_general(ctx, L, 2, dst_u, nullptr, nullptr, src_p, false)) return e; }
+  else if (int e = L.dim == 3 ? launch_velocity<3, 2>(ctx, L, P) : launch_velocity<2, 2>(ctx, L, P)) return e;
   return exchange_add(ctx, L.ex_u, dst_u);
 }
 int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero)
@@ -1791,7 +2001,18 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src,
   if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
   const size_t smem = (size_t)MASS_WARPS * 2 * L.max_nodes_p * sizeof(double);
   const unsigned grid = (unsigned)((L.n_batches + MASS_WARPS - 1) / MASS_WARPS);
-  if (L.dim == 3 && L.structured && L.sb_lists && ctx->use_pipelined) {
+  if (L.geo) {
+    ProfScope prof(ctx, B_MASS);
+    GeneralParams Q{};
+    Q.n_cells = L.n_cells; Q.cell_nodes_p = L.cell_nodes_p; Q.src_p = src; Q.dst_p = dst; Q.eta = L.eta; Q.n_eta = L.n_eta; Q.ps = L.ps; Q.geo = L.geo;
+    const unsigned g = (unsigned)((L.n_cells + 127) / 128);
+    if (L.dim == 3) { if (L.n_eta == 1) curved_mass_kernel<3, false><<<g, 128, 0, ctx->stream>>>(Q); else curved_mass_kernel<3, true><<<g, 128, 0, ctx->stream>>>(Q); }
+    else { if (L.n_eta == 1) curved_mass_kernel<2, false><<<g, 128, 0, ctx->stream>>>(Q); else curved_mass_kernel<2, true><<<g, 128, 0, ctx->stream>>>(Q); }
+    if (L.n_constrained_p) {
+      copy_entries_kernel<<<(unsigned)((L.n_constrained_p + 255) / 256), 256, 0, ctx->stream>>>(dst, src, L.constrained_p, L.n_constrained_p);
+      ctx->launches++;
+    }
+  } else if (L.dim == 3 && L.structured && L.sb_lists && ctx->use_pipelined) {
     ProfScope prof(ctx, B_MASS);
     const unsigned g = (unsigned)((L.n_batches + MSB_WARPS - 1) / MSB_WARPS);
     if (L.n_eta == 1) mass_sb_kernel<false><<<g, 32 * MSB_WARPS, 0, ctx->stream>>>(P, L.sb_lists, L.n_batches);
@@ -1819,7 +2040,7 @@ int launch_diag(smf_ctx *ctx, LevelDev &L)
   double vol = 1.0;
   for (int d = 0; d < L.dim; ++d) { P.ih[d] = 1.0 / L.h[d]; vol *= L.h[d]; }
   P.vol = vol; P.ps = L.ps; P.compressible = L.compressible || L.nd.dilation;   // deviatoric A block (:999-1005)
-  P.diag_A = L.dinv_A; P.diag_M = L.dinv_M;
+  P.diag_A = L.dinv_A; P.diag_M = L.dinv_M; P.geo = L.geo;
   SMF_CUDA(cudaMemsetAsync(L.dinv_A, 0, sizeof(double) * L.n_u, ctx->stream));
   SMF_CUDA(cudaMemsetAsync(L.dinv_M, 0, sizeof(double) * L.n_p, ctx->stream));
   const int NN = L.dim == 3 ? 27 : 9;

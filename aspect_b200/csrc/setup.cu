@@ -29,7 +29,7 @@ static void free_level(LevelDev &L)
 {
   cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.sb_lists); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
   cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
-  cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M);
+  cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M); cudaFree(L.geo);
   cudaFree(L.nd.eps); cudaFree(L.nd.deta); cudaFree(L.nd.detadp); cudaFree(L.nd.dil_lhs); cudaFree(L.nd.ddil); cudaFree(L.nd.ddildp);
   free_exchange(L.ex_u); free_exchange(L.ex_p);
   L = LevelDev();
@@ -269,6 +269,7 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   else if (option == SMF_OPT_CUDA_GRAPHS) { ctx->use_graphs = value ? 1 : 0; ctx->graph_A_stale = ctx->graph_S_stale = true; }
   else if (option == SMF_OPT_ORTHO_SINGLE_PASS) ctx->ortho_single_pass = value ? 1 : 0;
   else if (option == SMF_OPT_PIPELINED_KERNEL) ctx->use_pipelined = value ? 1 : 0;
+  else if (option == SMF_OPT_CURVED_SUMFAC) ctx->use_curved_fast = value ? 1 : 0;
   else if (option == SMF_OPT_MAX_GRID_BLOCKS) ctx->max_grid_blocks = value > 0 ? value : 0;
   else if (option == SMF_OPT_P2P_EXCHANGE) ctx->use_p2p = value ? 1 : 0;
   else return ctx->fail(SMF_ERR_INVALID, "unknown option");
@@ -289,8 +290,10 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
 {
   if (!ctx || !m) return SMF_ERR_INVALID;
   if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
-  if (m->geometry != 0) return ctx->fail(SMF_ERR_UNSUPPORTED, "only Cartesian level geometry (geometry = 0) is implemented");
-  if (m->n_cells < 1 || !m->cell_dofs_u || !m->cell_dofs_p || !m->cell_size) return ctx->fail(SMF_ERR_INVALID, "incomplete level mesh");
+  if (m->geometry != 0 && m->geometry != 1) return ctx->fail(SMF_ERR_UNSUPPORTED, "level geometry: 0 (Cartesian) or 1 (per-quadrature-point inverse Jacobians and JxW)");
+  if (m->n_cells < 1 || !m->cell_dofs_u || !m->cell_dofs_p) return ctx->fail(SMF_ERR_INVALID, "incomplete level mesh");
+  if (m->geometry == 0 && !m->cell_size) return ctx->fail(SMF_ERR_INVALID, "Cartesian level mesh without cell_size");
+  if (m->geometry == 1 && (!m->inverse_jacobians || !m->jxw)) return ctx->fail(SMF_ERR_INVALID, "curved level mesh without inverse_jacobians / jxw");
   if (m->n_dofs_u >= (int64_t)NODE_IDX_MASK || m->n_dofs_p >= (int64_t)NODE_IDX_MASK)
     return ctx->fail(SMF_ERR_UNSUPPORTED, "more than 2^29 local DoFs per rank");
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
@@ -299,7 +302,21 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   free_level(L);
   const int dim = ctx->cfg.dim, NN = dim == 3 ? 27 : 9, NP = dim == 3 ? 8 : 4;
   L.dim = dim; L.n_cells = m->n_cells; L.n_u = m->n_dofs_u; L.n_p = m->n_dofs_p;
-  for (int d = 0; d < dim; ++d) L.h[d] = m->cell_size[d];
+  for (int d = 0; d < dim; ++d) L.h[d] = m->cell_size ? m->cell_size[d] : 1.0;
+  if (m->geometry == 1) {
+    // [cell][q][r][d], [cell][q]  ->  [q][dim*dim + 1][cell]: consecutive cells (one per thread) read consecutive doubles
+    const int D2 = dim * dim, G = D2 + 1;
+    std::vector<double> geo((size_t)NN * G * L.n_cells);
+    for (int64_t cell = 0; cell < L.n_cells; ++cell)
+      for (int q = 0; q < NN; ++q) {
+        const double *ji = m->inverse_jacobians + ((size_t)cell * NN + q) * D2;
+        for (int k = 0; k < D2; ++k) geo[((size_t)q * G + k) * L.n_cells + cell] = ji[k];
+        const double w = m->jxw[(size_t)cell * NN + q];
+        if (!(w > 0.0)) return ctx->fail(SMF_ERR_INVALID, "jxw must be positive (inverted cell?)");
+        geo[((size_t)q * G + D2) * L.n_cells + cell] = w;
+      }
+    if (int e = upload(ctx, &L.geo, geo, &L.bytes)) return e;
+  }
 
   // constraint bitmaps
   std::vector<uint8_t> cu((size_t)L.n_u, 0), cp((size_t)L.n_p, 0);
@@ -542,7 +559,7 @@ __global__ void transpose_eta_kernel(const double *raw, double *out, int64_t n_c
 // interpolate_to_mg of the DGQ0 vector = mean of the 2^dim children, level by level (local_smoothing.cc:220-226).
 // One thread per cell; per-block extrema are finished on the host.
 __host__ __device__ constexpr double gw1(int i) { return i == 1 ? 8.0 / 18.0 : 5.0 / 18.0; }      // 3-point Gauss weights on [0,1]
-__global__ void k_average_viscosity(const double *raw_q, int64_t n_cells, int nq, int op, double *active_raw, double *dg0,
+__global__ void k_average_viscosity(const double *raw_q, int64_t n_cells, int nq, int op, const double *geo, double *active_raw, double *dg0,
                                     double *blk_min, double *blk_max)
 {
   __shared__ double s_min[256], s_max[256];
@@ -558,14 +575,17 @@ __global__ void k_average_viscosity(const double *raw_q, int64_t n_cells, int nq
       for (int q = 0; q < nq; ++q) { zero = zero || v[q] == 0.0; avg += 1.0 / v[q]; }
       avg = zero ? 0.0 : 1.0 / (avg / nq);
     } else if (op == 3) { avg = 1.0; for (int q = 0; q < nq; ++q) avg *= pow(v[q], 1.0 / nq); }
-    double proj = 0.0;
+    double proj = 0.0, wsum = 0.0;
     for (int q = 0; q < nq; ++q) {
       const double o = op == 0 ? v[q] : avg;
-      const double w = dim == 3 ? gw1(q % 3) * gw1((q / 3) % 3) * gw1(q / 9) : gw1(q % 3) * gw1(q / 3);
-      proj += w * o;                                   // (the reference-cell weights sum to 1)
+      // Cartesian: reference-cell weights; curved cells: JxW of the cell (entry dim*dim of the geometry table)
+      const double w = geo ? geo[((int64_t)q * (dim * dim + 1) + dim * dim) * n_cells + cell]
+                           : (dim == 3 ? gw1(q % 3) * gw1((q / 3) % 3) * gw1(q / 9) : gw1(q % 3) * gw1(q / 3));
+      proj += w * o; wsum += w;
       vmin = fmin(vmin, o); vmax = fmax(vmax, o);
       if (op == 0) active_raw[cell * nq + q] = o;
     }
+    if (geo) proj /= wsum;                              // (the reference-cell weights sum to 1)
     if (op != 0) active_raw[cell] = proj;
     dg0[cell] = proj;
   }
@@ -659,7 +679,7 @@ int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, d
   SMF_CUDA(cudaMalloc(&dg0, sizeof(double) * nc));
   SMF_CUDA(cudaMalloc(&ext, sizeof(double) * 2 * blocks));
   SMF_CUDA(cudaMemcpyAsync(raw, viscosity_q, sizeof(double) * nc * nq, cudaMemcpyHostToDevice, ctx->stream));
-  k_average_viscosity<<<blocks, 256, 0, ctx->stream>>>(raw, nc, nq, averaging, act, dg0, ext, ext + blocks);
+  k_average_viscosity<<<blocks, 256, 0, ctx->stream>>>(raw, nc, nq, averaging, A.geo, act, dg0, ext, ext + blocks);
   ctx->launches++;
   int rc = install_table(ctx, A, act, n_act, pressure_scaling, is_compressible);
   double *fine = dg0;

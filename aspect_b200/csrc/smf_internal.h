@@ -89,6 +89,8 @@ struct NewtonDev {
   double *eps = nullptr, *deta = nullptr, *detadp = nullptr, *dil_lhs = nullptr, *ddil = nullptr, *ddildp = nullptr;
 };
 
+constexpr int SMF_MAX_RESTART = 200;   // longest GMRES / FGMRES restart length (nsinker_spherical_shell/gmg.prm uses 200); sizes the multi-dot scratch
+
 struct LevelDev {
   int dim = 0;
   int64_t n_cells = 0, n_u = 0, n_p = 0;
@@ -109,6 +111,7 @@ struct LevelDev {
   uint32_t *constrained_u = nullptr; int64_t n_constrained_u = 0;
   uint32_t *constrained_p = nullptr; int64_t n_constrained_p = 0;
   double h[3] = {1, 1, 1};
+  double *geo = nullptr;                      // curved cells (geometry = 1): [3^dim][dim*dim + 1][n_cells] inverse Jacobian (r-major) and JxW, cell fastest
   // cell data
   double *eta = nullptr; int n_eta = 0; double ps = 1.0; int compressible = 0; bool has_cell_data = false;
   NewtonDev nd;
@@ -199,6 +202,7 @@ struct smf_ctx {
   int use_graphs = 1;
   int ortho_single_pass = 1;                          // GMRES: re-orthogonalise through the Gram matrix (1) or with a second pass over the basis (0)
   int max_grid_blocks = 0;                            // > 0: cap on the persistent grids (tests: forces several bricks per block)
+  int use_curved_fast = 1;                            // curved cells: sum-factorised one-thread-per-cell kernel (0: the general restatement kernel)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
   int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)
   // profiler: 0 off, 1 operator kernels of the finest level only, 2 every launch

@@ -402,7 +402,8 @@ static int gmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double 
 {
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   const int64_t nu = A.n_u, np = A.n_p, n = nu + np;
-  const int restart = std::max(1, std::min(prm->gmres_restart_length, 100));
+  if (prm->gmres_restart_length > SMF_MAX_RESTART) return ctx->fail(SMF_ERR_UNSUPPORTED, "GMRES solver restart length above 200");
+  const int restart = std::max(1, prm->gmres_restart_length);
   const int max_its = prm->n_cheap_stokes_solver_steps;
   TRY(ensure_krylov(ctx, restart + 3));
   DotWeights dw(ctx, ctx->block_weights);
@@ -506,7 +507,8 @@ static int fgmres(smf_ctx *ctx, const smf_solve_params *prm, double *x_u, double
 {
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   const int64_t nu = A.n_u, np = A.n_p, n = nu + np;
-  const int restart = std::max(1, std::min(prm->gmres_restart_length, 100));
+  if (prm->gmres_restart_length > SMF_MAX_RESTART) return ctx->fail(SMF_ERR_UNSUPPORTED, "GMRES solver restart length above 200");
+  const int restart = std::max(1, prm->gmres_restart_length);
   const int max_its = prm->n_expensive_stokes_solver_steps;
   TRY(ensure_krylov(ctx, 4));
   DotWeights dw(ctx, ctx->block_weights);

@@ -7,7 +7,7 @@ namespace smf {
 
 constexpr int VT = 256;                 // threads per block
 constexpr int RED_BLOCKS = 148 * 4;     // persistent reduction grid: 4 blocks per SM
-constexpr int MD_CHUNK = 100;           // max basis vectors per multi-dot pass
+constexpr int MD_CHUNK = SMF_MAX_RESTART;   // max basis vectors per multi-dot pass (= longest GMRES restart length)
 
 static inline unsigned ew_blocks(int64_t n)
 {
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(VT) k_multi_axpy(double *w, const double *cons
 
 // scratch layout (doubles): [0, SCR_OUT) results | [SCR_OUT, SCR_OUT + RED_BLOCKS*SCR_PART) partials | then 2 counters |
 // device pointer table | Gram-matrix defect E = V^T V - I of the current Krylov basis (GRAM_LD x GRAM_LD)
-constexpr int SCR_OUT = 384;                    // results: [0, 2k] dots, [OUT_NRM] the norm multi_axpy returns
+constexpr int SCR_OUT = 2 * MD_CHUNK + 16;                   // results: [0, 2k] dots, [OUT_NRM] the norm multi_axpy returns
 constexpr int OUT_NRM = 2 * MD_CHUNK + 4;
 constexpr int SCR_PART = 2 * MD_CHUNK + 1;      // partials per block
 constexpr int GRAM_LD = MD_CHUNK + 4;
@@ -256,8 +256,8 @@ static int ensure_scratch(smf_ctx *ctx)
   SMF_CUDA(cudaMalloc(&ctx->scratch, n * sizeof(double)));
   SMF_CUDA(cudaMemsetAsync(ctx->scratch, 0, n * sizeof(double), ctx->stream));
   ctx->scratch_n = n;
-  SMF_CUDA(cudaMallocHost(&ctx->host_pinned, 512 * sizeof(double)));
-  ctx->host_pinned_n = 512;
+  SMF_CUDA(cudaMallocHost(&ctx->host_pinned, 1024 * sizeof(double)));
+  ctx->host_pinned_n = 1024;
   return SMF_OK;
 }
 static double *scr_out(smf_ctx *ctx) { return ctx->scratch; }
@@ -344,7 +344,7 @@ int vec_multi_dot_gram(smf_ctx *ctx, double *const *V_host_ptrs, int k, const do
                                                       ctx->md_vec2 = (all_aligned16(w, V_host_ptrs, k) && ((uintptr_t)ctx->dot_weights & 15u) == 0),
                                                       ctx->dot_weights); }
   if (int e = allreduce_sum(ctx, scr_out(ctx), 2 * k + 1)) return e;
-  k_gram_correct<<<1, 128, 0, ctx->stream>>>(scr_gram(ctx), scr_out(ctx), k);
+  k_gram_correct<<<1, 256, 0, ctx->stream>>>(scr_gram(ctx), scr_out(ctx), k);
   ctx->launches += 2;
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;
@@ -375,9 +375,9 @@ int vec_multi_add(smf_ctx *ctx, double *x, double *const *V_host_ptrs, const dou
   if (int e = ensure_scratch(ctx)) return e;
   if (k > MD_CHUNK) return ctx->fail(SMF_ERR_INVALID, "multi_add: too many vectors");
   if (k == 0) return SMF_OK;
-  for (int j = 0; j < k; ++j) ctx->host_pinned[256 + j] = -coef_host[j];
+  for (int j = 0; j < k; ++j) ctx->host_pinned[512 + j] = -coef_host[j];
   SMF_CUDA(cudaMemcpyAsync(scr_ptrs(ctx), V_host_ptrs, sizeof(double *) * k, cudaMemcpyHostToDevice, ctx->stream));
-  SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 256, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+  SMF_CUDA(cudaMemcpyAsync(scr_out(ctx), ctx->host_pinned + 512, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
   { ProfScope prof(ctx, ctx->vec_bucket);
   k_multi_axpy<<<red_blocks(k_multi_axpy, n), VT, 0, ctx->stream>>>(x, (const double *const *)scr_ptrs(ctx), scr_out(ctx), k, n,
                                                        scr_partial(ctx), scr_counter(ctx) + 1, scr_out(ctx) + OUT_NRM,

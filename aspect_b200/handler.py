@@ -74,6 +74,7 @@ class StokesMatrixFreeHandler:
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
         self.p2p_exchange = True                 # >1 rank: halo exchange as one kernel over NVLink peer memory (False: NCCL send/recv)
         self.gram_reorthogonalization = True     # GMRES: CGS2 in one sweep over the basis (False: two sweeps)
+        self.curved_sum_factorization = True     # curved cells: sum-factorised kernel (False: the general per-cell restatement kernel)
         # Chebyshev eigenvalue start vector from partition-independent global DoF numbers (always on for >1 rank)
         self.global_start_vector = False
         # "Solver parameters/Stokes solver parameters" (names verbatim from source/simulator/parameters.cc:439-584)
@@ -138,6 +139,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_PIPELINED_KERNEL, int(self.use_pipelined_kernel)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_SUMFAC, int(self.curved_sum_factorization)))
         self._keep = []
         self.rank, self.world = getattr(hierarchy, "rank", 0), getattr(hierarchy, "world", 1)
         self._comm_init()
@@ -147,7 +149,14 @@ class StokesMatrixFreeHandler:
             cp = np.ascontiguousarray(L.cell_dofs_p, dtype=np.uint32)
             cons = np.ascontiguousarray(L.constrained_u(boundary), dtype=np.uint32)
             h = np.ascontiguousarray(L.h, dtype=np.float64)
-            m = _lib.LevelMesh(L.n_cells, L.n_u, L.n_p, ptr(cu), ptr(cp), len(cons), ptr(cons), 0, ptr(None), 0, ptr(h))
+            if getattr(L, "jinv", None) is not None:
+                # curved cells: the mapping data MatrixFree holds per quadrature point (geometry = 1)
+                ji = np.ascontiguousarray(L.jinv, dtype=np.float64)
+                jw = np.ascontiguousarray(L.jxw, dtype=np.float64)
+                assert ji.shape == (L.n_cells, 3 ** self.dim, self.dim, self.dim) and jw.shape == (L.n_cells, 3 ** self.dim)
+                m = _lib.LevelMesh(L.n_cells, L.n_u, L.n_p, ptr(cu), ptr(cp), len(cons), ptr(cons), 0, ptr(None), 1, ptr(h), ptr(ji), ptr(jw))
+            else:
+                m = _lib.LevelMesh(L.n_cells, L.n_u, L.n_p, ptr(cu), ptr(cp), len(cons), ptr(cons), 0, ptr(None), 0, ptr(h), ptr(None), ptr(None))
             self._check(self.lib.smf_set_level(self.ctx, l, ctypes.byref(m)))
         if self.world > 1 or self.global_start_vector:
             for l in list(range(n_levels)) + [SMF_ACTIVE]:
@@ -329,7 +338,13 @@ class StokesMatrixFreeHandler:
         act, dim = self.hier.active, self.dim
         w = np.zeros(act.n_p)
         cp = np.asarray(act.cell_dofs_p, dtype=np.int64)
-        if kind == "volume":
+        if getattr(act, "jxw", None) is not None:
+            # curved cells: integral of every Q1 shape function with the cell's JxW values (volume normalisation only)
+            if kind != "volume":
+                raise SmfError(_lib.SMF_ERR_UNSUPPORTED, "curved meshes: Pressure normalization = volume | no")
+            from .benchmarks import _phi1_at_quad
+            np.add.at(w, cp, np.asarray(act.jxw) @ _phi1_at_quad(dim))
+        elif kind == "volume":
             np.add.at(w, cp.ravel(), float(np.prod(act.h)) / 2 ** dim)
         elif kind == "surface":
             top = np.asarray(act.cells)[:, dim - 1] == np.asarray(act.cells)[:, dim - 1].max()

@@ -1,0 +1,245 @@
+"""Synthetic spherical-shell driver (BASELINE config 3, SURVEY 8(d) "S-shell"): the arrays ASPECT's handler would pull out
+of deal.II for `Geometry model = spherical shell` in 3D -- per-level cell->DoF maps, constrained DoFs, parent->child
+tables and, because the cells are curved, the per-quadrature-point inverse Jacobians and JxW values that
+`MatrixFree::get_mapping_info()` holds.
+
+Coarse mesh = what `GridGenerator::hyper_shell(..., 96, true)` produces
+(/root/reference/source/geometry_model/spherical_shell.cc:361-373): the 12 rhombic faces of a rhombic dodecahedron
+(14 vertices: the 8 cube corners and the 6 axis points, projected onto the sphere), each split 2 x 2, times 2 radial
+layers = 96 hexahedra with 150 vertices (the reference golden `tests/spherical_nsinker_gmg_gc`: "coarse size S: 150").
+deal.II itself is not available here, so the ORDER of the coarse cells and the placement of points inside a coarse cell
+are this driver's own (documented) choice: every coarse cell is the root of one tree with the analytic map
+    X(xi, eta, zeta) = (r_a + zeta (r_b - r_a)) * normalize(bilinear blend of the 4 corner directions at (xi, eta)),
+level-l cells are the 8^l descendants in Morton order (deal.II child order), trees in coarse-cell order, and the mapping
+of every cell is the degree-4 Lagrange interpolant of X in the cell's Gauss-Lobatto points (ASPECT uses MappingQ(4)
+for curved geometries, source/simulator/core.cc:118-119).  Boundary ids: 0 = inner, 1 = outer
+(`Zero velocity boundary indicators = top, bottom` constrains both).
+
+DoF numbering: first touch over that cell sequence, FE-local order inside a cell, exactly as for the
+box driver (synthetic.py); nodes shared between trees are identified by their position.
+"""
+import numpy as np
+
+from .synthetic import _fe_local_order, _lex, morton_cells
+
+_UINT = np.uint32
+_S = np.sqrt(3.0 / 5.0)
+GAUSS3 = np.array([0.5 - 0.5 * _S, 0.5, 0.5 + 0.5 * _S])
+GAUSS3_W = np.array([5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0])
+_L = np.sqrt(3.0 / 7.0)
+LOBATTO5 = np.array([0.0, 0.5 - 0.5 * _L, 0.5, 0.5 + 0.5 * _L, 1.0])
+
+
+def coarse_shell_96():
+    """(96, 4, 3) unit corner directions (lexicographic: v00, v10, v01, v11, right-handed with the outward radial direction)
+    of the surface quad of every coarse cell, and (96,) radial layer (0 = inner half, 1 = outer half)."""
+    quads = []
+    for k in range(3):                                   # the cube edge runs along axis k
+        i, j = (k + 1) % 3, (k + 2) % 3
+        for sj in (-1.0, 1.0):
+            for si in (-1.0, 1.0):
+                c1 = np.zeros(3); c1[i], c1[j], c1[k] = si, sj, -1.0
+                c2 = c1.copy(); c2[k] = 1.0
+                a1 = np.zeros(3); a1[i] = si
+                a2 = np.zeros(3); a2[j] = sj
+                v = [a1, c1 / np.sqrt(3.0), c2 / np.sqrt(3.0), a2]          # v00, v10, v01, v11 (cyclic: a1, c1, a2, c2)
+                if np.dot(np.cross(v[1] - v[0], v[2] - v[0]), v[0] + v[3]) < 0.0:
+                    v[1], v[2] = v[2], v[1]
+                quads.append(np.array(v))
+    dirs, layer = [], []
+    for v in quads:
+        # 3 x 3 lattice of the face, projected onto the sphere
+        g = np.zeros((3, 3, 3))
+        for b in range(3):
+            for a in range(3):
+                x, y = a / 2.0, b / 2.0
+                p = (1 - x) * (1 - y) * v[0] + x * (1 - y) * v[1] + (1 - x) * y * v[2] + x * y * v[3]
+                g[b, a] = p / np.linalg.norm(p)
+        for r in range(2):
+            for sy in range(2):
+                for sx in range(2):
+                    dirs.append(np.array([g[sy, sx], g[sy, sx + 1], g[sy + 1, sx], g[sy + 1, sx + 1]]))
+                    layer.append(r)
+    return np.array(dirs), np.array(layer, dtype=np.int64)
+
+
+def tree_map(dirs, ra, rb, xi):
+    """X(xi) for arrays: dirs (..., 4, 3), ra/rb (...), xi (..., 3) -> (..., 3)."""
+    x, y, z = xi[..., 0:1], xi[..., 1:2], xi[..., 2:3]
+    p = (1 - x) * (1 - y) * dirs[..., 0, :] + x * (1 - y) * dirs[..., 1, :] + (1 - x) * y * dirs[..., 2, :] + x * y * dirs[..., 3, :]
+    p = p / np.sqrt((p * p).sum(-1, keepdims=True))
+    return (ra[..., None] + z * (rb - ra)[..., None]) * p
+
+
+def _lagrange_tables(nodes, x):
+    """values and derivatives of the 1D Lagrange basis on `nodes` at the points x: ([len(x)][len(nodes)]) each."""
+    n = len(nodes)
+    V = np.ones((len(x), n)); D = np.zeros((len(x), n))
+    for a in range(n):
+        for b in range(n):
+            if b != a:
+                V[:, a] *= (x - nodes[b]) / (nodes[a] - nodes[b])
+        for b in range(n):
+            if b != a:
+                t = np.ones(len(x)) / (nodes[a] - nodes[b])
+                for c in range(n):
+                    if c != a and c != b:
+                        t *= (x - nodes[c]) / (nodes[a] - nodes[c])
+                D[:, a] += t
+    return V, D
+
+
+def mapping_tables(degree=4, points=GAUSS3):
+    """Tensor Lagrange basis of MappingQ(degree) at the 3^3 tensor points: N[q][k], dN[q][k][r] (q, k lexicographic)."""
+    nodes = LOBATTO5 if degree == 4 else np.linspace(0.0, 1.0, degree + 1)
+    V, D = _lagrange_tables(nodes, points)
+    nq, nk = len(points), len(nodes)
+    N = np.einsum("ck,bj,ai->cbakji", V, V, V).reshape(nq ** 3, nk ** 3)
+    dN = np.stack([np.einsum("ck,bj,ai->cbakji", V, V, D).reshape(nq ** 3, nk ** 3),
+                   np.einsum("ck,bj,ai->cbakji", V, D, V).reshape(nq ** 3, nk ** 3),
+                   np.einsum("ck,bj,ai->cbakji", D, V, V).reshape(nq ** 3, nk ** 3)], axis=-1)
+    return nodes, N, dN
+
+
+class ShellLevel:
+    """One level of the uniformly refined 96-tree spherical shell."""
+    dim = 3
+    KEY_BITS = 21          # per-coordinate field of the position key; quantum 2^-19
+
+    def __init__(self, level, inner_radius=0.54, outer_radius=1.0, mapping_degree=4):
+        self.level = level
+        self.n = n = 1 << level
+        self.R0, self.R1 = float(inner_radius), float(outer_radius)
+        self.mapping_degree = mapping_degree
+        dirs, layer = coarse_shell_96()
+        self.n_trees = len(dirs)
+        m = morton_cells(level, 3)
+        self.cells = np.tile(m, (self.n_trees, 1))                       # integer coordinates inside the tree
+        self.tree = np.repeat(np.arange(self.n_trees), len(m))
+        self.n_cells = len(self.cells)
+        rm = 0.5 * (self.R0 + self.R1)
+        self._dirs = dirs
+        self._ra = np.where(layer == 0, self.R0, rm)
+        self._rb = np.where(layer == 0, rm, self.R1)
+        self.h = np.full(3, 1.0 / n)                                      # (reference-cell size inside the tree; unused by the curved kernels)
+        nodes_u, self.node_x_u = self._first_touch(2, _fe_local_order(2, 3), _lex(3, 3))
+        nodes_p, self.node_x_p = self._first_touch(1, _fe_local_order(1, 3), _lex(2, 3))
+        n_surface = 48 * 4 ** level
+        assert len(self.node_x_u) == (4 * n_surface + 2) * (4 * n + 1), "Q2 nodes of the shell were not identified one to one"
+        assert len(self.node_x_p) == (n_surface + 2) * (2 * n + 1), "Q1 nodes of the shell were not identified one to one"
+        self.n_u, self.n_p = 3 * len(self.node_x_u), len(self.node_x_p)
+        cu = np.empty((self.n_cells, 81), dtype=_UINT)
+        for c in range(3):
+            cu[:, c * 27:(c + 1) * 27] = 3 * nodes_u + c
+        self.cell_dofs_u = cu
+        self.cell_dofs_p = nodes_p.astype(_UINT)
+        self._geom = None
+
+    # -- points ------------------------------------------------------------------------------------------------
+    def points(self, ref, chunk=None):
+        """Physical positions X of the reference points ref (npts, 3) of every cell (or of the cells in `chunk`): (cells, npts, 3)."""
+        sel = slice(None) if chunk is None else chunk
+        cells, tree = self.cells[sel], self.tree[sel]
+        xi = (cells[:, None, :] + ref[None, :, :]) / self.n
+        return tree_map(self._dirs[tree][:, None], self._ra[tree][:, None], self._rb[tree][:, None], xi)
+
+    def _first_touch(self, npd_minus1, local_order, lex_order):
+        """Number the nodes in first-touch order; nodes are identified by their quantised position."""
+        scale = float(1 << (self.KEY_BITS - 2))
+
+        def keys(order):
+            out = np.empty((self.n_cells, len(order)), dtype=np.int64)
+            step = 1 << 14
+            for s in range(0, self.n_cells, step):
+                x = self.points(order / float(npd_minus1), slice(s, s + step))
+                q = np.rint((x + 1.0) * scale).astype(np.int64)
+                out[s:s + step] = (q[..., 0] << (2 * self.KEY_BITS)) | (q[..., 1] << self.KEY_BITS) | q[..., 2]
+            return out
+
+        kfe = keys(local_order.astype(np.float64)).ravel()
+        uniq, first = np.unique(kfe, return_index=True)
+        rank = np.empty(len(uniq), dtype=np.int64)
+        rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+        del kfe
+        klex = keys(lex_order.astype(np.float64))
+        cell_nodes = rank[np.searchsorted(uniq, klex.ravel())].reshape(klex.shape)
+        mask = (1 << self.KEY_BITS) - 1
+        x = np.empty((len(uniq), 3))
+        x[rank, 0] = (uniq >> (2 * self.KEY_BITS)) / scale - 1.0
+        x[rank, 1] = ((uniq >> self.KEY_BITS) & mask) / scale - 1.0
+        x[rank, 2] = (uniq & mask) / scale - 1.0
+        return cell_nodes, x                                             # (positions are accurate to the key quantum, 2e-6)
+
+    # -- constraints -------------------------------------------------------------------------------------------
+    def constrained_u(self, bc):
+        """'zero': all components on the inner and outer boundary (`Zero velocity boundary indicators = top, bottom`)."""
+        if bc == "none":
+            return np.zeros(0, dtype=_UINT)
+        if bc != "zero":
+            raise ValueError("the shell driver implements zero-velocity boundaries only (no-normal-flux on a curved boundary "
+                             "couples the components)")
+        r = np.sqrt((self.node_x_u ** 2).sum(-1))
+        on = (np.abs(r - self.R0) < 1e-4) | (np.abs(r - self.R1) < 1e-4)
+        return np.flatnonzero(np.repeat(on[:, None], 3, axis=1).ravel()).astype(_UINT)
+
+    # -- geometry (MappingQ(degree) of the analytic tree map) --------------------------------------------------
+    def geometry(self):
+        """(xq (cells, 27, 3), jinv (cells, 27, 3, 3) with jinv[r][d] = d xi_r / d x_d, jxw (cells, 27))."""
+        if self._geom is None:
+            nodes, N, dN = mapping_tables(self.mapping_degree)
+            ref = _lex(len(nodes), 3).astype(np.int64)
+            ref = nodes[ref]                                             # support points of the mapping on the unit cell
+            w = np.einsum("c,b,a->cba", GAUSS3_W, GAUSS3_W, GAUSS3_W).ravel()
+            dN2 = np.ascontiguousarray(dN.transpose(0, 2, 1).reshape(81, -1))         # [(q, r)][k]
+            xq = np.empty((self.n_cells, 27, 3)); jinv = np.empty((self.n_cells, 27, 3, 3)); jxw = np.empty((self.n_cells, 27))
+            step = 1 << 13
+            for s in range(0, self.n_cells, step):
+                X = self.points(ref, slice(s, s + step))                # (cells, 125, 3)
+                xq[s:s + step] = np.matmul(N[None], X)
+                # J[d][r] = d x_d / d xihat_r (cell-local reference coordinates), as one batched GEMM
+                J = np.matmul(dN2[None], X).reshape(len(X), 27, 3, 3).transpose(0, 1, 3, 2)
+                jinv[s:s + step] = np.linalg.inv(J)
+                jxw[s:s + step] = np.linalg.det(J) * w[None, :]
+            assert (jxw > 0).all()
+            self._geom = (xq, jinv, jxw)
+        return self._geom
+
+    def quadrature_points(self):
+        return self.geometry()[0]
+
+    def midpoint_geometry(self):
+        """(position (cells, 3), det J (cells,)) at the cell midpoints (QMidpoint of compute_pressure_scaling_factor)."""
+        nodes, N, dN = mapping_tables(self.mapping_degree, np.array([0.5]))
+        ref = nodes[_lex(len(nodes), 3).astype(np.int64)]
+        xm = np.empty((self.n_cells, 3)); det = np.empty(self.n_cells)
+        step = 1 << 14
+        for s in range(0, self.n_cells, step):
+            X = self.points(ref, slice(s, s + step))
+            xm[s:s + step] = np.einsum("k,ekd->ed", N[0], X)
+            det[s:s + step] = np.linalg.det(np.einsum("kr,ekd->edr", dN[0], X))
+        return xm, det
+
+    @property
+    def jinv(self):
+        return self.geometry()[1]
+
+    @property
+    def jxw(self):
+        return self.geometry()[2]
+
+    def dof_coords_u(self):
+        return np.repeat(self.node_x_u, 3, axis=0)
+
+
+class ShellHierarchy:
+    """Levels 0..R of the uniformly refined shell; active mesh = level R."""
+
+    def __init__(self, refinement, inner_radius=0.54, outer_radius=1.0, mapping_degree=4):
+        self.dim, self.R = 3, refinement
+        self.rank, self.world = 0, 1
+        self.levels = [ShellLevel(l, inner_radius, outer_radius, mapping_degree) for l in range(refinement + 1)]
+        self.active = self.levels[-1]
+
+    def children(self, level):
+        npar = self.levels[level - 1].n_cells
+        return (np.arange(npar, dtype=np.int64)[:, None] * 8 + np.arange(8)[None, :]).astype(np.int32)

@@ -52,6 +52,7 @@ const char *smf_last_error(const smf_ctx *ctx);
 #define SMF_OPT_MAX_GRID_BLOCKS 4      /* > 0: cap on the grid of the persistent kernels (testing aid; default 0 = one resident wave) */
 #define SMF_OPT_PIPELINED_KERNEL 3     /* structured levels: persistent, cp.async-pipelined velocity kernel (default 1) */
 #define SMF_OPT_P2P_EXCHANGE 5        /* halo exchange as one kernel over NVLink peer memory (default 1); 0 = pack + NCCL send/recv + accumulate */
+#define SMF_OPT_CURVED_SUMFAC 6        /* curved cells (geometry = 1): sum-factorised kernel (default 1); 0 = the general per-cell restatement kernel */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
@@ -69,8 +70,16 @@ typedef struct {
   const uint32_t *constrained_u;
   int64_t n_constrained_p;
   const uint32_t *constrained_p;
-  int geometry;                      /* 0: Cartesian, one cell size for the level (cell_size[dim]) */
+  int geometry;                      /* 0: Cartesian, one cell size for the level (cell_size[dim]);
+                                        1: general (curved) cells, per-quadrature-point geometry below   */
   const double *cell_size;
+  /* geometry = 1: what MatrixFree's MappingInfo holds for the 3^dim-point Gauss rule of the cell loops
+   * (matrix_free_operators.cc:384-385), in the cell order of cell_dofs_*, q lexicographic (x fastest):
+   * inverse_jacobians [n_cells][3^dim][dim][dim] with entry [r][d] = d xi_r / d x_d (FEEvaluation's inverse_jacobian:
+   * grad_x phi = J^-T grad_xi phi), jxw [n_cells][3^dim] = det(J) * quadrature weight.  Both are COPIED.
+   * Adds the G term of SURVEY 8(d) to the algorithmic bytes: 8 (dim^2 + 1) 3^dim bytes per cell and application. */
+  const double *inverse_jacobians;
+  const double *jxw;
 } smf_level_mesh;
 int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *mesh);
 

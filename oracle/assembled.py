@@ -38,7 +38,40 @@ def local_gradients(level):
     return G, t
 
 
+def _curved(level):
+    return getattr(level, "jinv", None) is not None
+
+
+def _phys_gradients(level, t):
+    """Curved cells: g[e, q, i, d] = sum_r dphi2[q, i, r] jinv[e, q, r, d] (scalar Q2 shape gradients in real space)."""
+    return np.einsum("qir,eqrd->eqid", t["dphi2"], level.jinv)
+
+
+def _assemble_A_curved(level, eta, constrained, compressible):
+    """2 eta eps(phi_I) : eps(phi_J) with I = (c, i), J = (c', j):
+    block (c, c') = sum_q eta JxW [ delta_cc' grad phi_i . grad phi_j + d_c' phi_i d_c phi_j - (2/3) d_c phi_i d_c' phi_j ]."""
+    dim = level.dim
+    t = fe.tensor_tables(dim)
+    nn = 3 ** dim
+    eta = _eta_q(eta, level.n_cells, len(t["w"]))
+    g = _phys_gradients(level, t)
+    coef = eta * level.jxw
+    Ke = np.zeros((level.n_cells, dim * nn, dim * nn))
+    lap = np.einsum("eq,eqid,eqjd->eij", coef, g, g)
+    for c in range(dim):
+        for c2 in range(dim):
+            blk = np.einsum("eq,eqi,eqj->eij", coef, g[..., c2], g[..., c])
+            if compressible:
+                blk = blk - (2.0 / 3.0) * np.einsum("eq,eqi,eqj->eij", coef, g[..., c], g[..., c2])
+            if c == c2:
+                blk = blk + lap
+            Ke[:, c * nn:(c + 1) * nn, c2 * nn:(c2 + 1) * nn] = blk
+    return _scatter(Ke, level.cell_dofs_u, level.cell_dofs_u, level.n_u, level.n_u, constrained, constrained, True)
+
+
 def assemble_A(level, eta, constrained=None, compressible=False):
+    if _curved(level):
+        return _assemble_A_curved(level, eta, constrained, compressible)
     dim = level.dim
     G, t = local_gradients(level)
     nq = len(t["w"])
@@ -59,6 +92,11 @@ def assemble_A(level, eta, constrained=None, compressible=False):
 def assemble_BT(level, pressure_scaling=1.0, constrained_u=None):
     """(n_u x n_p): u_dst = -ps int p div v."""
     dim = level.dim
+    if _curved(level):
+        t = fe.tensor_tables(dim)
+        g = _phys_gradients(level, t)
+        Ke = np.concatenate([-pressure_scaling * np.einsum("eq,eqi,qj->eij", level.jxw, g[..., c], t["phi1"]) for c in range(dim)], axis=1)
+        return _scatter(Ke, level.cell_dofs_u, level.cell_dofs_p, level.n_u, level.n_p, constrained_u, None, False)
     G, t = local_gradients(level)
     div = np.trace(G, axis1=2, axis2=3)                           # (q, I)
     coef = t["w"] * level.cell_volume()
@@ -72,7 +110,8 @@ def assemble_mass(level, eta, pressure_scaling=1.0):
     t = fe.tensor_tables(dim)
     nq = len(t["w"])
     eta = _eta_q(eta, level.n_cells, nq)
-    coef = (pressure_scaling ** 2 / eta) * (t["w"] * level.cell_volume())[None, :]
+    jxw = level.jxw if _curved(level) else (t["w"] * level.cell_volume())[None, :]
+    coef = (pressure_scaling ** 2 / eta) * jxw
     Ke = np.einsum("eq,qi,qj->eij", coef, t["phi1"], t["phi1"])
     return _scatter(Ke, level.cell_dofs_p, level.cell_dofs_p, level.n_p, level.n_p, None, None, False)
 
@@ -109,9 +148,23 @@ def rhs_gravity(level, rho_q, gravity):
     dim = level.dim
     t = fe.tensor_tables(dim)
     nn = 3 ** dim
-    coef = rho_q * (t["w"] * level.cell_volume())[None, :]
+    coef = rho_q * (level.jxw if _curved(level) else (t["w"] * level.cell_volume())[None, :])
     loc = np.einsum("eq,qi->ei", coef, t["phi2"])                # (cells, nodes)
     f = np.zeros(level.n_u)
     for c in range(dim):
         np.add.at(f, level.cell_dofs_u[:, c * nn:(c + 1) * nn], gravity[c] * loc)
+    return f
+
+
+def rhs_force(level, force_q):
+    """f_i = int force . phi_i for a force density given at the quadrature points, force_q (cells, nq, dim)
+    (e.g. rho * g with a radial gravity vector; assemblers/stokes.cc:387-396)."""
+    dim = level.dim
+    t = fe.tensor_tables(dim)
+    nn = 3 ** dim
+    jxw = level.jxw if _curved(level) else np.broadcast_to((t["w"] * level.cell_volume())[None, :], force_q.shape[:2])
+    f = np.zeros(level.n_u)
+    for c in range(dim):
+        loc = np.einsum("eq,qi->ei", force_q[..., c] * jxw, t["phi2"])
+        np.add.at(f, level.cell_dofs_u[:, c * nn:(c + 1) * nn], loc)
     return f

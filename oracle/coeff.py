@@ -30,7 +30,15 @@ NSINKER_CENTERS = np.array([
     [4.6986202126e-01, 9.7099129947e-01, 4.5077026191e-01],
     [9.5791877292e-02, 9.7408164664e-01, 3.9023506101e-01],
     [6.8067035576e-01, 2.6669318800e-02, 2.3124107450e-01],
-])  # first 16 of the 75 fixed centres (the configs use <= 8)
+    [4.6873909443e-01, 9.7960100555e-02, 4.1541002524e-01],
+    [7.9629418710e-01, 3.1640260216e-01, 7.7853444953e-01],
+    [8.2849331472e-01, 4.8714042059e-01, 3.6904878000e-01],
+    [6.0284549678e-01, 2.4264360789e-02, 8.1111178631e-01],
+    [3.5579259291e-01, 8.0610905439e-01, 2.7487712366e-01],
+    [8.5981739865e-01, 9.5101905612e-01, 7.7727618477e-01],
+    [6.8083745971e-01, 8.3518540665e-01, 9.6112961413e-01],
+    [7.0542474869e-01, 7.3751226102e-02, 5.3685709440e-01],
+])  # first 24 of the 75 fixed centres (the box configs use <= 8; 8 of the 24 lie inside the shell)
 
 
 def nsinker_chi(x, n_sinkers, delta=200.0, omega=0.1):
@@ -92,7 +100,9 @@ def viscosity_tables(hier, eta_q, averaging):
     out_q = average(eta_q, averaging)
     eta_min, eta_max = float(out_q.min()), float(out_q.max())          # matrix_free_operators.cc:248-262
     # cellwise L2 projection onto constants = JxW-weighted mean (utilities.cc:2738-2812)
-    dg0 = (out_q * t["w"][None, :]).sum(axis=1) / t["w"].sum()
+    jxw = getattr(hier.active, "jxw", None)                              # curved cells: per-cell JxW
+    w = t["w"][None, :] if jxw is None else jxw
+    dg0 = (out_q * w).sum(axis=1) / np.broadcast_to(w, out_q.shape).sum(axis=1)
     active = out_q.copy() if averaging == "none" else dg0[:, None].copy()
     levels = [None] * (hier.R + 1)
     levels[hier.R] = dg0[:, None].copy()
@@ -108,3 +118,32 @@ def pressure_scaling_box(hier, eta_fn):
     mid = (lev.cells + 0.5) * lev.h
     eta = eta_fn(mid)
     return float(np.exp(np.log(eta).mean()) / (0.01 * lev.extents[0]))
+
+
+def shell_sinker_centers(inner=0.54, outer=1.0):
+    """benchmarks/nsinker_spherical_shell/nsinker.cc:284-296: centres rescaled to [-1,1]^3, those outside the shell dropped."""
+    p = 2.0 * NSINKER_CENTERS - 1.0
+    r = np.sqrt((p * p).sum(-1))
+    return p[(r >= inner) & (r <= outer)]
+
+
+def nsinker_shell(x, n_sinkers=5, viscosity_ratio=1e2, sinker_density=10.0, transition_zone_jump=100.0):
+    """(eta, rho) of the spherical-shell NSinker material (nsinker_spherical_shell/nsinker.cc:57-71; delta = 400,
+    omega = 0.2, :204-205; viscosity times `Transition zone viscosity jump` below r = 0.89583)."""
+    centers = shell_sinker_centers()
+    assert n_sinkers <= len(centers)
+    chi = np.ones(x.shape[:-1])
+    for s in range(n_sinkers):
+        dist = np.sqrt(((x - centers[s]) ** 2).sum(-1))
+        chi = chi * (1.0 - np.exp(-400.0 * np.maximum(0.0, dist - 0.2 / 2.0) ** 2))
+    s = np.sqrt(viscosity_ratio)
+    eta = (s - 1.0 / s) * (1.0 - chi) + 1.0 / s
+    eta = np.where(np.sqrt((x * x).sum(-1)) < 0.89583, eta * transition_zone_jump, eta)
+    return eta, sinker_density * (1.0 - chi)
+
+
+def pressure_scaling_shell(level, eta_mid, jxw_mid, inner=0.54, outer=1.0):
+    """helper_functions.cc:253-348 with SphericalShell::length_scale (geometry_model/spherical_shell.cc:724-737):
+    exp(JxW-weighted mean of log eta at the cell midpoints) / (1e4 / (6336000 - 3481000) * (R1 - R0))."""
+    ref = np.exp((np.log(eta_mid) * jxw_mid).sum() / jxw_mid.sum())
+    return float(ref / (1e4 / (6336000.0 - 3481000.0) * (outer - inner)))

@@ -1,0 +1,168 @@
+"""GPU parity on curved cells (BASELINE config 3, spherical shell with MappingQ(4) geometry): every operator of the C ABI
+against the oracle's assembled curved-geometry matrices on the same seeded inputs, both CUDA kernels (the sum-factorised
+one-thread-per-cell kernel and the general restatement kernel), then the callers (table pipeline, right-hand side) and the
+whole block-GMG solve of benchmarks/nsinker_spherical_shell/gmg.prm against the oracle running the same algorithm.
+Tolerance: relative 1e-12 per operator application (BASELINE.json north_star), iterations +-1, solution 1e-8.
+"""
+import numpy as np
+import pytest
+
+from oracle import assembled, coeff, solver
+from oracle import shell as oshell
+from aspect_b200 import StokesMatrixFreeHandler, SMF_ACTIVE, benchmarks
+from aspect_b200 import shell as pshell
+from util import rel, seeded
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def meshes():
+    return oshell.ShellHierarchy(1), pshell.ShellHierarchy(1)
+
+
+def _setup(meshes, averaging, fast, ps=3.7, seed=5):
+    ohier, hier = meshes
+    eta_q = np.exp(np.random.default_rng(seed).uniform(-4, 4, size=(hier.active.n_cells, 27)))
+    h = StokesMatrixFreeHandler(3)
+    h.curved_sum_factorization = fast
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, averaging, ps)
+    h.build_preconditioner()
+    op = {"none": "none", "harmonic average": "harmonic"}[averaging]
+    active, levels, emin, emax = coeff.viscosity_tables(ohier, eta_q, op)
+    ob = solver.AssembledBackend(ohier, active, levels, ps, "zero")
+    return h, ob, (active, levels, emin, emax)
+
+
+@pytest.mark.parametrize("averaging", ["none", "harmonic average"])
+@pytest.mark.parametrize("fast", [True, False])
+def test_curved_operators(meshes, averaging, fast):
+    h, ob, tables = _setup(meshes, averaging, fast)
+    hier = meshes[1]
+    act = hier.active
+    # the table pipeline on curved cells: JxW-weighted DGQ0 projection, level tables, min / max
+    assert rel(h.get_cell_data(SMF_ACTIVE), tables[0]) < 1e-14
+    for l in range(2):
+        assert rel(h.get_cell_data(l), tables[1][l]) < 1e-14
+    assert abs(h.minimum_viscosity - tables[2]) < 1e-14 * tables[2] and abs(h.maximum_viscosity - tables[3]) < 1e-14 * tables[3]
+    xu, xp = seeded(act.n_u, 1), seeded(act.n_p, 2)
+    src = h.initialize_dof_vector(); dst = h.initialize_dof_vector()
+    src[0].from_host(xu); src[1].from_host(xp)
+    for _ in range(2):
+        h.stokes_matrix.vmult(dst, src)
+        yu, yp = ob.stokes(xu, xp)
+        assert rel(dst[0].to_host(), yu) < TOL and rel(dst[1].to_host(), yp) < TOL
+    h.BT_block.vmult(dst, src)
+    assert rel(dst[0].to_host(), ob.BT(xp)) < TOL
+    h.A_block_matrix.vmult(dst[0], src[0])
+    assert rel(dst[0].to_host(), ob.A_active(xu)) < TOL
+    h.Schur_complement_block_matrix.vmult(dst[1], src[1])
+    assert rel(dst[1].to_host(), ob.M_active(xp)) < TOL
+    for l, L in enumerate(hier.levels):
+        xl, pl = seeded(L.n_u, 10 + l), seeded(L.n_p, 20 + l)
+        su, du = h.initialize_dof_vector(0, l).from_host(xl), h.initialize_dof_vector(0, l)
+        sp, dp = h.initialize_dof_vector(1, l).from_host(pl), h.initialize_dof_vector(1, l)
+        h.mg_matrices_A_block[l].vmult(du, su)
+        assert rel(du.to_host(), ob.apply_A(l, xl)) < TOL
+        h.mg_matrices_Schur_complement[l].vmult(dp, sp)
+        assert rel(dp.to_host(), ob.apply_M(l, pl)) < TOL
+        assert rel(h.get_matrix_diagonal_inverse(l, 0), ob.dinv_A(l)) < TOL
+        assert rel(h.get_matrix_diagonal_inverse(l, 1), ob.dinv_M(l)) < TOL
+    # transfers between the two levels of the 96-tree mesh (trees with different orientations share faces)
+    C, F = hier.levels
+    cu, cp = seeded(C.n_u, 30), seeded(C.n_p, 31)
+    fu, fp = seeded(F.n_u, 32), seeded(F.n_p, 33)
+    du, dp = h.initialize_dof_vector(0, 1), h.initialize_dof_vector(1, 1)
+    h.prolongate(0, 1, du, h.initialize_dof_vector(0, 0).from_host(cu))
+    assert rel(du.to_host(), ob.prolongate_u(1, cu)) < TOL
+    h.prolongate(1, 1, dp, h.initialize_dof_vector(1, 0).from_host(cp))
+    assert rel(dp.to_host(), ob.prolongate_p(1, cp)) < TOL
+    ru, rp = h.initialize_dof_vector(0, 0).zero(), h.initialize_dof_vector(1, 0).zero()
+    h.restrict_and_add(0, 1, ru, h.initialize_dof_vector(0, 1).from_host(fu))
+    assert rel(ru.to_host(), ob.restrict_u(1, fu)) < TOL
+    h.restrict_and_add(1, 1, rp, h.initialize_dof_vector(1, 1).from_host(fp))
+    assert rel(rp.to_host(), ob.restrict_p(1, fp)) < TOL
+    h.close()
+
+
+def test_curved_compressible_A_block(meshes):
+    """is_compressible makes the A block deviatoric (matrix_free_operators.cc:999-1005): the general kernel with curved geometry."""
+    ohier, hier = meshes
+    eta = np.exp(np.random.default_rng(9).uniform(-2, 2, size=(hier.active.n_cells, 27)))
+    h = StokesMatrixFreeHandler(3)
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta, "none", 1.3, is_compressible=True)
+    h.build_preconditioner()
+    cons = ohier.active.constrained_u("zero")
+    A = assembled.assemble_A(ohier.active, eta, cons, compressible=True)
+    xu = seeded(hier.active.n_u, 4)
+    s, d = h.initialize_dof_vector(0).from_host(xu), h.initialize_dof_vector(0)
+    h.A_block_matrix.vmult(d, s)
+    assert rel(d.to_host(), A @ xu) < TOL
+    assert rel(h.get_matrix_diagonal_inverse(SMF_ACTIVE, 0), 1.0 / A.diagonal()) < TOL
+    h.close()
+
+
+def _shell_problem(meshes):
+    ohier, hier = meshes
+    eta_q, force_q, ps = benchmarks.nsinker_shell_problem(hier)
+    L = ohier.active
+    eo, ro = coeff.nsinker_shell(L.xq)
+    active, levels, emin, emax = coeff.viscosity_tables(ohier, eo, "harmonic")
+    g = -L.xq / np.linalg.norm(L.xq, axis=-1, keepdims=True)
+    f = assembled.rhs_force(L, coeff.average(ro, "harmonic")[..., None] * g)
+    f[L.constrained_u("zero")] = 0.0
+    return eta_q, force_q, ps, f, (active, levels, emin, emax)
+
+
+def test_shell_rhs_and_pressure_normalization(meshes):
+    ohier, hier = meshes
+    eta_q, force_q, ps, f, _ = _shell_problem(meshes)
+    h = StokesMatrixFreeHandler(3)
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, "harmonic average", ps)
+    r = h.initialize_dof_vector(0)
+    h.assemble_stokes_rhs(force_q, r)
+    assert rel(r.to_host(), f) < 1e-13
+    # volume normalisation: p := p - (int p) / |Omega| with the curved cells' JxW (helper_functions.cc:843-850)
+    p = seeded(hier.active.n_p, 6)
+    h.set_pressure_normalization("volume")
+    v = h.initialize_dof_vector(1).from_host(p)
+    adj = h.postprocess_pressure(v, 1.0, True)
+    M = assembled.assemble_mass(ohier.active, np.ones((ohier.active.n_cells, 27)), 1.0)
+    mean = float(np.ones(len(p)) @ (M @ p)) / ohier.active.jxw.sum()
+    assert abs(adj + mean) < 1e-12 and rel(v.to_host(), p - mean) < 1e-13
+    h.close()
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_shell_solve_matches_oracle(meshes, fast):
+    """benchmarks/nsinker_spherical_shell/gmg.prm (5 sinkers, viscosity ratio 1e2, transition-zone jump 100, harmonic
+    averaging, tolerance 1e-6, GMRES restart 200) at global refinement 1 -- the configuration of the reference golden
+    tests/spherical_nsinker_gmg_gc -- against the oracle running the same algorithm on the same mesh."""
+    ohier, hier = meshes
+    eta_q, force_q, ps, f, (active, levels, emin, emax) = _shell_problem(meshes)
+    ob = solver.AssembledBackend(ohier, active, levels, ps, "zero")
+    want = solver.BlockGMGStokes(ob).solve(np.concatenate([f, np.zeros(ohier.active.n_p)]), tol_rel=1e-6, restart=200, max_its=2000)
+    h = StokesMatrixFreeHandler(3)
+    h.curved_sum_factorization = fast
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, "harmonic average", ps)
+    h.build_preconditioner()
+    h.parameters.update({"Linear solver tolerance": 1e-6, "Number of cheap Stokes solver steps": 2000,
+                         "Maximum number of expensive Stokes solver steps": 0, "GMRES solver restart length": 200})
+    r = h.initialize_dof_vector(0)
+    h.assemble_stokes_rhs(force_q, r)
+    rhs = np.concatenate([r.to_host(), np.zeros(hier.active.n_p)])
+    sol, out = h.solve(rhs)
+    assert out["converged"]
+    assert abs(out["iterations"] - want["iterations"]) <= 1, (out["iterations"], want["iterations"])
+    assert out["n_A_preconditioner"] == out["iterations"] + (out["iterations"] - 1) // 200 + 1
+    nu = hier.active.n_u
+    xs = want["x"].copy(); xs[nu:] *= ps                       # the handler returns the pressure in physical units
+    assert rel(sol[:nu], xs[:nu]) < 1e-6
+    # the pressure is determined up to a constant (no-slip everywhere): compare after removing the mean
+    assert rel(sol[nu:] - sol[nu:].mean(), xs[nu:] - xs[nu:].mean()) < 1e-4
+    h.close()

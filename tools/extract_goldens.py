@@ -10,7 +10,7 @@ import re
 
 REF = "/root/reference/tests"
 TESTS = ["nsinker_gmg_no_avg", "nsinker_gmg_gc", "nsinker_gmg_gc_no_avg", "nsinker_gmg_idr", "sol_cx_2_gmg", "sol_cx_4_gmg",
-         "sol_cx_4_gmg_no_avg", "no_cheap_gmg", "performance/performance_nsinker_gmg_idr"]
+         "sol_cx_4_gmg_no_avg", "no_cheap_gmg", "performance/performance_nsinker_gmg_idr", "spherical_nsinker_gmg_gc"]
 
 
 def num(s):
