@@ -146,7 +146,7 @@ def nsinker_shell_material(x, n_sinkers=5, viscosity_ratio=1e2, sinker_density=1
 def pressure_scaling_shell(level, material):
     """helper_functions.cc:253-348 (JxW-weighted log average at the cell midpoints) over SphericalShell::length_scale()
     = 1e4 / (6336000 - 3481000) * (R1 - R0) (geometry_model/spherical_shell.cc:724-737)."""
-    xm, det = level.midpoint_geometry()
+    xm, det = level.global_midpoint_geometry()           # (Utilities::MPI::sum over the ranks, helper_functions.cc:337-339)
     eta = material(xm)[0]
     ref = np.exp((np.log(eta) * det).sum() / det.sum())
     return float(ref / (1e4 / (6336000.0 - 3481000.0) * (level.R1 - level.R0)))

@@ -1013,7 +1013,7 @@ struct DiagParams {
   const double *eta; int n_eta;     // lane-transposed table [cell/32][n_eta][32]
   double ih[3]; double vol, ps; int compressible;
   double *diag_A, *diag_M;
-  const double *geo;                // curved cells: [q][dim*dim + 1][n_cells] (NULL = Cartesian)
+  const double *geo;                // curved cells: blk_index table of the geometry (NULL = Cartesian)
 };
 __device__ __forceinline__ double q2v(int q, int i)
 { return q == 1 ? (i == 1 ? 1.0 : 0.0) : (i == 1 ? NB : ((i == 0) == (q == 0) ? NA : NC)); }
@@ -1036,8 +1036,9 @@ template <int DIM> __global__ void diag_kernel(const DiagParams P)
   double a[3] = {0, 0, 0};
   for (int q = 0; q < NN; ++q) {
     int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
-    const double *gq = P.geo ? P.geo + (int64_t)q * (DIM * DIM + 1) * P.n_cells + cell : nullptr;
-    const double JxW = gq ? gq[(int64_t)(DIM * DIM) * P.n_cells] : qweight<DIM>(q) * P.vol;
+    constexpr int GR = NN * (DIM * DIM + 1);
+    const double *gq = P.geo ? P.geo + blk_index(cell, q * (DIM * DIM + 1), GR) : nullptr;      // entry k of the point: gq[k * GEO_BLOCK]
+    const double JxW = gq ? gq[DIM * DIM * GEO_BLOCK] : qweight<DIM>(q) * P.vol;
     const double coef = JxW * P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)];
     double ref[DIM];
     for (int r = 0; r < DIM; ++r) {
@@ -1047,7 +1048,7 @@ template <int DIM> __global__ void diag_kernel(const DiagParams P)
     }
     for (int d = 0; d < DIM; ++d) {
       double g = 0.0;
-      if (gq) { for (int r = 0; r < DIM; ++r) g = fma(ref[r], gq[(int64_t)(r * DIM + d) * P.n_cells], g); }
+      if (gq) { for (int r = 0; r < DIM; ++r) g = fma(ref[r], gq[(r * DIM + d) * GEO_BLOCK], g); }
       else g = ref[d] * P.ih[d];
       a[d] += coef * g * g;
     }
@@ -1069,7 +1070,7 @@ template <int DIM> __global__ void diag_kernel(const DiagParams P)
       int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
       double v = 1.0;
       for (int d = 0; d < DIM; ++d) v *= q1v(qd[d], jd[d]);
-      const double JxW = P.geo ? P.geo[((int64_t)q * (DIM * DIM + 1) + DIM * DIM) * P.n_cells + cell] : qweight<DIM>(q) * P.vol;
+      const double JxW = P.geo ? P.geo[blk_index(cell, q * (DIM * DIM + 1) + DIM * DIM, NN * (DIM * DIM + 1))] : qweight<DIM>(q) * P.vol;
       m += JxW * (P.ps * P.ps / P.eta[((cell / SUB) * P.n_eta + (P.n_eta == 1 ? 0 : q)) * SUB + (cell % SUB)]) * v * v;
     }
     const uint32_t ep = P.cell_nodes_p[cell * NP + i];
@@ -1506,7 +1507,8 @@ struct GeneralParams {
   const double *eta; int n_eta;
   double ih[3], vol, ps;
   int mode;                 // 0 = A block, 1 = Stokes operator, 2 = B^T
-  const double *geo;        // curved cells: [q][dim*dim + 1][n_cells] inverse Jacobian (d xi_r / d x_d, r-major) and JxW; NULL = Cartesian
+  const double *geo;        // curved cells: rows q * (dim*dim + 1) + k of a blk_index table: inverse Jacobian (d xi_r / d x_d, r-major), JxW; NULL = Cartesian
+  const uint32_t *cell_nodes_u_t, *cell_nodes_p_t;   // curved_cell_kernel: transposed maps (blk_index tables, rows = nodes)
   int compressible, newton, symmetrize, average, dilation, plain;
   const double *eps, *deta, *detadp, *dil_lhs, *ddil, *ddildp;     // [cell][q][n_sym] / [cell][q]
 };
@@ -1544,9 +1546,9 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
   // inverse Jacobian and JxW at quadrature point q (Cartesian: diag(1/h), w_q vol)
   auto geometry = [&](int q, double (&Ji)[DIM][DIM], double &JxW) {
     if (P.geo) {
-      const double *g = P.geo + (int64_t)q * (DIM * DIM + 1) * P.n_cells + cell;
-      for (int r = 0; r < DIM; ++r) for (int d = 0; d < DIM; ++d) Ji[r][d] = g[(int64_t)(r * DIM + d) * P.n_cells];
-      JxW = g[(int64_t)(DIM * DIM) * P.n_cells];
+      const double *g = P.geo + blk_index(cell, q * (DIM * DIM + 1), NN * (DIM * DIM + 1));
+      for (int r = 0; r < DIM; ++r) for (int d = 0; d < DIM; ++d) Ji[r][d] = g[(r * DIM + d) * GEO_BLOCK];
+      JxW = g[DIM * DIM * GEO_BLOCK];
     } else {
       for (int r = 0; r < DIM; ++r) for (int d = 0; d < DIM; ++d) Ji[r][d] = r == d ? P.ih[d] : 0.0;
       JxW = qweight<DIM>(q) * P.vol;
@@ -1698,7 +1700,7 @@ template <int DIM> __global__ void __launch_bounds__(64) general_cell_kernel(con
 // points live in the thread's own column of shared memory (lane-fastest, conflict-free, no barriers), the 81 accumulated
 // test-side values in registers; per point 4 small (3 x 3) contractions: reference gradient by collocation
 // (D'/a along the three lines through the point), J^-1, the stress, J^-T, and the transposed collocation derivative.
-// HBM per cell: 27 x 10 doubles of geometry (2,160 B, coalesced: consecutive threads read consecutive doubles) next to
+// HBM per cell: 27 x 10 doubles of geometry (2,160 B; a thread block reads one contiguous 138 KB chunk, blk_index) next to
 // the ~400 B of vector data, i.e. the kernel is bound by the geometry stream (G term).  The node lists of
 // unstructured meshes have no collision-free rounds, results go to global memory with one RED per DoF.
 constexpr int CV_THREADS = 64;
@@ -1709,21 +1711,24 @@ __host__ __device__ constexpr double dpc(int i, int j)
          / HOST_GAUSS_A;
 }
 template <int MODE, bool PERQ>
-__global__ void __launch_bounds__(CV_THREADS) curved_cell_kernel(const GeneralParams P)
+__global__ void __launch_bounds__(CV_THREADS, 4) curved_cell_kernel(const GeneralParams P)
 {
   static_assert(MODE >= 0 && MODE <= 2, "A block, Stokes operator, B^T");
+  static_assert(CV_THREADS == GEO_BLOCK, "one thread block reads one block of the per-cell tables");
   constexpr int NN = 27, NP = 8, G = 10;
   extern __shared__ __align__(16) double cv_smem[];
   const int64_t cell = (int64_t)blockIdx.x * CV_THREADS + threadIdx.x;
   if (cell >= P.n_cells) return;                      // (no barriers below: every thread works in its own column)
   double *U = cv_smem + threadIdx.x;                  // U[(c * 27 + q) * CV_THREADS]
+  const uint32_t *nodes_u = P.cell_nodes_u_t + blk_index(cell, 0, NN);   // transposed maps: node i at nodes_u[i * GEO_BLOCK]
+  const uint32_t *nodes_p = P.cell_nodes_p_t + blk_index(cell, 0, NP);
   if (MODE != 2) {
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       double v[NN];
 #pragma unroll
       for (int i = 0; i < NN; ++i) {
-        const uint32_t e = P.cell_nodes_u[cell * NN + i];
+        const uint32_t e = nodes_u[i * GEO_BLOCK];
         const bool cons = ((e >> (NODE_FLAG_SHIFT + c)) & 1u) && !P.plain;
         v[i] = cons ? 0.0 : P.src_u[(e & NODE_IDX_MASK) + c];
       }
@@ -1732,12 +1737,15 @@ __global__ void __launch_bounds__(CV_THREADS) curved_cell_kernel(const GeneralPa
       for (int q = 0; q < NN; ++q) U[(c * NN + q) * CV_THREADS] = v[q];
     }
   }
+  // (volatile: every use below is a fresh 8-byte shared-memory load -- otherwise the compiler keeps all 81 values in
+  //  registers next to the 81 accumulators and spills; the loads are conflict-free and cheap)
+  const volatile double *Uv = U;
   double pn[NP], Tp[NP];
 #pragma unroll
   for (int a = 0; a < NP; ++a) {
     pn[a] = 0.0; Tp[a] = 0.0;
     if (MODE != 0) {
-      const uint32_t e = P.cell_nodes_p[cell * NP + a];
+      const uint32_t e = nodes_p[a * GEO_BLOCK];
       pn[a] = ((e >> 31) && !P.plain) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
     }
   }
@@ -1746,22 +1754,31 @@ __global__ void __launch_bounds__(CV_THREADS) curved_cell_kernel(const GeneralPa
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int i = 0; i < NN; ++i) T[c][i] = 0.0;
-  const double *geo = P.geo + cell;
+  const double *geo = P.geo + blk_index(cell, 0, NN * G);               // row q * 10 + k at geo[row * GEO_BLOCK]
   const double *etab = P.eta + (cell / SUB) * P.n_eta * SUB + (cell % SUB);
   const double eta_cell = (MODE != 2 && !PERQ) ? etab[0] : 1.0;
+  // geometry of the next point travels while the current one is being worked on
+  double gn[G];
+#pragma unroll
+  for (int k = 0; k < G; ++k) gn[k] = geo[k * GEO_BLOCK];
 #pragma unroll
   for (int q = 0; q < NN; ++q) {
     const int qd[3] = {q % 3, (q / 3) % 3, q / 9};
     double Ji[3][3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Ji[k / 3][k % 3] = geo[(int64_t)(q * G + k) * P.n_cells];
-    const double JxW = geo[(int64_t)(q * G + 9) * P.n_cells];
+    for (int k = 0; k < 9; ++k) Ji[k / 3][k % 3] = gn[k];
+    const double JxW = gn[9];
+    if (q + 1 < NN) {
+#pragma unroll
+      for (int k = 0; k < G; ++k) gn[k] = geo[((q + 1) * G + k) * GEO_BLOCK];
+    }
     double S[3][3];                                   // stress times JxW
     double div = 0.0;
     if (MODE != 2) {
       double Gx[3][3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
+        const double u0 = Uv[(c * NN + q) * CV_THREADS];
         double gh[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -1769,7 +1786,7 @@ __global__ void __launch_bounds__(CV_THREADS) curved_cell_kernel(const GeneralPa
           double acc = 0.0;
 #pragma unroll
           for (int j = 0; j < 3; ++j)
-            if (dpc(qd[r], j) != 0.0) acc = fma(dpc(qd[r], j), U[(c * NN + base + j * st) * CV_THREADS], acc);
+            if (dpc(qd[r], j) != 0.0) acc = fma(dpc(qd[r], j), j == qd[r] ? u0 : Uv[(c * NN + base + j * st) * CV_THREADS], acc);
           gh[r] = acc;
         }
 #pragma unroll
@@ -1815,14 +1832,14 @@ __global__ void __launch_bounds__(CV_THREADS) curved_cell_kernel(const GeneralPa
     interpT_all<3>(T[c]);
 #pragma unroll
     for (int i = 0; i < NN; ++i) {
-      const uint32_t e = P.cell_nodes_u[cell * NN + i];
+      const uint32_t e = nodes_u[i * GEO_BLOCK];
       if (!((e >> (NODE_FLAG_SHIFT + c)) & 1u)) atomicAdd(P.dst_u + (e & NODE_IDX_MASK) + c, T[c][i]);
     }
   }
   if (MODE == 1) {
 #pragma unroll
     for (int a = 0; a < NP; ++a) {
-      const uint32_t e = P.cell_nodes_p[cell * NP + a];
+      const uint32_t e = nodes_p[a * GEO_BLOCK];
       if (!(e >> 31)) atomicAdd(P.dst_p + (e & NODE_IDX_MASK), Tp[a]);
     }
   }
@@ -1846,7 +1863,7 @@ __global__ void __launch_bounds__(128) curved_mass_kernel(const GeneralParams P)
   const double ps2 = P.ps * P.ps;
 #pragma unroll
   for (int q = 0; q < NN; ++q) {
-    const double JxW = P.geo ? P.geo[(int64_t)(q * G + DIM * DIM) * P.n_cells + cell] : qweight<DIM>(q) * P.vol;
+    const double JxW = P.geo ? P.geo[blk_index(cell, q * G + DIM * DIM, NN * G)] : qweight<DIM>(q) * P.vol;
     pq[q] *= JxW * (ps2 / etab[PERQ ? q * SUB : 0]);
   }
   quad_to_q1T<DIM>(pq, out);
@@ -1887,6 +1904,7 @@ static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, do
       const unsigned grid = (unsigned)((L.n_cells + CV_THREADS - 1) / CV_THREADS);
       const size_t smem = sizeof(double) * 81 * CV_THREADS;
       const bool perq = L.n_eta != 1;
+      P.cell_nodes_u_t = L.cell_nodes_u_t; P.cell_nodes_p_t = L.cell_nodes_p_t;
       if (mode == 0) { if (perq) curved_cell_kernel<0, true><<<grid, CV_THREADS, smem, ctx->stream>>>(P); else curved_cell_kernel<0, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P); }
       else if (mode == 1) { if (perq) curved_cell_kernel<1, true><<<grid, CV_THREADS, smem, ctx->stream>>>(P); else curved_cell_kernel<1, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P); }
       else curved_cell_kernel<2, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P);
@@ -1927,7 +1945,7 @@ template <int DIM> __global__ void rhs_kernel(const double *force_q, const uint3
   for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
   for (int q = 0; q < NN; ++q) {
     int qd[3] = {q % 3, (q / 3) % 3, DIM == 3 ? q / 9 : 0};
-    double phi = geo ? geo[((int64_t)q * (DIM * DIM + 1) + DIM * DIM) * n_cells + cell] : qweight<DIM>(q) * vol;
+    double phi = geo ? geo[blk_index(cell, q * (DIM * DIM + 1) + DIM * DIM, NN * (DIM * DIM + 1))] : qweight<DIM>(q) * vol;
     for (int d = 0; d < DIM; ++d) phi *= q2v(qd[d], id[d]);
     const double *f = force_q + (cell * NN + q) * DIM;
     for (int c = 0; c < DIM; ++c) acc[c] = fma(f[c], phi, acc[c]);

@@ -5,6 +5,7 @@
 // (DESIGN.md "Data layout"): per 64-cell batch a list of unique nodes (private nodes first) and 16-bit
 // local slots per cell, lane-transposed so a warp reads them coalesced.
 #include "smf_internal.h"
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <chrono>
@@ -29,7 +30,7 @@ static void free_level(LevelDev &L)
 {
   cudaFree(L.batch_info); cudaFree(L.node_list_u); cudaFree(L.node_slot_u); cudaFree(L.sb_lists); cudaFree(L.node_list_p); cudaFree(L.cell_loc_u); cudaFree(L.cell_loc_p);
   cudaFree(L.cell_nodes_u); cudaFree(L.cell_nodes_p); cudaFree(L.constrained_u); cudaFree(L.constrained_p);
-  cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M); cudaFree(L.geo);
+  cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M); cudaFree(L.geo); cudaFree(L.cell_nodes_u_t); cudaFree(L.cell_nodes_p_t);
   cudaFree(L.nd.eps); cudaFree(L.nd.deta); cudaFree(L.nd.detadp); cudaFree(L.nd.dil_lhs); cudaFree(L.nd.ddil); cudaFree(L.nd.ddildp);
   free_exchange(L.ex_u); free_exchange(L.ex_p);
   L = LevelDev();
@@ -304,16 +305,17 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   L.dim = dim; L.n_cells = m->n_cells; L.n_u = m->n_dofs_u; L.n_p = m->n_dofs_p;
   for (int d = 0; d < dim; ++d) L.h[d] = m->cell_size ? m->cell_size[d] : 1.0;
   if (m->geometry == 1) {
-    // [cell][q][r][d], [cell][q]  ->  [q][dim*dim + 1][cell]: consecutive cells (one per thread) read consecutive doubles
+    // [cell][q][r][d], [cell][q]  ->  blocks of 64 cells, rows q * (dim*dim + 1) + k (blk_index): consecutive cells (one
+    // per thread) read consecutive doubles and a block's rows are contiguous
     const int D2 = dim * dim, G = D2 + 1;
-    std::vector<double> geo((size_t)NN * G * L.n_cells);
+    std::vector<double> geo((size_t)NN * G * blk_cells(L.n_cells), 1.0);
     for (int64_t cell = 0; cell < L.n_cells; ++cell)
       for (int q = 0; q < NN; ++q) {
         const double *ji = m->inverse_jacobians + ((size_t)cell * NN + q) * D2;
-        for (int k = 0; k < D2; ++k) geo[((size_t)q * G + k) * L.n_cells + cell] = ji[k];
+        for (int k = 0; k < D2; ++k) geo[blk_index(cell, q * G + k, NN * G)] = ji[k];
         const double w = m->jxw[(size_t)cell * NN + q];
         if (!(w > 0.0)) return ctx->fail(SMF_ERR_INVALID, "jxw must be positive (inverted cell?)");
-        geo[((size_t)q * G + D2) * L.n_cells + cell] = w;
+        geo[blk_index(cell, q * G + D2, NN * G)] = w;
       }
     if (int e = upload(ctx, &L.geo, geo, &L.bytes)) return e;
   }
@@ -408,6 +410,15 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   if ((e = upload(ctx, &L.cell_loc_p, loc_p, &L.bytes))) return e;
   if ((e = upload(ctx, &L.cell_nodes_u, nodes_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.cell_nodes_p, nodes_p, &L.bytes))) return e;
+  if (L.geo) {
+    std::vector<uint32_t> tu((size_t)blk_cells(L.n_cells) * NN, 0), tp((size_t)blk_cells(L.n_cells) * NP, 0);
+    for (int64_t cell = 0; cell < L.n_cells; ++cell) {
+      for (int n = 0; n < NN; ++n) tu[blk_index(cell, n, NN)] = nodes_u[(size_t)cell * NN + n];
+      for (int n = 0; n < NP; ++n) tp[blk_index(cell, n, NP)] = nodes_p[(size_t)cell * NP + n];
+    }
+    if ((e = upload(ctx, &L.cell_nodes_u_t, tu, &L.bytes))) return e;
+    if ((e = upload(ctx, &L.cell_nodes_p_t, tp, &L.bytes))) return e;
+  }
   if ((e = upload(ctx, &L.constrained_u, cons_u, &L.bytes))) return e;
   if ((e = upload(ctx, &L.constrained_p, cons_p, &L.bytes))) return e;
   SMF_CUDA(cudaMalloc(&L.dinv_A, sizeof(double) * L.n_u));
@@ -579,7 +590,7 @@ __global__ void k_average_viscosity(const double *raw_q, int64_t n_cells, int nq
     for (int q = 0; q < nq; ++q) {
       const double o = op == 0 ? v[q] : avg;
       // Cartesian: reference-cell weights; curved cells: JxW of the cell (entry dim*dim of the geometry table)
-      const double w = geo ? geo[((int64_t)q * (dim * dim + 1) + dim * dim) * n_cells + cell]
+      const double w = geo ? geo[blk_index(cell, q * (dim * dim + 1) + dim * dim, nq * (dim * dim + 1))]
                            : (dim == 3 ? gw1(q % 3) * gw1((q / 3) % 3) * gw1(q / 9) : gw1(q % 3) * gw1(q / 3));
       proj += w * o; wsum += w;
       vmin = fmin(vmin, o); vmax = fmax(vmax, o);

@@ -89,6 +89,15 @@ struct NewtonDev {
   double *eps = nullptr, *deta = nullptr, *detadp = nullptr, *dil_lhs = nullptr, *ddil = nullptr, *ddildp = nullptr;
 };
 
+// Per-cell tables read by one thread per cell (curved-cell geometry, transposed cell->DoF maps) are stored in blocks of
+// GEO_BLOCK cells: [cell / 64][row][cell % 64].  Consecutive threads read consecutive words, and everything a thread
+// block needs is one contiguous chunk (n_rows x 512 B) instead of n_rows rows that lie n_cells words apart (which costs
+// a DRAM page and a TLB entry per row).
+constexpr int GEO_BLOCK = 64;
+__host__ __device__ inline int64_t blk_index(int64_t cell, int row, int n_rows)
+{ return ((cell / GEO_BLOCK) * n_rows + row) * GEO_BLOCK + (cell % GEO_BLOCK); }
+__host__ __device__ inline int64_t blk_cells(int64_t n_cells) { return (n_cells + GEO_BLOCK - 1) / GEO_BLOCK * GEO_BLOCK; }
+
 constexpr int SMF_MAX_RESTART = 200;   // longest GMRES / FGMRES restart length (nsinker_spherical_shell/gmg.prm uses 200); sizes the multi-dot scratch
 
 struct LevelDev {
@@ -111,7 +120,8 @@ struct LevelDev {
   uint32_t *constrained_u = nullptr; int64_t n_constrained_u = 0;
   uint32_t *constrained_p = nullptr; int64_t n_constrained_p = 0;
   double h[3] = {1, 1, 1};
-  double *geo = nullptr;                      // curved cells (geometry = 1): [3^dim][dim*dim + 1][n_cells] inverse Jacobian (r-major) and JxW, cell fastest
+  uint32_t *cell_nodes_u_t = nullptr, *cell_nodes_p_t = nullptr;   // curved cells: transposed maps, rows = nodes of a blk_index table (one thread per cell reads coalesced)
+  double *geo = nullptr;                      // curved cells (geometry = 1): inverse Jacobian (r-major) and JxW, rows q * (dim*dim + 1) + k of a blk_index table
   // cell data
   double *eta = nullptr; int n_eta = 0; double ps = 1.0; int compressible = 0; bool has_cell_data = false;
   NewtonDev nd;

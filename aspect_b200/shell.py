@@ -102,31 +102,42 @@ def mapping_tables(degree=4, points=GAUSS3):
 
 
 class ShellLevel:
-    """One level of the uniformly refined 96-tree spherical shell."""
+    """One level of the (rank-local part of the) uniformly refined 96-tree spherical shell.
+
+    A rank owns a contiguous range of trees (p4est orders the cells tree by tree) and numbers the DoFs of its cells locally
+    in first-touch order; nodes on faces shared with trees of other ranks exist on every rank that touches them, which is
+    what the halo exchange of the C ABI works with (`exchange_lists`)."""
     dim = 3
     KEY_BITS = 21          # per-coordinate field of the position key; quantum 2^-19
 
-    def __init__(self, level, inner_radius=0.54, outer_radius=1.0, mapping_degree=4):
+    def __init__(self, level, inner_radius=0.54, outer_radius=1.0, mapping_degree=4, rank=0, world=1):
         self.level = level
         self.n = n = 1 << level
         self.R0, self.R1 = float(inner_radius), float(outer_radius)
         self.mapping_degree = mapping_degree
+        self.rank, self.world = rank, world
         dirs, layer = coarse_shell_96()
         self.n_trees = len(dirs)
-        m = morton_cells(level, 3)
-        self.cells = np.tile(m, (self.n_trees, 1))                       # integer coordinates inside the tree
-        self.tree = np.repeat(np.arange(self.n_trees), len(m))
+        assert self.n_trees % world == 0, "the number of coarse cells (96) must be a multiple of the number of ranks"
+        self.trees_per_rank = tpr = self.n_trees // world
+        m = self._morton = morton_cells(level, 3)
+        self.cells = np.tile(m, (tpr, 1))                                 # integer coordinates inside the tree
+        self.tree = np.repeat(np.arange(rank * tpr, (rank + 1) * tpr), len(m))
         self.n_cells = len(self.cells)
         rm = 0.5 * (self.R0 + self.R1)
         self._dirs = dirs
         self._ra = np.where(layer == 0, self.R0, rm)
         self._rb = np.where(layer == 0, rm, self.R1)
         self.h = np.full(3, 1.0 / n)                                      # (reference-cell size inside the tree; unused by the curved kernels)
-        nodes_u, self.node_x_u = self._first_touch(2, _fe_local_order(2, 3), _lex(3, 3))
-        nodes_p, self.node_x_p = self._first_touch(1, _fe_local_order(1, 3), _lex(2, 3))
+        self._keys = {}
+        nodes_u, self.node_x_u = self._first_touch("u", 2, _fe_local_order(2, 3), _lex(3, 3))
+        nodes_p, self.node_x_p = self._first_touch("p", 1, _fe_local_order(1, 3), _lex(2, 3))
         n_surface = 48 * 4 ** level
-        assert len(self.node_x_u) == (4 * n_surface + 2) * (4 * n + 1), "Q2 nodes of the shell were not identified one to one"
-        assert len(self.node_x_p) == (n_surface + 2) * (2 * n + 1), "Q1 nodes of the shell were not identified one to one"
+        self.n_global_nodes = {"u": (4 * n_surface + 2) * (4 * n + 1), "p": (n_surface + 2) * (2 * n + 1)}
+        if world == 1:
+            assert len(self.node_x_u) == self.n_global_nodes["u"], "Q2 nodes of the shell were not identified one to one"
+            assert len(self.node_x_p) == self.n_global_nodes["p"], "Q1 nodes of the shell were not identified one to one"
+        self._part = {}
         self.n_u, self.n_p = 3 * len(self.node_x_u), len(self.node_x_p)
         cu = np.empty((self.n_cells, 81), dtype=_UINT)
         for c in range(3):
@@ -136,25 +147,32 @@ class ShellLevel:
         self._geom = None
 
     # -- points ------------------------------------------------------------------------------------------------
-    def points(self, ref, chunk=None):
-        """Physical positions X of the reference points ref (npts, 3) of every cell (or of the cells in `chunk`): (cells, npts, 3)."""
-        sel = slice(None) if chunk is None else chunk
-        cells, tree = self.cells[sel], self.tree[sel]
+    def points(self, ref, chunk=None, cells=None, tree=None):
+        """Physical positions X of the reference points ref (npts, 3) of every local cell (or of the cells in `chunk`, or of
+        the given cells of the given trees): (cells, npts, 3)."""
+        if cells is None:
+            sel = slice(None) if chunk is None else chunk
+            cells, tree = self.cells[sel], self.tree[sel]
         xi = (cells[:, None, :] + ref[None, :, :]) / self.n
         return tree_map(self._dirs[tree][:, None], self._ra[tree][:, None], self._rb[tree][:, None], xi)
 
-    def _first_touch(self, npd_minus1, local_order, lex_order):
+    def _node_keys(self, cells, tree, ref):
+        """Position keys (63-bit integers) of the reference points ref of the given cells: (cells, npts)."""
+        scale = float(1 << (self.KEY_BITS - 2))
+        out = np.empty((len(cells), len(ref)), dtype=np.int64)
+        step = 1 << 14
+        for s in range(0, len(cells), step):
+            x = self.points(ref, cells=cells[s:s + step], tree=tree[s:s + step])
+            q = np.rint((x + 1.0) * scale).astype(np.int64)
+            out[s:s + step] = (q[..., 0] << (2 * self.KEY_BITS)) | (q[..., 1] << self.KEY_BITS) | q[..., 2]
+        return out
+
+    def _first_touch(self, family, npd_minus1, local_order, lex_order):
         """Number the nodes in first-touch order; nodes are identified by their quantised position."""
         scale = float(1 << (self.KEY_BITS - 2))
 
         def keys(order):
-            out = np.empty((self.n_cells, len(order)), dtype=np.int64)
-            step = 1 << 14
-            for s in range(0, self.n_cells, step):
-                x = self.points(order / float(npd_minus1), slice(s, s + step))
-                q = np.rint((x + 1.0) * scale).astype(np.int64)
-                out[s:s + step] = (q[..., 0] << (2 * self.KEY_BITS)) | (q[..., 1] << self.KEY_BITS) | q[..., 2]
-            return out
+            return self._node_keys(self.cells, self.tree, order / float(npd_minus1))
 
         kfe = keys(local_order.astype(np.float64)).ravel()
         uniq, first = np.unique(kfe, return_index=True)
@@ -163,6 +181,9 @@ class ShellLevel:
         del kfe
         klex = keys(lex_order.astype(np.float64))
         cell_nodes = rank[np.searchsorted(uniq, klex.ravel())].reshape(klex.shape)
+        key_of_node = np.empty(len(uniq), dtype=np.int64)
+        key_of_node[rank] = uniq
+        self._keys[family] = key_of_node
         mask = (1 << self.KEY_BITS) - 1
         x = np.empty((len(uniq), 3))
         x[rank, 0] = (uniq >> (2 * self.KEY_BITS)) / scale - 1.0
@@ -208,16 +229,8 @@ class ShellLevel:
         return self.geometry()[0]
 
     def midpoint_geometry(self):
-        """(position (cells, 3), det J (cells,)) at the cell midpoints (QMidpoint of compute_pressure_scaling_factor)."""
-        nodes, N, dN = mapping_tables(self.mapping_degree, np.array([0.5]))
-        ref = nodes[_lex(len(nodes), 3).astype(np.int64)]
-        xm = np.empty((self.n_cells, 3)); det = np.empty(self.n_cells)
-        step = 1 << 14
-        for s in range(0, self.n_cells, step):
-            X = self.points(ref, slice(s, s + step))
-            xm[s:s + step] = np.einsum("k,ekd->ed", N[0], X)
-            det[s:s + step] = np.linalg.det(np.einsum("kr,ekd->edr", dN[0], X))
-        return xm, det
+        """(position (cells, 3), det J (cells,)) at the midpoints of the local cells (QMidpoint of compute_pressure_scaling_factor)."""
+        return self._midpoints_of(self.cells, self.tree)
 
     @property
     def jinv(self):
@@ -230,14 +243,76 @@ class ShellLevel:
     def dof_coords_u(self):
         return np.repeat(self.node_x_u, 3, axis=0)
 
+    def global_midpoint_geometry(self):
+        """midpoint_geometry() over ALL trees (the pressure scaling is a global reduction, helper_functions.cc:337-339)."""
+        if self.world == 1:
+            return self.midpoint_geometry()
+        return ShellLevel._midpoints_of(self, np.tile(self._morton, (self.n_trees, 1)), np.repeat(np.arange(self.n_trees), len(self._morton)))
+
+    def _midpoints_of(self, cells, tree):
+        nodes, N, dN = mapping_tables(self.mapping_degree, np.array([0.5]))
+        ref = nodes[_lex(len(nodes), 3).astype(np.int64)]
+        xm = np.empty((len(cells), 3)); det = np.empty(len(cells))
+        step = 1 << 14
+        for s in range(0, len(cells), step):
+            X = self.points(ref, cells=cells[s:s + step], tree=tree[s:s + step])
+            xm[s:s + step] = np.einsum("k,ekd->ed", N[0], X)
+            det[s:s + step] = np.linalg.det(np.einsum("kr,ekd->edr", dN[0], X))
+        return xm, det
+
+    # -- distributed layout ------------------------------------------------------------------------------------
+    def _partition(self, family):
+        """(global ids of the local nodes, {neighbour rank: local node indices shared with it, ordered by global id},
+        number of ranks holding every local node).  The synthetic driver finds the sharers by generating the node keys of
+        the other ranks' trees; ASPECT would read them from the Utilities::MPI::Partitioner of the level."""
+        if family not in self._part:
+            mine = self._keys[family]
+            npd = 2 if family == "u" else 1
+            ref = _lex(npd + 1, 3).astype(np.float64) / npd
+            m = self._morton
+            per_rank = []
+            for q in range(self.world):
+                if q == self.rank:
+                    per_rank.append(np.unique(mine))
+                else:
+                    tr = np.repeat(np.arange(q * self.trees_per_rank, (q + 1) * self.trees_per_rank), len(m))
+                    per_rank.append(np.unique(self._node_keys(np.tile(m, (self.trees_per_rank, 1)), tr, ref)))
+            everyone = np.unique(np.concatenate(per_rank))
+            assert len(everyone) == self.n_global_nodes[family], "nodes of the shell were not identified one to one across ranks"
+            gid = np.searchsorted(everyone, mine)
+            order = np.argsort(mine, kind="stable")
+            lists, count = {}, np.ones(len(mine), dtype=np.int64)
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                common = np.intersect1d(mine, per_rank[q], assume_unique=True)           # sorted by key = by global id
+                if len(common):
+                    idx = order[np.searchsorted(mine[order], common)]
+                    lists[q] = idx.astype(_UINT)
+                    count[idx] += 1
+            self._part[family] = (gid, lists, count)
+        return self._part[family]
+
+    def global_node_ids(self, family):
+        """Partition-independent id of every local node (rank of its position key among all nodes of the level)."""
+        return self._partition(family)[0]
+
+    def exchange_lists(self, family):
+        """{neighbour rank: local node indices shared with it, ordered by global node id (identical on both sides)}."""
+        return self._partition(family)[1]
+
+    def sharer_counts(self, family):
+        """Number of ranks that hold each local node (weights of the distributed inner products are 1 / this)."""
+        return self._partition(family)[2]
+
 
 class ShellHierarchy:
     """Levels 0..R of the uniformly refined shell; active mesh = level R."""
 
-    def __init__(self, refinement, inner_radius=0.54, outer_radius=1.0, mapping_degree=4):
+    def __init__(self, refinement, inner_radius=0.54, outer_radius=1.0, mapping_degree=4, rank=0, world=1):
         self.dim, self.R = 3, refinement
-        self.rank, self.world = 0, 1
-        self.levels = [ShellLevel(l, inner_radius, outer_radius, mapping_degree) for l in range(refinement + 1)]
+        self.rank, self.world = rank, world
+        self.levels = [ShellLevel(l, inner_radius, outer_radius, mapping_degree, rank, world) for l in range(refinement + 1)]
         self.active = self.levels[-1]
 
     def children(self, level):

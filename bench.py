@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver-timings", action="store_true", help="skip the Execute-solver-timings harness (incl. the IDR(2) solve)")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the extra BASELINE cfg 2 (refinement 5) solve")
+    ap.add_argument("--shell-refinement", type=int, default=3, help="global refinement of the extra BASELINE cfg 3 (spherical shell) block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -395,6 +396,54 @@ def main():
                                           "dofs": n1, "e2e_wall_s": t1, "e2e_mdofs": n1 / t1 / 1e6, "iterations": o1["iterations"],
                                           "pressure_normalization_adjustment": o1["pressure_normalization_adjustment"]}
         h1.close()
+        # ---- BASELINE cfg 3: benchmarks/nsinker_spherical_shell (curved cells, MappingQ(4) geometry streamed per point) ------
+        try:
+            from aspect_b200 import shell as pshell
+            R3 = args.shell_refinement
+            hier3 = pshell.ShellHierarchy(R3)
+            eta3, force3, ps3 = benchmarks.nsinker_shell_problem(hier3)
+            act3 = hier3.active
+            h3 = StokesMatrixFreeHandler(3, device=local_rank)
+            h3.setup_dofs(hier3, "zero")
+            h3.assemble(eta3, "harmonic average", ps3)
+            h3.build_preconditioner()
+            h3.parameters.update({"Linear solver tolerance": 1e-6, "Number of cheap Stokes solver steps": 2000,
+                                  "Maximum number of expensive Stokes solver steps": 0, "GMRES solver restart length": 200})
+            r3 = h3.initialize_dof_vector(0)
+            h3.assemble_stokes_rhs(force3, r3)
+            rhs3 = np.concatenate([r3.to_host(), np.zeros(act3.n_p)])
+            for _ in range(2):
+                _, o3 = h3.solve(rhs3)
+            t0 = time.time()
+            for _ in range(3):
+                _, o3 = h3.solve(rhs3)
+            t3 = (time.time() - t0) / 3
+            s3, d3 = h3.initialize_dof_vector(), h3.initialize_dof_vector()
+            s3[0].from_host(np.sin(np.arange(act3.n_u))); s3[1].from_host(np.sin(np.arange(act3.n_p)))
+
+            def time3(fn, reps=20):
+                for _ in range(3):
+                    fn()
+                h3.synchronize()
+                a = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                h3.synchronize()
+                return (time.perf_counter() - a) / reps
+            ts3 = time3(lambda: h3.stokes_matrix.vmult(d3, s3))
+            ta3 = time3(lambda: h3.A_block_matrix.vmult(d3[0], s3[0]))
+            n3 = act3.n_u + act3.n_p
+            alg3 = 16 * act3.n_u + 8 * act3.n_cells * (1 + 270)        # vectors + viscosity + G (27 points x (9 + 1) doubles)
+            line["cfg3_spherical_shell"] = {
+                "workload": "nsinker_spherical_shell 3D (96 coarse cells, R0 0.54, R1 1, MappingQ(4) geometry), 5 sinkers, viscosity ratio 1e2, "
+                            "transition-zone jump 100, harmonic average, Q2-Q1, block GMG (GMRES(200), tol 1e-06), global refinement %d" % R3,
+                "dofs": n3, "cells": act3.n_cells, "e2e_wall_s": t3, "e2e_mdofs": n3 / t3 / 1e6, "iterations": o3["iterations"],
+                "stokes_gdofs": n3 / ts3 / 1e9, "A_gdofs": act3.n_u / ta3 / 1e9,
+                "A_roofline_frac": alg3 / ta3 / 1e9 / peak, "A_algorithmic_bytes": alg3, "A_ms": ta3 * 1e3,
+                "viscosity_range": [h3.minimum_viscosity, h3.maximum_viscosity]}
+            h3.close()
+        except Exception as exc:            # the headline line above must survive a failure of the extra configuration
+            line["cfg3_spherical_shell"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_solve_throughput(args.ref_refinement, 1, 0).items()
                                 if k in ("value", "unit", "cores", "kind", "sample")}

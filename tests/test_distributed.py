@@ -36,6 +36,21 @@ for level in (1, 2, 3):
         ok &= np.allclose(np.bincount(inv, weights=allw), 1.0)      # the inner-product weights of every DoF sum to one
         n_global = np.prod(L.grid_u if fam == "u" else L.grid_p)
         ok &= len(u) == n_global
+# the 96-tree spherical shell (curved cells): 48 trees per rank, interfaces between trees of different orientation
+from aspect_b200 import shell
+for level in (0, 1):
+    L = shell.ShellLevel(level, rank=rank, world=world)
+    for fam in "up":
+        lists, gid, w = L.exchange_lists(fam), L.global_node_ids(fam), 1.0 / L.sharer_counts(fam)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, {q: gid[v] for q, v in lists.items()})
+        for q, v in lists.items():
+            ok &= np.array_equal(gid[v], everyone[q][rank])
+        tot = [None] * world
+        dist.all_gather_object(tot, (gid, w))
+        allg = np.concatenate([t[0] for t in tot]); allw = np.concatenate([t[1] for t in tot])
+        u, inv = np.unique(allg, return_inverse=True)
+        ok &= np.allclose(np.bincount(inv, weights=allw), 1.0) and len(u) == L.n_global_nodes[fam]
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
