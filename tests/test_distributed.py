@@ -85,3 +85,15 @@ def test_two_gpu_solve_matches_one_gpu():
            "--master-port", "29519", os.path.join(ROOT, "tools", "dist_check.py"), "3"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_two_gpu_shell_solve_matches_one_gpu():
+    """Curved cells over two ranks: 48 trees of the spherical shell each, halo exchange over the tree interfaces."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29521", os.path.join(ROOT, "tools", "dist_check.py"), "2", "shell"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
