@@ -164,3 +164,64 @@ def nsinker_shell_problem(hier, n_sinkers=5, viscosity_ratio=1e2, averaging="har
         rho_q = average_viscosity(rho_q, averaging)
     g = -x / np.sqrt((x * x).sum(-1, keepdims=True))
     return eta_q, rho_q[..., None] * g, pressure_scaling_shell(act, material)
+
+
+# ---- benchmarks/hollow_sphere (analytic solution on the spherical shell; the reference's test hollow_sphere_gmg) ----
+def _hollow_sphere_constants(m, R1=0.5, R2=1.0, gamma=1.0):
+    """benchmarks/hollow_sphere/hollow_sphere.cc:72-85."""
+    if m == -1:
+        alpha = -gamma * (R2 ** 3 - R1 ** 3) / (R2 ** 3 * np.log(R1) - R1 ** 3 * np.log(R2))
+        beta = -3 * gamma * (np.log(R2) - np.log(R1)) / (R1 ** 3 * np.log(R2) - R2 ** 3 * np.log(R1))
+    else:
+        alpha = gamma * (m + 1) * (R1 ** -3 - R2 ** -3) / (R1 ** (-m - 4) - R2 ** (-m - 4))
+        beta = -3 * gamma * (R1 ** (m + 1) - R2 ** (m + 1)) / (R1 ** (m + 4) - R2 ** (m + 4))
+    return alpha, beta
+
+
+def hollow_sphere_velocity(x, m=-1, gamma=1.0):
+    """`HollowSphereBoundary` = the analytic velocity (hollow_sphere.cc:56-98), spherical coordinates as in
+    source/utilities.cc:697-720."""
+    r = np.sqrt((x * x).sum(-1))
+    phi = np.arctan2(x[..., 1], x[..., 0])
+    theta = np.arccos(x[..., 2] / r)
+    alpha, beta = _hollow_sphere_constants(m)
+    if m == -1:
+        fr = alpha / (r * r) + beta * r
+        gr = -2 / (r * r) * (alpha * np.log(r) + beta / 3 * r ** 3 + gamma)
+    else:
+        fr = alpha / r ** (m + 3) + beta * r
+        gr = -2 / (r * r) * (-alpha / (m + 1) * r ** (-m - 1) + beta / 3 * r ** 3 + gamma)
+    v_r, v_t, v_p = gr * np.cos(theta), fr * np.sin(theta), fr * np.sin(theta)
+    return np.stack([np.sin(theta) * np.cos(phi) * v_r + np.cos(theta) * np.cos(phi) * v_t - np.sin(phi) * v_p,
+                     np.sin(theta) * np.sin(phi) * v_r + np.cos(theta) * np.sin(phi) * v_t + np.cos(phi) * v_p,
+                     np.cos(theta) * v_r - np.sin(theta) * v_t], axis=-1)
+
+
+def hollow_sphere_material(x, m=-1, gamma=1.0, rho_0=1000.0):
+    """`HollowSphereMaterial` (hollow_sphere.cc:355-400): viscosity r^(m+1) and the density of the manufactured solution."""
+    r = np.sqrt((x * x).sum(-1))
+    cos_theta = x[..., 2] / r
+    alpha, beta = _hollow_sphere_constants(m)
+    if m == -1:
+        rho = -(alpha / r ** 4 * (8 * np.log(r) - 6) + 8.0 / 3.0 * beta / r + 8 * gamma / r ** 4) * cos_theta + rho_0
+    else:
+        rho = -(2 * alpha * r ** -4 * (m + 3) / (m + 1) * (m - 1) - 2 * beta / 3 * (m - 1) * (m + 3) * r ** m
+                - m * (m + 5) * 2 * gamma * r ** (m - 3)) * cos_theta + rho_0
+    return r ** (m + 1), rho
+
+
+def hollow_sphere_problem(hier, m=-1, averaging="harmonic average"):
+    """(viscosity_q, force_q, pressure_scaling, boundary velocity u0 (n_u,), zero except on the boundary) of
+    tests/hollow_sphere_gmg.prm on a ShellHierarchy(R, 0.5, 1.0, n_coarse=12): radial gravity of magnitude 1, velocity
+    prescribed on both boundaries from the analytic solution (`Prescribed velocity boundary indicators`)."""
+    act = hier.active
+    x = act.quadrature_points()
+    material = lambda y: hollow_sphere_material(y, m)
+    eta_q, rho_q = material(x)
+    if averaging != "none" and not averaging.endswith("only viscosity"):
+        rho_q = average_viscosity(rho_q, averaging)
+    g = -x / np.sqrt((x * x).sum(-1, keepdims=True))
+    u0 = np.zeros(act.n_u)
+    cons = act.constrained_u("zero").astype(np.int64)
+    u0[cons] = hollow_sphere_velocity(act.node_x_u, m).ravel()[cons]
+    return eta_q, rho_q[..., None] * g, pressure_scaling_shell(act, material), u0

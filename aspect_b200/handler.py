@@ -339,11 +339,14 @@ class StokesMatrixFreeHandler:
         w = np.zeros(act.n_p)
         cp = np.asarray(act.cell_dofs_p, dtype=np.int64)
         if getattr(act, "jxw", None) is not None:
-            # curved cells: integral of every Q1 shape function with the cell's JxW values (volume normalisation only)
-            if kind != "volume":
-                raise SmfError(_lib.SMF_ERR_UNSUPPORTED, "curved meshes: Pressure normalization = volume | no")
-            from .benchmarks import _phi1_at_quad
-            np.add.at(w, cp, np.asarray(act.jxw) @ _phi1_at_quad(dim))
+            # curved cells: integral of every Q1 shape function with the cell's JxW values, or over the outer boundary faces
+            if kind == "volume":
+                from .benchmarks import _phi1_at_quad
+                np.add.at(w, cp, np.asarray(act.jxw) @ _phi1_at_quad(dim))
+            elif kind == "surface":
+                w, _ = act.surface_weights()
+            else:
+                raise SmfError(_lib.SMF_ERR_INVALID, "Pressure normalization: surface | volume | no")
         elif kind == "volume":
             np.add.at(w, cp.ravel(), float(np.prod(act.h)) / 2 ** dim)
         elif kind == "surface":

@@ -7,13 +7,19 @@ Coarse mesh = what `GridGenerator::hyper_shell(..., 96, true)` produces
 (/root/reference/source/geometry_model/spherical_shell.cc:361-373): the 12 rhombic faces of a rhombic dodecahedron
 (14 vertices: the 8 cube corners and the 6 axis points, projected onto the sphere), each split 2 x 2, times 2 radial
 layers = 96 hexahedra with 150 vertices (the reference golden `tests/spherical_nsinker_gmg_gc`: "coarse size S: 150").
-deal.II itself is not available here, so the ORDER of the coarse cells and the placement of points inside a coarse cell
-are this driver's own (documented) choice: every coarse cell is the root of one tree with the analytic map
-    X(xi, eta, zeta) = (r_a + zeta (r_b - r_a)) * normalize(bilinear blend of the 4 corner directions at (xi, eta)),
-level-l cells are the 8^l descendants in Morton order (deal.II child order), trees in coarse-cell order, and the mapping
-of every cell is the degree-4 Lagrange interpolant of X in the cell's Gauss-Lobatto points (ASPECT uses MappingQ(4)
-for curved geometries, source/simulator/core.cc:118-119).  Boundary ids: 0 = inner, 1 = outer
-(`Zero velocity boundary indicators = top, bottom` constrains both).
+Geometry = what deal.II produces on a SphericalManifold (restated from its documented algorithms; pinned by the analytic
+errors of the reference golden tests/hollow_sphere_gmg, which this geometry reproduces to all printed digits, and by the
+`Viscosity range: 0.1 - 433.496` line of tests/spherical_nsinker_gmg_gc):
+  * refinement: uniform in the radius; on the sphere a new edge vertex is the normalised mean of the edge's end points, a
+    new face vertex the weighted spherical average of the face's 4 vertices (-1/4) and 4 new edge vertices (+1/2)
+    (`quad->center(true, true)` in Triangulation::execute_refinement);
+  * MappingQ(4) (source/simulator/core.cc:118-119): the 5^3 Gauss-Lobatto support points of a cell are the weighted
+    spherical averages of the cell's own vertices with the Q1 shape functions as weights (direction: minimiser of the
+    weighted squared geodesic distances, SphericalManifold::get_new_points; radius: weighted mean), and the cell map is
+    their degree-4 Lagrange interpolant.
+Every coarse cell is the root of one tree; level-l cells are its 8^l descendants in Morton order (deal.II child order),
+trees in coarse-cell order -- the ORDER of the coarse cells (hence the DoF numbering) is this driver's own choice.
+Boundary ids: 0 = inner, 1 = outer (`Zero velocity boundary indicators = top, bottom` constrains both).
 
 DoF numbering: first touch over that cell sequence, FE-local order inside a cell, exactly as for the
 box driver (synthetic.py); nodes shared between trees are identified by their position.
@@ -30,9 +36,12 @@ _L = np.sqrt(3.0 / 7.0)
 LOBATTO5 = np.array([0.0, 0.5 - 0.5 * _L, 0.5, 0.5 + 0.5 * _L, 1.0])
 
 
-def coarse_shell_96():
-    """(96, 4, 3) unit corner directions (lexicographic: v00, v10, v01, v11, right-handed with the outward radial direction)
-    of the surface quad of every coarse cell, and (96,) radial layer (0 = inner half, 1 = outer half)."""
+def coarse_shell(n_cells=96):
+    """Corner directions (n_cells, 4, 3) (lexicographic: v00, v10, v01, v11, unit vectors, right-handed with the outward radial
+    direction) of the surface quad of every coarse cell and its radial interval as indices into (R0, Rm, R1).
+    n_cells = 96 (`GridGenerator::hyper_shell(.., 96, true)`, the default of the 3D spherical shell): every rhombic face split
+    2 x 2, two radial layers; n_cells = 12 (`Cells along circumference = 12`): the 12 rhombic faces, one layer [R0, R1]."""
+    assert n_cells in (12, 96)
     quads = []
     for k in range(3):                                   # the cube edge runs along axis k
         i, j = (k + 1) % 3, (k + 2) % 3
@@ -46,6 +55,8 @@ def coarse_shell_96():
                 if np.dot(np.cross(v[1] - v[0], v[2] - v[0]), v[0] + v[3]) < 0.0:
                     v[1], v[2] = v[2], v[1]
                 quads.append(np.array(v))
+    if n_cells == 12:
+        return np.array(quads), np.zeros(12, dtype=np.int64), np.full(12, 2, dtype=np.int64)
     dirs, layer = [], []
     for v in quads:
         # 3 x 3 lattice of the face, projected onto the sphere
@@ -60,15 +71,43 @@ def coarse_shell_96():
                 for sx in range(2):
                     dirs.append(np.array([g[sy, sx], g[sy, sx + 1], g[sy + 1, sx], g[sy + 1, sx + 1]]))
                     layer.append(r)
-    return np.array(dirs), np.array(layer, dtype=np.int64)
+    layer = np.array(layer, dtype=np.int64)
+    return np.array(dirs), layer, layer + 1
 
 
-def tree_map(dirs, ra, rb, xi):
-    """X(xi) for arrays: dirs (..., 4, 3), ra/rb (...), xi (..., 3) -> (..., 3)."""
-    x, y, z = xi[..., 0:1], xi[..., 1:2], xi[..., 2:3]
-    p = (1 - x) * (1 - y) * dirs[..., 0, :] + x * (1 - y) * dirs[..., 1, :] + (1 - x) * y * dirs[..., 2, :] + x * y * dirs[..., 3, :]
-    p = p / np.sqrt((p * p).sum(-1, keepdims=True))
-    return (ra[..., None] + z * (rb - ra)[..., None]) * p
+def sph_avg(P, W, max_iter=200):
+    """Weighted spherical average of unit vectors, vectorised: P (..., m, 3), W (..., m) with sum 1 -> (..., 3): the point x
+    on the sphere with sum_i W_i log_x(P_i) = 0 (minimiser of the weighted squared geodesic distances), by the fixed-point
+    iteration x <- exp_x(sum_i W_i log_x(P_i)) from the normalised linear average."""
+    x = (W[..., None] * P).sum(-2)
+    x /= np.sqrt((x * x).sum(-1, keepdims=True))
+    for _ in range(max_iter):
+        c = (P * x[..., None, :]).sum(-1)
+        t = P - c[..., None] * x[..., None, :]
+        nt = np.sqrt((t * t).sum(-1))
+        f = np.where(nt > 1e-300, np.arctan2(nt, c) / np.maximum(nt, 1e-300), 0.0)
+        v = ((W * f)[..., None] * t).sum(-2)
+        nv = np.sqrt((v * v).sum(-1, keepdims=True))
+        if nv.max() < 1e-15:
+            break
+        x = np.cos(nv) * x + np.where(nv > 1e-300, np.sin(nv) / np.maximum(nv, 1e-300), 1.0) * v
+        x /= np.sqrt((x * x).sum(-1, keepdims=True))
+    return x
+
+
+def refine_lattice(D):
+    """Surface vertex directions of the children: D (trees, n+1, n+1, 3) -> (trees, 2n+1, 2n+1, 3)."""
+    T, n = D.shape[0], D.shape[1] - 1
+    unit = lambda v: v / np.sqrt((v * v).sum(-1, keepdims=True))
+    F = np.zeros((T, 2 * n + 1, 2 * n + 1, 3))
+    F[:, ::2, ::2] = D
+    F[:, ::2, 1::2] = unit(D[:, :, :-1] + D[:, :, 1:])
+    F[:, 1::2, ::2] = unit(D[:, :-1, :] + D[:, 1:, :])
+    P = np.stack([D[:, :-1, :-1], D[:, :-1, 1:], D[:, 1:, :-1], D[:, 1:, 1:],
+                  F[:, 0:-1:2, 1::2], F[:, 2::2, 1::2], F[:, 1::2, 0:-1:2], F[:, 1::2, 2::2]], axis=-2)
+    W = np.broadcast_to(np.array([-0.25] * 4 + [0.5] * 4), P.shape[:-1])
+    F[:, 1::2, 1::2] = sph_avg(P, W)
+    return F
 
 
 def _lagrange_tables(nodes, x):
@@ -110,30 +149,35 @@ class ShellLevel:
     dim = 3
     KEY_BITS = 21          # per-coordinate field of the position key; quantum 2^-19
 
-    def __init__(self, level, inner_radius=0.54, outer_radius=1.0, mapping_degree=4, rank=0, world=1):
+    def __init__(self, level, inner_radius=0.54, outer_radius=1.0, mapping_degree=4, rank=0, world=1, n_coarse=96):
         self.level = level
+        self.n_coarse = n_coarse
         self.n = n = 1 << level
         self.R0, self.R1 = float(inner_radius), float(outer_radius)
         self.mapping_degree = mapping_degree
         self.rank, self.world = rank, world
-        dirs, layer = coarse_shell_96()
+        dirs, ia, ib = coarse_shell(n_coarse)
         self.n_trees = len(dirs)
-        assert self.n_trees % world == 0, "the number of coarse cells (96) must be a multiple of the number of ranks"
+        assert self.n_trees % world == 0, "the number of coarse cells must be a multiple of the number of ranks"
         self.trees_per_rank = tpr = self.n_trees // world
         m = self._morton = morton_cells(level, 3)
         self.cells = np.tile(m, (tpr, 1))                                 # integer coordinates inside the tree
         self.tree = np.repeat(np.arange(rank * tpr, (rank + 1) * tpr), len(m))
         self.n_cells = len(self.cells)
-        rm = 0.5 * (self.R0 + self.R1)
-        self._dirs = dirs
-        self._ra = np.where(layer == 0, self.R0, rm)
-        self._rb = np.where(layer == 0, rm, self.R1)
+        radii = np.array([self.R0, 0.5 * (self.R0 + self.R1), self.R1])
+        self._ra, self._rb = radii[ia], radii[ib]
+        # surface vertex lattice of every tree at this level: _lattice[t, j, i] = direction of vertex (i, j)
+        D = np.stack([np.stack([dirs[:, 0], dirs[:, 1]], axis=1), np.stack([dirs[:, 2], dirs[:, 3]], axis=1)], axis=1)
+        for _ in range(level):
+            D = refine_lattice(D)
+        self._lattice = D
         self.h = np.full(3, 1.0 / n)                                      # (reference-cell size inside the tree; unused by the curved kernels)
         self._keys = {}
         nodes_u, self.node_x_u = self._first_touch("u", 2, _fe_local_order(2, 3), _lex(3, 3))
         nodes_p, self.node_x_p = self._first_touch("p", 1, _fe_local_order(1, 3), _lex(2, 3))
-        n_surface = 48 * 4 ** level
-        self.n_global_nodes = {"u": (4 * n_surface + 2) * (4 * n + 1), "p": (n_surface + 2) * (2 * n + 1)}
+        n_surface = (48 if n_coarse == 96 else 12) * 4 ** level          # surface quads; radial cells: 2 n (96) or n (12)
+        nr = (2 if n_coarse == 96 else 1) * n
+        self.n_global_nodes = {"u": (4 * n_surface + 2) * (2 * nr + 1), "p": (n_surface + 2) * (nr + 1)}
         if world == 1:
             assert len(self.node_x_u) == self.n_global_nodes["u"], "Q2 nodes of the shell were not identified one to one"
             assert len(self.node_x_p) == self.n_global_nodes["p"], "Q1 nodes of the shell were not identified one to one"
@@ -153,8 +197,17 @@ class ShellLevel:
         if cells is None:
             sel = slice(None) if chunk is None else chunk
             cells, tree = self.cells[sel], self.tree[sel]
-        xi = (cells[:, None, :] + ref[None, :, :]) / self.n
-        return tree_map(self._dirs[tree][:, None], self._ra[tree][:, None], self._rb[tree][:, None], xi)
+        ref = np.asarray(ref, dtype=np.float64)
+        # the direction depends on (x, y) only: spherical average of the cell's 4 corner directions with Q1 weights
+        xy, inv = np.unique(ref[:, :2], axis=0, return_inverse=True)
+        inv = inv.ravel()
+        L, i, j = self._lattice, cells[:, 0], cells[:, 1]
+        C = np.stack([L[tree, j, i], L[tree, j, i + 1], L[tree, j + 1, i], L[tree, j + 1, i + 1]], axis=1)       # (cells, 4, 3)
+        x, y = xy[:, 0], xy[:, 1]
+        W = np.stack([(1 - x) * (1 - y), x * (1 - y), (1 - x) * y, x * y], axis=1)                            # (pts, 4)
+        d = sph_avg(np.broadcast_to(C[:, None], (len(cells), len(xy), 4, 3)), np.broadcast_to(W[None], (len(cells), len(xy), 4)))
+        r = self._ra[tree][:, None] + (cells[:, 2:3] + ref[None, :, 2]) / self.n * (self._rb - self._ra)[tree][:, None]
+        return r[..., None] * d[:, inv]
 
     def _node_keys(self, cells, tree, ref):
         """Position keys (63-bit integers) of the reference points ref of the given cells: (cells, npts)."""
@@ -243,6 +296,31 @@ class ShellLevel:
     def dof_coords_u(self):
         return np.repeat(self.node_x_u, 3, axis=0)
 
+    def surface_weights(self):
+        """(integral of every Q1 pressure shape function over the outer boundary (n_p,), area of this rank's part of it):
+        `Pressure normalization = surface` (helper_functions.cc:765-870; 3 x 3 Gauss points per boundary face)."""
+        nodes, _, _ = mapping_tables(self.mapping_degree)
+        V, D = _lagrange_tables(nodes, GAUSS3)
+        V1, _ = _lagrange_tables(nodes, np.array([1.0]))
+        ref = nodes[_lex(len(nodes), 3).astype(np.int64)]
+        top = np.flatnonzero((self._rb[self.tree] == self.R1) & (self.cells[:, 2] == self.n - 1))
+        w = np.zeros(self.n_p)
+        area = 0.0
+        nk = len(nodes)
+        Tx = np.einsum("l,bj,ai->balji", V1[0], V, D).reshape(9, nk ** 3)          # d/dx of the face map at the 3 x 3 points
+        Ty = np.einsum("l,bj,ai->balji", V1[0], D, V).reshape(9, nk ** 3)
+        q1 = np.stack([1 - GAUSS3, GAUSS3], axis=1)
+        phi = np.einsum("bj,ai->baji", q1, q1).reshape(9, 4)                         # face shape functions (x fastest)
+        gw = np.einsum("b,a->ba", GAUSS3_W, GAUSS3_W).ravel()
+        step = 1 << 13
+        for s in range(0, len(top), step):
+            sel = top[s:s + step]
+            X = self.points(ref, cells=self.cells[sel], tree=self.tree[sel])
+            da = np.sqrt((np.cross(np.matmul(Tx[None], X), np.matmul(Ty[None], X)) ** 2).sum(-1)) * gw[None, :]
+            area += da.sum()
+            np.add.at(w, self.cell_dofs_p[sel][:, 4:].astype(np.int64), da @ phi)
+        return w, float(area)
+
     def global_midpoint_geometry(self):
         """midpoint_geometry() over ALL trees (the pressure scaling is a global reduction, helper_functions.cc:337-339)."""
         if self.world == 1:
@@ -309,10 +387,10 @@ class ShellLevel:
 class ShellHierarchy:
     """Levels 0..R of the uniformly refined shell; active mesh = level R."""
 
-    def __init__(self, refinement, inner_radius=0.54, outer_radius=1.0, mapping_degree=4, rank=0, world=1):
+    def __init__(self, refinement, inner_radius=0.54, outer_radius=1.0, mapping_degree=4, rank=0, world=1, n_coarse=96):
         self.dim, self.R = 3, refinement
         self.rank, self.world = rank, world
-        self.levels = [ShellLevel(l, inner_radius, outer_radius, mapping_degree, rank, world) for l in range(refinement + 1)]
+        self.levels = [ShellLevel(l, inner_radius, outer_radius, mapping_degree, rank, world, n_coarse) for l in range(refinement + 1)]
         self.active = self.levels[-1]
 
     def children(self, level):

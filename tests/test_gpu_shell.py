@@ -166,3 +166,50 @@ def test_shell_solve_matches_oracle(meshes, fast):
     # the pressure is determined up to a constant (no-slip everywhere): compare after removing the mean
     assert rel(sol[nu:] - sol[nu:].mean(), xs[nu:] - xs[nu:].mean()) < 1e-4
     h.close()
+
+
+def test_hollow_sphere_matches_oracle_and_reference_golden():
+    """tests/hollow_sphere_gmg through the C ABI: curved cells, inhomogeneous boundary values (smf_correct_stokes_rhs),
+    `Pressure normalization = surface` on the curved outer boundary.  Same iterations as the oracle, solution 1e-8, and the
+    reference's analytic error norms (golden: 1.307365e-01, 1.699214e+00, 5.712572e-02, 1.076640e+00)."""
+    from oracle import hollow_sphere as hs
+    from util import golden
+    g = golden("hollow_sphere_gmg")
+    ohier, hier = oshell.ShellHierarchy(1, 0.5, 1.0, n_coarse=12), pshell.ShellHierarchy(1, 0.5, 1.0, n_coarse=12)
+    L, act = ohier.active, hier.active
+    eta_q, force_q, ps, u0 = benchmarks.hollow_sphere_problem(hier)
+    # oracle
+    active, levels, _, _ = coeff.viscosity_tables(ohier, hs.material(L.xq)[0], "harmonic")
+    f = assembled.rhs_force(L, coeff.average(hs.material(L.xq)[1], "harmonic")[..., None] * (-L.xq / np.linalg.norm(L.xq, axis=-1, keepdims=True)))
+    cons = L.constrained_u("zero")
+    K, _, _ = assembled.stokes_matrix(L, active, ps, None)
+    rhs = np.concatenate([f, np.zeros(L.n_p)]) - K @ np.concatenate([u0, np.zeros(L.n_p)])
+    rhs[cons] = 0.0
+    want = solver.BlockGMGStokes(solver.AssembledBackend(ohier, active, levels, ps, "zero")).solve(rhs, tol_rel=1e-8, restart=100, max_its=200)
+    # GPU
+    h = StokesMatrixFreeHandler(3)
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, "harmonic average", ps)
+    h.build_preconditioner()
+    h.parameters.update({"Linear solver tolerance": 1e-8, "Number of cheap Stokes solver steps": 200,
+                         "Maximum number of expensive Stokes solver steps": 0, "Pressure normalization": "surface"})
+    r, b0, sol = h.initialize_dof_vector(), h.initialize_dof_vector(), h.initialize_dof_vector()
+    h.assemble_stokes_rhs(force_q, r[0]); r[1].zero()
+    b0[0].from_host(u0); b0[1].zero()
+    h.correct_stokes_rhs(r, b0)
+    assert rel(np.concatenate([r[0].to_host(), r[1].to_host()]), rhs) < 1e-12
+    sol[0].zero(); sol[1].zero()
+    out = h.solve_device(sol, r)
+    assert out["converged"] and out["iterations"] == want["iterations"]
+    assert abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 1
+    u = sol[0].to_host() + u0
+    assert rel(u, want["x"][:L.n_u] + u0) < 1e-8
+    h.set_pressure_normalization("surface")
+    h.postprocess_pressure(sol[1], ps, True)
+    p = sol[1].to_host()
+    w, area = hs.surface_mean_weights(L)
+    po = want["x"][L.n_u:] * ps
+    assert rel(p, po - (w @ po) / area) < 1e-8
+    for got, ref in zip(hs.errors(L, u, p), g["errors_uL1_pL1_uL2_pL2"][0]):
+        assert abs(got / float(ref) - 1.0) < 2e-6
+    h.close()

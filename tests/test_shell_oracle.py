@@ -71,8 +71,9 @@ def test_curved_assembled_operators(hiers):
 
 def test_shell_benchmark_inputs(hiers):
     """The material / gravity / pressure-scaling restatements of benchmarks/nsinker_spherical_shell agree between oracle and
-    driver; the viscosity range is close to the reference's 0.1 - 433.496 (the interior point placement of the mesh is
-    this repo's own, see aspect_b200/shell.py, so the maximum over the quadrature points differs in the second digit)."""
+    driver, and the "Viscosity range: 0.1 - 433.496" line of the reference golden is reproduced to its printed digits:
+    the maximum of the harmonic cell averages is sensitive to where the quadrature points lie, so this pins the
+    SphericalManifold / MappingQ(4) restatement of the geometry (a different placement of the interior points gave 420.7)."""
     o, p = hiers
     eta_q, force_q, ps = benchmarks.nsinker_shell_problem(p)
     eo, ro = coeff.nsinker_shell(o.active.xq)
@@ -81,7 +82,60 @@ def test_shell_benchmark_inputs(hiers):
     assert abs(ps - coeff.pressure_scaling_shell(o.active, coeff.nsinker_shell(xm)[0], det)) < 1e-9 * ps
     act, levels, emin, emax = coeff.viscosity_tables(o, eo, "harmonic")
     g = golden("spherical_nsinker_gmg_gc")["viscosity_range"][0]
-    assert abs(emin - g[0]) < 1e-12 and abs(emax - g[1]) < 0.05 * g[1]
+    assert abs(emin - g[0]) < 1e-12 and abs(emax - g[1]) < 5e-4
     rho = coeff.average(ro, "harmonic")
     gdir = -o.active.xq / np.linalg.norm(o.active.xq, axis=-1, keepdims=True)
     assert np.abs(force_q - rho[..., None] * gdir).max() < 1e-12
+
+
+def test_spherical_nsinker_golden_iterations(hiers):
+    """tests/spherical_nsinker_gmg_gc, first solve: 106 GMRES iterations in the reference (4 MPI ranks, deal.II's own
+    coarse-cell order); the oracle on this repository's numbering of the same mesh takes 110.  The Chebyshev eigenvalue
+    estimates start from `global DoF index mod 11`, so the count moves by a few iterations with the numbering; before the
+    geometry was pinned (other interior points) it was 345."""
+    from oracle import solver
+    o, _ = hiers
+    L = o.active
+    eo, ro = coeff.nsinker_shell(L.xq)
+    active, levels, emin, emax = coeff.viscosity_tables(o, eo, "harmonic")
+    xm, det = L.midpoint_geometry()
+    ps = coeff.pressure_scaling_shell(L, coeff.nsinker_shell(xm)[0], det)
+    g = -L.xq / np.linalg.norm(L.xq, axis=-1, keepdims=True)
+    f = assembled.rhs_force(L, coeff.average(ro, "harmonic")[..., None] * g)
+    f[L.constrained_u("zero")] = 0.0
+    be = solver.AssembledBackend(o, active, levels, ps, "zero")
+    out = solver.BlockGMGStokes(be).solve(np.concatenate([f, np.zeros(L.n_p)]), tol_rel=1e-6, restart=200, max_its=2000)
+    gold = golden("spherical_nsinker_gmg_gc")["stokes_iterations_cheap_expensive"][0][0]
+    assert out["converged"] and gold == 106 and abs(out["iterations"] - gold) <= 5, out["iterations"]
+
+
+def test_hollow_sphere_golden():
+    """tests/hollow_sphere_gmg (12-cell shell refined once, analytic solution prescribed on both boundaries, block GMG):
+    the four error norms of the reference golden are reproduced to their printed digits (p_L1 to 1e-6: solver tolerance)
+    and the solve takes 34 iterations against the reference's 33."""
+    from oracle import hollow_sphere as hs, solver
+    g = golden("hollow_sphere_gmg")
+    h = oshell.ShellHierarchy(1, 0.5, 1.0, n_coarse=12)
+    L = h.active
+    assert [L.n_u, L.n_p] == g["dofs_u_p"][0] and L.n_cells == g["active_cells"][0]
+    eta_q, rho_q = hs.material(L.xq)
+    active, levels, _, _ = coeff.viscosity_tables(h, eta_q, "harmonic")
+    xm, det = L.midpoint_geometry()
+    ps = float(np.exp((np.log(hs.material(xm)[0]) * det).sum() / det.sum()) / (1e4 / (6336000.0 - 3481000.0) * 0.5))
+    gdir = -L.xq / np.linalg.norm(L.xq, axis=-1, keepdims=True)
+    f = assembled.rhs_force(L, coeff.average(rho_q, "harmonic")[..., None] * gdir)
+    cons = L.constrained_u("zero")
+    u0 = np.zeros(L.n_u)
+    u0[cons] = hs.velocity(L.node_x_u).ravel()[cons]
+    K, _, _ = assembled.stokes_matrix(L, active, ps, None)
+    rhs = np.concatenate([f, np.zeros(L.n_p)]) - K @ np.concatenate([u0, np.zeros(L.n_p)])       # correct_stokes_rhs
+    rhs[cons] = 0.0
+    be = solver.AssembledBackend(h, active, levels, ps, "zero")
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-8, restart=100, max_its=200)
+    assert out["converged"] and abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 1
+    u, p = out["x"][:L.n_u] + u0, out["x"][L.n_u:] * ps
+    w, area = hs.surface_mean_weights(L)
+    p = p - (w @ p) / area                                            # Pressure normalization = surface
+    err = hs.errors(L, u, p)
+    for got, want in zip(err, g["errors_uL1_pL1_uL2_pL2"][0]):
+        assert abs(got / float(want) - 1.0) < 2e-6, (err, g["errors_uL1_pL1_uL2_pL2"][0])

@@ -126,7 +126,29 @@ def timing(R):
             h.close()
 
 
+def profile(R):
+    """A few launches of the curved-cell kernels for an ncu capture."""
+    hier = pshell.ShellHierarchy(R)
+    eta_q, force_q, ps = benchmarks.nsinker_shell_problem(hier)
+    act = hier.active
+    h = StokesMatrixFreeHandler(3)
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, "harmonic average", ps)
+    src = h.initialize_dof_vector(); dst = h.initialize_dof_vector()
+    rng = np.random.default_rng(0)
+    src[0].from_host(rng.uniform(-1, 1, act.n_u)); src[1].from_host(rng.uniform(-1, 1, act.n_p))
+    for _ in range(3):
+        h.A_block_matrix.vmult(dst[0], src[0])
+        h.stokes_matrix.vmult(dst, src)
+        h.BT_block.vmult(dst, src)
+    h.synchronize()
+    h.close()
+
+
 if __name__ == "__main__":
+    if "--profile" in sys.argv:
+        profile(int(sys.argv[-1]))
+        sys.exit(0)
     if "--no-parity" not in sys.argv:
         parity()
     Rs = [int(a) for a in sys.argv[1:] if a.isdigit()]
