@@ -13,6 +13,7 @@
 // dim warps of the block.  Results are accumulated in the shared staging area in collision-free rounds and
 // flushed once per batch: nodes private to the batch with plain stores, shared nodes with one RED each.
 #include "smf_internal.h"
+#include <cuda/ptx>
 #include <type_traits>
 #include <algorithm>
 
@@ -1845,6 +1846,170 @@ __global__ void __launch_bounds__(CV_THREADS, 4) curved_cell_kernel(const Genera
   }
 }
 
+// Same kernel with the geometry stream taken off the threads: the 64 cells of a block own one contiguous chunk of the
+// geometry table (blk_index), so thread 0 bulk-copies the 5,120 bytes of a quadrature point into a shared-memory stage
+// (cp.async.bulk = the TMA engine, completion on an mbarrier) CV_STAGES points ahead; no registers are tied up while the
+// data travels and the loads do not depend on the warps' progress.
+constexpr int CV_STAGES = 2;
+template <int MODE, bool PERQ>
+__global__ void __launch_bounds__(CV_THREADS, 4) curved_cell_kernel_tma(const GeneralParams P)
+{
+  static_assert(MODE >= 0 && MODE <= 2, "A block, Stokes operator, B^T");
+  static_assert(CV_THREADS == GEO_BLOCK, "one thread block reads one block of the per-cell tables");
+  constexpr int NN = 27, NP = 8, G = 10;
+  extern __shared__ __align__(128) double cv_smem[];
+  // [CV_STAGES][10][64] geometry of one quadrature point of the block's 64 cells per stage (bulk-copied, 5,120 B each),
+  // then the threads' columns of point values; one mbarrier per stage
+  double *stage = cv_smem;
+  double *U = cv_smem + CV_STAGES * G * CV_THREADS + threadIdx.x;          // U[(c * 27 + q) * CV_THREADS]
+  __shared__ __align__(8) uint64_t bar[CV_STAGES];
+  const int tid = threadIdx.x;
+  const int64_t cell0 = (int64_t)blockIdx.x * CV_THREADS, cell = cell0 + tid;
+  const bool active = cell < P.n_cells;               // (all threads stay: the block synchronises once per point)
+  const int64_t cc = active ? cell : P.n_cells - 1;   // idle threads of the last block repeat its last cell and write nothing
+  const double *geo_blk = P.geo + blk_index(cell0, 0, NN * G);             // the block's contiguous chunk: point q at + q * 640
+  constexpr uint32_t STAGE_BYTES = G * CV_THREADS * sizeof(double);
+  const auto issue = [&](int q) {                     // (thread 0) arm the stage's barrier and start the bulk copy of point q
+    const int st = q % CV_STAGES;
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar[st], STAGE_BYTES);
+    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, stage + st * G * CV_THREADS,
+                             geo_blk + (int64_t)q * G * CV_THREADS, STAGE_BYTES, &bar[st]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < CV_STAGES; ++st) cuda::ptx::mbarrier_init(&bar[st], 1);
+    cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);                // the initialised barriers are visible to the copy engine
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < CV_STAGES; ++q) issue(q);
+  }
+  const uint32_t *nodes_u = P.cell_nodes_u_t + blk_index(cc, 0, NN);     // transposed maps: node i at nodes_u[i * GEO_BLOCK]
+  const uint32_t *nodes_p = P.cell_nodes_p_t + blk_index(cc, 0, NP);
+  if (MODE != 2) {
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      double v[NN];
+#pragma unroll
+      for (int i = 0; i < NN; ++i) {
+        const uint32_t e = nodes_u[i * GEO_BLOCK];
+        const bool cons = ((e >> (NODE_FLAG_SHIFT + c)) & 1u) && !P.plain;
+        v[i] = cons ? 0.0 : P.src_u[(e & NODE_IDX_MASK) + c];      // (idle threads: the last cell's DoFs, valid addresses)
+      }
+      interp_all<3>(v);
+#pragma unroll
+      for (int q = 0; q < NN; ++q) U[(c * NN + q) * CV_THREADS] = v[q];
+    }
+  }
+  // (volatile: every use below is a fresh 8-byte shared-memory load -- otherwise the compiler keeps all 81 values in
+  //  registers next to the 81 accumulators and spills; the loads are conflict-free and cheap)
+  const volatile double *Uv = U;
+  double pn[NP], Tp[NP];
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    pn[a] = 0.0; Tp[a] = 0.0;
+    if (MODE != 0) {
+      const uint32_t e = nodes_p[a * GEO_BLOCK];
+      pn[a] = ((e >> 31) && !P.plain) ? 0.0 : P.src_p[e & NODE_IDX_MASK];
+    }
+  }
+  double T[3][NN];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < NN; ++i) T[c][i] = 0.0;
+  const double *etab = P.eta + (cc / SUB) * P.n_eta * SUB + (cc % SUB);
+  const double eta_cell = (MODE != 2 && !PERQ) ? etab[0] : 1.0;
+#pragma unroll
+  for (int q = 0; q < NN; ++q) {
+    const int qd[3] = {q % 3, (q / 3) % 3, q / 9};
+    // wait for the point's geometry (stage q % CV_STAGES, its (q / CV_STAGES)-th use), take this thread's 10 values, hand the
+    // stage back: the copies of the next CV_STAGES - 1 points are in flight meanwhile
+    {
+      const uint32_t parity = (q / CV_STAGES) & 1;
+      while (!cuda::ptx::mbarrier_try_wait_parity(&bar[q % CV_STAGES], parity)) {}
+    }
+    const double *sg = stage + (q % CV_STAGES) * G * CV_THREADS + tid;
+    double Ji[3][3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ji[k / 3][k % 3] = sg[k * CV_THREADS];
+    const double JxW = sg[9 * CV_THREADS];
+    __syncthreads();
+    if (tid == 0 && q + CV_STAGES < NN) issue(q + CV_STAGES);
+    double S[3][3];                                   // stress times JxW
+    double div = 0.0;
+    if (MODE != 2) {
+      double Gx[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double u0 = Uv[(c * NN + q) * CV_THREADS];
+        double gh[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int st = stride3(r), base = q - qd[r] * st;
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (dpc(qd[r], j) != 0.0) acc = fma(dpc(qd[r], j), j == qd[r] ? u0 : Uv[(c * NN + base + j * st) * CV_THREADS], acc);
+          gh[r] = acc;
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Gx[c][d] = gh[0] * Ji[0][d] + gh[1] * Ji[1][d] + gh[2] * Ji[2][d];
+      }
+      div = Gx[0][0] + Gx[1][1] + Gx[2][2];
+      const double ew = (PERQ ? etab[q * SUB] : eta_cell) * JxW;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) S[c][d] = ew * (Gx[c][d] + Gx[d][c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) S[c][d] = 0.0;
+    }
+    if (MODE != 0) {
+      double valp = 0.0;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) valp = fma(pn[a], q1v(qd[0], a & 1) * q1v(qd[1], (a >> 1) & 1) * q1v(qd[2], a >> 2), valp);
+      const double pw = P.ps * valp * JxW;
+      S[0][0] -= pw; S[1][1] -= pw; S[2][2] -= pw;
+      if (MODE == 1) {
+        const double pt = -P.ps * div * JxW;
+#pragma unroll
+        for (int a = 0; a < NP; ++a) Tp[a] = fma(pt, q1v(qd[0], a & 1) * q1v(qd[1], (a >> 1) & 1) * q1v(qd[2], a >> 2), Tp[a]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double sh = S[c][0] * Ji[r][0] + S[c][1] * Ji[r][1] + S[c][2] * Ji[r][2];
+        const int st = stride3(r), base = q - qd[r] * st;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (dpc(qd[r], j) != 0.0) T[c][base + j * st] = fma(dpc(qd[r], j), sh, T[c][base + j * st]);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    interpT_all<3>(T[c]);
+#pragma unroll
+    for (int i = 0; i < NN; ++i) {
+      const uint32_t e = nodes_u[i * GEO_BLOCK];
+      if (active && !((e >> (NODE_FLAG_SHIFT + c)) & 1u)) atomicAdd(P.dst_u + (e & NODE_IDX_MASK) + c, T[c][i]);
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      const uint32_t e = nodes_p[a * GEO_BLOCK];
+      if (active && !(e >> 31)) atomicAdd(P.dst_p + (e & NODE_IDX_MASK), Tp[a]);
+    }
+  }
+}
+
 // pressure mass matrix on curved cells (or any mesh without batch structure): one thread per cell
 template <int DIM, bool PERQ>
 __global__ void __launch_bounds__(128) curved_mass_kernel(const GeneralParams P)
@@ -1905,6 +2070,21 @@ static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, do
       const size_t smem = sizeof(double) * 81 * CV_THREADS;
       const bool perq = L.n_eta != 1;
       P.cell_nodes_u_t = L.cell_nodes_u_t; P.cell_nodes_p_t = L.cell_nodes_p_t;
+      if (ctx->use_curved_tma) {
+        const size_t smem_tma = smem + sizeof(double) * CV_STAGES * 10 * CV_THREADS;
+        static bool configured = false;
+        if (!configured) {
+          SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+          SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+          SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+          SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+          SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+          configured = true;
+        }
+        if (mode == 0) { if (perq) curved_cell_kernel_tma<0, true><<<grid, CV_THREADS, smem_tma, ctx->stream>>>(P); else curved_cell_kernel_tma<0, false><<<grid, CV_THREADS, smem_tma, ctx->stream>>>(P); }
+        else if (mode == 1) { if (perq) curved_cell_kernel_tma<1, true><<<grid, CV_THREADS, smem_tma, ctx->stream>>>(P); else curved_cell_kernel_tma<1, false><<<grid, CV_THREADS, smem_tma, ctx->stream>>>(P); }
+        else curved_cell_kernel_tma<2, false><<<grid, CV_THREADS, smem_tma, ctx->stream>>>(P);
+      } else
       if (mode == 0) { if (perq) curved_cell_kernel<0, true><<<grid, CV_THREADS, smem, ctx->stream>>>(P); else curved_cell_kernel<0, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P); }
       else if (mode == 1) { if (perq) curved_cell_kernel<1, true><<<grid, CV_THREADS, smem, ctx->stream>>>(P); else curved_cell_kernel<1, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P); }
       else curved_cell_kernel<2, false><<<grid, CV_THREADS, smem, ctx->stream>>>(P);

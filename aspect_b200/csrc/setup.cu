@@ -271,6 +271,7 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   else if (option == SMF_OPT_ORTHO_SINGLE_PASS) ctx->ortho_single_pass = value ? 1 : 0;
   else if (option == SMF_OPT_PIPELINED_KERNEL) ctx->use_pipelined = value ? 1 : 0;
   else if (option == SMF_OPT_CURVED_SUMFAC) ctx->use_curved_fast = value ? 1 : 0;
+  else if (option == SMF_OPT_CURVED_TMA) ctx->use_curved_tma = value ? 1 : 0;
   else if (option == SMF_OPT_MAX_GRID_BLOCKS) ctx->max_grid_blocks = value > 0 ? value : 0;
   else if (option == SMF_OPT_P2P_EXCHANGE) ctx->use_p2p = value ? 1 : 0;
   else return ctx->fail(SMF_ERR_INVALID, "unknown option");

@@ -212,6 +212,7 @@ struct smf_ctx {
   int use_graphs = 1;
   int ortho_single_pass = 1;                          // GMRES: re-orthogonalise through the Gram matrix (1) or with a second pass over the basis (0)
   int max_grid_blocks = 0;                            // > 0: cap on the persistent grids (tests: forces several bricks per block)
+  int use_curved_tma = 0;                             // curved cells: geometry staged by cp.async.bulk + mbarrier (SMF_OPT_CURVED_TMA)
   int use_curved_fast = 1;                            // curved cells: sum-factorised one-thread-per-cell kernel (0: the general restatement kernel)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
   int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)

@@ -10,6 +10,7 @@ and the same operator objects with `vmult(dst, src)`:
 All compute goes through aspect_b200/libsmf_b200.so; this file only marshals arrays.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -75,6 +76,7 @@ class StokesMatrixFreeHandler:
         self.p2p_exchange = True                 # >1 rank: halo exchange as one kernel over NVLink peer memory (False: NCCL send/recv)
         self.gram_reorthogonalization = True     # GMRES: CGS2 in one sweep over the basis (False: two sweeps)
         self.curved_sum_factorization = True     # curved cells: sum-factorised kernel (False: the general per-cell restatement kernel)
+        self.curved_tma_geometry = os.environ.get("SMF_CURVED_TMA", "0") == "1"    # geometry stream staged by cp.async.bulk + mbarrier
         # Chebyshev eigenvalue start vector from partition-independent global DoF numbers (always on for >1 rank)
         self.global_start_vector = False
         # "Solver parameters/Stokes solver parameters" (names verbatim from source/simulator/parameters.cc:439-584)
@@ -140,6 +142,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_SUMFAC, int(self.curved_sum_factorization)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_TMA, int(self.curved_tma_geometry)))
         self._keep = []
         self.rank, self.world = getattr(hierarchy, "rank", 0), getattr(hierarchy, "world", 1)
         self._comm_init()

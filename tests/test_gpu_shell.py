@@ -87,6 +87,34 @@ def test_curved_operators(meshes, averaging, fast):
     h.close()
 
 
+def test_curved_tma_staged_geometry(meshes):
+    """SMF_OPT_CURVED_TMA: the same kernel with the geometry of each quadrature point bulk-copied (cp.async.bulk + mbarrier)
+    into a two-stage shared-memory ring by one thread; identical results, kept as an option (it is slower)."""
+    ohier, hier = meshes
+    eta_q = np.exp(np.random.default_rng(5).uniform(-4, 4, size=(hier.active.n_cells, 27)))
+    h = StokesMatrixFreeHandler(3)
+    h.curved_tma_geometry = True
+    h.setup_dofs(hier, "zero")
+    h.assemble(eta_q, "none", 3.7)
+    active, levels, _, _ = coeff.viscosity_tables(ohier, eta_q, "none")
+    ob = solver.AssembledBackend(ohier, active, levels, 3.7, "zero")
+    act = hier.active
+    xu, xp = seeded(act.n_u, 1), seeded(act.n_p, 2)
+    src = h.initialize_dof_vector(); dst = h.initialize_dof_vector()
+    src[0].from_host(xu); src[1].from_host(xp)
+    h.stokes_matrix.vmult(dst, src)
+    yu, yp = ob.stokes(xu, xp)
+    assert rel(dst[0].to_host(), yu) < TOL and rel(dst[1].to_host(), yp) < TOL
+    h.BT_block.vmult(dst, src)
+    assert rel(dst[0].to_host(), ob.BT(xp)) < TOL
+    for l, L in enumerate(hier.levels):           # level 0 has 96 cells: the second thread block is half empty
+        xl = seeded(L.n_u, 10 + l)
+        su, du = h.initialize_dof_vector(0, l).from_host(xl), h.initialize_dof_vector(0, l)
+        h.mg_matrices_A_block[l].vmult(du, su)
+        assert rel(du.to_host(), ob.apply_A(l, xl)) < TOL
+    h.close()
+
+
 def test_curved_compressible_A_block(meshes):
     """is_compressible makes the A block deviatoric (matrix_free_operators.cc:999-1005): the general kernel with curved geometry."""
     ohier, hier = meshes
