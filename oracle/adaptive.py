@@ -158,7 +158,6 @@ class AdaptiveBox:
     def _hanging_of(self, npd, nodes, shape):
         """{node index: [(master node index, weight)]} for the scalar element with npd nodes per direction."""
         dim, per = self.dim, npd - 1
-        unit = per << self.Lmax                               # lattice length of the box
         by_cell = {c: {self.node_key(c, loc, npd) for loc in fe.lex_nodes(npd, dim)} for c in self.cells}
         lex = fe.lex_nodes(npd, dim)
         cons = {}

@@ -146,7 +146,6 @@ class ShellLevel:
         return r * spherical_average([D[j, i], D[j, i + 1], D[j + 1, i], D[j + 1, i + 1]], w)
 
     def _number(self):
-        n = self.n
         ord2, ord1 = fe.fe_q_local_order(2, 3), fe.fe_q_local_order(1, 3)
         lex2, lex1 = fe.lex_nodes(3, 3), fe.lex_nodes(2, 3)
         node_u, node_p, xu, xp = {}, {}, [], []
@@ -188,7 +187,6 @@ class ShellLevel:
         N = np.array([[V[q[0], k[0]] * V[q[1], k[1]] * V[q[2], k[2]] for k in ks] for q in qs])
         dN = np.array([[[np.prod([(D if d == r else V)[q[d], k[d]] for d in range(3)]) for r in range(3)] for k in ks] for q in qs])
         w = np.array([fe.GAUSS_W[q[0]] * fe.GAUSS_W[q[1]] * fe.GAUSS_W[q[2]] for q in qs])
-        n = self.n
         self.xq = np.zeros((self.n_cells, 27, 3)); self.jinv = np.zeros((self.n_cells, 27, 3, 3)); self.jxw = np.zeros((self.n_cells, 27))
         for m, (t, ijk) in enumerate(self.cells):
             X = np.array([self.position(t, ijk, [LOBATTO5[k[d]] for d in range(3)]) for k in ks])    # (125, 3)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
 
-from oracle import adaptive, assembled, coeff, fe, mesh
+from oracle import adaptive, assembled, coeff, mesh
 from util import golden
 
 

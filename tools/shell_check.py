@@ -80,7 +80,6 @@ def parity():
 
 
 def timing(R):
-    import torch
     t0 = time.time()
     hier = pshell.ShellHierarchy(R)
     eta_q, force_q, ps = benchmarks.nsinker_shell_problem(hier)
