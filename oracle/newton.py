@@ -156,3 +156,59 @@ def A_apply(level, eta, constrained_u, xu, is_compressible=False, enable_prescri
     if len(constrained_u):
         yu[constrained_u] = xu[constrained_u]
     return yu
+
+
+# ---- free-surface stabilisation faces (matrix_free_operators.cc:563-602) -------------------------------------------
+def boundary_faces(level, face_no):
+    """Cells of a box Level that have local face `face_no` (deal.II numbering x0, x1, y0, y1[, z0, z1]) on the boundary."""
+    d, side = face_no // 2, face_no % 2
+    want = 0 if side == 0 else level.n - 1
+    return np.flatnonzero(level.cells[:, d] == want)
+
+
+def free_surface_apply_add(level, cells, face_no, stabilization_term_table, constrained_u, xu, yu, plain=False):
+    """StokesOperator::local_apply_boundary_face: on every free-surface boundary face
+        yu_I -= int_face (g . u)(n . phi_I) dA
+    with g = stabilization_term_table[face][q] (= density * time step * theta * |gravity| * g_hat, filled by
+    stokes_matrix_free_local_smoothing.cc:555-612), n the outward normal, QGauss<dim-1>(degree + 1) = 3^(dim-1) face points
+    (q lexicographic over the two face-tangential directions, lower direction fastest).  Source values are read like in the
+    cell loop (constrained DoFs give 0 unless `plain`), nothing is added to constrained rows.
+    cells: the cells whose local face `face_no` is a free-surface face; stabilization_term_table: (len(cells), 3^(dim-1), dim)."""
+    dim = level.dim
+    d, side = face_no // 2, face_no % 2
+    tang = [e for e in range(dim) if e != d]
+    normal = np.zeros(dim); normal[d] = -1.0 if side == 0 else 1.0
+    area = float(np.prod([level.h[e] for e in tang]))
+    # face nodes of the cell (lexicographic cell index) and the Q2 face shape functions at the face Gauss points
+    lex = fe.lex_nodes(3, dim)
+    face_nodes = [a for a, loc in enumerate(lex) if loc[d] == (0 if side == 0 else 2)]
+    fq = fe.lex_nodes(3, dim - 1)
+    phi = np.array([[np.prod([fe.N2[q[k], lex[a][tang[k]]] for k in range(dim - 1)]) for a in face_nodes] for q in fq])   # [q][face node]
+    w = np.array([np.prod([fe.GAUSS_W[q[k]] for k in range(dim - 1)]) for q in fq]) * area
+    nn = 3 ** dim
+    xr = xu.copy()
+    if not plain and len(constrained_u):
+        xr[constrained_u] = 0.0
+    mask = np.ones(level.n_u, bool)
+    if len(constrained_u):
+        mask[constrained_u] = False
+    for k, cell in enumerate(cells):
+        dofs = np.array([[level.cell_dofs_u[cell, c * nn + a] for a in face_nodes] for c in range(dim)])     # [c][face node]
+        u_q = phi @ xr[dofs].T                                                  # [q][c]
+        g_dot_u = (stabilization_term_table[k] * u_q).sum(axis=1)               # [q]
+        val = -(g_dot_u * w)[:, None] * normal[None, :]                         # submit_value: -(g . u) n
+        contrib = phi.T @ val                                                   # [face node][c]
+        for c in range(dim):
+            idx = dofs[c]
+            np.add.at(yu, idx[mask[idx]], contrib[mask[idx], c])
+    return yu
+
+
+def free_surface_matrix(level, cells, face_no, stabilization_term_table, constrained_u):
+    """The same term as a dense-assembled sparse matrix (rows: test functions), for checks."""
+    import scipy.sparse as sp
+    cols = []
+    for j in range(level.n_u):
+        e = np.zeros(level.n_u); e[j] = 1.0
+        cols.append(free_surface_apply_add(level, cells, face_no, stabilization_term_table, constrained_u, e, np.zeros(level.n_u)))
+    return sp.csr_matrix(np.array(cols).T)

@@ -75,3 +75,38 @@ def test_dilation_changes_only_what_it_should():
     if M is not None:
         assert np.allclose(cp - yp, M @ x[lev.n_u:], rtol=0, atol=1e-12 * np.abs(yp).max())
     assert np.allclose(newton.A_apply(lev, eta, cons, x[:lev.n_u], False, True), newton.A_apply(lev, eta, cons, x[:lev.n_u], True))
+
+
+def test_free_surface_face_term():
+    """The boundary-face stabilisation term (matrix_free_operators.cc:563-602), oracle side: for g parallel to the
+    normal it is the symmetric negative semi-definite boundary mass term -|g| int (u.n)(v.n); for a constant u it integrates
+    -(g.u) n over the face; only face DoFs are touched; the matrix form agrees with the matrix-free form."""
+    from oracle import mesh, newton
+    for dim in (2, 3):
+        L = mesh.Level(dim, 2 if dim == 2 else 1)
+        face_no = 2 * dim - 1                                     # the top face
+        cells = newton.boundary_faces(L, face_no)
+        assert len(cells) == L.n ** (dim - 1)
+        nfq = 3 ** (dim - 1)
+        rng = np.random.default_rng(dim)
+        # (a) g = gamma n
+        gamma = 3.7
+        tab = np.zeros((len(cells), nfq, dim)); tab[..., dim - 1] = gamma
+        none = np.zeros(0, dtype=np.int64)
+        K = newton.free_surface_matrix(L, cells, face_no, tab, none)
+        assert abs(K - K.T).max() < 1e-14
+        v = rng.uniform(-1, 1, L.n_u)
+        assert v @ (K @ v) <= 1e-14
+        u = np.zeros(L.n_u); u[dim - 1::dim] = 1.0               # u = n everywhere: -gamma * (face area = 1) in total
+        assert abs((K @ u).sum() + gamma) < 1e-13
+        top = np.zeros(L.n_u, bool)
+        top[np.unique(L.cell_dofs_u[cells])] = True
+        coords = L.dof_coords_u()
+        assert not np.any((K @ v)[coords[:, dim - 1] < 1.0 - 1e-12])          # only DoFs on the top boundary receive anything
+        # (b) general g: matrix-free form = matrix form, constrained rows / columns are skipped
+        tab = rng.uniform(-1, 1, (len(cells), nfq, dim))
+        cons = L.constrained_u("tangential")
+        K = newton.free_surface_matrix(L, cells, face_no, tab, cons)
+        y = newton.free_surface_apply_add(L, cells, face_no, tab, cons, v, np.zeros(L.n_u))
+        assert np.abs(K @ v - y).max() < 1e-14
+        assert not np.any(y[cons]) and abs(K[:, cons]).max() == 0.0
