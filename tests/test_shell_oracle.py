@@ -89,10 +89,9 @@ def test_shell_benchmark_inputs(hiers):
 
 
 def test_spherical_nsinker_golden_iterations(hiers):
-    """tests/spherical_nsinker_gmg_gc, first solve: 106 GMRES iterations in the reference (4 MPI ranks, deal.II's own
-    coarse-cell order); the oracle on this repository's numbering of the same mesh takes 110.  The Chebyshev eigenvalue
-    estimates start from `global DoF index mod 11`, so the count moves by a few iterations with the numbering; before the
-    geometry was pinned (other interior points) it was 345."""
+    """tests/spherical_nsinker_gmg_gc, first solve: 106 GMRES iterations in the reference, produced by the global-coarsening
+    handler (GMG-GC, 4 MPI ranks); the local-smoothing restatement on the same mesh takes 110 (independent of the order of
+    the coarse cells: random permutations of the 96 trees give 110 as well).  Before the geometry was pinned it was 345."""
     from oracle import solver
     o, _ = hiers
     L = o.active
