@@ -178,6 +178,8 @@ namespace aspect_b200
       const auto sz = level == SMF_ACTIVE ? std::make_pair(n_u, n_p) : level_sizes.at((std::size_t)level);
       return std::make_unique<DeviceVector>(ctx, block == 0 ? sz.first : sz.second);
     }
+    /** wait for the work queued on the context's stream */
+    void synchronize() const { check(smf_synchronize(ctx)); }
     std::size_t get_cell_data_memory_consumption() const { return (std::size_t)smf_device_bytes(ctx); }
     std::int64_t n_velocity_dofs() const { return n_u; }
     std::int64_t n_pressure_dofs() const { return n_p; }
