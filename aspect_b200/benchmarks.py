@@ -225,3 +225,22 @@ def hollow_sphere_problem(hier, m=-1, averaging="harmonic average"):
     cons = act.constrained_u("zero").astype(np.int64)
     u0[cons] = hollow_sphere_velocity(act.node_x_u, m).ravel()[cons]
     return eta_q, rho_q[..., None] * g, pressure_scaling_shell(act, material), u0
+
+
+# ---- cookbooks/convection_box_3d (BASELINE config 4): the Stokes side of a time step ------------------------------------
+def convection_box_temperature(x, perturbation=0.01):
+    """Initial temperature of convection_box_3d.prm:49-57, (1 - z) - p cos(pi x) sin(pi z) y^3; a time loop changes p here."""
+    return (1.0 - x[..., 2]) - perturbation * np.cos(np.pi * x[..., 0]) * np.sin(np.pi * x[..., 2]) * x[..., 1] ** 3
+
+
+def convection_box_problem(hier, perturbation=0.01, rayleigh=1e6):
+    """(viscosity_q, rhs, pressure_scaling) of the Stokes solve of one time step of cookbooks/convection_box_3d on a box
+    hierarchy: viscosity 1, tangential velocity on all six faces, buoyancy Ra * T in z (density 1 - 1e-10 T under a gravity
+    of 1e16, convection_box_3d.prm:91-110, written in the reduced-pressure form: the hydrostatic part of the weight is a
+    gradient that the pressure absorbs).  `Material averaging` is none (the cookbook's default)."""
+    act = hier.active
+    x = act.quadrature_points()
+    g = np.zeros(act.dim); g[-1] = 1.0
+    f = assemble_rhs(act, rayleigh * convection_box_temperature(x, perturbation), g)
+    f[act.constrained_u("tangential").astype(np.int64)] = 0.0
+    return np.ones(x.shape[:-1]), np.concatenate([f, np.zeros(act.n_p)]), 1.0 / (0.01 * float(act.extents[0]))

@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver-timings", action="store_true", help="skip the Execute-solver-timings harness (incl. the IDR(2) solve)")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the extra BASELINE cfg 2 (refinement 5) solve")
+    ap.add_argument("--convbox-refinement", type=int, default=5, help="global refinement of the extra BASELINE cfg 4 (convection box) block")
     ap.add_argument("--shell-refinement", type=int, default=3, help="global refinement of the extra BASELINE cfg 3 (spherical shell) block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -444,6 +445,32 @@ def main():
             h3.close()
         except Exception as exc:            # the headline line above must survive a failure of the extra configuration
             line["cfg3_spherical_shell"] = {"error": repr(exc)}
+        # ---- BASELINE cfg 4 shape: cookbooks/convection_box_3d, the Stokes solve of successive time steps (same mesh and set-up,
+        #      changing right-hand side, warm start from the previous step); the temperature advection is not on this path ----
+        try:
+            R4 = args.convbox_refinement
+            hier4 = synthetic.BoxHierarchy(3, R4)
+            eta4, rhs4, ps4 = benchmarks.convection_box_problem(hier4)
+            h4 = StokesMatrixFreeHandler(3, device=local_rank)
+            h4.setup_dofs(hier4, "tangential")
+            h4.assemble(eta4, "none", ps4)
+            h4.build_preconditioner()
+            h4.parameters.update({"Linear solver tolerance": 1e-7, "Number of cheap Stokes solver steps": 200,
+                                  "Maximum number of expensive Stokes solver steps": 0})
+            steps4, sol4 = [], None
+            for k in range(4):
+                _, rhs4, _ = benchmarks.convection_box_problem(hier4, perturbation=0.01 * (1.0 + 0.5 * k))
+                t0 = time.time()
+                sol4, o4 = h4.solve(rhs4, sol4)
+                steps4.append({"iterations": o4["iterations"], "wall_s": time.time() - t0, "converged": bool(o4["converged"])})
+            n4 = hier4.active.n_u + hier4.active.n_p
+            line["cfg4_convection_box_3d_stokes_steps"] = {
+                "workload": "cookbooks/convection_box_3d shape: unit box, viscosity 1, tangential velocity on all faces, Ra 1e6 buoyancy, "
+                            "Q2-Q1, block GMG (tol 1e-07), global refinement %d, 4 successive right-hand sides, warm start" % R4,
+                "dofs": n4, "steps": steps4}
+            h4.close()
+        except Exception as exc:
+            line["cfg4_convection_box_3d_stokes_steps"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_solve_throughput(args.ref_refinement, 1, 0).items()
                                 if k in ("value", "unit", "cores", "kind", "sample")}

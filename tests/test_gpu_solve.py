@@ -257,3 +257,34 @@ def test_gram_reorthogonalization_equals_two_sweeps(case):
     assert res[0][1]["iterations"] == res[1][1]["iterations"]
     nu = hier.active.n_u
     assert rel(res[0][0][:nu], res[1][0][:nu]) < 1e-8
+
+
+@pytest.mark.parametrize("R", [2, 3])
+def test_convection_box_steps_match_oracle(R):
+    """SURVEY 8(d) "S-convbox" (cookbooks/convection_box_3d): viscosity 1, tangential velocity on all six faces, successive
+    right-hand sides on the same set-up, the second solve warm-started from the first.  Iterations within +-1 of the oracle,
+    velocity 1e-8."""
+    hier = synthetic.BoxHierarchy(3, R)
+    ohier = omesh.Hierarchy(3, R)
+    eta_q, rhs, ps = benchmarks.convection_box_problem(hier)
+    h = StokesMatrixFreeHandler(3)
+    h.setup_dofs(hier, "tangential")
+    h.assemble(eta_q, "none", ps)
+    h.build_preconditioner()
+    h.parameters.update({"Linear solver tolerance": 1e-7, "Number of cheap Stokes solver steps": 200,
+                         "Maximum number of expensive Stokes solver steps": 0})
+    ob, *_ = oracle_backend(ohier, eta_q, "none", ps, "tangential")
+    s = osolver.BlockGMGStokes(ob)
+    nu = hier.active.n_u
+    sol, osol = None, None
+    for k in range(2):
+        _, rhs, _ = benchmarks.convection_box_problem(hier, perturbation=0.01 * (1.0 + 0.5 * k))
+        sol, out = h.solve(rhs, sol)
+        x0 = None
+        if osol is not None:
+            x0 = osol.copy(); x0[nu:] /= ps
+        oout = s.solve(rhs, x0=x0, tol_rel=1e-7, restart=100, max_its=200)
+        osol = oout["x"].copy(); osol[nu:] *= ps
+        assert out["converged"] and abs(out["iterations"] - oout["iterations"]) <= 1, (k, out["iterations"], oout["iterations"])
+        assert rel(sol[:nu], osol[:nu]) < 1e-6
+    h.close()
