@@ -2158,6 +2158,16 @@ static int check_level(smf_ctx *ctx, const LevelDev &L)
   return SMF_OK;
 }
 
+// vec[idx[i]] = value (AffineConstraints::set_zero on a device vector)
+int launch_set_entries(smf_ctx *ctx, double *vec, const uint32_t *idx, int64_t n, double value)
+{
+  if (n <= 0) return SMF_OK;
+  set_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(vec, idx, n, value);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
 int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero)
 {
   if (int e = check_level(ctx, L)) return e;

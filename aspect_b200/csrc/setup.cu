@@ -299,7 +299,7 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   if (m->geometry == 1 && ctx->cfg.dim != 3)
     return ctx->fail(SMF_ERR_UNSUPPORTED, "curved cells (geometry = 1) are validated in 3D only; the 2D instantiations exist but no test covers them yet");
   if (m->n_dofs_u >= (int64_t)NODE_IDX_MASK || m->n_dofs_p >= (int64_t)NODE_IDX_MASK)
-    return ctx->fail(SMF_ERR_UNSUPPORTED, "more than 2^29 local DoFs per rank");
+    return ctx->fail(SMF_ERR_UNSUPPORTED, "more than 2^28 - 1 local DoFs per rank and block (28-bit node index of the batch lists)");
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   LevelDev &L = ctx->lev(level);
   ctx->bytes -= L.bytes;
@@ -675,7 +675,7 @@ int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, d
                        double *min_max_out)
 {
   if (!ctx || !viscosity_q) return SMF_ERR_INVALID;
-  if (averaging < 0 || averaging > 3) return ctx->fail(SMF_ERR_UNSUPPORTED, "averaging: 0 none, 1 arithmetic, 2 harmonic, 3 geometric (project to Q1 / pick largest / log average are not on the GMG path)");
+  if (averaging < 0 || averaging > 3) return ctx->fail(SMF_ERR_UNSUPPORTED, "averaging: 0 none, 1 arithmetic, 2 harmonic, 3 geometric (project to Q1, which the reference supports on the GMG path through DGQ1 tables, matrix_free_operators.cc:306-325, is not implemented here; pick largest / log average are rejected by the reference as well)");
   const int nl = ctx->cfg.n_levels;
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   if (A.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the level meshes first");

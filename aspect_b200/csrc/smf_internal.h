@@ -269,6 +269,7 @@ int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p,
 int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_p);
 int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero = false);
 int launch_diag(smf_ctx *ctx, LevelDev &L);
+int launch_set_entries(smf_ctx *ctx, double *vec, const uint32_t *idx, int64_t n, double value);
 int launch_rhs(smf_ctx *ctx, LevelDev &L, const double *force_q_dev, double *rhs_u);
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);

@@ -1054,6 +1054,10 @@ int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, dou
   SMF_CUDA(cudaMemcpyAsync(sp, sol_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
   SMF_CUDA(cudaMemcpyAsync(bu, rhs_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
   SMF_CUDA(cudaMemcpyAsync(bp, rhs_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
+  // get_current_constraints().set_zero(guess) (local_smoothing.cc:973): a guess that carries boundary values would put
+  // b - x into the constrained rows (unit diagonal) and change the initial residual
+  TRY(launch_set_entries(ctx, su, A.constrained_u, A.n_constrained_u, 0.0));
+  TRY(launch_set_entries(ctx, sp, A.constrained_p, A.n_constrained_p, 0.0));
   const int rc = smf_solve(ctx, prm, su, sp, bu, bp, result);
   if (rc == SMF_OK || rc == SMF_NO_CONVERGENCE) {
     cudaMemcpyAsync(sol_u, su, sizeof(double) * nu, cudaMemcpyDeviceToHost, ctx->stream);

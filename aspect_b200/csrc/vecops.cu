@@ -407,3 +407,53 @@ int vec_norm2(smf_ctx *ctx, const double *x, int64_t n, double *host_result)
 }
 
 }  // namespace smf
+
+// ---- measured FP64 peak (every kernel is reported against the HBM roofline AND the FP64 pipe) ----
+// 8 independent DFMA chains per thread, 4 resident blocks of 256 threads per SM; the result is written once so that the
+// compiler keeps the chains.  smf_measure_fp64_peak times `reps` launches with CUDA events on the context's stream.
+__global__ void __launch_bounds__(256) k_fp64_fma(double *out, double a, double b, int iters)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;      // (never true: a = 1 - 2^-20, b = 2^-30 keep the chains bounded)
+}
+
+extern "C" int smf_measure_fp64_peak(smf_ctx *ctx, double *tflops_out)
+{
+  if (!ctx || !tflops_out) return SMF_ERR_INVALID;
+  int dev = 0, sms = 0;
+  SMF_CUDA(cudaGetDevice(&dev));
+  SMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 2048, reps = 5;
+  double *out = nullptr;
+  SMF_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaEvent_t a, b;
+  SMF_CUDA(cudaEventCreate(&a)); SMF_CUDA(cudaEventCreate(&b));
+  const double fa = 1.0 - 1.0 / 1048576.0, fb = 1.0 / 1073741824.0;
+  k_fp64_fma<<<blocks, threads, 0, ctx->stream>>>(out, fa, fb, iters);      // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    SMF_CUDA(cudaEventRecord(a, ctx->stream));
+    k_fp64_fma<<<blocks, threads, 0, ctx->stream>>>(out, fa, fb, iters);
+    SMF_CUDA(cudaEventRecord(b, ctx->stream));
+    SMF_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    SMF_CUDA(cudaEventElapsedTime(&ms, a, b));
+    best = ms < best ? ms : best;
+    ctx->launches++;
+  }
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops_out = flops / ((double)best * 1e-3) / 1e12;
+  return SMF_OK;
+}

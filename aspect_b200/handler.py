@@ -128,6 +128,7 @@ class StokesMatrixFreeHandler:
         self.close()
         self.hier = hierarchy
         self.boundary = boundary
+        self._pnorm_kind = None            # the weights live in the context that was just destroyed
         n_levels = len(hierarchy.levels)
         cfg = _lib.Config(self.dim, self.degree, n_levels, self.device)
         ctx = ctypes.c_void_p()
@@ -323,7 +324,13 @@ class StokesMatrixFreeHandler:
                                 p["IDR(s) parameter"], p["Maximum number of expensive Stokes solver steps"],
                                 p["Linear solver A block tolerance"], p["Linear solver S block tolerance"],
                                 int(host_call and self.pressure_scaling != 1.0), int(host_call and self._pressure_normalization_set()),
-                                float(p["Surface pressure"]))
+                                self._surface_pressure())
+
+    def _surface_pressure(self):
+        """`Surface pressure` is added only by `Pressure normalization = surface`; with `volume` the adjustment is
+        -integral / volume alone (helper_functions.cc:858-861)."""
+        p = self.parameters
+        return float(p["Surface pressure"]) if p["Pressure normalization"] == "surface" else 0.0
 
     def _pressure_normalization_set(self):
         """Uploads the normalisation weights when "Pressure normalization" asks for them (once per mesh and kind)."""
@@ -368,7 +375,7 @@ class StokesMatrixFreeHandler:
         """Rescale and normalise a device pressure vector in place; returns the pressure normalisation adjustment."""
         adj = ctypes.c_double(0.0)
         self._check(self.lib.smf_postprocess_pressure(self.ctx, ptr(sol_p.ptr), ctypes.c_double(pressure_scaling), int(normalize),
-                                                      ctypes.c_double(self.parameters["Surface pressure"]), ctypes.byref(adj)))
+                                                      ctypes.c_double(self._surface_pressure()), ctypes.byref(adj)))
         return adj.value
 
     def assemble_stokes_rhs(self, force_q, rhs_u):
@@ -492,6 +499,12 @@ class StokesMatrixFreeHandler:
 
     def exchange_transport(self):
         return {0: "single rank", 1: "nccl send/recv", 2: "fused peer-memory kernel (CUDA IPC over NVLink)"}[int(self.lib.smf_exchange_transport(self.ctx))]
+
+    def measure_fp64_peak(self):
+        """Measured FP64 pipe peak of the device in TFLOP/s (DFMA micro-kernel inside the library)."""
+        out = ctypes.c_double()
+        self._check(self.lib.smf_measure_fp64_peak(self.ctx, ctypes.byref(out)))
+        return float(out.value)
 
     def exchange_count(self):
         return int(self.lib.smf_exchange_count(self.ctx))

@@ -51,51 +51,122 @@ def workload_name(R, world=1):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_solve_throughput(R, steps, warmup, budget_s=240.0):
-    """Complete block-GMG solves with the oracle (C cell kernels + OpenMP, numpy driver) on the host cores."""
-    from oracle import coeff, cpu, mesh as omesh, solver as osolver
+# The CPU arm: oracle/csrc/smf_cpu_solver.cc (C++17, OpenMP over all host cores, SIMD cell batches, the whole solver loop in
+# C++; kind "port" -- deal.II / ASPECT cannot be built in this image).  Complete solves up to refinement 5; above that a
+# complete solve takes minutes, so a step is a BOUNDED SAMPLE of the same solve on the same mesh: smoother set-up + eigenvalue
+# estimation + tolerance + the first SAMPLE_ITS GMRES iterations, and the wall time of the complete solve follows from the
+# sample's own timers (every part is linear in what it repeats):
+#     t_solve = t_sample_outside_the_iteration_loop + its * (t_iteration_without_orthogonalisation + t_ortho((its + 1) / 2))
+# (the orthogonalisation of iteration j streams j basis vectors; its mean cost over a cycle is the cost at the mean basis
+# length, measured with the solve's own routine on a basis of that length) where `its` is the iteration count of the CPU implementation's own complete solve of that configuration (refinement 7:
+# tests/golden/nsinker_R7_cpu_reference.npz, made once by tools/make_full_size_fixture.py).  The model is checked in every run
+# against complete solves at refinement 5 (`model_check`).
+SAMPLE_ITS = 2
+
+
+def _cpu_problem(R, hier=None, eta_q=None, rhs=None, ps=None, n_sinkers=N_SINKERS):
+    from oracle import coeff, cpuref
     from aspect_b200 import benchmarks, synthetic
-    hier = synthetic.BoxHierarchy(3, R)
-    eta_q, rhs, ps = benchmarks.nsinker_problem(hier, N_SINKERS, VISCOSITY_RATIO, AVERAGING)
-    ohier = omesh.Hierarchy(3, R)
-    active, levels, _, _ = coeff.viscosity_tables(ohier, eta_q, "harmonic")
-    ob = cpu.backend_from_hierarchy(ohier, active, levels, ps, "zero")
-    n = hier.active.n_u + hier.active.n_p
+    if hier is None:
+        hier = synthetic.BoxHierarchy(3, R)
+        eta_q, rhs, ps = benchmarks.nsinker_problem(hier, n_sinkers, VISCOSITY_RATIO, AVERAGING)
+    active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, "harmonic")
+    threads = cpuref.set_num_threads()                # all cores the process may use (torchrun exports OMP_NUM_THREADS=1)
+    cb = cpuref.from_hierarchy(hier, active, levels, ps, "zero")
+    return cb, np.ascontiguousarray(rhs), hier.active.n_u + hier.active.n_p, threads
+
+
+def _model_time(out, its_full, t_ortho_mean):
+    """Wall time of the complete solve from a sample of m = out['iterations'] iterations: everything outside the iteration loop
+    (set-up, tolerance, initial residual, the final update with its preconditioner application) happens once in both; inside
+    the loop everything but the orthogonalisation costs the same every iteration, and the orthogonalisation of iteration j
+    streams j basis vectors, so its mean over a cycle is the cost at the mean basis length (measured: smfc_time_ortho)."""
+    m = out["iterations"]
+    sp = out["split"]
+    t_outside = out["seconds"] - sp["iteration_loop"]
+    t_iter = (sp["iteration_loop"] - sp["gmres_ortho"]) / m
+    return t_outside + its_full * (t_iter + t_ortho_mean)
+
+
+def cpu_reference_steps(R, steps, warmup, hier=None, eta_q=None, rhs=None, ps=None, its_full=None):
+    """`warmup` + `steps` steps of the CPU arm at refinement R; returns the dict both arms print."""
+    from oracle import cpuref
+    cb, rhs, n, threads = _cpu_problem(R, hier, eta_q, rhs, ps)
+    width = int(cpuref.lib().smfc_width())
     times, its = [], None
-    t_all = time.time()
-    for i in range(warmup + steps):
-        s = osolver.BlockGMGStokes(ob)       # rebuilt every solve, like the reference (eigenvalue estimation inside)
-        t0 = time.time()
-        out = s.solve(rhs, tol_rel=TOL, restart=RESTART, max_its=CHEAP_STEPS)
-        dt = time.time() - t0
-        its = out["iterations"]
-        if i >= warmup:
-            times.append(dt)
-        if time.time() - t_all > budget_s and times:
-            break
-    t = float(np.mean(times))
-    return {"value": n / t / 1e6, "unit": UNIT, "cores": int(cpu.lib().smf_cpu_num_threads()), "kind": "port",
-            "sample": f"{len(times)} complete solve(s) of the same benchmark at global refinement {R} "
-                      f"({n} DoFs, {its} outer iterations, {t:.2f} s each); throughput in DoFs per solve-second",
-            "wall_s": t, "iterations": its, "dofs": n}
+    if R <= 5:
+        for i in range(warmup + steps):
+            out = cb.solve(rhs, tol_rel=TOL, restart=RESTART, max_its=CHEAP_STEPS)
+            its = out["iterations"]
+            if i >= warmup:
+                times.append(out["seconds"])
+        t = float(np.mean(times))
+        sample = (f"{len(times)} complete solve(s) of this configuration (refinement {R}, {n} DoFs, {its} outer iterations, {t:.2f} s each)")
+        model_check = None
+    else:
+        if its_full is None:
+            fx = os.path.join(ROOT, "tests", "golden", f"nsinker_R{R}_cpu_reference.npz")
+            if os.path.exists(fx):
+                its_full = int(np.load(fx)["iterations"])
+            else:                                         # no fixture for this size: one complete solve, outside the timed steps
+                its_full = cb.solve(rhs, tol_rel=TOL, restart=RESTART, max_its=CHEAP_STEPS)["iterations"]
+        t_ortho = cb.time_ortho((its_full + 1) // 2)
+        for i in range(warmup + steps):
+            out = cb.solve(rhs, tol_rel=TOL, restart=RESTART, max_its=SAMPLE_ITS)
+            if i >= warmup:
+                times.append(_model_time(out, its_full, t_ortho))
+        its = its_full
+        t = float(np.mean(times))
+        # the same model against complete solves where those are affordable (cfg 2)
+        cb5, rhs5, n5, _ = _cpu_problem(5)
+        full = [cb5.solve(rhs5, tol_rel=TOL, restart=RESTART, max_its=CHEAP_STEPS) for _ in range(2)][-1]
+        part = [cb5.solve(rhs5, tol_rel=TOL, restart=RESTART, max_its=SAMPLE_ITS) for _ in range(2)][-1]
+        model_check = {"refinement": 5, "complete_solve_s": full["seconds"],
+                       "modelled_from_sample_s": _model_time(part, full["iterations"], cb5.time_ortho((full["iterations"] + 1) // 2)),
+                       "iterations": full["iterations"]}
+        cb5.close()
+        sample = (f"{len(times)} bounded sample(s) of this configuration (refinement {R}, {n} DoFs): smoother set-up + eigenvalue estimation + "
+                  f"tolerance + the first {SAMPLE_ITS} of {its_full} GMRES iterations ({out['seconds']:.2f} s each) + one orthogonalisation at the mean "
+                  f"basis length {(its_full + 1) // 2} ({t_ortho:.2f} s); complete-solve time {t:.1f} s from the sample's timers (bench.py: _model_time; checked against complete solves at refinement 5 in model_check)")
+    cb.close()
+    return {"value": n / t / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "simd_cells_per_batch": width,
+            "wall_s": t, "iterations": its, "dofs": n, "model_check": model_check,
+            "implementation": "oracle/csrc/smf_cpu_solver.cc: C++17 -O3, OpenMP (one thread per core), SIMD cell batches, solver loop in C++"}
+
+
+def cfg2_cpu_reference(n_solves=2):
+    """Complete solves of BASELINE cfg 2 (refinement 5) by the CPU arm: the like-for-like partner of `cfg2_refinement5`."""
+    cb, rhs, n, threads = _cpu_problem(5)
+    outs = [cb.solve(rhs, tol_rel=TOL, restart=RESTART, max_its=CHEAP_STEPS) for _ in range(1 + n_solves)][1:]
+    cb.close()
+    t = float(np.mean([o["seconds"] for o in outs]))
+    return {"workload": workload_name(5), "dofs": n, "wall_s": t, "mdofs": n / t / 1e6, "iterations": outs[-1]["iterations"], "cores": threads,
+            "split_s": outs[-1]["split"]}
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; deal.II/ASPECT cannot be built here)."""
+    """--impl reference: the reference's algorithm on the host cores, on the configuration of the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    R = args.ref_refinement
-    warm = min(args.warmup, 1)
-    res = cpu_solve_throughput(R, args.steps, warm)
+    R = args.refinement
+    world = args.gpus if args.gpus in REPETITIONS else 1
+    res = cpu_reference_steps(R, args.steps, args.warmup)
+    note = None
+    if world > 1:
+        note = (f"the host cores do not multiply with --gpus: the CPU arm times ONE of the {world} coarse-cell trees of this workload "
+                f"(refinement {R}, {res['dofs']} DoFs) and reports its throughput")
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": warm, "ms_per_step": res["wall_s"] * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["wall_s"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.refinement, args.gpus if args.gpus in REPETITIONS else 1),
-                       "parallelism": "host cores (OpenMP)"},
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": workload_name(R, world), "dofs_per_gpu": res["dofs"], "levels": R + 1,
+                       "parallelism": f"host cores: OpenMP, {res['cores']} threads, {res['simd_cells_per_batch']} cells per SIMD batch",
+                       "impl": "reference"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "model_check", "implementation")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "solve_wall_s": res["wall_s"], "iterations": res["iterations"]}
+            "solve_wall_s": res["wall_s"], "iterations": res["iterations"], "note": note}
+    if not args.no_cfg2:
+        line["cfg2_refinement5"] = cfg2_cpu_reference()
     print(json.dumps(line), flush=True)
 
 
@@ -146,8 +217,7 @@ def build_problem(R, device, rank=0, world=1):
     h.build_preconditioner()
     h.parameters.update({"Linear solver tolerance": TOL, "Number of cheap Stokes solver steps": CHEAP_STEPS,
                          "GMRES solver restart length": RESTART})
-    del eta_q
-    return hier, h, rhs
+    return hier, h, rhs, eta_q, ps
 
 
 def timed_solves(torch, h, stream, rhs_dev, sol_dev, n_u, n_p, steps, barrier):
@@ -174,7 +244,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--refinement", type=int, default=int(os.environ.get("SMF_BENCH_REFINEMENT", "7")),
                     help="global refinement per GPU (7 = north-star single-GPU target; 8 GPUs x 7 = BASELINE cfg 5)")
-    ap.add_argument("--ref-refinement", type=int, default=4, help="refinement of the CPU sample (complete solves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solver-timings", action="store_true", help="skip the Execute-solver-timings harness (incl. the IDR(2) solve)")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the extra BASELINE cfg 2 (refinement 5) solve")
@@ -211,7 +280,9 @@ def main():
     from aspect_b200 import SMF_ACTIVE
     R = args.refinement
     t_setup = time.time()
-    hier, h, rhs = build_problem(R, local_rank, rank, world)
+    hier, h, rhs, eta_q, ps = build_problem(R, local_rank, rank, world)
+    cpu_inputs = (hier, eta_q, rhs.copy(), ps) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    del eta_q
     stream = torch.cuda.Stream()
     h.set_stream(stream.cuda_stream)
     n_u, n_p, n_cells = hier.active.n_u, hier.active.n_p, hier.active.n_cells
@@ -287,6 +358,7 @@ def main():
             torch.cuda.synchronize()
             return max_over_ranks(a.elapsed_time(b) / 1e3 / reps)
 
+        fp64_peak = h.measure_fp64_peak()
         t_stokes = time_op(lambda: h.stokes_matrix.vmult(dst, src))
         t_A = time_op(lambda: h.A_block_matrix.vmult(dst[0], src[0]))
         t_M = time_op(lambda: h.Schur_complement_block_matrix.vmult(dst[1], src[1]))
@@ -326,9 +398,15 @@ def main():
     bytes_stokes = 16.0 * n + 8.0 * n_cells
     a_ms, a_cnt = prof["A_fine"]
     t_A_kernel = a_ms / 1e3 / max(a_cnt, 1)
-    traffic = None
+    s_ms, s_cnt = prof["stokes_vmult"]                  # Stokes vmult kernel, timed live inside the timed solves as well
+    t_S_live = s_ms / 1e3 / max(s_cnt, 1)
+    # FP64 work per launch: 2,268 DFMA-class instructions per cell for the A block, + 369 for the
+    # pressure interpolation / divergence rows of the Stokes operator; 2 flops each
+    flops_A, flops_stokes = 2.0 * 2268 * n_cells, 2.0 * (2268 + 369) * n_cells
+    traffic = traffic_stokes = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"A_fine_R{R}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic, traffic_stokes = tj.get(f"A_fine_R{R}"), tj.get(f"stokes_R{R}")
     except (OSError, ValueError):
         pass
     line = {
@@ -336,7 +414,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(R, world), "dofs_global": n_global, "dofs_per_gpu": n, "cells_per_gpu": n_cells, "levels": R + 1,
-                   "parallelism": "1 subdomain per GPU" if world == 1 else f"domain decomposition, {world} subdomains (one coarse-cell tree per GPU), NCCL halo exchange + all-reduce",
+                   "parallelism": "1 subdomain per GPU" if world == 1 else f"domain decomposition, {world} subdomains (one coarse-cell tree per GPU), halo exchange = one fused pack/push/wait/accumulate kernel over NVLink peer memory (CUDA IPC), dot products by ncclAllReduce",
                    "l2": "vectors (%.0f MB each) exceed the 126 MB L2" % (8e-6 * n) if 8 * n > 126e6 else "vectors fit L2: each solve streams >100 distinct vectors between reuses",
                    "impl": "b200"},
         "solve_wall_s": wall, "iterations": its,
@@ -349,7 +427,15 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "velocity_kernel<3,0> (A block, finest level)", "achieved": bytes_A / t_A_kernel / 1e9,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes_A / t_A_kernel / 1e9 / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_A, "launches_timed": a_cnt,
-                     "avg_launch_us": t_A_kernel * 1e6, "share_of_solve": a_ms / 1e3 / t_dev},
+                     "avg_launch_us": t_A_kernel * 1e6, "share_of_solve": a_ms / 1e3 / t_dev,
+                     "fp64": {"achieved_tflops": flops_A / t_A_kernel / 1e12, "peak_tflops": fp64_peak, "frac": flops_A / t_A_kernel / 1e12 / fp64_peak,
+                              "peak_source": "measured in this run (smf_measure_fp64_peak: DFMA micro-kernel, best of 5 launches)"}},
+        "roofline_stokes_vmult": {"bound": "hbm", "kernel": "velocity_sb_kernel<1> (Stokes operator = the op the metric names, active level)",
+                                  "achieved": bytes_stokes / t_S_live / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_stokes / t_S_live / 1e9 / peak,
+                                  "traffic": traffic_stokes, "algorithmic_bytes_per_launch": bytes_stokes, "launches_timed": s_cnt,
+                                  "avg_launch_us": t_S_live * 1e6, "share_of_solve": s_ms / 1e3 / t_dev, "gdofs": n / t_S_live / 1e9,
+                                  "fp64": {"achieved_tflops": flops_stokes / t_S_live / 1e12, "peak_tflops": fp64_peak,
+                                           "frac": flops_stokes / t_S_live / 1e12 / fp64_peak}},
         "vmult": {"stokes_gdofs": n_global / t_stokes / 1e9, "stokes_kernel_gdofs": n_global / t_stokes_kernel / 1e9,
                   "stokes_roofline_frac": bytes_stokes / t_stokes_kernel / 1e9 / peak,
                   "A_gdofs": n_global / n * n_u / t_A / 1e9, "mass_gdofs": n_global / n * n_p / t_M / 1e9,
@@ -362,7 +448,7 @@ def main():
     h.close()
     # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------
     if not args.no_cfg2 and R != 5 and world == 1:
-        hier5, h5, rhs5 = build_problem(5, local_rank)
+        hier5, h5, rhs5, _, _ = build_problem(5, local_rank)
         n5 = hier5.active.n_u + hier5.active.n_p
         pin5 = torch.empty(n5, dtype=torch.float64).pin_memory().numpy()
         rp5 = torch.empty(n5, dtype=torch.float64).pin_memory().numpy(); rp5[:] = rhs5
@@ -472,8 +558,10 @@ def main():
         except Exception as exc:
             line["cfg4_convection_box_3d_stokes_steps"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = {k: v for k, v in cpu_solve_throughput(args.ref_refinement, 1, 0).items()
-                                if k in ("value", "unit", "cores", "kind", "sample")}
+        res = cpu_reference_steps(R, 2, 1, *cpu_inputs)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "model_check", "implementation")}
+        if "cfg2_refinement5" in line:
+            line["cfg2_refinement5"]["cpu_reference"] = cfg2_cpu_reference()
     else:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -16,5 +16,5 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _build_oracle():
     """The oracle's C restatement is test infrastructure: build it on demand (gcc only)."""
-    if not os.path.exists(os.path.join(ROOT, "oracle", "libsmf_cpu.so")):
+    if not all(os.path.exists(os.path.join(ROOT, "oracle", f)) for f in ("libsmf_cpu.so", "libsmf_cpuref_w4.so", "libsmf_cpuref_w8.so")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
