@@ -21,7 +21,7 @@ import numpy as np
 _GW = np.array([5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0])
 
 AVERAGING = ("none", "arithmetic average", "harmonic average", "geometric average",
-             "harmonic average only viscosity", "geometric average only viscosity")
+             "harmonic average only viscosity", "geometric average only viscosity", "project to Q1", "project to Q1 only viscosity")
 
 
 def quadrature_weights(dim):
@@ -47,9 +47,41 @@ def average_viscosity(eta_q, averaging):
     return np.repeat(a[:, None], eta_q.shape[1], axis=1)
 
 
-def fill_cell_data(dim, children, eta_q, averaging):
+def _q1_at_quad(dim):
+    s = np.sqrt(3.0 / 5.0)
+    x = np.array([0.5 - 0.5 * s, 0.5, 0.5 + 0.5 * s])
+    n1 = np.stack([1.0 - x, x], axis=1)
+    phi = n1
+    for _ in range(dim - 1):
+        phi = np.einsum("ab,cd->acbd", n1, phi).reshape(n1.shape[0] * phi.shape[0], -1)
+    return phi                                                           # [q lex][vertex lex]
+
+
+def fill_cell_data_q1(dim, children, eta_q, jxw=None):
+    """`project to Q1 [only viscosity]`: DGQ1 projection space (local_smoothing.cc:99-111).  Cellwise (JxW-weighted) L2
+    projection of the raw values onto Q1, evaluated at the quadrature points and clamped to the raw range
+    (matrix_free_operators.cc:226-232, :306-325); level transfer by interpolate_to_mg of the interpolatory DGQ1 element =
+    the parent's nodal value at vertex k is child k's nodal value k; 3^dim values per cell everywhere (:274-289)."""
+    v = np.asarray(eta_q, dtype=np.float64)
+    phi = _q1_at_quad(dim)
+    w = np.broadcast_to(quadrature_weights(dim)[None, :], v.shape) if jxw is None else np.asarray(jxw)
+    eta_min, eta_max = float(v.min()), float(v.max())
+    coef = np.linalg.solve(np.einsum("cq,qi,qj->cij", w, phi, phi), np.einsum("cq,qi->ci", w * v, phi)[..., None])[..., 0]
+    n_levels = len(children)
+    levels = [None] * n_levels
+    levels[-1] = np.ascontiguousarray(np.clip(coef @ phi.T, eta_min, eta_max))
+    for l in range(n_levels - 1, 0, -1):
+        ch = np.asarray(children[l])
+        coef = np.stack([coef[ch[:, k], k] for k in range(1 << dim)], axis=1)
+        levels[l - 1] = np.ascontiguousarray(np.clip(coef @ phi.T, eta_min, eta_max))
+    return levels[-1].copy(), levels, eta_min, eta_max
+
+
+def fill_cell_data(dim, children, eta_q, averaging, jxw=None):
     """children[l] (l = 1..R): parent->child tables; eta_q (cells_active, 3^dim).
     Returns (active_table, [level tables 0..R], eta_min, eta_max)."""
+    if averaging.startswith("project to Q1"):
+        return fill_cell_data_q1(dim, children, eta_q, jxw)
     w = quadrature_weights(dim)
     out_q = average_viscosity(np.asarray(eta_q, dtype=np.float64), averaging)
     eta_min, eta_max = float(out_q.min()), float(out_q.max())

@@ -619,6 +619,71 @@ __global__ void k_coarsen_dg0(const double *fine, const int32_t *children, int n
   for (int c = 0; c < nch; ++c) s += fine[children[par * nch + c]];
   coarse[par] = s / nch;
 }
+// ---- `Material averaging = project to Q1 [only viscosity]`: DGQ1 projection space (local_smoothing.cc:99-111) ----
+// k_project_q1: cellwise L2 projection (JxW-weighted; Utilities::project_cellwise) of the RAW quadrature-point viscosities onto
+// the 2^dim Q1 shape functions: (Phi^T W Phi) c = Phi^T W v, solved per cell by Cholesky; extrema of the raw values per block.
+// k_eval_q1: the DGQ1 function back at the quadrature points, clamped to the global [min, max] (matrix_free_operators.cc:
+// 306-325, local_smoothing.cc:274-289).  k_coarsen_dg1: interpolate_to_mg of the DGQ1 vector -- FE_DGQ(1) is interpolatory,
+// its restriction is not additive: the parent's nodal value at vertex k is child k's own nodal value k.
+__device__ __forceinline__ double q1_shape_at(int dim, int q, int i)
+{
+  const double s = 0.7745966692414834, gx[3] = {0.5 - 0.5 * s, 0.5, 0.5 + 0.5 * s};
+  double v = 1.0;
+  for (int d = 0; d < dim; ++d) { const double x = gx[q % 3]; q /= 3; v *= ((i >> d) & 1) ? x : 1.0 - x; }
+  return v;
+}
+__global__ void k_project_q1(const double *raw_q, int64_t n_cells, int nq, const double *geo, double *coef, double *blk_min, double *blk_max)
+{
+  __shared__ double s_min[128], s_max[128];
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double vmin = 1e300, vmax = -1e300;
+  if (cell < n_cells) {
+    const int dim = nq == 27 ? 3 : 2, nn = 1 << dim;
+    double M[8][8], b[8];
+    for (int i = 0; i < nn; ++i) { b[i] = 0.0; for (int j = 0; j < nn; ++j) M[i][j] = 0.0; }
+    for (int q = 0; q < nq; ++q) {
+      const double v = raw_q[cell * nq + q];
+      vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+      const double w = geo ? geo[blk_index(cell, q * (dim * dim + 1) + dim * dim, nq * (dim * dim + 1))]
+                           : (dim == 3 ? gw1(q % 3) * gw1((q / 3) % 3) * gw1(q / 9) : gw1(q % 3) * gw1(q / 3));
+      double phi[8];
+      for (int i = 0; i < nn; ++i) phi[i] = q1_shape_at(dim, q, i);
+      for (int i = 0; i < nn; ++i) { b[i] += w * v * phi[i]; for (int j = 0; j <= i; ++j) M[i][j] += w * phi[i] * phi[j]; }
+    }
+    for (int j = 0; j < nn; ++j) {                 // Cholesky M = L L^T (lower triangle in place)
+      for (int k = 0; k < j; ++k) M[j][j] -= M[j][k] * M[j][k];
+      M[j][j] = sqrt(M[j][j]);
+      for (int i = j + 1; i < nn; ++i) { for (int k = 0; k < j; ++k) M[i][j] -= M[i][k] * M[j][k]; M[i][j] /= M[j][j]; }
+    }
+    for (int i = 0; i < nn; ++i) { for (int k = 0; k < i; ++k) b[i] -= M[i][k] * b[k]; b[i] /= M[i][i]; }
+    for (int i = nn - 1; i >= 0; --i) { for (int k = i + 1; k < nn; ++k) b[i] -= M[k][i] * b[k]; b[i] /= M[i][i]; }
+    for (int i = 0; i < nn; ++i) coef[cell * nn + i] = b[i];
+  }
+  s_min[threadIdx.x] = vmin; s_max[threadIdx.x] = vmax;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { s_min[threadIdx.x] = fmin(s_min[threadIdx.x], s_min[threadIdx.x + s]); s_max[threadIdx.x] = fmax(s_max[threadIdx.x], s_max[threadIdx.x + s]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { blk_min[blockIdx.x] = s_min[0]; blk_max[blockIdx.x] = s_max[0]; }
+}
+__global__ void k_eval_q1(const double *coef, int64_t n_cells, int nq, double lo, double hi, double *table)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cells * nq) return;
+  const int64_t cell = t / nq; const int q = (int)(t % nq);
+  const int dim = nq == 27 ? 3 : 2, nn = 1 << dim;
+  double v = 0.0;
+  for (int i = 0; i < nn; ++i) v += coef[cell * nn + i] * q1_shape_at(dim, q, i);
+  table[t] = fmin(fmax(v, lo), hi);
+}
+__global__ void k_coarsen_dg1(const double *fine, const int32_t *children, int nch, double *coarse, int64_t n_parents)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_parents * nch) return;
+  const int64_t par = t / nch; const int k = (int)(t % nch);
+  coarse[t] = fine[(int64_t)children[par * nch + k] * nch + k];
+}
 }  // namespace smf
 
 extern "C" {
@@ -675,7 +740,7 @@ int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, d
                        double *min_max_out)
 {
   if (!ctx || !viscosity_q) return SMF_ERR_INVALID;
-  if (averaging < 0 || averaging > 3) return ctx->fail(SMF_ERR_UNSUPPORTED, "averaging: 0 none, 1 arithmetic, 2 harmonic, 3 geometric (project to Q1, which the reference supports on the GMG path through DGQ1 tables, matrix_free_operators.cc:306-325, is not implemented here; pick largest / log average are rejected by the reference as well)");
+  if (averaging < 0 || averaging > 4) return ctx->fail(SMF_ERR_UNSUPPORTED, "averaging: 0 none, 1 arithmetic, 2 harmonic, 3 geometric, 4 project to Q1 (pick largest / log average are rejected by the reference's GMG path as well)");
   const int nl = ctx->cfg.n_levels;
   LevelDev &A = ctx->lev(SMF_ACTIVE);
   if (A.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the level meshes first");
@@ -685,6 +750,50 @@ int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, d
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   const int nq = A.dim == 3 ? 27 : 9, nch = 1 << A.dim;
   const int64_t nc = A.n_cells;
+  if (averaging == SMF_AVG_PROJECT_Q1) {
+    // DGQ1 tables: n_q values per cell on the active mesh and on every level
+    const unsigned pb = (unsigned)((nc + 127) / 128);
+    double *raw = nullptr, *coef = nullptr, *ext = nullptr, *table = nullptr;
+    SMF_CUDA(cudaMalloc(&raw, sizeof(double) * nc * nq));
+    SMF_CUDA(cudaMalloc(&coef, sizeof(double) * nc * nch));
+    SMF_CUDA(cudaMalloc(&table, sizeof(double) * nc * nq));
+    SMF_CUDA(cudaMalloc(&ext, sizeof(double) * 2 * pb));
+    SMF_CUDA(cudaMemcpyAsync(raw, viscosity_q, sizeof(double) * nc * nq, cudaMemcpyHostToDevice, ctx->stream));
+    k_project_q1<<<pb, 128, 0, ctx->stream>>>(raw, nc, nq, A.geo, coef, ext, ext + pb);
+    ctx->launches++;
+    std::vector<double> h_ext(2 * (size_t)pb);
+    SMF_CUDA(cudaMemcpyAsync(h_ext.data(), ext, sizeof(double) * 2 * pb, cudaMemcpyDeviceToHost, ctx->stream));
+    SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+    double mn = 1e300, mx = -1e300;
+    for (unsigned b = 0; b < pb; ++b) { mn = std::min(mn, h_ext[b]); mx = std::max(mx, h_ext[pb + b]); }
+    int rc = SMF_OK;
+    double *fine = coef;
+    std::vector<double *> tmp;
+    for (int l = nl - 1; l >= 0 && rc == SMF_OK; --l) {
+      LevelDev &L = ctx->levels[l];
+      k_eval_q1<<<(unsigned)((L.n_cells * nq + 255) / 256), 256, 0, ctx->stream>>>(fine, L.n_cells, nq, mn, mx, table);
+      ctx->launches++;
+      if (l == nl - 1) rc = install_table(ctx, A, table, nq, pressure_scaling, is_compressible);
+      if (rc == SMF_OK) rc = install_table(ctx, L, table, nq, pressure_scaling, is_compressible);
+      if (l > 0 && rc == SMF_OK) {
+        LevelDev &C = ctx->levels[l - 1];
+        double *coarse = nullptr;
+        if (cudaMalloc(&coarse, sizeof(double) * C.n_cells * nch) != cudaSuccess) { rc = ctx->fail(SMF_ERR_CUDA, "cudaMalloc failed"); break; }
+        tmp.push_back(coarse);
+        k_coarsen_dg1<<<(unsigned)((C.n_cells * nch + 255) / 256), 256, 0, ctx->stream>>>(fine, ctx->transfers[l].children, nch, coarse, C.n_cells);
+        ctx->launches++;
+        fine = coarse;
+      }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    if (rc == SMF_OK && cudaGetLastError() != cudaSuccess) rc = ctx->fail(SMF_ERR_CUDA, "smf_fill_cell_data: kernel failure");
+    cudaFree(raw); cudaFree(coef); cudaFree(table); cudaFree(ext);
+    for (double *p : tmp) cudaFree(p);
+    if (rc != SMF_OK) return rc;
+    if (min_max_out) { min_max_out[0] = mn; min_max_out[1] = mx; }
+    ctx->smoothers_ready = false;
+    return SMF_OK;
+  }
   const int n_act = averaging == 0 ? nq : 1;
   const unsigned blocks = (unsigned)((nc + 255) / 256);
   double *raw = nullptr, *act = nullptr, *dg0 = nullptr, *ext = nullptr;

@@ -232,7 +232,7 @@ class StokesMatrixFreeHandler:
         if self.device_cell_data:
             # averaging, DGQ0 projection, min / max and the level tables on the device (smf_fill_cell_data)
             op = material_averaging.replace(" only viscosity", "")
-            codes = {"none": 0, "arithmetic average": 1, "harmonic average": 2, "geometric average": 3}
+            codes = {"none": 0, "arithmetic average": 1, "harmonic average": 2, "geometric average": 3, "project to Q1": 4}
             if op not in codes:
                 raise SmfError(_lib.SMF_ERR_UNSUPPORTED, f"unsupported Material averaging for the GMG path: {material_averaging}")
             q = np.ascontiguousarray(viscosity_q, dtype=np.float64)
@@ -244,7 +244,7 @@ class StokesMatrixFreeHandler:
             return
         children = [None] + [self.hier.children(l) for l in range(1, self.n_levels)]
         active, levels, self.minimum_viscosity, self.maximum_viscosity = cell_data.fill_cell_data(
-            self.dim, children, viscosity_q, material_averaging)
+            self.dim, children, viscosity_q, material_averaging, getattr(self.hier.active, "jxw", None))
         self.set_cell_data(SMF_ACTIVE, active, pressure_scaling, is_compressible)
         for l in range(self.n_levels):
             self.set_cell_data(l, levels[l], pressure_scaling, is_compressible)

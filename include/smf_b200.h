@@ -128,7 +128,7 @@ int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *data);
 
 /* The array work of evaluate_material_model() on the device: viscosity_q = the material plugin's output at
  * the 3^dim velocity quadrature points of every active cell, host array [n_cells][3^dim].  Averaging over the points of a
- * cell (source/material_model/interface.cc:523-650; 0 none, 1 arithmetic, 2 harmonic, 3 geometric), cellwise projection
+ * cell (source/material_model/interface.cc:523-650; 0 none, 1 arithmetic, 2 harmonic, 3 geometric; 4 = no averaging, DGQ1 space), cellwise projection
  * onto DGQ0 (source/utilities.cc:2738-2812), the active table (matrix_free_operators.cc:227-246: n_q values per cell without
  * averaging, else 1), min / max after averaging (:248-262) and the level tables by interpolate_to_mg = mean of the children
  * (local_smoothing.cc:211-294).  Needs smf_set_level on all levels and smf_set_transfer; uniformly refined meshes.
@@ -137,6 +137,8 @@ int smf_set_cell_data(smf_ctx *ctx, int level, const smf_cell_data *data);
 #define SMF_AVG_ARITHMETIC 1
 #define SMF_AVG_HARMONIC 2
 #define SMF_AVG_GEOMETRIC 3
+#define SMF_AVG_PROJECT_Q1 4   /* `project to Q1 [only viscosity]`: DGQ1 projection space, 3^dim values per cell on the active mesh and on every level,
+                                 clamped to the range of the raw values (matrix_free_operators.cc:306-325, local_smoothing.cc:99-111, :274-289) */
 int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, double pressure_scaling, int is_compressible,
                        double *min_max_out);
 /* host copy [n_cells][n_per_cell] of a level's table as the kernels see it */

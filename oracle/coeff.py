@@ -97,6 +97,8 @@ def viscosity_tables(hier, eta_q, averaging):
     """
     dim = hier.dim
     t = fe.tensor_tables(dim)
+    if averaging == "project_q1":
+        return viscosity_tables_q1(hier, eta_q)
     out_q = average(eta_q, averaging)
     eta_min, eta_max = float(out_q.min()), float(out_q.max())          # matrix_free_operators.cc:248-262
     # cellwise L2 projection onto constants = JxW-weighted mean (utilities.cc:2738-2812)
@@ -110,6 +112,35 @@ def viscosity_tables(hier, eta_q, averaging):
         ch = hier.children(l)
         levels[l - 1] = levels[l][ch, 0].mean(axis=1)[:, None]
     return active, levels, eta_min, eta_max
+
+
+def viscosity_tables_q1(hier, eta_q):
+    """`Material averaging = project to Q1 [only viscosity]`: the projection space is DGQ1 (local_smoothing.cc:99-111).
+    * active level: cellwise L2 projection (JxW-weighted) of the RAW quadrature-point viscosities onto Q1
+      (Utilities::project_cellwise; no averaging, matrix_free_operators.cc:226-232), evaluated back at the quadrature points
+      and clamped to the [min, max] of the raw values (:306-325);
+    * levels: interpolate_to_mg of the DGQ1 vector -- FE_DGQ(1) is interpolatory with non-additive restriction, so a parent's
+      nodal value at vertex k is child k's function value there = child k's own nodal value k -- then the same evaluation and
+      clamp (local_smoothing.cc:274-289).  n_q values per cell on every level.
+    Returns (active_table, level_tables, eta_min, eta_max)."""
+    dim = hier.dim
+    t = fe.tensor_tables(dim)
+    phi = t["phi1"]                                                      # (nq, 2^dim), nodes lexicographic = vertex order
+    v = np.asarray(eta_q, float)
+    eta_min, eta_max = float(v.min()), float(v.max())
+    jxw = getattr(hier.active, "jxw", None)
+    w = np.broadcast_to(t["w"][None, :], v.shape) if jxw is None else np.asarray(jxw)
+    M = np.einsum("cq,qi,qj->cij", w, phi, phi)
+    b = np.einsum("cq,qi->ci", w * v, phi)
+    coef = np.linalg.solve(M, b[..., None])[..., 0]                      # DGQ1 nodal values per cell
+    ev = lambda c: np.clip(c @ phi.T, eta_min, eta_max)
+    levels = [None] * (hier.R + 1)
+    levels[hier.R] = ev(coef)
+    for l in range(hier.R, 0, -1):
+        ch = hier.children(l)
+        coef = np.stack([coef[ch[:, k], k] for k in range(1 << dim)], axis=1)
+        levels[l - 1] = ev(coef)
+    return levels[hier.R].copy(), levels, eta_min, eta_max
 
 
 def pressure_scaling_box(hier, eta_fn):

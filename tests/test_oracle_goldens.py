@@ -187,3 +187,30 @@ def test_operator_properties():
     fc = lambda X: X[:, 0] ** 2 - 0.5 * X[:, 1] * X[:, 2] + X[:, 2] ** 2
     uc = fc(hier.levels[1].dof_coords_u())
     assert np.abs(cb0.prolongate_u(2, uc) - fc(hier.levels[2].dof_coords_u())).max() < 1e-14
+
+
+@pytest.mark.parametrize("R,mesh_index", [(3, 0), (4, 1)])
+def test_prescribed_dilation_gmg_golden(R, mesh_index):
+    """tests/prescribed_dilation_gmg (2D box [0,2]^2, both meshes are uniform: refinement fraction 1): "35+0" / "36+0"
+    iterations and the printed errors u_L2, p_L2 = 1.794305e-04, 8.789932e-05 / 2.245432e-05, 5.910004e-06.  Pins the
+    prescribed-dilation branch (deviatoric active operators, right-hand side term -ps R q) AND that the level operators stay
+    non-deviatoric (local_smoothing.cc:312); with deviatoric level operators the solve takes 26 / 27 iterations."""
+    from oracle import prescribed_dilation as pd
+    g = golden("prescribed_dilation_gmg")
+    hier = mesh.Hierarchy(2, R, extents=[pd.EXTENT, pd.EXTENT])
+    act = hier.active
+    assert [act.n_u, act.n_p] == g["dofs_u_p"][mesh_index]
+    eta_q, ps, rhs, u0 = pd.problem(act)
+    active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, "harmonic")
+    be = solver.AssembledBackend(hier, active, levels, ps, "zero", compressible=False)            # level operators: not deviatoric
+    be.K, be.A_act, _ = assembled.stokes_matrix(act, active, ps, be.cu[-1], True)                 # active operators: deviatoric
+    K_plain, _, _ = assembled.stokes_matrix(act, active, ps, None, True)
+    rhs = rhs - K_plain @ np.concatenate([u0, np.zeros(act.n_p)])                                # correct_stokes_rhs
+    rhs[be.cu[-1]] = 0.0
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-12, restart=100, max_its=200)
+    assert out["converged"] and out["iterations"] == g["stokes_iterations_cheap_expensive"][2 * mesh_index][0]
+    u = out["x"][:act.n_u] + u0
+    p, _ = postprocess.normalize_pressure_volume(act, out["x"][act.n_u:] * ps)
+    eu, ep = pd.errors(act, u, p)
+    gu, gp = (float(v) for v in g["errors_uL2_pL2"][mesh_index])
+    assert abs(eu / gu - 1) < 2e-6 and abs(ep / gp - 1) < 2e-6, (eu, ep, gu, gp)

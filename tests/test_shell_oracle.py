@@ -138,3 +138,39 @@ def test_hollow_sphere_golden():
     err = hs.errors(L, u, p)
     for got, want in zip(err, g["errors_uL1_pL1_uL2_pL2"][0]):
         assert abs(got / float(want) - 1.0) < 2e-6, (err, g["errors_uL1_pL1_uL2_pL2"][0])
+
+
+def test_hollow_sphere_project_q1_golden():
+    """tests/hollow_sphere_gmg_project_q1 (`Material averaging = project to Q1 only viscosity`, viscosity parameter m = 3 of
+    benchmarks/hollow_sphere/hollow_sphere.prm): the DGQ1 viscosity tables (cellwise JxW-weighted L2 projection, evaluation at
+    the quadrature points, clamp, vertex-value level transfer; oracle/coeff.py: viscosity_tables_q1) reproduce the golden's
+    35 iterations exactly and its four error norms to the printed digits."""
+    from oracle import hollow_sphere as hs, solver
+    g = golden("hollow_sphere_gmg_project_q1")
+    m = 3
+    h = oshell.ShellHierarchy(1, 0.5, 1.0, n_coarse=12)
+    L = h.active
+    assert [L.n_u, L.n_p] == g["dofs_u_p"][0] and L.n_cells == g["active_cells"][0]
+    eta_q, rho_q = hs.material(L.xq, m)
+    active, levels, emin, emax = coeff.viscosity_tables(h, eta_q, "project_q1")
+    assert active.shape == (L.n_cells, 27) and levels[0].shape[1] == 27
+    assert active.min() >= emin and active.max() <= emax
+    xm, det = L.midpoint_geometry()
+    ps = float(np.exp((np.log(hs.material(xm, m)[0]) * det).sum() / det.sum()) / (1e4 / (6336000.0 - 3481000.0) * 0.5))
+    gdir = -L.xq / np.linalg.norm(L.xq, axis=-1, keepdims=True)
+    f = assembled.rhs_force(L, rho_q[..., None] * gdir)                 # "only viscosity": the density is not averaged
+    cons = L.constrained_u("zero")
+    u0 = np.zeros(L.n_u)
+    u0[cons] = hs.velocity(L.node_x_u, m).ravel()[cons]
+    K, _, _ = assembled.stokes_matrix(L, active, ps, None)
+    rhs = np.concatenate([f, np.zeros(L.n_p)]) - K @ np.concatenate([u0, np.zeros(L.n_p)])
+    rhs[cons] = 0.0
+    be = solver.AssembledBackend(h, active, levels, ps, "zero")
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-8, restart=100, max_its=100)
+    assert out["converged"] and out["iterations"] == g["stokes_iterations_cheap_expensive"][0][0] == 35
+    u, p = out["x"][:L.n_u] + u0, out["x"][L.n_u:] * ps
+    w, area = hs.surface_mean_weights(L)
+    p = p - (w @ p) / area
+    err = hs.errors(L, u, p, m)
+    for got, want in zip(err, g["errors_uL1_pL1_uL2_pL2"][0]):
+        assert abs(got / float(want) - 1.0) < 2e-6, (err, g["errors_uL1_pL1_uL2_pL2"][0])

@@ -10,7 +10,8 @@ import re
 
 REF = "/root/reference/tests"
 TESTS = ["nsinker_gmg_no_avg", "nsinker_gmg_gc", "nsinker_gmg_gc_no_avg", "nsinker_gmg_idr", "sol_cx_2_gmg", "sol_cx_4_gmg",
-         "sol_cx_4_gmg_no_avg", "no_cheap_gmg", "performance/performance_nsinker_gmg_idr", "spherical_nsinker_gmg_gc", "hollow_sphere_gmg"]
+         "sol_cx_4_gmg_no_avg", "no_cheap_gmg", "performance/performance_nsinker_gmg_idr", "spherical_nsinker_gmg_gc", "hollow_sphere_gmg",
+         "hollow_sphere_gmg_project_q1", "prescribed_dilation_gmg", "shell_3d_gmg"]
 
 
 def num(s):
@@ -31,6 +32,7 @@ def parse(path):
     out["A_preconditioner_applications"] = [int(a) for a in re.findall(r"A block preconditioner: (\d+)\+", txt)]
     m = re.findall(r"Errors u_L1, p_L1, u_L2, p_L2(?: topo_L2)?: (\S+), (\S+), (\S+), ([^\s,]+)", txt)
     out["errors_uL1_pL1_uL2_pL2"] = [list(x) for x in m]      # kept as the printed strings
+    out["errors_uL2_pL2"] = [list(x) for x in re.findall(r"Errors u_L2, p_L2:\s+(\S+), (\S+)", txt)]
     return out
 
 
