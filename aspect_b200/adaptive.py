@@ -135,6 +135,7 @@ class AdaptiveActive(_Mesh):
     def __init__(self, dim, levels, ijk, Lmax, extents):
         super().__init__(dim, levels, ijk, Lmax, extents)
         self.h_cell = extents[None, :] / (1 << levels)[:, None]                     # (cells, dim)
+        self.h = extents / (1 << Lmax)                                              # (unused: the cells go in with geometry = 1)
         self.hanging_u = self._hanging("u", 3, lambda x: np.stack([(1 - x) * (1 - 2 * x), 4 * x * (1 - x), x * (2 * x - 1)], -1))
         self.hanging_p = self._hanging("p", 2, lambda x: np.stack([1 - x, x], -1))
 
@@ -145,7 +146,7 @@ class AdaptiveActive(_Mesh):
         return (self.cells[:, None, :] + g[_lex(3, self.dim)][None, :, :]) * self.h_cell[:, None, :]
 
     @property
-    def inverse_jacobians(self):
+    def jinv(self):
         nq, dim = 3 ** self.dim, self.dim
         out = np.zeros((self.n_cells, nq, dim, dim))
         for d in range(dim):

@@ -2174,8 +2174,10 @@ int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bo
   CellParams P = make_params(L);
   P.src_u = src; P.dst_u = dst;
   if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_u, ctx->stream));
+  if (int e = hanging_pre(ctx, L.hang_u, src)) return e;              // read_dof_values resolves the hanging-node lines
   if (needs_general(L, 0)) { if (int e = launch_general(ctx, L, 0, dst, nullptr, src, nullptr, false)) return e; }
   else if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
+  if (int e = hanging_post(ctx, L.hang_u, dst, src, true)) return e;  // distribute_local_to_global + unit diagonal
   return exchange_add(ctx, L.ex_u, dst);
 }
 int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool plain)
@@ -2186,8 +2188,14 @@ int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p,
   P.plain = plain ? 1 : 0;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
   SMF_CUDA(cudaMemsetAsync(dst_p, 0, sizeof(double) * L.n_p, ctx->stream));
+  if (plain && (L.hang_u.n || L.hang_p.n))
+    return ctx->fail(SMF_ERR_UNSUPPORTED, "correct_stokes_rhs (read_dof_values_plain) on a mesh with hanging nodes: inhomogeneous hanging-node constraints are not implemented");
+  if (int e = hanging_pre(ctx, L.hang_u, src_u)) return e;
+  if (int e = hanging_pre(ctx, L.hang_p, src_p)) return e;
   if (needs_general(L, 1)) { if (int e = launch_general(ctx, L, 1, dst_u, dst_p, src_u, src_p, plain)) return e; }
   else if (int e = L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P)) return e;
+  if (int e = hanging_post(ctx, L.hang_u, dst_u, src_u, true)) return e;
+  if (int e = hanging_post(ctx, L.hang_p, dst_p, src_p, true)) return e;
   if (int e = exchange_add(ctx, L.ex_u, dst_u)) return e;
   return exchange_add(ctx, L.ex_p, dst_p);
 }
@@ -2197,8 +2205,11 @@ int launch_vmult_BT(smf_ctx *ctx, LevelDev &L, double *dst_u, const double *src_
   CellParams P = make_params(L);
   P.src_p = src_p; P.dst_u = dst_u;
   SMF_CUDA(cudaMemsetAsync(dst_u, 0, sizeof(double) * L.n_u, ctx->stream));
+  if (int e = hanging_pre(ctx, L.hang_p, src_p)) return e;
   if (L.geo) { if (int e = launch_general(ctx, L, 2, dst_u, nullptr, nullptr, src_p, false)) return e; }
   else if (int e = L.dim == 3 ? launch_velocity<3, 2>(ctx, L, P) : launch_velocity<2, 2>(ctx, L, P)) return e;
+  if (int e = hanging_restore(ctx, L.hang_p, src_p)) return e;
+  if (int e = hanging_post(ctx, L.hang_u, dst_u, nullptr, false)) return e;      // (the velocity source block of B^T is zero)
   return exchange_add(ctx, L.ex_u, dst_u);
 }
 int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero)
@@ -2207,6 +2218,7 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src,
   CellParams P = make_params(L);
   P.src_p = src; P.dst_p = dst;
   if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_p, ctx->stream));
+  if (int e = hanging_pre(ctx, L.hang_p, src)) return e;
   const size_t smem = (size_t)MASS_WARPS * 2 * L.max_nodes_p * sizeof(double);
   const unsigned grid = (unsigned)((L.n_batches + MASS_WARPS - 1) / MASS_WARPS);
   if (L.geo) {
@@ -2237,6 +2249,7 @@ int launch_vmult_mass(smf_ctx *ctx, LevelDev &L, double *dst, const double *src,
   }
   ctx->launches++;
   SMF_CUDA(cudaGetLastError());
+  if (int e = hanging_post(ctx, L.hang_p, dst, src, true)) return e;
   return exchange_add(ctx, L.ex_p, dst);
 }
 
@@ -2269,6 +2282,13 @@ int launch_diag(smf_ctx *ctx, LevelDev &L)
     set_entries_kernel<<<(unsigned)((L.n_constrained_p + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_M, L.constrained_p, L.n_constrained_p, 1.0);
     ctx->launches++;
   }
+  // refinement-edge rows of a level operator and hanging rows of the active operator carry a unit diagonal, too
+  // (A_l = (I - E) A_bc (I - E) + E; the diagonal of C^T A C on the masters of hanging nodes is not corrected: the active
+  // diagonal is not used by the solve)
+  if (L.edge_u.n) { set_entries_kernel<<<(unsigned)((L.edge_u.n + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_A, L.edge_u.idx, L.edge_u.n, 1.0); ctx->launches++; }
+  if (L.edge_p.n) { set_entries_kernel<<<(unsigned)((L.edge_p.n + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_M, L.edge_p.idx, L.edge_p.n, 1.0); ctx->launches++; }
+  if (L.hang_u.n) { set_entries_kernel<<<(unsigned)((L.hang_u.n + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_A, L.hang_u.dof, L.hang_u.n, 1.0); ctx->launches++; }
+  if (L.hang_p.n) { set_entries_kernel<<<(unsigned)((L.hang_p.n + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_M, L.hang_p.dof, L.hang_p.n, 1.0); ctx->launches++; }
   invert_diag_kernel<<<(unsigned)((L.n_u + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_A, L.n_u);
   invert_diag_kernel<<<(unsigned)((L.n_p + 255) / 256), 256, 0, ctx->stream>>>(L.dinv_M, L.n_p);
   ctx->launches += 2;

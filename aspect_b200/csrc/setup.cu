@@ -33,6 +33,7 @@ static void free_level(LevelDev &L)
   cudaFree(L.eta); cudaFree(L.dinv_A); cudaFree(L.dinv_M); cudaFree(L.geo); cudaFree(L.cell_nodes_u_t); cudaFree(L.cell_nodes_p_t);
   cudaFree(L.nd.eps); cudaFree(L.nd.deta); cudaFree(L.nd.detadp); cudaFree(L.nd.dil_lhs); cudaFree(L.nd.ddil); cudaFree(L.nd.ddildp);
   free_exchange(L.ex_u); free_exchange(L.ex_p);
+  free_adaptive(L);
   L = LevelDev();
 }
 
@@ -245,7 +246,7 @@ void smf_destroy(smf_ctx *ctx)
   for (auto &L : ctx->levels) free_level(L);
   for (auto &T : ctx->transfers) { cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u); cudaFree(T.children); }
   for (auto *mg : {&ctx->mgv_A, &ctx->mgv_S})
-    for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); }
+    for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); cudaFree(v.e); }
   for (double *p : ctx->krylov) cudaFree(p);
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
   cudaFree(ctx->io_buf); cudaFree(ctx->block_weights); cudaFree(ctx->pnorm_weights); cudaFree(ctx->cg_buf); cudaFree(ctx->idr_normals);
@@ -460,7 +461,11 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
     for (int d = 0; d < dim; ++d) { npatch *= npp; nloc *= npd; }
     patch.assign((size_t)T.n_parents * npatch, 0);
     std::vector<uint8_t> seen((size_t)n_fine_index, 0);
-    for (int64_t par = 0; par < T.n_parents; ++par)
+    for (int64_t par = 0; par < T.n_parents; ++par) {
+      if (children[par * NCH] < 0) {       // adaptive mesh: this parent is not refined -- its patch stays empty (no owner bits)
+        for (int ch = 1; ch < NCH; ++ch) if (children[par * NCH + ch] >= 0) return false;
+        continue;
+      }
       for (int s = 0; s < npatch; ++s) {
         int r = s, child = 0, a = 0, mul = 1;
         for (int d = 0; d < dim; ++d) {
@@ -481,11 +486,12 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
         }
         patch[(size_t)par * npatch + s] = e;
       }
+    }
     return true;
   };
   std::vector<uint32_t> pu, pp;
   if (!build(3, F.h_nodes_u, F.n_u, F.h_not_owned_u, pu) || !build(2, F.h_nodes_p, F.n_p, F.h_not_owned_p, pp))
-    return ctx->fail(SMF_ERR_UNSUPPORTED, "children table has unrefined / out-of-range entries (adaptive meshes not implemented)");
+    return ctx->fail(SMF_ERR_INVALID, "children table: out-of-range entries, or a parent with only some of its children");
   int64_t bytes = 0;
   int e;
   if ((e = upload(ctx, &T.patch_u, pu, &bytes))) return e;
@@ -494,7 +500,10 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
   if (dim == 3 && F.structured && F.sb_lists && !F.h_sb_list.empty()) {
     std::vector<int32_t> parent_of((size_t)F.n_cells, -1), child_no((size_t)F.n_cells, -1);
     for (int64_t par = 0; par < T.n_parents; ++par)
-      for (int ch = 0; ch < 8; ++ch) { parent_of[children[par * 8 + ch]] = (int32_t)par; child_no[children[par * 8 + ch]] = ch; }
+      for (int ch = 0; ch < 8; ++ch) {
+        if (children[par * 8 + ch] < 0) continue;
+        parent_of[children[par * 8 + ch]] = (int32_t)par; child_no[children[par * 8 + ch]] = ch;
+      }
     const int nbr = F.n_batches;
     std::vector<unsigned char> tb((size_t)nbr * TB_BYTES, 0);
     std::vector<uint8_t> seen((size_t)F.n_u, 0);

@@ -100,6 +100,16 @@ __host__ __device__ inline int64_t blk_cells(int64_t n_cells) { return (n_cells 
 
 constexpr int SMF_MAX_RESTART = 200;   // longest GMRES / FGMRES restart length (nsinker_spherical_shell/gmg.prm uses 200); sizes the multi-dot scratch
 
+// closed constraint lines u_k = sum_j w_j u_{m_j} (hanging nodes) of one DoF family, CSR on the device (adaptive.cu)
+struct ConstraintLines {
+  int64_t n = 0;
+  uint32_t *dof = nullptr, *start = nullptr, *master = nullptr;
+  double *weight = nullptr, *save = nullptr;       // save: [n] the constrained entries of src while the cell loop runs
+};
+// refinement-edge indices of one level and family + scratch
+struct EdgeSet { int64_t n = 0; uint32_t *idx = nullptr; double *save = nullptr; };
+struct CopyPairs { int64_t n = 0; uint32_t *active = nullptr, *level = nullptr; };
+
 struct LevelDev {
   int dim = 0;
   int64_t n_cells = 0, n_u = 0, n_p = 0;
@@ -133,6 +143,10 @@ struct LevelDev {
   std::vector<uint8_t> h_cons_u, h_cons_p;      // host constraint bitmaps (needed by smf_set_exchange)
   std::vector<uint8_t> h_not_owned_u, h_not_owned_p;   // DoFs whose owner is a lower rank (set by smf_set_exchange)
   ExchangeDev ex_u, ex_p;
+  // adaptive meshes (adaptive.cu)
+  ConstraintLines hang_u, hang_p;               // ACTIVE level: hanging-node lines
+  EdgeSet edge_u, edge_p;                       // levels: refinement-edge indices
+  CopyPairs copy_u, copy_p;                     // levels: copy_to_mg / copy_from_mg pairs
 };
 
 constexpr int TB_COARSE = 76;      // coarse velocity nodes under a fine brick: 5 x 5 x 3 lattice = 75, padded
@@ -164,6 +178,7 @@ struct ProfEvent { int bucket; cudaEvent_t a, b; };
 
 struct MGVectors {                // per level: solution, defect, t, and a Chebyshev scratch
   double *x = nullptr, *b = nullptr, *t = nullptr, *xo = nullptr;
+  double *e = nullptr;            // adaptive meshes: the edge part of the iterate (vmult_interface_up), allocated on demand
   double *res = nullptr;          // where the last level_v_step left the solution (x or xo)
   bool t_zero = false;            // t is known to be all zero (left so by cheb_update): the next operator application skips its memset
 };
@@ -181,6 +196,7 @@ struct smf_ctx {
   std::vector<smf::MGVectors> mgv_A, mgv_S;
   uint32_t *copy_u = nullptr, *copy_p = nullptr;      // active -> finest level index maps (nullptr = identity)
   bool smoothers_ready = false;
+  bool adaptive = false;                              // per-level copy indices set: adaptive V-cycle (solver.cu)
   int64_t launches = 0;
   int64_t bytes = 0;
   double *scratch = nullptr; int64_t scratch_n = 0;   // reduction scratch
@@ -273,6 +289,16 @@ int launch_set_entries(smf_ctx *ctx, double *vec, const uint32_t *idx, int64_t n
 int launch_rhs(smf_ctx *ctx, LevelDev &L, const double *force_q_dev, double *rhs_u);
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);
+// adaptive.cu: hanging-node lines around a cell loop; refinement-edge handling of the level operators
+int hanging_pre(smf_ctx *ctx, ConstraintLines &H, const double *src);                // save src[k]; src[k] = sum_j w_j src[m_j]
+int hanging_post(smf_ctx *ctx, ConstraintLines &H, double *dst, const double *src, bool unit_diagonal);   // dst[m_j] += w_j dst[k]; dst[k] = saved (or 0); src[k] = saved
+int hanging_restore(smf_ctx *ctx, ConstraintLines &H, const double *src);                                                   // src[k] = saved
+int edge_pre(smf_ctx *ctx, EdgeSet &E, const double *src);                           // save src[e]; src[e] = 0
+int edge_post(smf_ctx *ctx, EdgeSet &E, double *dst, const double *src, bool add);   // dst[e] = saved (add: += saved); src[e] = saved
+int edge_extract(smf_ctx *ctx, const EdgeSet &E, double *xe, const double *x, int64_t n);        // xe = E x
+int edge_subtract_off(smf_ctx *ctx, const EdgeSet &E, double *b, const double *y, int64_t n);   // b -= (I - E) y
+int copy_pairs(smf_ctx *ctx, const CopyPairs &C, double *level_vec, double *active_vec, bool to_level);
+void free_adaptive(LevelDev &L);
 // comm.cu
 void free_exchange(ExchangeDev &E);
 int exchange_add(smf_ctx *ctx, ExchangeDev &E, double *vec);

@@ -68,8 +68,21 @@ struct MGSide {           // one of the two hierarchies
 
 static int64_t lsize(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].n_u : ctx->levels[l].n_p; }
 static const double *ldinv(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].dinv_A : ctx->levels[l].dinv_M; }
-static int lapply(smf_ctx *ctx, const MGSide &S, int l, double *dst, const double *src, bool dst_is_zero = false)
+static int lapply_raw(smf_ctx *ctx, const MGSide &S, int l, double *dst, const double *src, bool dst_is_zero = false)
 { return S.velocity ? launch_vmult_A(ctx, ctx->levels[l], dst, src, dst_is_zero) : launch_vmult_mass(ctx, ctx->levels[l], dst, src, dst_is_zero); }
+static EdgeSet &ledge(smf_ctx *ctx, const MGSide &S, int l) { return S.velocity ? ctx->levels[l].edge_u : ctx->levels[l].edge_p; }
+// Level operator of local smoothing.  Without refinement edges: the cell loop.  With them (MatrixFreeOperators::Base with
+// edge_constrained_indices): the edge entries of src are parked and zeroed around the loop, which then yields
+// A_bc (I - E) x on all rows; the edge rows become x_E (the level operator A_l = (I - E) A_bc (I - E) + E of the smoothers) or,
+// with_interface_down, A_bc (I - E) x + x_E = (A_l + vmult_interface_down) x, what the V-cycle's residual needs
+static int lapply(smf_ctx *ctx, const MGSide &S, int l, double *dst, const double *src, bool dst_is_zero = false, bool with_interface_down = false)
+{
+  EdgeSet &E = ledge(ctx, S, l);
+  if (E.n == 0) return lapply_raw(ctx, S, l, dst, src, dst_is_zero);
+  TRY(edge_pre(ctx, E, src));
+  TRY(lapply_raw(ctx, S, l, dst, src, dst_is_zero));
+  return edge_post(ctx, E, dst, src, with_interface_down);
+}
 // operator application into the level's t vector: the memset is skipped when the last cheb_update left t zeroed
 static int lapply_t(smf_ctx *ctx, const MGSide &S, int l, const double *src)
 {
@@ -199,6 +212,60 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
   return SMF_OK;
 }
 
+// Multigrid::level_v_step on an adaptively refined mesh (local smoothing; oracle/adaptive.py: AdaptiveVCycle._run):
+// the defect of every level was filled by copy_to_mg, so the restriction ADDS; the residual carries the edge_out term
+// (vmult_interface_down, fused into the level's cell loop), and before post-smoothing the defect loses
+// vmult_interface_up(x) = (I - E) A_bc (E x) (one more cell loop on the edge part of the iterate).
+static int level_v_step_adaptive(smf_ctx *ctx, const MGSide &S, int l)
+{
+  MGVectors &V = (*S.v)[l];
+  const int which = S.velocity ? 0 : 1;
+  VecBucket vb(ctx, B_SMOOTH_VEC);
+  const int64_t n = lsize(ctx, S, l);
+  double *x = V.x, *xo = V.xo;
+  V.t_zero = false;
+  TRY(cheb_vmult(ctx, S, l, x, xo, V.b, V.t));
+  for (int s = 1; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));
+  if (l > 0) {
+    MGVectors &C = (*S.v)[l - 1];
+    V.t_zero = false;
+    TRY(lapply(ctx, S, l, V.t, x, false, true));                              // t = (A_l + interface_down) x
+    TRY(vec_residual(ctx, V.t, V.b, n));                                     // t = defect - t
+    TRY(launch_restrict_add(ctx, which, l, C.b, V.t));                       // onto the copy_to_mg part of the coarse defect
+    TRY(level_v_step_adaptive(ctx, S, l - 1));
+    TRY(launch_prolongate(ctx, which, l, x, C.res, true));
+    EdgeSet &E = ledge(ctx, S, l);
+    if (E.n) {
+      if (!V.e) { SMF_CUDA(cudaMalloc(&V.e, sizeof(double) * n)); ctx->bytes += sizeof(double) * n; }
+      TRY(edge_extract(ctx, E, V.e, x, n));                                  // e = E x
+      TRY(lapply_raw(ctx, S, l, V.t, V.e, false));                           // t = A_bc e
+      TRY(edge_subtract_off(ctx, E, V.b, V.t, n));                           // defect -= (I - E) t
+    }
+    V.t_zero = false;
+    for (int s = 0; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));
+  }
+  V.res = x;
+  return SMF_OK;
+}
+
+// PreconditionMG::vmult on an adaptive mesh: copy_to_mg fills the defects of ALL levels from the active vector, copy_from_mg
+// collects the solutions of all levels (MGTransferMatrixFree copy indices, smf_set_level_copy_indices)
+static int vcycle_adaptive(smf_ctx *ctx, const MGSide &S, double *dst, const double *src)
+{
+  const int nl = ctx->cfg.n_levels;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  for (int l = 0; l < nl; ++l) {
+    MGVectors &V = (*S.v)[l];
+    TRY(vec_set(ctx, V.b, 0.0, lsize(ctx, S, l)));
+    TRY(copy_pairs(ctx, S.velocity ? ctx->levels[l].copy_u : ctx->levels[l].copy_p, V.b, const_cast<double *>(src), true));
+  }
+  TRY(level_v_step_adaptive(ctx, S, nl - 1));
+  TRY(vec_set(ctx, dst, 0.0, S.velocity ? A.n_u : A.n_p));
+  for (int l = 0; l < nl; ++l)
+    TRY(copy_pairs(ctx, S.velocity ? ctx->levels[l].copy_u : ctx->levels[l].copy_p, (*S.v)[l].res, dst, false));
+  return SMF_OK;
+}
+
 // Levels <= ctx->graph_level are small: their part of the V-cycle is launch-latency bound, so it is captured once per
 // smoother set-up into a CUDA graph (all buffers and coefficients are fixed between set-ups) and replayed.
 static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
@@ -246,6 +313,7 @@ static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
 {
   if (!ctx->smoothers_ready) return ctx->fail(SMF_ERR_INVALID, "call smf_setup_smoothers before applying a V-cycle");
   MGSide S{velocity, velocity ? &ctx->smoother_A : &ctx->smoother_S, velocity ? &ctx->mgv_A : &ctx->mgv_S, velocity ? 1 : 4};
+  if (ctx->adaptive) return vcycle_adaptive(ctx, S, dst, src);
   const int L = ctx->cfg.n_levels - 1;
   const int64_t n = lsize(ctx, S, L);
   const uint32_t *map = velocity ? ctx->copy_u : ctx->copy_p;
@@ -775,6 +843,10 @@ int smf_vmult_A(smf_ctx *ctx, int level, double *dst, const double *src)
 {
   if (!ctx) return SMF_ERR_INVALID;
   if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  if (level >= 0 && ctx->levels[level].edge_u.n) {       // level operator with refinement-edge rows: A_l = (I - E) A_bc (I - E) + E
+    MGSide S{true, nullptr, nullptr, 1};
+    return lapply(ctx, S, level, dst, src);
+  }
   return launch_vmult_A(ctx, ctx->lev(level), dst, src);
 }
 int smf_vmult_BT(smf_ctx *ctx, double *dst_u, const double *src_p)
@@ -783,6 +855,10 @@ int smf_vmult_mass(smf_ctx *ctx, int level, double *dst, const double *src)
 {
   if (!ctx) return SMF_ERR_INVALID;
   if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  if (level >= 0 && ctx->levels[level].edge_p.n) {
+    MGSide S{false, nullptr, nullptr, 4};
+    return lapply(ctx, S, level, dst, src);
+  }
   return launch_vmult_mass(ctx, ctx->lev(level), dst, src);
 }
 

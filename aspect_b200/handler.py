@@ -171,6 +171,23 @@ class StokesMatrixFreeHandler:
             ch = np.ascontiguousarray(hierarchy.children(l), dtype=np.int32)
             self._check(self.lib.smf_set_transfer(self.ctx, l, ptr(ch)))
         self._check(self.lib.smf_set_copy_indices(self.ctx, ptr(None), ptr(None)))
+        self.adaptive = bool(getattr(hierarchy, "adaptive", False))
+        self._lines = {}
+        if self.adaptive:
+            # hanging-node lines of the active mesh, refinement edges and copy indices of the levels
+            u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+            for family, name in ((0, "u"), (1, "p")):
+                dof, start, master, weight = hierarchy.active.constraint_lines(name, boundary)
+                self._lines[name] = (dof.astype(np.int64), start.astype(np.int64), master.astype(np.int64), weight)
+                self._check(self.lib.smf_set_constraints(self.ctx, SMF_ACTIVE, family, ctypes.c_int64(len(dof)), ptr(u32(dof)), ptr(u32(start)),
+                                                         ptr(u32(master)), ptr(np.ascontiguousarray(weight, dtype=np.float64))))
+            for l in range(n_levels):
+                L = hierarchy.levels[l]
+                eu, ep = u32(L.edge_u), u32(L.edge_p)
+                self._check(self.lib.smf_set_refinement_edges(self.ctx, l, ctypes.c_int64(len(eu)), ptr(eu), ctypes.c_int64(len(ep)), ptr(ep)))
+                au, lu, ap, lp = hierarchy.copy_indices(l)
+                self._check(self.lib.smf_set_level_copy_indices(self.ctx, l, 0, ctypes.c_int64(len(au)), ptr(u32(au)), ptr(u32(lu))))
+                self._check(self.lib.smf_set_level_copy_indices(self.ctx, l, 1, ctypes.c_int64(len(ap)), ptr(u32(ap)), ptr(u32(lp))))
         self.n_u, self.n_p = hierarchy.active.n_u, hierarchy.active.n_p
         self.n_levels = n_levels
         # operator objects (duck-typed vmult like the reference's)
@@ -229,6 +246,20 @@ class StokesMatrixFreeHandler:
         """evaluate_material_model(): viscosity_q = plugin output at the velocity quadrature points of the
         active cells, (n_cells, 3^dim)."""
         self.pressure_scaling = float(pressure_scaling)
+        if getattr(self, "adaptive", False):
+            # adaptive mesh: cell-wise averaging as always; the level tables follow interpolate_to_mg on the partial levels
+            # (a level cell carries its own value where it is active, else the mean of its children; local_smoothing.cc:220-226)
+            q = cell_data.average_viscosity(np.asarray(viscosity_q, dtype=np.float64), material_averaging)
+            self.minimum_viscosity, self.maximum_viscosity = float(q.min()), float(q.max())
+            w = cell_data.quadrature_weights(self.dim)
+            dg0 = (q * w[None, :]).sum(axis=1) / w.sum()
+            active = q if material_averaging == "none" else dg0[:, None]
+            levels = [np.ascontiguousarray(v[:, None]) for v in self.hier.level_viscosity(dg0)]
+            self.set_cell_data(SMF_ACTIVE, np.ascontiguousarray(active), pressure_scaling, is_compressible)
+            for l in range(self.n_levels):
+                self.set_cell_data(l, levels[l], pressure_scaling, is_compressible)
+            self._tables = (active, levels)
+            return
         if self.device_cell_data:
             # averaging, DGQ0 projection, min / max and the level tables on the device (smf_fill_cell_data)
             op = material_averaging.replace(" only viscosity", "")
@@ -406,7 +437,30 @@ class StokesMatrixFreeHandler:
         out = self._outputs(res)
         self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
         out["converged"] = rc == 0
+        if getattr(self, "adaptive", False):
+            self.distribute_constraints(sol)
         return sol, out
+
+    def distribute_constraints(self, sol):
+        """`current_constraints.distribute(solution)` for the hanging-node lines (local_smoothing.cc:1424): the solve leaves
+        zeros in the constrained entries; they take the value of their masters.  sol = host [u | p], changed in place."""
+        for name, off in (("u", 0), ("p", self.n_u)):
+            dof, start, master, weight = self._lines.get(name, (np.zeros(0, np.int64),) * 4)
+            if len(dof):
+                vals = np.add.reduceat(weight * sol[off + master], start[:-1]) if len(master) else np.zeros(len(dof))
+                vals[start[:-1] == start[1:]] = 0.0
+                sol[off + dof] = vals
+        return sol
+
+    def condense_rhs(self, rhs):
+        """`constraints.distribute_local_to_global` on an assembled right-hand side: rhs += C^T-part of the hanging rows, then
+        the constrained rows are zeroed.  rhs = host [u | p], changed in place."""
+        for name, off in (("u", 0), ("p", self.n_u)):
+            dof, start, master, weight = self._lines.get(name, (np.zeros(0, np.int64),) * 4)
+            if len(dof):
+                np.add.at(rhs, off + master, weight * np.repeat(rhs[off + dof], np.diff(start)))
+                rhs[off + dof] = 0.0
+        return rhs
 
     def correct_stokes_rhs(self, rhs, u0):
         """`StokesMatrixFreeHandler::correct_stokes_rhs` (local_smoothing.cc:617-754): rhs -= Stokes(u0) for inhomogeneous

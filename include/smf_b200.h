@@ -86,10 +86,34 @@ typedef struct {
 int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *mesh);
 
 /* MGTransferMatrixFree::build (local_smoothing.cc:1843-1850): parent->children table of level `fine_level`
- * ([n_cells(fine_level-1)][2^dim] cell ids on fine_level, deal.II child order). */
+ * ([n_cells(fine_level-1)][2^dim] cell ids on fine_level, deal.II child order).  On adaptively refined meshes a parent that
+ * is not refined has -1 in all its entries (it takes no part in the transfer). */
 int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children);
 /* copy_to_mg / copy_from_mg index map: level-(n_levels-1) DoF of every active DoF (NULL = identity). */
 int smf_set_copy_indices(smf_ctx *ctx, const uint32_t *active_to_level_u, const uint32_t *active_to_level_p);
+
+/* ---- adaptively refined meshes (hanging nodes, local smoothing with refinement edges) ---------------------------------
+ * What setup_dofs() builds on an adaptive mesh and the matrix-free operators / the V-cycle apply:
+ *
+ * smf_set_constraints: the closed lines u_k = sum_j w_j u_{m_j} of the level's AffineConstraints that are not plain
+ *   homogeneous Dirichlet rows -- the hanging-node constraints of DoFTools::make_hanging_node_constraints
+ *   (local_smoothing.cc:1508, :1580; ACTIVE level) -- in CSR form: line i constrains constrained_dof[i] to the masters
+ *   master_dof[row_start[i] .. row_start[i+1]) with weights weight[..].  Masters are unconstrained DoFs (the lines are
+ *   closed; Dirichlet masters dropped).  The operators then act as MatrixFreeOperators::Base does: read_dof_values
+ *   resolves the lines, distribute_local_to_global applies their transpose, constrained rows get dst = src
+ *   (A_mf = C^T A C + I_constrained).  family 0: velocity, 1: pressure.  n_lines = 0 clears.
+ * smf_set_refinement_edges: MGConstrainedDoFs::get_refinement_edge_indices of one level (:1733-1773).  The level operators
+ *   then treat these DoFs like Dirichlet DoFs (A_l = (I - E) A_bc (I - E) + E, as Base::vmult with edge_constrained_indices),
+ *   and the V-cycles add the interface products vmult_interface_down / vmult_interface_up (mg::Matrix edge matrices,
+ *   :879-911).  Levels keep only the boundary indices in smf_level_mesh::constrained_u.
+ * smf_set_level_copy_indices: MGTransferMatrixFree's copy_indices of one level: active DoF active_idx[i] <-> level DoF
+ *   level_idx[i] (copy_to_mg / copy_from_mg on an adaptive mesh).  Setting them on any level switches the V-cycles to the
+ *   adaptive algorithm (defects of all levels filled from the active vector, restriction ADDS, solutions of all levels
+ *   copied back). */
+int smf_set_constraints(smf_ctx *ctx, int level, int family, int64_t n_lines, const uint32_t *constrained_dof,
+                        const uint32_t *row_start, const uint32_t *master_dof, const double *weight);
+int smf_set_refinement_edges(smf_ctx *ctx, int level, int64_t n_u, const uint32_t *edge_u, int64_t n_p, const uint32_t *edge_p);
+int smf_set_level_copy_indices(smf_ctx *ctx, int level, int family, int64_t n, const uint32_t *active_idx, const uint32_t *level_idx);
 
 /* ---- distributed runs: one context per MPI rank / GPU ----------------------------------------------------------
  * Replaces LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) around every cell loop

@@ -67,5 +67,5 @@ def test_driver_equals_oracle(dim, base, n_adaptive, marker):
     hanging_dofs = {dim * k + c for k in act.hanging_u for c in range(dim)}
     assert set(range(act.n_u)) - set(seen.tolist()) <= hanging_dofs
     # geometry tables of the active mesh
-    assert act.inverse_jacobians.shape == (act.n_cells, 3 ** dim, dim, dim) and np.allclose(act.jxw.sum(), 1.0)
+    assert act.jinv.shape == (act.n_cells, 3 ** dim, dim, dim) and np.allclose(act.jxw.sum(), 1.0)
     assert np.allclose(act.quadrature_points(), box.quadrature_points())
