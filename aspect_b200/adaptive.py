@@ -10,8 +10,8 @@ adaptively refined `parallel::distributed::Triangulation` of a one-tree box and 
 * the DGQ0 level viscosity tables of `interpolate_to_mg` on such a hierarchy (:220-226): a level cell carries its own value
   where it is active, else the mean of its children.
 
-Vectorised numpy over integer lattice keys; the oracle holds an independent, dictionary-based restatement
-(oracle/adaptive.py) and tests/test_adaptive_driver.py checks that both produce identical arrays.
+Vectorised numpy over integer lattice keys; tests/test_adaptive_driver.py checks the arrays against an independent,
+dictionary-based restatement kept with the test infrastructure.
 """
 import itertools
 

@@ -6,7 +6,7 @@
 // the deal.II semantics of MatrixFreeOperators::Base: read_dof_values resolves the constraint lines,
 // distribute_local_to_global applies their transpose, constrained rows get dst = src; with edge_constrained_indices the
 // level operator is A_l = (I - E) A_bc (I - E) + E and vmult_interface_down / _up are E A_bc (I - E) / (I - E) A_bc E.
-// Semantics fixed by oracle/adaptive.py (AdaptiveBox.assemble, AdaptiveHierarchy.level_operators, AdaptiveVCycle).
+// (tests/test_gpu_adaptive.py checks every piece against the CPU restatement of these semantics.)
 //
 // The cell kernels stay untouched: a hanging node is an ordinary node of its cell.  Around the cell loop
 //   hanging_pre   src[k] <- sum_j w_j src[m_j]   (the old entry is parked; a constrained entry of src is never read otherwise)

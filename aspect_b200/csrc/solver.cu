@@ -212,7 +212,7 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
   return SMF_OK;
 }
 
-// Multigrid::level_v_step on an adaptively refined mesh (local smoothing; oracle/adaptive.py: AdaptiveVCycle._run):
+// Multigrid::level_v_step on an adaptively refined mesh (local smoothing, SURVEY App. A.3 with edge matrices):
 // the defect of every level was filled by copy_to_mg, so the restriction ADDS; the residual carries the edge_out term
 // (vmult_interface_down, fused into the level's cell loop), and before post-smoothing the defect loses
 // vmult_interface_up(x) = (I - E) A_bc (E x) (one more cell loop on the edge part of the iterate).
