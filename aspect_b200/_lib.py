@@ -17,6 +17,8 @@ SMF_OPT_STRUCTURED_BRICKS, SMF_OPT_CUDA_GRAPHS, SMF_OPT_ORTHO_SINGLE_PASS, SMF_O
 SMF_OPT_P2P_EXCHANGE = 5
 SMF_OPT_CURVED_SUMFAC = 6
 SMF_OPT_CURVED_TMA = 7
+SMF_OPT_WARP_BRICK_KERNEL = 8
+SMF_OPT_COARSE_TAIL = 9
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p

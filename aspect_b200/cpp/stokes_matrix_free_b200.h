@@ -13,6 +13,7 @@
 #define ASPECT_B200_STOKES_MATRIX_FREE_B200_H
 
 #include <cstdint>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -115,6 +116,8 @@ namespace aspect_b200
         throw std::runtime_error("smf_create failed: a CUDA device is required (there is no CPU fallback)");
       char id[SMF_UNIQUE_ID_BYTES] = {0};
       check(smf_comm_init(ctx, 0, 1, id));
+      if (const char *e = std::getenv("SMF_WARP_BRICK")) check(smf_set_option(ctx, SMF_OPT_WARP_BRICK_KERNEL, std::atoi(e)));   // kernel experiments
+      if (const char *e = std::getenv("SMF_COARSE_TAIL")) check(smf_set_option(ctx, SMF_OPT_COARSE_TAIL, std::atoi(e)));
       for (int level = 0; level <= n_levels; ++level)
         {
           const LevelArrays &L = level < n_levels ? h.levels[level] : h.active;

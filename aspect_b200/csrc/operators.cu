@@ -843,6 +843,250 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
   }
 }
 
+// ---- structured bricks, ONE WARP PER BRICK, all three velocity components of a cell in one thread -----------------
+// velocity_sb_kernel above is bound by the shared-memory pipe (69 % of its wavefront peak at 38 % FP64): half of its
+// shared-memory traffic is the exchange of the symmetric off-diagonal stress between the three component warps, and its
+// three warps meet at four block-wide barriers per brick.  Here lane l owns cell l of the brick with ALL 81 values in
+// registers: the exchange disappears -- X_cd = eta w (d_d u_c + d_c u_d) is formed in registers, once along the d-lines
+// for test component c and once along the c-lines for test component d (+29 % FP64 instructions, the price for not
+// holding two 27-value accumulators next to the 81 values) -- and a warp depends on nobody: no __syncthreads, only
+// __syncwarp.  Per cell the shared-memory traffic is 81 gathers + 81 read-modify-writes + staging / flush (0.85 kB per
+// cell-component instead of 1.7 kB).  Each warp is its own block, persistent over the bricks b, b + G, ...; two
+// staging buffers per warp ([3][SB_SLOTS] doubles each: the values of brick i+1 arrive by cp.async while brick i is
+// computed; the buffer of brick i turns into its accumulation buffer once the gathers are done, first-touch stores
+// instead of a zero fill as above); node lists double-buffered the same way.
+constexpr size_t sbw_smem_bytes(int mode)
+{ return (size_t)(2 * 3 * SB_SLOTS) * sizeof(double) + 2 * (size_t)(mode == 0 ? SB_LIST_BYTES : SB_BLOCK_BYTES) + (mode == 0 ? 0 : 2 * SB_PLIST * sizeof(double)); }
+
+// value of (2 D'_DIR w) at point n, from the line of w through n along DIR
+template <int DIR> __device__ __forceinline__ double dpoint(const double (&w)[27], int n)
+{
+  constexpr int S = stride3(DIR);
+  const int pos = (n / S) % 3, base = n - pos * S;
+  const double a = w[base], b = w[base + S], c = w[base + 2 * S];
+  return pos == 0 ? fma(4.0, b - a, a - c) : (pos == 1 ? c - a : fma(4.0, c - b, a - c));
+}
+// T (+)= e_D (2D'_D)^T [ cvol w_q eta_q (e_D 2D'_D uc + e_C 2D'_C ud) ] : the off-diagonal pair (C, D) seen from test component C
+template <int C, int D, bool PERQ>
+__device__ __forceinline__ void sbw_offdiag(const double (&uc)[27], const double (&ud)[27], double (&T)[27], double eC, double eD, double cvol, const double *etab)
+{
+  const double e3 = 3.0 * eD, e4 = 4.0 * eD;
+  for_lines<3, D>([&](int a, int b, int c) {
+    double ga, gb, gc;
+    dline(uc[a], uc[b], uc[c], ga, gb, gc);
+    double xa = fma(eD, ga, eC * dpoint<C>(ud, a)), xb = fma(eD, gb, eC * dpoint<C>(ud, b)), xc = fma(eD, gc, eC * dpoint<C>(ud, c));
+    if (PERQ) { xa *= cvol * qweight<3>(a) * etab[a * SUB]; xb *= cvol * qweight<3>(b) * etab[b * SUB]; xc *= cvol * qweight<3>(c) * etab[c * SUB]; }
+    else { xa *= cvol * qweight<3>(a); xb *= cvol * qweight<3>(b); xc *= cvol * qweight<3>(c); }
+    dTline_add(T[a], T[b], T[c], xa, xb, xc, eD, e3, e4);
+  });
+}
+// rows of test component C: pressure term (MODE 1), diagonal direction, the two off-diagonal pairs, transposed interpolation
+template <int C, int MODE, bool PERQ>
+__device__ __forceinline__ void sbw_rows(const double (&u0)[27], const double (&u1)[27], const double (&u2)[27], double (&T)[27],
+                                         const double (&ee)[3], double vol, double eta0, const double *etab, const double (&pn)[8], double ps)
+{
+  constexpr int D1 = (C + 1) % 3, D2 = (C + 2) % 3;
+  const double (&uc)[27] = C == 0 ? u0 : (C == 1 ? u1 : u2);
+  const double (&ud1)[27] = D1 == 0 ? u0 : (D1 == 1 ? u1 : u2);
+  const double (&ud2)[27] = D2 == 0 ? u0 : (D2 == 1 ? u1 : u2);
+  if (MODE == 1) {
+    double pq[27];
+    q1_to_quad<3>(pn, pq);
+    const double f = -ee[C] * ps * vol;
+#pragma unroll
+    for (int q = 0; q < 27; ++q) pq[q] *= f * qweight<3>(q);
+    for_lines<3, C>([&](int a, int b, int c) {
+      T[a] = fma(-3.0, pq[a], pq[c] - pq[b]); T[b] = 4.0 * (pq[a] - pq[c]); T[c] = fma(3.0, pq[c], pq[b] - pq[a]);
+    });
+  }
+  {
+    const double f2 = 2.0 * ee[C] * ee[C] * vol * eta0;
+    for_lines<3, C>([&](int a, int b, int c) {
+      double ga, gb, gc;
+      dline(uc[a], uc[b], uc[c], ga, gb, gc);
+      if (PERQ) { ga *= f2 * qweight<3>(a) * etab[a * SUB]; gb *= f2 * qweight<3>(b) * etab[b * SUB]; gc *= f2 * qweight<3>(c) * etab[c * SUB]; }
+      else { ga *= f2 * qweight<3>(a); gb *= f2 * qweight<3>(b); gc *= f2 * qweight<3>(c); }
+      const double ta = fma(-3.0, ga, gc - gb), tb = 4.0 * (ga - gc), tc = fma(3.0, gc, gb - ga);
+      if (MODE == 1) { T[a] += ta; T[b] += tb; T[c] += tc; }
+      else { T[a] = ta; T[b] = tb; T[c] = tc; }
+    });
+  }
+  sbw_offdiag<C, D1, PERQ>(uc, ud1, T, ee[C], ee[D1], vol * eta0, etab);
+  sbw_offdiag<C, D2, PERQ>(uc, ud2, T, ee[C], ee[D2], vol * eta0, etab);
+  interpT_all<3>(T);
+}
+
+template <int MODE, bool PERQ>
+__global__ void __launch_bounds__(32, 6) velocity_sbw_kernel(const CellParams P, const unsigned char *lists, int n_batches)
+{
+  static_assert(MODE == 0 || MODE == 1, "A block, Stokes operator");
+  constexpr int MU = SB_SLOTS;
+  constexpr int LBYTES = MODE == 0 ? SB_LIST_BYTES : SB_BLOCK_BYTES;
+  extern __shared__ __align__(16) double smem[];
+  double *buf = smem;                                                            // [2][3][MU]
+  unsigned char *sI = reinterpret_cast<unsigned char *>(buf + 2 * 3 * MU);       // [2][LBYTES]
+  double *sP = reinterpret_cast<double *>(sI + 2 * LBYTES);                      // [2][SB_PLIST] pressure values (MODE 1)
+  const int lane = threadIdx.x, G = gridDim.x;
+  int b = blockIdx.x;
+  if (b >= n_batches) return;
+  const int x = sb_x(lane), y = sb_y(lane), z = sb_z(lane);
+  int lb[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) lb[v] = x + sb_sy(v) * y + sb_sz(v) * z;
+  unsigned first_mask = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if ((!(r & 1) || x == 0) && (!(r & 2) || y == 0) && (!(r & 4) || z == 0)) first_mask |= 1u << r;
+  const double ee[3] = {P.ee[0], P.ee[1], P.ee[2]};
+
+  const auto load_list = [&](unsigned char *dst, int brick) {
+    const unsigned char *src = lists + (size_t)brick * SB_BLOCK_BYTES;
+    for (int ch = lane; ch < LBYTES / 16; ch += 32) cp_async16(smem_u32(dst + 16 * ch), src + 16 * ch);
+  };
+  // values of one brick: lane l stages the nodes l, l + 32, ... of the list (ascending DoF order), three components each
+  const auto issue_values = [&](const unsigned char *I, double *dstbuf, double *dstp) {
+    const uint32_t *le = reinterpret_cast<const uint32_t *>(I);
+    const uint16_t *ls = reinterpret_cast<const uint16_t *>(I + SB_LIST * 4);
+    const uint32_t base = smem_u32(dstbuf);
+    constexpr int SUBB = 4;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 12; k0 += SUBB) {
+      uint32_t e[SUBB], sl[SUBB];
+#pragma unroll
+      for (int k = 0; k < SUBB; ++k) { const int j = lane + 32 * (k0 + k); e[k] = le[j]; sl[k] = ls[j]; }
+#pragma unroll
+      for (int k = 0; k < SUBB; ++k) {
+        const double *src = P.src_u + (e[k] & NODE_IDX_MASK);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const bool cons = ((e[k] >> (NODE_FLAG_SHIFT + d)) & 1u) && !P.plain;
+          cp_async8_zfill(base + 8u * (sl[k] + d * MU), src + d, cons ? 0 : 8);
+        }
+      }
+    }
+    if (lane < 405 - 384) {
+      const uint32_t e = le[lane + 384], sl = ls[lane + 384];
+      const double *src = P.src_u + (e & NODE_IDX_MASK);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const bool cons = ((e >> (NODE_FLAG_SHIFT + d)) & 1u) && !P.plain;
+        cp_async8_zfill(base + 8u * (sl + d * MU), src + d, cons ? 0 : 8);
+      }
+    }
+    if (MODE == 1) {
+      const uint32_t *lp = reinterpret_cast<const uint32_t *>(I + SB_LIST_BYTES);
+      for (int j = lane; j < 75; j += 32) {
+        const uint32_t e = lp[j];
+        cp_async8_zfill(smem_u32(dstp + j), P.src_p + (e & NODE_IDX_MASK), ((e >> 31) && !P.plain) ? 0 : 8);
+      }
+    }
+  };
+
+  load_list(sI, b);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  issue_values(sI, buf, sP);
+  cp_async_commit();
+
+  for (int it = 0; b < n_batches; b += G, ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    double *B = buf + cur * 3 * MU;
+    unsigned char *I_cur = sI + cur * LBYTES, *I_nxt = sI + nxt * LBYTES;
+    const int bn = b + G;
+    cp_async_wait_all();
+    __syncwarp();                       // values of this brick are in B; the flush of the previous brick is done with the other buffer
+    if (bn < n_batches) load_list(I_nxt, bn);
+    cp_async_commit();
+    const double *etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+    const double eta0 = PERQ ? 1.0 : etab[0];
+
+    double u0[27], u1[27], u2[27];
+    sb_gather<0>(u0, B, lb); sb_gather<0>(u1, B + MU, lb); sb_gather<0>(u2, B + 2 * MU, lb);
+    double pn[8];
+    if (MODE == 1) sb_gather_p<0>(pn, sP + cur * SB_PLIST, x, y, z);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pn[i] = 0.0;
+    }
+    cp_async_wait_all();                // (this lane's chunks of the next node list)
+    __syncwarp();                       // every gather from B is done; the next list is visible
+    if (bn < n_batches) issue_values(I_nxt, buf + nxt * 3 * MU, sP + nxt * SB_PLIST);
+    cp_async_commit();
+    interp_all<3>(u0); interp_all<3>(u1); interp_all<3>(u2);
+
+    if (MODE == 1) {
+      // pressure rows -ps (div u, q): this cell's share is parked in B (free until the accumulation), summed lattice node by
+      // lattice node in a fixed order and sent straight to global memory
+      double dq[27], yv[8];
+      const double f = -P.ps * P.vol;
+      for_lines<3, 0>([&](int a, int b2, int c) { double ga, gb, gc; dline(u0[a], u0[b2], u0[c], ga, gb, gc); dq[a] = ee[0] * ga; dq[b2] = ee[0] * gb; dq[c] = ee[0] * gc; });
+      for_lines<3, 1>([&](int a, int b2, int c) { double ga, gb, gc; dline(u1[a], u1[b2], u1[c], ga, gb, gc); dq[a] = fma(ee[1], ga, dq[a]); dq[b2] = fma(ee[1], gb, dq[b2]); dq[c] = fma(ee[1], gc, dq[c]); });
+      for_lines<3, 2>([&](int a, int b2, int c) { double ga, gb, gc; dline(u2[a], u2[b2], u2[c], ga, gb, gc); dq[a] = fma(ee[2], ga, dq[a]); dq[b2] = fma(ee[2], gb, dq[b2]); dq[c] = fma(ee[2], gc, dq[c]); });
+#pragma unroll
+      for (int q = 0; q < 27; ++q) dq[q] *= f * qweight<3>(q);
+      quad_to_q1T<3>(dq, yv);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) B[m * SUB + lane] = yv[m];
+      __syncwarp();
+      const uint32_t *lp = reinterpret_cast<const uint32_t *>(I_cur + SB_LIST_BYTES);
+      for (int t = lane; t < 75; t += 32) {
+        const int X = t % 5, Y = (t / 5) % 5, Z = t / 25;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int cx = X - i, cy = Y - j, cz = Z - k;
+              if (cx >= 0 && cx < 4 && cy >= 0 && cy < 4 && cz >= 0 && cz < 2) {
+                const int ln = (cx & 1) | ((cy & 1) << 1) | (cz << 2) | ((cx >> 1) << 3) | ((cy >> 1) << 4);
+                acc += B[(i + 2 * j + 4 * k) * SUB + ln];
+              }
+            }
+        const uint32_t e = lp[t];
+        const uint32_t idx = e & NODE_IDX_MASK;
+        if (e >> 31) P.dst_p[idx] = P.plain ? 0.0 : P.src_p[idx];
+        else if (!(e & NODE_SHARED_BIT)) P.dst_p[idx] = acc;
+        else atomicAdd(P.dst_p + idx, acc);
+      }
+      __syncwarp();
+    }
+
+    {
+      double T[27];
+      sbw_rows<0, MODE, PERQ>(u0, u1, u2, T, ee, P.vol, eta0, etab, pn, P.ps);
+      sb_accumulate<0>(T, B, lb, first_mask);
+      sbw_rows<1, MODE, PERQ>(u0, u1, u2, T, ee, P.vol, eta0, etab, pn, P.ps);
+      sb_accumulate<0>(T, B + MU, lb, first_mask);
+      sbw_rows<2, MODE, PERQ>(u0, u1, u2, T, ee, P.vol, eta0, etab, pn, P.ps);
+      sb_accumulate<0>(T, B + 2 * MU, lb, first_mask);
+    }
+    __syncwarp();
+    // flush: private nodes with plain stores, shared nodes with one RED per DoF; constrained DoFs are skipped (dst = src
+    // on those rows is the small list kernel after this one)
+    {
+      const uint32_t *le = reinterpret_cast<const uint32_t *>(I_cur);
+      const uint16_t *ls = reinterpret_cast<const uint16_t *>(I_cur + SB_LIST * 4);
+      const int n_private = (int)le[405];
+#pragma unroll 1
+      for (int k = 0; k < 13; ++k) {
+        const int j = lane + 32 * k;
+        if (j < 405) {
+          const uint32_t e = le[j], sl = ls[j];
+          double *dst = P.dst_u + (e & NODE_IDX_MASK);
+          const double v0 = B[sl], v1 = B[MU + sl], v2 = B[2 * MU + sl];
+          const bool priv = j < n_private;
+          if (!((e >> NODE_FLAG_SHIFT) & 1u)) { if (priv) dst[0] = v0; else atomicAdd(dst, v0); }
+          if (!((e >> (NODE_FLAG_SHIFT + 1)) & 1u)) { if (priv) dst[1] = v1; else atomicAdd(dst + 1, v1); }
+          if (!((e >> (NODE_FLAG_SHIFT + 2)) & 1u)) { if (priv) dst[2] = v2; else atomicAdd(dst + 2, v2); }
+        }
+      }
+    }
+  }
+}
+
 // ---- pressure mass matrix: one warp per batch (one cell per lane), MASS_WARPS independent warps per block --------
 // With one viscosity per cell the cell matrix is (ps^2 vol / eta) M1 x M1 x M1 with the exact 1D Q1 mass matrix
 // M1 = [2 1; 1 2] / 6 (the 3-point Gauss rule integrates it exactly), applied as 2x2 sweeps on the 2^dim nodal
@@ -1479,8 +1723,39 @@ template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, Level
   SMF_CUDA(cudaGetLastError());
   return SMF_OK;
 }
+template <int MODE, bool PERQ> static int launch_velocity_sbw(smf_ctx *ctx, LevelDev &L, CellParams &P)
+{
+  constexpr size_t smem = sbw_smem_bytes(MODE);
+  static int resident = 0;
+  if (resident == 0) {
+    SMF_CUDA(cudaFuncSetAttribute(velocity_sbw_kernel<MODE, PERQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 148;
+    SMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+    SMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, velocity_sbw_kernel<MODE, PERQ>, 32, smem));
+    if (per_sm < 1) return ctx->fail(SMF_ERR_CUDA, "velocity_sbw_kernel does not fit on an SM");
+    resident = per_sm * sms;
+  }
+  const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
+  {
+    ProfScope prof(ctx, MODE == 1 ? B_STOKES : (fine ? B_A_FINE : B_A_COARSE));
+    int grid = std::min(L.n_batches, resident);
+    if (ctx->max_grid_blocks > 0) grid = std::min(grid, ctx->max_grid_blocks);
+    velocity_sbw_kernel<MODE, PERQ><<<grid, 32, smem, ctx->stream>>>(P, L.sb_lists, L.n_batches);
+    if (!P.plain && L.n_constrained_u) {      // unit diagonal on the constrained rows: dst = src
+      copy_entries_kernel<<<(unsigned)((L.n_constrained_u + 255) / 256), 256, 0, ctx->stream>>>(P.dst_u, P.src_u, L.constrained_u, L.n_constrained_u);
+      ctx->launches++;
+    }
+  }
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
 template <int DIM, int MODE> static int launch_velocity(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
+  if (DIM == 3 && MODE != 2 && L.structured && ctx->use_pipelined && ctx->use_warp_brick && L.sb_lists) {
+    if (L.n_eta != 1) return launch_velocity_sbw<MODE == 2 ? 0 : MODE, true>(ctx, L, P);
+    return launch_velocity_sbw<MODE == 2 ? 0 : MODE, false>(ctx, L, P);
+  }
   if (DIM == 3 && L.structured && ctx->use_pipelined && L.sb_lists) {
     if (MODE != 2 && L.n_eta != 1) return launch_velocity_sb<MODE, true>(ctx, L, P);
     return launch_velocity_sb<MODE, false>(ctx, L, P);

@@ -230,6 +230,9 @@ struct smf_ctx {
   int max_grid_blocks = 0;                            // > 0: cap on the persistent grids (tests: forces several bricks per block)
   int use_curved_tma = 0;                             // curved cells: geometry staged by cp.async.bulk + mbarrier (SMF_OPT_CURVED_TMA)
   int use_curved_fast = 1;                            // curved cells: sum-factorised one-thread-per-cell kernel (0: the general restatement kernel)
+  int use_coarse_tail = 1;                            // Schur V-cycle: levels 0..tail_level in one single-block kernel (coarse_tail.cu)
+  int tail_level = -1;                                // set by smf_setup_smoothers (-1: not applicable)
+  int use_warp_brick = 0;                             // structured levels: one-warp-per-brick velocity kernel, three components per thread (SMF_OPT_WARP_BRICK_KERNEL)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
   int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)
   // profiler: 0 off, 1 operator kernels of the finest level only, 2 every launch
@@ -299,6 +302,9 @@ int edge_extract(smf_ctx *ctx, const EdgeSet &E, double *xe, const double *x, in
 int edge_subtract_off(smf_ctx *ctx, const EdgeSet &E, double *b, const double *y, int64_t n);   // b -= (I - E) y
 int copy_pairs(smf_ctx *ctx, const CopyPairs &C, double *level_vec, double *active_vec, bool to_level);
 void free_adaptive(LevelDev &L);
+// coarse_tail.cu
+int schur_tail_top_level(smf_ctx *ctx);
+int launch_schur_tail(smf_ctx *ctx, int top);
 // comm.cu
 void free_exchange(ExchangeDev &E);
 int exchange_add(smf_ctx *ctx, ExchangeDev &E, double *vec);

@@ -204,7 +204,8 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
     TRY(vec_residual(ctx, V.t, V.b, n));                                     // t = defect - A x
     TRY(vec_set(ctx, C.b, 0.0, lsize(ctx, S, l - 1)));
     TRY(launch_restrict_add(ctx, which, l, C.b, V.t));
-    TRY(level_v_step_maybe_graph(ctx, S, l - 1));
+    if (!S.velocity && l - 1 == ctx->tail_level) TRY(launch_schur_tail(ctx, l - 1));      // levels 0..l-1 in one launch
+    else TRY(level_v_step_maybe_graph(ctx, S, l - 1));
     TRY(launch_prolongate(ctx, which, l, x, C.res, true));                   // x += P x_coarse
     for (int s = 0; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));   // post-smoothing
   }
@@ -271,6 +272,7 @@ static int vcycle_adaptive(smf_ctx *ctx, const MGSide &S, double *dst, const dou
 static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
 {
   const bool profiling_inside = ctx->prof_mode == 2 || (ctx->prof_mode == 1 && l == ctx->cfg.n_levels - 1);
+  // the coarse tail of the Schur V-cycle: levels 0..l in one launch (coarse_tail.cu); inside a graph it is one node
   if (!ctx->use_graphs || l != ctx->graph_level || profiling_inside) return level_v_step(ctx, S, l);
   void *&exec = S.velocity ? ctx->graph_A : ctx->graph_S;
   bool &stale = S.velocity ? ctx->graph_A_stale : ctx->graph_S_stale;
@@ -940,6 +942,7 @@ int smf_setup_smoothers(smf_ctx *ctx)
   ctx->graph_level = -1;
   for (int l = 0; l < nl; ++l)
     if (ctx->levels[l].n_cells <= GRAPH_MAX_CELLS) ctx->graph_level = l;
+  ctx->tail_level = std::min(schur_tail_top_level(ctx), nl - 2);            // (never the finest level: its defect is the caller's vector)
   return SMF_OK;
 }
 

@@ -71,6 +71,8 @@ class StokesMatrixFreeHandler:
         self.allow_structured_bricks = True      # implementation switches (smf_set_option); tests exercise both paths
         self.use_cuda_graphs = True
         self.device_cell_data = True             # assemble(): averaging / projection / level tables on the device (False: host numpy)
+        self.use_warp_brick_kernel = os.environ.get("SMF_WARP_BRICK", "0") == "1"    # structured levels: one warp per brick, 3 components per thread
+        self.use_coarse_tail = True              # Schur V-cycle: coarse levels in one single-block kernel
         self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
         self.p2p_exchange = True                 # >1 rank: halo exchange as one kernel over NVLink peer memory (False: NCCL send/recv)
@@ -140,6 +142,8 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CUDA_GRAPHS, int(self.use_cuda_graphs)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_ORTHO_SINGLE_PASS, int(self.gram_reorthogonalization)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_PIPELINED_KERNEL, int(self.use_pipelined_kernel)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_WARP_BRICK_KERNEL, int(self.use_warp_brick_kernel)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_COARSE_TAIL, int(self.use_coarse_tail)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_SUMFAC, int(self.curved_sum_factorization)))

@@ -54,6 +54,10 @@ const char *smf_last_error(const smf_ctx *ctx);
 #define SMF_OPT_P2P_EXCHANGE 5        /* halo exchange as one kernel over NVLink peer memory (default 1); 0 = pack + NCCL send/recv + accumulate */
 #define SMF_OPT_CURVED_SUMFAC 6        /* curved cells (geometry = 1): sum-factorised kernel (default 1); 0 = the general per-cell restatement kernel */
 #define SMF_OPT_CURVED_TMA 7           /* curved cells: geometry stream staged in shared memory by cp.async.bulk (TMA) + mbarrier (default 0) */
+#define SMF_OPT_WARP_BRICK_KERNEL 8    /* structured levels, A block / Stokes: one warp per brick with the three velocity components of a cell in one thread
+                                         (no cross-warp stress exchange, no block barriers) instead of one warp per component */
+#define SMF_OPT_COARSE_TAIL 9          /* Schur-complement V-cycle: the levels that fit one thread block's shared memory run in ONE kernel launch
+                                         (default 1; one rank, one viscosity per cell on those levels) */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
