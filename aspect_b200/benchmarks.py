@@ -82,8 +82,9 @@ def assemble_rhs(level, rho_q, gravity):
     """Velocity right-hand side; rho_q (n_cells, 3^dim) (already averaged if `Material averaging` says so)."""
     dim = level.dim
     nn = 3 ** dim
-    w = quadrature_weights(dim) * float(np.prod(level.h))
-    loc = (rho_q * w[None, :]) @ _phi2_at_quad(dim)                   # (cells, nodes)
+    jxw = getattr(level, "jxw", None)                                 # cells of different sizes (adaptive meshes) carry their own JxW
+    w = quadrature_weights(dim)[None, :] * float(np.prod(level.h)) if jxw is None else np.asarray(jxw)
+    loc = (rho_q * w) @ _phi2_at_quad(dim)                            # (cells, nodes)
     f = np.zeros(level.n_u)
     for c in range(dim):
         if gravity[c] != 0.0:

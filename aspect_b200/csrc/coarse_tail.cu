@@ -6,7 +6,7 @@
 // solve -- for vectors of a few hundred to a few thousand doubles.  This kernel runs levels 0..k of that hierarchy inside a
 // single thread block: the four level vectors of every level (x, x_old, defect, t) live in shared memory (levels 0..4 of a 3D
 // box: 5,802 pressure DoFs, 186 kB), the level operators are the same arithmetic as mass_kernel (per cell (ps^2 vol / eta)
-// M1 x M1 x M1 on the 2^dim nodal values, accumulated with shared-memory atomics), the smoother is the same three-term
+// M1 x M1 x M1 on the 2^dim nodal values, evaluated node by node from the cells around a node: no atomics, the Chebyshev update of an iteration fused into the same pass), the smoother is the same three-term
 // recurrence as cheb_first / cheb_update / cheb_tail (solver.cu), the transfers use the patch tables of smf_set_transfer with
 // their owner bits.  Block-wide barriers replace kernel boundaries (~0.2 us instead of ~3 us each).
 // Semantics: Multigrid::level_v_step + SmootherRelaxation + MGCoarseGridApplySmoother as in solver.cu: level_v_step.
@@ -26,24 +26,51 @@ struct TailLevel {
   const uint32_t *coarse_nodes;   // cell_nodes of level l-1
   double scale;                   // ps^2 * cell volume
   double theta, delta; int degree;
-  int off;                        // offset of this level's vectors in shared memory (doubles): x, xo, b, t each n_dofs
+  int off;                        // offset (bytes) of this level's block in shared memory, layout below
 };
 struct TailParams {
-  int n_levels, steps;
+  int n_levels, steps, scratch_off;
   TailLevel lv[TAIL_MAX_LEVELS];
   const double *defect;           // defect of level n_levels-1 (global memory)
   double *solution;               // solution of level n_levels-1 (global memory)
 };
 
-template <int DIM> __device__ __forceinline__ void tail_mass(const TailLevel &L, const double *x, double *t)
+// shared-memory block of one level: x, xo, b, t, dinv [n_dofs] doubles | coef [n_cells] doubles | nodes [n_cells][NP] u16 |
+// adj [n_dofs][NP] u16 (cell * NP + local node of the cells around a node) | cnt [n_dofs] i32
+template <int DIM> struct TailView {
+  static constexpr int NP = 1 << DIM;
+  double *x, *xo, *b, *t, *dinv, *coef;
+  unsigned short *nodes, *adj;
+  int *cnt;
+  __device__ TailView(unsigned char *base, const TailLevel &L)
+  {
+    x = reinterpret_cast<double *>(base + L.off); xo = x + L.n_dofs; b = xo + L.n_dofs; t = b + L.n_dofs; dinv = t + L.n_dofs;
+    coef = dinv + L.n_dofs;
+    nodes = reinterpret_cast<unsigned short *>(coef + L.n_cells);
+    adj = nodes + (size_t)L.n_cells * NP;
+    cnt = reinterpret_cast<int *>(adj + (size_t)L.n_dofs * NP);      // ((n_cells + n_dofs) * NP u16 entries: a multiple of 8 bytes)
+  }
+};
+template <int DIM> __host__ __device__ inline size_t tail_level_bytes(int n_cells, int n_dofs)
+{
+  constexpr int NP = 1 << DIM;
+  size_t b = (size_t)(5 * n_dofs + n_cells) * 8 + (size_t)(n_cells + n_dofs) * NP * 2;
+  b = (b + 3) & ~(size_t)3;
+  b += (size_t)n_dofs * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+// Level operator in two passes without atomics: pass 1, one thread per cell, y[cell][a] = (ps^2 vol / eta) (M1 x M1 x M1 p)_a
+// on the cell's nodal values (M1 = [2 1; 1 2] / 6; the arithmetic of mass_kernel); pass 2, one thread per node, the sum of
+// the entries of the cells around the node in a fixed order (adj is sorted).
+template <int DIM> __device__ __forceinline__ void tail_cells(const TailLevel &L, const TailView<DIM> &V, const double *x, double *y)
 {
   constexpr int NP = 1 << DIM;
   for (int c = threadIdx.x; c < L.n_cells; c += blockDim.x) {
     double p[NP];
-    uint32_t idx[NP];
+    const unsigned short *nd = V.nodes + c * NP;
 #pragma unroll
-    for (int a = 0; a < NP; ++a) { idx[a] = L.cell_nodes[(size_t)c * NP + a] & NODE_IDX_MASK; p[a] = x[idx[a]]; }
-    // M1 = [2 1; 1 2] / 6 along every direction
+    for (int a = 0; a < NP; ++a) p[a] = x[nd[a]];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       const int s = 1 << d;
@@ -54,29 +81,36 @@ template <int DIM> __device__ __forceinline__ void tail_mass(const TailLevel &L,
           p[a] = (2.0 * u + v) * (1.0 / 6.0); p[a + s] = (u + 2.0 * v) * (1.0 / 6.0);
         }
     }
-    const double coef = L.scale / L.eta[c];
+    const double coef = V.coef[c];
 #pragma unroll
-    for (int a = 0; a < NP; ++a) atomicAdd(t + idx[a], coef * p[a]);
+    for (int a = 0; a < NP; ++a) y[c * NP + a] = coef * p[a];
   }
 }
+template <int DIM> __device__ __forceinline__ double tail_node(const TailView<DIM> &V, const double *y, int i)
+{
+  constexpr int NP = 1 << DIM;
+  double acc = 0.0;
+  const int n = V.cnt[i];
+  for (int s = 0; s < n; ++s) acc += y[V.adj[i * NP + s]];
+  return acc;
+}
 
-// one Chebyshev sweep on level l: from_zero -> x = p(A) b from a zero start (degree - 1 operator applications), else one
-// more sweep from the current x (degree applications); the result ends in the array the returned pointer names
-template <int DIM> __device__ double *tail_cheb(const TailLevel &L, double *x, double *xo, const double *b, double *t, bool from_zero)
+// one Chebyshev sweep: from_zero -> x = p(A) b from a zero start (degree - 1 operator applications), else one more sweep
+// from the current iterate (degree applications).  The vector update of an iteration is fused into the node pass of the
+// operator.  Returns the array that holds the result.
+template <int DIM> __device__ double *tail_cheb(const TailLevel &L, const TailView<DIM> &V, double *y, double *x, double *xo, bool from_zero)
 {
   const int n = L.n_dofs;
   bool have_old;
   if (from_zero) {
     const double it = 1.0 / L.theta;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { x[i] = it * L.dinv[i] * b[i]; t[i] = 0.0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = it * V.dinv[i] * V.b[i];
     have_old = false;
   } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) t[i] = 0.0;
-    __syncthreads();
-    tail_mass<DIM>(L, x, t);
+    tail_cells<DIM>(L, V, x, y);
     __syncthreads();
     const double f2 = 1.0 / L.theta;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double xi = x[i]; xo[i] = xi + f2 * L.dinv[i] * (b[i] - t[i]); t[i] = 0.0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xo[i] = x[i] + f2 * V.dinv[i] * (V.b[i] - tail_node<DIM>(V, y, i));
     double *s = x; x = xo; xo = s;
     have_old = true;
   }
@@ -85,17 +119,16 @@ template <int DIM> __device__ double *tail_cheb(const TailLevel &L, double *x, d
   double rhok = L.delta / L.theta;
   const double sigma = L.theta / L.delta;
   for (int k = 0; k < L.degree - 1; ++k) {
-    tail_mass<DIM>(L, x, t);
-    __syncthreads();
     const double rhokp = 1.0 / (2.0 * sigma - rhok);
     const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / L.delta;
     rhok = rhokp;
+    tail_cells<DIM>(L, V, x, y);
+    __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const double xi = x[i];
-      double v = xi + f2 * L.dinv[i] * (b[i] - t[i]);
+      double v = xi + f2 * V.dinv[i] * (V.b[i] - tail_node<DIM>(V, y, i));
       v += have_old ? f1 * (xi - xo[i]) : f1 * xi;
       xo[i] = v;
-      t[i] = 0.0;
     }
     double *s = x; x = xo; xo = s;
     have_old = true;
@@ -109,32 +142,61 @@ __device__ __forceinline__ double tail_p1(int r, int j) { return r == 0 ? (j == 
 template <int DIM>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) schur_tail_kernel(const TailParams P)
 {
-  extern __shared__ double sm[];
-  constexpr int NPATCH = DIM == 3 ? 27 : 9, NC = 1 << DIM;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int NPATCH = DIM == 3 ? 27 : 9, NC = 1 << DIM, NP = NC;
   const int top = P.n_levels - 1;
   double *xs[TAIL_MAX_LEVELS];          // where the current iterate of every level lives
-  // defect of the top level
+  double *y = reinterpret_cast<double *>(smraw + P.scratch_off);      // [n_cells][NP] of the largest level: per-cell results
+  // stage the static data of every level and build the node -> cells adjacency (sorted: fixed summation order)
+  for (int l = 0; l <= top; ++l) {
+    const TailLevel &L = P.lv[l];
+    TailView<DIM> V(smraw, L);
+    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) { V.dinv[i] = L.dinv[i]; V.cnt[i] = 0; }
+    for (int c = threadIdx.x; c < L.n_cells; c += blockDim.x) V.coef[c] = L.scale / L.eta[c];
+    for (int w = threadIdx.x; w < L.n_cells * NP; w += blockDim.x) V.nodes[w] = (unsigned short)(L.cell_nodes[w] & NODE_IDX_MASK);
+  }
   {
     const TailLevel &L = P.lv[top];
-    double *b = sm + L.off + 2 * L.n_dofs;
-    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) b[i] = P.defect[i];
+    TailView<DIM> V(smraw, L);
+    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) V.b[i] = P.defect[i];
   }
   __syncthreads();
+  for (int l = 0; l <= top; ++l) {
+    const TailLevel &L = P.lv[l];
+    TailView<DIM> V(smraw, L);
+    for (int w = threadIdx.x; w < L.n_cells * NP; w += blockDim.x) {
+      const int node = V.nodes[w];
+      const int slot = atomicAdd(&V.cnt[node], 1);
+      V.adj[node * NP + slot] = (unsigned short)w;
+    }
+  }
+  __syncthreads();
+  for (int l = 0; l <= top; ++l) {
+    const TailLevel &L = P.lv[l];
+    TailView<DIM> V(smraw, L);
+    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) {
+      unsigned short *a = V.adj + i * NP;
+      const int n = V.cnt[i];
+      for (int p = 1; p < n; ++p) { const unsigned short key = a[p]; int q = p - 1; while (q >= 0 && a[q] > key) { a[q + 1] = a[q]; --q; } a[q + 1] = key; }
+    }
+  }
+  __syncthreads();
+
   for (int l = top; l >= 0; --l) {
     const TailLevel &L = P.lv[l];
-    double *x = sm + L.off, *xo = x + L.n_dofs, *b = xo + L.n_dofs, *t = b + L.n_dofs;
+    TailView<DIM> V(smraw, L);
     // pre-smoothing (on level 0: the coarse solver): SmootherRelaxation::apply = vmult + (steps - 1) x step
-    double *cur = tail_cheb<DIM>(L, x, xo, b, t, true);
-    for (int s = 1; s < P.steps; ++s) cur = tail_cheb<DIM>(L, cur, cur == x ? xo : x, b, t, false);
+    double *cur = tail_cheb<DIM>(L, V, y, V.x, V.xo, true);
+    for (int s = 1; s < P.steps; ++s) cur = tail_cheb<DIM>(L, V, y, cur, cur == V.x ? V.xo : V.x, false);
     xs[l] = cur;
     if (l == 0) break;
     // residual t = b - A x, restricted into the zeroed defect of the coarser level
-    tail_mass<DIM>(L, cur, t);          // (t was left zeroed by the smoother)
     const TailLevel &C = P.lv[l - 1];
-    double *bc = sm + C.off + 2 * C.n_dofs;
-    for (int i = threadIdx.x; i < C.n_dofs; i += blockDim.x) bc[i] = 0.0;
+    TailView<DIM> VC(smraw, C);
+    for (int i = threadIdx.x; i < C.n_dofs; i += blockDim.x) VC.b[i] = 0.0;
+    tail_cells<DIM>(L, V, cur, y);
     __syncthreads();
-    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) t[i] = b[i] - t[i];
+    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) V.t[i] = V.b[i] - tail_node<DIM>(V, y, i);
     __syncthreads();
     for (int w = threadIdx.x; w < L.n_parents * NC; w += blockDim.x) {
       const int par = w / NC, j = w % NC;
@@ -146,17 +208,15 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) schur_tail_kernel(const TailP
         int r = s, jj = j;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { wt *= tail_p1(r % 3, jj & 1); r /= 3; jj >>= 1; }
-        if (wt != 0.0) acc = fma(wt, t[pe & NODE_IDX_MASK], acc);
+        if (wt != 0.0) acc = fma(wt, V.t[pe & NODE_IDX_MASK], acc);
       }
-      if (acc != 0.0) atomicAdd(bc + (L.coarse_nodes[(size_t)par * NC + j] & NODE_IDX_MASK), acc);
+      if (acc != 0.0) atomicAdd(VC.b + VC.nodes[par * NC + j], acc);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) t[i] = 0.0;
     __syncthreads();
   }
   for (int l = 1; l <= top; ++l) {
     const TailLevel &L = P.lv[l], &C = P.lv[l - 1];
-    double *x = sm + L.off, *xo = x + L.n_dofs, *b = xo + L.n_dofs, *t = b + L.n_dofs;
+    TailView<DIM> V(smraw, L), VC(smraw, C);
     double *cur = xs[l];
     const double *xc = xs[l - 1];
     // x += P x_coarse: the parent that owns a fine node writes it
@@ -170,12 +230,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) schur_tail_kernel(const TailP
         int r = s, jj = j;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { wt *= tail_p1(r % 3, jj & 1); r /= 3; jj >>= 1; }
-        if (wt != 0.0) acc = fma(wt, xc[C.n_dofs ? (L.coarse_nodes[(size_t)par * NC + j] & NODE_IDX_MASK) : 0], acc);
+        if (wt != 0.0) acc = fma(wt, xc[VC.nodes[par * NC + j]], acc);
       }
       cur[pe & NODE_IDX_MASK] += acc;
     }
     __syncthreads();
-    for (int s = 0; s < P.steps; ++s) cur = tail_cheb<DIM>(L, cur, cur == x ? xo : x, b, t, false);
+    for (int s = 0; s < P.steps; ++s) cur = tail_cheb<DIM>(L, V, y, cur, cur == V.x ? V.xo : V.x, false);
     xs[l] = cur;
   }
   {
@@ -192,14 +252,14 @@ int schur_tail_top_level(smf_ctx *ctx)
   int dev = 0, max_smem = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int64_t doubles = 0;
+  size_t bytes = 0;
   int top = -1;
   for (int l = 0; l < ctx->cfg.n_levels && l < TAIL_MAX_LEVELS; ++l) {
     const LevelDev &L = ctx->levels[l];
-    if (L.n_eta != 1 || L.n_constrained_p || L.geo || L.edge_p.n || L.n_cells > 40000) break;
+    if (L.n_eta != 1 || L.n_constrained_p || L.geo || L.edge_p.n || L.n_cells > ctx->tail_max_cells || L.n_p > 60000 || L.n_cells * 8 > 60000) break;
     if (l > 0 && !ctx->transfers[l].patch_p) break;
-    doubles += 4 * L.n_p;
-    if (doubles * (int64_t)sizeof(double) > (int64_t)max_smem - 1024) break;
+    bytes += L.dim == 3 ? tail_level_bytes<3>((int)L.n_cells, (int)L.n_p) : tail_level_bytes<2>((int)L.n_cells, (int)L.n_p);
+    if (bytes + (size_t)L.n_cells * (1 << L.dim) * 8 > (size_t)max_smem - 1024) break;      // + the per-cell scratch of the largest level
     top = l;
   }
   return top;
@@ -210,7 +270,7 @@ int launch_schur_tail(smf_ctx *ctx, int top)
 {
   TailParams P{};
   P.n_levels = top + 1; P.steps = 4;
-  int64_t off = 0;
+  size_t off = 0;
   for (int l = 0; l <= top; ++l) {
     const LevelDev &L = ctx->levels[l];
     const Smoother &sm = ctx->smoother_S[l];
@@ -222,12 +282,13 @@ int launch_schur_tail(smf_ctx *ctx, int top)
     T.scale = L.ps * L.ps * vol;
     T.theta = sm.theta; T.delta = sm.delta; T.degree = sm.degree;
     T.off = (int)off;
-    off += 4 * L.n_p;
+    off += L.dim == 3 ? tail_level_bytes<3>((int)L.n_cells, (int)L.n_p) : tail_level_bytes<2>((int)L.n_cells, (int)L.n_p);
     if (l > 0) { T.patch = ctx->transfers[l].patch_p; T.n_parents = (int)ctx->transfers[l].n_parents; T.coarse_nodes = ctx->levels[l - 1].cell_nodes_p; }
   }
   MGVectors &V = ctx->mgv_S[top];
   P.defect = V.b; P.solution = V.x;
-  const size_t smem = (size_t)off * sizeof(double);
+  P.scratch_off = (int)off;
+  const size_t smem = off + (size_t)ctx->levels[top].n_cells * (1 << ctx->cfg.dim) * sizeof(double);
   static size_t configured2 = 0, configured3 = 0;
   size_t &configured = ctx->cfg.dim == 3 ? configured3 : configured2;
   if (smem > configured) {

@@ -276,7 +276,7 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   else if (option == SMF_OPT_MAX_GRID_BLOCKS) ctx->max_grid_blocks = value > 0 ? value : 0;
   else if (option == SMF_OPT_P2P_EXCHANGE) ctx->use_p2p = value ? 1 : 0;
   else if (option == SMF_OPT_WARP_BRICK_KERNEL) ctx->use_warp_brick = value ? 1 : 0;
-  else if (option == SMF_OPT_COARSE_TAIL) { ctx->use_coarse_tail = value ? 1 : 0; ctx->smoothers_ready = false; ctx->graph_A_stale = ctx->graph_S_stale = true; }
+  else if (option == SMF_OPT_COARSE_TAIL) { ctx->use_coarse_tail = value ? 1 : 0; if (value > 1) ctx->tail_max_cells = value; ctx->smoothers_ready = false; ctx->graph_A_stale = ctx->graph_S_stale = true; }
   else return ctx->fail(SMF_ERR_INVALID, "unknown option");
   return SMF_OK;
 }

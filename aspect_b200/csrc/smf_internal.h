@@ -231,6 +231,7 @@ struct smf_ctx {
   int use_curved_tma = 0;                             // curved cells: geometry staged by cp.async.bulk + mbarrier (SMF_OPT_CURVED_TMA)
   int use_curved_fast = 1;                            // curved cells: sum-factorised one-thread-per-cell kernel (0: the general restatement kernel)
   int use_coarse_tail = 1;                            // Schur V-cycle: levels 0..tail_level in one single-block kernel (coarse_tail.cu)
+  int tail_max_cells = 1024;                          // largest level (cells) the coarse tail takes (SMF_OPT_COARSE_TAIL value > 1 overrides)
   int tail_level = -1;                                // set by smf_setup_smoothers (-1: not applicable)
   int use_warp_brick = 0;                             // structured levels: one-warp-per-brick velocity kernel, three components per thread (SMF_OPT_WARP_BRICK_KERNEL)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
