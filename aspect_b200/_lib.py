@@ -19,6 +19,7 @@ SMF_OPT_CURVED_SUMFAC = 6
 SMF_OPT_CURVED_TMA = 7
 SMF_OPT_WARP_BRICK_KERNEL = 8
 SMF_OPT_COARSE_TAIL = 9
+SMF_OPT_NONSYMMETRIC_A_SOLVER = 10
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -70,7 +71,7 @@ class SolveResult(ctypes.Structure):
 # every symbol include/smf_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "smf_create", "smf_destroy", "smf_last_error", "smf_set_option", "smf_set_stream", "smf_set_level", "smf_set_transfer",
-    "smf_set_copy_indices", "smf_set_constraints", "smf_set_refinement_edges", "smf_set_level_copy_indices", "smf_set_cell_data", "smf_fill_cell_data", "smf_get_cell_data", "smf_set_newton_data", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
+    "smf_set_copy_indices", "smf_set_constraints", "smf_set_refinement_edges", "smf_set_level_copy_indices", "smf_set_cell_data", "smf_fill_cell_data", "smf_get_cell_data", "smf_set_newton_data", "smf_set_free_surface_faces", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
     "smf_synchronize", "smf_vmult_stokes", "smf_vmult_A", "smf_vmult_BT", "smf_vmult_mass", "smf_vmult_stokes_host", "smf_correct_stokes_rhs",
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",

@@ -77,6 +77,69 @@ __global__ void k_copy_pairs(double *level_vec, double *active_vec, const uint32
   else active_vec[ia[i]] = level_vec[il[i]];
 }
 
+// StokesOperator::local_apply_boundary_face (matrix_free_operators.cc:563-602) on Cartesian cells: one thread per face and
+// face node I (3^(dim-1) nodes, all components): dst_I -= n_c int_face (g . u) phi_I dA with the 3^(dim-1)-point Gauss rule.
+// Source values are read like in the cell loop (constrained DoFs read 0 unless plain), constrained rows receive nothing.
+template <int DIM>
+__global__ void k_free_surface_faces(const uint32_t *cells, const int32_t *face_no, const double *table, const uint32_t *cell_nodes_u,
+                                     const double *src, double *dst, int64_t n_faces, double hx, double hy, double hz, int plain)
+{
+  constexpr int NF = DIM == 3 ? 9 : 3, NN = DIM == 3 ? 27 : 9;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_faces * NF) return;
+  const int64_t f = t / NF; const int I = (int)(t % NF);
+  const int fn = face_no[f], d = fn / 2, side = fn % 2;
+  const double h[3] = {hx, hy, hz};
+  int tang[2] = {0, 0}, nt = 0;
+  double area = 1.0;
+  for (int e = 0; e < DIM; ++e) if (e != d) { tang[nt++] = e; area *= h[e]; }
+  const double s5 = 0.7745966692414834, gx[3] = {0.5 - 0.5 * s5, 0.5, 0.5 + 0.5 * s5}, gwt[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  auto shape = [](int i, double x) { return i == 0 ? (1 - x) * (1 - 2 * x) : (i == 1 ? 4 * x * (1 - x) : x * (2 * x - 1)); };
+  auto local_node = [&](int a) {       // lexicographic cell index of face node a (tangential digits, lower direction fastest)
+    int idx[3] = {0, 0, 0};
+    idx[d] = side == 0 ? 0 : 2;
+    idx[tang[0]] = a % 3;
+    if (DIM == 3) idx[tang[1]] = a / 3;
+    return idx[0] + 3 * idx[1] + 9 * idx[2];
+  };
+  const uint32_t *cn = cell_nodes_u + (size_t)cells[f] * NN;
+  // values of u at the face nodes
+  double u[NF][DIM];
+  for (int a = 0; a < NF; ++a) {
+    const uint32_t e = cn[local_node(a)];
+    for (int c = 0; c < DIM; ++c) {
+      const bool cons = (e >> (NODE_FLAG_SHIFT + c)) & 1u;
+      u[a][c] = (cons && !plain) ? 0.0 : src[(e & NODE_IDX_MASK) + c];
+    }
+  }
+  double acc = 0.0;
+  for (int q = 0; q < NF; ++q) {
+    const int q0 = q % 3, q1 = DIM == 3 ? q / 3 : 0;
+    double gu = 0.0;
+    for (int a = 0; a < NF; ++a) {
+      const double ph = shape(a % 3, gx[q0]) * (DIM == 3 ? shape(a / 3, gx[q1]) : 1.0);
+      for (int c = 0; c < DIM; ++c) gu = fma(table[((size_t)f * NF + q) * DIM + c] * ph, u[a][c], gu);
+    }
+    const double w = gwt[q0] * (DIM == 3 ? gwt[q1] : 1.0) * area;
+    acc = fma(gu * w, shape(I % 3, gx[q0]) * (DIM == 3 ? shape(I / 3, gx[q1]) : 1.0), acc);
+  }
+  const uint32_t e = cn[local_node(I)];
+  if (!((e >> (NODE_FLAG_SHIFT + d)) & 1u)) atomicAdd(dst + (e & NODE_IDX_MASK) + d, side == 0 ? acc : -acc);     // -(g . u) n, n = -+ e_d
+}
+
+int free_surface_faces_apply(smf_ctx *ctx, const LevelDev &L, double *dst_u, const double *src_u, bool plain)
+{
+  const FaceSet &F = L.fs_faces;
+  if (F.n == 0) return SMF_OK;
+  const int NF = L.dim == 3 ? 9 : 3;
+  const unsigned g = (unsigned)((F.n * NF + 127) / 128);
+  if (L.dim == 3) k_free_surface_faces<3><<<g, 128, 0, ctx->stream>>>(F.cells, F.face_no, F.table, L.cell_nodes_u, src_u, dst_u, F.n, L.h[0], L.h[1], L.h[2], plain ? 1 : 0);
+  else k_free_surface_faces<2><<<g, 128, 0, ctx->stream>>>(F.cells, F.face_no, F.table, L.cell_nodes_u, src_u, dst_u, F.n, L.h[0], L.h[1], 1.0, plain ? 1 : 0);
+  ctx->launches++;
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
 static inline unsigned blocks(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 int hanging_pre(smf_ctx *ctx, ConstraintLines &H, const double *src)
@@ -151,8 +214,9 @@ static void free_lines(ConstraintLines &H)
 { cudaFree(H.dof); cudaFree(H.start); cudaFree(H.master); cudaFree(H.weight); cudaFree(H.save); H = ConstraintLines(); }
 static void free_edge(EdgeSet &E) { cudaFree(E.idx); cudaFree(E.save); E = EdgeSet(); }
 static void free_pairs(CopyPairs &C) { cudaFree(C.active); cudaFree(C.level); C = CopyPairs(); }
+static void free_faces(FaceSet &F) { cudaFree(F.cells); cudaFree(F.face_no); cudaFree(F.table); F = FaceSet(); }
 void free_adaptive(LevelDev &L)
-{ free_lines(L.hang_u); free_lines(L.hang_p); free_edge(L.edge_u); free_edge(L.edge_p); free_pairs(L.copy_u); free_pairs(L.copy_p); }
+{ free_lines(L.hang_u); free_lines(L.hang_p); free_edge(L.edge_u); free_edge(L.edge_p); free_pairs(L.copy_u); free_pairs(L.copy_p); free_faces(L.fs_faces); }
 
 template <class T> static int to_device(smf_ctx *ctx, T **dev, const T *host, int64_t n)
 {
@@ -199,6 +263,28 @@ int smf_set_constraints(smf_ctx *ctx, int level, int family, int64_t n_lines, co
   H.n = n_lines;
   L.has_diag = false;
   ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
+int smf_set_free_surface_faces(smf_ctx *ctx, int64_t n_faces, const uint32_t *cells, const int32_t *face_numbers, const double *table)
+{
+  if (!ctx || n_faces < 0) return SMF_ERR_INVALID;
+  LevelDev &L = ctx->lev(SMF_ACTIVE);
+  if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the active level mesh first");
+  SMF_CUDA(cudaSetDevice(ctx->cfg.device));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  free_faces(L.fs_faces);
+  if (n_faces == 0) return SMF_OK;
+  if (!cells || !face_numbers || !table) return ctx->fail(SMF_ERR_INVALID, "smf_set_free_surface_faces: missing array");
+  if (L.geo) return ctx->fail(SMF_ERR_UNSUPPORTED, "free-surface stabilisation faces on curved cells (geometry = 1) are not implemented");
+  for (int64_t i = 0; i < n_faces; ++i)
+    if (cells[i] >= L.n_cells || face_numbers[i] < 0 || face_numbers[i] >= 2 * L.dim) return ctx->fail(SMF_ERR_INVALID, "smf_set_free_surface_faces: face out of range");
+  const int NF = L.dim == 3 ? 9 : 3;
+  int e;
+  if ((e = to_device(ctx, &L.fs_faces.cells, cells, n_faces))) return e;
+  if ((e = to_device(ctx, &L.fs_faces.face_no, face_numbers, n_faces))) return e;
+  if ((e = to_device(ctx, &L.fs_faces.table, table, n_faces * NF * L.dim))) return e;
+  L.fs_faces.n = n_faces;
   return SMF_OK;
 }
 

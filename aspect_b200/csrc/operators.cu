@@ -2469,6 +2469,7 @@ int launch_vmult_stokes(smf_ctx *ctx, LevelDev &L, double *dst_u, double *dst_p,
   if (int e = hanging_pre(ctx, L.hang_p, src_p)) return e;
   if (needs_general(L, 1)) { if (int e = launch_general(ctx, L, 1, dst_u, dst_p, src_u, src_p, plain)) return e; }
   else if (int e = L.dim == 3 ? launch_velocity<3, 1>(ctx, L, P) : launch_velocity<2, 1>(ctx, L, P)) return e;
+  if (int e = free_surface_faces_apply(ctx, L, dst_u, src_u, plain)) return e;      // local_apply_boundary_face (:563-602)
   if (int e = hanging_post(ctx, L.hang_u, dst_u, src_u, true)) return e;
   if (int e = hanging_post(ctx, L.hang_p, dst_p, src_p, true)) return e;
   if (int e = exchange_add(ctx, L.ex_u, dst_u)) return e;

@@ -249,7 +249,7 @@ void smf_destroy(smf_ctx *ctx)
     for (auto &v : *mg) { cudaFree(v.x); cudaFree(v.b); cudaFree(v.t); cudaFree(v.xo); cudaFree(v.e); }
   for (double *p : ctx->krylov) cudaFree(p);
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p); cudaFree(ctx->scratch);
-  cudaFree(ctx->io_buf); cudaFree(ctx->block_weights); cudaFree(ctx->pnorm_weights); cudaFree(ctx->cg_buf); cudaFree(ctx->idr_normals);
+  cudaFree(ctx->io_buf); cudaFree(ctx->block_weights); cudaFree(ctx->pnorm_weights); cudaFree(ctx->cg_buf); cudaFree(ctx->bicg_buf); cudaFree(ctx->idr_normals);
   smf_comm_destroy_internal(ctx);
   cudaFree(ctx->tmp_u); cudaFree(ctx->tmp_u2);   // tmp_p / tmp_p2 point into the same allocations
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
@@ -276,6 +276,7 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   else if (option == SMF_OPT_MAX_GRID_BLOCKS) ctx->max_grid_blocks = value > 0 ? value : 0;
   else if (option == SMF_OPT_P2P_EXCHANGE) ctx->use_p2p = value ? 1 : 0;
   else if (option == SMF_OPT_WARP_BRICK_KERNEL) ctx->use_warp_brick = value ? 1 : 0;
+  else if (option == SMF_OPT_NONSYMMETRIC_A_SOLVER) ctx->force_nonsymmetric_A = value ? 1 : 0;
   else if (option == SMF_OPT_COARSE_TAIL) { ctx->use_coarse_tail = value ? 1 : 0; if (value > 1) ctx->tail_max_cells = value; ctx->smoothers_ready = false; ctx->graph_A_stale = ctx->graph_S_stale = true; }
   else return ctx->fail(SMF_ERR_INVALID, "unknown option");
   return SMF_OK;

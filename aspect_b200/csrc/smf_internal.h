@@ -108,6 +108,8 @@ struct ConstraintLines {
 };
 // refinement-edge indices of one level and family + scratch
 struct EdgeSet { int64_t n = 0; uint32_t *idx = nullptr; double *save = nullptr; };
+// free-surface boundary faces of the active level (adaptive.cu: free_surface_faces_apply)
+struct FaceSet { int64_t n = 0; uint32_t *cells = nullptr; int32_t *face_no = nullptr; double *table = nullptr; };
 struct CopyPairs { int64_t n = 0; uint32_t *active = nullptr, *level = nullptr; };
 
 struct LevelDev {
@@ -147,6 +149,7 @@ struct LevelDev {
   ConstraintLines hang_u, hang_p;               // ACTIVE level: hanging-node lines
   EdgeSet edge_u, edge_p;                       // levels: refinement-edge indices
   CopyPairs copy_u, copy_p;                     // levels: copy_to_mg / copy_from_mg pairs
+  FaceSet fs_faces;                             // ACTIVE level: free-surface stabilisation faces
 };
 
 constexpr int TB_COARSE = 76;      // coarse velocity nodes under a fine brick: 5 x 5 x 3 lattice = 75, padded
@@ -208,6 +211,8 @@ struct smf_ctx {
   int n_A_prec = 0, n_S_prec = 0;
   int n_A_exp = 0, n_S_exp = 0;                       // inner CG iterations of the expensive phase
   double *pnorm_weights = nullptr; double pnorm_area = 0.0;   // pressure normalisation: integral of every pressure shape function over the surface / volume
+  double *bicg_buf = nullptr;                         // [7][n_u] scratch of the inner BiCGStab solve
+  int force_nonsymmetric_A = 0;                       // `Force nonsymmetric A block solver` (SMF_OPT_NONSYMMETRIC_A_SOLVER)
   double *cg_buf = nullptr;                           // [3][n_u] scratch of the inner CG solves
   double *idr_normals = nullptr; int64_t idr_normals_n = 0;   // IDR(s) shadow-vector entries (kept between solves)
   // distributed run (comm.cu): one subdomain per rank
@@ -302,6 +307,7 @@ int edge_post(smf_ctx *ctx, EdgeSet &E, double *dst, const double *src, bool add
 int edge_extract(smf_ctx *ctx, const EdgeSet &E, double *xe, const double *x, int64_t n);        // xe = E x
 int edge_subtract_off(smf_ctx *ctx, const EdgeSet &E, double *b, const double *y, int64_t n);   // b -= (I - E) y
 int copy_pairs(smf_ctx *ctx, const CopyPairs &C, double *level_vec, double *active_vec, bool to_level);
+int free_surface_faces_apply(smf_ctx *ctx, const LevelDev &L, double *dst_u, const double *src_u, bool plain);    // dst_u -= int_face (g . u)(n . v)
 void free_adaptive(LevelDev &L);
 // coarse_tail.cu
 int schur_tail_top_level(smf_ctx *ctx);

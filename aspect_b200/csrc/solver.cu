@@ -408,6 +408,78 @@ static int inner_cg(smf_ctx *ctx, bool velocity, double *x, const double *b, dou
   }
 }
 
+// deal.II SolverBicgstab(AdditionalData(exact_residual = false)) from a zero start vector, preconditioned by the A-block
+// V-cycle: InverseVelocityBlock::vmult when the A block is flagged non-symmetric (block_stokes_preconditioner.h:119-132: the
+// free-surface stabilisation, or `Force nonsymmetric A block solver`).  Restated from deal.II 9.6 (solver_bicgstab.h, iterate()):
+// the early-success check after the first half step, the residual norm updated by add_and_dot, breakdown -> restart from the
+// current iterate.  Iterations = SolverControl::last_step().
+static int inner_bicgstab(smf_ctx *ctx, double *x, const double *b, double tol, int max_its, int *its_out)
+{
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t n = A.n_u;
+  if (!ctx->bicg_buf) {
+    SMF_CUDA(cudaMalloc(&ctx->bicg_buf, sizeof(double) * 7 * n));
+    ctx->bytes += sizeof(double) * 7 * n;
+  }
+  double *r = ctx->bicg_buf, *rbar = r + n, *p = rbar + n, *y = p + n, *z = y + n, *t = z + n, *v = t + n;
+  DotWeights dw(ctx, A.ex_u.weights);
+  const double breakdown = 1e-10;                   // SolverBicgstab::AdditionalData default
+  *its_out = 0;
+  TRY(vec_set(ctx, x, 0.0, n));
+  int step = 0;
+  while (true) {                                    // solve(): iterate() again after a breakdown
+    TRY(launch_vmult_A(ctx, A, r, x));
+    TRY(vec_sadd(ctx, r, -1.0, 1.0, b, n));         // r = b - A x
+    TRY(vec_copy(ctx, rbar, r, n));
+    double r2;
+    TRY(vec_norm2(ctx, r, n, &r2));
+    double res = std::sqrt(r2);
+    *its_out = step;
+    if (res <= tol) return SMF_OK;
+    if (step >= max_its) return SMF_NO_CONVERGENCE;
+    double alpha = 1.0, rho = 1.0, omega = 1.0;
+    const int first = step + 1;
+    bool broke = false;
+    while (true) {
+      ++step;
+      double rhobar;
+      if (step == first) rhobar = res * res; else TRY(vec_dot(ctx, r, rbar, n, &rhobar));
+      if (std::fabs(rhobar) < breakdown) { broke = true; break; }
+      const double beta = rhobar * alpha / (rho * omega);
+      rho = rhobar;
+      if (step == first) TRY(vec_copy(ctx, p, r, n));
+      else { TRY(vec_sadd(ctx, p, beta, 1.0, r, n)); TRY(vec_axpy(ctx, p, -beta * omega, v, n)); }
+      TRY(vcycle(ctx, true, y, p));
+      TRY(launch_vmult_A(ctx, A, v, y));
+      double rbar_v;
+      TRY(vec_dot(ctx, rbar, v, n, &rbar_v));
+      if (std::fabs(rbar_v) < breakdown) { broke = true; break; }
+      alpha = rho / rbar_v;
+      TRY(vec_axpy(ctx, r, -alpha, v, n));
+      TRY(vec_norm2(ctx, r, n, &r2));
+      res = std::sqrt(r2);
+      *its_out = step;
+      if (res <= tol) { TRY(vec_axpy(ctx, x, alpha, y, n)); return SMF_OK; }      // early success
+      TRY(vcycle(ctx, true, z, r));
+      TRY(launch_vmult_A(ctx, A, t, z));
+      double t_r, t_t;
+      TRY(vec_dot(ctx, t, r, n, &t_r));
+      TRY(vec_norm2(ctx, t, n, &t_t));
+      if (t_t < breakdown) { broke = true; break; }
+      omega = t_r / t_t;
+      TRY(vec_axpy(ctx, x, alpha, y, n));
+      TRY(vec_axpy(ctx, x, omega, z, n));
+      TRY(vec_axpy(ctx, r, -omega, t, n));
+      TRY(vec_norm2(ctx, r, n, &r2));
+      res = std::sqrt(r2);
+      if (res <= tol) return SMF_OK;
+      if (step >= max_its) return SMF_NO_CONVERGENCE;
+    }
+    if (!broke) break;
+  }
+  return SMF_OK;
+}
+
 // BlockSchurPreconditioner::vmult (block_stokes_preconditioner.h:220-255): cheap variant = one V-cycle per block;
 // expensive variant = CG solves with the active-level mass matrix / A block, preconditioned by the V-cycles
 static int precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double *src_u, const double *src_p,
@@ -440,7 +512,10 @@ static int precondition(smf_ctx *ctx, double *dst_u, double *dst_p, const double
     double r2;
     { DotWeights dw(ctx, A.ex_u.weights); TRY(vec_norm2(ctx, ctx->tmp_u, A.n_u, &r2)); }
     int its = 0;
-    const int rc = inner_cg(ctx, true, dst_u, ctx->tmp_u, std::sqrt(r2) * expensive->linear_solver_A_block_tolerance, 10000, &its);
+    // sim.stokes_A_block_is_symmetric() (local_smoothing.cc:1071): false with the free-surface stabilisation or when forced
+    const bool nonsymmetric = ctx->force_nonsymmetric_A || A.fs_faces.n > 0;
+    const int rc = nonsymmetric ? inner_bicgstab(ctx, dst_u, ctx->tmp_u, std::sqrt(r2) * expensive->linear_solver_A_block_tolerance, 10000, &its)
+                                : inner_cg(ctx, true, dst_u, ctx->tmp_u, std::sqrt(r2) * expensive->linear_solver_A_block_tolerance, 10000, &its);
     ctx->n_A_exp += its;
     if (rc == SMF_NO_CONVERGENCE) return ctx->fail(SMF_NO_CONVERGENCE, "iterative (top left) solver did not converge in BlockSchurPreconditioner::vmult");
     TRY(rc);

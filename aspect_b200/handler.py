@@ -285,6 +285,20 @@ class StokesMatrixFreeHandler:
             self.set_cell_data(l, levels[l], pressure_scaling, is_compressible)
         self._tables = (active, levels)
 
+    def set_free_surface_faces(self, cells, face_numbers, stabilization_term_table):
+        """`apply_stabilization_free_surface_faces` + `free_surface_stabilization_term_table` of the active OperatorCellData
+        (local_smoothing.cc:528-612): boundary faces (active cell, local face number) and g = pressure perturbation * g_hat at the
+        3^(dim-1) face Gauss points, (n_faces, 3^(dim-1), dim).  Pass empty arrays to clear."""
+        c = np.ascontiguousarray(cells, dtype=np.uint32)
+        f = np.ascontiguousarray(face_numbers, dtype=np.int32)
+        t = np.ascontiguousarray(stabilization_term_table, dtype=np.float64)
+        assert len(c) == len(f) and (len(c) == 0 or t.shape == (len(c), 3 ** (self.dim - 1), self.dim))
+        self._check(self.lib.smf_set_free_surface_faces(self.ctx, ctypes.c_int64(len(c)), ptr(c), ptr(f), ptr(t)))
+
+    def force_nonsymmetric_A_block_solver(self, on=True):
+        """`Force nonsymmetric A block solver`: BiCGStab for the A block in the expensive phase."""
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_NONSYMMETRIC_A_SOLVER, int(bool(on))))
+
     def get_cell_data(self, level):
         """The viscosity table of a level as the kernels see it, (n_cells, 1 or 3^dim)."""
         L = self.hier.active if level == SMF_ACTIVE else self.hier.levels[level]

@@ -58,6 +58,8 @@ const char *smf_last_error(const smf_ctx *ctx);
                                          (no cross-warp stress exchange, no block barriers) instead of one warp per component */
 #define SMF_OPT_COARSE_TAIL 9          /* Schur-complement V-cycle: the levels that fit one thread block's shared memory run in ONE kernel launch
                                          (default 1; one rank, one viscosity per cell on those levels) */
+#define SMF_OPT_NONSYMMETRIC_A_SOLVER 10 /* `Force nonsymmetric A block solver` (parameters.cc): BiCGStab instead of CG for the A block in the expensive phase
+                                         (block_stokes_preconditioner.h:119-132); implied by smf_set_free_surface_faces */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
@@ -177,7 +179,8 @@ int smf_get_cell_data(smf_ctx *ctx, int level, double *host_out, int *n_per_cell
  * tables, [n_cells][n_q][n_sym] or [n_cells][n_q] in the cell order of smf_set_level, n_q = 3^dim, symmetric tensors in
  * deal.II's unrolled order 00, 11, (22,) 01, (02, 12).  Tables are COPIED.  They enter StokesOperator::local_apply
  * (matrix_free_operators.cc:400-446, :464-538); enable_prescribed_dilation also makes the A block deviatoric
- * (:999-1005).  Passing NULL clears them.  The free-surface face term (:563-602) returns SMF_ERR_UNSUPPORTED. */
+ * (:999-1005).  Passing NULL clears them.  The free-surface face term (:563-602) has its own entry point below
+ * (apply_stabilization_free_surface_faces in this struct must stay 0). */
 typedef struct {
   int enable_newton_derivatives;
   int symmetrize_newton_system;
@@ -192,6 +195,17 @@ typedef struct {
   const double *dilation_derivative_wrt_pressure_table;
 } smf_newton_data;
 int smf_set_newton_data(smf_ctx *ctx, const smf_newton_data *data);
+
+/* OperatorCellData::apply_stabilization_free_surface_faces + free_surface_stabilization_term_table
+ * (matrix_free_operators.h:181-196; filled by local_smoothing.cc:528-612): the boundary faces with a free-surface indicator,
+ * given as (active cell, local face number 2 d + side in deal.II's order), and for each of them the vector
+ * g = pressure perturbation * g_hat at the 3^(dim-1) face Gauss points ([n_faces][3^(dim-1)][dim], q lexicographic over the
+ * two tangential directions, lower direction fastest).  StokesOperator::local_apply_boundary_face (matrix_free_operators.cc:
+ * 563-602) then adds  -int_face (g . u)(n . v)  to the velocity rows of the ACTIVE Stokes operator, which makes the A block
+ * non-symmetric: the expensive phase solves it with BiCGStab instead of CG (block_stokes_preconditioner.h:119-132).
+ * Cartesian cells (geometry = 0).  n_faces = 0 clears. */
+int smf_set_free_surface_faces(smf_ctx *ctx, int64_t n_faces, const uint32_t *cells, const int32_t *face_numbers,
+                               const double *stabilization_term_table);
 
 /* ---- device vectors ------------------------------------------------------------------------- */
 int smf_vec_alloc(smf_ctx *ctx, int64_t n, double **dev_ptr);   /* initialize_dof_vector */

@@ -364,6 +364,60 @@ def cg(apply, prec, b, tol, max_its):
             return x, it, False
 
 
+def bicgstab(apply, prec, b, tol, max_its, breakdown=1e-10):
+    """deal.II 9.6 SolverBicgstab(AdditionalData(exact_residual=False)) from a zero start vector (InverseVelocityBlock::vmult with
+    a non-symmetric A block, block_stokes_preconditioner.h:119-132), recalled from solver_bicgstab.h: iterate() with the early
+    success check after the first half step (x += alpha y), residual norms from add_and_dot, restart after a breakdown.
+    Returns (x, iterations = SolverControl::last_step, converged)."""
+    x = np.zeros_like(b)
+    step = 0
+    while True:
+        r = b - apply(x)
+        rbar = r.copy()
+        res = np.linalg.norm(r)
+        if res <= tol:
+            return x, step, True
+        if step >= max_its:
+            return x, step, False
+        alpha = rho = omega = 1.0
+        first = step + 1
+        broke = False
+        p = v = None
+        while True:
+            step += 1
+            rhobar = res * res if step == first else r @ rbar
+            if abs(rhobar) < breakdown:
+                broke = True; break
+            beta = rhobar * alpha / (rho * omega)
+            rho = rhobar
+            p = r.copy() if step == first else beta * p + r - beta * omega * v
+            y = prec(p)
+            v = apply(y)
+            rbar_v = rbar @ v
+            if abs(rbar_v) < breakdown:
+                broke = True; break
+            alpha = rho / rbar_v
+            r = r - alpha * v
+            res = np.linalg.norm(r)
+            if res <= tol:
+                return x + alpha * y, step, True
+            z = prec(r)
+            t = apply(z)
+            t_r, t_t = t @ r, t @ t
+            if t_t < breakdown:
+                broke = True; break
+            omega = t_r / t_t
+            x = x + alpha * y + omega * z
+            r = r - omega * t
+            res = np.linalg.norm(r)
+            if res <= tol:
+                return x, step, True
+            if step >= max_its:
+                return x, step, False
+        if not broke:
+            return x, step, True
+
+
 def fgmres(op, prec, b, x0, tol, restart, max_its, history=None):
     """deal.II SolverFGMRES(AdditionalData(max_basis_size = restart)) (local_smoothing.cc:1333-1350): flexible GMRES,
     the preconditioned vectors z_j are stored and x += Z y.  Returns (x, iterations, last_residual, converged)."""
@@ -572,7 +626,10 @@ class BlockGMGStokes:
                 raise RuntimeError("iterative (bottom right) solver did not converge")
         zp = -zp
         t = r[:self.n_u] - self.be.BT(zp)
-        zu, its, ok = cg(self.be.A_active, self.mg_A.vmult, t, np.linalg.norm(t) * a_tol, 10000)
+        if getattr(self, "A_block_is_symmetric", True):
+            zu, its, ok = cg(self.be.A_active, self.mg_A.vmult, t, np.linalg.norm(t) * a_tol, 10000)
+        else:
+            zu, its, ok = bicgstab(self.be.A_active, self.mg_A.vmult, t, np.linalg.norm(t) * a_tol, 10000)
         self.n_A_cg += its
         if not ok:
             raise RuntimeError("iterative (top left) solver did not converge")

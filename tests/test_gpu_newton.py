@@ -4,7 +4,7 @@ oracle's restatement (oracle/newton.py, itself anchored on the assembled operato
 import numpy as np
 import pytest
 
-from oracle import assembled, coeff, mesh as omesh, newton, solver as osolver
+from oracle import assembled, coeff, cpu, mesh as omesh, newton, solver as osolver
 from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
 from test_newton_oracle import random_newton_data
 from util import rel, seeded
@@ -113,4 +113,58 @@ def test_compressible_solve_matches_oracle():
     oout = osolver.BlockGMGStokes(ob).solve(rhs, tol_rel=1e-7, restart=100, max_its=1000)
     assert out["converged"] and out["iterations"] == oout["iterations"]
     assert rel(sol[:hier.active.n_u], oout["x"][:hier.active.n_u]) < 1e-8
+    h.close()
+
+
+@pytest.mark.parametrize("dim,R", [(2, 3), (3, 2)])
+def test_free_surface_face_term_and_bicgstab(dim, R):
+    """StokesOperator::local_apply_boundary_face (matrix_free_operators.cc:563-602) on the top faces of the box against the
+    oracle's restatement, and the expensive phase with BiCGStab for the A block (block_stokes_preconditioner.h:119-132):
+    same FGMRES iterations and inner-iteration totals as the oracle."""
+    hier = synthetic.BoxHierarchy(dim, R)
+    ohier = omesh.Hierarchy(dim, R)
+    act, L = hier.active, ohier.active
+    rng = np.random.default_rng(7)
+    eta_q = 10.0 ** rng.uniform(-1, 1, (act.n_cells, 3 ** dim))
+    bc = "tangential"
+    cons = L.constrained_u(bc)
+    cells = np.flatnonzero(act.cells[:, dim - 1] == (1 << R) - 1)                 # cells under the top boundary
+    face_no = 2 * (dim - 1) + 1
+    tab = rng.uniform(-1.0, 1.0, (len(cells), 3 ** (dim - 1), dim)) * 0.05
+    tab[..., dim - 1] -= 0.2                                                       # g ~ rho dt theta |g| g_hat, pointing down
+    h = StokesMatrixFreeHandler(dim)
+    h.setup_dofs(hier, bc)
+    h.assemble(eta_q, "harmonic average", 1.3)
+    h.set_free_surface_faces(cells, np.full(len(cells), face_no), tab)
+    active, levels, _, _ = coeff.viscosity_tables(ohier, eta_q, "harmonic")
+    xu, xp = seeded(act.n_u, 3), seeded(act.n_p, 4)
+    s, d = h.initialize_dof_vector(), h.initialize_dof_vector()
+    s[0].from_host(xu); s[1].from_host(xp)
+    h.stokes_matrix.vmult(d, s)
+    ob = cpu.backend_from_hierarchy(ohier, active, levels, 1.3, bc)
+    xr = xu.copy(); xr[cons] = 0.0
+    yu, yp = ob.stokes(xr, xp)
+    yu[cons] = xu[cons]
+    yu = newton.free_surface_apply_add(L, cells, face_no, tab, cons, xu, yu)
+    assert rel(d[0].to_host(), yu) < 1e-12 and rel(d[1].to_host(), yp) < 1e-12
+    # without faces the term is gone again
+    h.set_free_surface_faces([], [], np.zeros((0, 3 ** (dim - 1), dim)))
+    h.stokes_matrix.vmult(d, s)
+    yu0, _ = ob.stokes(xr, xp); yu0[cons] = xu[cons]
+    assert rel(d[0].to_host(), yu0) < 1e-12
+    # expensive phase with BiCGStab on the A block (forced: the operator itself is the symmetric one)
+    h.build_preconditioner()
+    h.force_nonsymmetric_A_block_solver(True)
+    h.parameters.update({"Linear solver tolerance": 1e-7, "Number of cheap Stokes solver steps": 0,
+                         "Maximum number of expensive Stokes solver steps": 100})
+    rhs = np.concatenate([seeded(act.n_u, 8), np.zeros(act.n_p)])
+    rhs[cons] = 0.0
+    sol, out = h.solve(rhs)
+    sb = osolver.BlockGMGStokes(ob)
+    sb.A_block_is_symmetric = False
+    want = sb.solve(rhs, tol_rel=1e-7, max_its=0, n_expensive=100)
+    assert out["converged"] and want["converged"]
+    assert out["iterations_expensive"] == want["iterations_expensive"]
+    assert abs(out["n_A_expensive"] - want["n_A_cg"]) <= 2
+    assert rel(sol[:act.n_u], want["x"][:act.n_u]) < 1e-6
     h.close()

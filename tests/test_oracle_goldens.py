@@ -214,3 +214,30 @@ def test_prescribed_dilation_gmg_golden(R, mesh_index):
     eu, ep = pd.errors(act, u, p)
     gu, gp = (float(v) for v in g["errors_uL2_pL2"][mesh_index])
     assert abs(eu / gu - 1) < 2e-6 and abs(ep / gp - 1) < 2e-6, (eu, ep, gu, gp)
+
+
+def test_bicgstab_inner_solver():
+    """The BiCGStab restatement (deal.II 9.6 SolverBicgstab, exact_residual = false) used for a non-symmetric A block in the
+    expensive phase: solves the A block to the same solution as CG, and the outer FGMRES takes the same steps with either."""
+    hier = mesh.Hierarchy(2, 4)
+    act = hier.active
+    eta_q, rho_q = coeff.solcx(act.quadrature_points())
+    active, levels, _, _ = coeff.viscosity_tables(hier, eta_q, "harmonic")
+    ps = coeff.pressure_scaling_box(hier, lambda x: coeff.solcx(x)[0])
+    be = solver.AssembledBackend(hier, active, levels, ps, "tangential")
+    s = solver.BlockGMGStokes(be)
+    b = np.sin(np.arange(act.n_u)); b[be.cu[-1]] = 0.0
+    # (deal.II's breakdown threshold is the absolute value 1e-10 on r . rbar ~ |r|^2: tolerances below 1e-5 only restart)
+    x1, it1, ok1 = solver.cg(be.A_active, s.mg_A.vmult, b, 1e-4 * np.linalg.norm(b), 1000)
+    x2, it2, ok2 = solver.bicgstab(be.A_active, s.mg_A.vmult, b, 1e-4 * np.linalg.norm(b), 1000)
+    assert ok1 and ok2 and np.linalg.norm(x1 - x2) < 1e-3 * np.linalg.norm(x1) and it2 <= it1
+    # expensive phase with either inner solver on a problem of O(1) scaling (with SolCx's pressure scaling of 1e5 the residuals
+    # of the A block fall below deal.II's absolute breakdown threshold and BiCGStab only restarts)
+    rhs = np.concatenate([b, np.zeros(act.n_p)])
+    outs = []
+    for sym in (True, False):
+        s.A_block_is_symmetric = sym
+        outs.append(s.solve(rhs, tol_rel=1e-6, max_its=0, n_expensive=100))
+    assert all(o["converged"] for o in outs) and abs(outs[0]["iterations_expensive"] - outs[1]["iterations_expensive"]) <= 1
+    nu = act.n_u
+    assert np.linalg.norm(outs[0]["x"][:nu] - outs[1]["x"][:nu]) < 1e-4 * np.linalg.norm(outs[0]["x"][:nu])
