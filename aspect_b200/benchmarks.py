@@ -40,9 +40,42 @@ NSINKER_CENTERS = np.array([
 ])
 
 
+def _nsinker_chi_threads(x, n_sinkers, delta, omega):
+    """chi of nsinker_material for many points: the same formula evaluated chunk by chunk on all host threads."""
+    import concurrent.futures as cf
+    import os
+    dim = x.shape[-1]
+    flat = x.reshape(-1, dim)
+    out = np.empty(len(flat))
+    step = 1 << 16
+
+    def work(a):
+        p = flat[a:a + step]
+        chi = np.ones(len(p))
+        for s in range(n_sinkers):
+            d = p - NSINKER_CENTERS[s, :dim]
+            dist = np.sqrt(np.einsum("ij,ij->i", d, d))
+            np.subtract(dist, omega / 2.0, out=dist)
+            np.maximum(dist, 0.0, out=dist)
+            np.multiply(dist, dist, out=dist)
+            np.multiply(dist, -delta, out=dist)
+            np.exp(dist, out=dist)
+            np.subtract(1.0, dist, out=dist)
+            chi *= dist
+        out[a:a + step] = chi
+    n_thr = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with cf.ThreadPoolExecutor(max_workers=n_thr) as ex:
+        list(ex.map(work, range(0, len(flat), step)))
+    return out.reshape(x.shape[:-1])
+
+
 def nsinker_material(x, n_sinkers=8, viscosity_ratio=1e4, sinker_density=10.0, delta=200.0, omega=0.1):
     assert n_sinkers <= len(NSINKER_CENTERS)
     dim = x.shape[-1]
+    if x.size > 3_000_000:                   # (numpy releases the GIL inside these kernels)
+        chi = _nsinker_chi_threads(x, n_sinkers, delta, omega)
+        s = np.sqrt(viscosity_ratio)
+        return (s - 1.0 / s) * (1.0 - chi) + 1.0 / s, sinker_density * (1.0 - chi)
     chi = np.ones(x.shape[:-1])
     for s in range(n_sinkers):
         dist = np.sqrt(((x - NSINKER_CENTERS[s, :dim]) ** 2).sum(-1))
@@ -88,7 +121,7 @@ def assemble_rhs(level, rho_q, gravity):
     f = np.zeros(level.n_u)
     for c in range(dim):
         if gravity[c] != 0.0:
-            np.add.at(f, level.cell_dofs_u[:, c * nn:(c + 1) * nn].astype(np.int64), gravity[c] * loc)
+            f += np.bincount(level.cell_dofs_u[:, c * nn:(c + 1) * nn].ravel(), weights=(gravity[c] * loc).ravel(), minlength=level.n_u)
     return f
 
 

@@ -42,6 +42,13 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    # host-only helper of the synthetic driver (index maps of large boxes in plain loops)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-O2", "-shared", "-fPIC", "-o", os.path.join(HERE, "libbox_maps.so"), os.path.join(HERE, "cpp", "box_maps.cc")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("box_maps.cc failed to compile")
     with open(os.path.join(CSRC, "build.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -46,10 +46,41 @@ def morton_cells(level, dim):
     return out
 
 
+_box_lib = False
+
+
+def _box_maps_lib():
+    """aspect_b200/libbox_maps.so (cpp/box_maps.cc): the same numbering in plain C++ loops, used for large meshes."""
+    global _box_lib
+    if _box_lib is False:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbox_maps.so")
+        _box_lib = None
+        if os.path.exists(path) and os.environ.get("SMF_NUMPY_MAPS") != "1":
+            _box_lib = ctypes.CDLL(path)
+            _box_lib.box_first_touch.restype = ctypes.c_int64
+    return _box_lib
+
+
 def _first_touch(cells, npd_minus1, local_order, lex_order, grid):
     """Number the grid nodes in first-touch order; returns (cell_nodes_lex, node_grid).  grid: nodes per dimension."""
     dim = cells.shape[1]
     grid = np.asarray(grid, dtype=np.int64)
+    lib = _box_maps_lib() if len(cells) >= 4096 else None
+    if lib is not None:
+        import ctypes
+        c = np.ascontiguousarray(cells, dtype=np.int64)
+        lo, lx = np.ascontiguousarray(local_order, dtype=np.int64), np.ascontiguousarray(lex_order, dtype=np.int64)
+        cap = int(min(np.prod(grid), len(c) * len(lo)))
+        cell_nodes = np.empty((len(c), len(lo)), dtype=np.int64)
+        node_grid = np.empty((cap, dim), dtype=np.int64)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        n = lib.box_first_touch(ctypes.c_int(dim), ctypes.c_int64(len(c)), vp(c), ctypes.c_int(npd_minus1), vp(grid), ctypes.c_int(len(lo)),
+                                vp(lo), vp(lx), vp(cell_nodes), vp(node_grid), ctypes.c_int64(cap))
+        if n < 0:
+            raise RuntimeError("box_first_touch failed")
+        return cell_nodes, node_grid[:n].copy()
     mult = np.concatenate([[1], np.cumprod(grid[:-1])]).astype(np.int64)
 
     def keys(order):
