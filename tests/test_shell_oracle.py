@@ -105,7 +105,13 @@ def test_spherical_nsinker_golden_iterations(hiers):
     be = solver.AssembledBackend(o, active, levels, ps, "zero")
     out = solver.BlockGMGStokes(be).solve(np.concatenate([f, np.zeros(L.n_p)]), tol_rel=1e-6, restart=200, max_its=2000)
     gold = golden("spherical_nsinker_gmg_gc")["stokes_iterations_cheap_expensive"][0][0]
-    assert out["converged"] and gold == 106 and abs(out["iterations"] - gold) <= 5, out["iterations"]
+    # The golden (106) is a run of the GLOBAL-COARSENING handler on 4 MPI ranks ("# MPI: 4", "Solving Stokes system (GMG-GC)");
+    # this repository restates the local-smoothing handler on one rank.  Same mesh, DoF counts, coarse sizes and viscosity range
+    # (all reproduced exactly), but not the same run: the restatement takes 110 iterations, independent of the order of the 96
+    # trees.  The north-star +-1 is therefore NOT met against this golden and is not claimed; what is pinned here is the
+    # restatement's own count (a regression guard for the GPU path, which must repeat it +-1: tests/test_gpu_shell.py).  The
+    # two local-smoothing shell goldens the reference holds are met: hollow_sphere_gmg 34 vs 33, hollow_sphere_gmg_project_q1 35 = 35.
+    assert out["converged"] and gold == 106 and out["iterations"] == 110, out["iterations"]
 
 
 def test_hollow_sphere_golden():
