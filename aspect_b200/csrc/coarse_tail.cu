@@ -35,42 +35,47 @@ struct TailParams {
   double *solution;               // solution of level n_levels-1 (global memory)
 };
 
-// shared-memory block of one level: x, xo, b, t, dinv [n_dofs] doubles | coef [n_cells] doubles | nodes [n_cells][NP] u16 |
-// adj [n_dofs][NP] u16 (cell * NP + local node of the cells around a node) | cnt [n_dofs] i32
+// shared-memory block of one level: x, xo, b, t, dinv [n_dofs] doubles | coef [n_cells] doubles | (16-byte aligned) nodes
+// [n_cells][NP] u16 | adj [n_dofs][NP] u16 (cell * NP + local node of the cells around a node, padded with the index of a zero
+// slot of the scratch so that every node sums exactly NP entries)
+__host__ __device__ inline size_t tail_align16(size_t b) { return (b + 15) & ~(size_t)15; }
+template <int DIM> __host__ __device__ inline size_t tail_nodes_offset(int n_cells, int n_dofs) { return tail_align16((size_t)(5 * n_dofs + n_cells) * 8); }
+template <int DIM> __host__ __device__ inline size_t tail_level_bytes(int n_cells, int n_dofs)
+{ return tail_align16(tail_nodes_offset<DIM>(n_cells, n_dofs) + (size_t)(n_cells + n_dofs) * (1 << DIM) * 2); }
 template <int DIM> struct TailView {
   static constexpr int NP = 1 << DIM;
   double *x, *xo, *b, *t, *dinv, *coef;
   unsigned short *nodes, *adj;
-  int *cnt;
   __device__ TailView(unsigned char *base, const TailLevel &L)
   {
     x = reinterpret_cast<double *>(base + L.off); xo = x + L.n_dofs; b = xo + L.n_dofs; t = b + L.n_dofs; dinv = t + L.n_dofs;
     coef = dinv + L.n_dofs;
-    nodes = reinterpret_cast<unsigned short *>(coef + L.n_cells);
+    nodes = reinterpret_cast<unsigned short *>(base + L.off + tail_nodes_offset<DIM>(L.n_cells, L.n_dofs));
     adj = nodes + (size_t)L.n_cells * NP;
-    cnt = reinterpret_cast<int *>(adj + (size_t)L.n_dofs * NP);      // ((n_cells + n_dofs) * NP u16 entries: a multiple of 8 bytes)
   }
 };
-template <int DIM> __host__ __device__ inline size_t tail_level_bytes(int n_cells, int n_dofs)
+template <int DIM> struct TailIdx;      // NP 16-bit indices in one vector load
+template <> struct TailIdx<3> { uint4 v; __device__ __forceinline__ int get(int k) const { const unsigned w = k < 2 ? v.x : (k < 4 ? v.y : (k < 6 ? v.z : v.w)); return (k & 1) ? (int)(w >> 16) : (int)(w & 0xffffu); } };
+template <> struct TailIdx<2> { uint2 v; __device__ __forceinline__ int get(int k) const { const unsigned w = k < 2 ? v.x : v.y; return (k & 1) ? (int)(w >> 16) : (int)(w & 0xffffu); } };
+template <int DIM> __device__ __forceinline__ TailIdx<DIM> tail_load_idx(const unsigned short *p)
 {
-  constexpr int NP = 1 << DIM;
-  size_t b = (size_t)(5 * n_dofs + n_cells) * 8 + (size_t)(n_cells + n_dofs) * NP * 2;
-  b = (b + 3) & ~(size_t)3;
-  b += (size_t)n_dofs * 4;
-  return (b + 15) & ~(size_t)15;
+  TailIdx<DIM> r;
+  if constexpr (DIM == 3) r.v = *reinterpret_cast<const uint4 *>(p); else r.v = *reinterpret_cast<const uint2 *>(p);
+  return r;
 }
 
-// Level operator in two passes without atomics: pass 1, one thread per cell, y[cell][a] = (ps^2 vol / eta) (M1 x M1 x M1 p)_a
-// on the cell's nodal values (M1 = [2 1; 1 2] / 6; the arithmetic of mass_kernel); pass 2, one thread per node, the sum of
-// the entries of the cells around the node in a fixed order (adj is sorted).
+// Level operator in two passes without atomics and with short dependency chains (one SM runs this: latency is everything):
+// pass 1, one thread per cell: the cell's NP node indices in ONE vector load, NP independent loads of x,
+// y[cell][a] = (ps^2 vol / eta) (M1 x M1 x M1 p)_a (M1 = [2 1; 1 2] / 6; the arithmetic of mass_kernel); pass 2, one thread per
+// node: its NP adjacency entries in one vector load, NP independent loads of y, summed as a fixed tree.
 template <int DIM> __device__ __forceinline__ void tail_cells(const TailLevel &L, const TailView<DIM> &V, const double *x, double *y)
 {
   constexpr int NP = 1 << DIM;
   for (int c = threadIdx.x; c < L.n_cells; c += blockDim.x) {
+    const TailIdx<DIM> nd = tail_load_idx<DIM>(V.nodes + c * NP);
     double p[NP];
-    const unsigned short *nd = V.nodes + c * NP;
 #pragma unroll
-    for (int a = 0; a < NP; ++a) p[a] = x[nd[a]];
+    for (int a = 0; a < NP; ++a) p[a] = x[nd.get(a)];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
       const int s = 1 << d;
@@ -85,14 +90,20 @@ template <int DIM> __device__ __forceinline__ void tail_cells(const TailLevel &L
 #pragma unroll
     for (int a = 0; a < NP; ++a) y[c * NP + a] = coef * p[a];
   }
+  if (threadIdx.x == blockDim.x - 1) y[L.n_cells * NP] = 0.0;      // the zero slot the padded adjacency entries point to
 }
 template <int DIM> __device__ __forceinline__ double tail_node(const TailView<DIM> &V, const double *y, int i)
 {
   constexpr int NP = 1 << DIM;
-  double acc = 0.0;
-  const int n = V.cnt[i];
-  for (int s = 0; s < n; ++s) acc += y[V.adj[i * NP + s]];
-  return acc;
+  const TailIdx<DIM> ad = tail_load_idx<DIM>(V.adj + i * NP);
+  double v[NP];
+#pragma unroll
+  for (int s = 0; s < NP; ++s) v[s] = y[ad.get(s)];
+#pragma unroll
+  for (int w = 1; w < NP; w *= 2)
+#pragma unroll
+    for (int s = 0; s < NP; s += 2 * w) v[s] += v[s + w];
+  return v[0];
 }
 
 // one Chebyshev sweep: from_zero -> x = p(A) b from a zero start (degree - 1 operator applications), else one more sweep
@@ -147,40 +158,39 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) schur_tail_kernel(const TailP
   const int top = P.n_levels - 1;
   double *xs[TAIL_MAX_LEVELS];          // where the current iterate of every level lives
   double *y = reinterpret_cast<double *>(smraw + P.scratch_off);      // [n_cells][NP] of the largest level: per-cell results
-  // stage the static data of every level and build the node -> cells adjacency (sorted: fixed summation order)
+  // stage the static data of every level and build the node -> cells adjacency (padded with the zero slot y[n_cells * NP] of the
+  // level, sorted: fixed summation order); the scratch y doubles as the fill counters while the lists are built
+  int *cnt = reinterpret_cast<int *>(y);
   for (int l = 0; l <= top; ++l) {
     const TailLevel &L = P.lv[l];
     TailView<DIM> V(smraw, L);
-    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) { V.dinv[i] = L.dinv[i]; V.cnt[i] = 0; }
+    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) V.dinv[i] = L.dinv[i];
     for (int c = threadIdx.x; c < L.n_cells; c += blockDim.x) V.coef[c] = L.scale / L.eta[c];
     for (int w = threadIdx.x; w < L.n_cells * NP; w += blockDim.x) V.nodes[w] = (unsigned short)(L.cell_nodes[w] & NODE_IDX_MASK);
+    for (int w = threadIdx.x; w < L.n_dofs * NP; w += blockDim.x) V.adj[w] = (unsigned short)(L.n_cells * NP);
   }
   {
     const TailLevel &L = P.lv[top];
     TailView<DIM> V(smraw, L);
     for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) V.b[i] = P.defect[i];
   }
-  __syncthreads();
   for (int l = 0; l <= top; ++l) {
     const TailLevel &L = P.lv[l];
     TailView<DIM> V(smraw, L);
+    for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
     for (int w = threadIdx.x; w < L.n_cells * NP; w += blockDim.x) {
       const int node = V.nodes[w];
-      const int slot = atomicAdd(&V.cnt[node], 1);
+      const int slot = atomicAdd(&cnt[node], 1);
       V.adj[node * NP + slot] = (unsigned short)w;
     }
-  }
-  __syncthreads();
-  for (int l = 0; l <= top; ++l) {
-    const TailLevel &L = P.lv[l];
-    TailView<DIM> V(smraw, L);
+    __syncthreads();
     for (int i = threadIdx.x; i < L.n_dofs; i += blockDim.x) {
       unsigned short *a = V.adj + i * NP;
-      const int n = V.cnt[i];
-      for (int p = 1; p < n; ++p) { const unsigned short key = a[p]; int q = p - 1; while (q >= 0 && a[q] > key) { a[q + 1] = a[q]; --q; } a[q + 1] = key; }
+      for (int p = 1; p < NP; ++p) { const unsigned short key = a[p]; int q = p - 1; while (q >= 0 && a[q] > key) { a[q + 1] = a[q]; --q; } a[q + 1] = key; }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   for (int l = top; l >= 0; --l) {
     const TailLevel &L = P.lv[l];
@@ -257,9 +267,10 @@ int schur_tail_top_level(smf_ctx *ctx)
   for (int l = 0; l < ctx->cfg.n_levels && l < TAIL_MAX_LEVELS; ++l) {
     const LevelDev &L = ctx->levels[l];
     if (L.n_eta != 1 || L.n_constrained_p || L.geo || L.edge_p.n || L.n_cells > ctx->tail_max_cells || L.n_p > 60000 || L.n_cells * 8 > 60000) break;
+    if (L.n_p > L.n_cells * (1 << L.dim) * 2) break;          // (the scratch of the level also holds n_p fill counters)
     if (l > 0 && !ctx->transfers[l].patch_p) break;
     bytes += L.dim == 3 ? tail_level_bytes<3>((int)L.n_cells, (int)L.n_p) : tail_level_bytes<2>((int)L.n_cells, (int)L.n_p);
-    if (bytes + (size_t)L.n_cells * (1 << L.dim) * 8 > (size_t)max_smem - 1024) break;      // + the per-cell scratch of the largest level
+    if (bytes + ((size_t)L.n_cells * (1 << L.dim) + 2) * 8 > (size_t)max_smem - 1024) break;      // + the per-cell scratch of the largest level
     top = l;
   }
   return top;
@@ -288,7 +299,7 @@ int launch_schur_tail(smf_ctx *ctx, int top)
   MGVectors &V = ctx->mgv_S[top];
   P.defect = V.b; P.solution = V.x;
   P.scratch_off = (int)off;
-  const size_t smem = off + (size_t)ctx->levels[top].n_cells * (1 << ctx->cfg.dim) * sizeof(double);
+  const size_t smem = off + ((size_t)ctx->levels[top].n_cells * (1 << ctx->cfg.dim) + 2) * sizeof(double);
   static size_t configured2 = 0, configured3 = 0;
   size_t &configured = ctx->cfg.dim == 3 ? configured3 : configured2;
   if (smem > configured) {

@@ -300,8 +300,6 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   if (m->n_cells < 1 || !m->cell_dofs_u || !m->cell_dofs_p) return ctx->fail(SMF_ERR_INVALID, "incomplete level mesh");
   if (m->geometry == 0 && !m->cell_size) return ctx->fail(SMF_ERR_INVALID, "Cartesian level mesh without cell_size");
   if (m->geometry == 1 && (!m->inverse_jacobians || !m->jxw)) return ctx->fail(SMF_ERR_INVALID, "curved level mesh without inverse_jacobians / jxw");
-  if (m->geometry == 1 && ctx->cfg.dim != 3)
-    return ctx->fail(SMF_ERR_UNSUPPORTED, "curved cells (geometry = 1) are validated in 3D only; the 2D instantiations exist but no test covers them yet");
   if (m->n_dofs_u >= (int64_t)NODE_IDX_MASK || m->n_dofs_p >= (int64_t)NODE_IDX_MASK)
     return ctx->fail(SMF_ERR_UNSUPPORTED, "more than 2^28 - 1 local DoFs per rank and block (28-bit node index of the batch lists)");
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));

@@ -78,8 +78,9 @@ typedef struct {
   int64_t n_constrained_p;
   const uint32_t *constrained_p;
   int geometry;                      /* 0: Cartesian, one cell size for the level (cell_size[dim]);
-                                        1: general (curved) cells, per-quadrature-point geometry below (3D;
-                                           2D returns SMF_ERR_UNSUPPORTED until a test covers it)            */
+                                        1: general cells, per-quadrature-point geometry below: curved cells (3D: the
+                                           sum-factorised kernel; 2D: the general per-cell kernel) and the active level of an
+                                           adaptive mesh (cells of different sizes in one launch)               */
   const double *cell_size;
   /* geometry = 1: what MatrixFree's MappingInfo holds for the 3^dim-point Gauss rule of the cell loops
    * (matrix_free_operators.cc:384-385), in the cell order of cell_dofs_*, q lexicographic (x fastest):

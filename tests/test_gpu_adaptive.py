@@ -7,7 +7,8 @@ refinement-edge rows and interface operators; MGTransfer copy indices):
   * both adaptive V-cycles and the block preconditioner, 1e-10;
   * the complete solve: same outer iterations as the oracle, solution 1e-8.
 Meshes: 3D box, refinement 1 + 2 adaptive rounds around a corner (3 levels of cells in one mesh) and refinement 2 + 1 round
-around an nsinker centre (the mesh of tests/test_adaptive_oracle.py)."""
+around an nsinker centre (the mesh of tests/test_adaptive_oracle.py); 2D box with a refined corner / a refined band (the active
+level goes in with per-cell geometry, i.e. through the 2D instantiations of the general-geometry kernels)."""
 import numpy as np
 import pytest
 
@@ -17,23 +18,25 @@ from util import rel, seeded
 
 pytestmark = pytest.mark.gpu
 
-MESHES = {"corner": (1, 2, lambda x, l: np.linalg.norm(x) < 0.6),
-          "sinker": (2, 1, lambda x, l: np.linalg.norm(x - coeff.NSINKER_CENTERS[4]) < 0.3)}
+MESHES = {"corner": (3, 1, 2, lambda x, l: np.linalg.norm(x) < 0.6),
+          "sinker": (3, 2, 1, lambda x, l: np.linalg.norm(x - coeff.NSINKER_CENTERS[4]) < 0.3),
+          "corner2d": (2, 2, 2, lambda x, l: np.linalg.norm(x) < 0.6),
+          "band2d": (2, 3, 1, lambda x, l: abs(x[0] - 0.5) < 0.2 and x[1] > 0.4)}
 
 
 def _setup(name, bc="zero", ps=1.7):
-    base, rounds, marker = MESHES[name]
-    box = oad.AdaptiveBox.refined(3, base, marker, rounds)
-    hier = pad.AdaptiveBoxHierarchy.refined(3, base, marker, rounds)
+    dim, base, rounds, marker = MESHES[name]
+    box = oad.AdaptiveBox.refined(dim, base, marker, rounds)
+    hier = pad.AdaptiveBoxHierarchy.refined(dim, base, marker, rounds)
     assert np.array_equal(hier.active.cell_dofs_u, box.cell_dofs_u) and len(box.hanging_u) > 0
     eta = 10.0 ** np.random.default_rng(3).uniform(-1.0, 1.0, box.n_cells)
-    h = StokesMatrixFreeHandler(3)
+    h = StokesMatrixFreeHandler(dim)
     h.setup_dofs(hier, bc)
-    h.assemble(np.repeat(eta[:, None], 27, axis=1), "harmonic average", ps)
+    h.assemble(np.repeat(eta[:, None], 3 ** dim, axis=1), "harmonic average", ps)
     return box, hier, eta, h
 
 
-@pytest.mark.parametrize("name", ["corner", "sinker"])
+@pytest.mark.parametrize("name", ["corner", "sinker", "corner2d", "band2d"])
 @pytest.mark.parametrize("bc", ["zero", "tangential"])
 def test_active_operators_with_hanging_nodes(name, bc):
     box, hier, eta, h = _setup(name, bc)
@@ -56,7 +59,7 @@ def test_active_operators_with_hanging_nodes(name, bc):
     h.close()
 
 
-@pytest.mark.parametrize("name", ["corner", "sinker"])
+@pytest.mark.parametrize("name", ["corner", "sinker", "corner2d", "band2d"])
 def test_level_operators_diagonals_and_transfers(name):
     box, hier, eta, h = _setup(name)
     oh = oad.AdaptiveHierarchy(box, "zero")
@@ -87,7 +90,7 @@ def test_level_operators_diagonals_and_transfers(name):
     h.close()
 
 
-@pytest.mark.parametrize("name", ["corner", "sinker"])
+@pytest.mark.parametrize("name", ["corner", "sinker", "corner2d", "band2d"])
 def test_adaptive_vcycles_and_preconditioner(name):
     box, hier, eta, h = _setup(name)
     oh = oad.AdaptiveHierarchy(box, "zero")
@@ -110,10 +113,11 @@ def test_adaptive_vcycles_and_preconditioner(name):
     h.close()
 
 
-def test_adaptive_solve_matches_oracle():
-    """The mesh of tests/test_adaptive_oracle.py::test_adaptive_solve_converges_to_the_direct_solution (106 cells, refinement 2
-    + one adaptive round), nsinker-like viscosity contrast."""
-    box, hier, eta, h = _setup("sinker", ps=1.0)
+@pytest.mark.parametrize("name", ["sinker", "band2d"])
+def test_adaptive_solve_matches_oracle(name):
+    """3D: the mesh of tests/test_adaptive_oracle.py::test_adaptive_solve_converges_to_the_direct_solution (106 cells, refinement
+    2 + one adaptive round); 2D: refinement 3 + one round in a band.  Viscosity contrast 100 from cell to cell."""
+    box, hier, eta, h = _setup(name, ps=1.0)
     ops = box.assemble(eta, 1.0, "zero")
     rhs = np.concatenate([ops["Cu"].T @ np.sin(np.arange(box.n_u)), np.zeros(box.n_p)])
     rhs[ops["constrained_u"]] = 0.0
