@@ -242,6 +242,7 @@ int smf_set_constraints(smf_ctx *ctx, int level, int family, int64_t n_lines, co
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   ConstraintLines &H = family == 0 ? L.hang_u : L.hang_p;
   free_lines(H);
+  lattice_free(ctx);
   if (n_lines == 0) return SMF_OK;
   if (!constrained_dof || !row_start || !master_dof || !weight) return ctx->fail(SMF_ERR_INVALID, "smf_set_constraints: missing array");
   const int64_t n_dofs = family == 0 ? L.n_u : L.n_p, nnz = row_start[n_lines];
@@ -297,6 +298,7 @@ int smf_set_refinement_edges(smf_ctx *ctx, int level, int64_t n_u, const uint32_
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   free_edge(L.edge_u); free_edge(L.edge_p);
+  lattice_free(ctx);
   for (int64_t i = 0; i < n_u; ++i) if (edge_u[i] >= L.n_u) return ctx->fail(SMF_ERR_INVALID, "refinement-edge index out of range");
   for (int64_t i = 0; i < n_p; ++i) if (edge_p[i] >= L.n_p) return ctx->fail(SMF_ERR_INVALID, "refinement-edge index out of range");
   int e;
@@ -325,6 +327,7 @@ int smf_set_level_copy_indices(smf_ctx *ctx, int level, int family, int64_t n, c
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   CopyPairs &C = family == 0 ? L.copy_u : L.copy_p;
   free_pairs(C);
+  lattice_free(ctx);
   const int64_t na = family == 0 ? A.n_u : A.n_p, nl = family == 0 ? L.n_u : L.n_p;
   for (int64_t i = 0; i < n; ++i)
     if (active_idx[i] >= na || level_idx[i] >= nl) return ctx->fail(SMF_ERR_INVALID, "copy index out of range");

@@ -359,6 +359,7 @@ int smf_comm_init(smf_ctx *ctx, int rank, int world, const char *id)
   return SMF_OK;
 }
 
+int smf_lattice_schur_active(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? 1 : 0; }
 int smf_exchange_transport(const smf_ctx *ctx) { return !ctx || ctx->world == 1 ? 0 : (ctx->p2p ? 2 : 1); }
 
 void smf_comm_destroy_internal(smf_ctx *ctx)
@@ -385,6 +386,7 @@ int smf_set_exchange(smf_ctx *ctx, int level, int family, const smf_exchange *x)
   if (L.n_cells == 0) return ctx->fail(SMF_ERR_INVALID, "set the level mesh first");
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   ExchangeDev &E = family == 0 ? L.ex_u : L.ex_p;
+  lattice_free(ctx);
   free_exchange(E);
   const int ncomp = family == 0 ? L.dim : 1;
   const int64_t n_dofs = family == 0 ? L.n_u : L.n_p;

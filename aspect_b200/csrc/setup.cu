@@ -255,6 +255,7 @@ void smf_destroy(smf_ctx *ctx)
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
   for (auto &e : ctx->prof_live) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+  lattice_free(ctx);
   if (ctx->graph_A) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_A);
   if (ctx->graph_S) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_S);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -276,6 +277,7 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   else if (option == SMF_OPT_MAX_GRID_BLOCKS) ctx->max_grid_blocks = value > 0 ? value : 0;
   else if (option == SMF_OPT_P2P_EXCHANGE) ctx->use_p2p = value ? 1 : 0;
   else if (option == SMF_OPT_WARP_BRICK_KERNEL) ctx->use_warp_brick = value ? 1 : 0;
+  else if (option == SMF_OPT_LATTICE_SCHUR) { ctx->use_lattice = value ? 1 : 0; lattice_free(ctx); ctx->smoothers_ready = false; }
   else if (option == SMF_OPT_NONSYMMETRIC_A_SOLVER) ctx->force_nonsymmetric_A = value ? 1 : 0;
   else if (option == SMF_OPT_COARSE_TAIL) { ctx->use_coarse_tail = value ? 1 : 0; if (value > 1) ctx->tail_max_cells = value; ctx->smoothers_ready = false; ctx->graph_A_stale = ctx->graph_S_stale = true; }
   else return ctx->fail(SMF_ERR_INVALID, "unknown option");
@@ -304,6 +306,7 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
     return ctx->fail(SMF_ERR_UNSUPPORTED, "more than 2^28 - 1 local DoFs per rank and block (28-bit node index of the batch lists)");
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   LevelDev &L = ctx->lev(level);
+  lattice_free(ctx);
   ctx->bytes -= L.bytes;
   free_level(L);
   const int dim = ctx->cfg.dim, NN = dim == 3 ? 27 : 9, NP = dim == 3 ? 8 : 4;
@@ -450,7 +453,9 @@ int smf_set_transfer(smf_ctx *ctx, int fine_level, const int32_t *children)
   TransferDev &T = ctx->transfers[fine_level];
   cudaFree(T.patch_u); cudaFree(T.patch_p); cudaFree(T.tb_u); cudaFree(T.children);
   T = TransferDev();
+  lattice_free(ctx);
   T.n_parents = C.n_cells;
+  T.h_children.assign(children, children + (size_t)C.n_cells * NCH);
   SMF_CUDA(cudaMalloc(&T.children, sizeof(int32_t) * (size_t)C.n_cells * NCH));      // (smf_fill_cell_data: interpolate_to_mg of the DGQ0 viscosity)
   SMF_CUDA(cudaMemcpy(T.children, children, sizeof(int32_t) * (size_t)C.n_cells * NCH, cudaMemcpyHostToDevice));
   // bit 31: this parent writes the node in prolongation (first local parent that touches it);
@@ -554,6 +559,7 @@ int smf_set_copy_indices(smf_ctx *ctx, const uint32_t *au, const uint32_t *ap)
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   cudaFree(ctx->copy_u); cudaFree(ctx->copy_p);
   ctx->copy_u = ctx->copy_p = nullptr;
+  lattice_free(ctx);
   int64_t bytes = 0;
   int e;
   if (au) { std::vector<uint32_t> v(au, au + A.n_u); if ((e = upload(ctx, &ctx->copy_u, v, &bytes))) return e; }

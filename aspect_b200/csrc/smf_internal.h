@@ -164,7 +164,26 @@ struct TransferDev {              // level l-1 -> l
   uint32_t *patch_u = nullptr;    // [n_parents][5^dim] fine node (component-0 DoF) | bit31 = this parent owns the node
   uint32_t *patch_p = nullptr;    // [n_parents][3^dim]
   int32_t *children = nullptr;    // [n_parents][2^dim] fine cells of every coarse cell (device copy)
+  std::vector<int32_t> h_children;   // host copy (the lattice detection of schur_lattice.cu checks the child order against it)
   bool set = false;
+};
+
+// Lattice view of one level of the Schur-complement V-cycle (schur_lattice.cu): the pressure nodes of a Cartesian box level
+// form an nx x ny x nz lattice; inside the V-cycle the level vectors are stored in lattice order (x fastest), so the
+// pressure mass matrix is a 27-point node-centred stencil with one coefficient per cell -- no atomics, a fixed summation
+// order, and the Chebyshev update fused into the same kernel.
+struct LatLevel {
+  int nx = 0, ny = 0, nz = 0;      // pressure nodes per direction (cells: nx-1, ny-1, nz-1)
+  int64_t n = 0;                   // nx * ny * nz = n_p of the level
+  uint32_t *dof2lat = nullptr;     // [n] lattice index of every pressure DoF of the level
+  uint32_t *cell2lat = nullptr;    // [n_cells] lattice index of every cell
+  double *coef = nullptr;          // [cells] ps^2 vol / (216 eta), lattice order
+  double *dinv = nullptr;          // [n] inverse diagonal, lattice order
+  double *x = nullptr, *xo = nullptr, *b = nullptr, *t = nullptr;
+  // several ranks: interface nodes keep partial sums until the exchange; bit 0 = shared with another rank, bit 1 = owned by a lower rank
+  unsigned char *mask = nullptr;
+  uint32_t *if_nodes = nullptr; int64_t n_if = 0;    // lattice indices of the distinct interface nodes
+  ExchangeDev ex;                                    // twin of LevelDev::ex_p with lattice indices (owns send_idx / if_idx only)
 };
 
 struct Smoother {                 // PreconditionChebyshev state of one level
@@ -238,6 +257,15 @@ struct smf_ctx {
   int use_coarse_tail = 1;                            // Schur V-cycle: levels 0..tail_level in one single-block kernel (coarse_tail.cu)
   int tail_max_cells = 1024;                          // largest level (cells) the coarse tail takes (SMF_OPT_COARSE_TAIL value > 1 overrides)
   int tail_level = -1;                                // set by smf_setup_smoothers (-1: not applicable)
+  // lattice path of the Schur V-cycle (schur_lattice.cu)
+  std::vector<smf::LatLevel> lat;                     // per level; empty = not built
+  int lat_state = 0;                                  // 0 unknown, 1 usable, -1 the hierarchy is not a box lattice
+  int use_lattice = 1;                                // SMF_OPT_LATTICE_SCHUR
+  uint32_t *lat_act = nullptr;                        // [n_p active] lattice index on the finest level of every active pressure DoF
+  void *graph_L = nullptr; bool graph_L_stale = true; // cudaGraphExec_t of the whole lattice V-cycle
+  int64_t graph_L_launches = 0, graph_L_exchanges = 0;
+  int lat_tail = -1;                                  // levels 0..lat_tail of the lattice cycle run in one thread block
+  double *lat_res = nullptr;                          // buffer the captured cycle leaves its result in
   int use_warp_brick = 0;                             // structured levels: one-warp-per-brick velocity kernel, three components per thread (SMF_OPT_WARP_BRICK_KERNEL)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
   int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)
@@ -312,6 +340,10 @@ void free_adaptive(LevelDev &L);
 // coarse_tail.cu
 int schur_tail_top_level(smf_ctx *ctx);
 int launch_schur_tail(smf_ctx *ctx, int top);
+// schur_lattice.cu
+int lattice_prepare(smf_ctx *ctx);                                   // detection (once per mesh) + coefficients / diagonals (every smoother set-up)
+int lattice_vcycle(smf_ctx *ctx, double *dst, const double *src);    // prec_Schur on the lattice
+void lattice_free(smf_ctx *ctx);
 // comm.cu
 void free_exchange(ExchangeDev &E);
 int exchange_add(smf_ctx *ctx, ExchangeDev &E, double *vec);

@@ -316,6 +316,7 @@ static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
   if (!ctx->smoothers_ready) return ctx->fail(SMF_ERR_INVALID, "call smf_setup_smoothers before applying a V-cycle");
   MGSide S{velocity, velocity ? &ctx->smoother_A : &ctx->smoother_S, velocity ? &ctx->mgv_A : &ctx->mgv_S, velocity ? 1 : 4};
   if (ctx->adaptive) return vcycle_adaptive(ctx, S, dst, src);
+  if (!velocity && ctx->lat_state == 1 && ctx->use_lattice) return lattice_vcycle(ctx, dst, src);      // box levels: schur_lattice.cu
   const int L = ctx->cfg.n_levels - 1;
   const int64_t n = lsize(ctx, S, L);
   const uint32_t *map = velocity ? ctx->copy_u : ctx->copy_p;
@@ -1018,6 +1019,7 @@ int smf_setup_smoothers(smf_ctx *ctx)
   for (int l = 0; l < nl; ++l)
     if (ctx->levels[l].n_cells <= GRAPH_MAX_CELLS) ctx->graph_level = l;
   ctx->tail_level = std::min(schur_tail_top_level(ctx), nl - 2);            // (never the finest level: its defect is the caller's vector)
+  TRY(lattice_prepare(ctx));
   return SMF_OK;
 }
 

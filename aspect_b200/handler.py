@@ -73,6 +73,7 @@ class StokesMatrixFreeHandler:
         self.device_cell_data = True             # assemble(): averaging / projection / level tables on the device (False: host numpy)
         self.use_warp_brick_kernel = os.environ.get("SMF_WARP_BRICK", "0") == "1"    # structured levels: one warp per brick, 3 components per thread
         self.use_coarse_tail = True              # Schur V-cycle: coarse levels in one single-block kernel
+        self.use_lattice_schur = os.environ.get("SMF_LATTICE", "1") == "1"    # Schur V-cycle on box levels in lattice order (node-centred fused kernels)
         self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
         self.p2p_exchange = True                 # >1 rank: halo exchange as one kernel over NVLink peer memory (False: NCCL send/recv)
@@ -144,6 +145,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_PIPELINED_KERNEL, int(self.use_pipelined_kernel)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_WARP_BRICK_KERNEL, int(self.use_warp_brick_kernel)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_COARSE_TAIL, int(self.use_coarse_tail)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_LATTICE_SCHUR, int(self.use_lattice_schur)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_SUMFAC, int(self.curved_sum_factorization)))
@@ -577,6 +579,10 @@ class StokesMatrixFreeHandler:
         out = ctypes.c_double()
         self._check(self.lib.smf_measure_fp64_peak(self.ctx, ctypes.byref(out)))
         return float(out.value)
+
+    def lattice_schur_active(self):
+        """True when prec_Schur runs on the lattice path (box levels; decided by setup_smoothers)."""
+        return bool(self.lib.smf_lattice_schur_active(self.ctx))
 
     def exchange_count(self):
         return int(self.lib.smf_exchange_count(self.ctx))

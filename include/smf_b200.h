@@ -60,6 +60,8 @@ const char *smf_last_error(const smf_ctx *ctx);
                                          (default 1; one rank, one viscosity per cell on those levels) */
 #define SMF_OPT_NONSYMMETRIC_A_SOLVER 10 /* `Force nonsymmetric A block solver` (parameters.cc): BiCGStab instead of CG for the A block in the expensive phase
                                          (block_stokes_preconditioner.h:119-132); implied by smf_set_free_surface_faces */
+#define SMF_OPT_LATTICE_SCHUR 11        /* Schur-complement V-cycle on box levels: level vectors in lattice order inside the cycle, node-centred 27-point mass
+                                         stencil with the Chebyshev update fused, one CUDA graph per cycle (default 1; 3D, Cartesian, one viscosity per cell) */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
@@ -325,6 +327,7 @@ int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out);
 int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this context so far */
 int64_t smf_device_bytes(const smf_ctx *ctx);        /* get_*_memory_consumption() analogue      */
 int64_t smf_exchange_count(const smf_ctx *ctx);      /* halo exchanges performed by this context so far */
+int smf_lattice_schur_active(const smf_ctx *ctx);    /* 1: prec_Schur runs on the lattice path (SMF_OPT_LATTICE_SCHUR; decided by smf_setup_smoothers) */
 int smf_exchange_transport(const smf_ctx *ctx);      /* 0 = single rank, 1 = NCCL send/recv, 2 = fused peer-memory kernel (CUDA IPC over NVLink) */
 /* measured FP64 pipe peak of this device (dependent-chain-free DFMA micro-kernel, best of 5 launches, CUDA events): the
  * denominator of the FP64 fractions bench.py prints next to the HBM fractions */
