@@ -360,6 +360,7 @@ int smf_comm_init(smf_ctx *ctx, int rank, int world, const char *id)
 }
 
 int smf_lattice_schur_active(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? 1 : 0; }
+int smf_lattice_replicated_levels(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? ctx->lat_repl + 1 : 0; }
 int smf_exchange_transport(const smf_ctx *ctx) { return !ctx || ctx->world == 1 ? 0 : (ctx->p2p ? 2 : 1); }
 
 void smf_comm_destroy_internal(smf_ctx *ctx)
@@ -508,6 +509,7 @@ int smf_set_exchange(smf_ctx *ctx, int level, int family, const smf_exchange *x)
   if (x->global_dof_ids) {
     std::vector<int64_t> gid(x->global_dof_ids, x->global_dof_ids + n_dofs);
     if ((e = up(&E.gid, gid))) return e;
+    if (family == 1) E.h_gid = gid;
     double acc[2] = {0.0, 0.0};
     for (int64_t i = 0; i < n_dofs; ++i) { acc[0] += weights[i] * (double)(gid[i] % 11); acc[1] += weights[i]; }
     if (ctx->world > 1) {          // collective: every rank calls smf_set_exchange for the same (level, family)

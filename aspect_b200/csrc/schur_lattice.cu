@@ -34,6 +34,11 @@ namespace smf {
 #define TRY(x) do { int e__ = (x); if (e__) return e__; } while (0)
 
 struct LatDims { int nx, ny, nz; };
+// coarse side of a transfer: extent of the region under the fine lattice, pitches and origin of the array it lives in
+// (the rank's own coarse lattice: pitch = extent, origin 0; a replicated global lattice: the rank's box inside it)
+struct LatBox { int nx, ny, nz, px, py, ox, oy, oz; };
+__host__ __device__ inline int64_t lb_index(const LatBox &b, int x, int y, int z)
+{ return ((int64_t)(z + b.oz) * b.py + (y + b.oy)) * b.px + (x + b.ox); }
 
 // ---- kernels ---------------------------------------------------------------------------------------------------
 __global__ void k_lat_coef(double *coef, const double *eta_t, const uint32_t *cell2lat, int64_t n_cells, double scale)
@@ -50,6 +55,28 @@ __global__ void k_lat_gather(double *vec, const double *lat, const uint32_t *to_
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) vec[i] = lat[to_lat[i]];
+}
+
+// replicated levels: this rank's coefficients into the global table (the other ranks' cells stay zero until the all-reduce)
+__global__ void k_lat_coef_global(double *gcoef, const double *coef, LatDims cells, LatBox g)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)cells.nx * cells.ny * cells.nz) return;
+  const int X = (int)(i % cells.nx), Y = (int)((i / cells.nx) % cells.ny), Z = (int)(i / ((int64_t)cells.nx * cells.ny));
+  gcoef[lb_index(g, X, Y, Z)] = coef[i];
+}
+// inverse diagonal of the lattice mass matrix in closed form: 1 / (8 x sum of the coefficients of the cells around the node)
+__global__ void k_lat_dinv(double *dinv, const double *coef, LatDims d)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)d.nx * d.ny * d.nz) return;
+  const int X = (int)(i % d.nx), Y = (int)((i / d.nx) % d.ny), Z = (int)(i / ((int64_t)d.nx * d.ny));
+  const int cxn = d.nx - 1, cyn = d.ny - 1;
+  double ks = 0.0;
+  for (int cz = max(Z - 1, 0); cz <= min(Z, d.nz - 2); ++cz)
+    for (int cy = max(Y - 1, 0); cy <= min(Y, cyn - 1); ++cy)
+      for (int cx = max(X - 1, 0); cx <= min(X, cxn - 1); ++cx) ks += coef[((int64_t)cz * cyn + cy) * cxn + cx];
+  dinv[i] = 1.0 / (8.0 * ks);
 }
 
 // MODE 0: t = M x;  1: xo <- x + f1 (x - xo | x) + f2 dinv (b - M x);  2: t = b - M x.
@@ -170,7 +197,7 @@ __global__ void k_lat_finish(const uint32_t *nodes, int64_t n, const double *x, 
 }
 // coarse defect = P^T (fine residual): coarse node (X, Y, Z) gathers the 27 fine nodes around (2X, 2Y, 2Z);
 // fine nodes owned by a lower rank (mask bit 1) are counted there
-__global__ void k_lat_restrict(double *coarse, const double *fine, const unsigned char *fine_mask, LatDims c, LatDims f)
+__global__ void k_lat_restrict(double *coarse, const double *fine, const unsigned char *fine_mask, LatBox c, LatDims f)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)c.nx * c.ny * c.nz) return;
@@ -194,16 +221,16 @@ __global__ void k_lat_restrict(double *coarse, const double *fine, const unsigne
       acc = fma(wyz, r, acc);
     }
   }
-  coarse[i] = acc;
+  coarse[lb_index(c, X, Y, Z)] = acc;
 }
 // fine += P coarse
-__global__ void k_lat_prolong_add(double *fine, const double *coarse, LatDims c, LatDims f)
+__global__ void k_lat_prolong_add(double *fine, const double *coarse, LatBox c, LatDims f)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)f.nx * f.ny * f.nz) return;
   const int X = (int)(i % f.nx), Y = (int)((i / f.nx) % f.ny), Z = (int)(i / ((int64_t)f.nx * f.ny));
   const int x0 = X >> 1, x1 = (X + 1) >> 1, y0 = Y >> 1, y1 = (Y + 1) >> 1, z0 = Z >> 1, z1 = (Z + 1) >> 1;
-  const auto at = [&](int a, int b, int cc) { return coarse[((int64_t)cc * c.ny + b) * c.nx + a]; };
+  const auto at = [&](int a, int b, int cc) { return coarse[lb_index(c, a, b, cc)]; };
   const auto linex = [&](int b, int cc) { return x0 == x1 ? at(x0, b, cc) : 0.5 * (at(x0, b, cc) + at(x1, b, cc)); };
   const auto faceyz = [&](int cc) { return y0 == y1 ? linex(y0, cc) : 0.5 * (linex(y0, cc) + linex(y1, cc)); };
   const double v = z0 == z1 ? faceyz(z0) : 0.5 * (faceyz(z0) + faceyz(z1));
@@ -476,41 +503,64 @@ void lattice_free(smf_ctx *ctx)
     cudaFree(L.ex.send_idx); cudaFree(L.ex.if_idx);
   }
   ctx->lat.clear();
+  for (auto &L : ctx->glat) { cudaFree(L.coef); cudaFree(L.dinv); cudaFree(L.x); cudaFree(L.xo); cudaFree(L.b); cudaFree(L.t); }
+  ctx->glat.clear();
+  ctx->lat_repl = -1;
   cudaFree(ctx->lat_act); ctx->lat_act = nullptr;
-  if (ctx->graph_L) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_L); ctx->graph_L = nullptr; }
+  for (void *g : ctx->graph_L_seg) cudaGraphExecDestroy((cudaGraphExec_t)g);
+  ctx->graph_L_seg.clear();
   ctx->graph_L_stale = true;
   ctx->lat_state = 0;
+}
+
+// local part of the detection: is every level of this rank a box lattice, consistent from level to level?
+static bool lattice_detect_local(smf_ctx *ctx, std::vector<LatHost> &H)
+{
+  const int nl = ctx->cfg.n_levels;
+  if (ctx->cfg.dim != 3 || ctx->adaptive) return false;
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  if (A.hang_p.n || A.n_p != ctx->levels[nl - 1].n_p) return false;
+  for (int l = 0; l < nl; ++l) {
+    const LevelDev &L = ctx->levels[l];
+    if (L.geo || L.n_constrained_p || L.edge_p.n || L.copy_p.n || L.h_nodes_p.size() != (size_t)L.n_cells * 8) return false;
+    if (ctx->world > 1 && !L.ex_p.set) return false;
+    if (!detect_lattice(L.h_nodes_p, L.n_cells, L.n_p, H[l])) return false;
+    if (l > 0) {
+      // the children of cell (cx, cy, cz) are the cells (2 cx + i, 2 cy + j, 2 cz + k) in deal.II's child order i + 2 j + 4 k
+      const std::vector<int32_t> &ch = ctx->transfers[l].h_children;
+      const LatHost &C = H[l - 1], &F = H[l];
+      if (ch.size() != (size_t)ctx->levels[l - 1].n_cells * 8) return false;
+      if (F.nx != 2 * C.nx - 1 || F.ny != 2 * C.ny - 1 || F.nz != 2 * C.nz - 1) return false;
+      for (int64_t p = 0; p < ctx->levels[l - 1].n_cells; ++p)
+        for (int k = 0; k < 8; ++k) {
+          const int32_t fc = ch[p * 8 + k];
+          if (fc < 0 || fc >= L.n_cells) return false;
+          if (F.cell_xyz[(size_t)fc * 3] != 2 * C.cell_xyz[p * 3] + (k & 1) || F.cell_xyz[(size_t)fc * 3 + 1] != 2 * C.cell_xyz[p * 3 + 1] + ((k >> 1) & 1) ||
+              F.cell_xyz[(size_t)fc * 3 + 2] != 2 * C.cell_xyz[p * 3 + 2] + (k >> 2))
+            return false;
+        }
+    }
+  }
+  return true;
 }
 
 static int lattice_detect(smf_ctx *ctx)
 {
   const int nl = ctx->cfg.n_levels;
   ctx->lat_state = -1;
-  if (ctx->cfg.dim != 3 || ctx->adaptive) return SMF_OK;
-  LevelDev &A = ctx->lev(SMF_ACTIVE);
-  if (A.hang_p.n || A.n_p != ctx->levels[nl - 1].n_p) return SMF_OK;
   std::vector<LatHost> H(nl);
-  for (int l = 0; l < nl; ++l) {
-    const LevelDev &L = ctx->levels[l];
-    if (L.geo || L.n_constrained_p || L.edge_p.n || L.copy_p.n || L.h_nodes_p.size() != (size_t)L.n_cells * 8) return SMF_OK;
-    if (ctx->world > 1 && !L.ex_p.set) return SMF_OK;
-    if (!detect_lattice(L.h_nodes_p, L.n_cells, L.n_p, H[l])) return SMF_OK;
-    if (l > 0) {
-      // the children of cell (cx, cy, cz) are the cells (2 cx + i, 2 cy + j, 2 cz + k) in deal.II's child order i + 2 j + 4 k
-      const std::vector<int32_t> &ch = ctx->transfers[l].h_children;
-      const LatHost &C = H[l - 1], &F = H[l];
-      if (ch.size() != (size_t)ctx->levels[l - 1].n_cells * 8) return SMF_OK;
-      if (F.nx != 2 * C.nx - 1 || F.ny != 2 * C.ny - 1 || F.nz != 2 * C.nz - 1) return SMF_OK;
-      for (int64_t p = 0; p < ctx->levels[l - 1].n_cells; ++p)
-        for (int k = 0; k < 8; ++k) {
-          const int32_t fc = ch[p * 8 + k];
-          if (fc < 0 || fc >= L.n_cells) return SMF_OK;
-          if (F.cell_xyz[(size_t)fc * 3] != 2 * C.cell_xyz[p * 3] + (k & 1) || F.cell_xyz[(size_t)fc * 3 + 1] != 2 * C.cell_xyz[p * 3 + 1] + ((k >> 1) & 1) ||
-              F.cell_xyz[(size_t)fc * 3 + 2] != 2 * C.cell_xyz[p * 3 + 2] + (k >> 2))
-            return SMF_OK;
-        }
-    }
+  bool ok = lattice_detect_local(ctx, H);
+  if (ctx->world > 1) {      // the path changes the sequence of halo exchanges: all ranks or none
+    double v = ok ? 1.0 : 0.0, *d = nullptr;
+    SMF_CUDA(cudaMalloc(&d, sizeof(double)));
+    SMF_CUDA(cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(allreduce_sum(ctx, d, 1));
+    SMF_CUDA(cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    ok = v == (double)ctx->world;
   }
+  if (!ok) return SMF_OK;
   ctx->lat.assign(nl, LatLevel());
   for (int l = 0; l < nl; ++l) {
     LevelDev &L = ctx->levels[l];
@@ -548,7 +598,69 @@ static int lattice_detect(smf_ctx *ctx)
       TRY(up(ctx, &T.ex.if_idx, ifx));
     }
   }
+  if (ctx->world > 1) {
+    // Where does this rank's box sit in the global lattice of every level?  The partition-independent DoF numbers of
+    // smf_set_exchange tell, if they are lexicographic in that lattice (checked, not assumed): gid = g0 + X + gnx (Y + gny Z).
+    // The decision to replicate coarse levels is collective: one all-reduce carries every rank's answer.
+    std::vector<double> mine((size_t)4 * nl * ctx->world, 0.0);
+    for (int l = 0; l < nl; ++l) {
+      LatLevel &T = ctx->lat[l];
+      const std::vector<int64_t> &gid = ctx->levels[l].ex_p.h_gid;
+      bool ok = gid.size() == (size_t)T.n && T.nx >= 2 && T.ny >= 2 && T.nz >= 2;
+      int64_t g0 = 0, sy = 0, sz = 0;
+      if (ok) {
+        std::vector<int64_t> lg((size_t)T.n);
+        for (int64_t v = 0; v < T.n; ++v) lg[H[l].dof2lat[v]] = gid[v];
+        g0 = lg[0]; sy = lg[T.nx] - g0; sz = lg[(size_t)T.nx * T.ny] - g0;
+        ok = sy >= T.nx && sz >= sy * T.ny && sz % sy == 0;
+        for (int64_t z = 0; ok && z < T.nz; ++z)
+          for (int64_t y = 0; ok && y < T.ny; ++y)
+            for (int64_t x = 0; x < T.nx; ++x)
+              if (lg[(z * T.ny + y) * T.nx + x] != g0 + x + sy * y + sz * z) { ok = false; break; }
+      }
+      if (ok) {
+        T.gnx = (int)sy; T.gny = (int)(sz / sy);
+        T.oz = (int)(g0 / sz); T.oy = (int)((g0 % sz) / sy); T.ox = (int)(g0 % sy);
+        ok = T.ox + T.nx <= T.gnx && T.oy + T.ny <= T.gny;
+      }
+      double *m = mine.data() + ((size_t)ctx->rank * nl + l) * 4;
+      m[0] = ok ? 1.0 : 0.0; m[1] = T.gnx; m[2] = T.gny; m[3] = T.oz + T.nz;
+    }
+    double *d = nullptr;
+    SMF_CUDA(cudaMalloc(&d, sizeof(double) * mine.size()));
+    SMF_CUDA(cudaMemcpyAsync(d, mine.data(), sizeof(double) * mine.size(), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(allreduce_sum(ctx, d, (int)mine.size()));
+    SMF_CUDA(cudaMemcpyAsync(mine.data(), d, sizeof(double) * mine.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    const char *env = getenv("SMF_LAT_REPLICATE");
+    const int64_t max_nodes = env ? atoll(env) : 2300000;      // largest global level every rank computes redundantly
+    for (int l = 0; l < nl - 1; ++l) {
+      bool ok = true;
+      int gnz = 0;
+      for (int r = 0; r < ctx->world; ++r) {
+        const double *m = mine.data() + ((size_t)r * nl + l) * 4;
+        ok = ok && m[0] == 1.0 && (int)m[1] == ctx->lat[l].gnx && (int)m[2] == ctx->lat[l].gny;
+        gnz = std::max(gnz, (int)m[3]);
+      }
+      ctx->lat[l].gnz = gnz;
+      if (!ok || (int64_t)ctx->lat[l].gnx * ctx->lat[l].gny * gnz > max_nodes) break;
+      ctx->lat_repl = l;
+    }
+    ctx->glat.assign(ctx->lat_repl + 1, LatLevel());
+    for (int l = 0; l <= ctx->lat_repl; ++l) {
+      LatLevel &G = ctx->glat[l];
+      const LatLevel &T = ctx->lat[l];
+      G.nx = T.gnx; G.ny = T.gny; G.nz = T.gnz; G.n = (int64_t)G.nx * G.ny * G.nz;
+      const int64_t nc = (int64_t)(G.nx - 1) * (G.ny - 1) * (G.nz - 1);
+      SMF_CUDA(cudaMalloc(&G.coef, sizeof(double) * nc)); SMF_CUDA(cudaMalloc(&G.dinv, sizeof(double) * G.n));
+      SMF_CUDA(cudaMalloc(&G.x, sizeof(double) * G.n)); SMF_CUDA(cudaMalloc(&G.xo, sizeof(double) * G.n));
+      SMF_CUDA(cudaMalloc(&G.b, sizeof(double) * G.n)); SMF_CUDA(cudaMalloc(&G.t, sizeof(double) * G.n));
+      ctx->bytes += sizeof(double) * (nc + 5 * G.n);
+    }
+  }
   {
+    LevelDev &A = ctx->lev(SMF_ACTIVE);
     // active pressure DoF -> lattice index on the finest level (copy_to_mg / copy_from_mg composed with the permutation)
     std::vector<uint32_t> act((size_t)A.n_p);
     std::vector<uint32_t> map;
@@ -579,17 +691,29 @@ int lattice_prepare(smf_ctx *ctx)
     k_lat_scatter<<<(unsigned)((T.n + 255) / 256), 256, 0, ctx->stream>>>(T.dinv, L.dinv_M, T.dof2lat, T.n);
     ctx->launches += 2;
   }
+  for (int l = 0; l <= ctx->lat_repl; ++l) {
+    LatLevel &G = ctx->glat[l];
+    const LatLevel &T = ctx->lat[l];
+    const int64_t nc = (int64_t)(G.nx - 1) * (G.ny - 1) * (G.nz - 1), lc = (int64_t)(T.nx - 1) * (T.ny - 1) * (T.nz - 1);
+    SMF_CUDA(cudaMemsetAsync(G.coef, 0, sizeof(double) * nc, ctx->stream));
+    k_lat_coef_global<<<(unsigned)((lc + 255) / 256), 256, 0, ctx->stream>>>(G.coef, T.coef, LatDims{T.nx - 1, T.ny - 1, T.nz - 1},
+                                                                        LatBox{T.nx - 1, T.ny - 1, T.nz - 1, G.nx - 1, G.ny - 1, T.ox, T.oy, T.oz});
+    TRY(allreduce_sum(ctx, G.coef, (int)nc));       // every cell belongs to one rank: the sum is a gather, bitwise equal everywhere
+    k_lat_dinv<<<(unsigned)((G.n + 255) / 256), 256, 0, ctx->stream>>>(G.dinv, G.coef, LatDims{G.nx, G.ny, G.nz});
+    ctx->launches += 2;
+  }
   SMF_CUDA(cudaGetLastError());
   ctx->graph_L_stale = true;
-  // coarse tail: the levels whose vectors fit one block's shared memory (one rank only: no exchanges inside a block)
+  // coarse tail: the levels whose vectors fit one block's shared memory (no exchanges inside a block: one rank, or replicated levels)
   ctx->lat_tail = -1;
-  if (ctx->use_coarse_tail && ctx->world == 1) {
+  if (ctx->use_coarse_tail) {
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     size_t doubles = 0;
     for (int l = 0; l < ctx->cfg.n_levels - 1 && l < LT_MAX_LEVELS; ++l) {
-      const LatLevel &T = ctx->lat[l];
+      if (ctx->world > 1 && l > ctx->lat_repl) break;
+      const LatLevel &T = ctx->world > 1 ? ctx->glat[l] : ctx->lat[l];
       if (T.n > ctx->tail_max_cells * 2) break;
       doubles += (size_t)4 * T.n + (size_t)(T.nx - 1) * (T.ny - 1) * (T.nz - 1);
       if (doubles * 8 + 1024 > (size_t)max_smem) break;
@@ -599,18 +723,21 @@ int lattice_prepare(smf_ctx *ctx)
   return SMF_OK;
 }
 
+// the lattice the cycle works on at level l: the rank's own box, or the replicated global lattice
+static LatLevel &lat_level(smf_ctx *ctx, int l) { return l <= ctx->lat_repl ? ctx->glat[l] : ctx->lat[l]; }
+
 static int lat_launch_tail(smf_ctx *ctx, int top)
 {
   LatTail P{};
   P.n_levels = top + 1; P.steps = 4;
   int off = 0;
   for (int l = 0; l <= top; ++l) {
-    const LatLevel &T = ctx->lat[l];
+    const LatLevel &T = lat_level(ctx, l);
     const Smoother &sm = ctx->smoother_S[l];
     P.lv[l] = LatTailLevel{T.nx, T.ny, T.nz, off, sm.theta, sm.delta, sm.degree, T.coef};
     off += lt_doubles(P.lv[l]);
   }
-  P.b_in = ctx->lat[top].b; P.x_out = ctx->lat[top].x;
+  P.b_in = lat_level(ctx, top).b; P.x_out = lat_level(ctx, top).x;
   const size_t bytes = (size_t)off * sizeof(double);
   static size_t configured = 0;
   if (bytes > configured) { SMF_CUDA(cudaFuncSetAttribute(k_lat_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); configured = bytes; }
@@ -635,7 +762,7 @@ static int lat_zpt(const LatLevel &T)
 template <int MODE>
 static int lat_apply(smf_ctx *ctx, int l, const double *x, double *xo, const double *b, double *t, double f1, double f2, bool use_xo)
 {
-  LatLevel &T = ctx->lat[l];
+  LatLevel &T = lat_level(ctx, l);
   LatStep P{};
   P.d = LatDims{T.nx, T.ny, T.nz};
   P.x = x; P.coef = T.coef; P.dinv = T.dinv; P.b = b; P.xo = xo; P.t = t; P.mask = T.mask;
@@ -668,7 +795,7 @@ static int lat_cheb_tail(smf_ctx *ctx, int l, double *&x, double *&xo, const dou
     const double rhokp = 1.0 / (2.0 * sigma - rhok);
     const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / sm.delta;
     rhok = rhokp;
-    TRY(lat_apply<1>(ctx, l, x, xo, b, ctx->lat[l].t, f1, f2, have_old));
+    TRY(lat_apply<1>(ctx, l, x, xo, b, lat_level(ctx, l).t, f1, f2, have_old));
     std::swap(x, xo);
     have_old = true;
   }
@@ -677,38 +804,61 @@ static int lat_cheb_tail(smf_ctx *ctx, int l, double *&x, double *&xo, const dou
 static int lat_cheb_vmult(smf_ctx *ctx, int l, double *&x, double *&xo, const double *b)
 {
   VecBucket vb(ctx, B_SMOOTH_VEC);
-  TRY(cheb_first(ctx, x, ctx->lat[l].dinv, b, 1.0 / ctx->smoother_S[l].theta, ctx->lat[l].n));
+  TRY(cheb_first(ctx, x, lat_level(ctx, l).dinv, b, 1.0 / ctx->smoother_S[l].theta, lat_level(ctx, l).n));
   return lat_cheb_tail(ctx, l, x, xo, b, false);
 }
 static int lat_cheb_step(smf_ctx *ctx, int l, double *&x, double *&xo, const double *b)
 {
-  TRY(lat_apply<1>(ctx, l, x, xo, b, ctx->lat[l].t, 0.0, 1.0 / ctx->smoother_S[l].theta, false));
+  TRY(lat_apply<1>(ctx, l, x, xo, b, lat_level(ctx, l).t, 0.0, 1.0 / ctx->smoother_S[l].theta, false));
   std::swap(x, xo);
   return lat_cheb_tail(ctx, l, x, xo, b, true);
 }
 // Multigrid::level_v_step (solver.cu: level_v_step) with 4 smoothing steps on either side; the result ends in res
+// The cycle is captured into CUDA graphs; the one NCCL all-reduce of a cycle on several ranks (defect of the finest replicated
+// level) stays outside: the capture is cut there into two segments and the replay runs segment, all-reduce, segment.
+static int lat_cut_capture(smf_ctx *ctx, std::vector<cudaGraph_t> *segs)
+{
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+  if (ce != cudaSuccess) return ctx->fail(SMF_ERR_CUDA, std::string("cudaStreamEndCapture (lattice V-cycle): ") + cudaGetErrorString(ce));
+  segs->push_back(g);
+  return SMF_OK;
+}
+static std::vector<cudaGraph_t> *g_lat_segs = nullptr;       // segments of the capture in progress
+
 static int lat_level_step(smf_ctx *ctx, int l, double *&res)
 {
-  LatLevel &T = ctx->lat[l];
+  LatLevel &T = lat_level(ctx, l);
   if (l == ctx->lat_tail) { res = T.x; return lat_launch_tail(ctx, l); }
   const int steps = 4;
   double *x = T.x, *xo = T.xo;
   TRY(lat_cheb_vmult(ctx, l, x, xo, T.b));
   for (int s = 1; s < steps; ++s) TRY(lat_cheb_step(ctx, l, x, xo, T.b));
   if (l > 0) {
-    LatLevel &C = ctx->lat[l - 1];
+    LatLevel &C = lat_level(ctx, l - 1);
+    const bool into_global = l - 1 <= ctx->lat_repl && l > ctx->lat_repl;      // distributed level -> replicated level
+    const LatLevel &CL = ctx->lat[l - 1];                                       // (the rank's own coarse box: extent of the region under T)
+    const LatBox cbox = into_global ? LatBox{CL.nx, CL.ny, CL.nz, C.nx, C.ny, CL.ox, CL.oy, CL.oz} : LatBox{C.nx, C.ny, C.nz, C.nx, C.ny, 0, 0, 0};
     TRY(lat_apply<2>(ctx, l, x, nullptr, T.b, T.t, 0.0, 0.0, false));      // t = defect - M x
     {
       ProfScope prof(ctx, B_TRANSFER);
-      k_lat_restrict<<<(unsigned)((C.n + 127) / 128), 128, 0, ctx->stream>>>(C.b, T.t, T.mask, LatDims{C.nx, C.ny, C.nz}, LatDims{T.nx, T.ny, T.nz});
+      if (into_global) SMF_CUDA(cudaMemsetAsync(C.b, 0, sizeof(double) * C.n, ctx->stream));
+      const int64_t nc = (int64_t)cbox.nx * cbox.ny * cbox.nz;
+      k_lat_restrict<<<(unsigned)((nc + 127) / 128), 128, 0, ctx->stream>>>(C.b, T.t, T.mask, cbox, LatDims{T.nx, T.ny, T.nz});
       ctx->launches++;
     }
-    if (C.mask && ctx->world > 1) TRY(exchange_add(ctx, C.ex, C.b));
+    if (into_global) {
+      // sum of the ranks' partial defects (interface nodes) = gather of the rest: every rank now holds the global coarse defect
+      if (ctx->lat_capturing) {
+        TRY(lat_cut_capture(ctx, g_lat_segs));
+        SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+      } else TRY(allreduce_sum(ctx, C.b, (int)C.n));
+    } else if (C.mask && ctx->world > 1) TRY(exchange_add(ctx, C.ex, C.b));
     double *cres = nullptr;
     TRY(lat_level_step(ctx, l - 1, cres));
     {
       ProfScope prof(ctx, B_TRANSFER);
-      k_lat_prolong_add<<<(unsigned)((T.n + 255) / 256), 256, 0, ctx->stream>>>(x, cres, LatDims{C.nx, C.ny, C.nz}, LatDims{T.nx, T.ny, T.nz});
+      k_lat_prolong_add<<<(unsigned)((T.n + 255) / 256), 256, 0, ctx->stream>>>(x, cres, cbox, LatDims{T.nx, T.ny, T.nz});
       ctx->launches++;
     }
     for (int s = 0; s < steps; ++s) TRY(lat_cheb_step(ctx, l, x, xo, T.b));
@@ -732,32 +882,48 @@ int lattice_vcycle(smf_ctx *ctx, double *dst, const double *src)
   if (!graph) TRY(lat_level_step(ctx, top, res));
   else {
     if (ctx->graph_L_stale) {
-      cudaGraph_t g = nullptr;
+      std::vector<cudaGraph_t> segs;
+      g_lat_segs = &segs;
+      ctx->lat_capturing = true;
       SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
       const int64_t l0 = ctx->launches, x0 = ctx->exchanges;
-      const int rc = lat_level_step(ctx, top, res);
-      const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-      if (ce != cudaSuccess) return ctx->fail(SMF_ERR_CUDA, std::string("cudaStreamEndCapture (lattice V-cycle): ") + cudaGetErrorString(ce));
+      int rc = lat_level_step(ctx, top, res);
+      const int rc2 = lat_cut_capture(ctx, &segs);
+      ctx->lat_capturing = false;
+      g_lat_segs = nullptr;
+      if (!rc) rc = rc2;
+      if (rc) { for (cudaGraph_t g : segs) if (g) cudaGraphDestroy(g); return rc; }
       ctx->graph_L_launches = ctx->launches - l0; ctx->launches = l0;
       ctx->graph_L_exchanges = ctx->exchanges - x0; ctx->exchanges = x0;
-      bool updated = false;
-      if (ctx->graph_L) {
-        cudaGraphExecUpdateResultInfo info;
-        updated = cudaGraphExecUpdate((cudaGraphExec_t)ctx->graph_L, g, &info) == cudaSuccess;
-        if (!updated) { cudaGetLastError(); cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_L); ctx->graph_L = nullptr; }
+      if (ctx->graph_L_seg.size() != segs.size()) {
+        for (void *g : ctx->graph_L_seg) cudaGraphExecDestroy((cudaGraphExec_t)g);
+        ctx->graph_L_seg.assign(segs.size(), nullptr);
       }
-      if (!updated) {
-        cudaGraphExec_t ge = nullptr;
-        const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
-        if (ie != cudaSuccess) { cudaGraphDestroy(g); return ctx->fail(SMF_ERR_CUDA, std::string("cudaGraphInstantiate (lattice V-cycle): ") + cudaGetErrorString(ie)); }
-        ctx->graph_L = ge;
+      for (size_t k = 0; k < segs.size(); ++k) {
+        bool updated = false;
+        if (ctx->graph_L_seg[k]) {
+          cudaGraphExecUpdateResultInfo info;
+          updated = cudaGraphExecUpdate((cudaGraphExec_t)ctx->graph_L_seg[k], segs[k], &info) == cudaSuccess;
+          if (!updated) { cudaGetLastError(); cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_L_seg[k]); ctx->graph_L_seg[k] = nullptr; }
+        }
+        if (!updated) {
+          cudaGraphExec_t ge = nullptr;
+          const cudaError_t ie = cudaGraphInstantiate(&ge, segs[k], 0);
+          if (ie != cudaSuccess) { for (cudaGraph_t g : segs) cudaGraphDestroy(g); return ctx->fail(SMF_ERR_CUDA, std::string("cudaGraphInstantiate (lattice V-cycle): ") + cudaGetErrorString(ie)); }
+          ctx->graph_L_seg[k] = ge;
+        }
+        cudaGraphDestroy(segs[k]);
       }
-      cudaGraphDestroy(g);
       ctx->graph_L_stale = false;
       ctx->lat_res = res;
     }
-    SMF_CUDA(cudaGraphLaunch((cudaGraphExec_t)ctx->graph_L, ctx->stream));
+    for (size_t k = 0; k < ctx->graph_L_seg.size(); ++k) {
+      SMF_CUDA(cudaGraphLaunch((cudaGraphExec_t)ctx->graph_L_seg[k], ctx->stream));
+      if (k + 1 < ctx->graph_L_seg.size()) {      // the cut: all-reduce of the defect of the finest replicated level
+        LatLevel &C = ctx->glat[ctx->lat_repl];
+        TRY(allreduce_sum(ctx, C.b, (int)C.n));
+      }
+    }
     ctx->launches += ctx->graph_L_launches;
     ctx->exchanges += ctx->graph_L_exchanges;
     res = ctx->lat_res;

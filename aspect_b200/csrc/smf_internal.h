@@ -79,6 +79,7 @@ struct ExchangeDev {
   uint32_t *if_idx = nullptr; int *if_ptr = nullptr, *if_src = nullptr;   // rank-ordered accumulation tables
   double *weights = nullptr;                  // [n_dofs] 1 / (ranks sharing the DoF); nullptr on one rank
   int64_t *gid = nullptr; double gid_mean = 0.0;     // global DoF numbers (Chebyshev start vector)
+  std::vector<int64_t> h_gid;                        // host copy (pressure family only: schur_lattice.cu locates the rank's box in the global lattice)
   // fused peer-memory transport (comm.cu): neighbour table, {epoch, counters}, this rank's inbox (2 parity buffers)
   void *p2p_tab = nullptr, *p2p_state = nullptr; double *p2p_inbox = nullptr;
 };
@@ -175,6 +176,8 @@ struct TransferDev {              // level l-1 -> l
 struct LatLevel {
   int nx = 0, ny = 0, nz = 0;      // pressure nodes per direction (cells: nx-1, ny-1, nz-1)
   int64_t n = 0;                   // nx * ny * nz = n_p of the level
+  int ox = 0, oy = 0, oz = 0;      // several ranks: position of this rank's box in the global lattice of the level
+  int gnx = 0, gny = 0, gnz = 0;   // ... and the size of that lattice (0: unknown)
   uint32_t *dof2lat = nullptr;     // [n] lattice index of every pressure DoF of the level
   uint32_t *cell2lat = nullptr;    // [n_cells] lattice index of every cell
   double *coef = nullptr;          // [cells] ps^2 vol / (216 eta), lattice order
@@ -262,7 +265,11 @@ struct smf_ctx {
   int lat_state = 0;                                  // 0 unknown, 1 usable, -1 the hierarchy is not a box lattice
   int use_lattice = 1;                                // SMF_OPT_LATTICE_SCHUR
   uint32_t *lat_act = nullptr;                        // [n_p active] lattice index on the finest level of every active pressure DoF
-  void *graph_L = nullptr; bool graph_L_stale = true; // cudaGraphExec_t of the whole lattice V-cycle
+  std::vector<smf::LatLevel> glat;                    // several ranks: levels 0..lat_repl as GLOBAL lattices, computed redundantly by every rank
+  int lat_repl = -1;                                  // (no halo exchange on those levels; one all-reduce of the restricted defect per cycle)
+  std::vector<void *> graph_L_seg;                    // cudaGraphExec_t of the segments of the lattice V-cycle (split at the all-reduce)
+  bool lat_capturing = false;
+  void *graph_L = nullptr; bool graph_L_stale = true; // (unused: kept for layout) 
   int64_t graph_L_launches = 0, graph_L_exchanges = 0;
   int lat_tail = -1;                                  // levels 0..lat_tail of the lattice cycle run in one thread block
   double *lat_res = nullptr;                          // buffer the captured cycle leaves its result in

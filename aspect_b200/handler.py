@@ -584,6 +584,10 @@ class StokesMatrixFreeHandler:
         """True when prec_Schur runs on the lattice path (box levels; decided by setup_smoothers)."""
         return bool(self.lib.smf_lattice_schur_active(self.ctx))
 
+    def lattice_replicated_levels(self):
+        """Several ranks: number of coarse Schur levels every rank computes redundantly on the global lattice."""
+        return int(self.lib.smf_lattice_replicated_levels(self.ctx))
+
     def exchange_count(self):
         return int(self.lib.smf_exchange_count(self.ctx))
 

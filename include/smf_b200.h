@@ -328,6 +328,7 @@ int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this
 int64_t smf_device_bytes(const smf_ctx *ctx);        /* get_*_memory_consumption() analogue      */
 int64_t smf_exchange_count(const smf_ctx *ctx);      /* halo exchanges performed by this context so far */
 int smf_lattice_schur_active(const smf_ctx *ctx);    /* 1: prec_Schur runs on the lattice path (SMF_OPT_LATTICE_SCHUR; decided by smf_setup_smoothers) */
+int smf_lattice_replicated_levels(const smf_ctx *ctx);   /* several ranks: coarse levels of the lattice path that every rank computes on the GLOBAL lattice (no halo exchange) */
 int smf_exchange_transport(const smf_ctx *ctx);      /* 0 = single rank, 1 = NCCL send/recv, 2 = fused peer-memory kernel (CUDA IPC over NVLink) */
 /* measured FP64 pipe peak of this device (dependent-chain-free DFMA micro-kernel, best of 5 launches, CUDA events): the
  * denominator of the FP64 fractions bench.py prints next to the HBM fractions */
