@@ -300,8 +300,8 @@ int launch_schur_tail(smf_ctx *ctx, int top)
   P.defect = V.b; P.solution = V.x;
   P.scratch_off = (int)off;
   const size_t smem = off + ((size_t)ctx->levels[top].n_cells * (1 << ctx->cfg.dim) + 2) * sizeof(double);
-  static size_t configured2 = 0, configured3 = 0;
-  size_t &configured = ctx->cfg.dim == 3 ? configured3 : configured2;
+  static size_t configured2[MAX_DEVICES] = {0}, configured3[MAX_DEVICES] = {0};
+  size_t &configured = (ctx->cfg.dim == 3 ? configured3 : configured2)[ctx->cfg.device % MAX_DEVICES];
   if (smem > configured) {
     if (ctx->cfg.dim == 3) SMF_CUDA(cudaFuncSetAttribute(schur_tail_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else SMF_CUDA(cudaFuncSetAttribute(schur_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -262,6 +262,25 @@ int allreduce_sum(smf_ctx *ctx, double *dev, int count)
   return SMF_OK;
 }
 
+// global minimum / maximum of a pair of host values (Utilities::MPI::min / max, matrix_free_operators.cc:258-259): every
+// rank puts its pair into its own slot of a zeroed table, the table is summed over the ranks, then reduced on the host
+int allreduce_minmax(smf_ctx *ctx, double *mn, double *mx)
+{
+  if (ctx->world == 1) return SMF_OK;
+  std::vector<double> tab((size_t)2 * ctx->world, 0.0);
+  tab[2 * ctx->rank] = *mn; tab[2 * ctx->rank + 1] = *mx;
+  double *d = nullptr;
+  SMF_CUDA(cudaMalloc(&d, sizeof(double) * tab.size()));
+  SMF_CUDA(cudaMemcpyAsync(d, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+  const int e = allreduce_sum(ctx, d, (int)tab.size());
+  if (e) { cudaFree(d); return e; }
+  SMF_CUDA(cudaMemcpyAsync(tab.data(), d, sizeof(double) * tab.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  for (int r = 0; r < ctx->world; ++r) { *mn = std::min(*mn, tab[2 * r]); *mx = std::max(*mx, tab[2 * r + 1]); }
+  return SMF_OK;
+}
+
 int start_vector_mod11(smf_ctx *ctx, const ExchangeDev &E, double *x, int64_t n)
 {
   k_mod11_gid<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, E.gid, E.gid_mean, n);

@@ -1680,7 +1680,8 @@ static CellParams make_params(const LevelDev &L)
 template <int DIM, int MODE, bool PERQ, bool STRUCT> static int launch_velocity_t(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
   const size_t smem = vel_smem_bytes<DIM>(L.max_nodes_u, L.max_nodes_p, MODE);
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {0};      // (function attributes are per device; a process may hold one context per device)
+  size_t &configured = configured_dev[ctx->cfg.device % MAX_DEVICES];
   if (smem > configured) {
     SMF_CUDA(cudaFuncSetAttribute(velocity_kernel<DIM, MODE, PERQ, STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -1699,7 +1700,8 @@ __global__ void copy_entries_kernel(double *dst, const double *src, const uint32
 template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
   constexpr size_t smem = sbk_smem_bytes(MODE);
-  static int resident = 0;
+  static int resident_dev[MAX_DEVICES] = {0};
+  int &resident = resident_dev[ctx->cfg.device % MAX_DEVICES];
   if (resident == 0) {
     SMF_CUDA(cudaFuncSetAttribute(velocity_sb_kernel<MODE, PERQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, sms = 148;
@@ -1726,7 +1728,8 @@ template <int MODE, bool PERQ> static int launch_velocity_sb(smf_ctx *ctx, Level
 template <int MODE, bool PERQ> static int launch_velocity_sbw(smf_ctx *ctx, LevelDev &L, CellParams &P)
 {
   constexpr size_t smem = sbw_smem_bytes(MODE);
-  static int resident = 0;
+  static int resident_dev[MAX_DEVICES] = {0};
+  int &resident = resident_dev[ctx->cfg.device % MAX_DEVICES];
   if (resident == 0) {
     SMF_CUDA(cudaFuncSetAttribute(velocity_sbw_kernel<MODE, PERQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, sms = 148;
@@ -2347,7 +2350,8 @@ static int launch_general(smf_ctx *ctx, LevelDev &L, int mode, double *dst_u, do
       P.cell_nodes_u_t = L.cell_nodes_u_t; P.cell_nodes_p_t = L.cell_nodes_p_t;
       if (ctx->use_curved_tma) {
         const size_t smem_tma = smem + sizeof(double) * CV_STAGES * 10 * CV_THREADS;
-        static bool configured = false;
+        static bool configured_dev[MAX_DEVICES] = {false};
+        bool &configured = configured_dev[ctx->cfg.device % MAX_DEVICES];
         if (!configured) {
           SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
           SMF_CUDA(cudaFuncSetAttribute(curved_cell_kernel_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));

@@ -739,7 +739,8 @@ static int lat_launch_tail(smf_ctx *ctx, int top)
   }
   P.b_in = lat_level(ctx, top).b; P.x_out = lat_level(ctx, top).x;
   const size_t bytes = (size_t)off * sizeof(double);
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {0};
+  size_t &configured = configured_dev[ctx->cfg.device % MAX_DEVICES];
   if (bytes > configured) { SMF_CUDA(cudaFuncSetAttribute(k_lat_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); configured = bytes; }
   ProfScope prof(ctx, B_MASS);
   k_lat_tail<<<1, LT_THREADS, bytes, ctx->stream>>>(P);

@@ -782,6 +782,8 @@ int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, d
     SMF_CUDA(cudaStreamSynchronize(ctx->stream));
     double mn = 1e300, mx = -1e300;
     for (unsigned b = 0; b < pb; ++b) { mn = std::min(mn, h_ext[b]); mx = std::max(mx, h_ext[pb + b]); }
+    // the clamp uses the GLOBAL range (Utilities::MPI::min / max, matrix_free_operators.cc:258-259)
+    if (int e = allreduce_minmax(ctx, &mn, &mx)) { cudaFree(raw); cudaFree(coef); cudaFree(table); cudaFree(ext); return e; }
     int rc = SMF_OK;
     double *fine = coef;
     std::vector<double *> tmp;
@@ -843,10 +845,11 @@ int smf_fill_cell_data(smf_ctx *ctx, const double *viscosity_q, int averaging, d
   cudaFree(raw); cudaFree(act); cudaFree(dg0); cudaFree(ext);
   for (double *p : tmp) cudaFree(p);
   if (rc != SMF_OK) return rc;
-  if (min_max_out) {
+  {
     double mn = 1e300, mx = -1e300;
     for (unsigned b = 0; b < blocks; ++b) { mn = std::min(mn, h_ext[b]); mx = std::max(mx, h_ext[blocks + b]); }
-    min_max_out[0] = mn; min_max_out[1] = mx;
+    if ((rc = allreduce_minmax(ctx, &mn, &mx))) return rc;       // "Viscosity range" is global (Utilities::MPI::min / max)
+    if (min_max_out) { min_max_out[0] = mn; min_max_out[1] = mx; }
   }
   ctx->smoothers_ready = false;
   return SMF_OK;

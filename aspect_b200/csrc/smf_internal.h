@@ -99,6 +99,7 @@ __host__ __device__ inline int64_t blk_index(int64_t cell, int row, int n_rows)
 { return ((cell / GEO_BLOCK) * n_rows + row) * GEO_BLOCK + (cell % GEO_BLOCK); }
 __host__ __device__ inline int64_t blk_cells(int64_t n_cells) { return (n_cells + GEO_BLOCK - 1) / GEO_BLOCK * GEO_BLOCK; }
 
+constexpr int MAX_DEVICES = 64;        // per-device caches of function attributes / occupancy (indexed by the device ordinal)
 constexpr int SMF_MAX_RESTART = 200;   // longest GMRES / FGMRES restart length (nsinker_spherical_shell/gmg.prm uses 200); sizes the multi-dot scratch
 
 // closed constraint lines u_k = sum_j w_j u_{m_j} (hanging nodes) of one DoF family, CSR on the device (adaptive.cu)
@@ -355,6 +356,7 @@ void lattice_free(smf_ctx *ctx);
 void free_exchange(ExchangeDev &E);
 int exchange_add(smf_ctx *ctx, ExchangeDev &E, double *vec);
 int allreduce_sum(smf_ctx *ctx, double *dev, int count);
+int allreduce_minmax(smf_ctx *ctx, double *mn, double *mx);    // host values; collective
 int start_vector_mod11(smf_ctx *ctx, const ExchangeDev &E, double *x, int64_t n);
 // vector kernels (vecops.cu)
 int vec_set(smf_ctx *ctx, double *x, double v, int64_t n);

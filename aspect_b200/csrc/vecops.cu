@@ -275,10 +275,11 @@ static int all_aligned16(const void *w, double *const *V, int k)
 // persistent grids: never more blocks than are resident at once (a partial second wave would idle most SMs)
 template <class K> static unsigned red_blocks(K kernel, int64_t n)
 {
-  static int resident = 0;
+  static int resident_dev[MAX_DEVICES] = {0};
+  int per_sm = 1, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  int &resident = resident_dev[dev % MAX_DEVICES];
   if (resident == 0) {
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, VT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     resident = per_sm * sms;
