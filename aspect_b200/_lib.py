@@ -21,6 +21,7 @@ SMF_OPT_WARP_BRICK_KERNEL = 8
 SMF_OPT_COARSE_TAIL = 9
 SMF_OPT_NONSYMMETRIC_A_SOLVER = 10
 SMF_OPT_LATTICE_SCHUR = 11
+SMF_OPT_LATTICE_VELOCITY = 12
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p

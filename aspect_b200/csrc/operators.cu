@@ -13,6 +13,7 @@
 // dim warps of the block.  Results are accumulated in the shared staging area in collision-free rounds and
 // flushed once per batch: nodes private to the batch with plain stores, shared nodes with one RED each.
 #include "smf_internal.h"
+#include <cuda.h>
 #include <cuda/ptx>
 #include <type_traits>
 #include <algorithm>
@@ -841,6 +842,206 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
       }
     }
   }
+}
+
+// ---- structured bricks on LATTICE-ORDERED vectors: the brick is a box of the tensor [component][Z][Y][X] and arrives by TMA ----
+// (SMF_OPT_LATTICE_VELOCITY; set-up and rationale: velocity_lattice.cu.)  Same thread mapping and arithmetic as
+// velocity_sb_kernel<0>: one block per brick, warp c owns component c, lane = cell.  What changes is how the 9 x 9 x 5 lattice gets
+// into shared memory and back:
+//   * the vectors are stored as [component][x parity][Z][Y][X / 2] (even and odd lattice columns apart: TMA has no element stride
+//     in the innermost dimension), and thread 0 issues six cp.async.bulk.tensor loads per brick (3 components x 2 parities: boxes
+//     of 6 x 10 x 5 doubles), completion on an mbarrier; no index lists, no per-thread copies;
+//   * in shared memory a row is 6 doubles (5 even-x or 4 odd-x points + padding) and a plane 10 rows (9 + 1): the slot of local
+//     node (i, j, k) of the cell in lane (cx, cy, cz) is const(i, j, k) + cx + 12 cy + 120 cz, and the 16 lanes of a half-warp
+//     (x0 y0 z0 x1 of the Morton lane order) fall into 16 different 8-byte banks: cx + 12 y0 + 8 z0 (mod 16);
+//   * the flush computes its global addresses from the brick's lattice origin: rows of 9 consecutive doubles, plain stores for
+//     the 7 x 7 x 3 interior, one RED per DoF on the brick's faces, nothing on constrained boundary faces.
+constexpr int VL_ROW = 6, VL_ROWS = 10, VL_PLANE = VL_ROW * VL_ROWS;       // doubles per staged row / rows per plane / plane pitch
+constexpr int VL_BOX = VL_PLANE * 5;                                        // one (component, x-parity) box: 300 doubles = 2,400 bytes
+constexpr int VL_BOX_PITCH = 304;                                           // boxes start 128-byte aligned
+constexpr int VL_COMP = 2 * VL_BOX_PITCH, VL_STAGE = 3 * VL_COMP;           // per component / per buffer (1,824 doubles)
+__host__ __device__ constexpr int vl_const(int n)
+{ return ((n / 9) * VL_ROWS + ((n / 3) % 3)) * VL_ROW + ((n % 3) >> 1) + (((n % 3) & 1) ? VL_BOX_PITCH : 0); }
+constexpr size_t vl_smem_bytes() { return (size_t)(2 * VL_STAGE + 3 * 27 * SUB) * sizeof(double) + 128; }
+
+template <int C> __device__ __forceinline__ void vl_gather(double (&u)[27], const double *stage)
+{
+#pragma unroll
+  for (int m = 0; m < 27; ++m) u[m] = stage[vl_const(rot_actual<C, 3>(m))];
+}
+template <int C> __device__ __forceinline__ void vl_accumulate(double (&T)[27], double *stage, unsigned first_mask)
+{
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const bool first = (first_mask >> r) & 1u;
+    if (r != 0) {
+#pragma unroll
+      for (int m = 0; m < 27; ++m) {
+        const int n = rot_actual<C, 3>(m);
+        if (lowface(n) == r) { const double old = first ? 0.0 : stage[vl_const(n)]; T[m] += old; }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 27; ++m) {
+      const int n = rot_actual<C, 3>(m);
+      if (lowface(n) == r) stage[vl_const(n)] = T[m];
+    }
+    __syncwarp();
+  }
+}
+
+struct VLParams {
+  const int *brick_org;      // [n_batches][4]
+  double *dst;               // lattice-ordered result (zero on entry)
+  int Xp, ny, nz, cons_mask, plain;
+};
+
+template <bool PERQ>
+__global__ void __launch_bounds__(SBK_THREADS, 4) velocity_lat_kernel(const __grid_constant__ CUtensorMap tmap, const CellParams P, const VLParams V, int n_batches)
+{
+  constexpr int NN = 27;
+  extern __shared__ __align__(128) unsigned char vl_raw[];
+  // (the dynamic shared-memory window is 16-byte aligned by the ABI; the TMA destination wants 128)
+  double *sA = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(vl_raw) + 127) & ~uintptr_t(127));      // [3][2][VL_BOX_PITCH] values of the current brick
+  double *sB = sA + VL_STAGE;                 // accumulated results
+  double *s_ex = sB + VL_STAGE;               // [3][NN][32] pair buffers
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, c = tid >> 5, lane = tid & 31, G = gridDim.x;
+  int b = blockIdx.x;
+  if (b >= n_batches) return;
+  const int x = sb_x(lane), y = sb_y(lane), z = sb_z(lane);
+  const int lb = x + 2 * VL_ROW * y + 2 * VL_PLANE * z;
+  unsigned first_mask = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if ((!(r & 1) || x == 0) && (!(r & 2) || y == 0) && (!(r & 4) || z == 0)) first_mask |= 1u << r;
+  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+  const double e0 = P.ee[c], e1 = P.ee[c1], e2 = P.ee[c2];
+  double *ex_lo = s_ex + (size_t)c * NN * SUB + lane;
+  double *ex_up = s_ex + (size_t)c2 * NN * SUB + lane;
+  double *myA = sA + c * VL_COMP + lb, *myB = sB + c * VL_COMP + lb;
+  EtaRot eta;
+  eta.es0 = SUB * stride3(c); eta.es1 = SUB * stride3(c1); eta.es2 = SUB * stride3(c2);
+
+  const int frow = tid / 9, fx = tid - 9 * frow;      // flush: first row and column of this thread
+  constexpr uint32_t STAGE_BYTES = 6 * VL_BOX * sizeof(double);
+  const auto issue = [&](int brick) {      // (thread 0) arm the barrier, start the six box loads of `brick`
+    const int4 o = *reinterpret_cast<const int4 *>(V.brick_org + 4 * (size_t)brick);
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar, STAGE_BYTES);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int32_t crd[4] = {o.x >> 1, o.y, o.z, 2 * d + par};
+        cuda::ptx::cp_async_bulk_tensor(cuda::ptx::space_cluster, cuda::ptx::space_global, sA + d * VL_COMP + par * VL_BOX_PITCH, &tmap, crd, &bar);
+      }
+  };
+  if (tid == 0) {
+    cuda::ptx::mbarrier_init(&bar, 1);
+    cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+  }
+  __syncthreads();
+  if (tid == 0) issue(b);
+  double eta_next = PERQ ? 1.0 : P.eta_t[(size_t)b * P.n_eta * SUB + lane];
+  uint32_t parity = 0;
+
+  for (; b < n_batches; b += G) {
+    const int bn = b + G;
+    const int4 org = *reinterpret_cast<const int4 *>(V.brick_org + 4 * (size_t)b);
+    while (!cuda::ptx::mbarrier_try_wait_parity(&bar, parity)) {}
+    parity ^= 1;
+    const double eta0 = eta_next;
+    eta.etab = P.eta_t + (size_t)b * P.n_eta * SUB + lane;
+    // read_dof_values: constrained DoFs enter as zero -- only bricks on a constrained boundary face have any
+    if (org.w && V.cons_mask && !V.plain) {
+      for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, side = f & 1;
+        if (!((org.w >> (side ? 3 + d : d)) & 1)) continue;
+        const int cm = (V.cons_mask >> (3 * f)) & 7;
+        if (!cm) continue;
+        const int n1 = d == 0 ? 9 : 9, n2 = d == 2 ? 9 : 5;      // extents of the two other directions: (Y, Z) / (X, Z) / (X, Y)
+        for (int t = tid; t < 3 * n1 * n2; t += SBK_THREADS) {
+          const int comp = t / (n1 * n2), r = t - comp * n1 * n2, a = r % n1, bb = r / n1;
+          if (!((cm >> comp) & 1)) continue;
+          const int X = d == 0 ? (side ? 8 : 0) : a, Y = d == 1 ? (side ? 8 : 0) : (d == 0 ? a : bb), Z = d == 2 ? (side ? 4 : 0) : bb;
+          sA[comp * VL_COMP + ((X & 1) ? VL_BOX_PITCH : 0) + (Z * VL_ROWS + Y) * VL_ROW + (X >> 1)] = 0.0;
+        }
+      }
+      __syncthreads();
+    }
+    double u[NN], T[NN];
+    if (c == 0) vl_gather<0>(u, myA); else if (c == 1) vl_gather<1>(u, myA); else vl_gather<2>(u, myA);
+    interp_all<3>(u);
+    sb_diag<PERQ>(u, T, 2.0 * e0 * e0 * P.vol * eta0, eta, false);
+    sb_publish(u, ex_lo, e1);
+    __syncthreads();                        // publishes visible; every gather from sA is done
+    if (bn < n_batches) {
+      if (tid == 0) issue(bn);
+      if (!PERQ) eta_next = P.eta_t[(size_t)bn * P.n_eta * SUB + lane];
+    }
+    sb_upper<PERQ>(u, T, ex_up, e2, P.vol * eta0, eta);
+    __syncthreads();
+    sb_lower(T, ex_lo, e1);
+    interpT_all<3>(T);
+    if (c == 0) vl_accumulate<0>(T, myB, first_mask); else if (c == 1) vl_accumulate<1>(T, myB, first_mask); else vl_accumulate<2>(T, myB, first_mask);
+    __syncthreads();
+    // flush: thread (tid / 9, tid % 9) owns column X = tid % 9 of every 10th row (component, Z, Y) of the 135 rows; the row
+    // counters advance by additions only (no division in the loop: the first version decoded a flat item index and spent
+    // more instructions here than on the arithmetic of the cell)
+    if (tid < 90) {
+      const int X = fx, par = X & 1;
+      int cons_x = 0;
+      if (org.w) {
+        if (X == 0 && (org.w & 1)) cons_x |= V.cons_mask;            // faces 0..5: (d, side) = (0,0) (0,1) (1,0) (1,1) (2,0) (2,1)
+        if (X == 8 && (org.w & 8)) cons_x |= V.cons_mask >> 3;
+      }
+      const bool priv_x = X > 0 && X < 8;
+      // running 32-bit offsets (a level has fewer than 2^28 DoFs per family): additions only
+      const int sY = V.Xp, sZ = V.ny * V.Xp, cpl = V.nz * sZ;      // row / plane / (component, parity) array pitch of the result
+      int goff = par * cpl + (org.z + (frow >= 9 ? 1 : 0)) * sZ + (org.y + (frow >= 9 ? frow - 9 : frow)) * sY + ((org.x + X) >> 1);
+      int soff = par * VL_BOX_PITCH + (X >> 1) + (frow >= 9 ? VL_PLANE + (frow - 9) * VL_ROW : frow * VL_ROW);
+      int comp = 0, Z = frow >= 9 ? 1 : 0, Y = frow >= 9 ? frow - 9 : frow;      // row = frow, frow + 10, ... = comp * 45 + Z * 9 + Y
+#pragma unroll 1
+      for (int row = frow; row < 135; row += 10) {
+        const double v = sB[soff];
+        int cons = cons_x;
+        if (org.w) {
+          if (Y == 0 && (org.w & 2)) cons |= V.cons_mask >> 6;
+          if (Y == 8 && (org.w & 16)) cons |= V.cons_mask >> 9;
+          if (Z == 0 && (org.w & 4)) cons |= V.cons_mask >> 12;
+          if (Z == 4 && (org.w & 32)) cons |= V.cons_mask >> 15;
+        }
+        if (!((cons >> comp) & 1)) {      // constrained rows are skipped (dst = src there is the list kernel after this one)
+          if (priv_x && (unsigned)(Y - 1) < 7u && (unsigned)(Z - 1) < 3u) V.dst[goff] = v; else atomicAdd(V.dst + goff, v);
+        }
+        Y += 1; Z += 1; goff += sY + sZ; soff += VL_ROW + VL_PLANE;      // + 10 rows = + 1 plane + 1 row
+        if (Y >= 9) { Y -= 9; Z += 1; goff += sZ - 9 * sY; soff += VL_PLANE - 9 * VL_ROW; }
+        if (Z >= 5) { Z -= 5; comp += 1; goff += 2 * cpl - 5 * sZ; soff += VL_COMP - 5 * VL_PLANE; }
+      }
+    }
+  }
+}
+
+// host numbering <-> lattice order (thread per lattice node; the three components of a node are consecutive DoFs)
+__global__ void vl_to_lattice(double *lat, const double *vec, const uint32_t *lat2dof, int nx, int ny, int nz, int Xp)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n = (int64_t)nx * ny * nz;
+  if (i >= n) return;
+  const int X = (int)(i % nx);
+  const int64_t row = i / nx, cpl = (int64_t)nz * ny * Xp;
+  const uint32_t d = lat2dof[i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) lat[(2 * c + (X & 1)) * cpl + row * Xp + (X >> 1)] = vec[d + c];
+}
+__global__ void vl_from_lattice(double *vec, const double *lat, const uint32_t *lat2dof, int nx, int ny, int nz, int Xp)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n = (int64_t)nx * ny * nz;
+  if (i >= n) return;
+  const int X = (int)(i % nx);
+  const int64_t row = i / nx, cpl = (int64_t)nz * ny * Xp;
+  const uint32_t d = lat2dof[i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) vec[d + c] = lat[(2 * c + (X & 1)) * cpl + row * Xp + (X >> 1)];
 }
 
 // ---- structured bricks, ONE WARP PER BRICK, all three velocity components of a cell in one thread -----------------
@@ -2447,6 +2648,74 @@ int launch_set_entries(smf_ctx *ctx, double *vec, const uint32_t *idx, int64_t n
   return SMF_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// A block through the lattice mirror: dst (zero on entry, host numbering) = A src on the unconstrained rows
+int launch_velocity_lat(smf_ctx *ctx, LevelDev &L, double *dst, const double *src)
+{
+  VLat &V = *L.vlat;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return ctx->fail(SMF_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)V.Xp, (cuuint64_t)V.ny, (cuuint64_t)V.nz, 6};
+  const cuuint64_t strides[3] = {(cuuint64_t)V.Xp * 8, (cuuint64_t)V.Xp * V.ny * 8, (cuuint64_t)V.Xp * V.ny * V.nz * 8};
+  const cuuint32_t box[4] = {VL_ROW, VL_ROWS, 5, 1}, estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, V.src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ctx->fail(SMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  const unsigned nb = (unsigned)((V.n_nodes + 255) / 256);
+  {
+    ProfScope prof(ctx, B_VEC);
+    vl_to_lattice<<<nb, 256, 0, ctx->stream>>>(V.src, src, V.lat2dof, V.nx, V.ny, V.nz, V.Xp);
+    SMF_CUDA(cudaMemsetAsync(V.dst, 0, sizeof(double) * V.n_lat, ctx->stream));
+    ctx->launches++;
+  }
+  CellParams P = make_params(L);
+  VLParams Q{V.brick_org, V.dst, V.Xp, V.ny, V.nz, V.cons_mask, 0};
+  constexpr size_t smem = vl_smem_bytes();
+  static int resident_dev[MAX_DEVICES] = {0};
+  int &resident = resident_dev[ctx->cfg.device % MAX_DEVICES];
+  if (resident == 0) {
+    SMF_CUDA(cudaFuncSetAttribute(velocity_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 148;
+    SMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+    SMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, velocity_lat_kernel<false>, SBK_THREADS, smem));
+    if (per_sm < 1) return ctx->fail(SMF_ERR_CUDA, "velocity_lat_kernel does not fit on an SM");
+    resident = per_sm * sms;
+  }
+  const bool fine = (&L == &ctx->lev(SMF_ACTIVE)) || (&L == &ctx->levels[ctx->cfg.n_levels - 1]);
+  {
+    ProfScope prof(ctx, fine ? B_A_FINE : B_A_COARSE);
+    int grid = std::min(L.n_batches, resident);
+    if (ctx->max_grid_blocks > 0) grid = std::min(grid, ctx->max_grid_blocks);
+    velocity_lat_kernel<false><<<grid, SBK_THREADS, smem, ctx->stream>>>(tmap, P, Q, L.n_batches);
+    ctx->launches++;
+  }
+  {
+    ProfScope prof(ctx, B_VEC);
+    vl_from_lattice<<<nb, 256, 0, ctx->stream>>>(dst, V.dst, V.lat2dof, V.nx, V.ny, V.nz, V.Xp);
+    ctx->launches++;
+    if (L.n_constrained_u) {      // unit diagonal on the constrained rows: dst = src
+      copy_entries_kernel<<<(unsigned)((L.n_constrained_u + 255) / 256), 256, 0, ctx->stream>>>(dst, src, L.constrained_u, L.n_constrained_u);
+      ctx->launches++;
+    }
+  }
+  SMF_CUDA(cudaGetLastError());
+  return SMF_OK;
+}
+
 int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bool dst_is_zero)
 {
   if (int e = check_level(ctx, L)) return e;
@@ -2454,7 +2723,9 @@ int launch_vmult_A(smf_ctx *ctx, LevelDev &L, double *dst, const double *src, bo
   P.src_u = src; P.dst_u = dst;
   if (!dst_is_zero) SMF_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * L.n_u, ctx->stream));
   if (int e = hanging_pre(ctx, L.hang_u, src)) return e;              // read_dof_values resolves the hanging-node lines
+  if (ctx->use_vlat && !L.vlat && L.structured && L.has_cell_data) { if (int e = vlat_prepare(ctx, L)) return e; }
   if (needs_general(L, 0)) { if (int e = launch_general(ctx, L, 0, dst, nullptr, src, nullptr, false)) return e; }
+  else if (ctx->use_vlat && L.vlat && L.n_eta == 1) { if (int e = launch_velocity_lat(ctx, L, dst, src)) return e; }      // experimental: TMA-staged bricks
   else if (int e = L.dim == 3 ? launch_velocity<3, 0>(ctx, L, P) : launch_velocity<2, 0>(ctx, L, P)) return e;
   if (int e = hanging_post(ctx, L.hang_u, dst, src, true)) return e;  // distribute_local_to_global + unit diagonal
   return exchange_add(ctx, L.ex_u, dst);

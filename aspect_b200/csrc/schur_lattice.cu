@@ -487,6 +487,16 @@ static bool detect_lattice(const std::vector<uint32_t> &nodes_p, int64_t n_cells
   return true;
 }
 
+// cell coordinates of a box level (used by velocity_lattice.cu): dims = pressure nodes per direction
+bool lattice_cell_coords(const std::vector<uint32_t> &nodes_p, int64_t n_cells, int64_t n_p, int dims[3], std::vector<int> &cell_xyz)
+{
+  LatHost H;
+  if (nodes_p.size() != (size_t)n_cells * 8 || !detect_lattice(nodes_p, n_cells, n_p, H)) return false;
+  dims[0] = H.nx; dims[1] = H.ny; dims[2] = H.nz;
+  cell_xyz.swap(H.cell_xyz);
+  return true;
+}
+
 template <class T> static int up(smf_ctx *ctx, T **dev, const std::vector<T> &h)
 {
   SMF_CUDA(cudaMalloc(dev, sizeof(T) * std::max<size_t>(h.size(), 1)));

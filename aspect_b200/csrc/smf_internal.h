@@ -114,6 +114,17 @@ struct EdgeSet { int64_t n = 0; uint32_t *idx = nullptr; double *save = nullptr;
 struct FaceSet { int64_t n = 0; uint32_t *cells = nullptr; int32_t *face_no = nullptr; double *table = nullptr; };
 struct CopyPairs { int64_t n = 0; uint32_t *active = nullptr, *level = nullptr; };
 
+// Lattice-ordered mirror of the velocity vectors of a structured box level: [component][x parity][Z][Y][X / 2], row pitch Xp
+// (even, so that every row starts 16-byte aligned), for the kernel that stages its bricks with TMA box loads (velocity_lat_kernel)
+struct VLat {
+  int nx = 0, ny = 0, nz = 0, Xp = 0;
+  int64_t n_nodes = 0, n_lat = 0;           // nx * ny * nz;  6 * nz * ny * Xp
+  uint32_t *lat2dof = nullptr;              // [n_nodes] first DoF of every lattice node (host numbering)
+  int *brick_org = nullptr;                 // [n_batches][4]: lattice origin of the brick, bit d / 3 + d: on the low / high domain face of direction d
+  int cons_mask = 0;                        // bit 3 f + c: component c is constrained on boundary face f = 2 d + side
+  double *src = nullptr, *dst = nullptr;    // lattice-ordered copies of the operand / the result
+};
+
 struct LevelDev {
   int dim = 0;
   int64_t n_cells = 0, n_u = 0, n_p = 0;
@@ -152,6 +163,7 @@ struct LevelDev {
   EdgeSet edge_u, edge_p;                       // levels: refinement-edge indices
   CopyPairs copy_u, copy_p;                     // levels: copy_to_mg / copy_from_mg pairs
   FaceSet fs_faces;                             // ACTIVE level: free-surface stabilisation faces
+  VLat *vlat = nullptr;                         // SMF_OPT_LATTICE_VELOCITY: lattice-ordered mirror (velocity_lattice.cu)
 };
 
 constexpr int TB_COARSE = 76;      // coarse velocity nodes under a fine brick: 5 x 5 x 3 lattice = 75, padded
@@ -274,6 +286,7 @@ struct smf_ctx {
   int64_t graph_L_launches = 0, graph_L_exchanges = 0;
   int lat_tail = -1;                                  // levels 0..lat_tail of the lattice cycle run in one thread block
   double *lat_res = nullptr;                          // buffer the captured cycle leaves its result in
+  int use_vlat = 0;                                   // SMF_OPT_LATTICE_VELOCITY: A block of structured box levels through the TMA-staged lattice kernel
   int use_warp_brick = 0;                             // structured levels: one-warp-per-brick velocity kernel, three components per thread (SMF_OPT_WARP_BRICK_KERNEL)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
   int allow_structured = 1;                           // structured-brick fast path of the velocity kernels (tests may switch it off)
@@ -348,7 +361,12 @@ void free_adaptive(LevelDev &L);
 // coarse_tail.cu
 int schur_tail_top_level(smf_ctx *ctx);
 int launch_schur_tail(smf_ctx *ctx, int top);
+// velocity_lattice.cu / operators.cu
+int vlat_prepare(smf_ctx *ctx, LevelDev &L);                         // builds L.vlat if the level qualifies (else leaves it null)
+void vlat_free(LevelDev &L);
+int launch_velocity_lat(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);      // A block: dst (zeroed) += A src, both in host numbering
 // schur_lattice.cu
+bool lattice_cell_coords(const std::vector<uint32_t> &nodes_p, int64_t n_cells, int64_t n_p, int dims[3], std::vector<int> &cell_xyz);
 int lattice_prepare(smf_ctx *ctx);                                   // detection (once per mesh) + coefficients / diagonals (every smoother set-up)
 int lattice_vcycle(smf_ctx *ctx, double *dst, const double *src);    // prec_Schur on the lattice
 void lattice_free(smf_ctx *ctx);

@@ -73,6 +73,7 @@ class StokesMatrixFreeHandler:
         self.device_cell_data = True             # assemble(): averaging / projection / level tables on the device (False: host numpy)
         self.use_warp_brick_kernel = os.environ.get("SMF_WARP_BRICK", "0") == "1"    # structured levels: one warp per brick, 3 components per thread
         self.use_coarse_tail = True              # Schur V-cycle: coarse levels in one single-block kernel
+        self.use_lattice_velocity = os.environ.get("SMF_LATTICE_VELOCITY", "0") == "1"   # experimental: TMA-staged A-block kernel on lattice-ordered vectors
         self.use_lattice_schur = os.environ.get("SMF_LATTICE", "1") == "1"    # Schur V-cycle on box levels in lattice order (node-centred fused kernels)
         self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
@@ -146,6 +147,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_WARP_BRICK_KERNEL, int(self.use_warp_brick_kernel)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_COARSE_TAIL, int(self.use_coarse_tail)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_LATTICE_SCHUR, int(self.use_lattice_schur)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_LATTICE_VELOCITY, int(self.use_lattice_velocity)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_SUMFAC, int(self.curved_sum_factorization)))

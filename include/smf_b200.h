@@ -62,6 +62,8 @@ const char *smf_last_error(const smf_ctx *ctx);
                                          (block_stokes_preconditioner.h:119-132); implied by smf_set_free_surface_faces */
 #define SMF_OPT_LATTICE_SCHUR 11        /* Schur-complement V-cycle on box levels: level vectors in lattice order inside the cycle, node-centred 27-point mass
                                          stencil with the Chebyshev update fused, one CUDA graph per cycle (default 1; 3D, Cartesian, one viscosity per cell) */
+#define SMF_OPT_LATTICE_VELOCITY 12     /* experimental (default 0): A block of structured box levels on lattice-ordered copies of the vectors, bricks staged by
+                                         TMA box loads (cp.async.bulk.tensor, x de-interleaved by the element stride) instead of node lists + cp.async */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
