@@ -1740,6 +1740,7 @@ struct TransferSbParams {
   const unsigned char *lists;    // fine level's sb_lists [n_bricks][SB_BLOCK_BYTES]
   const double *src; double *dst;
   int add;
+  const double *minus;           // restriction only: the restricted vector is src - minus (the V-cycle's residual b - A x, never stored); may be null
 };
 
 // One thread per line of each sweep; all weights and loop bounds are compile-time constants.
@@ -1824,8 +1825,10 @@ __global__ void __launch_bounds__(TSB_THREADS) restrict_sb_kernel(const Transfer
   const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
   const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
   const int j0 = tid / 3, d0 = tid - 3 * j0;
-  for (int j = j0; j < 405; j += 32)
-    sO[d0][ls[j]] = (ob[j] & 2) ? P.src[(le[j] & NODE_IDX_MASK) + d0] : 0.0;
+  for (int j = j0; j < 405; j += 32) {
+    const uint32_t idx = (le[j] & NODE_IDX_MASK) + d0;
+    sO[d0][ls[j]] = (ob[j] & 2) ? (P.minus ? P.src[idx] - P.minus[idx] : P.src[idx]) : 0.0;
+  }
   __syncthreads();
   for (int t = tid; t < 243; t += TSB_THREADS) {       // z^T: lines (d, Y, X): 5 -> 3
     const int d = t / 81, yx = t - 81 * d, Y = yx / 9, X = yx - 9 * Y;
@@ -2858,7 +2861,12 @@ static void launch_transfer_t(smf_ctx *ctx, const TransferParams &P, bool prolon
   ctx->launches++;
 }
 
-static int launch_transfer(smf_ctx *ctx, int which, int fine_level, double *dst, const double *src, bool prolong, bool add)
+static bool transfer_is_brickwise(smf_ctx *ctx, int which, int fine_level)
+{
+  return which == 0 && ctx->cfg.dim == 3 && fine_level >= 1 && fine_level < ctx->cfg.n_levels && ctx->transfers[fine_level].tb_u &&
+         ctx->levels[fine_level].sb_lists && ctx->use_pipelined;
+}
+static int launch_transfer(smf_ctx *ctx, int which, int fine_level, double *dst, const double *src, bool prolong, bool add, const double *minus = nullptr)
 {
   if (fine_level < 1 || fine_level >= ctx->cfg.n_levels || !ctx->transfers[fine_level].set)
     return ctx->fail(SMF_ERR_INVALID, "transfer not set for this level (smf_set_transfer)");
@@ -2869,7 +2877,7 @@ static int launch_transfer(smf_ctx *ctx, int which, int fine_level, double *dst,
   const int dim = ctx->cfg.dim;
   LevelDev &F = ctx->levels[fine_level];
   if (which == 0 && dim == 3 && T.tb_u && F.sb_lists && ctx->use_pipelined) {
-    TransferSbParams Q{T.tb_u, F.sb_lists, src, dst, add ? 1 : 0};
+    TransferSbParams Q{T.tb_u, F.sb_lists, src, dst, add ? 1 : 0, prolong ? nullptr : minus};
     ProfScope prof(ctx, B_TRANSFER);
     if (prolong) prolongate_sb_kernel<<<F.n_batches, TSB_THREADS, 0, ctx->stream>>>(Q);
     else restrict_sb_kernel<<<F.n_batches, TSB_THREADS, 0, ctx->stream>>>(Q);
@@ -2891,5 +2899,13 @@ int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const 
 { return launch_transfer(ctx, which, to_level, dst, src, true, add); }
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src)
 { return launch_transfer(ctx, which, from_level, dst, src, false, true); }
+// dst += R (b - t): the residual of the V-cycle restricted without being stored (brick-wise velocity transfers); elsewhere
+// t <- b - t first.  Returns through *fused whether t was left untouched.
+int launch_restrict_add_residual(smf_ctx *ctx, int which, int from_level, double *dst, const double *b, double *t, int64_t n_fine)
+{
+  if (transfer_is_brickwise(ctx, which, from_level)) return launch_transfer(ctx, which, from_level, dst, b, false, true, t);
+  if (int e = vec_residual(ctx, t, b, n_fine)) return e;
+  return launch_transfer(ctx, which, from_level, dst, t, false, true);
+}
 
 }  // namespace smf

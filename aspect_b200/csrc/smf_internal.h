@@ -347,6 +347,7 @@ int launch_set_entries(smf_ctx *ctx, double *vec, const uint32_t *idx, int64_t n
 int launch_rhs(smf_ctx *ctx, LevelDev &L, const double *force_q_dev, double *rhs_u);
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add);
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src);
+int launch_restrict_add_residual(smf_ctx *ctx, int which, int from_level, double *dst, const double *b, double *t, int64_t n_fine);   // dst += R (b - t)
 // adaptive.cu: hanging-node lines around a cell loop; refinement-edge handling of the level operators
 int hanging_pre(smf_ctx *ctx, ConstraintLines &H, const double *src);                // save src[k]; src[k] = sum_j w_j src[m_j]
 int hanging_post(smf_ctx *ctx, ConstraintLines &H, double *dst, const double *src, bool unit_diagonal);   // dst[m_j] += w_j dst[k]; dst[k] = saved (or 0); src[k] = saved

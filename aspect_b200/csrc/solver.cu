@@ -201,9 +201,8 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
     const int64_t n = lsize(ctx, S, l);
     MGVectors &C = (*S.v)[l - 1];
     TRY(lapply_t(ctx, S, l, x));
-    TRY(vec_residual(ctx, V.t, V.b, n));                                     // t = defect - A x
     TRY(vec_set(ctx, C.b, 0.0, lsize(ctx, S, l - 1)));
-    TRY(launch_restrict_add(ctx, which, l, C.b, V.t));
+    TRY(launch_restrict_add_residual(ctx, which, l, C.b, V.b, V.t, n));      // coarse defect = R (defect - A x)
     if (!S.velocity && l - 1 == ctx->tail_level) TRY(launch_schur_tail(ctx, l - 1));      // levels 0..l-1 in one launch
     else TRY(level_v_step_maybe_graph(ctx, S, l - 1));
     TRY(launch_prolongate(ctx, which, l, x, C.res, true));                   // x += P x_coarse

@@ -384,6 +384,7 @@ def main():
             solver_timings = h.execute_solver_timings(rhs_np, n_timings=3, out=lambda *_: None)
             solver_timings = {k: max_over_ranks(v) for k, v in sorted(solver_timings.items())}
 
+    lattice_active, lattice_repl = h.lattice_schur_active(), h.lattice_replicated_levels()
     its = outs[-1]["iterations"]
     wall = t_dev / args.steps
     wall_e2e = t_e2e / args.steps
@@ -444,8 +445,18 @@ def main():
         "time_split_ms": {k: round(v[0], 3) for k, v in split.items()},
         "launch_split": {k: v[1] for k, v in split.items()},
         "clocks": clock_info, "host_setup_s": setup_s, "solver_timings_s": solver_timings, "halo_exchanges_per_solve": int(exchanges), "halo_transport": h.exchange_transport(),
+        "schur_vcycle": {"path": "lattice (node-centred mass stencil + fused Chebyshev update, one CUDA graph)" if lattice_active else "cell batches",
+                         "replicated_coarse_levels": lattice_repl,
+                         "ms": None if not solver_timings else solver_timings.get("S_preconditioner", 0.0) * 1e3,
+                         # algorithmic bytes of one cycle: 32 smoothing steps per level, 40 B per pressure DoF and step (x, xo in/out, b,
+                         # one coefficient), levels sum to 8/7 of the finest
+                         "algorithmic_bytes": 32 * 40.0 * n_p * 8.0 / 7.0,
+                         "hbm_frac": None if not solver_timings or not solver_timings.get("S_preconditioner") else
+                         32 * 40.0 * n_p * 8.0 / 7.0 / solver_timings["S_preconditioner"] / 1e9 / peak},
     }
     h.close()
+    if world > 1 and lattice_repl:
+        line["config"]["parallelism"] += f"; Schur V-cycle: the {lattice_repl} coarsest levels replicated on every rank (global lattice, one all-reduce per cycle)"
     # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------
     if not args.no_cfg2 and R != 5 and world == 1:
         hier5, h5, rhs5, _, _ = build_problem(5, local_rank)
