@@ -78,7 +78,7 @@ EXPORTS = [
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",
     "smf_solve_host", "smf_kernel_launches", "smf_device_bytes", "smf_profile_enable", "smf_profile_read",
-    "smf_exchange_count", "smf_exchange_transport", "smf_lattice_schur_active", "smf_lattice_replicated_levels", "smf_assemble_rhs", "smf_set_pressure_normalization",
+    "smf_exchange_count", "smf_exchange_transport", "smf_lattice_schur_active", "smf_lattice_replicated_levels", "smf_detect_box_lattice", "smf_assemble_rhs", "smf_set_pressure_normalization",
     "smf_postprocess_pressure", "smf_measure_fp64_peak", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
 ]
 

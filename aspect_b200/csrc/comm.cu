@@ -378,6 +378,18 @@ int smf_comm_init(smf_ctx *ctx, int rank, int world, const char *id)
   return SMF_OK;
 }
 
+int smf_detect_box_lattice(const uint32_t *cell_dofs_p, int64_t n_cells, int64_t n_dofs_p, int32_t *nodes_per_direction, int32_t *cell_xyz)
+{
+  if (!cell_dofs_p || n_cells < 1 || n_dofs_p < 1 || n_dofs_p >= (int64_t)NODE_IDX_MASK) return 0;
+  for (int64_t i = 0; i < n_cells * 8; ++i) if (cell_dofs_p[i] >= (uint64_t)n_dofs_p) return 0;
+  std::vector<uint32_t> nodes(cell_dofs_p, cell_dofs_p + n_cells * 8);
+  std::vector<int> xyz;
+  int dims[3];
+  if (!lattice_cell_coords(nodes, n_cells, n_dofs_p, dims, xyz)) return 0;
+  if (nodes_per_direction) for (int d = 0; d < 3; ++d) nodes_per_direction[d] = dims[d];
+  if (cell_xyz) for (size_t i = 0; i < xyz.size(); ++i) cell_xyz[i] = xyz[i];
+  return 1;
+}
 int smf_lattice_schur_active(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? 1 : 0; }
 int smf_lattice_replicated_levels(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? ctx->lat_repl + 1 : 0; }
 int smf_exchange_transport(const smf_ctx *ctx) { return !ctx || ctx->world == 1 ? 0 : (ctx->p2p ? 2 : 1); }

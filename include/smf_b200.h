@@ -329,6 +329,10 @@ int smf_profile_read(smf_ctx *ctx, double *ms_out, int64_t *count_out);
 int64_t smf_kernel_launches(const smf_ctx *ctx);     /* kernels launched by this context so far */
 int64_t smf_device_bytes(const smf_ctx *ctx);        /* get_*_memory_consumption() analogue      */
 int64_t smf_exchange_count(const smf_ctx *ctx);      /* halo exchanges performed by this context so far */
+/* The lattice detection of the Schur V-cycle as a host-only utility (no CUDA call, no context): given the pressure part of a level's
+ * cell -> DoF map ([n_cells][8], 3D, lexicographic vertex order), decide whether the cells form a Cartesian box and, if so, return
+ * the number of pressure nodes per direction and the integer coordinates of every cell ([n_cells][3]).  Returns 1 (box), 0 (not a box). */
+int smf_detect_box_lattice(const uint32_t *cell_dofs_p, int64_t n_cells, int64_t n_dofs_p, int32_t *nodes_per_direction, int32_t *cell_xyz);
 int smf_lattice_schur_active(const smf_ctx *ctx);    /* 1: prec_Schur runs on the lattice path (SMF_OPT_LATTICE_SCHUR; decided by smf_setup_smoothers) */
 int smf_lattice_replicated_levels(const smf_ctx *ctx);   /* several ranks: coarse levels of the lattice path that every rank computes on the GLOBAL lattice (no halo exchange) */
 int smf_exchange_transport(const smf_ctx *ctx);      /* 0 = single rank, 1 = NCCL send/recv, 2 = fused peer-memory kernel (CUDA IPC over NVLink) */
