@@ -257,6 +257,7 @@ void smf_destroy(smf_ctx *ctx)
   for (auto &e : ctx->prof_live) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   lattice_free(ctx);
+  cudaFree(ctx->ad_in_u); cudaFree(ctx->ad_out_u); cudaFree(ctx->ad_in_p); cudaFree(ctx->ad_out_p);
   if (ctx->graph_A) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_A);
   if (ctx->graph_S) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_S);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -309,6 +310,10 @@ int smf_set_level(smf_ctx *ctx, int level, const smf_level_mesh *m)
   SMF_CUDA(cudaSetDevice(ctx->cfg.device));
   LevelDev &L = ctx->lev(level);
   lattice_free(ctx);
+  cudaFree(ctx->ad_in_u); cudaFree(ctx->ad_out_u); cudaFree(ctx->ad_in_p); cudaFree(ctx->ad_out_p);      // staging of the adaptive V-cycle graphs
+  ctx->ad_in_u = ctx->ad_out_u = ctx->ad_in_p = ctx->ad_out_p = nullptr;
+  ctx->ad_warm_u = ctx->ad_warm_p = false;
+  ctx->graph_A_stale = ctx->graph_S_stale = true;
   ctx->bytes -= L.bytes;
   free_level(L);
   const int dim = ctx->cfg.dim, NN = dim == 3 ? 27 : 9, NP = dim == 3 ? 8 : 4;

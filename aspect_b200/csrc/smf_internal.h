@@ -265,6 +265,8 @@ struct smf_ctx {
   int64_t graph_A_launches = 0, graph_S_launches = 0; // kernels inside one replay
   int64_t graph_A_exchanges = 0, graph_S_exchanges = 0;   // halo exchanges inside one replay
   int graph_level = -1;                               // finest level inside the graphs (-1: graphs unused)
+  double *ad_in_u = nullptr, *ad_out_u = nullptr, *ad_in_p = nullptr, *ad_out_p = nullptr;   // adaptive meshes: staging of the graph-replayed V-cycles
+  bool ad_warm_u = false, ad_warm_p = false;          // the first adaptive cycle after a mesh change runs eagerly (allocations)
   int use_graphs = 1;
   int ortho_single_pass = 1;                          // GMRES: re-orthogonalise through the Gram matrix (1) or with a second pass over the basis (0)
   int max_grid_blocks = 0;                            // > 0: cap on the persistent grids (tests: forces several bricks per block)

@@ -266,6 +266,57 @@ static int vcycle_adaptive(smf_ctx *ctx, const MGSide &S, double *dst, const dou
   return SMF_OK;
 }
 
+// The adaptive cycle issues ~40 launches per level plus a dozen list kernels (edges, copy indices), nearly all of them tiny: on
+// BASELINE cfg 4 (38 k cells) a solve was pure launch latency.  All buffers and coefficients are fixed between smoother set-ups,
+// so the whole cycle is captured once into a CUDA graph between two staging copies (the caller's vectors change from call to
+// call); the first call after a set-up runs eagerly (it allocates the edge scratch vectors).
+static int vcycle_adaptive_maybe_graph(smf_ctx *ctx, const MGSide &S, double *dst, const double *src)
+{
+  if (!ctx->use_graphs || ctx->prof_mode != 0 || ctx->world > 1) return vcycle_adaptive(ctx, S, dst, src);
+  LevelDev &A = ctx->lev(SMF_ACTIVE);
+  const int64_t n = S.velocity ? A.n_u : A.n_p;
+  double *&in = S.velocity ? ctx->ad_in_u : ctx->ad_in_p, *&out = S.velocity ? ctx->ad_out_u : ctx->ad_out_p;
+  bool &warm = S.velocity ? ctx->ad_warm_u : ctx->ad_warm_p;
+  void *&exec = S.velocity ? ctx->graph_A : ctx->graph_S;
+  bool &stale = S.velocity ? ctx->graph_A_stale : ctx->graph_S_stale;
+  int64_t &n_launch = S.velocity ? ctx->graph_A_launches : ctx->graph_S_launches;
+  if (!in) {
+    SMF_CUDA(cudaMalloc(&in, sizeof(double) * n)); SMF_CUDA(cudaMalloc(&out, sizeof(double) * n));
+    ctx->bytes += 2 * sizeof(double) * n;
+  }
+  if (!warm) { warm = true; stale = true; return vcycle_adaptive(ctx, S, dst, src); }
+  VecBucket vb(ctx, B_VEC);
+  TRY(vec_copy(ctx, in, src, n));
+  if (stale) {
+    cudaGraph_t graph = nullptr;
+    SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    const int64_t l0 = ctx->launches;
+    const int rc = vcycle_adaptive(ctx, S, out, in);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return ctx->fail(SMF_ERR_CUDA, std::string("cudaStreamEndCapture (adaptive V-cycle): ") + cudaGetErrorString(ce));
+    n_launch = ctx->launches - l0;
+    ctx->launches = l0;
+    bool updated = false;
+    if (exec) {
+      cudaGraphExecUpdateResultInfo info;
+      updated = cudaGraphExecUpdate((cudaGraphExec_t)exec, graph, &info) == cudaSuccess;
+      if (!updated) { cudaGetLastError(); cudaGraphExecDestroy((cudaGraphExec_t)exec); exec = nullptr; }
+    }
+    if (!updated) {
+      cudaGraphExec_t ge = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&ge, graph, 0);
+      if (ie != cudaSuccess) { cudaGraphDestroy(graph); return ctx->fail(SMF_ERR_CUDA, std::string("cudaGraphInstantiate (adaptive V-cycle): ") + cudaGetErrorString(ie)); }
+      exec = ge;
+    }
+    cudaGraphDestroy(graph);
+    stale = false;
+  }
+  SMF_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, ctx->stream));
+  ctx->launches += n_launch;
+  return vec_copy(ctx, dst, out, n);
+}
+
 // Levels <= ctx->graph_level are small: their part of the V-cycle is launch-latency bound, so it is captured once per
 // smoother set-up into a CUDA graph (all buffers and coefficients are fixed between set-ups) and replayed.
 static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
@@ -314,7 +365,7 @@ static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
 {
   if (!ctx->smoothers_ready) return ctx->fail(SMF_ERR_INVALID, "call smf_setup_smoothers before applying a V-cycle");
   MGSide S{velocity, velocity ? &ctx->smoother_A : &ctx->smoother_S, velocity ? &ctx->mgv_A : &ctx->mgv_S, velocity ? 1 : 4};
-  if (ctx->adaptive) return vcycle_adaptive(ctx, S, dst, src);
+  if (ctx->adaptive) return vcycle_adaptive_maybe_graph(ctx, S, dst, src);
   if (!velocity && ctx->lat_state == 1 && ctx->use_lattice) return lattice_vcycle(ctx, dst, src);      // box levels: schur_lattice.cu
   const int L = ctx->cfg.n_levels - 1;
   const int64_t n = lsize(ctx, S, L);
