@@ -57,7 +57,7 @@ static void tridiag_extreme(const std::vector<double> &d, const std::vector<doub
   lmin = kth(0); lmax = kth(n - 1);
 }
 
-constexpr int64_t GRAPH_MAX_CELLS = 40000;   // levels up to this size are replayed from a CUDA graph
+constexpr int64_t GRAPH_MAX_CELLS = 70000;   // levels up to this size are replayed from a CUDA graph (the 49,152-cell level of the refinement-3 shell included)
 
 struct MGSide {           // one of the two hierarchies
   bool velocity;
