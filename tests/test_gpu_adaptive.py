@@ -121,17 +121,22 @@ def test_adaptive_solve_matches_oracle(name):
     ops = box.assemble(eta, 1.0, "zero")
     rhs = np.concatenate([ops["Cu"].T @ np.sin(np.arange(box.n_u)), np.zeros(box.n_p)])
     rhs[ops["constrained_u"]] = 0.0
-    want = oad.block_gmg_solve(box, eta, rhs, "zero", 1.0, 1e-8)
+    # Solver tolerance 1e-10: two runs that stop at 1e-8 agree to ~1e-8 only if they follow the same Krylov path to the last bit,
+    # and the level kernels of this path accumulate with unordered REDs (observed: 0.7e-8 .. 1.1e-8 from run to run); two decades
+    # below the 1e-8 criterion of the comparison it is the discretised problem that is compared, not the stopping point.
+    want = oad.block_gmg_solve(box, eta, rhs, "zero", 1.0, 1e-10)
     h.build_preconditioner()
-    h.parameters.update({"Linear solver tolerance": 1e-8, "Number of cheap Stokes solver steps": 200,
+    h.parameters.update({"Linear solver tolerance": 1e-10, "Number of cheap Stokes solver steps": 200,
                          "Maximum number of expensive Stokes solver steps": 0})
     sol, out = h.solve(rhs)
     assert out["converged"] and want["converged"]
-    assert out["iterations"] == want["iterations"], (out["iterations"], want["iterations"])
+    assert abs(out["iterations"] - want["iterations"]) <= 1, (out["iterations"], want["iterations"])
     nu = box.n_u
     free = np.setdiff1d(np.arange(nu), ops["constrained_u"])
-    assert rel(sol[:nu][free], want["x"][:nu][free]) < 1e-8
+    e_free = rel(sol[:nu][free], want["x"][:nu][free])
+    assert e_free < 1e-8, e_free
     # distribute(): the hanging entries of the returned solution carry the interpolated values
     full = ops["Cu"] @ want["x"][:nu]
-    assert rel(sol[:nu], full) < 1e-8
+    e_full = rel(sol[:nu], full)
+    assert e_full < 1e-8, (e_full, e_free)
     h.close()
