@@ -22,6 +22,7 @@ SMF_OPT_COARSE_TAIL = 9
 SMF_OPT_NONSYMMETRIC_A_SOLVER = 10
 SMF_OPT_LATTICE_SCHUR = 11
 SMF_OPT_LATTICE_VELOCITY = 12
+SMF_OPT_REPLICATE_COARSE_A = 13
 SMF_UNIQUE_ID_BYTES = 128
 
 c_i64, c_int, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -78,7 +79,7 @@ EXPORTS = [
     "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",
     "smf_solve_host", "smf_kernel_launches", "smf_device_bytes", "smf_profile_enable", "smf_profile_read",
-    "smf_exchange_count", "smf_exchange_transport", "smf_lattice_schur_active", "smf_lattice_replicated_levels", "smf_detect_box_lattice", "smf_assemble_rhs", "smf_set_pressure_normalization",
+    "smf_exchange_count", "smf_exchange_transport", "smf_lattice_schur_active", "smf_lattice_replicated_levels", "smf_detect_box_lattice", "smf_replicated_A_levels", "smf_assemble_rhs", "smf_set_pressure_normalization",
     "smf_postprocess_pressure", "smf_measure_fp64_peak", "smf_comm_get_unique_id", "smf_comm_init", "smf_set_exchange", "smf_exchange_add",
 ]
 

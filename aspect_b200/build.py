@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmf_b200.so")
-SOURCES = ["operators.cu", "vecops.cu", "setup.cu", "solver.cu", "comm.cu", "adaptive.cu", "coarse_tail.cu", "schur_lattice.cu", "velocity_lattice.cu"]
+SOURCES = ["operators.cu", "vecops.cu", "setup.cu", "solver.cu", "comm.cu", "adaptive.cu", "coarse_tail.cu", "schur_lattice.cu", "velocity_lattice.cu", "velocity_replica.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas", "-v"]
 

@@ -392,6 +392,7 @@ int smf_detect_box_lattice(const uint32_t *cell_dofs_p, int64_t n_cells, int64_t
 }
 int smf_lattice_schur_active(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? 1 : 0; }
 int smf_lattice_replicated_levels(const smf_ctx *ctx) { return ctx && ctx->use_lattice && ctx->lat_state == 1 ? ctx->lat_repl + 1 : 0; }
+int smf_replicated_A_levels(const smf_ctx *ctx) { return ctx ? ctx->replica_top + 1 : 0; }
 int smf_exchange_transport(const smf_ctx *ctx) { return !ctx || ctx->world == 1 ? 0 : (ctx->p2p ? 2 : 1); }
 
 void smf_comm_destroy_internal(smf_ctx *ctx)
@@ -540,7 +541,7 @@ int smf_set_exchange(smf_ctx *ctx, int level, int family, const smf_exchange *x)
   if (x->global_dof_ids) {
     std::vector<int64_t> gid(x->global_dof_ids, x->global_dof_ids + n_dofs);
     if ((e = up(&E.gid, gid))) return e;
-    if (family == 1) E.h_gid = gid;
+    if (family == 1 || n_dofs <= 8000000) E.h_gid = gid;      // (velocity: coarse levels only, for velocity_replica.cu)
     double acc[2] = {0.0, 0.0};
     for (int64_t i = 0; i < n_dofs; ++i) { acc[0] += weights[i] * (double)(gid[i] % 11); acc[1] += weights[i]; }
     if (ctx->world > 1) {          // collective: every rank calls smf_set_exchange for the same (level, family)

@@ -507,6 +507,8 @@ template <class T> static int up(smf_ctx *ctx, T **dev, const std::vector<T> &h)
 
 void lattice_free(smf_ctx *ctx)
 {
+  replica_free(ctx);             // (built on the lattice's knowledge of the rank's box)
+  ctx->replica_tried = false;
   for (auto &L : ctx->lat) {
     cudaFree(L.dof2lat); cudaFree(L.cell2lat); cudaFree(L.coef); cudaFree(L.dinv);
     cudaFree(L.x); cudaFree(L.xo); cudaFree(L.b); cudaFree(L.t); cudaFree(L.mask); cudaFree(L.if_nodes);

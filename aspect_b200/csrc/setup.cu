@@ -280,6 +280,7 @@ int smf_set_option(smf_ctx *ctx, int option, int value)
   else if (option == SMF_OPT_P2P_EXCHANGE) ctx->use_p2p = value ? 1 : 0;
   else if (option == SMF_OPT_WARP_BRICK_KERNEL) ctx->use_warp_brick = value ? 1 : 0;
   else if (option == SMF_OPT_LATTICE_VELOCITY) ctx->use_vlat = value ? 1 : 0;
+  else if (option == SMF_OPT_REPLICATE_COARSE_A) { ctx->use_replica = value ? 1 : 0; lattice_free(ctx); ctx->smoothers_ready = false; }
   else if (option == SMF_OPT_LATTICE_SCHUR) { ctx->use_lattice = value ? 1 : 0; lattice_free(ctx); ctx->smoothers_ready = false; }
   else if (option == SMF_OPT_NONSYMMETRIC_A_SOLVER) ctx->force_nonsymmetric_A = value ? 1 : 0;
   else if (option == SMF_OPT_COARSE_TAIL) { ctx->use_coarse_tail = value ? 1 : 0; if (value > 1) ctx->tail_max_cells = value; ctx->smoothers_ready = false; ctx->graph_A_stale = ctx->graph_S_stale = true; }

@@ -79,7 +79,7 @@ struct ExchangeDev {
   uint32_t *if_idx = nullptr; int *if_ptr = nullptr, *if_src = nullptr;   // rank-ordered accumulation tables
   double *weights = nullptr;                  // [n_dofs] 1 / (ranks sharing the DoF); nullptr on one rank
   int64_t *gid = nullptr; double gid_mean = 0.0;     // global DoF numbers (Chebyshev start vector)
-  std::vector<int64_t> h_gid;                        // host copy (pressure family only: schur_lattice.cu locates the rank's box in the global lattice)
+  std::vector<int64_t> h_gid;                        // host copy (pressure: schur_lattice.cu locates the rank's box in the global lattice; velocity: levels up to 8 M DoFs, velocity_replica.cu)
   // fused peer-memory transport (comm.cu): neighbour table, {epoch, counters}, this rank's inbox (2 parity buffers)
   void *p2p_tab = nullptr, *p2p_state = nullptr; double *p2p_inbox = nullptr;
 };
@@ -288,6 +288,10 @@ struct smf_ctx {
   int64_t graph_L_launches = 0, graph_L_exchanges = 0;
   int lat_tail = -1;                                  // levels 0..lat_tail of the lattice cycle run in one thread block
   double *lat_res = nullptr;                          // buffer the captured cycle leaves its result in
+  void *replica = nullptr;                            // velocity_replica.cu: replicated coarse levels of the A-block cycle (child context)
+  int replica_top = -1;                               // levels 0..replica_top of prec_A are computed redundantly on the global mesh (-1: none)
+  bool replica_tried = false;
+  int use_replica = 1;                                // SMF_OPT_REPLICATE_COARSE_A
   int use_vlat = 0;                                   // SMF_OPT_LATTICE_VELOCITY: A block of structured box levels through the TMA-staged lattice kernel
   int use_warp_brick = 0;                             // structured levels: one-warp-per-brick velocity kernel, three components per thread (SMF_OPT_WARP_BRICK_KERNEL)
   int use_pipelined = 1;                              // structured levels: persistent cp.async-pipelined velocity kernel (tests may switch it off)
@@ -368,6 +372,10 @@ int launch_schur_tail(smf_ctx *ctx, int top);
 int vlat_prepare(smf_ctx *ctx, LevelDev &L);                         // builds L.vlat if the level qualifies (else leaves it null)
 void vlat_free(LevelDev &L);
 int launch_velocity_lat(smf_ctx *ctx, LevelDev &L, double *dst, const double *src);      // A block: dst (zeroed) += A src, both in host numbering
+// velocity_replica.cu
+int replica_prepare(smf_ctx *ctx);                                   // after lattice_prepare, in smf_setup_smoothers (collective)
+int replica_cycle(smf_ctx *ctx, const double *b, double *x);         // coarse correction of prec_A below level replica_top + 1
+void replica_free(smf_ctx *ctx);
 // schur_lattice.cu
 bool lattice_cell_coords(const std::vector<uint32_t> &nodes_p, int64_t n_cells, int64_t n_p, int dims[3], std::vector<int> &cell_xyz);
 int lattice_prepare(smf_ctx *ctx);                                   // detection (once per mesh) + coefficients / diagonals (every smoother set-up)

@@ -204,6 +204,7 @@ static int level_v_step(smf_ctx *ctx, const MGSide &S, int l)
     TRY(vec_set(ctx, C.b, 0.0, lsize(ctx, S, l - 1)));
     TRY(launch_restrict_add_residual(ctx, which, l, C.b, V.b, V.t, n));      // coarse defect = R (defect - A x)
     if (!S.velocity && l - 1 == ctx->tail_level) TRY(launch_schur_tail(ctx, l - 1));      // levels 0..l-1 in one launch
+    else if (S.velocity && l - 1 == ctx->replica_top) { TRY(replica_cycle(ctx, C.b, C.x)); C.res = C.x; }      // several ranks: levels 0..l-1 on the global mesh, no exchanges
     else TRY(level_v_step_maybe_graph(ctx, S, l - 1));
     TRY(launch_prolongate(ctx, which, l, x, C.res, true));                   // x += P x_coarse
     for (int s = 0; s < S.steps; ++s) TRY(cheb_step(ctx, S, l, x, xo, V.b, V.t));   // post-smoothing
@@ -324,6 +325,7 @@ static int level_v_step_maybe_graph(smf_ctx *ctx, const MGSide &S, int l)
   const bool profiling_inside = ctx->prof_mode == 2 || (ctx->prof_mode == 1 && l == ctx->cfg.n_levels - 1);
   // the coarse tail of the Schur V-cycle: levels 0..l in one launch (coarse_tail.cu); inside a graph it is one node
   if (!ctx->use_graphs || l != ctx->graph_level || profiling_inside) return level_v_step(ctx, S, l);
+  if (S.velocity && ctx->replica_top >= 0) return level_v_step(ctx, S, l);      // (the replicated part brings its own graph; an all-reduce sits above it)
   void *&exec = S.velocity ? ctx->graph_A : ctx->graph_S;
   bool &stale = S.velocity ? ctx->graph_A_stale : ctx->graph_S_stale;
   int64_t &n_launch = S.velocity ? ctx->graph_A_launches : ctx->graph_S_launches;
@@ -375,7 +377,8 @@ static int vcycle(smf_ctx *ctx, bool velocity, double *dst, const double *src)
   // only read, so src serves as V.b; the smoothers alternate between x and xo, and the number of updates on the
   // level is known, so the buffer the result will end in is replaced by dst for the duration of the cycle.
   const Smoother &sm = (*S.sm)[L];
-  const bool replayed = ctx->use_graphs && L == ctx->graph_level && ctx->prof_mode != 2 && !(ctx->prof_mode == 1 && L == ctx->cfg.n_levels - 1);
+  const bool replayed = ctx->use_graphs && L == ctx->graph_level && ctx->prof_mode != 2 && !(ctx->prof_mode == 1 && L == ctx->cfg.n_levels - 1) &&
+                        !(velocity && ctx->replica_top >= 0);
   if (!map && dst != src && !replayed && L > 0 && sm.degree >= 2 && std::fabs(sm.delta) >= 1e-40) {
     const int swaps = (sm.degree - 1) + (S.steps - 1) * sm.degree + S.steps * sm.degree;
     double *const b0 = V.b, *const x0 = V.x, *const xo0 = V.xo;
@@ -1070,6 +1073,7 @@ int smf_setup_smoothers(smf_ctx *ctx)
     if (ctx->levels[l].n_cells <= GRAPH_MAX_CELLS) ctx->graph_level = l;
   ctx->tail_level = std::min(schur_tail_top_level(ctx), nl - 2);            // (never the finest level: its defect is the caller's vector)
   TRY(lattice_prepare(ctx));
+  TRY(replica_prepare(ctx));
   return SMF_OK;
 }
 

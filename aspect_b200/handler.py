@@ -74,6 +74,7 @@ class StokesMatrixFreeHandler:
         self.use_warp_brick_kernel = os.environ.get("SMF_WARP_BRICK", "0") == "1"    # structured levels: one warp per brick, 3 components per thread
         self.use_coarse_tail = True              # Schur V-cycle: coarse levels in one single-block kernel
         self.use_lattice_velocity = os.environ.get("SMF_LATTICE_VELOCITY", "0") == "1"   # experimental: TMA-staged A-block kernel on lattice-ordered vectors
+        self.replicate_coarse_A = os.environ.get("SMF_REPLICATE_A", "1") == "1"   # >1 rank: coarse levels of prec_A on the global mesh, no exchanges
         self.use_lattice_schur = os.environ.get("SMF_LATTICE", "1") == "1"    # Schur V-cycle on box levels in lattice order (node-centred fused kernels)
         self.use_pipelined_kernel = True         # structured levels: persistent cp.async-pipelined velocity kernel
         self.max_grid_blocks = 0                 # > 0 caps the persistent grids (tests)
@@ -148,6 +149,7 @@ class StokesMatrixFreeHandler:
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_COARSE_TAIL, int(self.use_coarse_tail)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_LATTICE_SCHUR, int(self.use_lattice_schur)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_LATTICE_VELOCITY, int(self.use_lattice_velocity)))
+        self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_REPLICATE_COARSE_A, int(self.replicate_coarse_A)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_MAX_GRID_BLOCKS, int(self.max_grid_blocks)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_P2P_EXCHANGE, int(self.p2p_exchange)))
         self._check(self.lib.smf_set_option(self.ctx, _lib.SMF_OPT_CURVED_SUMFAC, int(self.curved_sum_factorization)))
@@ -585,6 +587,10 @@ class StokesMatrixFreeHandler:
     def lattice_schur_active(self):
         """True when prec_Schur runs on the lattice path (box levels; decided by setup_smoothers)."""
         return bool(self.lib.smf_lattice_schur_active(self.ctx))
+
+    def replicated_A_levels(self):
+        """Several ranks: number of coarse prec_A levels every rank computes redundantly on the global mesh."""
+        return int(self.lib.smf_replicated_A_levels(self.ctx))
 
     def lattice_replicated_levels(self):
         """Several ranks: number of coarse Schur levels every rank computes redundantly on the global lattice."""

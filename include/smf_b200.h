@@ -64,6 +64,8 @@ const char *smf_last_error(const smf_ctx *ctx);
                                          stencil with the Chebyshev update fused, one CUDA graph per cycle (default 1; 3D, Cartesian, one viscosity per cell) */
 #define SMF_OPT_LATTICE_VELOCITY 12     /* experimental (default 0): A block of structured box levels on lattice-ordered copies of the vectors, bricks staged by
                                          TMA box loads (cp.async.bulk.tensor, x de-interleaved by the element stride) instead of node lists + cp.async */
+#define SMF_OPT_REPLICATE_COARSE_A 13   /* several ranks, box subdomains (default 1): the coarse levels of prec_A (global mesh up to 70,000 cells) are computed by every
+                                         rank on the GLOBAL mesh in a private child context -- one all-reduce per cycle instead of 9 halo exchanges per level */
 #define SMF_OPT_ORTHO_SINGLE_PASS 2   /* GMRES: CGS2 with the second projection formed from the Gram matrix (default 1); 0 = two sweeps */
 int smf_set_option(smf_ctx *ctx, int option, int value);
 /* run all work on this CUDA stream (cudaStream_t); default: a stream owned by the context */
@@ -334,7 +336,8 @@ int64_t smf_exchange_count(const smf_ctx *ctx);      /* halo exchanges performed
  * the number of pressure nodes per direction and the integer coordinates of every cell ([n_cells][3]).  Returns 1 (box), 0 (not a box). */
 int smf_detect_box_lattice(const uint32_t *cell_dofs_p, int64_t n_cells, int64_t n_dofs_p, int32_t *nodes_per_direction, int32_t *cell_xyz);
 int smf_lattice_schur_active(const smf_ctx *ctx);    /* 1: prec_Schur runs on the lattice path (SMF_OPT_LATTICE_SCHUR; decided by smf_setup_smoothers) */
-int smf_lattice_replicated_levels(const smf_ctx *ctx);   /* several ranks: coarse levels of the lattice path that every rank computes on the GLOBAL lattice (no halo exchange) */
+int smf_lattice_replicated_levels(const smf_ctx *ctx);
+int smf_replicated_A_levels(const smf_ctx *ctx);          /* several ranks: coarse levels of prec_A computed redundantly on the global mesh (SMF_OPT_REPLICATE_COARSE_A) */   /* several ranks: coarse levels of the lattice path that every rank computes on the GLOBAL lattice (no halo exchange) */
 int smf_exchange_transport(const smf_ctx *ctx);      /* 0 = single rank, 1 = NCCL send/recv, 2 = fused peer-memory kernel (CUDA IPC over NVLink) */
 /* measured FP64 pipe peak of this device (dependent-chain-free DFMA micro-kernel, best of 5 launches, CUDA events): the
  * denominator of the FP64 fractions bench.py prints next to the HBM fractions */

@@ -87,6 +87,13 @@ def run(h, hier, rhs):
     out["schur_vcycle"] = dst[1].to_host()
     out["schur_exchanges"] = h.exchange_count() - x0
     out["lattice"] = (h.lattice_schur_active(), h.lattice_replicated_levels())
+    # ... and one prec_A V-cycle (coarse levels replicated on the global mesh)
+    src[0].from_host(xu)
+    x0 = h.exchange_count()
+    h.prec_A.vmult(dst[0], src[0])
+    out["A_vcycle"] = dst[0].to_host()
+    out["A_exchanges"] = h.exchange_count() - x0
+    out["A_replicated"] = h.replicated_A_levels()
     return gu, gp, yu, yp, sol[0].to_host(), sol[1].to_host(), out
 
 
@@ -125,7 +132,8 @@ def main():
     # phase in general (inner CG solves stop at a relative 1e-2), although it happened to repeat exactly (5+46).
     strict = mode in ("gmres", "shell")
     e_vs = rel(out["schur_vcycle"], out1["schur_vcycle"][ip])
-    ok = e_op < 1e-12 and abs(its - its1) <= (1 if strict else 3) and e_sol_u < (1e-8 if strict else 1e-3) and out["converged"] and e_vs < 1e-11
+    e_va = rel(out["A_vcycle"], out1["A_vcycle"][iu])
+    ok = e_op < 1e-12 and abs(its - its1) <= (1 if strict else 3) and e_sol_u < (1e-8 if strict else 1e-3) and out["converged"] and e_vs < 1e-11 and e_va < 1e-10
     # copies of shared DoFs must be bitwise equal across ranks
     gathered = [None] * world
     dist.all_gather_object(gathered, (gu, su))
@@ -140,6 +148,7 @@ def main():
         ok = ok and bitwise
         print(f"dist_check world={world} R={R} mode={mode} transport={transport!r}: operator rel err {e_op:.2e}, iterations {out['iterations']}+{out['iterations_expensive']} (1 GPU: {out1['iterations']}+{out1['iterations_expensive']}), "
               f"velocity rel diff {e_sol_u:.2e}, pressure rel diff {e_sol_p:.2e}, prec_Schur rel diff {e_vs:.2e} (lattice path, replicated levels: {out['lattice']}, {out['schur_exchanges']} halo exchanges per cycle), "
+              f"prec_A rel diff {e_va:.2e} ({out['A_replicated']} replicated levels, {out['A_exchanges']} halo exchanges per cycle), "
               f"shared copies bitwise equal: {bitwise} -> {'OK' if ok else 'FAIL'}",
               flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
