@@ -384,7 +384,7 @@ def main():
             solver_timings = h.execute_solver_timings(rhs_np, n_timings=3, out=lambda *_: None)
             solver_timings = {k: max_over_ranks(v) for k, v in sorted(solver_timings.items())}
 
-    lattice_active, lattice_repl = h.lattice_schur_active(), h.lattice_replicated_levels()
+    lattice_active, lattice_repl, repl_A = h.lattice_schur_active(), h.lattice_replicated_levels(), h.replicated_A_levels()
     its = outs[-1]["iterations"]
     wall = t_dev / args.steps
     wall_e2e = t_e2e / args.steps
@@ -456,7 +456,9 @@ def main():
     }
     h.close()
     if world > 1 and lattice_repl:
-        line["config"]["parallelism"] += f"; Schur V-cycle: the {lattice_repl} coarsest levels replicated on every rank (global lattice, one all-reduce per cycle)"
+        line["config"]["parallelism"] += (f"; Schur V-cycle: the {lattice_repl} coarsest levels replicated on every rank (global lattice, one all-reduce per cycle)"
+                                          f"; prec_A: the {repl_A} coarsest levels replicated on every rank (global mesh in a child context, one all-reduce per cycle)")
+        line["replicated_coarse_levels"] = {"schur": lattice_repl, "A": repl_A}
     # ---- BASELINE cfg 2 (refinement 5) on the same GPU, for the apples-to-apples comparison with the CPU arm ------
     if not args.no_cfg2 and R != 5 and world == 1:
         hier5, h5, rhs5, _, _ = build_problem(5, local_rank)
