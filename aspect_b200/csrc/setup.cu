@@ -258,6 +258,8 @@ void smf_destroy(smf_ctx *ctx)
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   lattice_free(ctx);
   cudaFree(ctx->ad_in_u); cudaFree(ctx->ad_out_u); cudaFree(ctx->ad_in_p); cudaFree(ctx->ad_out_p);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h2d_event) cudaEventDestroy(ctx->h2d_event);
   if (ctx->graph_A) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_A);
   if (ctx->graph_S) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_S);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

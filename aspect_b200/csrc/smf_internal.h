@@ -243,6 +243,7 @@ struct smf_ctx {
   std::vector<double *> krylov; int64_t krylov_n = 0;
   double *tmp_u = nullptr, *tmp_p = nullptr, *tmp_u2 = nullptr, *tmp_p2 = nullptr;
   double *io_buf = nullptr; int64_t io_n = 0;         // device staging of smf_solve_host
+  cudaStream_t copy_stream = nullptr; cudaEvent_t h2d_event = nullptr; bool h2d_pending = false;   // smf_solve_host: the H2D copies overlap the smoother set-up
   int n_A_prec = 0, n_S_prec = 0;
   int n_A_exp = 0, n_S_exp = 0;                       // inner CG iterations of the expensive phase
   double *pnorm_weights = nullptr; double pnorm_area = 0.0;   // pressure normalisation: integral of every pressure shape function over the surface / volume

@@ -1201,6 +1201,12 @@ int smf_solve(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, double *
   TRY(ensure_tmp(ctx));
   SMF_CUDA(cudaStreamSynchronize(ctx->stream));
   const double t1 = now_s();
+  if (ctx->h2d_pending) {      // smf_solve_host: the vectors arrive on the copy stream
+    ctx->h2d_pending = false;
+    SMF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->h2d_event, 0));
+    TRY(launch_set_entries(ctx, sol_u, A.constrained_u, A.n_constrained_u, 0.0));
+    TRY(launch_set_entries(ctx, sol_p, A.constrained_p, A.n_constrained_p, 0.0));
+  }
   // tolerance (:1016-1025): residual with the velocity part of the guess zeroed
   const int64_t nu = A.n_u, np = A.n_p;
   TRY(ensure_krylov(ctx, 2));
@@ -1260,15 +1266,23 @@ int smf_solve_host(smf_ctx *ctx, const smf_solve_params *prm, double *sol_u, dou
   }
   double *buf = ctx->io_buf;
   double *su = buf, *sp = buf + nu, *bu = buf + nu + np, *bp = bu + nu;
-  SMF_CUDA(cudaMemcpyAsync(su, sol_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
-  SMF_CUDA(cudaMemcpyAsync(sp, sol_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
-  SMF_CUDA(cudaMemcpyAsync(bu, rhs_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->stream));
-  SMF_CUDA(cudaMemcpyAsync(bp, rhs_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->stream));
-  // get_current_constraints().set_zero(guess) (local_smoothing.cc:973): a guess that carries boundary values would put
-  // b - x into the constrained rows (unit diagonal) and change the initial residual
-  TRY(launch_set_entries(ctx, su, A.constrained_u, A.n_constrained_u, 0.0));
-  TRY(launch_set_entries(ctx, sp, A.constrained_p, A.n_constrained_p, 0.0));
+  // The right-hand side and the guess travel on a copy stream while the solve's first phase -- smoother set-up and eigenvalue
+  // estimation, which need neither -- runs on the context's stream; smf_solve waits for the event before it touches them and
+  // then zeroes the constrained entries of the guess (get_current_constraints().set_zero(guess), local_smoothing.cc:973: a guess
+  // that carries boundary values would put b - x into the constrained rows and change the initial residual).
+  if (!ctx->copy_stream) {
+    SMF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    SMF_CUDA(cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming));
+  }
+  SMF_CUDA(cudaStreamSynchronize(ctx->stream));      // (the staging buffers may still be read by work queued before this call)
+  SMF_CUDA(cudaMemcpyAsync(bu, rhs_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->copy_stream));
+  SMF_CUDA(cudaMemcpyAsync(bp, rhs_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->copy_stream));
+  SMF_CUDA(cudaMemcpyAsync(su, sol_u, sizeof(double) * nu, cudaMemcpyHostToDevice, ctx->copy_stream));
+  SMF_CUDA(cudaMemcpyAsync(sp, sol_p, sizeof(double) * np, cudaMemcpyHostToDevice, ctx->copy_stream));
+  SMF_CUDA(cudaEventRecord(ctx->h2d_event, ctx->copy_stream));
+  ctx->h2d_pending = true;
   const int rc = smf_solve(ctx, prm, su, sp, bu, bp, result);
+  if (ctx->h2d_pending) { cudaStreamSynchronize(ctx->copy_stream); ctx->h2d_pending = false; }      // (smf_solve failed before it consumed the event)
   if (rc == SMF_OK || rc == SMF_NO_CONVERGENCE) {
     cudaMemcpyAsync(sol_u, su, sizeof(double) * nu, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(sol_p, sp, sizeof(double) * np, cudaMemcpyDeviceToHost, ctx->stream);
