@@ -1799,11 +1799,26 @@ __global__ void __launch_bounds__(TSB_THREADS) prolongate_sb_kernel(const Transf
   __syncthreads();
   const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
   const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
-  for (int j = j0; j < 405; j += 32) {
-    if (!(ob[j] & 1)) continue;
-    const uint32_t idx = (le[j] & NODE_IDX_MASK) + d0;
-    const double v = sO[d0][ls[j]];
-    if (P.add) P.dst[idx] += v; else P.dst[idx] = v;
+  // x += P x_c is a read-modify-write of the fine vector: all loads of a thread first (13 independent ones in flight), then the
+  // stores -- one load -> add -> store chain per loop trip exposed the memory latency 13 times per block
+  {
+    constexpr int NIT = (405 + 31) / 32;
+    uint32_t idx[NIT];
+    double v[NIT];
+    bool w[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int j = j0 + 32 * k;
+      w[k] = j < 405 && (ob[min(j, 404)] & 1);
+      idx[k] = w[k] ? (le[j] & NODE_IDX_MASK) + d0 : 0u;
+      v[k] = w[k] ? sO[d0][ls[j]] : 0.0;
+    }
+    if (P.add) {
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) if (w[k]) v[k] += P.dst[idx[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) if (w[k]) P.dst[idx[k]] = v[k];
   }
 }
 
@@ -1825,9 +1840,23 @@ __global__ void __launch_bounds__(TSB_THREADS) restrict_sb_kernel(const Transfer
   const uint32_t *le = reinterpret_cast<const uint32_t *>(s_l);
   const uint16_t *ls = reinterpret_cast<const uint16_t *>(s_l + SB_LIST * 4);
   const int j0 = tid / 3, d0 = tid - 3 * j0;
-  for (int j = j0; j < 405; j += 32) {
-    const uint32_t idx = (le[j] & NODE_IDX_MASK) + d0;
-    sO[d0][ls[j]] = (ob[j] & 2) ? (P.minus ? P.src[idx] - P.minus[idx] : P.src[idx]) : 0.0;
+  {
+    constexpr int NIT = (405 + 31) / 32;      // all loads of a thread in flight before the first shared-memory store
+    double v[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int j = j0 + 32 * k;
+      v[k] = 0.0;
+      if (j < 405 && (ob[j] & 2)) {
+        const uint32_t idx = (le[j] & NODE_IDX_MASK) + d0;
+        v[k] = P.minus ? P.src[idx] - P.minus[idx] : P.src[idx];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int j = j0 + 32 * k;
+      if (j < 405) sO[d0][ls[j]] = v[k];
+    }
   }
   __syncthreads();
   for (int t = tid; t < 243; t += TSB_THREADS) {       // z^T: lines (d, Y, X): 5 -> 3

@@ -837,7 +837,6 @@ static int lat_cut_capture(smf_ctx *ctx, std::vector<cudaGraph_t> *segs)
   segs->push_back(g);
   return SMF_OK;
 }
-static std::vector<cudaGraph_t> *g_lat_segs = nullptr;       // segments of the capture in progress
 
 static int lat_level_step(smf_ctx *ctx, int l, double *&res)
 {
@@ -863,7 +862,7 @@ static int lat_level_step(smf_ctx *ctx, int l, double *&res)
     if (into_global) {
       // sum of the ranks' partial defects (interface nodes) = gather of the rest: every rank now holds the global coarse defect
       if (ctx->lat_capturing) {
-        TRY(lat_cut_capture(ctx, g_lat_segs));
+        TRY(lat_cut_capture(ctx, (std::vector<cudaGraph_t> *)ctx->lat_capture_segs));
         SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
       } else TRY(allreduce_sum(ctx, C.b, (int)C.n));
     } else if (C.mask && ctx->world > 1) TRY(exchange_add(ctx, C.ex, C.b));
@@ -896,14 +895,14 @@ int lattice_vcycle(smf_ctx *ctx, double *dst, const double *src)
   else {
     if (ctx->graph_L_stale) {
       std::vector<cudaGraph_t> segs;
-      g_lat_segs = &segs;
+      ctx->lat_capture_segs = &segs;
       ctx->lat_capturing = true;
       SMF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
       const int64_t l0 = ctx->launches, x0 = ctx->exchanges;
       int rc = lat_level_step(ctx, top, res);
       const int rc2 = lat_cut_capture(ctx, &segs);
       ctx->lat_capturing = false;
-      g_lat_segs = nullptr;
+      ctx->lat_capture_segs = nullptr;
       if (!rc) rc = rc2;
       if (rc) { for (cudaGraph_t g : segs) if (g) cudaGraphDestroy(g); return rc; }
       ctx->graph_L_launches = ctx->launches - l0; ctx->launches = l0;

@@ -285,6 +285,7 @@ struct smf_ctx {
   int lat_repl = -1;                                  // (no halo exchange on those levels; one all-reduce of the restricted defect per cycle)
   std::vector<void *> graph_L_seg;                    // cudaGraphExec_t of the segments of the lattice V-cycle (split at the all-reduce)
   bool lat_capturing = false;
+  void *lat_capture_segs = nullptr;                   // std::vector<cudaGraph_t> * of the capture in progress
   void *graph_L = nullptr; bool graph_L_stale = true; // (unused: kept for layout) 
   int64_t graph_L_launches = 0, graph_L_exchanges = 0;
   int lat_tail = -1;                                  // levels 0..lat_tail of the lattice cycle run in one thread block

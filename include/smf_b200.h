@@ -251,7 +251,9 @@ int smf_setup_smoothers(smf_ctx *ctx);
 /* (lambda_min_estimate, lambda_max_estimate*1.2, cg iterations) per level; which = 0 (A) / 1 (mass) */
 int smf_get_eigenvalue_estimates(smf_ctx *ctx, int level, int which, double *min_max_its);
 
-/* MGTransfer prolongate / restrict_and_add (which = 0 velocity, 1 pressure), level vectors */
+/* MGTransfer prolongate / restrict_and_add (which = 0 velocity, 1 pressure), level vectors.  On several ranks smf_restrict_add ends in
+ * the halo exchange of the coarse vector (compress(add)): dst must be zero on DoFs shared with other ranks when it is called (the
+ * V-cycles zero it), otherwise the already consistent values there are summed once more. */
 int smf_prolongate(smf_ctx *ctx, int which, int to_level, double *dst_fine, const double *src_coarse);
 int smf_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst_coarse, const double *src_fine);
 
