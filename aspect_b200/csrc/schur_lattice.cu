@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 using namespace smf;
 
@@ -108,7 +109,9 @@ __global__ void __launch_bounds__(LAT_THREADS, 4) k_lat_step(const LatStep P)
   // clamped neighbour columns; cells outside the box have coefficient zero
   const int Xm = max(X - 1, 0), Xp = min(X + 1, nx - 1), Ym = max(Y - 1, 0), Yp = min(Y + 1, ny - 1);
   const bool cxm = X > 0, cxp = X < nx - 1, cym = Y > 0, cyp = Y < ny - 1;
-  const int64_t pl = (int64_t)nx * ny, cpl = (int64_t)cx_n * cy_n;
+  // (32-bit indices throughout: a level has fewer than 2^28 pressure DoFs; the first version spent 160 of its 290 instructions
+  //  per node on 64-bit address arithmetic and ran at 56 % issue-slot utilisation)
+  const int pl = nx * ny, cpl = cx_n * cy_n;
   const int o_mm = Xm + nx * Ym, o_0m = X + nx * Ym, o_pm = Xp + nx * Ym;
   const int o_m0 = Xm + nx * Y, o_00 = X + nx * Y, o_p0 = Xp + nx * Y;
   const int o_mp = Xm + nx * Yp, o_0p = X + nx * Yp, o_pp = Xp + nx * Yp;
@@ -116,7 +119,9 @@ __global__ void __launch_bounds__(LAT_THREADS, 4) k_lat_step(const LatStep P)
   const int c_mm = max(X - 1, 0) + cx_n * max(Y - 1, 0), c_pm = min(X, cx_n - 1) + cx_n * max(Y - 1, 0);
   const int c_mp = max(X - 1, 0) + cx_n * min(Y, cy_n - 1), c_pp = min(X, cx_n - 1) + cx_n * min(Y, cy_n - 1);
   const auto load_plane = [&](int Z, double (&a)[9]) {
-    const double *p = xs + pl * min(max(Z, 0), nz - 1);
+    long long zo = (long long)pl * min(max(Z, 0), nz - 1);
+    asm volatile("" : "+l"(zo));     // (opaque plane offset: the plane pointer is formed once, every load is one IMAD.WIDE + LDG instead of a 64-bit add chain)
+    const double *__restrict__ p = xs + zo;
     a[0] = p[o_mm]; a[1] = p[o_0m]; a[2] = p[o_pm]; a[3] = p[o_m0]; a[4] = p[o_00]; a[5] = p[o_p0]; a[6] = p[o_mp]; a[7] = p[o_0p]; a[8] = p[o_pp];
   };
   // q[k]: x-y partial sums of a node plane for cell column k (mm, pm, mp, pp), weights 2 towards (X, Y)
@@ -129,29 +134,33 @@ __global__ void __launch_bounds__(LAT_THREADS, 4) k_lat_step(const LatStep P)
   };
   const auto load_coefs = [&](int cz, double (&k)[4]) {
     const bool in = cz >= 0 && cz < nz - 1;
-    const double *c = cf + cpl * min(max(cz, 0), nz - 2);
+    long long co = (long long)cpl * min(max(cz, 0), nz - 2);
+    asm volatile("" : "+l"(co));
+    const double *__restrict__ c = cf + co;
     k[0] = (in && cxm && cym) ? c[c_mm] : 0.0; k[1] = (in && cxp && cym) ? c[c_pm] : 0.0;
     k[2] = (in && cxm && cyp) ? c[c_mp] : 0.0; k[3] = (in && cxp && cyp) ? c[c_pp] : 0.0;
   };
-  double a0[9], a1[9], an[9], q0[4], q1[4], q2[4], k0[4], k1[4], kn[4];
+  // q[s][k]: plane sums of three consecutive node planes, kc[s][k]: coefficients of three consecutive cell layers; the roles
+  // (previous / current / next) rotate through the slots with the phase of the step, so the march is unrolled three times and no
+  // register is ever copied (the rotating copies were 40 of the ~240 instructions per node)
+  double a0[9], a1[9], an[9], q[3][4], kc[3][4];
   load_plane(Z0 - 1, a0); load_plane(Z0, a1); load_plane(Z0 + 1, an);
-  load_coefs(Z0 - 1, k0); load_coefs(Z0, kn);
-  int64_t i = o_00 + pl * Z0;
+  load_coefs(Z0 - 1, kc[0]); load_coefs(Z0, kc[1]);
+  int i = o_00 + pl * Z0;
   double bn = MODE != 0 ? bs[i] : 0.0, xon = (MODE == 1 && P.use_xo) ? P.xo[i] : 0.0;
   unsigned char mn = mk ? mk[i] : 0;
-  plane_sums(a0, q0); plane_sums(a1, q1);
+  plane_sums(a0, q[0]); plane_sums(a1, q[1]);
   double xc1 = a1[4];
-  for (int Z = Z0; Z < Z1; ++Z, i += pl) {
-    // take what was prefetched ...
-    plane_sums(an, q2);
+  // one node: phase PH = (Z - Z0) mod 3; slots: planes Z-1, Z, Z+1 -> q[PH], q[PH+1], q[PH+2]; layers Z-1, Z -> kc[PH], kc[PH+1];
+  // the layer prefetched for the next node goes to kc[PH+2]
+  const auto step = [&](auto phase, int Z) {
+    constexpr int PH = decltype(phase)::value, S0 = PH % 3, S1 = (PH + 1) % 3, S2 = (PH + 2) % 3;
+    plane_sums(an, q[S2]);
     const double xc2 = an[4], bv = bn, xov = xon;
     const bool shared = mn & 1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) k1[k] = kn[k];
-    // ... and start the loads of the next node
-    if (Z + 1 < Z1) {
+    if (Z + 1 < Z1) {      // start the loads of the next node before anything of this one is consumed
       load_plane(Z + 2, an);
-      load_coefs(Z + 1, kn);
+      load_coefs(Z + 1, kc[S2]);
       if (MODE != 0) bn = bs[i + pl];
       if (MODE == 1 && P.use_xo) xon = P.xo[i + pl];
       if (mk) mn = mk[i + pl];
@@ -159,23 +168,28 @@ __global__ void __launch_bounds__(LAT_THREADS, 4) k_lat_step(const LatStep P)
     double acc = 0.0, ksum = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      acc = fma(k0[k], fma(2.0, q1[k], q0[k]), acc);      // cell layer Z-1: node planes Z-1, Z
-      acc = fma(k1[k], fma(2.0, q1[k], q2[k]), acc);      // cell layer Z:   node planes Z, Z+1
-      ksum += k0[k] + k1[k];
+      acc = fma(kc[S0][k], fma(2.0, q[S1][k], q[S0][k]), acc);      // cell layer Z-1: node planes Z-1, Z
+      acc = fma(kc[S1][k], fma(2.0, q[S1][k], q[S2][k]), acc);      // cell layer Z:   node planes Z, Z+1
+      ksum += kc[S0][k] + kc[S1][k];
     }
     if (MODE == 0 || shared) P.t[i] = acc;
     else if (MODE == 2) P.t[i] = bv - acc;
     else {
       // diagonal of the mass matrix = 8 x (sum of the coefficients of the cells around the node): no D^-1 stream
-      // (MassMatrixOperator::compute_diagonal, matrix_free_operators.cc:861-908, in closed form)
-      double v = xc1 + P.f2 * (bv - acc) / (8.0 * ksum);
+      // (MassMatrixOperator::compute_diagonal, matrix_free_operators.cc:861-908, in closed form); reciprocal + multiply:
+      // a quarter of the instructions of an IEEE division
+      double v = xc1 + P.f2 * (bv - acc) * __drcp_rn(8.0 * ksum);
       if (P.use_xo) v += P.f1 * (xc1 - xov);
       else v += P.f1 * xc1;
       P.xo[i] = v;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { q0[k] = q1[k]; q1[k] = q2[k]; k0[k] = k1[k]; }
     xc1 = xc2;
+    i += pl;
+  };
+  for (int Z = Z0; Z < Z1; Z += 3) {
+    step(std::integral_constant<int, 0>(), Z);
+    if (Z + 1 < Z1) step(std::integral_constant<int, 1>(), Z + 1);
+    if (Z + 2 < Z1) step(std::integral_constant<int, 2>(), Z + 2);
   }
 }
 // the interface nodes after the exchange: t holds the complete M x
