@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--refinement", type=int, default=int(os.environ.get("SMF_BENCH_REFINEMENT", "7")),
                     help="global refinement per GPU (7 = north-star single-GPU target; 8 GPUs x 7 = BASELINE cfg 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the N-rank = 1-rank parity block")
+    ap.add_argument("--parity-refinement", type=int, default=4, help="N > 1: refinement per tree of the parity block")
     ap.add_argument("--no-solver-timings", action="store_true", help="skip the Execute-solver-timings harness (incl. the IDR(2) solve)")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the extra BASELINE cfg 2 (refinement 5) solve")
     ap.add_argument("--convbox-refinement", type=int, default=5, help="global refinement of the extra BASELINE cfg 4 (convection box) block")
@@ -601,6 +603,16 @@ def main():
             h4a.close()
         except Exception as exc:
             line["cfg4_convection_box_3d_adaptive"] = {"error": repr(exc)}
+    # ---- N > 1: the N-rank run against ONE rank on the same global mesh (tools/dist_check.py: operator 1e-12, iterations +-1,
+    #      solution 1e-8, both V-cycles, copies of shared DoFs bitwise equal), at a size rank 0 solves alone in seconds; outside
+    #      the timed region, every rank takes part (collective) ----
+    if world > 1 and not args.no_parity:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import dist_check
+            line["multi_gpu_parity"] = dist_check.parity(args.parity_refinement, "gmres")
+        except Exception as exc:            # must be collective-safe: every rank fails or none (same code, same inputs)
+            line["multi_gpu_parity"] = {"ok": False, "error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_steps(R, 2, 1, *cpu_inputs)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "model_check", "implementation")}

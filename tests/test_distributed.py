@@ -97,3 +97,99 @@ def test_two_gpu_shell_solve_matches_one_gpu():
            "--master-port", "29521", os.path.join(ROOT, "tools", "dist_check.py"), "2", "shell"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _gids(L, dim=3):
+    gu = L.global_node_ids("u")
+    return (gu[:, None] * dim + np.arange(dim)[None, :]).ravel(), L.global_node_ids("p")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rep,world", [((2, 1, 1), 2), ((2, 2, 1), 4)])
+def test_subdomains_on_one_gpu_sum_to_the_global_operators(rep, world):
+    """The partition on ONE device (runs on a 1-GPU box): the subdomains of all `world` ranks live in `world` single-rank
+    contexts, the host plays the halo exchange (sum of the per-rank partial sums over the partition-independent DoF numbers,
+    = what k_exchange_p2p / NCCL do between the ranks), and the result must be the operator of the global mesh held by one more
+    context: active Stokes operator, A block and pressure mass matrix of every level, inverse diagonals.  What this does not
+    cover is the transport itself (tests above, >= 2 GPUs; tools/dist_check.py inside bench.py at N > 1)."""
+    from aspect_b200 import StokesMatrixFreeHandler, benchmarks, synthetic
+    from util import rel
+    R, avg = 2, "harmonic average"
+
+    def context(rank, nranks):
+        hier = synthetic.BoxHierarchy(3, R, None, rep, rank, nranks)
+        eta_q, _, ps = benchmarks.nsinker_problem(hier, 8, 1e4, avg)
+        hier.rank, hier.world = 0, 1                    # the handler sees one rank: no communicator, operators leave partial sums
+        h = StokesMatrixFreeHandler(3, device=0)
+        h.setup_dofs(hier, "zero")
+        h.assemble(eta_q, avg, ps)
+        h.build_preconditioner()
+        return hier, h
+
+    hg, Hg = context(0, 1)
+    subs = [context(r, world) for r in range(world)]
+    assert sum(s[0].active.n_cells for s in subs) == hg.active.n_cells
+
+    def check(level_of, apply, family, salt, diag=None):
+        Lg = level_of(hg)
+        gid_g = _gids(Lg)[family]
+        n_glob = int(gid_g.max()) + 1
+        x_glob = np.sin(0.37 * np.arange(n_glob) + salt)
+        cons_g = np.zeros(n_glob, bool)
+        if family == 0:
+            cons_g[gid_g[Lg.constrained_u("zero").astype(np.int64)]] = True
+            x_glob[cons_g] = 0.0
+        y_ref = np.zeros(n_glob); y_ref[gid_g] = apply(Hg, x_glob[gid_g], Lg)
+        y_sum = np.zeros(n_glob)
+        for hs, Hs in subs:
+            Ls = level_of(hs)
+            gid = _gids(Ls)[family]
+            if family == 0:                             # each rank constrains exactly the global boundary DoFs it holds
+                mine = np.zeros(n_glob, bool); mine[gid[Ls.constrained_u("zero").astype(np.int64)]] = True
+                assert np.array_equal(mine[gid], cons_g[gid])
+            y = apply(Hs, x_glob[gid], Ls)
+            assert len(np.unique(gid)) == len(gid)
+            y_sum[gid] += y
+        free = ~cons_g
+        assert rel(y_sum[free], y_ref[free]) < 1e-12, (family, salt)
+
+    def vec(H, x, block, l):
+        return H.initialize_dof_vector(block, l).from_host(x), H.initialize_dof_vector(block, l)
+
+    def stokes(H, xu, xp):
+        src, dst = H.initialize_dof_vector(), H.initialize_dof_vector()
+        src[0].from_host(xu); src[1].from_host(xp)
+        H.stokes_matrix.vmult(dst, src)
+        return dst[0].to_host(), dst[1].to_host()
+
+    # active Stokes operator: both blocks of the result
+    from aspect_b200 import SMF_ACTIVE
+    Lg = hg.active
+    gu_g, gp_g = _gids(Lg)
+    nu_glob, np_glob = int(gu_g.max()) + 1, int(gp_g.max()) + 1
+    xu_glob, xp_glob = np.sin(0.37 * np.arange(nu_glob) + 1.0), np.sin(0.37 * np.arange(np_glob) + 2.0)
+    cons = np.zeros(nu_glob, bool); cons[gu_g[Lg.constrained_u("zero").astype(np.int64)]] = True
+    xu_glob[cons] = 0.0
+    yu_ref, yp_ref = np.zeros(nu_glob), np.zeros(np_glob)
+    a, b = stokes(Hg, xu_glob[gu_g], xp_glob[gp_g]); yu_ref[gu_g] = a; yp_ref[gp_g] = b
+    yu_sum, yp_sum = np.zeros(nu_glob), np.zeros(np_glob)
+    for hs, Hs in subs:
+        gu, gp = _gids(hs.active)
+        a, b = stokes(Hs, xu_glob[gu], xp_glob[gp])
+        yu_sum[gu] += a; yp_sum[gp] += b
+    assert rel(yu_sum[~cons], yu_ref[~cons]) < 1e-12 and rel(yp_sum, yp_ref) < 1e-12
+
+    # level operators and diagonals
+    for l in range(R + 1):
+        def A(H, x, L, l=l):
+            s, d = vec(H, x, 0, l); H.mg_matrices_A_block[l].vmult(d, s); return d.to_host()
+
+        def M(H, x, L, l=l):
+            s, d = vec(H, x, 1, l); H.mg_matrices_Schur_complement[l].vmult(d, s); return d.to_host()
+        check(lambda h, l=l: h.levels[l], A, 0, 10.0 + l)
+        check(lambda h, l=l: h.levels[l], M, 1, 20.0 + l)
+        # diagonals: the per-rank diagonals are partial sums as well (the distributed set-up exchanges them before inverting)
+        check(lambda h, l=l: h.levels[l], lambda H, x, L, l=l: 1.0 / H.get_matrix_diagonal_inverse(l, 0), 0, 0.0)
+        check(lambda h, l=l: h.levels[l], lambda H, x, L, l=l: 1.0 / H.get_matrix_diagonal_inverse(l, 1), 1, 0.0)
+    for _, H in subs + [(hg, Hg)]:
+        H.close()

@@ -34,8 +34,8 @@ def setup_shell(R, rank, world, avg):
     return hier, h, force_q
 
 
-def setup(R, rep, rank, world, avg):
-    if len(sys.argv) > 2 and sys.argv[2] == "shell":
+def setup(R, rep, rank, world, avg, mode="gmres"):
+    if mode == "shell":
         return setup_shell(R, rank, world, avg)
     hier = synthetic.BoxHierarchy(3, R, None, rep, rank, world)
     eta_q, rhs, ps = benchmarks.nsinker_problem(hier, 8, 1e4, avg)
@@ -45,7 +45,6 @@ def setup(R, rep, rank, world, avg):
     h.assemble(eta_q, avg, ps)
     h.build_preconditioner()
     h.parameters.update({"Linear solver tolerance": 1e-6, "Number of cheap Stokes solver steps": 200})
-    mode = sys.argv[2] if len(sys.argv) > 2 else "gmres"
     if mode == "idr":            # shadow vectors hashed from the global DoF numbers: partition independent
         h.parameters["Krylov method for cheap solver steps"] = "IDR(s)"
     elif mode == "expensive":    # 5 cheap steps, then FGMRES with inner CG solves (weighted inner products on every rank)
@@ -97,22 +96,18 @@ def run(h, hier, rhs):
     return gu, gp, yu, yp, sol[0].to_host(), sol[1].to_host(), out
 
 
-def main():
-    R = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    avg = "harmonic average"
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29513")
-    os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
-    dist.init_process_group("nccl" if world > 1 else "gloo", device_id=torch.device("cuda", torch.cuda.current_device()) if world > 1 else None)
+def parity(R, mode="gmres", avg="harmonic average"):
+    """The check itself, inside an initialised process group (one rank per GPU): returns the figures as a dict (identical on
+    every rank).  Used by main() below and by bench.py at N > 1 (`multi_gpu_parity` of the bench line)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
     rep = REPS[world]
-    hier, h, rhs = setup(R, rep, rank, world, avg)
+    hier, h, rhs = setup(R, rep, rank, world, avg, mode)
     gu, gp, yu, yp, su, sp, out = run(h, hier, rhs)
     transport = h.exchange_transport()
     h.close()
     ref = [None]
     if rank == 0:
-        hier1, h1, rhs1 = setup(R, rep, 0, 1, avg)
+        hier1, h1, rhs1 = setup(R, rep, 0, 1, avg, mode)
         ref[0] = run(h1, hier1, rhs1)
         h1.close()
     dist.broadcast_object_list(ref, src=0)
@@ -120,42 +115,66 @@ def main():
     pu, pp = np.argsort(gu1), np.argsort(gp1)
     iu, ip = pu[np.searchsorted(gu1[pu], gu)], pp[np.searchsorted(gp1[pp], gp)]
     rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
-    e_op = max(rel(yu, yu1[iu]), rel(yp, yp1[ip]))
-    e_sol_u = rel(su, su1[iu])
+    # every figure is the maximum over the ranks
+    def worst(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    e_op = worst(max(rel(yu, yu1[iu]), rel(yp, yp1[ip])))
+    e_sol_u = worst(rel(su, su1[iu]))
     # no-slip box: pressure up to a constant
-    e_sol_p = rel(sp - sp.mean() + sp1[ip].mean(), sp1[ip])
-    mode = sys.argv[2] if len(sys.argv) > 2 else "gmres"
+    e_sol_p = worst(rel(sp - sp.mean() + sp1[ip].mean(), sp1[ip]))
     its, its1 = out["iterations"] + out["iterations_expensive"], out1["iterations"] + out1["iterations_expensive"]
     # GMRES repeats the 1-GPU run (same iterations, 1e-15).  IDR(s) is a short-recurrence method: the different
     # summation order of a different partition is amplified from step to step, so the two runs leave each other's path
     # after ~20 steps (measured: 28 vs 30 iterations) and agree to the solver tolerance only; same for the expensive
     # phase in general (inner CG solves stop at a relative 1e-2), although it happened to repeat exactly (5+46).
     strict = mode in ("gmres", "shell")
-    e_vs = rel(out["schur_vcycle"], out1["schur_vcycle"][ip])
-    e_va = rel(out["A_vcycle"], out1["A_vcycle"][iu])
+    e_vs = worst(rel(out["schur_vcycle"], out1["schur_vcycle"][ip]))
+    e_va = worst(rel(out["A_vcycle"], out1["A_vcycle"][iu]))
     ok = e_op < 1e-12 and abs(its - its1) <= (1 if strict else 3) and e_sol_u < (1e-8 if strict else 1e-3) and out["converged"] and e_vs < 1e-11 and e_va < 1e-10
     # copies of shared DoFs must be bitwise equal across ranks
     gathered = [None] * world
-    dist.all_gather_object(gathered, (gu, su))
+    dist.all_gather_object(gathered, (gu[::97], su[::97]))
+    table = {}
+    bitwise = True
+    for g, s in gathered:
+        for k, v in zip(g.tolist(), s.tolist()):
+            if k in table and table[k] != v:
+                bitwise = False
+            table[k] = v
+    ok = bool(ok and bitwise)
+    return {"ok": ok, "world": world, "refinement_per_tree": R, "mode": mode, "transport": transport,
+            "operator_rel_err": e_op, "iterations": [out["iterations"], out["iterations_expensive"]],
+            "iterations_1gpu": [out1["iterations"], out1["iterations_expensive"]],
+            "velocity_rel_diff": e_sol_u, "pressure_rel_diff": e_sol_p,
+            "prec_Schur_rel_diff": e_vs, "prec_A_rel_diff": e_va, "shared_copies_bitwise_equal": bitwise,
+            "lattice": list(out["lattice"]), "schur_exchanges_per_cycle": out["schur_exchanges"],
+            "A_replicated_levels": out["A_replicated"], "A_exchanges_per_cycle": out["A_exchanges"],
+            "tolerances": {"operator": 1e-12, "iterations": 1 if strict else 3, "velocity": 1e-8 if strict else 1e-3,
+                           "prec_Schur": 1e-11, "prec_A": 1e-10}}
+
+
+def main():
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    mode = sys.argv[2] if len(sys.argv) > 2 else "gmres"
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29513")
+    os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+    dist.init_process_group("nccl" if world > 1 else "gloo", device_id=torch.device("cuda", torch.cuda.current_device()) if world > 1 else None)
+    r = parity(R, mode)
     if rank == 0:
-        table = {}
-        bitwise = True
-        for g, s in gathered:
-            for k, v in zip(g[::97], s[::97]):
-                if k in table and table[k] != v:
-                    bitwise = False
-                table[k] = v
-        ok = ok and bitwise
-        print(f"dist_check world={world} R={R} mode={mode} transport={transport!r}: operator rel err {e_op:.2e}, iterations {out['iterations']}+{out['iterations_expensive']} (1 GPU: {out1['iterations']}+{out1['iterations_expensive']}), "
-              f"velocity rel diff {e_sol_u:.2e}, pressure rel diff {e_sol_p:.2e}, prec_Schur rel diff {e_vs:.2e} (lattice path, replicated levels: {out['lattice']}, {out['schur_exchanges']} halo exchanges per cycle), "
-              f"prec_A rel diff {e_va:.2e} ({out['A_replicated']} replicated levels, {out['A_exchanges']} halo exchanges per cycle), "
-              f"shared copies bitwise equal: {bitwise} -> {'OK' if ok else 'FAIL'}",
+        print(f"dist_check world={world} R={R} mode={mode} transport={r['transport']!r}: operator rel err {r['operator_rel_err']:.2e}, "
+              f"iterations {r['iterations'][0]}+{r['iterations'][1]} (1 GPU: {r['iterations_1gpu'][0]}+{r['iterations_1gpu'][1]}), "
+              f"velocity rel diff {r['velocity_rel_diff']:.2e}, pressure rel diff {r['pressure_rel_diff']:.2e}, "
+              f"prec_Schur rel diff {r['prec_Schur_rel_diff']:.2e} (lattice path, replicated levels: {tuple(r['lattice'])}, {r['schur_exchanges_per_cycle']} halo exchanges per cycle), "
+              f"prec_A rel diff {r['prec_A_rel_diff']:.2e} ({r['A_replicated_levels']} replicated levels, {r['A_exchanges_per_cycle']} halo exchanges per cycle), "
+              f"shared copies bitwise equal: {r['shared_copies_bitwise_equal']} -> {'OK' if r['ok'] else 'FAIL'}",
               flush=True)
-    flag = torch.tensor([0 if ok else 1], device="cuda")
-    if world > 1:
-        dist.all_reduce(flag)
     dist.destroy_process_group()
-    sys.exit(int(flag.item() > 0))
+    sys.exit(0 if r["ok"] else 1)
 
 
 if __name__ == "__main__":
