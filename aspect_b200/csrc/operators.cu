@@ -538,6 +538,14 @@ template <int C, int B> __host__ __device__ constexpr int rot_actual(int m)
 // index in the frame of warp c-1 of the point with index m in the frame of warp c
 __host__ __device__ constexpr int xperm(int m) { return (m / 9) + 3 * (m % 3) + 9 * ((m / 3) % 3); }
 
+// one DoF of a brick's flush without branches: plain store (private to the brick), RED (shared with other bricks) or nothing
+__device__ __forceinline__ void flush_dof(double *addr, double v, bool store, bool red)
+{
+  asm volatile("{\n\t.reg .pred ps, pr;\n\tsetp.ne.u32 ps, %2, 0;\n\tsetp.ne.u32 pr, %3, 0;\n\t"
+               "@ps st.global.f64 [%0], %1;\n\t@pr red.global.add.f64 [%0], %1;\n\t}"
+               ::"l"(addr), "d"(v), "r"((unsigned)store), "r"((unsigned)red) : "memory");
+}
+
 constexpr int SBK_THREADS = 96;
 constexpr int SBK_SU = 13;            // ceil(3 * 405 / 96) staged items per thread
 constexpr size_t sbk_smem_bytes(int mode)
@@ -809,36 +817,28 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
       const double *sBd = sB + d0 * MU;
       double *dstd = P.dst_u + d0;
       const int n_private = (int)le[405];
-      constexpr int SUBB = 4;
-#pragma unroll 1
-      for (int k0 = 0; k0 < 12; k0 += SUBB) {
-        uint32_t e[SUBB], sl[SUBB];
-        double v[SUBB];
+      // u and T are dead here: all list reads of the thread first, then all value reads, then straight-line predicated
+      // stores / REDs (flush_dof) -- the branchy version (store / RED / skip per item, three sub-batches) held 18 % of the
+      // kernel's stall samples on its BSSY / BRA / BSYNC sequences
+      constexpr int NF = 12;
+      uint32_t e[NF], sl[NF];
+      double v[NF];
 #pragma unroll
-        for (int k = 0; k < SUBB; ++k) {
-          const int j = j0 + 32 * (k0 + k);
-          e[k] = le[j]; sl[k] = ls[j];
-        }
+      for (int k = 0; k < NF; ++k) { const int j = j0 + 32 * k; e[k] = le[j]; sl[k] = ls[j]; }
 #pragma unroll
-        for (int k = 0; k < SUBB; ++k) v[k] = sBd[sl[k]];
+      for (int k = 0; k < NF; ++k) v[k] = sBd[sl[k]];
 #pragma unroll
-        for (int k = 0; k < SUBB; ++k) {
-          const int j = j0 + 32 * (k0 + k);
-          const bool cons = (e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u;
-          if (!cons) {
-            if (j < n_private) dstd[e[k] & NODE_IDX_MASK] = v[k];
-            else atomicAdd(dstd + (e[k] & NODE_IDX_MASK), v[k]);
-          }
-        }
+      for (int k = 0; k < NF; ++k) {
+        const int j = j0 + 32 * k;
+        const bool free_dof = !((e[k] >> (NODE_FLAG_SHIFT + d0)) & 1u);
+        flush_dof(dstd + (e[k] & NODE_IDX_MASK), v[k], free_dof && j < n_private, free_dof && j >= n_private);
       }
       if (j0 < 405 - 384) {
         const int j = j0 + 384;
-        const uint32_t e = le[j];
-        const double v = sBd[ls[j]];
-        if (!((e >> (NODE_FLAG_SHIFT + d0)) & 1u)) {
-          if (j < n_private) dstd[e & NODE_IDX_MASK] = v;
-          else atomicAdd(dstd + (e & NODE_IDX_MASK), v);
-        }
+        const uint32_t e1 = le[j];
+        const double v1 = sBd[ls[j]];
+        const bool free_dof = !((e1 >> (NODE_FLAG_SHIFT + d0)) & 1u);
+        flush_dof(dstd + (e1 & NODE_IDX_MASK), v1, free_dof && j < n_private, free_dof && j >= n_private);
       }
     }
   }
