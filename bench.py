@@ -427,7 +427,7 @@ def main():
                 "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
                 "call": "StokesMatrixFreeHandler.solve -> smf_solve_host (pinned host rhs + guess in, solution out)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "velocity_kernel<3,0> (A block, finest level)", "achieved": bytes_A / t_A_kernel / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "velocity_sb_kernel<0> (A block, finest level)", "achieved": bytes_A / t_A_kernel / 1e9,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes_A / t_A_kernel / 1e9 / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": bytes_A, "launches_timed": a_cnt,
                      "avg_launch_us": t_A_kernel * 1e6, "share_of_solve": a_ms / 1e3 / t_dev,
