@@ -758,7 +758,8 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
           dq[a] *= f * qweight<DIM>(a); dq[b2] *= f * qweight<DIM>(b2); dq[c2_] *= f * qweight<DIM>(c2_);
         });
         quad_to_q1T<DIM>(dq, yv);
-        if (c == 0) sb_park_p<0>(yv, myB + lane); else if (c == 1) sb_park_p<1>(yv, myB + lane); else sb_park_p<2>(yv, myB + lane);
+        const int pc = x + 4 * y + 16 * z;      // lexicographic cell number within the brick
+        if (c == 0) sb_park_p<0>(yv, myB + pc); else if (c == 1) sb_park_p<1>(yv, myB + pc); else sb_park_p<2>(yv, myB + pc);
       }
     }
     if (MODE != 2) {
@@ -776,8 +777,12 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
     cp_async_commit();
     if (MODE == 1 && tid < 75) {
       // pressure rows: lattice node tid sums the shares of the (up to 8) cells around it, all components, in a fixed
-      // order, and goes straight to global memory (private node: store, shared: RED, constrained: dst = src)
+      // order, and goes straight to global memory (private node: store, shared: RED, constrained: dst = src).  The
+      // shares are parked by LEXICOGRAPHIC cell number (x + 4 y + 16 z, not by lane), so the eight reads are one base
+      // address plus compile-time offsets: with lane-ordered parking the kernel kept four loop-invariant addresses,
+      // spilled them, and the reload in front of the first read held 7 % of the stall samples.
       const int X = tid % 5, Y = (tid / 5) % 5, Z = tid / 25;
+      const double *pk = sB + (X + 4 * Y + 16 * Z);
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
@@ -787,9 +792,8 @@ __global__ void __launch_bounds__(SBK_THREADS, 4) velocity_sb_kernel(const CellP
           for (int i = 0; i < 2; ++i) {
             const int cx = X - i, cy = Y - j, cz = Z - k;
             if (cx >= 0 && cx < 4 && cy >= 0 && cy < 4 && cz >= 0 && cz < 2) {
-              const int ln = (cx & 1) | ((cy & 1) << 1) | (cz << 2) | ((cx >> 1) << 3) | ((cy >> 1) << 4);
-              const int off = (i + 2 * j + 4 * k) * SUB + ln;
-              acc += sB[off] + sB[MU + off] + sB[2 * MU + off];
+                      const int off = (i + 2 * j + 4 * k) * SUB - (i + 4 * j + 16 * k);
+              acc += pk[off] + pk[MU + off] + pk[2 * MU + off];
             }
           }
       const uint32_t e = reinterpret_cast<const uint32_t *>(I_cur + SB_LIST_BYTES)[tid];
