@@ -180,3 +180,45 @@ def test_hollow_sphere_project_q1_golden():
     err = hs.errors(L, u, p, m)
     for got, want in zip(err, g["errors_uL1_pL1_uL2_pL2"][0]):
         assert abs(got / float(want) - 1.0) < 2e-6, (err, g["errors_uL1_pL1_uL2_pL2"][0])
+
+
+def _no_normal_flux_solve(r_zero, r_flux):
+    from oracle import no_normal_flux as nnf, solver
+    R0, R1 = 3481000.0, 6336000.0
+    h = oshell.ShellHierarchy(1, R0, R1)
+    L = h.active
+    eta_q, force_q, ps = nnf.shell_3d_gmg_problem(h, R0, R1)
+    active, levels, _, _ = coeff.viscosity_tables(h, eta_q, "harmonic")
+    be = nnf.NoNormalFluxBackend(h, active, levels, ps, {"inner": R0, None: None}[r_zero], {"outer": R1, "both": (R0, R1)}[r_flux])
+    rhs = np.concatenate([be.condense_rhs(assembled.rhs_force(L, force_q)), np.zeros(L.n_p)])
+    hist = []
+    out = solver.BlockGMGStokes(be).solve(rhs, tol_rel=1e-4, restart=100, max_its=200, history=hist)
+    u = be.distribute(out["x"][:L.n_u]).reshape(-1, 3)
+    top = nnf.boundary_nodes(L, R1)
+    n = L.node_x_u[top] / np.linalg.norm(L.node_x_u[top], axis=1)[:, None]
+    assert np.abs((u[top] * n).sum(axis=1)).max() < 1e-12 * np.abs(u).max()          # no flux through the outer boundary
+    return L, out, np.array(hist, float)
+
+
+def test_shell_3d_gmg_local_smoothing_golden():
+    """tests/shell_3d_gmg (first solve): the ONE local-smoothing golden the reference holds on the 96-cell shell mesh of BASELINE
+    cfg 3 refined once (768 cells, 20,790 + 970 DoFs) -- zero velocity at the bottom, tangential at the top (no-normal-flux lines
+    on the active level and on every multigrid level), constant viscosity, PREM gravity, tolerance 1e-4: 24+0 iterations.
+    The restatement (oracle/no_normal_flux.py on top of the unchanged smoothers / transfers / GMRES of oracle/solver.py) takes 25."""
+    g = golden("shell_3d_gmg")
+    L, out, hist = _no_normal_flux_solve("inner", "outer")
+    assert [L.n_u, L.n_p] == g["dofs_u_p"][0] and L.n_cells == g["active_cells"][0]
+    assert out["converged"] and abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 1, out["iterations"]
+
+
+def test_gmg_no_normal_flux_only_golden_sits_on_a_plateau():
+    """tests/gmg_no_normal_flux_only (first solve; tangential velocity on BOTH boundaries, rotations in the null space):
+    30+0 iterations in the reference, 28 here.  Not claimed as +-1: the residual history ends in a plateau that sits 0.6 %
+    above the stopping tolerance (iterations 24 .. 27: 4.356e19, 4.355e19, 4.350e19, 4.268e19 against 4.242e19), so the count
+    is decided by the last per cent of the residual norm; asserted is the plateau itself and a count within 3."""
+    g = golden("gmg_no_normal_flux_only")
+    L, out, hist = _no_normal_flux_solve(None, "both")
+    assert [L.n_u, L.n_p] == g["dofs_u_p"][0]
+    assert out["converged"] and abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 3, out["iterations"]
+    tol = out["tolerance"]
+    assert hist[-2] < 1.02 * tol and hist[-5] < 1.05 * tol          # four iterations within 5 % of the tolerance before it is met
