@@ -97,6 +97,9 @@ namespace aspect_b200
       int idr_s_parameter = 2;
       double linear_solver_A_block_tolerance = 1e-2;
       double linear_solver_S_block_tolerance = 1e-6;
+      /** "Stokes GMG type = global coarsening" (parameters.cc:448-453): on uniformly refined meshes the coarsening sequence is the
+          sequence of refinement levels and this hierarchy serves both types (handler.py::_check_gmg_type); name() follows. */
+      bool global_coarsening = false;
     } parameters;
 
     explicit StokesMatrixFreeHandlerB200(int dim, int device = 0) : dim(dim), device(device) {}
@@ -104,7 +107,7 @@ namespace aspect_b200
     StokesMatrixFreeHandlerB200(const StokesMatrixFreeHandlerB200 &) = delete;
     StokesMatrixFreeHandlerB200 &operator=(const StokesMatrixFreeHandlerB200 &) = delete;
 
-    std::string name() const { return "GMG"; }
+    std::string name() const { return parameters.global_coarsening ? "GMG-GC" : "GMG"; }
 
     /** setup_dofs() (local_smoothing.cc:1450-1851): index maps, constraints, geometry, transfers of every level */
     void setup_dofs(const HierarchyArrays &h)

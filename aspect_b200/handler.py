@@ -90,6 +90,7 @@ class StokesMatrixFreeHandler:
             "Number of cheap Stokes solver steps": 1000,
             "Maximum number of expensive Stokes solver steps": 1000,
             "GMRES solver restart length": 100,
+            "Stokes GMG type": "local smoothing",                 # or "global coarsening": uniformly refined meshes only (setup_dofs)
             "Krylov method for cheap solver steps": "GMRES",      # or "IDR(s)"
             "IDR(s) parameter": 2,
             "Linear solver A block tolerance": 1e-2,
@@ -100,7 +101,23 @@ class StokesMatrixFreeHandler:
         }
 
     def name(self):
-        return "GMG"
+        """`StokesSolver::Interface::name()`: "GMG" (local smoothing) or "GMG-GC" (stokes_matrix_free_global_coarsening.cc:142-145)."""
+        return "GMG-GC" if self.parameters["Stokes GMG type"] == "global coarsening" else "GMG"
+
+    def _check_gmg_type(self, hierarchy):
+        """`Stokes GMG type` (parameters.cc:448-453).  On a UNIFORMLY refined mesh the coarsening sequence of the global-coarsening
+        handler (create_geometric_coarsening_sequence, global_coarsening.cc:1466) is the sequence of refinement levels, its level
+        operators, smoothers and coarse solver are the local-smoothing ones (:796-913) and its two-level transfers are the same
+        polynomial embeddings, so this hierarchy serves both types -- the reference's own global-coarsening goldens nsinker_gmg_gc
+        (21), nsinker_gmg_gc_no_avg, and gmg_test_project_q1-style runs are what tests/ reproduces on it.  On an ADAPTIVE mesh
+        global coarsening needs levels that are themselves meshes with hanging nodes and transfers between them: not built."""
+        kind = self.parameters["Stokes GMG type"]
+        if kind not in ("local smoothing", "global coarsening"):
+            raise SmfError(_lib.SMF_ERR_INVALID, "Stokes GMG type: local smoothing | global coarsening")
+        if kind == "global coarsening" and getattr(hierarchy, "adaptive", False):
+            raise SmfError(_lib.SMF_ERR_UNSUPPORTED,
+                           "Stokes GMG type = global coarsening on an adaptively refined mesh (levels with hanging nodes) is not built; "
+                           "use local smoothing")
 
     # ------------------------------------------------------------------
     def _check(self, rc, allow=()):
@@ -130,6 +147,7 @@ class StokesMatrixFreeHandler:
     def setup_dofs(self, hierarchy, boundary="zero"):
         """hierarchy: levels[l] with n_cells, n_u, n_p, cell_dofs_u, cell_dofs_p, h, constrained_u(bc); children(l).
         boundary: 'zero' (Zero velocity boundary indicators = all), 'tangential' (Tangential velocity ... = all)."""
+        self._check_gmg_type(hierarchy)
         self.close()
         self.hier = hierarchy
         self.boundary = boundary

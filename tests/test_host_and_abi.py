@@ -128,3 +128,22 @@ def test_ctypes_structs_match_the_header(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for n, _ in cls._fields_:
             assert int(got[f"{cname}.{n}"]) == getattr(cls, n).offset, f"{cname}.{n}"
+
+
+def test_stokes_gmg_type_parameter():
+    """`Stokes GMG type` (parameters.cc:448-453): both values are accepted on uniformly refined meshes (same hierarchy, name()
+    follows the reference's "GMG" / "GMG-GC"); global coarsening on an adaptive mesh and unknown values are refused before any
+    device work."""
+    from aspect_b200 import SmfError, StokesMatrixFreeHandler, _lib
+    from aspect_b200 import adaptive as padapt
+    h = StokesMatrixFreeHandler(3)
+    assert h.name() == "GMG"
+    h.parameters["Stokes GMG type"] = "global coarsening"
+    assert h.name() == "GMG-GC"
+    hier = padapt.AdaptiveBoxHierarchy.refined(3, 1, lambda x, l: x[2] < 0.5, 1)
+    with pytest.raises(SmfError) as e:
+        h.setup_dofs(hier, "zero")
+    assert e.value.args[0] == _lib.SMF_ERR_UNSUPPORTED or "global coarsening" in str(e.value)
+    h.parameters["Stokes GMG type"] = "algebraic"
+    with pytest.raises(SmfError):
+        h.setup_dofs(hier, "zero")
