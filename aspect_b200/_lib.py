@@ -76,7 +76,7 @@ EXPORTS = [
     "smf_create", "smf_destroy", "smf_last_error", "smf_set_option", "smf_set_stream", "smf_set_level", "smf_set_transfer",
     "smf_set_copy_indices", "smf_set_constraints", "smf_set_refinement_edges", "smf_set_level_copy_indices", "smf_set_cell_data", "smf_fill_cell_data", "smf_get_cell_data", "smf_set_newton_data", "smf_set_free_surface_faces", "smf_vec_alloc", "smf_vec_free", "smf_vec_h2d", "smf_vec_d2h", "smf_vec_set", "smf_vec_copy",
     "smf_synchronize", "smf_vmult_stokes", "smf_vmult_A", "smf_vmult_BT", "smf_vmult_mass", "smf_vmult_stokes_host", "smf_correct_stokes_rhs",
-    "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
+    "smf_compute_diagonals", "smf_get_inverse_diagonal", "smf_set_inverse_diagonal_entries", "smf_setup_smoothers", "smf_get_eigenvalue_estimates",
     "smf_prolongate", "smf_restrict_add", "smf_vcycle_A", "smf_vcycle_S", "smf_precondition", "smf_solve",
     "smf_solve_host", "smf_kernel_launches", "smf_device_bytes", "smf_profile_enable", "smf_profile_read",
     "smf_exchange_count", "smf_exchange_transport", "smf_lattice_schur_active", "smf_lattice_replicated_levels", "smf_detect_box_lattice", "smf_replicated_A_levels", "smf_assemble_rhs", "smf_set_pressure_normalization",

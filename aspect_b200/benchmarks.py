@@ -200,6 +200,44 @@ def nsinker_shell_problem(hier, n_sinkers=5, viscosity_ratio=1e2, averaging="har
     return eta_q, rho_q[..., None] * g, pressure_scaling_shell(act, material)
 
 
+# ---- tests/shell_3d_gmg.prm: zero velocity at the bottom, TANGENTIAL top boundary (no-normal-flux lines on a curved boundary) ----
+# data/gravity-model/prem.txt (the default profile of `Gravity model = ascii data`): depth [m], gravity [m/s^2]
+PREM_GRAVITY = np.array([
+    [0, 9.816], [3000, 9.822], [15000, 9.833], [24000, 9.839], [80000, 9.855], [150000, 9.878], [220000, 9.905], [310000, 9.936],
+    [400000, 9.969], [500000, 9.988], [600000, 10.004], [670000, 10.014], [771000, 9.999], [971000, 9.97], [1171000, 9.947],
+    [1371000, 9.933], [1571000, 9.931], [1771000, 9.947], [1971000, 9.986], [2171000, 10.054], [2371000, 10.158], [2571000, 10.31],
+    [2741000, 10.484], [2771000, 10.52], [2891000, 10.682], [2971000, 10.507], [3171000, 10.046], [3371000, 9.557], [3571000, 9.041],
+    [3771000, 8.502], [3971000, 7.943], [4171000, 7.365], [4371000, 6.772], [4571000, 6.167], [4771000, 5.555], [4971000, 4.941],
+    [5149000, 4.4], [5171000, 4.325], [5371000, 3.62], [5571000, 2.907], [5771000, 2.186], [5971000, 1.46], [6171000, 0.731],
+    [6371000, 0.0]])
+SHELL_3D_RADII_M = (3481000.0, 6336000.0)
+
+
+def shell_3d_gmg_problem(hier):
+    """(viscosity_q, force_q, pressure_scaling) of tests/shell_3d_gmg.prm (`simple` material: viscosity 1e22, rho = 3300 (1 - 4e-5
+    (T - 293)); T = 1473 K with 973 / 1973 K in the nodes of the outer / inner boundary of the Q2 temperature field; PREM
+    gravity) on a ShellHierarchy whose length unit is the OUTER RADIUS (inner_radius = 3481 / 6336, outer_radius = 1: the
+    driver's node keys need coordinates in [-1, 1]).  With x = s x' (s = 6,336,000 m) the system of the metric mesh divided by s
+    is the system of the unit mesh with pressure scaling s * ps and force density s^2 * rho g: same Krylov iteration, same
+    velocities; these scaled coefficients are what is returned."""
+    s = SHELL_3D_RADII_M[1]
+    act = hier.active
+    assert abs(act.R1 - 1.0) < 1e-12 and abs(act.R0 - SHELL_3D_RADII_M[0] / s) < 1e-12
+    x = act.quadrature_points()
+    r = np.sqrt((x * x).sum(-1))
+    rn = np.sqrt((act.node_x_u ** 2).sum(-1))
+    T_node = np.full(len(rn), 1473.0)
+    T_node[np.abs(rn - act.R1) < 1e-4] = 973.0
+    T_node[np.abs(rn - act.R0) < 1e-4] = 1973.0
+    cell_nodes = (np.asarray(act.cell_dofs_u[:, :27]) // 3).astype(np.int64)
+    T_q = T_node[cell_nodes] @ _phi2_at_quad(3).T
+    rho_q = 3300.0 * (1.0 - 4e-5 * (T_q - 293.0))
+    g_mag = np.interp((1.0 - r) * s, PREM_GRAVITY[:, 0], PREM_GRAVITY[:, 1])
+    force_q = (s * s) * (rho_q * g_mag)[..., None] * (-x / r[..., None])
+    ps = 1e22 / (1e4 / (6336000.0 - 3481000.0) * (SHELL_3D_RADII_M[1] - SHELL_3D_RADII_M[0]))
+    return np.full(x.shape[:2], 1e22), force_q, s * ps
+
+
 # ---- benchmarks/hollow_sphere (analytic solution on the spherical shell; the reference's test hollow_sphere_gmg) ----
 def _hollow_sphere_constants(m, R1=0.5, R2=1.0, gamma=1.0):
     """benchmarks/hollow_sphere/hollow_sphere.cc:72-85."""

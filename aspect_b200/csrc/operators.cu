@@ -2929,7 +2929,21 @@ static int launch_transfer(smf_ctx *ctx, int which, int fine_level, double *dst,
 }
 
 int launch_prolongate(smf_ctx *ctx, int which, int to_level, double *dst, const double *src, bool add)
-{ return launch_transfer(ctx, which, to_level, dst, src, true, add); }
+{
+  // constraint lines on the COARSE level (no-normal-flux on a curved boundary: user constraints of MGConstrainedDoFs):
+  // MGTransferMatrixFree::prolongate distributes them on its source vector before it interpolates; the source comes back
+  // unchanged (the entries are parked and restored)
+  ConstraintLines *H = nullptr;
+  if (to_level >= 1 && to_level < ctx->cfg.n_levels) {
+    LevelDev &C = ctx->levels[to_level - 1];
+    H = which == 0 ? &C.hang_u : &C.hang_p;
+    if (!H->n) H = nullptr;
+  }
+  if (H) { if (int e = hanging_pre(ctx, *H, src)) return e; }
+  if (int e = launch_transfer(ctx, which, to_level, dst, src, true, add)) return e;
+  if (H) return hanging_restore(ctx, *H, src);
+  return SMF_OK;
+}
 int launch_restrict_add(smf_ctx *ctx, int which, int from_level, double *dst, const double *src)
 { return launch_transfer(ctx, which, from_level, dst, src, false, true); }
 // dst += R (b - t): the residual of the V-cycle restricted without being stored (brick-wise velocity transfers); elsewhere

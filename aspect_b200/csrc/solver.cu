@@ -1043,6 +1043,27 @@ int smf_get_inverse_diagonal(smf_ctx *ctx, int level, int which, double *host_ou
   return smf_vec_d2h(ctx, host_out, which == 0 ? L.dinv_A : L.dinv_M, which == 0 ? L.n_u : L.n_p);
 }
 
+int smf_set_inverse_diagonal_entries(smf_ctx *ctx, int level, int which, int64_t n, const uint32_t *idx, const double *values)
+{
+  if (!ctx || n < 0 || (n > 0 && (!idx || !values)) || (which != 0 && which != 1)) return SMF_ERR_INVALID;
+  if (level < SMF_ACTIVE || level >= ctx->cfg.n_levels) return ctx->fail(SMF_ERR_INVALID, "level out of range");
+  LevelDev &L = ctx->lev(level);
+  if (!L.has_diag) return ctx->fail(SMF_ERR_INVALID, "call smf_compute_diagonals first");
+  const int64_t nd = which == 0 ? L.n_u : L.n_p;
+  double *d = which == 0 ? L.dinv_A : L.dinv_M;
+  // set-up path: one round trip of the vector (the entries are few: masters of constraint lines)
+  std::vector<double> h((size_t)nd);
+  TRY(smf_vec_d2h(ctx, h.data(), d, nd));
+  for (int64_t i = 0; i < n; ++i) {
+    if (idx[i] >= nd) return ctx->fail(SMF_ERR_INVALID, "smf_set_inverse_diagonal_entries: index out of range");
+    if (!(values[i] > 0.0)) return ctx->fail(SMF_ERR_INVALID, "smf_set_inverse_diagonal_entries: entries of a positive definite operator's diagonal must be positive");
+    h[idx[i]] = values[i];
+  }
+  TRY(smf_vec_h2d(ctx, d, h.data(), nd));
+  ctx->smoothers_ready = false;
+  return SMF_OK;
+}
+
 int smf_setup_smoothers(smf_ctx *ctx)
 {
   if (!ctx) return SMF_ERR_INVALID;

@@ -216,6 +216,22 @@ class StokesMatrixFreeHandler:
                 au, lu, ap, lp = hierarchy.copy_indices(l)
                 self._check(self.lib.smf_set_level_copy_indices(self.ctx, l, 0, ctypes.c_int64(len(au)), ptr(u32(au)), ptr(u32(lu))))
                 self._check(self.lib.smf_set_level_copy_indices(self.ctx, l, 1, ctypes.c_int64(len(ap)), ptr(u32(ap)), ptr(u32(lp))))
+        # no-normal-flux lines on a curved boundary (`Tangential velocity boundary indicators` on the shell): constraint lines on
+        # the active level AND on every multigrid level (user constraints of MGConstrainedDoFs, local_smoothing.cc:1719-1789)
+        self._level_lines = {}
+        if not self.adaptive and hasattr(hierarchy.active, "constraint_lines"):
+            u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+            for l in list(range(n_levels)) + [SMF_ACTIVE]:
+                L = hierarchy.levels[l] if l >= 0 else hierarchy.active
+                dof, start, master, weight = L.constraint_lines("u", boundary)
+                if len(dof) == 0:
+                    continue
+                self._check(self.lib.smf_set_constraints(self.ctx, l, 0, ctypes.c_int64(len(dof)), ptr(u32(dof)), ptr(u32(start)),
+                                                         ptr(u32(master)), ptr(np.ascontiguousarray(weight, dtype=np.float64))))
+                if l >= 0:
+                    self._level_lines[l] = (dof.astype(np.int64), start.astype(np.int64), master.astype(np.int64), weight)
+                else:
+                    self._lines["u"] = (dof.astype(np.int64), start.astype(np.int64), master.astype(np.int64), weight)
         self.n_u, self.n_p = hierarchy.active.n_u, hierarchy.active.n_p
         self.n_levels = n_levels
         # operator objects (duck-typed vmult like the reference's)
@@ -365,6 +381,52 @@ class StokesMatrixFreeHandler:
 
     def build_preconditioner(self):
         self._check(self.lib.smf_compute_diagonals(self.ctx))
+        for l in sorted(getattr(self, "_level_lines", {})):
+            self._constrained_level_diagonal(l)
+
+    def _constrained_level_diagonal(self, l):
+        """Masters' entries of diag(C^T A C) on a level with constraint lines (what MatrixFreeTools::compute_diagonal returns in
+        the reference, matrix_free_operators.cc:1068-1098): smf_compute_diagonals knows the operator without the lines, so the
+        level operator WITH its lines is probed with unit vectors.  Masters of nodes that share no cell do not interact (a line
+        couples the components of one node only), so one probe per (colour, component) gives all their entries at once;
+        nodes are coloured greedily over the cell cliques.  3 x (number of colours <= ~30) operator applications per level."""
+        dof, start, master, weight = self._level_lines[l]
+        L = self.hier.levels[l]
+        nodes = np.unique(dof // self.dim)
+        is_line_node = np.zeros(L.n_u // self.dim, bool); is_line_node[nodes] = True
+        nn = 3 ** self.dim
+        cell_nodes = (np.asarray(L.cell_dofs_u[:, :nn]) // self.dim).astype(np.int64)
+        touched = np.flatnonzero(is_line_node[cell_nodes].any(axis=1))
+        colour = np.full(L.n_u // self.dim, -1, dtype=np.int64)
+        neigh = {int(n): set() for n in nodes}
+        for c in touched:
+            group = [int(n) for n in cell_nodes[c] if is_line_node[n]]
+            for n in group:
+                neigh[n].update(group)
+        for n in nodes:                                   # greedy colouring in ascending node order
+            used = {colour[m] for m in neigh[int(n)] if colour[m] >= 0}
+            k = 0
+            while k in used:
+                k += 1
+            colour[n] = k
+        is_line_dof = np.zeros(L.n_u, bool); is_line_dof[dof] = True
+        src, dst = self.initialize_dof_vector(0, l), self.initialize_dof_vector(0, l)
+        idx, val = [], []
+        for k in range(int(colour.max()) + 1):
+            group = nodes[colour[nodes] == k]
+            for c in range(self.dim):
+                probe = self.dim * group + c
+                probe = probe[~is_line_dof[probe]]           # masters only: the eliminated component has a unit diagonal
+                if len(probe) == 0:
+                    continue
+                v = np.zeros(L.n_u); v[probe] = 1.0
+                src.from_host(v)
+                self.mg_matrices_A_block[l].vmult(dst, src)
+                idx.append(probe); val.append(dst.to_host()[probe])
+        idx = np.concatenate(idx); val = np.concatenate(val)
+        self._check(self.lib.smf_set_inverse_diagonal_entries(self.ctx, l, 0, ctypes.c_int64(len(idx)),
+                                                              ptr(np.ascontiguousarray(idx, dtype=np.uint32)),
+                                                              ptr(np.ascontiguousarray(1.0 / val, dtype=np.float64))))
 
     def get_matrix_diagonal_inverse(self, level, which):
         L = self.hier.active if level == SMF_ACTIVE else self.hier.levels[level]
@@ -479,7 +541,7 @@ class StokesMatrixFreeHandler:
         out = self._outputs(res)
         self._check(rc, allow=(_lib.SMF_NO_CONVERGENCE,))
         out["converged"] = rc == 0
-        if getattr(self, "adaptive", False):
+        if getattr(self, "adaptive", False) or getattr(self, "_lines", None):
             self.distribute_constraints(sol)
         return sol, out
 

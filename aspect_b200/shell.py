@@ -245,16 +245,56 @@ class ShellLevel:
         return cell_nodes, x                                             # (positions are accurate to the key quantum, 2e-6)
 
     # -- constraints -------------------------------------------------------------------------------------------
+    def _boundary_nodes(self, which):
+        r = np.sqrt((self.node_x_u ** 2).sum(-1))
+        on = np.zeros(len(r), bool)
+        if which in ("bottom", "both"):
+            on |= np.abs(r - self.R0) < 1e-4
+        if which in ("top", "both"):
+            on |= np.abs(r - self.R1) < 1e-4
+        return on
+
     def constrained_u(self, bc):
-        """'zero': all components on the inner and outer boundary (`Zero velocity boundary indicators = top, bottom`)."""
+        """Dirichlet DoFs.  'zero': all components on the inner and outer boundary (`Zero velocity boundary indicators = top,
+        bottom`); 'zero bottom, tangential top': the inner boundary only (tests/shell_3d_gmg.prm) -- the outer boundary then
+        carries the no-normal-flux lines of constraint_lines()."""
         if bc == "none":
             return np.zeros(0, dtype=_UINT)
-        if bc != "zero":
-            raise ValueError("the shell driver implements zero-velocity boundaries only (no-normal-flux on a curved boundary "
-                             "couples the components)")
-        r = np.sqrt((self.node_x_u ** 2).sum(-1))
-        on = (np.abs(r - self.R0) < 1e-4) | (np.abs(r - self.R1) < 1e-4)
+        if bc not in ("zero", "zero bottom, tangential top"):
+            raise ValueError("shell boundaries: 'zero' | 'zero bottom, tangential top' | 'none'")
+        on = self._boundary_nodes("both" if bc == "zero" else "bottom")
         return np.flatnonzero(np.repeat(on[:, None], 3, axis=1).ravel()).astype(_UINT)
+
+    def constraint_lines(self, family, bc):
+        """No-normal-flux lines of `Tangential velocity boundary indicators = top` (one rank): (dof, start, master, weight) in the
+        format of smf_set_constraints.  As VectorTools::compute_no_normal_flux_constraints[_on_level] with
+        use_manifold_for_normal = true (stokes_matrix_free_local_smoothing.cc:1736-1745): at every node of the outer boundary the
+        normal is the radial direction, the component with the largest |n_k| (the first of them within 1e-9) is eliminated,
+        u_k = -sum_{j != k} (n_j / n_k) u_j.  The node positions are evaluated exactly (node_x_u is accurate to the key quantum
+        only)."""
+        empty = (np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0))
+        if family != "u" or bc != "zero bottom, tangential top":
+            return empty
+        assert self.world == 1, "no-normal-flux lines: one rank"
+        top = self._boundary_nodes("top")
+        cell_nodes = (self.cell_dofs_u[:, :27] // 3).astype(np.int64)
+        cells = np.flatnonzero(top[cell_nodes].any(axis=1))                 # cells with a face on the outer boundary
+        ref = _lex(3, 3).astype(np.float64) / 2.0
+        x = self.points(ref, cells=self.cells[cells], tree=self.tree[cells])   # (cells, 27, 3), exact
+        nodes = cell_nodes[cells].ravel()
+        uniq, first = np.unique(nodes, return_index=True)
+        keep = top[uniq]
+        uniq, xn = uniq[keep], x.reshape(-1, 3)[first[keep]]
+        nrm = xn / np.sqrt((xn ** 2).sum(-1))[:, None]
+        a = np.abs(nrm)
+        k = np.argmax(a >= a.max(axis=1, keepdims=True) - 1e-9, axis=1)      # first component within 1e-9 of the largest
+        others = np.array([[1, 2], [0, 2], [0, 1]])[k]
+        rows = np.arange(len(uniq))
+        dof = 3 * uniq + k
+        master = (3 * uniq[:, None] + others).ravel()
+        weight = (-nrm[rows[:, None], others] / nrm[rows, k][:, None]).ravel()
+        start = 2 * np.arange(len(uniq) + 1)
+        return dof.astype(np.int64), start.astype(np.int64), master.astype(np.int64), weight
 
     # -- geometry (MappingQ(degree) of the analytic tree map) --------------------------------------------------
     def geometry(self):

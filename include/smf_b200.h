@@ -244,6 +244,14 @@ int smf_vmult_stokes_host(smf_ctx *ctx, double *dst_u, double *dst_p, const doub
 int smf_compute_diagonals(smf_ctx *ctx);
 /* get_matrix_diagonal_inverse() (local_smoothing.cc:794, :822): which = 0 (A) or 1 (mass); host output */
 int smf_get_inverse_diagonal(smf_ctx *ctx, int level, int which, double *host_out);
+/* Overwrite entries of a level's inverse diagonal (after smf_compute_diagonals, before the smoothers are set up).
+ * smf_compute_diagonals returns the diagonal of the operator WITHOUT the constraint lines of smf_set_constraints; on a level
+ * that smooths with such lines (no-normal-flux on a curved boundary: user constraints of MGConstrainedDoFs,
+ * stokes_matrix_free_local_smoothing.cc:1719-1789) the masters' entries of diag(C^T A C) -- what
+ * MatrixFreeTools::compute_diagonal returns in the reference (matrix_free_operators.cc:1068-1098) -- come from the caller:
+ * the ASPECT adapter passes deal.II's values, handler.py obtains them by probing the level operator with coloured unit
+ * vectors.  values = INVERSE diagonal entries (> 0). */
+int smf_set_inverse_diagonal_entries(smf_ctx *ctx, int level, int which, int64_t n, const uint32_t *idx, const double *values);
 
 /* PreconditionChebyshev set-up + estimate_eigenvalues on every level, both hierarchies
  * (local_smoothing.cc:774-849).  Must follow smf_compute_diagonals. */

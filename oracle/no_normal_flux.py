@@ -8,7 +8,7 @@ restatement of smoothers, transfers and Krylov solver that every other test uses
 Reference:
 * active level: `VectorTools::compute_no_normal_flux_constraints(..., use_manifold_for_normal = true)`
   (source/simulator/core.cc, compute_initial_velocity_boundary_constraints): at every boundary node the component with the largest
-  |n_k| is constrained, u_k = - sum_{j != k} (n_j / n_k) u_j, n = the manifold's normal = the radial direction on a sphere;
+  |n_k| (ties: the first) is constrained, u_k = - sum_{j != k} (n_j / n_k) u_j, n = the manifold's normal = the radial direction;
 * levels: `compute_no_normal_flux_constraints_on_level` into user constraints of `MGConstrainedDoFs`, merged into the level
   constraints of the level MatrixFree objects, Dirichlet values win (stokes_matrix_free_local_smoothing.cc:1719-1789);
 * a MatrixFree operator with constraints C is C^T A C on the unconstrained DoFs and the identity on the constrained ones
@@ -65,7 +65,8 @@ def constraint_matrix(level, dirichlet_nodes, flux_nodes):
     for k in flux_nodes:
         x = level.node_x_u[k]
         nrm = x / np.sqrt(x @ x)
-        c = int(np.argmax(np.abs(nrm)))
+        a = np.abs(nrm)
+        c = int(np.argmax(a >= a.max() - 1e-9))                       # the first component within 1e-9 of the largest
         cons[3 * k + c] = True
         for j in range(3):
             if j != c:

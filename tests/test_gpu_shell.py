@@ -243,3 +243,84 @@ def test_hollow_sphere_matches_oracle_and_reference_golden():
     for got, ref in zip(hs.errors(L, u, p), g["errors_uL1_pL1_uL2_pL2"][0]):
         assert abs(got / float(ref) - 1.0) < 2e-5
     h.close()
+
+
+def test_shell_tangential_top_matches_oracle_and_reference_golden():
+    """tests/shell_3d_gmg (first solve; the reference's local-smoothing golden on the cfg-3 mesh: 24+0 iterations): zero velocity
+    at the bottom, TANGENTIAL velocity at the top -- no-normal-flux lines that couple the components of a node, on the active
+    level and on every multigrid level (smf_set_constraints per level, constrained level diagonals through
+    smf_set_inverse_diagonal_entries, prolongation that distributes the coarse lines).  Device against the oracle's
+    restatement (oracle/no_normal_flux.py) on the same mesh (length unit = outer radius, coefficients scaled accordingly,
+    benchmarks.shell_3d_gmg_problem): operators, diagonals and transfers 1e-12, the A-block V-cycle 1e-10, the solve: the
+    oracle's iteration count (25), the golden's +-1, velocities 1e-5 (see below)."""
+    from oracle import no_normal_flux as nnf
+    from util import golden
+    bc = "zero bottom, tangential top"
+    R0 = benchmarks.SHELL_3D_RADII_M[0] / benchmarks.SHELL_3D_RADII_M[1]
+    ohier, hier = oshell.ShellHierarchy(1, R0, 1.0), pshell.ShellHierarchy(1, R0, 1.0)
+    eta_q, force_q, ps = benchmarks.shell_3d_gmg_problem(hier)
+    active, levels, _, _ = coeff.viscosity_tables(ohier, eta_q, "harmonic")
+    ob = nnf.NoNormalFluxBackend(ohier, active, levels, ps, R0, 1.0)
+    h = StokesMatrixFreeHandler(3)
+    h.setup_dofs(hier, bc)
+    h.assemble(eta_q, "harmonic average", ps)
+    h.build_preconditioner()
+    act, nu = hier.active, hier.active.n_u
+    # level operators, their diagonals, the transfers
+    for l, L in enumerate(hier.levels):
+        x = seeded(L.n_u, 50 + l)
+        s, d = h.initialize_dof_vector(0, l).from_host(x), h.initialize_dof_vector(0, l)
+        h.mg_matrices_A_block[l].vmult(d, s)
+        assert rel(d.to_host(), ob.apply_A(l, x)) < TOL
+        assert rel(s.to_host(), x) == 0.0                                   # the source comes back untouched
+        assert rel(h.get_matrix_diagonal_inverse(l, 0), ob.dinv_A(l)) < TOL
+        if l > 0:
+            C = hier.levels[l - 1]
+            xc = seeded(C.n_u, 60 + l)
+            sc = h.initialize_dof_vector(0, l - 1).from_host(xc)
+            h.prolongate(0, l, d, sc)
+            assert rel(d.to_host(), ob.prolongate_u(l, xc)) < TOL
+            assert rel(sc.to_host(), xc) == 0.0
+            rc = h.initialize_dof_vector(0, l - 1)
+            h.restrict_and_add(0, l, rc, s)
+            assert rel(rc.to_host(), ob.restrict_u(l, x)) < TOL
+    # active Stokes operator with the lines
+    xu, xp = seeded(nu, 1), seeded(act.n_p, 2)
+    src, dst = h.initialize_dof_vector(), h.initialize_dof_vector()
+    src[0].from_host(xu); src[1].from_host(xp)
+    h.stokes_matrix.vmult(dst, src)
+    yu, yp = ob.stokes(xu, xp)
+    assert rel(dst[0].to_host(), yu) < TOL and rel(dst[1].to_host(), yp) < TOL
+    # the solve
+    h.parameters.update({"Linear solver tolerance": 1e-4, "Number of cheap Stokes solver steps": 200,
+                         "Maximum number of expensive Stokes solver steps": 0, "GMRES solver restart length": 100})
+    r = h.initialize_dof_vector(0)
+    h.assemble_stokes_rhs(force_q, r)
+    f = r.to_host()
+    assert rel(f, _masked(assembled.rhs_force(ohier.active, force_q), act.constrained_u(bc))) < 1e-12
+    rhs = h.condense_rhs(np.concatenate([f, np.zeros(act.n_p)]))
+    want_rhs = np.concatenate([ob.condense_rhs(assembled.rhs_force(ohier.active, force_q)), np.zeros(act.n_p)])
+    assert rel(rhs, want_rhs) < 1e-12
+    want = solver.BlockGMGStokes(ob).solve(want_rhs, tol_rel=1e-4, restart=100, max_its=200)
+    sol, out = h.solve(rhs)
+    gold = golden("shell_3d_gmg")["stokes_iterations_cheap_expensive"][0][0]
+    assert out["converged"] and want["converged"]
+    assert out["iterations"] == want["iterations"] and abs(out["iterations"] - gold) <= 1, (out["iterations"], want["iterations"], gold)
+    u_want = ob.distribute(want["x"][:nu])
+    # (the right-hand side is the full hydrostatic load, 1e4 times the buoyancy that drives the flow, and the solve stops at a
+    # relative 1e-4: the two runs walk the same Krylov sequence, round-off differences are amplified by that cancellation --
+    # measured 1.8e-6; the operator-level comparisons above are the 1e-12 ones)
+    assert rel(sol[:nu], u_want) < 1e-5
+    top = nnf.boundary_nodes(ohier.active, 1.0)
+    n = ohier.active.node_x_u[top] / np.linalg.norm(ohier.active.node_x_u[top], axis=1)[:, None]
+    assert np.abs((sol[:nu].reshape(-1, 3)[top] * n).sum(axis=1)).max() < 1e-12 * np.abs(sol[:nu]).max()
+    # one A-block V-cycle on the right-hand side (the smoothers were set up by the solve)
+    s, d = h.initialize_dof_vector(0).from_host(rhs[:nu]), h.initialize_dof_vector(0)
+    h.prec_A.vmult(d, s)
+    assert rel(d.to_host(), solver.BlockGMGStokes(ob).mg_A.vmult(rhs[:nu])) < 1e-10
+    h.close()
+
+
+def _masked(f, constrained):
+    f = f.copy(); f[np.asarray(constrained, dtype=np.int64)] = 0.0
+    return f
