@@ -186,6 +186,14 @@ namespace aspect_b200
     }
     /** wait for the work queued on the context's stream */
     void synchronize() const { check(smf_synchronize(ctx)); }
+    /** user constraints of MGConstrainedDoFs on a multigrid level (no-normal-flux on a curved boundary,
+        local_smoothing.cc:1719-1789) or lines of the active constraints (level = SMF_ACTIVE): closed lines u_k = sum w_j u_mj */
+    void set_constraint_lines(int level, int family, const std::vector<std::uint32_t> &dof, const std::vector<std::uint32_t> &row_start,
+                              const std::vector<std::uint32_t> &master, const std::vector<double> &weight)
+    { check(smf_set_constraints(ctx, level, family, (std::int64_t)dof.size(), dof.data(), row_start.data(), master.data(), weight.data())); }
+    /** masters' entries of the constrained level operator's diagonal (MatrixFreeTools::compute_diagonal), after build_preconditioner() */
+    void set_inverse_diagonal_entries(int level, int which, const std::vector<std::uint32_t> &dofs, const std::vector<double> &inverse_diagonal)
+    { check(smf_set_inverse_diagonal_entries(ctx, level, which, (std::int64_t)dofs.size(), dofs.data(), inverse_diagonal.data())); }
     std::size_t get_cell_data_memory_consumption() const { return (std::size_t)smf_device_bytes(ctx); }
     std::int64_t n_velocity_dofs() const { return n_u; }
     std::int64_t n_pressure_dofs() const { return n_p; }

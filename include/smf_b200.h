@@ -115,6 +115,12 @@ int smf_set_copy_indices(smf_ctx *ctx, const uint32_t *active_to_level_u, const 
  *   closed; Dirichlet masters dropped).  The operators then act as MatrixFreeOperators::Base does: read_dof_values
  *   resolves the lines, distribute_local_to_global applies their transpose, constrained rows get dst = src
  *   (A_mf = C^T A C + I_constrained).  family 0: velocity, 1: pressure.  n_lines = 0 clears.
+ *   level = SMF_ACTIVE: hanging nodes and / or no-normal-flux lines of the active constraints.  level >= 0: the USER
+ *   CONSTRAINTS of MGConstrainedDoFs on that multigrid level -- no-normal-flux on a curved boundary,
+ *   VectorTools::compute_no_normal_flux_constraints_on_level (stokes_matrix_free_local_smoothing.cc:1719-1789): the level
+ *   operator and its smoother then work with the lines, smf_prolongate distributes the COARSE level's lines on its source
+ *   before it interpolates (MGTransferMatrixFree::prolongate), and the masters' diagonal entries come in through
+ *   smf_set_inverse_diagonal_entries (below).
  * smf_set_refinement_edges: MGConstrainedDoFs::get_refinement_edge_indices of one level (:1733-1773).  The level operators
  *   then treat these DoFs like Dirichlet DoFs (A_l = (I - E) A_bc (I - E) + E, as Base::vmult with edge_constrained_indices),
  *   and the V-cycles add the interface products vmult_interface_down / vmult_interface_up (mg::Matrix edge matrices,
