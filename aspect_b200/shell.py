@@ -260,25 +260,27 @@ class ShellLevel:
         carries the no-normal-flux lines of constraint_lines()."""
         if bc == "none":
             return np.zeros(0, dtype=_UINT)
-        if bc not in ("zero", "zero bottom, tangential top"):
-            raise ValueError("shell boundaries: 'zero' | 'zero bottom, tangential top' | 'none'")
+        if bc not in ("zero", "zero bottom, tangential top", "tangential"):
+            raise ValueError("shell boundaries: 'zero' | 'zero bottom, tangential top' | 'tangential' | 'none'")
+        if bc == "tangential":                 # `Tangential velocity boundary indicators = top, bottom` (tests/gmg_no_normal_flux_only.prm)
+            return np.zeros(0, dtype=_UINT)
         on = self._boundary_nodes("both" if bc == "zero" else "bottom")
         return np.flatnonzero(np.repeat(on[:, None], 3, axis=1).ravel()).astype(_UINT)
 
     def constraint_lines(self, family, bc):
-        """No-normal-flux lines of `Tangential velocity boundary indicators = top` (one rank): (dof, start, master, weight) in the
+        """No-normal-flux lines of `Tangential velocity boundary indicators = top` (or `top, bottom` for bc = 'tangential'; one rank): (dof, start, master, weight) in the
         format of smf_set_constraints.  As VectorTools::compute_no_normal_flux_constraints[_on_level] with
         use_manifold_for_normal = true (stokes_matrix_free_local_smoothing.cc:1736-1745): at every node of the outer boundary the
         normal is the radial direction, the component with the largest |n_k| (the first of them within 1e-9) is eliminated,
         u_k = -sum_{j != k} (n_j / n_k) u_j.  The node positions are evaluated exactly (node_x_u is accurate to the key quantum
         only)."""
         empty = (np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0))
-        if family != "u" or bc != "zero bottom, tangential top":
+        if family != "u" or bc not in ("zero bottom, tangential top", "tangential"):
             return empty
         assert self.world == 1, "no-normal-flux lines: one rank"
-        top = self._boundary_nodes("top")
+        top = self._boundary_nodes("top" if bc == "zero bottom, tangential top" else "both")
         cell_nodes = (self.cell_dofs_u[:, :27] // 3).astype(np.int64)
-        cells = np.flatnonzero(top[cell_nodes].any(axis=1))                 # cells with a face on the outer boundary
+        cells = np.flatnonzero(top[cell_nodes].any(axis=1))                 # cells with a face on a no-normal-flux boundary
         ref = _lex(3, 3).astype(np.float64) / 2.0
         x = self.points(ref, cells=self.cells[cells], tree=self.tree[cells])   # (cells, 27, 3), exact
         nodes = cell_nodes[cells].ravel()
