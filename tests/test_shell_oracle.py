@@ -224,3 +224,46 @@ def test_gmg_no_normal_flux_only_golden_sits_on_a_plateau():
     tol = out["tolerance"]
     print("gmg_no_normal_flux_only: iterations", out["iterations"], "last residuals / tolerance", hist[-6:] / tol)
     assert hist[-2] < 1.05 * tol and hist[-4] < 1.10 * tol          # the last iterations sit within 10 % of the tolerance
+
+
+@pytest.mark.parametrize("bc,r_zero,r_flux", [("zero bottom, tangential top", "inner", "outer"), ("tangential", None, "both")])
+def test_no_normal_flux_lines_of_the_driver_match_the_oracle(bc, r_zero, r_flux):
+    """The constraint lines the product's shell driver hands to smf_set_constraints (every level) against the oracle's
+    constraint matrix: the same constrained DoFs, the same masters, weights to 1e-15 (exact radial normals on both sides, the
+    same tie-break between equal normal components)."""
+    from oracle import no_normal_flux as nnf
+    R0 = benchmarks.SHELL_3D_RADII_M[0] / benchmarks.SHELL_3D_RADII_M[1]
+    hp, ho = pshell.ShellHierarchy(1, R0, 1.0), oshell.ShellHierarchy(1, R0, 1.0)
+    radii = {"inner": R0, "outer": 1.0, "both": (R0, 1.0), None: None}
+    for Lp, Lo in zip(hp.levels, ho.levels):
+        assert np.array_equal(Lp.cell_dofs_u, Lo.cell_dofs_u)
+        dof, start, master, w = Lp.constraint_lines("u", bc)
+        assert len(Lp.constraint_lines("p", bc)[0]) == 0
+        C, cons = nnf.constraint_matrix(Lo, nnf.boundary_nodes(Lo, radii[r_zero]), nnf.boundary_nodes(Lo, radii[r_flux]))
+        C = C.tocsr()
+        assert set(cons.tolist()) == set(Lp.constrained_u(bc).tolist()) | set(dof.tolist())
+        assert len(dof) == len(nnf.boundary_nodes(Lo, radii[r_flux])) and np.array_equal(np.diff(start), np.full(len(dof), 2))
+        for i, k in enumerate(dof):
+            row = C.getrow(k)
+            m, ww = master[start[i]:start[i + 1]], w[start[i]:start[i + 1]]
+            assert k // 3 == m[0] // 3 == m[1] // 3 and k not in m                      # the other two components of the same node
+            want = dict(zip(row.indices.tolist(), row.data.tolist()))
+            assert set(m.tolist()) == set(want) and max(abs(want[a] - b) for a, b in zip(m.tolist(), ww)) < 1e-14
+        # the eliminated component carries the largest normal component
+        x = Lo.node_x_u[dof // 3]
+        n = np.abs(x / np.linalg.norm(x, axis=1)[:, None])
+        assert np.all(n[np.arange(len(dof)), dof % 3] >= n.max(axis=1) - 1e-9)
+
+
+def test_shell_3d_gmg_problem_of_the_driver_matches_the_oracle():
+    """benchmarks.shell_3d_gmg_problem (unit outer radius, scaled coefficients) against the oracle's metric problem: force density
+    / s^2 and pressure scaling / s agree to round-off (s = 6,336,000 m)."""
+    from oracle import no_normal_flux as nnf
+    s = benchmarks.SHELL_3D_RADII_M[1]
+    hp = pshell.ShellHierarchy(1, benchmarks.SHELL_3D_RADII_M[0] / s, 1.0)
+    hm = oshell.ShellHierarchy(1, *benchmarks.SHELL_3D_RADII_M)
+    eta_p, force_p, ps_p = benchmarks.shell_3d_gmg_problem(hp)
+    eta_o, force_o, ps_o = nnf.shell_3d_gmg_problem(hm, *benchmarks.SHELL_3D_RADII_M)
+    assert np.array_equal(eta_p, eta_o) and abs(ps_p / s / ps_o - 1.0) < 1e-14
+    assert np.abs(force_p / s ** 2 - force_o).max() < 1e-13 * np.abs(force_o).max()
+    assert np.array_equal(benchmarks.PREM_GRAVITY, nnf.PREM)
