@@ -110,3 +110,67 @@ def test_free_surface_face_term():
         y = newton.free_surface_apply_add(L, cells, face_no, tab, cons, v, np.zeros(L.n_u))
         assert np.abs(K @ v - y).max() < 1e-14
         assert not np.any(y[cons]) and abs(K[:, cons]).max() == 0.0
+
+
+@pytest.mark.parametrize("dim,R", [(2, 2), (3, 1)])
+@pytest.mark.parametrize("deviatoric", [False, True])
+def test_newton_operator_is_the_jacobian_of_the_picard_operator(dim, R, deviatoric):
+    """An anchor that does not depend on the restated formulas: with the tables filled as the reference fills them
+    (stokes_matrix_free_local_smoothing.cc:436-445: strain_rate_table = eps(u0), newton_factor_wrt_strain_rate_table =
+    scaling * d eta / d eps at u0) the unsymmetrised Newton operator must be the derivative of the Picard operator
+    F(u) = A(eta(eps(u))) u at u0 -- checked by central differences for a power-law viscosity
+    eta = eta0 (e_II^2 + e_min^2)^((1/n - 1)/2), e_II^2 = eps':eps'/2 (deviatoric) or eps:eps/2; and the symmetrised operator must be
+    the symmetric part (J + J^T)/2 of that derivative's Newton term added to the Picard matrix."""
+    lev = mesh.Level(dim, R)
+    rng = np.random.default_rng(11)
+    none = np.zeros(0, dtype=np.int64)
+    nq, ns = 3 ** dim, dim * (dim + 1) // 2
+    t = newton.fe.tensor_tables(dim)
+    G = t["dphi2"] / lev.h[None, None, :]
+    eta0, n_exp, e_min = 1.3, 3.0, 0.05
+    I = np.eye(dim)
+
+    def strain(xu):
+        u = xu[lev.cell_dofs_u].reshape(lev.n_cells, dim, nq)
+        g = np.einsum("kci,qid->kqcd", u, G)
+        return 0.5 * (g + np.swapaxes(g, -1, -2))
+
+    def viscosity(eps):
+        e = eps - (np.trace(eps, axis1=-2, axis2=-1) / 3.0)[..., None, None] * I if deviatoric else eps
+        s = 0.5 * np.einsum("kqcd,kqcd->kq", e, e) + e_min ** 2
+        eta = eta0 * s ** (0.5 * (1.0 / n_exp - 1.0))
+        # d eta / d eps_ij = eta0 (1/n - 1)/2 s^((1/n - 1)/2 - 1) * d s / d eps_ij;  d s / d eps = e : d e / d eps = e - tr(e)/3 I
+        # for e = eps - tr(eps)/3 I (tr(e) = 0 in 3D only: the "deviator" keeps the reference's 1/3 in 2D as well), = eps otherwise
+        ds = e - (np.trace(e, axis1=-2, axis2=-1) / 3.0)[..., None, None] * I if deviatoric else e
+        deta = (eta0 * 0.5 * (1.0 / n_exp - 1.0) * s ** (0.5 * (1.0 / n_exp - 1.0) - 1.0))[..., None, None] * ds
+        return eta, deta
+
+    def picard(xu):                                    # F(u) = A(eta(eps(u))) u, velocity rows, no constraints
+        eta, _ = viscosity(strain(xu))
+        yu, _ = newton.stokes_apply(lev, eta, 1.0, none, xu, np.zeros(lev.n_p), deviatoric)
+        return yu
+
+    def unroll(tensor):                                # (cells, q, dim, dim) -> (cells, q, n_sym) in the tables' order
+        return np.stack([tensor[..., i, j] for (i, j) in newton.SYM_INDEX[dim]], axis=-1)
+
+    u0, du = rng.uniform(-1, 1, lev.n_u), rng.uniform(-1, 1, lev.n_u)
+    eps0 = strain(u0)
+    eta_q, deta = viscosity(eps0)
+    nd = newton.NewtonData(dim, enable_newton_derivatives=True, symmetrize_newton_system=False, average_newton_factors=False,
+                           strain_rate_table=unroll(eps0), newton_factor_wrt_strain_rate_table=unroll(deta),
+                           newton_factor_wrt_pressure_table=np.zeros((lev.n_cells, nq)))
+    j_du, _ = newton.stokes_apply(lev, eta_q, 1.0, none, du, np.zeros(lev.n_p), deviatoric, nd)
+    h = 1e-5
+    fd = (picard(u0 + h * du) - picard(u0 - h * du)) / (2.0 * h)
+    assert np.linalg.norm(j_du - fd) <= 1e-7 * np.linalg.norm(fd), np.linalg.norm(j_du - fd) / np.linalg.norm(fd)
+    # the derivative term matters (the Picard matrix alone is not the Jacobian)
+    a_du, _ = newton.stokes_apply(lev, eta_q, 1.0, none, du, np.zeros(lev.n_p), deviatoric)
+    assert np.linalg.norm(a_du - fd) > 1e-2 * np.linalg.norm(fd)
+    # symmetrised system = Picard matrix + symmetric part of the Newton term: x.(J_s y) = x.(A y) + (x.(N y) + y.(N x)) / 2
+    x, y = rng.uniform(-1, 1, lev.n_u), rng.uniform(-1, 1, lev.n_u)
+    op = lambda v, data: newton.stokes_apply(lev, eta_q, 1.0, none, v, np.zeros(lev.n_p), deviatoric, data)[0]
+    n_y, n_x = op(y, nd) - op(y, None), op(x, nd) - op(x, None)
+    nd.symmetrize_newton_system = True
+    lhs = x @ op(y, nd)
+    rhs = x @ op(y, None) + 0.5 * (x @ n_y + y @ n_x)
+    assert abs(lhs - rhs) <= 1e-12 * abs(rhs)
