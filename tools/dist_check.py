@@ -107,10 +107,15 @@ def parity(R, mode="gmres", avg="harmonic average"):
     h.close()
     ref = [None]
     if rank == 0:
-        hier1, h1, rhs1 = setup(R, rep, 0, 1, avg, mode)
-        ref[0] = run(h1, hier1, rhs1)
-        h1.close()
+        try:                                  # (a failure of the one-rank run must not leave the other ranks in the broadcast)
+            hier1, h1, rhs1 = setup(R, rep, 0, 1, avg, mode)
+            ref[0] = run(h1, hier1, rhs1)
+            h1.close()
+        except Exception as exc:
+            ref[0] = ("error", repr(exc))
     dist.broadcast_object_list(ref, src=0)
+    if isinstance(ref[0], tuple) and len(ref[0]) == 2 and ref[0][0] == "error":
+        raise RuntimeError("one-rank reference run failed on rank 0: " + ref[0][1])
     gu1, gp1, yu1, yp1, su1, sp1, out1 = ref[0]
     pu, pp = np.argsort(gu1), np.argsort(gp1)
     iu, ip = pu[np.searchsorted(gu1[pu], gu)], pp[np.searchsorted(gp1[pp], gp)]
