@@ -4,7 +4,7 @@ What the reference gets from deal.II on an adaptively refined `parallel::distrib
 (BASELINE cfg 3 / cfg 4 refine adaptively; /root/reference/source/simulator/solver/stokes_matrix_free_local_smoothing.cc:
 1487-1633 builds the constraints, :1695-1803 the level constraints):
 
-* mesh: one tree, leaves = active cells, 2:1 balanced across faces, edges and corners (p4est `P4EST_CONNECT_FULL`), active
+* mesh: one tree (or `repetitions` trees of a subdivided box, tree by tree), leaves = active cells, 2:1 balanced across faces, edges and corners (p4est `P4EST_CONNECT_FULL`), active
   cells in depth-first (z-) order;
 * active DoFs: `distribute_dofs` + `DoFRenumbering::hierarchical` = first touch over the active cells in that order, FE-local
   order inside a cell; hanging nodes carry DoFs like any other node;
@@ -22,8 +22,9 @@ Checks (tests/test_adaptive_oracle.py): without adaptive refinement everything r
 index maps, same matrices, the reference's 21 iterations of tests/nsinker_gmg_gc); Q2 / Q1 polynomials satisfy the hanging
 constraints exactly; rigid motions are in the null space; the GMG-preconditioned solve on an adaptive mesh converges to the
 direct solution of the constrained system, with the iteration count of the uniform mesh for a constant viscosity.
-parity unpinned beyond that: the reference's adaptive goldens depend on its Kelly refinement indicators, which are outside
-this path, and the CUDA path has no hanging-node support yet (the C ABI rejects non-uniform children tables).
+Pinned by the reference golden tests/muparser_temperature_example (oracle/muparser_example.py: meshes from a minimum refinement
+function alone; cells, levels, pressure DoFs exact, 6 / 9 / 9 iterations reproduced as 7 / 9 / 10); the other adaptive goldens of the
+reference depend on Kelly refinement indicators, which are outside this path.
 """
 import itertools
 
@@ -39,22 +40,28 @@ def _children(cell, dim):
 
 
 class AdaptiveBox:
-    """Unit box [0,1]^dim, one coarse cell; `leaves` = set of active cells (level, (i, j[, k]))."""
+    """Box of `repetitions` coarse cells (trees; default one) of edge length `coarse_size` (default 1: the unit box);
+    `leaves` = set of active cells (level, (i, j[, k])) with 0 <= i < repetitions[0] * 2^level etc."""
 
-    def __init__(self, dim, leaves):
+    def __init__(self, dim, leaves, repetitions=None, coarse_size=1.0):
         self.dim = dim
+        self.reps = tuple(repetitions) if repetitions is not None else (1,) * dim
+        self.coarse_size = float(coarse_size)
         self.leaves = set(leaves)
         self.Lmax = max(l for l, _ in self.leaves)
         self._balance_check()
-        # depth-first order = Morton order of the anchors at the finest resolution
+        # p4est order: tree by tree (trees of GridGenerator::subdivided_hyper_rectangle: x fastest), inside a tree depth-first
+        # = Morton order of the anchors at the finest resolution
         def morton(cell):
             l, ijk = cell
             s = self.Lmax - l
+            tree = [ijk[d] >> l for d in range(dim)]
+            t = sum(tree[d] * int(np.prod(self.reps[:d])) for d in range(dim))
             m = 0
             for b in range(self.Lmax):
                 for d in range(dim):
-                    m |= (((ijk[d] << s) >> b) & 1) << (dim * b + d)
-            return m
+                    m |= ((((ijk[d] - (tree[d] << l)) << s) >> b) & 1) << (dim * b + d)
+            return (t, m)
         self.cells = sorted(self.leaves, key=morton)
         self.n_cells = len(self.cells)
         self._number()
@@ -62,29 +69,30 @@ class AdaptiveBox:
 
     # -- construction helpers ---------------------------------------------------------------------------------
     @classmethod
-    def refined(cls, dim, base_level, marker, n_adaptive):
+    def refined(cls, dim, base_level, marker, n_adaptive, repetitions=None, coarse_size=1.0):
         """Uniform refinement to `base_level`, then `n_adaptive` rounds: refine every active cell with marker(center, level)
         true and whatever the 2:1 balance (faces, edges, corners) then requires."""
-        leaves = {(base_level, ijk) for ijk in itertools.product(range(1 << base_level), repeat=dim)}
+        reps = tuple(repetitions) if repetitions is not None else (1,) * dim
+        leaves = {(base_level, ijk) for ijk in itertools.product(*[range(reps[d] << base_level) for d in range(dim)])}
         for _ in range(n_adaptive):
-            marked = {c for c in leaves if marker(np.array([(i + 0.5) / (1 << c[0]) for i in c[1]]), c[0])}
-            leaves = cls._refine(dim, leaves, marked)
-        return cls(dim, leaves)
+            marked = {c for c in leaves if marker(np.array([(i + 0.5) * coarse_size / (1 << c[0]) for i in c[1]]), c[0])}
+            leaves = cls._refine(dim, leaves, marked, reps)
+        return cls(dim, leaves, reps, coarse_size)
 
     @staticmethod
-    def _neighbours(cell, dim):
+    def _neighbours(cell, dim, reps=None):
         l, ijk = cell
-        n = 1 << l
+        reps = reps if reps is not None else (1,) * dim
         out = []
         for off in itertools.product((-1, 0, 1), repeat=dim):
             if any(off):
                 q = tuple(ijk[d] + off[d] for d in range(dim))
-                if all(0 <= q[d] < n for d in range(dim)):
+                if all(0 <= q[d] < (reps[d] << l) for d in range(dim)):
                     out.append((l, q))
         return out
 
     @classmethod
-    def _refine(cls, dim, leaves, marked):
+    def _refine(cls, dim, leaves, marked, reps=None):
         leaves = set(leaves)
         queue = list(marked)
         while queue:
@@ -95,8 +103,10 @@ class AdaptiveBox:
             kids = _children(c, dim)
             leaves.update(kids)
             # every same-level neighbour position of c must be covered by a leaf of level >= l: coarser ones are refined
-            for nb in cls._neighbours(c, dim):
+            for nb in cls._neighbours(c, dim, reps):
                 l, ijk = nb
+                if l == 0:
+                    continue
                 anc = (l - 1, tuple(i // 2 for i in ijk))
                 if anc in leaves:
                     queue.append(anc)
@@ -113,7 +123,7 @@ class AdaptiveBox:
 
     def _balance_check(self):
         for c in self.leaves:
-            for nb in self._neighbours(c, self.dim):
+            for nb in self._neighbours(c, self.dim, self.reps):
                 cov = self._covering_leaf(*nb)
                 assert cov is None or cov[0] >= c[0] - 1, f"mesh is not 2:1 balanced at {c}"
 
@@ -125,11 +135,11 @@ class AdaptiveBox:
         return tuple(((npd - 1) * ijk[d] + loc[d]) * s for d in range(self.dim))
 
     def cell_size(self, cell):
-        return 1.0 / (1 << cell[0])
+        return self.coarse_size / (1 << cell[0])
 
     def quadrature_points(self):
         t = fe.tensor_tables(self.dim)
-        return np.array([[(np.array(ijk) + xq) / (1 << l) for xq in t["xq"]] for l, ijk in self.cells])
+        return np.array([[(np.array(ijk) + xq) * self.coarse_size / (1 << l) for xq in t["xq"]] for l, ijk in self.cells])
 
     # -- numbering ----------------------------------------------------------------------------------------------
     def _number(self):
@@ -171,7 +181,8 @@ class AdaptiveBox:
                 if nodes[key] in cons:
                     continue
                 # coarser active cells that contain the point
-                cands = itertools.product(*[{max(0, min(key[d] // span, (1 << (l - 1)) - 1)), max(0, min((key[d] - 1) // span, (1 << (l - 1)) - 1))}
+                cands = itertools.product(*[{max(0, min(key[d] // span, (self.reps[d] << (l - 1)) - 1)),
+                                             max(0, min((key[d] - 1) // span, (self.reps[d] << (l - 1)) - 1))}
                                             for d in range(dim)])
                 for q in cands:
                     coarse = (l - 1, tuple(q))
@@ -212,11 +223,12 @@ class AdaptiveBox:
         """Constrained velocity DoFs on the box boundary: 'zero' | 'tangential' | 'none' (as oracle/mesh.py)."""
         if bc == "none":
             return np.zeros(0, dtype=np.int64)
-        hi = 2 << self.Lmax
+        hi = [self.reps[d] * (2 << self.Lmax) for d in range(self.dim)]
         out = []
         for key, k in self.node_u.items():
             for c in range(self.dim):
-                on = any(v == 0 or v == hi for v in key) if bc == "zero" else (key[c] == 0 or key[c] == hi)
+                on = (any(v == 0 or v == hi[d] for d, v in enumerate(key)) if bc == "zero"
+                      else (key[c] == 0 or key[c] == hi[c]))
                 if on:
                     out.append(self.dim * k + c)
         return np.array(sorted(out), dtype=np.int64)
@@ -325,13 +337,17 @@ class AdaptiveHierarchy:
                 cells[ll].add((ll, q))
                 q = tuple(i // 2 for i in q)
 
+        reps = box.reps
+
         def morton(cell):
             l, ijk = cell
+            tree = [ijk[d] >> l for d in range(dim)]
+            t = sum(tree[d] * int(np.prod(reps[:d])) for d in range(dim))
             m = 0
             for b in range(l):
                 for d in range(dim):
-                    m |= ((ijk[d] >> b) & 1) << (dim * b + d)
-            return m
+                    m |= (((ijk[d] - (tree[d] << l)) >> b) & 1) << (dim * b + d)
+            return (t, m)
         self.cells = [sorted(c, key=morton) for c in cells]
         self.index = [{c: k for k, c in enumerate(cl)} for cl in self.cells]
         self.levels = [self._number_level(l) for l in range(self.n_levels)]
@@ -364,24 +380,25 @@ class AdaptiveHierarchy:
         def edge_nodes(nodes, per):
             """nodes of the level that touch a level-l cell position inside the box that is not part of the level mesh"""
             span = per << (box.Lmax - l)
-            n = 1 << l
+            n = [box.reps[d] << l for d in range(dim)]
             out = set()
             for key, k in nodes.items():
-                touching = itertools.product(*[{max(0, min(key[d] // span, n - 1)), max(0, min((key[d] - 1) // span, n - 1))}
+                touching = itertools.product(*[{max(0, min(key[d] // span, n[d] - 1)), max(0, min((key[d] - 1) // span, n[d] - 1))}
                                                for d in range(dim)])
                 if any((l, tuple(q)) not in self.index[l] for q in touching):
                     out.add(k)
             return out
         eu, ep = edge_nodes(nu, 2), edge_nodes(npn, 1)
-        hi = 2 << box.Lmax
+        hi = [box.reps[d] * (2 << box.Lmax) for d in range(dim)]
         bnd = []
         if self.bc != "none":
             for key, k in nu.items():
                 for c in range(dim):
-                    on = any(v == 0 or v == hi for v in key) if self.bc == "zero" else (key[c] == 0 or key[c] == hi)
+                    on = (any(v == 0 or v == hi[d] for d, v in enumerate(key)) if self.bc == "zero"
+                          else (key[c] == 0 or key[c] == hi[c]))
                     if on:
                         bnd.append(dim * k + c)
-        return dict(cell_dofs_u=cu, cell_dofs_p=cp, node_u=nu, node_p=npn, n_u=dim * len(nu), n_p=len(npn), h=1.0 / (1 << l),
+        return dict(cell_dofs_u=cu, cell_dofs_p=cp, node_u=nu, node_p=npn, n_u=dim * len(nu), n_p=len(npn), h=box.coarse_size / (1 << l),
                     boundary_u=np.array(sorted(bnd), dtype=np.int64),
                     edge_u=np.array(sorted(dim * k + c for k in eu for c in range(dim)), dtype=np.int64),
                     edge_p=np.array(sorted(ep), dtype=np.int64))

@@ -93,3 +93,23 @@ def test_adaptive_solve_converges_to_the_direct_solution():
             assert np.linalg.norm(out["x"][:nu] - xd[:nu]) < 1e-6 * np.linalg.norm(xd[:nu])
     # the refinement edge does not spoil the multigrid: same iteration count as the uniform mesh up to a few
     assert abs(its["adaptive"] - its["uniform"]) <= 5, its
+
+
+@pytest.mark.parametrize("which", [1, 2, 3])
+def test_muparser_temperature_example_golden_pins_the_adaptive_path(which):
+    """tests/muparser_temperature_example of the reference: block GMG (local smoothing) on a 5 x 1-tree box, uniform and after two
+    adaptive steps driven by a `minimum refinement function` alone -- the meshes are known without any error indicator, so this
+    golden pins hanging nodes, refinement edges, interface operators and copy indices of the restatement against the reference:
+    cells, levels and pressure DoFs exactly, velocity DoFs up to deal.II's identity-constrained duplicates on coarse-fine edges,
+    iterations 6 / 9 / 9 within +-1 (7 / 9 / 10)."""
+    from oracle import muparser_example as mx
+    from util import golden
+    g = golden("muparser_temperature_example")
+    box, out = mx.solve(which)
+    k = which - 1
+    assert box.n_cells == g["active_cells"][k] and box.Lmax + 1 == g["levels"][k]
+    assert box.n_p == g["dofs_u_p"][k][1]
+    n_edges = len(box.hanging_p)                      # one hanging Q1 node per coarse-fine edge (2D)
+    assert box.n_u + 2 * n_edges == g["dofs_u_p"][k][0], (box.n_u, n_edges)
+    assert (n_edges == 0) == (which == 1)
+    assert out["converged"] and abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][k][0]) <= 1, out["iterations"]
