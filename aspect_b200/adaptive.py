@@ -31,6 +31,20 @@ def _morton(ijk, nbits):
     return m
 
 
+def _tree_code(ijk, level, reps):
+    """Sort key of level-`level` cell positions in p4est order: tree by tree (trees of a subdivided box: x fastest), Morton order
+    inside a tree."""
+    dim = ijk.shape[1]
+    nbits = max(level, 1)
+    tree = ijk >> level
+    t = np.zeros(len(ijk), dtype=np.int64)
+    mult = 1
+    for d in range(dim):
+        t += tree[:, d] * mult
+        mult *= int(reps[d])
+    return (t << (dim * nbits)) | _morton(ijk - (tree << level), nbits)
+
+
 def _first_touch(keys_fe, keys_lex):
     """Number the distinct keys in the order of their first occurrence in keys_fe (cells x local order, row-major);
     returns (cell_nodes for keys_lex, sorted unique keys, number of every sorted key)."""
@@ -45,12 +59,14 @@ class _Mesh:
     """Cells of one mesh (the active one or a level) with their Q2 / Q1 numbering.  Lattice keys: node position in units of
     the finest cell size / 2 (Q2) or / 1 (Q1), packed x-fastest into one int64."""
 
-    def __init__(self, dim, levels, ijk, Lmax, extents):
+    def __init__(self, dim, levels, ijk, Lmax, extents, reps=None):
         self.dim, self.Lmax = dim, Lmax
         self.cell_level, self.cells = levels, ijk
         self.n_cells = len(ijk)
         self.extents = extents
-        self.G2, self.G1 = (2 << Lmax) + 1, (1 << Lmax) + 1
+        self.reps = np.ones(dim, dtype=np.int64) if reps is None else np.asarray(reps, dtype=np.int64)
+        self.hi_u, self.hi_p = self.reps * (2 << Lmax), self.reps * (1 << Lmax)      # largest lattice coordinate per direction
+        self.G2, self.G1 = int(self.hi_u.max()) + 1, int(self.hi_p.max()) + 1        # packing bases of the lattice keys
         shift = (Lmax - levels)[:, None]
 
         def keys(order, per, G):
@@ -79,8 +95,8 @@ class _Mesh:
 
     def constrained_u(self, bc):
         """Dirichlet DoFs on the box boundary: 'zero' | 'tangential' | 'none' (as synthetic.BoxLevel)."""
-        g, hi, dim = self.node_grid_u, self.G2 - 1, self.dim
-        on = (g == 0) | (g == hi)
+        g, dim = self.node_grid_u, self.dim
+        on = (g == 0) | (g == self.hi_u[None, :])
         if bc == "zero":
             mask = np.repeat(on.any(axis=1)[:, None], dim, axis=1)
         elif bc == "tangential":
@@ -92,32 +108,32 @@ class _Mesh:
         return np.flatnonzero(mask.ravel()).astype(_UINT)
 
     def dof_coords_u(self):
-        return np.repeat(self.node_grid_u * (self.extents / (self.G2 - 1)), self.dim, axis=0)
+        return np.repeat(self.node_grid_u * (self.extents / self.hi_u), self.dim, axis=0)
 
 
 class AdaptiveLevel(_Mesh):
     """Level l of local smoothing: uniform cell size, boundary + refinement-edge indices."""
 
-    def __init__(self, dim, level, ijk, Lmax, extents):
-        super().__init__(dim, np.full(len(ijk), level, dtype=np.int64), ijk, Lmax, extents)
+    def __init__(self, dim, level, ijk, Lmax, extents, reps=None):
+        super().__init__(dim, np.full(len(ijk), level, dtype=np.int64), ijk, Lmax, extents, reps)
         self.level = level
-        self.h = extents / (1 << level)
-        self.codes = _morton(ijk, max(level, 1))                   # sorted (cells are in Morton order)
+        self.h = extents / (self.reps << level)
+        self.codes = _tree_code(ijk, level, self.reps)             # sorted (cells are in tree-major Morton order)
         self.edge_u = self._edge(self.node_grid_u, 2, True)
         self.edge_p = self._edge(self.node_grid_p, 1, False)
 
     def cell_index(self, ijk):
         """index of level-cell positions ijk (n, dim) in this level's mesh, -1 where the level has no such cell."""
-        n = 1 << self.level
+        n = (self.reps << self.level)[None, :]
         inside = ((ijk >= 0) & (ijk < n)).all(axis=1)
-        code = _morton(np.clip(ijk, 0, n - 1), max(self.level, 1))
+        code = _tree_code(np.clip(ijk, 0, n - 1), self.level, self.reps)
         pos = np.clip(np.searchsorted(self.codes, code), 0, len(self.codes) - 1)
         return np.where(inside & (self.codes[pos] == code), pos, -1)
 
     def _edge(self, grid, per, vector):
         """DoFs of the nodes that touch a level-l cell position inside the box which is not part of the level mesh."""
         span = per << (self.Lmax - self.level)
-        n = 1 << self.level
+        n = (self.reps << self.level)[None, :]
         edge = np.zeros(len(grid), dtype=bool)
         for off in itertools.product((0, 1), repeat=self.dim):
             q = (grid - np.array(off)) // span
@@ -132,10 +148,10 @@ class AdaptiveLevel(_Mesh):
 class AdaptiveActive(_Mesh):
     """The active mesh: cells of different sizes, hanging-node lines."""
 
-    def __init__(self, dim, levels, ijk, Lmax, extents):
-        super().__init__(dim, levels, ijk, Lmax, extents)
-        self.h_cell = extents[None, :] / (1 << levels)[:, None]                     # (cells, dim)
-        self.h = extents / (1 << Lmax)                                              # (unused: the cells go in with geometry = 1)
+    def __init__(self, dim, levels, ijk, Lmax, extents, reps=None):
+        super().__init__(dim, levels, ijk, Lmax, extents, reps)
+        self.h_cell = (extents / self.reps)[None, :] / (1 << levels)[:, None]       # (cells, dim)
+        self.h = extents / (self.reps << Lmax)                                      # (unused: the cells go in with geometry = 1)
         self.hanging_u = self._hanging("u", 3, lambda x: np.stack([(1 - x) * (1 - 2 * x), 4 * x * (1 - x), x * (2 * x - 1)], -1))
         self.hanging_p = self._hanging("p", 2, lambda x: np.stack([1 - x, x], -1))
 
@@ -240,20 +256,22 @@ class AdaptiveActive(_Mesh):
 
 
 class AdaptiveBoxHierarchy:
-    """Active mesh + local-smoothing levels of an adaptively refined one-tree box."""
+    """Active mesh + local-smoothing levels of an adaptively refined box (one coarse cell, or `repetitions` of them)."""
 
     adaptive = True
 
-    def __init__(self, dim, leaves, extents=None):
-        """leaves: iterable of (level, (i, j[, k]))."""
+    def __init__(self, dim, leaves, extents=None, repetitions=None):
+        """leaves: iterable of (level, (i, j[, k])), 0 <= i < repetitions[0] * 2^level etc.; extents: of the whole box;
+        repetitions: coarse cells (trees) per direction (`X / Y / Z repetitions`), default one."""
         self.dim = dim
         self.extents = np.ones(dim) if extents is None else np.asarray(extents, float)
+        self.reps = reps = np.ones(dim, dtype=np.int64) if repetitions is None else np.asarray(repetitions, dtype=np.int64)
         lv = np.array([l for l, _ in leaves], dtype=np.int64)
         ijk = np.array([c for _, c in leaves], dtype=np.int64).reshape(-1, dim)
         self.Lmax = Lmax = int(lv.max())
-        order = np.argsort(_morton(ijk << (Lmax - lv)[:, None], max(Lmax, 1)), kind="stable")
+        order = np.argsort(_tree_code(ijk << (Lmax - lv)[:, None], Lmax, reps), kind="stable")
         lv, ijk = lv[order], ijk[order]
-        self.active = AdaptiveActive(dim, lv, ijk, Lmax, self.extents)
+        self.active = AdaptiveActive(dim, lv, ijk, Lmax, self.extents, reps)
         self.R = Lmax
         # level meshes: every leaf and all its ancestors
         self.levels = []
@@ -262,11 +280,11 @@ class AdaptiveBoxHierarchy:
         for l in range(Lmax, -1, -1):
             here = cur[cur_l == l]
             here = np.unique(here, axis=0) if len(here) else here
-            per_level[l] = here[np.argsort(_morton(here, max(l, 1)), kind="stable")]
+            per_level[l] = here[np.argsort(_tree_code(here, l, reps), kind="stable")]
             up = cur_l == l
             cur = np.where(up[:, None], cur >> 1, cur)
             cur_l = np.where(up, l - 1, cur_l)
-        self.levels = [AdaptiveLevel(dim, l, per_level[l], Lmax, self.extents) for l in range(Lmax + 1)]
+        self.levels = [AdaptiveLevel(dim, l, per_level[l], Lmax, self.extents, reps) for l in range(Lmax + 1)]
 
     @classmethod
     def refined(cls, dim, base_level, marker, n_adaptive, extents=None):

@@ -238,6 +238,50 @@ def shell_3d_gmg_problem(hier):
     return np.full(x.shape[:2], 1e22), force_q, s * ps
 
 
+# ---- tests/muparser_temperature_example.prm: the reference golden whose ADAPTIVE meshes follow from a `minimum refinement function`
+#      alone (level 5 within 150 km of the top, else the minimum), so they can be written down without an error indicator ----
+MUPARSER_BOX = dict(extents=(5e6, 1e6), repetitions=(5, 1))
+
+
+def muparser_example_leaves(which):
+    """Active cells (level, (i, j)) of solve `which` (1: global refinement 3; 2, 3: after one / two adaptive steps): every cell
+    is coarsened to what the function and the 2:1 balance allow -- level 3 | 4, 3, 2 | 5, 4, 3, 2 from the top down (boundaries
+    at 875, 750 and 500 km above the bottom)."""
+    H = 1e6
+    required = {1: lambda y1: 3,
+                2: lambda y1: 4 if y1 > 0.875e6 else (3 if y1 > 0.75e6 else 2),
+                3: lambda y1: 5 if y1 > 0.875e6 else (4 if y1 > 0.75e6 else (3 if y1 > 0.5e6 else 2))}[which]
+    leaves, todo = [], [(0, (i, 0)) for i in range(MUPARSER_BOX["repetitions"][0])]
+    while todo:
+        l, (i, j) = todo.pop()
+        if required((j + 1) * H / (1 << l)) > l:
+            todo += [(l + 1, (2 * i + a, 2 * j + b)) for b in (0, 1) for a in (0, 1)]
+        else:
+            leaves.append((l, (i, j)))
+    return sorted(leaves)
+
+
+def muparser_example_problem(hier):
+    """(viscosity_q, rhs before condensation, pressure_scaling) on an AdaptiveBoxHierarchy built from muparser_example_leaves:
+    `simple` material (viscosity 1e21, rho = 3300 (1 - 2e-5 (T - 273))), gravity 9.81 downwards, T = the prm's half-space-cooling
+    function at the Q2 nodes with the boundary temperatures (273 top, 1673 bottom) and the hanging nodes distributed."""
+    from scipy.special import erfc
+    act = hier.active
+    xy = act.node_grid_u * (act.extents / act.hi_u)
+    x, y = xy[:, 0], xy[:, 1]
+    ymax, xtrm, vsub, ageop, Tm, Ts, kappa = 1.0e6, 2.2e6, 7.927e-10, 9.46e14, 1673.0, 273.0, 1e-6
+    age = np.where((x > 0.0) & (x <= xtrm), x / vsub, ageop)
+    T = np.where(x > 0.0, Ts + (Tm - Ts) * (1.0 - erfc((ymax - y) / (2.0 * np.sqrt(kappa * age)))), Tm)
+    T[act.node_grid_u[:, 1] == act.hi_u[1]] = 273.0
+    T[act.node_grid_u[:, 1] == 0] = 1673.0
+    for k, (ms, ws) in act.hanging_u.items():
+        T[k] = ws @ T[ms]
+    T_q = T[(np.asarray(act.cell_dofs_u[:, :9]) // 2).astype(np.int64)] @ _phi2_at_quad(2).T
+    rho_q = 3300.0 * (1.0 - 2e-5 * (T_q - 273.0))
+    f = assemble_rhs(act, rho_q, np.array([0.0, -9.81]))
+    return np.full(T_q.shape, 1e21), np.concatenate([f, np.zeros(act.n_p)]), 1e21 / (0.01 * 1e6)
+
+
 # ---- benchmarks/hollow_sphere (analytic solution on the spherical shell; the reference's test hollow_sphere_gmg) ----
 def _hollow_sphere_constants(m, R1=0.5, R2=1.0, gamma=1.0):
     """benchmarks/hollow_sphere/hollow_sphere.cc:72-85."""

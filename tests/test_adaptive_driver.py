@@ -15,8 +15,21 @@ CASES = [(2, 1, 2, lambda x, l: np.linalg.norm(x) < 0.6), (2, 2, 2, lambda x, l:
 @pytest.mark.parametrize("dim,base,n_adaptive,marker", CASES)
 def test_driver_equals_oracle(dim, base, n_adaptive, marker):
     box = oad.AdaptiveBox.refined(dim, base, marker, n_adaptive)
-    oh = oad.AdaptiveHierarchy(box, "zero")
     ph = pad.AdaptiveBoxHierarchy.refined(dim, base, marker, n_adaptive)
+    _compare(box, ph, dim)
+
+
+@pytest.mark.parametrize("which", [1, 2, 3])
+def test_driver_equals_oracle_on_several_coarse_cells(which):
+    """The three meshes of the reference's tests/muparser_temperature_example (5 x 1 coarse cells of 1,000 km, refined by depth)."""
+    from oracle import muparser_example as mx
+    box = mx.mesh(which)
+    ph = pad.AdaptiveBoxHierarchy(2, sorted(box.leaves), extents=(5e6, 1e6), repetitions=(5, 1))
+    _compare(box, ph, 2)
+
+
+def _compare(box, ph, dim):
+    oh = oad.AdaptiveHierarchy(box, "zero")
     act = ph.active
     # active mesh
     assert act.n_cells == box.n_cells and [(int(l), tuple(int(v) for v in c)) for l, c in zip(act.cell_level, act.cells)] == box.cells
@@ -67,5 +80,5 @@ def test_driver_equals_oracle(dim, base, n_adaptive, marker):
     hanging_dofs = {dim * k + c for k in act.hanging_u for c in range(dim)}
     assert set(range(act.n_u)) - set(seen.tolist()) <= hanging_dofs
     # geometry tables of the active mesh
-    assert act.jinv.shape == (act.n_cells, 3 ** dim, dim, dim) and np.allclose(act.jxw.sum(), 1.0)
+    assert act.jinv.shape == (act.n_cells, 3 ** dim, dim, dim) and np.allclose(act.jxw.sum(), np.prod(ph.extents))
     assert np.allclose(act.quadrature_points(), box.quadrature_points())

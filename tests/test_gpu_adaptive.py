@@ -140,3 +140,36 @@ def test_adaptive_solve_matches_oracle(name):
     e_full = rel(sol[:nu], full)
     assert e_full < 1e-8, (e_full, e_free)
     h.close()
+
+
+@pytest.mark.parametrize("which", [2, 3])
+def test_muparser_temperature_example_reference_golden(which):
+    """The reference's adaptive golden tests/muparser_temperature_example (second and third solve: 260 cells on 5 levels, 920 on 6;
+    5 x 1 coarse cells; meshes given by a `minimum refinement function`, see oracle/muparser_example.py) through the C ABI:
+    local smoothing with hanging nodes, refinement edges, interface operators and copy indices on the device.  Golden: 9 and 9
+    GMRES iterations; the oracle takes 9 and 10; the device must repeat the oracle (+-1) and stay within 2 of the golden."""
+    from oracle import muparser_example as mx
+    from aspect_b200 import benchmarks
+    from util import golden
+    gold = golden("muparser_temperature_example")["stokes_iterations_cheap_expensive"][which - 1][0]
+    box, want = mx.solve(which)
+    hier = pad.AdaptiveBoxHierarchy(2, benchmarks.muparser_example_leaves(which), **benchmarks.MUPARSER_BOX)
+    act = hier.active
+    assert np.array_equal(act.cell_dofs_u, box.cell_dofs_u) and len(act.hanging_u) == len(box.hanging_u) > 0
+    eta_q, rhs, ps = benchmarks.muparser_example_problem(hier)
+    h = StokesMatrixFreeHandler(2)
+    h.setup_dofs(hier, "tangential")
+    h.assemble(eta_q, "harmonic average", ps)
+    h.build_preconditioner()
+    h.parameters.update({"Linear solver tolerance": 1e-6, "Number of cheap Stokes solver steps": 200,
+                         "Maximum number of expensive Stokes solver steps": 0, "GMRES solver restart length": 100})
+    rhs = h.condense_rhs(rhs)
+    rhs[act.constrained_u("tangential").astype(np.int64)] = 0.0
+    sol, out = h.solve(rhs)
+    print(f"muparser_temperature_example solve {which}: device {out['iterations']}, oracle {want['iterations']}, reference {gold}")
+    assert out["converged"] and want["converged"]
+    assert abs(out["iterations"] - want["iterations"]) <= 1 and abs(out["iterations"] - gold) <= 2, (out["iterations"], want["iterations"], gold)
+    nu = box.n_u
+    full = want["ops"]["Cu"] @ want["x"][:nu]
+    assert rel(sol[:nu], full) < 1e-4, rel(sol[:nu], full)            # (both stop at a relative 1e-6 of a mostly hydrostatic load)
+    h.close()
