@@ -34,6 +34,22 @@ import scipy.sparse as sp
 from . import fe
 
 
+def _constrained_components(key, hi, bc, dim):
+    """Velocity components that carry a Dirichlet value at the lattice point `key`: bc = 'zero' | 'tangential' | 'none' for all
+    faces alike, or a dict {(direction, side): 'zero' | 'tangential' | 'none'} per face (side 0: low, 1: high)."""
+    out = set()
+    for d in range(dim):
+        for side, v in ((0, 0), (1, hi[d])):
+            if key[d] != v:
+                continue
+            kind = bc.get((d, side), "none") if isinstance(bc, dict) else bc
+            if kind == "zero":
+                out.update(range(dim))
+            elif kind == "tangential":
+                out.add(d)
+    return out
+
+
 def _children(cell, dim):
     l, ijk = cell
     return [(l + 1, tuple(2 * ijk[d] + ((k >> d) & 1) for d in range(dim))) for k in range(1 << dim)]
@@ -46,7 +62,7 @@ class AdaptiveBox:
     def __init__(self, dim, leaves, repetitions=None, coarse_size=1.0):
         self.dim = dim
         self.reps = tuple(repetitions) if repetitions is not None else (1,) * dim
-        self.coarse_size = float(coarse_size)
+        self.coarse_size = np.full(dim, float(coarse_size)) if np.ndim(coarse_size) == 0 else np.asarray(coarse_size, float)
         self.leaves = set(leaves)
         self.Lmax = max(l for l, _ in self.leaves)
         self._balance_check()
@@ -75,7 +91,8 @@ class AdaptiveBox:
         reps = tuple(repetitions) if repetitions is not None else (1,) * dim
         leaves = {(base_level, ijk) for ijk in itertools.product(*[range(reps[d] << base_level) for d in range(dim)])}
         for _ in range(n_adaptive):
-            marked = {c for c in leaves if marker(np.array([(i + 0.5) * coarse_size / (1 << c[0]) for i in c[1]]), c[0])}
+            size = np.full(dim, float(coarse_size)) if np.ndim(coarse_size) == 0 else np.asarray(coarse_size, float)
+            marked = {c for c in leaves if marker((np.array(c[1]) + 0.5) * size / (1 << c[0]), c[0])}
             leaves = cls._refine(dim, leaves, marked, reps)
         return cls(dim, leaves, reps, coarse_size)
 
@@ -135,6 +152,7 @@ class AdaptiveBox:
         return tuple(((npd - 1) * ijk[d] + loc[d]) * s for d in range(self.dim))
 
     def cell_size(self, cell):
+        """edge lengths (dim,) of a cell"""
         return self.coarse_size / (1 << cell[0])
 
     def quadrature_points(self):
@@ -220,17 +238,14 @@ class AdaptiveBox:
 
     # -- constraint matrices ------------------------------------------------------------------------------------
     def dirichlet_u(self, bc):
-        """Constrained velocity DoFs on the box boundary: 'zero' | 'tangential' | 'none' (as oracle/mesh.py)."""
+        """Constrained velocity DoFs on the box boundary: 'zero' | 'tangential' | 'none' (as oracle/mesh.py), or per face
+        (_constrained_components)."""
         if bc == "none":
             return np.zeros(0, dtype=np.int64)
         hi = [self.reps[d] * (2 << self.Lmax) for d in range(self.dim)]
         out = []
         for key, k in self.node_u.items():
-            for c in range(self.dim):
-                on = (any(v == 0 or v == hi[d] for d, v in enumerate(key)) if bc == "zero"
-                      else (key[c] == 0 or key[c] == hi[c]))
-                if on:
-                    out.append(self.dim * k + c)
+            out += [self.dim * k + c for c in _constrained_components(key, hi, bc, self.dim)]
         return np.array(sorted(out), dtype=np.int64)
 
     def constraint_matrices(self, bc):
@@ -276,19 +291,20 @@ class AdaptiveBox:
         Ra, Ca, Va, Rb, Cb, Vb, Rm, Cm, Vm = ([] for _ in range(9))
         for m, cell in enumerate(self.cells):
             h = self.cell_size(cell)
+            vol = float(np.prod(h))
             G = np.zeros((nq, dim * nn, dim, dim))
             for c in range(dim):
-                G[:, c * nn:(c + 1) * nn, c, :] = t["dphi2"] / h
+                G[:, c * nn:(c + 1) * nn, c, :] = t["dphi2"] / h[None, None, :]
             E = 0.5 * (G + np.swapaxes(G, 2, 3))
-            coef = eta[m] * t["w"] * h ** dim
+            coef = eta[m] * t["w"] * vol
             Ke = 2.0 * np.einsum("q,qiab,qjab->ij", coef, E, E)
             du = self.cell_dofs_u[m]
             Ra.append(np.repeat(du, len(du))); Ca.append(np.tile(du, len(du))); Va.append(Ke.ravel())
             div = np.trace(G, axis1=2, axis2=3)
-            Be = -pressure_scaling * np.einsum("q,qi,qj->ij", t["w"] * h ** dim, div, t["phi1"])
+            Be = -pressure_scaling * np.einsum("q,qi,qj->ij", t["w"] * vol, div, t["phi1"])
             dp = self.cell_dofs_p[m]
             Rb.append(np.repeat(du, len(dp))); Cb.append(np.tile(dp, len(du))); Vb.append(Be.ravel())
-            Me = np.einsum("q,qi,qj->ij", pressure_scaling ** 2 / eta[m] * t["w"] * h ** dim, t["phi1"], t["phi1"])
+            Me = np.einsum("q,qi,qj->ij", pressure_scaling ** 2 / eta[m] * t["w"] * vol, t["phi1"], t["phi1"])
             Rm.append(np.repeat(dp, len(dp))); Cm.append(np.tile(dp, len(dp))); Vm.append(Me.ravel())
         cat = np.concatenate
         A = sp.coo_matrix((cat(Va), (cat(Ra), cat(Ca))), shape=(self.n_u, self.n_u)).tocsr()
@@ -393,11 +409,7 @@ class AdaptiveHierarchy:
         bnd = []
         if self.bc != "none":
             for key, k in nu.items():
-                for c in range(dim):
-                    on = (any(v == 0 or v == hi[d] for d, v in enumerate(key)) if self.bc == "zero"
-                          else (key[c] == 0 or key[c] == hi[c]))
-                    if on:
-                        bnd.append(dim * k + c)
+                bnd += [dim * k + c for c in _constrained_components(key, hi, self.bc, dim)]
         return dict(cell_dofs_u=cu, cell_dofs_p=cp, node_u=nu, node_p=npn, n_u=dim * len(nu), n_p=len(npn), h=box.coarse_size / (1 << l),
                     boundary_u=np.array(sorted(bnd), dtype=np.int64),
                     edge_u=np.array(sorted(dim * k + c for k in eu for c in range(dim)), dtype=np.int64),
@@ -447,13 +459,14 @@ class AdaptiveHierarchy:
         nn = 3 ** dim
         ops = []
         for l, L in enumerate(self.levels):
-            h = L["h"]
+            h = np.asarray(L["h"], float)
+            vol = float(np.prod(h))
             G = np.zeros((len(t["w"]), dim * nn, dim, dim))
             for c in range(dim):
-                G[:, c * nn:(c + 1) * nn, c, :] = t["dphi2"] / h
+                G[:, c * nn:(c + 1) * nn, c, :] = t["dphi2"] / h[None, None, :]
             E = 0.5 * (G + np.swapaxes(G, 2, 3))
-            K1 = 2.0 * np.einsum("q,qiab,qjab->ij", t["w"] * h ** dim, E, E)
-            M1 = np.einsum("q,qi,qj->ij", t["w"] * h ** dim, t["phi1"], t["phi1"])
+            K1 = 2.0 * np.einsum("q,qiab,qjab->ij", t["w"] * vol, E, E)
+            M1 = np.einsum("q,qi,qj->ij", t["w"] * vol, t["phi1"], t["phi1"])
             cu, cp = L["cell_dofs_u"], L["cell_dofs_p"]
             eta = eta_levels[l]
             A = sp.coo_matrix(((eta[:, None, None] * K1[None]).ravel(),

@@ -69,8 +69,8 @@ def problem(box):
     rho = 3300.0 * (1.0 - 2e-5 * (T_q - 273.0))
     f = np.zeros(box.n_u)
     for m, cell in enumerate(box.cells):
-        h = box.cell_size(cell)
-        np.add.at(f, box.cell_dofs_u[m, 9:18], (rho[m] * (-9.81) * t["w"] * h ** 2) @ t["phi2"])
+        vol = float(np.prod(box.cell_size(cell)))
+        np.add.at(f, box.cell_dofs_u[m, 9:18], (rho[m] * (-9.81) * t["w"] * vol) @ t["phi2"])
     return np.full(box.n_cells, 1e21), f, 1e21 / (0.01 * 1e6)
 
 

@@ -113,3 +113,17 @@ def test_muparser_temperature_example_golden_pins_the_adaptive_path(which):
     assert box.n_u + 2 * n_edges == g["dofs_u_p"][k][0], (box.n_u, n_edges)
     assert (n_edges == 0) == (which == 1)
     assert out["converged"] and abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][k][0]) <= 1, out["iterations"]
+
+
+def test_initial_global_refinement_golden_anisotropic_cells_and_mixed_boundaries():
+    """tests/initial_global_refinement of the reference: 1,855 cells of FIVE sizes (0.24 x 0.2 coarse cells, levels 0 .. 4 by depth),
+    tangential velocity on one face and zero velocity on the other three, default solver (block GMG): the mesh is reproduced
+    exactly (cells, levels, pressure DoFs; velocity DoFs up to deal.II's duplicates on the 75 coarse-fine edges), 23+0 iterations
+    as 24."""
+    from oracle import initial_global_refinement as igr
+    g = golden("initial_global_refinement")
+    box, out = igr.solve()
+    assert box.n_cells == g["active_cells"][0] == 1855 and box.Lmax + 1 == g["levels"][0]
+    assert sorted({c[0] for c in box.cells}) == [0, 1, 2, 3, 4]
+    assert box.n_p == g["dofs_u_p"][0][1] and box.n_u + 2 * len(box.hanging_p) == g["dofs_u_p"][0][0]
+    assert out["converged"] and abs(out["iterations"] - g["stokes_iterations_cheap_expensive"][0][0]) <= 1, out["iterations"]

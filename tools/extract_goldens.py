@@ -11,7 +11,7 @@ import re
 REF = "/root/reference/tests"
 TESTS = ["nsinker_gmg_no_avg", "nsinker_gmg_gc", "nsinker_gmg_gc_no_avg", "nsinker_gmg_idr", "sol_cx_2_gmg", "sol_cx_4_gmg",
          "sol_cx_4_gmg_no_avg", "no_cheap_gmg", "performance/performance_nsinker_gmg_idr", "spherical_nsinker_gmg_gc", "hollow_sphere_gmg",
-         "hollow_sphere_gmg_project_q1", "prescribed_dilation_gmg", "shell_3d_gmg", "gmg_no_normal_flux_only", "muparser_temperature_example"]
+         "hollow_sphere_gmg_project_q1", "prescribed_dilation_gmg", "shell_3d_gmg", "gmg_no_normal_flux_only", "muparser_temperature_example", "initial_global_refinement"]
 
 
 def num(s):
