@@ -15,6 +15,14 @@ Golden (tests/muparser_temperature_example/screen-output): 2,754+369 / 2,546+347
 its own, constrained to the coarse edge's DoF with weight one; this restatement (and the product's driver) identifies the two,
 so its velocity count is lower by dim x (number of coarse-fine edges) -- 120 and 280 here -- and nothing else differs.
 
+Start vector: the tests here solve from a ZERO guess with the tolerance 1e-6 |b| (7 / 9 / 10 iterations).  The reference starts
+from its initial pressure field -- the adiabatic (lithostatic) pressure, initial_conditions.cc:499-554 -- and measures the tolerance
+against |b_u - B^T p_0| (local_smoothing.cc:1001-1025); with the adiabatic profile of this prm (surface temperature 273 K against a
+1673 K mantle: p_0 balances the weight to 2.8 %) the restatement then needs 8 / 10 / 11.  In both variants the first GMRES step
+makes no progress (the residual is a gradient field, which the block-triangular preconditioner turns into a pressure residual of the
+same size: 1, 1, 0.16, 1e-2, ...), and the reference's counts are those of the same history WITHOUT that step; why its first step is
+productive is not known.  Within +-1 from a zero guess, within 2 with the reference's start.
+
 Physics: `simple` material (viscosity 1e21, rho = 3300 (1 - 2e-5 (T - 273))), vertical gravity 9.81, tangential velocity on all
 sides, the half-space-cooling initial temperature of the prm interpolated to the Q2 nodes with the boundary temperatures (top 273,
 bottom 1673) and the hanging-node constraints distributed, pressure scaling = viscosity / (0.01 x depth) (geometry_model/box.cc:252-255).
